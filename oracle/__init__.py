@@ -1,0 +1,7 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU oracle of the ORB-SLAM3 hot path.
+
+May be imported only by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  See orc_common.h for the pinning note
+("parity unpinned" by the reference's own tests; pinned against cv2 4.13).
+"""
+from .oracle import *  # noqa: F401,F403

@@ -1,0 +1,166 @@
+"""ctypes binding of liborb_oracle.so (TEST INFRASTRUCTURE ONLY)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liborb_oracle.so")
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28
+
+
+def build(force=False):
+    """Compile the oracle with the committed Makefile (gcc only)."""
+    srcs = [f for f in os.listdir(_HERE) if f.startswith("orc_") or f.endswith(".inc")]
+    if not force and os.path.exists(_LIB_PATH):
+        so_m = os.path.getmtime(_LIB_PATH)
+        if all(os.path.getmtime(os.path.join(_HERE, f)) <= so_m for f in srcs):
+            return _LIB_PATH
+    subprocess.check_call(["make", "-C", _HERE, "-B", "liborb_oracle.so"],
+                          stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        L = C.CDLL(_LIB_PATH)
+        u8p = C.POINTER(C.c_uint8)
+        ip = C.POINTER(C.c_int)
+        L.orc_extractor_create.restype = C.c_void_p
+        L.orc_extractor_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.orc_extractor_destroy.argtypes = [C.c_void_p]
+        L.orc_extract.restype = C.c_int
+        L.orc_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  C.c_void_p, C.c_void_p, C.c_int, ip]
+        L.orc_level_info.argtypes = [C.c_void_p, C.c_int, ip, ip, ip, C.POINTER(C.c_float)]
+        L.orc_level_ptr.restype = u8p
+        L.orc_level_ptr.argtypes = [C.c_void_p, C.c_int]
+        L.orc_level_candidates.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.orc_level_keypoints.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.orc_umax.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_resize_linear_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                           C.c_int, C.c_int]
+        L.orc_fast.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.orc_gaussian_blur7.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.orc_fast_atan2.restype = C.c_float
+        L.orc_fast_atan2.argtypes = [C.c_float, C.c_float]
+        L.orc_cos_sin_deg.argtypes = [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.orc_pattern.argtypes = [C.c_void_p]
+        L.orc_sort_nodes.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class OracleExtractor:
+    """CPU restatement of ORB_SLAM3::ORBextractor (src/ORBextractor.cc)."""
+
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+        self.nlevels = nlevels
+        self.nfeatures = nfeatures
+        self._h = lib().orc_extractor_create(nfeatures, scale_factor, nlevels, ini_th, min_th)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_extractor_destroy(self._h)
+            self._h = None
+
+    def extract(self, img, lap=(0, 0)):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        cap = self.nfeatures * 2 + 64 * self.nlevels
+        kps = np.zeros(cap, dtype=KP_DTYPE)
+        desc = np.zeros((cap, 32), dtype=np.uint8)
+        n = C.c_int(0)
+        mono = lib().orc_extract(self._h, _ptr(img), img.shape[0], img.shape[1], img.strides[0],
+                                 int(lap[0]), int(lap[1]), _ptr(kps), _ptr(desc), cap, C.byref(n))
+        if mono < 0:
+            raise RuntimeError("oracle extract rc=%d" % mono)
+        return kps[:n.value].copy(), desc[:n.value].copy(), mono
+
+    def level_info(self, level):
+        w, h, q = C.c_int(), C.c_int(), C.c_int()
+        s = C.c_float()
+        lib().orc_level_info(self._h, level, C.byref(w), C.byref(h), C.byref(q), C.byref(s))
+        return w.value, h.value, q.value, s.value
+
+    def level_image(self, level):
+        w, h, _, _ = self.level_info(level)
+        p = lib().orc_level_ptr(self._h, level)
+        return np.ctypeslib.as_array(p, shape=(h, w)).copy()
+
+    def level_candidates(self, level):
+        n = lib().orc_level_candidates(self._h, level, None, 0)
+        out = np.zeros(n, dtype=KP_DTYPE)
+        lib().orc_level_candidates(self._h, level, _ptr(out), n)
+        return out
+
+    def level_keypoints(self, level):
+        n = lib().orc_level_keypoints(self._h, level, None, 0)
+        out = np.zeros(n, dtype=KP_DTYPE)
+        lib().orc_level_keypoints(self._h, level, _ptr(out), n)
+        return out
+
+    def umax(self):
+        out = np.zeros(16, dtype=np.int32)
+        lib().orc_umax(self._h, _ptr(out))
+        return out
+
+
+def resize_linear_u8(src, dw, dh):
+    src = np.ascontiguousarray(src, dtype=np.uint8)
+    dst = np.zeros((dh, dw), dtype=np.uint8)
+    lib().orc_resize_linear_u8(_ptr(src), src.shape[1], src.shape[0], src.strides[0], _ptr(dst), dw, dh, dw)
+    return dst
+
+
+def fast(img, threshold, nonmax=True):
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    cap = img.size
+    out = np.zeros((cap, 3), dtype=np.int32)
+    n = lib().orc_fast(_ptr(img), img.shape[1], img.shape[0], img.strides[0], threshold, int(nonmax),
+                       _ptr(out), cap)
+    return out[:n].copy()
+
+
+def gaussian_blur7(img):
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    dst = np.zeros_like(img)
+    lib().orc_gaussian_blur7(_ptr(img), img.shape[1], img.shape[0], img.strides[0], _ptr(dst), dst.strides[0])
+    return dst
+
+
+def fast_atan2(y, x):
+    return lib().orc_fast_atan2(float(y), float(x))
+
+
+def cos_sin_deg(angle):
+    c, s = C.c_float(), C.c_float()
+    lib().orc_cos_sin_deg(float(angle), C.byref(c), C.byref(s))
+    return c.value, s.value
+
+
+def pattern():
+    out = np.zeros(1024, dtype=np.int32)
+    lib().orc_pattern(_ptr(out))
+    return out
+
+
+def sort_nodes(count, ulx):
+    count = np.ascontiguousarray(count, dtype=np.int32)
+    ulx = np.ascontiguousarray(ulx, dtype=np.int32)
+    perm = np.zeros(len(count), dtype=np.int32)
+    lib().orc_sort_nodes(_ptr(count), _ptr(ulx), len(count), _ptr(perm))
+    return perm
