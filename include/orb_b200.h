@@ -1,0 +1,130 @@
+/* orb_b200.h -- C ABI of liborbb200.so, the B200 (sm_100a) replacement for the
+ * hot path of UZ-SLAMLab/ORB_SLAM3.  Plain pointers and sizes only; every entry
+ * point cites the reference interface it stands in for (paths relative to the
+ * reference tree).  The C++ shims in orb_slam3_b200/shim/ keep the reference's
+ * class signatures on top of these calls; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - return value: >= 0 success (often a count), < 0 error (ORB_E_*).  There is
+ *     no CPU fallback: without a usable CUDA device every compute call fails.
+ *   - all buffers are owned by the caller unless stated otherwise.
+ *   - a handle owns its CUDA stream and device memory and is NOT thread-safe;
+ *     distinct handles may be used concurrently from distinct threads (the
+ *     reference runs the left/right extractors on two threads, Frame.cc:122-125).
+ */
+#ifndef ORB_B200_H_
+#define ORB_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORB_OK 0
+#define ORB_E_EMPTY (-1)      /* empty image: ORBextractor::operator() returns -1 (ORBextractor.cc:1090) */
+#define ORB_E_ARG (-2)        /* bad argument */
+#define ORB_E_CUDA (-3)       /* CUDA runtime error, see orb_last_error() */
+#define ORB_E_CAPACITY (-4)   /* caller buffer too small (*n tells the need) */
+#define ORB_E_NODEVICE (-5)   /* no CUDA device: the engine has no CPU path */
+#define ORB_E_NCCL (-6)
+
+/* Same 28-byte layout as cv::KeyPoint. */
+typedef struct orb_keypoint {
+  float x, y;      /* pt, level-0 pixel coordinates */
+  float size;      /* 31 * scale[octave], truncated (ORBextractor.cc:880) */
+  float angle;     /* degrees [0,360), IC_Angle (ORBextractor.cc:76-103) */
+  float response;  /* FAST score */
+  int32_t octave;
+  int32_t class_id; /* -1 */
+} orb_keypoint;
+
+typedef struct orb_extractor orb_extractor;
+
+const char* orb_version(void);
+/* Last error text of the calling thread (also set when a handle call fails). */
+const char* orb_last_error(void);
+/* Number of CUDA devices visible; 0 when there is none (then every compute call
+ * returns ORB_E_NODEVICE). */
+int orb_device_count(void);
+
+/* ---- ORBextractor (include/ORBextractor.h:49-83, src/ORBextractor.cc) ---- */
+
+/* ORBextractor::ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST,
+ * minThFAST) (ORBextractor.cc:409-469).  `device` = CUDA ordinal.  Tables are
+ * computed on the host exactly as the reference does; no device work happens
+ * until the first extract, so creation succeeds without a GPU. */
+int orb_create(int nfeatures, float scale_factor, int nlevels, int ini_th_fast, int min_th_fast,
+               int device, orb_extractor** out);
+void orb_destroy(orb_extractor* h);
+
+/* Getters of ORBextractor.h:61-81.  `out` has nlevels entries. */
+int orb_get_levels(const orb_extractor* h);
+float orb_get_scale_factor(const orb_extractor* h);
+int orb_get_scale_factors(const orb_extractor* h, float* out);
+int orb_get_inverse_scale_factors(const orb_extractor* h, float* out);
+int orb_get_scale_sigma_squares(const orb_extractor* h, float* out);
+int orb_get_inverse_scale_sigma_squares(const orb_extractor* h, float* out);
+int orb_get_features_per_level(const orb_extractor* h, int* out);
+
+/* int ORBextractor::operator()(image, mask (ignored), keypoints, descriptors,
+ * vLappingArea) (ORBextractor.cc:1086-1168) for one CV_8UC1 image.
+ *   img/rows/cols/step : host image (step in bytes)
+ *   lap0, lap1         : vLappingArea[0], [1]
+ *   kps, desc          : caller buffers for `cap` keypoints / cap*32 bytes
+ *   *n                 : total keypoints written (the size of _keypoints)
+ * Returns monoIndex (>= 0) like the reference, ORB_E_EMPTY for an empty image. */
+int orb_extract(orb_extractor* h, const uint8_t* img, int rows, int cols, size_t step, int lap0,
+                int lap1, orb_keypoint* kps, uint8_t* desc, int cap, int* n);
+
+/* The same for `batch` equally sized frames in one submission (a camera stream
+ * or the eyes of stereo rigs).  imgs[b] are host pointers (pinned memory makes
+ * the copies asynchronous).  Frame b writes kps[b*cap ..], desc[b*cap*32 ..],
+ * n[b], mono_index[b].  lap = NULL or 2*batch ints.  Returns batch or < 0. */
+int orb_extract_batch(orb_extractor* h, int batch, const uint8_t* const* imgs, int rows, int cols,
+                      size_t step, const int* lap, orb_keypoint* kps, uint8_t* desc, int cap, int* n,
+                      int* mono_index);
+
+/* Device-resident variant: d_imgs = batch frames already in HBM (frame b at
+ * d_imgs + b*frame_stride, row pitch `step`), results stay in HBM.  Runs on the
+ * handle's stream, or on `cuda_stream` (a cudaStream_t) when non-NULL.  Result
+ * pointers are valid until the next call on the handle. */
+int orb_extract_batch_device(orb_extractor* h, int batch, const uint8_t* d_imgs, size_t frame_stride,
+                             int rows, int cols, size_t step, const int* lap, void* cuda_stream);
+int orb_device_results(orb_extractor* h, const orb_keypoint** d_kps, const uint8_t** d_desc,
+                       const int** d_n, const int** d_mono_index, int* cap_per_frame);
+/* Block until the work submitted by orb_extract_batch_device has finished. */
+int orb_synchronize(orb_extractor* h);
+
+/* Host mirror of ORBextractor::mvImagePyramid (ORBextractor.h:83) for frame
+ * `frame` of the last batch: *ptr points at the unpadded level (rows x cols,
+ * pitch *step) in engine-owned pinned memory, valid until the next extract.
+ * The device->host copy happens on first request per extract. */
+int orb_pyramid(orb_extractor* h, int frame, int level, const uint8_t** ptr, int* rows, int* cols,
+                size_t* step);
+
+/* Per-stage device timing (CUDA events on the launching stream).  Stages:
+ * 0 h2d, 1 pyramid, 2 fast, 3 octree, 4 blur, 5 layout, 6 orient+describe,
+ * 7 d2h.  orb_stage_times fills ms[8] (accumulated) and launches[8]. */
+#define ORB_NUM_STAGES 8
+int orb_set_profiling(orb_extractor* h, int enabled);
+int orb_stage_times(orb_extractor* h, double* ms, long long* launches, int reset);
+const char* orb_stage_name(int stage);
+/* Kernel launches issued by the handle since creation (the gpu_launches claim of bench.py). */
+long long orb_kernel_launches(const orb_extractor* h);
+
+/* Intermediate results of the last batch, for the parity tests: raw FAST
+ * candidates handed to the octree for (frame, level): x,y relative to the
+ * 16-px border (ORBextractor.cc:863-868) and score; returns the count. */
+int orb_debug_candidates(orb_extractor* h, int frame, int level, int* xys, int cap);
+/* Host execution of the array octree formulation (no GPU needed). */
+int orb_debug_octree_host(const int* xys, int n, int band_w, int band_h, int n_features, int w_cell,
+                          int h_cell, int n_cols, int* out_xys, int out_cap);
+/* Host execution of the libstdc++ introsort emulation: perm_out[i] = input index. */
+int orb_debug_introsort(const int* count, const int* ulx, int n, int* perm_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORB_B200_H_ */

@@ -56,6 +56,7 @@ def lib():
         L.orc_fast_atan2.argtypes = [C.c_float, C.c_float]
         L.orc_cos_sin_deg.argtypes = [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.orc_pattern.argtypes = [C.c_void_p]
+        L.orc_distribute.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.orc_sort_nodes.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _lib = L
     return _lib
@@ -164,3 +165,12 @@ def sort_nodes(count, ulx):
     perm = np.zeros(len(count), dtype=np.int32)
     lib().orc_sort_nodes(_ptr(count), _ptr(ulx), len(count), _ptr(perm))
     return perm
+
+
+def distribute(xys, band_w, band_h, n_features):
+    """DistributeOctTree on candidates xys (n,3) int32 [x, y, response]."""
+    xys = np.ascontiguousarray(xys, dtype=np.int32).reshape(-1, 3)
+    cap = n_features + 64
+    out = np.zeros((cap, 3), dtype=np.int32)
+    m = lib().orc_distribute(_ptr(xys), len(xys), band_w, band_h, n_features, _ptr(out), cap)
+    return out[:m].copy()

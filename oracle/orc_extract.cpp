@@ -642,6 +642,22 @@ void orc_cos_sin_deg(float angle_deg, float* c, float* s) {
 }
 void orc_pattern(int* out1024) { memcpy(out1024, kPattern, sizeof(kPattern)); }
 
+// DistributeOctTree alone (ORBextractor.cc:555-779) on an arbitrary candidate
+// list: xys = n x {x, y, response}, coordinates relative to minBorder.
+int orc_distribute(const int* xys, int n, int band_w, int band_h, int N, int* out_xys, int cap) {
+  Extractor e(1000, 1.2f, 8, 20, 7);
+  std::vector<orc_keypoint> pts(n);
+  for (int i = 0; i < n; i++) {
+    pts[i].x = (float)xys[3 * i]; pts[i].y = (float)xys[3 * i + 1]; pts[i].response = (float)xys[3 * i + 2];
+    pts[i].size = 7; pts[i].angle = -1; pts[i].octave = 0; pts[i].class_id = -1;
+  }
+  std::vector<orc_keypoint> r = e.distribute_octtree(pts, 0, band_w, 0, band_h, N);
+  for (int i = 0; i < (int)r.size() && i < cap; i++) {
+    out_xys[3 * i] = (int)r[i].x; out_xys[3 * i + 1] = (int)r[i].y; out_xys[3 * i + 2] = (int)r[i].response;
+  }
+  return (int)r.size();
+}
+
 // std::sort with the reference's comparator on (count, ulx) pairs; returns the
 // permutation -- used to pin the product's re-implementation of libstdc++'s
 // introsort tie behaviour (ORBextractor.cc:700).

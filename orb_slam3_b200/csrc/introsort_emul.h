@@ -1,0 +1,174 @@
+// Re-implementation of libstdc++'s std::sort control flow (introsort: median-of-3
+// unguarded partition down to 16-element runs, heapsort when the depth limit is
+// hit, then one final insertion sort) for use inside the GPU octree cull.
+//
+// Why: ORBextractor::DistributeOctTree sorts its expandable nodes with an
+// unstable std::sort whose comparator ties on (count, UL.x)
+// (reference src/ORBextractor.cc:538-553, :700).  Which of several tied nodes is
+// split last decides the surviving keypoint set, so bit-exact parity needs the
+// same permutation the reference's libstdc++ produces.  The sequence of
+// comparisons and moves below is that of GCC's bits/stl_algo.h / stl_heap.h
+// (__introsort_loop, __unguarded_partition_pivot, __final_insertion_sort,
+// __heap_select + __sort_heap); it is pinned against the host's real std::sort
+// in tests/test_introsort.py.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define ORB_HD __host__ __device__ __forceinline__
+#else
+#define ORB_HD inline
+#endif
+
+namespace orbb200 {
+
+// One sortable record: ordering key (count, ulx); `id` is the payload.
+struct SortNode {
+  int count;
+  int ulx;
+  int id;
+};
+
+ORB_HD bool node_less(const SortNode& a, const SortNode& b) {
+  if (a.count < b.count) return true;
+  if (a.count > b.count) return false;
+  return a.ulx < b.ulx;
+}
+
+ORB_HD void sn_swap(SortNode& a, SortNode& b) {
+  SortNode t = a;
+  a = b;
+  b = t;
+}
+
+// ---- heap helpers (stl_heap.h: __push_heap / __adjust_heap) ----
+ORB_HD void sn_push_heap(SortNode* first, int hole, int top, SortNode value) {
+  int parent = (hole - 1) / 2;
+  while (hole > top && node_less(first[parent], value)) {
+    first[hole] = first[parent];
+    hole = parent;
+    parent = (hole - 1) / 2;
+  }
+  first[hole] = value;
+}
+
+ORB_HD void sn_adjust_heap(SortNode* first, int hole, int len, SortNode value) {
+  const int top = hole;
+  int child = hole;
+  while (child < (len - 1) / 2) {
+    child = 2 * (child + 1);
+    if (node_less(first[child], first[child - 1])) child--;
+    first[hole] = first[child];
+    hole = child;
+  }
+  if ((len & 1) == 0 && child == (len - 2) / 2) {
+    child = 2 * (child + 1);
+    first[hole] = first[child - 1];
+    hole = child - 1;
+  }
+  sn_push_heap(first, hole, top, value);
+}
+
+// __partial_sort(first, last, last) == __heap_select(first,last,last) + __sort_heap
+ORB_HD void sn_heap_sort(SortNode* first, int len) {
+  if (len < 2) return;
+  // __make_heap
+  for (int parent = (len - 2) / 2;; parent--) {
+    SortNode v = first[parent];
+    sn_adjust_heap(first, parent, len, v);
+    if (parent == 0) break;
+  }
+  // __heap_select's scan over [middle,last) is empty (middle == last)
+  // __sort_heap
+  for (int last = len; last > 1;) {
+    --last;
+    SortNode v = first[last];  // __pop_heap(first, last, last)
+    first[last] = first[0];
+    sn_adjust_heap(first, 0, last, v);
+  }
+}
+
+ORB_HD void sn_move_median_to_first(SortNode* a, int result, int ia, int ib, int ic) {
+  if (node_less(a[ia], a[ib])) {
+    if (node_less(a[ib], a[ic])) sn_swap(a[result], a[ib]);
+    else if (node_less(a[ia], a[ic])) sn_swap(a[result], a[ic]);
+    else sn_swap(a[result], a[ia]);
+  } else if (node_less(a[ia], a[ic])) sn_swap(a[result], a[ia]);
+  else if (node_less(a[ib], a[ic])) sn_swap(a[result], a[ic]);
+  else sn_swap(a[result], a[ib]);
+}
+
+ORB_HD int sn_unguarded_partition(SortNode* a, int first, int last, int pivot) {
+  while (true) {
+    while (node_less(a[first], a[pivot])) ++first;
+    --last;
+    while (node_less(a[pivot], a[last])) --last;
+    if (!(first < last)) return first;
+    sn_swap(a[first], a[last]);
+    ++first;
+  }
+}
+
+ORB_HD void sn_unguarded_linear_insert(SortNode* a, int last) {
+  SortNode val = a[last];
+  int next = last - 1;
+  while (node_less(val, a[next])) {
+    a[last] = a[next];
+    last = next;
+    --next;
+  }
+  a[last] = val;
+}
+
+ORB_HD void sn_insertion_sort(SortNode* a, int first, int last) {
+  if (first == last) return;
+  for (int i = first + 1; i != last; ++i) {
+    if (node_less(a[i], a[first])) {
+      SortNode val = a[i];
+      for (int k = i; k > first; --k) a[k] = a[k - 1];  // move_backward
+      a[first] = val;
+    } else {
+      sn_unguarded_linear_insert(a, i);
+    }
+  }
+}
+
+// std::sort(a, a+n, compareNodes).  `stack` needs 2*64 ints of scratch.
+ORB_HD void introsort_emul(SortNode* a, int n) {
+  if (n <= 1) return;
+  int lg = 0;
+  for (int t = n; t > 1; t >>= 1) lg++;
+  // explicit stack replaces the recursion __introsort_loop(cut, last, depth)
+  int stk_first[64], stk_last[64], stk_depth[64];
+  int sp = 0;
+  stk_first[0] = 0; stk_last[0] = n; stk_depth[0] = 2 * lg; sp = 1;
+  while (sp > 0) {
+    --sp;
+    int first = stk_first[sp], last = stk_last[sp], depth = stk_depth[sp];
+    // libstdc++ recurses on the right part first and loops on the left part;
+    // the two parts are disjoint so finishing the right part before continuing
+    // with the left one is the same sequence of operations per sub-range.
+    while (last - first > 16) {
+      if (depth == 0) {
+        sn_heap_sort(a + first, last - first);
+        break;
+      }
+      --depth;
+      int mid = first + (last - first) / 2;
+      sn_move_median_to_first(a, first, first + 1, mid, last - 1);
+      int cut = sn_unguarded_partition(a, first + 1, last, first);
+      // "recurse" on [cut,last): push the left remainder, continue with right
+      stk_first[sp] = first; stk_last[sp] = cut; stk_depth[sp] = depth; ++sp;
+      first = cut;
+    }
+  }
+  // __final_insertion_sort
+  if (n > 16) {
+    sn_insertion_sort(a, 0, 16);
+    for (int i = 16; i < n; ++i) sn_unguarded_linear_insert(a, i);
+  } else {
+    sn_insertion_sort(a, 0, n);
+  }
+}
+
+}  // namespace orbb200

@@ -1,0 +1,102 @@
+// Host-side state of one ORB extractor handle (see orb_extract.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/orb_b200.h"
+#include "octree_core.h"
+
+namespace orbb200 {
+
+void set_last_error(const std::string& s);
+const char* last_error();
+
+// Per pyramid level; lives in host and device memory.
+struct LevelDev {
+  int w, h, pitch;
+  size_t img_off;        // byte offset inside a frame's pyramid slab
+  float scale;           // mvScaleFactor[level]
+  int patch_size;        // (int)(31 * scale)
+  OctreeLevelParams oct;
+  int cand_cap;
+  size_t cand_off;       // element offset inside a frame's candidate slab
+  int sel_off;           // element offset inside a frame's selected-keypoint slab
+  size_t scratch_off;    // byte offset inside a frame's octree scratch slab
+};
+
+// One FAST cell (ORBextractor.cc:805-822): image rectangle and the shift the
+// reference adds to cell-local keypoint coordinates (:863-868).
+struct CellDesc {
+  int level, x0, y0, x1, y1, shift_x, shift_y;
+};
+
+struct BlurTile {
+  int level, x0, y0;
+};
+
+struct ResizeTab {
+  int x_off = 0, y_off = 0;
+};
+
+struct Engine {
+  // parameters and tables (ORBextractor.cc:409-469)
+  int nfeatures, nlevels, ini_th, min_th, device;
+  double scale_factor;
+  std::vector<float> scale, inv_scale, sigma2, inv_sigma2;
+  std::vector<int> quota;
+  int umax[16];
+
+  // geometry for the current image size
+  std::vector<LevelDev> levels;
+  std::vector<ResizeTab> rs;
+  size_t pyr_frame_bytes = 0, cand_frame_elems = 0, scratch_frame_bytes = 0, sel_frame_elems = 0;
+  int out_cap = 0, num_cells = 0, num_tiles = 0;
+  int cap_rows = 0, cap_cols = 0, cap_batch = 0, cap_batch_hint = 1;
+
+  // device state
+  bool initialized = false;
+  cudaStream_t stream = nullptr, last_stream = nullptr;
+  std::vector<void*> dev_allocs, host_allocs;
+  uint8_t *d_pyr = nullptr, *d_blur = nullptr, *d_scratch = nullptr, *d_desc = nullptr, *d_stage = nullptr;
+  Cand* d_cand = nullptr;
+  int *d_sel = nullptr, *d_slot = nullptr, *d_cand_count = nullptr, *d_sel_count = nullptr;
+  int *d_n = nullptr, *d_mono = nullptr, *d_lap = nullptr, *d_warp_level = nullptr;
+  int *d_xofs = nullptr, *d_yofs = nullptr;
+  short2 *d_alpha = nullptr, *d_beta = nullptr;
+  orb_keypoint* d_kps = nullptr;
+  LevelDev* d_levels = nullptr;
+  CellDesc* d_cells = nullptr;
+  BlurTile* d_tiles = nullptr;
+  int* h_counts = nullptr;
+  uint8_t* h_pyr = nullptr;
+  bool pyramid_fetched = false;
+  int last_batch = 0;
+
+  // profiling
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool[ORB_NUM_STAGES + 1];
+  double stage_ms[ORB_NUM_STAGES] = {0};
+  long long stage_launches[ORB_NUM_STAGES] = {0};
+  long long total_launches = 0;
+
+  Engine(int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th, int device);
+  ~Engine();
+  void release();
+  template <class T> int dalloc(T** p, size_t count);
+  int ensure(int rows, int cols, int batch);
+  void stage_begin(int st, cudaStream_t s);
+  void stage_end(int st, cudaStream_t s, int launches);
+  int collect_times(double* ms, long long* launches, bool reset);
+  int run_device(int batch, const int* lap_host, cudaStream_t s);
+  int extract_batch_host(int batch, const uint8_t* const* imgs, int rows, int cols, size_t step, const int* lap,
+                         orb_keypoint* kps, uint8_t* desc, int cap, int* n, int* mono);
+  int extract_batch_device(int batch, const uint8_t* d_imgs, size_t frame_stride, int rows, int cols, size_t step,
+                           const int* lap, cudaStream_t user);
+  int fetch_pyramid();
+  int debug_candidates(int frame, int level, int* xys, int cap);
+};
+
+}  // namespace orbb200

@@ -1,0 +1,906 @@
+// ORB front-end for B200 (sm_100a): pyramid -> per-cell FAST-9/16 + NMS ->
+// octree cull -> intensity-centroid angle -> 7x7 blur -> steered rBRIEF-256,
+// batched over frames.  Replaces ORBextractor::operator() (reference
+// src/ORBextractor.cc:1086-1168) behind the C ABI of include/orb_b200.h.
+//
+// All integer/float semantics follow SURVEY.md Appendix A (bit-exact with the
+// CPU oracle): fixed-point bilinear resize, FAST score = max arc threshold - 1,
+// per-cell NMS band + minTh fallback, libstdc++-ordered octree, strict-IEEE
+// fastAtan2 and rBRIEF rotation (no FMA contraction: built with -fmad=false and
+// explicit _rn intrinsics).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/orb_b200.h"
+#include "octree_core.h"
+#include "orb_engine.h"
+
+namespace orbb200 {
+
+// ----------------------------------------------------------------- constants
+__constant__ int c_pattern[1024];
+__constant__ int c_umax[16];
+static const int h_pattern[1024] = {
+#include "pattern_31.inc"
+};
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& s) { g_last_error = s; }
+const char* last_error() { return g_last_error.c_str(); }
+
+#define CUDA_TRY(expr)                                                                  \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      set_last_error(std::string(#expr) + ": " + cudaGetErrorString(_e));               \
+      return ORB_E_CUDA;                                                                \
+    }                                                                                   \
+  } while (0)
+
+static inline int h_cv_round(float v) { return (int)lrintf(v); }
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// -------------------------------------------------------------- device backend
+struct CtaBackend {
+  int* smem_ints;  // [0..3] user slots, [4..4+32] scan partials, [40] total
+  __device__ int tid() const { return threadIdx.x; }
+  __device__ int nthreads() const { return blockDim.x; }
+  __device__ void sync() { __syncthreads(); }
+  __device__ int atomic_add(int* p, int v) { return atomicAdd(p, v); }
+  __device__ void atomic_max64(unsigned long long* p, unsigned long long v) { atomicMax(p, v); }
+  __device__ int* shared_int(int i) { return smem_ints + i; }
+  // In-place exclusive scan of d[0..n) by the whole CTA; every thread gets the total.
+  __device__ int exclusive_scan(int* d, int n) {
+    __syncthreads();
+    const int nt = blockDim.x, t = threadIdx.x;
+    const int chunk = (n + nt - 1) / nt;
+    const int lo = min(t * chunk, n), hi = min(lo + chunk, n);
+    int sum = 0;
+    for (int i = lo; i < hi; i++) sum += d[i];
+    // block exclusive scan of `sum`
+    const int lane = t & 31, warp = t >> 5;
+    int incl = sum;
+    for (int o = 1; o < 32; o <<= 1) {
+      int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    int* wsum = smem_ints + 4;
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      const int nw = (nt + 31) >> 5;
+      int v = lane < nw ? wsum[lane] : 0;
+      int inc2 = v;
+      for (int o = 1; o < 32; o <<= 1) {
+        int u = __shfl_up_sync(0xffffffffu, inc2, o);
+        if (lane >= o) inc2 += u;
+      }
+      if (lane < nw) wsum[lane] = inc2 - v;
+      if (lane == 31) smem_ints[40] = inc2;
+    }
+    __syncthreads();
+    int acc = wsum[warp] + incl - sum;
+    for (int i = lo; i < hi; i++) {
+      int v = d[i];
+      d[i] = acc;
+      acc += v;
+    }
+    const int total = smem_ints[40];
+    __syncthreads();
+    return total;
+  }
+};
+
+// ------------------------------------------------------------------- kernels
+
+// cv::resize INTER_LINEAR 8UC1, fixed-point; one launch per
+// level over the whole batch, 4 output pixels per thread.
+__global__ void __launch_bounds__(256)
+resize_level_kernel(uint8_t* __restrict__ pyr, size_t frame_stride, size_t src_off, int sw, int sh,
+                    int spitch, size_t dst_off, int dw, int dh, int dpitch,
+                    const int* __restrict__ xofs, const short2* __restrict__ alpha,
+                    const int* __restrict__ yofs, const short2* __restrict__ beta) {
+  const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int y = blockIdx.y;
+  if (x4 >= dw) return;
+  uint8_t* base = pyr + (size_t)blockIdx.z * frame_stride;
+  const uint8_t* S = base + src_off;
+  const int sy = yofs[y];
+  const int sy0 = min(max(sy, 0), sh - 1), sy1 = min(max(sy + 1, 0), sh - 1);
+  const uint8_t* S0 = S + (size_t)sy0 * spitch;
+  const uint8_t* S1 = S + (size_t)sy1 * spitch;
+  const short2 b = beta[y];
+  uint32_t packed = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int x = x4 + k;
+    int v = 0;
+    if (x < dw) {
+      const int sx = xofs[x];
+      const int sx1 = min(sx + 1, sw - 1);
+      const short2 a = alpha[x];
+      const int h0 = S0[sx] * a.x + S0[sx1] * a.y;
+      const int h1 = S1[sx] * a.x + S1[sx1] * a.y;
+      v = (((b.x * (h0 >> 4)) >> 16) + ((b.y * (h1 >> 4)) >> 16) + 2) >> 2;
+    }
+    packed |= (uint32_t)(v & 0xff) << (8 * k);
+  }
+  *reinterpret_cast<uint32_t*>(base + dst_off + (size_t)y * dpitch + x4) = packed;
+}
+
+// Copy the caller's level-0 image (arbitrary pitch) into the pyramid slab.
+__global__ void copy_level0_kernel(const uint8_t* __restrict__ src, size_t src_frame_stride,
+                                   size_t src_step, uint8_t* __restrict__ pyr, size_t frame_stride,
+                                   int w, int h, int pitch) {
+  const int x = (blockIdx.x * blockDim.x + threadIdx.x);
+  const int y = blockIdx.y;
+  if (x >= w) return;
+  pyr[(size_t)blockIdx.z * frame_stride + (size_t)y * pitch + x] =
+      src[(size_t)blockIdx.z * src_frame_stride + (size_t)y * src_step + x];
+}
+
+// FAST-9/16 score of the centre pixel from its ring; returns best (=score+1) or
+// 0 when the pixel is not a corner at threshold t.
+__device__ __forceinline__ int fast_best(const uint8_t* __restrict__ c, int pitch, int t) {
+  const int v = c[0];
+  const int hi = v + t, lo = v - t;
+  // a 9-arc contains one end of every diameter: test 2 diameters first
+  const int r0 = c[3 * pitch], r8 = c[-3 * pitch];
+  bool bp = (r0 > hi) | (r8 > hi), dp = (r0 < lo) | (r8 < lo);
+  if (!(bp | dp)) return 0;
+  const int r4 = c[3], r12 = c[-3];
+  bp = bp & ((r4 > hi) | (r12 > hi));
+  dp = dp & ((r4 < lo) | (r12 < lo));
+  if (!(bp | dp)) return 0;
+  int r[16];
+  r[0] = r0; r[8] = r8; r[4] = r4; r[12] = r12;
+  r[1] = c[3 * pitch + 1];  r[2] = c[2 * pitch + 2];   r[3] = c[pitch + 3];
+  r[5] = c[-pitch + 3];     r[6] = c[-2 * pitch + 2];  r[7] = c[-3 * pitch + 1];
+  r[9] = c[-3 * pitch - 1]; r[10] = c[-2 * pitch - 2]; r[11] = c[-pitch - 3];
+  r[13] = c[pitch - 3];     r[14] = c[2 * pitch - 2];  r[15] = c[3 * pitch - 1];
+  // bright arcs: v - max(window9 of r); dark arcs: min(window9 of r) - v
+  int mx2[16], mn2[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) { mx2[k] = max(r[k], r[(k + 1) & 15]); mn2[k] = min(r[k], r[(k + 1) & 15]); }
+  int mx4[16], mn4[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) { mx4[k] = max(mx2[k], mx2[(k + 2) & 15]); mn4[k] = min(mn2[k], mn2[(k + 2) & 15]); }
+  int best = 0;
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    const int mx9 = max(max(mx4[k], mx4[(k + 4) & 15]), r[(k + 8) & 15]);
+    const int mn9 = min(min(mn4[k], mn4[(k + 4) & 15]), r[(k + 8) & 15]);
+    best = max(best, max(v - mx9, mn9 - v));
+  }
+  return best > t ? best : 0;
+}
+
+// One CTA per FAST cell of ComputeKeyPointsOctTree (ORBextractor.cc:805-872):
+// score map at minTh in shared memory, 3x3 strict NMS inside the cell's band,
+// keep score>=iniTh survivors, or all survivors when there is none.
+constexpr int FAST_THREADS = 128;
+constexpr int FAST_TILE_MAX = 80;  // wCell+6 <= 75
+
+__global__ void __launch_bounds__(FAST_THREADS)
+fast_cells_kernel(const uint8_t* __restrict__ pyr, size_t frame_stride,
+                  const CellDesc* __restrict__ cells, const LevelDev* __restrict__ lv, int ini_th,
+                  int min_th, Cand* __restrict__ cand, size_t cand_frame_stride,
+                  int* __restrict__ cand_count, int nlevels) {
+  __shared__ uint8_t tile[FAST_TILE_MAX * FAST_TILE_MAX];
+  __shared__ uint8_t smap[(FAST_TILE_MAX - 4) * (FAST_TILE_MAX - 4)];
+  __shared__ int s_cnt_ini, s_cnt_all, s_base;
+  const CellDesc cd = cells[blockIdx.x];
+  const LevelDev L = lv[cd.level];
+  const int f = blockIdx.y;
+  const uint8_t* img = pyr + (size_t)f * frame_stride + L.img_off;
+  const int tw = cd.x1 - cd.x0, th = cd.y1 - cd.y0;
+  const int bw = tw - 6, bh = th - 6;
+  const int sw = bw + 2;
+  if (threadIdx.x == 0) { s_cnt_ini = 0; s_cnt_all = 0; }
+  for (int i = threadIdx.x; i < tw * th; i += FAST_THREADS) {
+    const int y = i / tw, x = i - y * tw;
+    tile[y * FAST_TILE_MAX + x] = img[(size_t)(cd.y0 + y) * L.pitch + cd.x0 + x];
+  }
+  for (int i = threadIdx.x; i < (bw + 2) * (bh + 2); i += FAST_THREADS) smap[i] = 0;
+  __syncthreads();
+  if (bw <= 0 || bh <= 0) return;
+  for (int i = threadIdx.x; i < bw * bh; i += FAST_THREADS) {
+    const int y = i / bw, x = i - y * bw;
+    const int best = fast_best(&tile[(y + 3) * FAST_TILE_MAX + x + 3], FAST_TILE_MAX, min_th);
+    smap[(y + 1) * sw + x + 1] = (uint8_t)best;
+  }
+  __syncthreads();
+  // NMS; a thread remembers its survivors as one bit per visited pixel
+  // (<= 70*70/128 = 39 visits)
+  unsigned long long keep_bits = 0, ini_bits = 0;
+  int it = 0;
+  for (int i = threadIdx.x; i < bw * bh; i += FAST_THREADS, it++) {
+    const int y = i / bw, x = i - y * bw;
+    const uint8_t* p = &smap[(y + 1) * sw + x + 1];
+    const int s = p[0];
+    if (s && s > p[-1] && s > p[1] && s > p[-sw - 1] && s > p[-sw] && s > p[-sw + 1] &&
+        s > p[sw - 1] && s > p[sw] && s > p[sw + 1]) {
+      keep_bits |= 1ull << it;
+      if (s - 1 >= ini_th) ini_bits |= 1ull << it;
+    }
+  }
+  if (keep_bits) atomicAdd(&s_cnt_all, __popcll(keep_bits));
+  if (ini_bits) atomicAdd(&s_cnt_ini, __popcll(ini_bits));
+  __syncthreads();
+  // cv::FAST(cell, iniTh) first, cv::FAST(cell, minTh) only when that is empty (:826-846)
+  const bool use_ini = s_cnt_ini > 0;
+  const int total = use_ini ? s_cnt_ini : s_cnt_all;
+  if (total == 0) return;
+  if (threadIdx.x == 0) s_base = atomicAdd(&cand_count[f * nlevels + cd.level], total);
+  __syncthreads();
+  const unsigned long long bits = use_ini ? ini_bits : keep_bits;
+  if (!bits) return;
+  // the order inside the level's list is irrelevant (the octree uses order keys)
+  Cand* out = cand + (size_t)f * cand_frame_stride + L.cand_off;
+  it = 0;
+  for (int i = threadIdx.x; i < bw * bh; i += FAST_THREADS, it++) {
+    if (!(bits & (1ull << it))) continue;
+    const int y = i / bw, x = i - y * bw;
+    const int pos = atomicAdd(&s_base, 1);
+    if (pos < L.cand_cap) {
+      Cand c;
+      c.xy = (uint32_t)(x + 3 + cd.shift_x) | ((uint32_t)(y + 3 + cd.shift_y) << 16);
+      c.score = (uint32_t)(smap[(y + 1) * sw + x + 1] - 1);
+      out[pos] = c;
+    }
+  }
+}
+
+// One CTA per (level, frame): DistributeOctTree (octree_core.h).
+constexpr int OCT_THREADS = 512;
+
+__host__ __device__ inline size_t carve(size_t& off, size_t bytes) {
+  size_t o = off;
+  off = (off + bytes + 15) & ~(size_t)15;
+  return o;
+}
+
+__host__ __device__ inline size_t octree_scratch_layout(uint8_t* base, int cand_cap, int node_cap,
+                                                        OctreeScratch* s) {
+  size_t off = 0;
+  size_t o;
+  o = carve(off, sizeof(int) * (size_t)cand_cap); if (s) s->pt_node = (int*)(base + o);
+  o = carve(off, (size_t)cand_cap);               if (s) s->pt_q = base + o;
+  for (int b = 0; b < 2; b++)
+    for (int f = 0; f < 5; f++) {
+      o = carve(off, sizeof(int) * (size_t)node_cap);
+      if (s) s->nd[b][f] = (int*)(base + o);
+    }
+  o = carve(off, sizeof(int) * 4 * (size_t)node_cap); if (s) s->childcnt = (int*)(base + o);
+  o = carve(off, sizeof(int) * 4 * (size_t)node_cap); if (s) s->cidx = (int*)(base + o);
+  o = carve(off, sizeof(int) * 4 * (size_t)node_cap); if (s) s->eidx = (int*)(base + o);
+  o = carve(off, sizeof(int) * 4 * (size_t)node_cap); if (s) s->remap = (int*)(base + o);
+  o = carve(off, sizeof(int) * (size_t)node_cap); if (s) s->rank = (int*)(base + o);
+  o = carve(off, sizeof(int) * (size_t)node_cap); if (s) s->proc = (int*)(base + o);
+  o = carve(off, sizeof(int) * (size_t)node_cap); if (s) s->surv = (int*)(base + o);
+  o = carve(off, sizeof(int) * (size_t)node_cap); if (s) s->tmp = (int*)(base + o);
+  o = carve(off, sizeof(int) * (size_t)node_cap); if (s) s->expand_pos = (int*)(base + o);
+  o = carve(off, sizeof(SortNode) * (size_t)node_cap); if (s) s->sortbuf = (SortNode*)(base + o);
+  o = carve(off, sizeof(unsigned long long) * (size_t)node_cap);
+  if (s) s->best = (unsigned long long*)(base + o);
+  return off;
+}
+
+__global__ void __launch_bounds__(OCT_THREADS)
+octree_kernel(const Cand* __restrict__ cand, size_t cand_frame_stride, const int* __restrict__ cand_count,
+              const LevelDev* __restrict__ lv, uint8_t* __restrict__ scratch, size_t scratch_frame_stride,
+              int* __restrict__ sel, size_t sel_frame_stride, int* __restrict__ sel_count, int nlevels) {
+  __shared__ int smem_ints[48];
+  const int level = blockIdx.x, f = blockIdx.y;
+  const LevelDev L = lv[level];
+  CtaBackend be;
+  be.smem_ints = smem_ints;
+  OctreeScratch s;
+  octree_scratch_layout(scratch + (size_t)f * scratch_frame_stride + L.scratch_off, L.cand_cap,
+                        L.oct.node_cap, &s);
+  const int n = min(cand_count[f * nlevels + level], L.cand_cap);
+  const Cand* c = cand + (size_t)f * cand_frame_stride + L.cand_off;
+  int* out = sel + (size_t)f * sel_frame_stride + 3 * (size_t)L.sel_off;
+  const int m = octree_select(be, c, n, L.oct, s, out);
+  if (threadIdx.x == 0) sel_count[f * nlevels + level] = m;
+}
+
+// GaussianBlur 7x7 sigma 2 over every level of every frame.
+constexpr int BLUR_TW = 128, BLUR_TH = 16;
+
+__global__ void __launch_bounds__(256)
+blur_kernel(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blr, size_t frame_stride,
+            const BlurTile* __restrict__ tiles, const LevelDev* __restrict__ lv) {
+  __shared__ uint8_t in[(BLUR_TH + 6) * (BLUR_TW + 8)];
+  __shared__ uint16_t hb[(BLUR_TH + 6) * BLUR_TW];
+  const BlurTile t = tiles[blockIdx.x];
+  const LevelDev L = lv[t.level];
+  const uint8_t* src = pyr + (size_t)blockIdx.y * frame_stride + L.img_off;
+  uint8_t* dst = blr + (size_t)blockIdx.y * frame_stride + L.img_off;
+  const int w = L.w, h = L.h;
+  const int IW = BLUR_TW + 8;
+  for (int i = threadIdx.x; i < (BLUR_TH + 6) * (BLUR_TW + 6); i += 256) {
+    const int ly = i / (BLUR_TW + 6), lx = i - ly * (BLUR_TW + 6);
+    int gx = t.x0 + lx - 3, gy = t.y0 + ly - 3;
+    // BORDER_REFLECT_101 at the true image edge
+    if (gx < 0) gx = -gx; if (gx >= w) gx = 2 * w - 2 - gx;
+    if (gy < 0) gy = -gy; if (gy >= h) gy = 2 * h - 2 - gy;
+    gx = min(max(gx, 0), w - 1);  // tiles past the right/bottom edge: value unused
+    gy = min(max(gy, 0), h - 1);
+    in[ly * IW + lx] = src[(size_t)gy * L.pitch + gx];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < (BLUR_TH + 6) * BLUR_TW; i += 256) {
+    const int ly = i / BLUR_TW, lx = i - ly * BLUR_TW;
+    const uint8_t* p = &in[ly * IW + lx];
+    hb[i] = (uint16_t)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < BLUR_TH * BLUR_TW; i += 256) {
+    const int ly = i / BLUR_TW, lx = i - ly * BLUR_TW;
+    const int gx = t.x0 + lx, gy = t.y0 + ly;
+    if (gx >= w || gy >= h) continue;
+    const uint16_t* p = &hb[ly * BLUR_TW + lx];
+    const uint32_t acc = 18u * (p[0] + p[6 * BLUR_TW]) + 34u * (p[BLUR_TW] + p[5 * BLUR_TW]) +
+                         48u * (p[2 * BLUR_TW] + p[4 * BLUR_TW]) + 56u * p[3 * BLUR_TW];
+    dst[(size_t)gy * L.pitch + gx] = (uint8_t)((acc + (1u << 15)) >> 16);
+  }
+}
+
+// Output slot of every selected keypoint: operator() walks levels and list
+// order, lapping-area points fill the array from the back (ORBextractor.cc
+// :1122-1163).  One CTA per frame.
+__global__ void __launch_bounds__(256)
+layout_kernel(const int* __restrict__ sel, size_t sel_frame_stride, const int* __restrict__ sel_count,
+              const LevelDev* __restrict__ lv, int nlevels, const int* __restrict__ lap,
+              int* __restrict__ slot, int* __restrict__ n_out, int* __restrict__ mono_out, int out_cap) {
+  __shared__ int smem_ints[48];
+  __shared__ int s_total;
+  CtaBackend be;
+  be.smem_ints = smem_ints;
+  const int f = blockIdx.x;
+  const float lap0 = lap ? (float)lap[2 * f] : 0.f, lap1 = lap ? (float)lap[2 * f + 1] : 0.f;
+  const int* fsel = sel + (size_t)f * sel_frame_stride;
+  int* fslot = slot + (size_t)f * sel_frame_stride / 3;
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int l = 0; l < nlevels; l++) t += sel_count[f * nlevels + l];
+    s_total = t;
+  }
+  __syncthreads();
+  const int total = s_total;
+  int mono = 0, stereo = total - 1;
+  for (int l = 0; l < nlevels; l++) {
+    const LevelDev L = lv[l];
+    const int m = sel_count[f * nlevels + l];
+    int* ls = fslot + L.sel_off;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+      float x = (float)fsel[3 * (L.sel_off + i)];
+      if (l != 0) x = __fmul_rn(x, L.scale);
+      ls[i] = (x >= lap0 && x <= lap1) ? 1 : 0;
+    }
+    __syncthreads();
+    // ls[i] <- number of lapped points before i; then slot
+    const int nlap = be.exclusive_scan(ls, m);
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+      float x = (float)fsel[3 * (L.sel_off + i)];
+      if (l != 0) x = __fmul_rn(x, L.scale);
+      const bool lapped = (x >= lap0 && x <= lap1);
+      const int before = ls[i];
+      const int pos = lapped ? (stereo - before) : (mono + (i - before));
+      ls[i] = pos < out_cap ? pos : -1;
+    }
+    __syncthreads();
+    mono += m - nlap;
+    stereo -= nlap;
+  }
+  if (threadIdx.x == 0) { n_out[f] = total; mono_out[f] = mono; }
+}
+
+// cv::fastAtan2, every operation rounded to float.
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+  const float s180 = 57.29577951308232f;  // (float)(180/pi)
+  const float p1 = __fmul_rn(0.9997878412794807f, s180), p3 = __fmul_rn(-0.3258083974640975f, s180);
+  const float p5 = __fmul_rn(0.1555786518463281f, s180), p7 = __fmul_rn(-0.04432655554792128f, s180);
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float eps = 2.220446049250313e-16f;
+  float a;
+  if (ax >= ay) {
+    const float c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+    const float c2 = __fmul_rn(c, c);
+    a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+  } else {
+    const float c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+    const float c2 = __fmul_rn(c, c);
+    a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+  }
+  if (x < 0) a = __fsub_rn(180.f, a);
+  if (y < 0) a = __fsub_rn(360.f, a);
+  return a;
+}
+
+// One warp per selected keypoint: IC_Angle (ORBextractor.cc:76-103) on the raw
+// level, computeOrbDescriptor (:107-146) on the blurred level, final
+// KeyPoint fields (:880-890, :1149-1151), written to its output slot.
+__global__ void __launch_bounds__(256)
+describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blr, size_t frame_stride,
+                const int* __restrict__ sel, size_t sel_frame_stride, const int* __restrict__ sel_count,
+                const int* __restrict__ slot, const LevelDev* __restrict__ lv, int nlevels,
+                const int* __restrict__ warp_level, orb_keypoint* __restrict__ kps,
+                uint8_t* __restrict__ desc, int out_cap) {
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // index in the sel slab
+  const int f = blockIdx.y;
+  const int level = warp_level[gw];
+  if (level < 0) return;
+  const LevelDev L = lv[level];
+  const int i = gw - L.sel_off;
+  if (i >= sel_count[f * nlevels + level]) return;
+  const int* rec = sel + (size_t)f * sel_frame_stride + 3 * (size_t)gw;
+  const int x = rec[0] + 16, y = rec[1] + 16, score = rec[2];  // add minBorder back (:884-885)
+  const int pos = slot[(size_t)f * sel_frame_stride / 3 + gw];
+  if (pos < 0) return;
+  const uint8_t* img = pyr + (size_t)f * frame_stride + L.img_off;
+  // ---- IC_Angle: lane <-> u = lane-15
+  int m10 = 0, m01 = 0;
+  if (lane < 31) {
+    const int u = lane - 15, au = abs(u);
+    const uint8_t* c = img + (size_t)y * L.pitch + x + u;
+    for (int v = -15; v <= 15; v++) {
+      if (au <= c_umax[abs(v)]) {
+        const int val = c[v * L.pitch];
+        m10 += u * val;
+        m01 += v * val;
+      }
+    }
+  }
+  m10 = __reduce_add_sync(0xffffffffu, m10);
+  m01 = __reduce_add_sync(0xffffffffu, m01);
+  const float angle = fast_atan2_deg((float)m01, (float)m10);
+  // ---- steered BRIEF: lane <-> descriptor byte
+  const float factorPI = 0.017453292519943295f;  // (float)(CV_PI/180.f)
+  const float ang = __fmul_rn(angle, factorPI);
+  const float a = (float)cos((double)ang), b = (float)sin((double)ang);
+  const uint8_t* bc = blr + (size_t)f * frame_stride + L.img_off + (size_t)y * L.pitch + x;
+  const int* pat = c_pattern + 32 * lane;
+  int val = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const float x0 = (float)pat[4 * k], y0 = (float)pat[4 * k + 1];
+    const float x1 = (float)pat[4 * k + 2], y1 = (float)pat[4 * k + 3];
+    const int ry0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+    const int rx0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+    const int ry1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+    const int rx1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+    const int t0 = bc[ry0 * L.pitch + rx0], t1 = bc[ry1 * L.pitch + rx1];
+    val |= (t0 < t1) << k;
+  }
+  desc[((size_t)f * out_cap + pos) * 32 + lane] = (uint8_t)val;
+  if (lane == 0) {
+    orb_keypoint kp;
+    float fx = (float)x, fy = (float)y;
+    if (level != 0) { fx = __fmul_rn(fx, L.scale); fy = __fmul_rn(fy, L.scale); }
+    kp.x = fx; kp.y = fy;
+    kp.size = (float)L.patch_size;
+    kp.angle = angle;
+    kp.response = (float)score;
+    kp.octave = level;
+    kp.class_id = -1;
+    kps[(size_t)f * out_cap + pos] = kp;
+  }
+}
+
+// ------------------------------------------------------------------- engine
+Engine::Engine(int nf, float sf, int nl, int ini, int mn, int dev)
+    : nfeatures(nf), nlevels(nl), ini_th(ini), min_th(mn), device(dev), scale_factor(sf) {
+  // ORBextractor.cc:409-469
+  scale.resize(nl); sigma2.resize(nl); inv_scale.resize(nl); inv_sigma2.resize(nl); quota.resize(nl);
+  scale[0] = 1.0f; sigma2[0] = 1.0f;
+  for (int i = 1; i < nl; i++) {
+    scale[i] = (float)(scale[i - 1] * scale_factor);
+    sigma2[i] = scale[i] * scale[i];
+  }
+  for (int i = 0; i < nl; i++) {
+    inv_scale[i] = 1.0f / scale[i];
+    inv_sigma2[i] = 1.0f / sigma2[i];
+  }
+  float factor = (float)(1.0f / scale_factor);
+  float nDesired = nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nlevels));
+  int sum = 0;
+  for (int l = 0; l < nl - 1; l++) {
+    quota[l] = h_cv_round(nDesired);
+    sum += quota[l];
+    nDesired *= factor;
+  }
+  quota[nl - 1] = std::max(nfeatures - sum, 0);
+  int um[17];
+  memset(um, 0, sizeof(um));
+  const int HP = 15;
+  int vmax = (int)floorf(HP * sqrtf(2.f) / 2 + 1);
+  int vmin = (int)ceilf(HP * sqrtf(2.f) / 2);
+  const double hp2 = HP * HP;
+  for (int v = 0; v <= vmax; ++v) um[v] = (int)lrint(sqrt(hp2 - v * v));
+  for (int v = HP, v0 = 0; v >= vmin; --v) {
+    while (um[v0] == um[v0 + 1]) ++v0;
+    um[v] = v0;
+    ++v0;
+  }
+  for (int i = 0; i < 16; i++) umax[i] = um[i];
+}
+
+Engine::~Engine() { release(); }
+
+void Engine::release() {
+  if (!initialized) return;
+  cudaSetDevice(device);
+  for (void* p : dev_allocs) cudaFree(p);
+  dev_allocs.clear();
+  for (void* p : host_allocs) cudaFreeHost(p);
+  host_allocs.clear();
+  for (int i = 0; i < ORB_NUM_STAGES + 1; i++)
+    for (auto& e : ev_pool[i]) cudaEventDestroy(e);
+  if (stream) cudaStreamDestroy(stream);
+  stream = nullptr;
+  initialized = false;
+  cap_rows = cap_cols = cap_batch = 0;
+}
+
+template <class T>
+int Engine::dalloc(T** p, size_t count) {
+  void* q = nullptr;
+  CUDA_TRY(cudaMalloc(&q, std::max<size_t>(count * sizeof(T), 16)));
+  dev_allocs.push_back(q);
+  *p = (T*)q;
+  return 0;
+}
+
+int Engine::ensure(int rows, int cols, int batch) {
+  if (rows == cap_rows && cols == cap_cols && batch <= cap_batch) return 0;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_last_error("no CUDA device: orb_slam3_b200 has no CPU path");
+    return ORB_E_NODEVICE;
+  }
+  release();
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  initialized = true;
+  CUDA_TRY(cudaMemcpyToSymbol(c_pattern, h_pattern, sizeof(h_pattern)));
+  CUDA_TRY(cudaMemcpyToSymbol(c_umax, umax, sizeof(umax)));
+
+  // ---- geometry (ComputePyramid :1170-1195, ComputeKeyPointsOctTree :781-822)
+  levels.assign(nlevels, LevelDev());
+  std::vector<CellDesc> cells;
+  std::vector<BlurTile> tiles;
+  std::vector<int> h_xofs, h_yofs;
+  std::vector<short2> h_alpha, h_beta;
+  size_t img_off = 0, cand_off = 0, scratch_off = 0;
+  int sel_off = 0;
+  rs.assign(nlevels, ResizeTab());
+  for (int l = 0; l < nlevels; l++) {
+    LevelDev& L = levels[l];
+    L.w = h_cv_round((float)cols * inv_scale[l]);
+    L.h = h_cv_round((float)rows * inv_scale[l]);
+    if (L.w < 40 || L.h < 40) {
+      set_last_error("image too small for the pyramid (level < 40 px)");
+      return ORB_E_ARG;
+    }
+    L.pitch = (int)align_up(L.w, 64);
+    L.img_off = img_off;
+    img_off += align_up((size_t)L.pitch * L.h, 256);
+    L.scale = scale[l];
+    L.patch_size = (int)(31 * scale[l]);
+    const int minB = 16, maxBX = L.w - 16, maxBY = L.h - 16;
+    const float width = (float)(maxBX - minB), height = (float)(maxBY - minB);
+    const int nCols = (int)(width / 35.f), nRows = (int)(height / 35.f);
+    const int wCell = (int)ceilf(width / nCols), hCell = (int)ceilf(height / nRows);
+    if (wCell + 6 > FAST_TILE_MAX - 4 || hCell + 6 > FAST_TILE_MAX - 4 || wCell >= 128 || hCell >= 128) {
+      set_last_error("unsupported FAST cell size");
+      return ORB_E_ARG;
+    }
+    for (int i = 0; i < nRows; i++) {
+      const float iniY = (float)(minB + i * hCell);
+      float maxY = iniY + hCell + 6;
+      if (iniY >= maxBY - 3) continue;
+      if (maxY > maxBY) maxY = (float)maxBY;
+      for (int j = 0; j < nCols; j++) {
+        const float iniX = (float)(minB + j * wCell);
+        float maxX = iniX + wCell + 6;
+        if (iniX >= maxBX - 6) continue;
+        if (maxX > maxBX) maxX = (float)maxBX;
+        CellDesc c;
+        c.level = l; c.x0 = (int)iniX; c.y0 = (int)iniY; c.x1 = (int)maxX; c.y1 = (int)maxY;
+        c.shift_x = j * wCell; c.shift_y = i * hCell;
+        cells.push_back(c);
+      }
+    }
+    OctreeLevelParams& o = L.oct;
+    o.bandW = maxBX - minB; o.bandH = maxBY - minB;
+    o.N = quota[l];
+    o.nIni = (int)roundf((float)o.bandW / (float)o.bandH);
+    if (o.nIni < 1) {
+      set_last_error("aspect ratio < 0.5 is undefined in the reference (nIni == 0)");
+      return ORB_E_ARG;
+    }
+    o.hX = (float)o.bandW / o.nIni;
+    o.wCell = wCell; o.hCell = hCell; o.nCols = nCols;
+    o.node_cap = o.N + 4 * o.nIni + 16;
+    L.cand_cap = (o.bandW / 2 + nCols + 2) * (o.bandH / 2 + nRows + 2);
+    L.cand_off = cand_off;
+    cand_off += align_up(L.cand_cap, 4);
+    L.sel_off = sel_off;
+    sel_off += o.node_cap;
+    L.scratch_off = scratch_off;
+    scratch_off += align_up(octree_scratch_layout(nullptr, L.cand_cap, o.node_cap, nullptr), 256);
+    for (int ty = 0; ty < L.h; ty += BLUR_TH)
+      for (int tx = 0; tx < L.w; tx += BLUR_TW) tiles.push_back(BlurTile{l, tx, ty});
+    if (l > 0) {
+      // cv::resize coefficient tables
+      const LevelDev& S = levels[l - 1];
+      ResizeTab& R = rs[l];
+      R.x_off = (int)h_xofs.size(); R.y_off = (int)h_yofs.size();
+      const double scale_x = 1. / ((double)L.w / S.w), scale_y = 1. / ((double)L.h / S.h);
+      auto sat = [](int v) { return (short)std::min(32767, std::max(-32768, v)); };
+      for (int dx = 0; dx < L.w; dx++) {
+        float fx = (float)((dx + 0.5) * scale_x - 0.5);
+        int sx = (int)floorf(fx);
+        fx -= sx;
+        if (sx < 0) { fx = 0; sx = 0; }
+        if (sx >= S.w - 1) { fx = 0; sx = S.w - 1; }
+        h_xofs.push_back(sx);
+        h_alpha.push_back(make_short2(sat(h_cv_round((1.f - fx) * 2048.f)), sat(h_cv_round(fx * 2048.f))));
+      }
+      for (int dy = 0; dy < L.h; dy++) {
+        float fy = (float)((dy + 0.5) * scale_y - 0.5);
+        int sy = (int)floorf(fy);
+        fy -= sy;
+        h_yofs.push_back(sy);
+        h_beta.push_back(make_short2(sat(h_cv_round((1.f - fy) * 2048.f)), sat(h_cv_round(fy * 2048.f))));
+      }
+    }
+  }
+  pyr_frame_bytes = align_up(img_off, 256);
+  cand_frame_elems = cand_off;
+  scratch_frame_bytes = scratch_off;
+  sel_frame_elems = align_up(sel_off, 32);
+  out_cap = sel_off;  // >= any possible keypoint count
+  num_cells = (int)cells.size();
+  num_tiles = (int)tiles.size();
+  std::vector<int> warp_level(sel_frame_elems, -1);
+  for (int l = 0; l < nlevels; l++)
+    for (int i = 0; i < levels[l].oct.node_cap; i++) warp_level[levels[l].sel_off + i] = l;
+
+  const size_t B = batch;
+  if (dalloc(&d_pyr, pyr_frame_bytes * B)) return ORB_E_CUDA;
+  if (dalloc(&d_blur, pyr_frame_bytes * B)) return ORB_E_CUDA;
+  if (dalloc(&d_cand, cand_frame_elems * B)) return ORB_E_CUDA;
+  if (dalloc(&d_scratch, scratch_frame_bytes * B)) return ORB_E_CUDA;
+  if (dalloc(&d_sel, 3 * sel_frame_elems * B)) return ORB_E_CUDA;
+  if (dalloc(&d_slot, sel_frame_elems * B)) return ORB_E_CUDA;
+  if (dalloc(&d_cand_count, (size_t)nlevels * B)) return ORB_E_CUDA;
+  if (dalloc(&d_sel_count, (size_t)nlevels * B)) return ORB_E_CUDA;
+  if (dalloc(&d_n, B)) return ORB_E_CUDA;
+  if (dalloc(&d_mono, B)) return ORB_E_CUDA;
+  if (dalloc(&d_lap, 2 * B)) return ORB_E_CUDA;
+  if (dalloc(&d_kps, (size_t)out_cap * B)) return ORB_E_CUDA;
+  if (dalloc(&d_desc, (size_t)out_cap * 32 * B)) return ORB_E_CUDA;
+  if (dalloc(&d_levels, (size_t)nlevels)) return ORB_E_CUDA;
+  if (dalloc(&d_cells, cells.size())) return ORB_E_CUDA;
+  if (dalloc(&d_tiles, tiles.size())) return ORB_E_CUDA;
+  if (dalloc(&d_warp_level, warp_level.size())) return ORB_E_CUDA;
+  if (dalloc(&d_xofs, h_xofs.size())) return ORB_E_CUDA;
+  if (dalloc(&d_yofs, h_yofs.size())) return ORB_E_CUDA;
+  if (dalloc(&d_alpha, h_alpha.size())) return ORB_E_CUDA;
+  if (dalloc(&d_beta, h_beta.size())) return ORB_E_CUDA;
+  if (dalloc(&d_stage, (size_t)rows * cols * B)) return ORB_E_CUDA;
+  CUDA_TRY(cudaMemcpy(d_levels, levels.data(), sizeof(LevelDev) * nlevels, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(d_cells, cells.data(), sizeof(CellDesc) * cells.size(), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(d_tiles, tiles.data(), sizeof(BlurTile) * tiles.size(), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(d_warp_level, warp_level.data(), sizeof(int) * warp_level.size(), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(d_xofs, h_xofs.data(), sizeof(int) * h_xofs.size(), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(d_yofs, h_yofs.data(), sizeof(int) * h_yofs.size(), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(d_alpha, h_alpha.data(), sizeof(short2) * h_alpha.size(), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(d_beta, h_beta.data(), sizeof(short2) * h_beta.size(), cudaMemcpyHostToDevice));
+  void* hp = nullptr;
+  CUDA_TRY(cudaHostAlloc(&hp, sizeof(int) * 2 * B, cudaHostAllocDefault));
+  host_allocs.push_back(hp);
+  h_counts = (int*)hp;
+  CUDA_TRY(cudaHostAlloc(&hp, pyr_frame_bytes * B, cudaHostAllocDefault));
+  host_allocs.push_back(hp);
+  h_pyr = (uint8_t*)hp;
+  cap_rows = rows; cap_cols = cols; cap_batch = batch;
+  return 0;
+}
+
+void Engine::stage_begin(int st, cudaStream_t s) {
+  if (!profiling) return;
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  ev_pool[st].push_back(a);
+  ev_pool[st].push_back(b);
+  cudaEventRecord(a, s);
+}
+void Engine::stage_end(int st, cudaStream_t s, int launches) {
+  stage_launches[st] += launches;
+  total_launches += launches;
+  if (!profiling) return;
+  cudaEventRecord(ev_pool[st].back(), s);
+}
+
+int Engine::collect_times(double* ms, long long* launches, bool reset) {
+  for (int st = 0; st < ORB_NUM_STAGES; st++) {
+    for (size_t i = 0; i + 1 < ev_pool[st].size(); i += 2) {
+      float t = 0;
+      cudaEventSynchronize(ev_pool[st][i + 1]);
+      if (cudaEventElapsedTime(&t, ev_pool[st][i], ev_pool[st][i + 1]) == cudaSuccess) stage_ms[st] += t;
+      cudaEventDestroy(ev_pool[st][i]);
+      cudaEventDestroy(ev_pool[st][i + 1]);
+    }
+    ev_pool[st].clear();
+    if (ms) ms[st] = stage_ms[st];
+    if (launches) launches[st] = stage_launches[st];
+    if (reset) { stage_ms[st] = 0; stage_launches[st] = 0; }
+  }
+  return 0;
+}
+
+// Everything between "level 0 is in the pyramid slab" and "results are in
+// d_kps/d_desc/d_n/d_mono", on stream s.
+int Engine::run_device(int batch, const int* lap_host, cudaStream_t s) {
+  const int B = batch;
+  pyramid_fetched = false;
+  last_batch = batch;
+  if (lap_host) {
+    CUDA_TRY(cudaMemcpyAsync(d_lap, lap_host, sizeof(int) * 2 * B, cudaMemcpyHostToDevice, s));
+  }
+  // 1. pyramid
+  stage_begin(1, s);
+  for (int l = 1; l < nlevels; l++) {
+    const LevelDev& S = levels[l - 1];
+    const LevelDev& D = levels[l];
+    dim3 grid((D.w + 4 * 256 - 1) / (4 * 256), D.h, B);
+    resize_level_kernel<<<grid, 256, 0, s>>>(d_pyr, pyr_frame_bytes, S.img_off, S.w, S.h, S.pitch, D.img_off,
+                                            D.w, D.h, D.pitch, d_xofs + rs[l].x_off, d_alpha + rs[l].x_off,
+                                            d_yofs + rs[l].y_off, d_beta + rs[l].y_off);
+  }
+  stage_end(1, s, nlevels - 1);
+  // 2. FAST cells
+  stage_begin(2, s);
+  CUDA_TRY(cudaMemsetAsync(d_cand_count, 0, sizeof(int) * nlevels * B, s));
+  fast_cells_kernel<<<dim3(num_cells, B), FAST_THREADS, 0, s>>>(d_pyr, pyr_frame_bytes, d_cells, d_levels, ini_th,
+                                                                min_th, d_cand, cand_frame_elems, d_cand_count,
+                                                                nlevels);
+  stage_end(2, s, 1);
+  // 3. octree
+  stage_begin(3, s);
+  octree_kernel<<<dim3(nlevels, B), OCT_THREADS, 0, s>>>(d_cand, cand_frame_elems, d_cand_count, d_levels, d_scratch,
+                                                         scratch_frame_bytes, d_sel, 3 * sel_frame_elems, d_sel_count,
+                                                         nlevels);
+  stage_end(3, s, 1);
+  // 4. blur
+  stage_begin(4, s);
+  blur_kernel<<<dim3(num_tiles, B), 256, 0, s>>>(d_pyr, d_blur, pyr_frame_bytes, d_tiles, d_levels);
+  stage_end(4, s, 1);
+  // 5. output layout
+  stage_begin(5, s);
+  layout_kernel<<<B, 256, 0, s>>>(d_sel, 3 * sel_frame_elems, d_sel_count, d_levels, nlevels,
+                                  lap_host ? d_lap : nullptr, d_slot, d_n, d_mono, out_cap);
+  stage_end(5, s, 1);
+  // 6. orientation + descriptors
+  stage_begin(6, s);
+  describe_kernel<<<dim3((unsigned)(sel_frame_elems / 8), B), 256, 0, s>>>(
+      d_pyr, d_blur, pyr_frame_bytes, d_sel, 3 * sel_frame_elems, d_sel_count, d_slot, d_levels, nlevels,
+      d_warp_level, d_kps, d_desc, out_cap);
+  stage_end(6, s, 1);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int Engine::extract_batch_host(int batch, const uint8_t* const* imgs, int rows, int cols, size_t step,
+                               const int* lap, orb_keypoint* kps, uint8_t* desc, int cap, int* n, int* mono) {
+  if (batch <= 0 || !imgs || !kps || !desc || !n || !mono) { set_last_error("bad argument"); return ORB_E_ARG; }
+  if (rows <= 0 || cols <= 0) return ORB_E_EMPTY;
+  for (int b = 0; b < batch; b++)
+    if (!imgs[b]) return ORB_E_EMPTY;
+  int rc = ensure(rows, cols, std::max(batch, cap_batch_hint));
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(device));
+  cudaStream_t s = stream;
+  stage_begin(0, s);
+  const LevelDev& L0 = levels[0];
+  for (int b = 0; b < batch; b++)
+    CUDA_TRY(cudaMemcpy2DAsync(d_pyr + (size_t)b * pyr_frame_bytes, L0.pitch, imgs[b], step, cols, rows,
+                               cudaMemcpyHostToDevice, s));
+  stage_end(0, s, 0);
+  rc = run_device(batch, lap, s);
+  if (rc) return rc;
+  stage_begin(7, s);
+  CUDA_TRY(cudaMemcpyAsync(h_counts, d_n, sizeof(int) * batch, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(h_counts + batch, d_mono, sizeof(int) * batch, cudaMemcpyDeviceToHost, s));
+  // keypoints are dense from slot 0; copy the quota-sized prefix now, the rare
+  // overshoot (<= 3 per level) after the counts are known
+  const int guess = std::min(std::min(cap, out_cap), nfeatures + 4 * nlevels);
+  for (int b = 0; b < batch; b++) {
+    CUDA_TRY(cudaMemcpyAsync(kps + (size_t)b * cap, d_kps + (size_t)b * out_cap, sizeof(orb_keypoint) * guess,
+                             cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(desc + (size_t)b * cap * 32, d_desc + (size_t)b * out_cap * 32, (size_t)32 * guess,
+                             cudaMemcpyDeviceToHost, s));
+  }
+  CUDA_TRY(cudaStreamSynchronize(s));
+  int worst = 0;
+  for (int b = 0; b < batch; b++) {
+    n[b] = h_counts[b];
+    mono[b] = h_counts[batch + b];
+    worst = std::max(worst, n[b]);
+  }
+  if (worst > cap) { set_last_error("keypoint buffer too small"); return ORB_E_CAPACITY; }
+  if (worst > guess) {
+    for (int b = 0; b < batch; b++) {
+      if (n[b] <= guess) continue;
+      CUDA_TRY(cudaMemcpyAsync(kps + (size_t)b * cap + guess, d_kps + (size_t)b * out_cap + guess,
+                               sizeof(orb_keypoint) * (n[b] - guess), cudaMemcpyDeviceToHost, s));
+      CUDA_TRY(cudaMemcpyAsync(desc + ((size_t)b * cap + guess) * 32, d_desc + ((size_t)b * out_cap + guess) * 32,
+                               (size_t)32 * (n[b] - guess), cudaMemcpyDeviceToHost, s));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));
+  }
+  stage_end(7, s, 0);
+  return batch;
+}
+
+int Engine::extract_batch_device(int batch, const uint8_t* d_imgs, size_t frame_stride, int rows, int cols,
+                                 size_t step, const int* lap, cudaStream_t user) {
+  if (batch <= 0 || !d_imgs) { set_last_error("bad argument"); return ORB_E_ARG; }
+  if (rows <= 0 || cols <= 0) return ORB_E_EMPTY;
+  int rc = ensure(rows, cols, std::max(batch, cap_batch_hint));
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(device));
+  cudaStream_t s = user ? user : stream;
+  last_stream = s;
+  const LevelDev& L0 = levels[0];
+  stage_begin(0, s);
+  CUDA_TRY(cudaMemcpy2DAsync(d_pyr, L0.pitch, d_imgs, step, cols, rows, cudaMemcpyDeviceToDevice, s));
+  if (batch > 1) {
+    for (int b = 1; b < batch; b++)
+      CUDA_TRY(cudaMemcpy2DAsync(d_pyr + (size_t)b * pyr_frame_bytes, L0.pitch, d_imgs + (size_t)b * frame_stride,
+                                 step, cols, rows, cudaMemcpyDeviceToDevice, s));
+  }
+  stage_end(0, s, 0);
+  return run_device(batch, lap, s) ? ORB_E_CUDA : batch;
+}
+
+int Engine::fetch_pyramid() {
+  if (pyramid_fetched) return 0;
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaMemcpyAsync(h_pyr, d_pyr, pyr_frame_bytes * last_batch, cudaMemcpyDeviceToHost, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  pyramid_fetched = true;
+  return 0;
+}
+
+int Engine::debug_candidates(int frame, int level, int* xys, int cap) {
+  if (!initialized || frame < 0 || frame >= last_batch || level < 0 || level >= nlevels) return ORB_E_ARG;
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  int cnt = 0;
+  CUDA_TRY(cudaMemcpy(&cnt, d_cand_count + frame * nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+  const int m = std::min(std::min(cnt, levels[level].cand_cap), cap);
+  std::vector<Cand> tmp(std::max(m, 1));
+  CUDA_TRY(cudaMemcpy(tmp.data(), d_cand + (size_t)frame * cand_frame_elems + levels[level].cand_off,
+                      sizeof(Cand) * m, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < m; i++) {
+    xys[3 * i] = tmp[i].xy & 0xffff;
+    xys[3 * i + 1] = tmp[i].xy >> 16;
+    xys[3 * i + 2] = tmp[i].score;
+  }
+  return cnt;
+}
+
+}  // namespace orbb200

@@ -1,0 +1,121 @@
+"""GPU parity: liborbb200.so (through the C ABI / ORBextractor mirror) against
+the CPU oracle on the same seeded frames -- bit-exact keypoints
+(x, y, octave, angle, response, size), 32-byte descriptors, order and
+monoIndex (BASELINE.json configs[0] and [1])."""
+import numpy as np
+import pytest
+
+from orb_slam3_b200.synth import synth_frame, shifted_frame
+
+pytestmark = pytest.mark.gpu
+
+
+def _assert_same(ref, got, ctx=""):
+    rk, rd, rm = ref
+    gm, gk, gd = got
+    assert gm == rm, (ctx, "monoIndex", gm, rm)
+    assert len(gk) == len(rk), (ctx, "count", len(gk), len(rk))
+    for f in ("x", "y", "size", "angle", "response", "octave", "class_id"):
+        bad = np.nonzero(gk[f] != rk[f])[0]
+        assert len(bad) == 0, (ctx, f, len(bad), bad[:5], gk[f][bad[:5]], rk[f][bad[:5]])
+    assert np.array_equal(gd, rd), (ctx, "descriptors", int((gd != rd).any(1).sum()))
+
+
+@pytest.fixture(scope="module")
+def ext1000():
+    from orb_slam3_b200.extractor import ORBextractor
+    return ORBextractor(1000, 1.2, 8, 20, 7)
+
+
+def test_pyramid_and_candidates_match_oracle(oracle, ext1000):
+    img = synth_frame(480, 640, 2)
+    ex = oracle.OracleExtractor(1000)
+    ex.extract(img)
+    ext1000(img)
+    for lvl in range(8):
+        assert np.array_equal(ex.level_image(lvl), ext1000.image_pyramid(lvl)), lvl
+        c = ex.level_candidates(lvl)
+        ref = np.stack([c["x"], c["y"], c["response"]], 1).astype(np.int32)
+        got = ext1000.debug_candidates(lvl)
+        key = lambda a: a[np.lexsort((a[:, 0], a[:, 1]))]
+        assert len(ref) == len(got), (lvl, len(ref), len(got))
+        assert np.array_equal(key(ref), key(got)), lvl
+
+
+@pytest.mark.parametrize("seed,low", [(1, False), (2, False), (3, True), (4, False)])
+def test_config1_640x480_1000_bit_exact(oracle, ext1000, seed, low):
+    img = synth_frame(480, 640, seed, low_texture=low)
+    ref = oracle.OracleExtractor(1000).extract(img)
+    _assert_same(ref, ext1000(img), "seed%d" % seed)
+
+
+def test_config2_1280x720_2000_bit_exact(oracle):
+    from orb_slam3_b200.extractor import ORBextractor
+    ext = ORBextractor(2000, 1.2, 8, 20, 7)
+    orc = oracle.OracleExtractor(2000)
+    for seed in (1, 7):
+        img = synth_frame(720, 1280, seed)
+        _assert_same(orc.extract(img), ext(img), "seed%d" % seed)
+
+
+def test_lapping_area_and_mono_index(oracle, ext1000):
+    img = synth_frame(480, 640, 5)
+    for lap in ((0, 0), (0, 1000), (200, 400), (0, 320)):
+        ref = oracle.OracleExtractor(1000).extract(img, lap)
+        _assert_same(ref, ext1000(img, None, lap), str(lap))
+
+
+def test_batch_equals_single(oracle):
+    from orb_slam3_b200.extractor import ORBextractor
+    ext = ORBextractor(1000, 1.2, 8, 20, 7)
+    base = synth_frame(480, 640, 9)
+    frames = [base]
+    for t in range(1, 6):
+        frames.append(shifted_frame(frames[-1], 3 - t, t - 2, 100 + t))
+    res = ext.extract_batch(frames)
+    orc = oracle.OracleExtractor(1000)
+    for t, fr in enumerate(frames):
+        _assert_same(orc.extract(fr), res[t], "frame%d" % t)
+
+
+def test_other_geometries_and_parameters(oracle):
+    from orb_slam3_b200.extractor import ORBextractor
+    for (h, w, nf, sf, nl, ini, mn) in [(376, 1241, 2000, 1.2, 8, 20, 7), (480, 752, 1200, 1.2, 8, 20, 7),
+                                        (400, 400, 500, 1.3, 5, 15, 5), (480, 640, 5000, 1.2, 8, 20, 7)]:
+        img = synth_frame(h, w, 11)
+        ref = oracle.OracleExtractor(nf, sf, nl, ini, mn).extract(img)
+        got = ORBextractor(nf, sf, nl, ini, mn)(img)
+        _assert_same(ref, got, str((h, w, nf)))
+
+
+def test_strided_input_and_empty(oracle, ext1000):
+    big = synth_frame(500, 700, 12)
+    view = big[10:490, 30:670]  # 480x640 view with a 700-byte step
+    ref = oracle.OracleExtractor(1000).extract(np.ascontiguousarray(view))
+    _assert_same(ref, ext1000(view), "strided")
+    mono, k, d = ext1000(np.zeros((0, 0), np.uint8))
+    assert mono == -1 and len(k) == 0
+
+
+def test_device_resident_path(oracle):
+    import torch
+    from orb_slam3_b200.extractor import ORBextractor
+    from orb_slam3_b200._lib import KP_DTYPE
+    ext = ORBextractor(1000, 1.2, 8, 20, 7)
+    frames = np.stack([synth_frame(480, 640, 20 + i) for i in range(3)])
+    d = torch.from_numpy(frames).cuda()
+    ext.extract_batch_device(d.data_ptr(), 3, 480, 640, 640, 480 * 640)
+    ext.synchronize()
+    kp, ds, n, mono, cap = ext.device_results()
+    import ctypes as C
+    cudart = torch.cuda.cudart()
+    nn = np.zeros(3, np.int32)
+    cudart.cudaMemcpy(nn.ctypes.data, n, 12, 2)
+    orc = oracle.OracleExtractor(1000)
+    for b in range(3):
+        k = np.zeros(nn[b], KP_DTYPE)
+        dd = np.zeros((nn[b], 32), np.uint8)
+        cudart.cudaMemcpy(k.ctypes.data, kp + b * cap * 28, int(nn[b]) * 28, 2)
+        cudart.cudaMemcpy(dd.ctypes.data, ds + b * cap * 32, int(nn[b]) * 32, 2)
+        rk, rd, rm = orc.extract(frames[b])
+        _assert_same((rk, rd, rm), (rm, k, dd), "dev%d" % b)
