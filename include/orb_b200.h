@@ -94,6 +94,9 @@ int orb_extract_batch_device(orb_extractor* h, int batch, const uint8_t* d_imgs,
                              int rows, int cols, size_t step, const int* lap, void* cuda_stream);
 int orb_device_results(orb_extractor* h, const orb_keypoint** d_kps, const uint8_t** d_desc,
                        const int** d_n, const int** d_mono_index, int* cap_per_frame);
+/* Copy frame `frame`'s results of the last device-resident batch to host buffers
+ * (synchronises the stream).  Returns monoIndex, *n = keypoint count. */
+int orb_download_results(orb_extractor* h, int frame, orb_keypoint* kps, uint8_t* desc, int cap, int* n);
 /* Block until the work submitted by orb_extract_batch_device has finished. */
 int orb_synchronize(orb_extractor* h);
 
@@ -103,6 +106,122 @@ int orb_synchronize(orb_extractor* h);
  * The device->host copy happens on first request per extract. */
 int orb_pyramid(orb_extractor* h, int frame, int level, const uint8_t** ptr, int* rows, int* cols,
                 size_t* step);
+
+/* ------------------------------------------------------------------------
+ * ORBmatcher (include/ORBmatcher.h:43-76, src/ORBmatcher.cc) on flat views.
+ * Only the Pinhole single-camera layout (Frame::Nleft == -1) is covered; the
+ * fisheye-stereo branches (ORBmatcher.cc:144-210, 1797-1857) are out of scope.
+ * TH_HIGH=100, TH_LOW=50, HISTO_LENGTH=30 (ORBmatcher.cc:35-37) are built in.
+ * ---------------------------------------------------------------------- */
+
+/* static int ORBmatcher::DescriptorDistance(const cv::Mat&, const cv::Mat&)
+ * (ORBmatcher.cc:2058-2074): Hamming distance of two 32-byte descriptors.
+ * Host helper (the device kernels use __popc on the same 8 words). */
+int ham_distance(const uint8_t* a, const uint8_t* b);
+
+/* The Frame / KeyFrame fields the matchers read (include/Frame.h, KeyFrame.h). */
+typedef struct orb_frame_view {
+  int32_t n;                    /* N */
+  const orb_keypoint* keys;     /* mvKeysUn: pt, octave, angle are read */
+  const float* u_right;         /* mvuRight; NULL = monocular (all -1) */
+  const uint8_t* desc;          /* mDescriptors, n x 32 */
+  float min_x, min_y, max_x, max_y;   /* mnMinX, mnMinY, mnMaxX, mnMaxY */
+  float grid_w_inv, grid_h_inv;       /* mfGridElementWidthInv / HeightInv (64 x 48 grid) */
+  int32_t n_levels;
+  const float* scale_factors;   /* mvScaleFactors */
+  const float* level_sigma2;    /* mvLevelSigma2 */
+  float fx, fy, cx, cy, bf, b;  /* Pinhole parameters, mbf, mb */
+  const uint8_t* kp_taken;      /* per keypoint: mvpMapPoints[i] != NULL && ->Observations() > 0
+                                   (SearchByProjection) / GetMapPoint(i) != NULL (SearchForTriangulation); NULL = none */
+} orb_frame_view;
+
+/* The MapPoint tracking fields SearchByProjection(Frame&, vector<MapPoint*>&) reads
+ * (ORBmatcher.cc:43-141), one entry per element of vpMapPoints. */
+typedef struct orb_mappoint_view {
+  int32_t n;
+  const uint8_t* track_in_view; /* mbTrackInView */
+  const uint8_t* is_bad;        /* isBad() */
+  const uint8_t* has_obs;       /* Observations() > 0 */
+  const float* proj_x;          /* mTrackProjX */
+  const float* proj_y;          /* mTrackProjY */
+  const float* proj_xr;         /* mTrackProjXR */
+  const int32_t* scale_level;   /* mnTrackScaleLevel */
+  const float* view_cos;        /* mTrackViewCos */
+  const float* depth;           /* mTrackDepth */
+  const uint8_t* desc;          /* GetDescriptor(), n x 32 */
+} orb_mappoint_view;
+
+/* What SearchByProjection(Frame& Cur, const Frame& Last, ...) reads of LastFrame
+ * (ORBmatcher.cc:1695-1733), one entry per last-frame keypoint. */
+typedef struct orb_lastframe_view {
+  int32_t n;                    /* LastFrame.N */
+  const uint8_t* has_mp;        /* mvpMapPoints[i] != NULL && !mvbOutlier[i] */
+  const uint8_t* has_obs;       /* that MapPoint's Observations() > 0 */
+  const float* world_pos;       /* GetWorldPos(), n x 3 */
+  const uint8_t* desc;          /* pMP->GetDescriptor(), n x 32 */
+  const int32_t* octave;        /* mvKeys[i].octave */
+  const float* angle;           /* mvKeysUn[i].angle */
+} orb_lastframe_view;
+
+/* DBoW2::FeatureVector as CSR: node_ids ascending (std::map order),
+ * feature indices of node k are idx[ptr[k] .. ptr[k+1]). */
+typedef struct orb_featvec_view {
+  int32_t n_nodes;
+  const uint32_t* node_ids;
+  const int32_t* ptr;
+  const int32_t* idx;
+} orb_featvec_view;
+
+typedef struct orb_matcher orb_matcher;
+int match_create(int device, orb_matcher** out);
+void match_destroy(orb_matcher* m);
+
+/* int ORBmatcher(nnratio).SearchByProjection(Frame& F, const vector<MapPoint*>&, th,
+ * bFarPoints, thFarPoints) (ORBmatcher.cc:43-141).  assign_out[i] (F.n entries) =
+ * index into `mps` written to F.mvpMapPoints[i] by this call, or -1 when the
+ * call leaves the slot untouched.  Returns nmatches. */
+int match_project_local(orb_matcher* m, const orb_frame_view* F, const orb_mappoint_view* mps, float th,
+                        float nn_ratio, int far_points, float th_far, int32_t* assign_out);
+
+/* int ORBmatcher(nnratio, checkOri).SearchByProjection(Frame& Cur, const Frame& Last, th,
+ * bMono) (ORBmatcher.cc:1676-1887).  Tcw = Cur.GetPose() as Sophus stores it:
+ * unit quaternion (x,y,z,w) then translation.  forward/backward are the
+ * reference's bForward/bBackward (:1692-1693, computed by the shim).
+ * assign_out[i] (Cur.n entries) = index of the last-frame keypoint whose
+ * MapPoint ends up in Cur.mvpMapPoints[i]; -1 = untouched; -2 = written and then
+ * cleared by the rotation-consistency check (:1875-1884).  Returns nmatches. */
+int match_project_last(orb_matcher* m, const orb_frame_view* cur, const orb_lastframe_view* last,
+                       const float* Tcw_qt7, int forward, int backward, float th, int check_orientation,
+                       int32_t* assign_out);
+
+/* int ORBmatcher(nnratio, checkOri).SearchForTriangulation(KF1, KF2, vMatchedPairs,
+ * bOnlyStereo, bCoarse) (ORBmatcher.cc:907-1146), both KFs Pinhole without a
+ * second camera.  F12 = K1^-T [t12]x R12 K2^-1 (Pinhole.cpp:107-112, computed by the
+ * shim with Eigen), ep = epipole of KF1 in KF2 (:919-920).  pairs_out receives
+ * (idx1, idx2) pairs in increasing idx1; returns the pair count (>cap: ORB_E_CAPACITY). */
+int match_triangulate(orb_matcher* m, const orb_frame_view* kf1, const orb_frame_view* kf2,
+                      const orb_featvec_view* fv1, const orb_featvec_view* fv2, const float* F12_rowmajor9,
+                      const float* ep2, int only_stereo, int coarse, int check_orientation,
+                      int32_t* pairs_out, int cap);
+
+/* Batched forms: `count` independent problems in one submission (frames of a
+ * stream, keyframe pairs).  All views are host memory unless `on_device` != 0,
+ * in which case every pointer inside the views (and the outputs) is a device
+ * pointer and nothing is copied.  results[k] = per-problem return value. */
+int match_project_last_batch(orb_matcher* m, int count, const orb_frame_view* cur, const orb_lastframe_view* last,
+                             const float* Tcw_qt7, const int32_t* forward, const int32_t* backward, float th,
+                             int check_orientation, int32_t* const* assign_out, int32_t* results, int on_device);
+int match_project_local_batch(orb_matcher* m, int count, const orb_frame_view* F, const orb_mappoint_view* mps,
+                              float th, float nn_ratio, int far_points, float th_far, int32_t* const* assign_out,
+                              int32_t* results, int on_device);
+int match_triangulate_batch(orb_matcher* m, int count, const orb_frame_view* kf1, const orb_frame_view* kf2,
+                            const orb_featvec_view* fv1, const orb_featvec_view* fv2, const float* F12_rowmajor9,
+                            const float* ep2, int only_stereo, int coarse, int check_orientation,
+                            int32_t* const* pairs_out, int cap, int32_t* results, int on_device);
+int match_synchronize(orb_matcher* m);
+long long match_kernel_launches(const orb_matcher* m);
+/* Device time of the last batch (CUDA events on the matcher's stream), ms. */
+double match_last_ms(orb_matcher* m);
 
 /* Per-stage device timing (CUDA events on the launching stream).  Stages:
  * 0 h2d, 1 pyramid, 2 fast, 3 octree, 4 blur, 5 layout, 6 orient+describe,

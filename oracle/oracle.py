@@ -57,6 +57,16 @@ def lib():
         L.orc_cos_sin_deg.argtypes = [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.orc_pattern.argtypes = [C.c_void_p]
         L.orc_distribute.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.orc_extract_throughput.restype = C.c_double
+        L.orc_extract_throughput.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                             C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]
+        L.orc_ham_distance.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_match_project_local.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_float,
+                                              C.c_void_p]
+        L.orc_match_project_last.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float,
+                                             C.c_int, C.c_void_p]
+        L.orc_match_triangulate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.orc_sort_nodes.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _lib = L
     return _lib
@@ -174,3 +184,45 @@ def distribute(xys, band_w, band_h, n_features):
     out = np.zeros((cap, 3), dtype=np.int32)
     m = lib().orc_distribute(_ptr(xys), len(xys), band_w, band_h, n_features, _ptr(out), cap)
     return out[:m].copy()
+
+
+def extract_throughput(frames, nfeatures, nthreads, iters, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+    """frames [n,H,W] uint8 -> (frames_per_second, frames_done, seconds) using C++ std::threads."""
+    frames = np.ascontiguousarray(frames, dtype=np.uint8)
+    tot = C.c_longlong(0)
+    dt = lib().orc_extract_throughput(nfeatures, scale_factor, nlevels, ini_th, min_th, _ptr(frames),
+                                      frames.shape[0], frames.shape[1], frames.shape[2], nthreads, iters,
+                                      C.byref(tot))
+    done = nthreads * iters
+    return done / dt, done, dt
+
+
+# ---- matchers: the views are the ctypes structs of orb_slam3_b200/views.py (interface types)
+def ham_distance(a, b):
+    a = np.ascontiguousarray(a, np.uint8)
+    b = np.ascontiguousarray(b, np.uint8)
+    return lib().orc_ham_distance(_ptr(a), _ptr(b))
+
+
+def match_project_local(F, mps, th, nn_ratio, far_points=False, th_far=50.0):
+    out = np.empty(F.n, np.int32)
+    n = lib().orc_match_project_local(C.byref(F), C.byref(mps), th, nn_ratio, int(far_points), th_far, _ptr(out))
+    return n, out
+
+
+def match_project_last(cur, last, Tcw_qt7, th, forward=False, backward=False, check_ori=True):
+    T = np.ascontiguousarray(Tcw_qt7, np.float32)
+    out = np.empty(cur.n, np.int32)
+    n = lib().orc_match_project_last(C.byref(cur), C.byref(last), _ptr(T), int(forward), int(backward), th,
+                                     int(check_ori), _ptr(out))
+    return n, out
+
+
+def match_triangulate(kf1, kf2, fv1, fv2, F12, ep, only_stereo=False, coarse=False, check_ori=True, cap=None):
+    cap = cap or max(kf1.n, 1)
+    F12 = np.ascontiguousarray(F12, np.float32).reshape(9)
+    ep = np.ascontiguousarray(ep, np.float32).reshape(2)
+    out = np.empty((cap, 2), np.int32)
+    n = lib().orc_match_triangulate(C.byref(kf1), C.byref(kf2), C.byref(fv1), C.byref(fv2), _ptr(F12), _ptr(ep),
+                                    int(only_stereo), int(coarse), int(check_ori), _ptr(out), cap)
+    return n, out[:n]

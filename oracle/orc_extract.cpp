@@ -26,7 +26,9 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <list>
+#include <thread>
 #include <vector>
 
 #include "orc_common.h"
@@ -209,9 +211,10 @@ inline int reflect101(int p, int n) {
   return p;
 }
 
-void gaussian_blur7(const uint8_t* src, int w, int h, int sstep, uint8_t* dst, int dstep) {
+void gaussian_blur7(const uint8_t* src, int w, int h, int sstep, uint8_t* dst, int dstep,
+                    std::vector<uint16_t>& hb) {
   static const int K[7] = {18, 34, 48, 56, 48, 34, 18};
-  std::vector<uint16_t> hb((size_t)w * h);
+  hb.resize((size_t)w * h);  // caller-owned scratch: no per-call mmap/munmap
   std::vector<int> xi(w + 6);
   for (int x = -3; x < w + 3; x++) xi[x + 3] = reflect101(x, w);
   for (int y = 0; y < h; y++) {
@@ -279,6 +282,8 @@ struct Extractor {
   std::vector<Image> pyr;
   std::vector<std::vector<orc_keypoint>> cand;   // per level, vToDistributeKeys (cell-shifted coords)
   std::vector<std::vector<orc_keypoint>> lvl_kp; // per level after octree+orientation (level coords)
+  Image blurred;                 // reused across calls
+  std::vector<uint16_t> blur_tmp;
 
   // ORBextractor.cc:409-469
   Extractor(int nf, float sf, int nl, int ini, int mn)
@@ -556,14 +561,13 @@ struct Extractor {
     *n_out = nkeypoints;
     if (nkeypoints > cap) return -2;
     int monoIndex = 0, stereoIndex = nkeypoints - 1;
-    Image blurred;
     uint8_t d[32];
     for (int l = 0; l < nlevels; l++) {
       std::vector<orc_keypoint>& kps = lvl_kp[l];
       if (kps.empty()) continue;
       blurred.w = pyr[l].w; blurred.h = pyr[l].h;
       blurred.px.resize(pyr[l].px.size());
-      gaussian_blur7(pyr[l].px.data(), pyr[l].w, pyr[l].h, pyr[l].w, blurred.px.data(), blurred.w);
+      gaussian_blur7(pyr[l].px.data(), pyr[l].w, pyr[l].h, pyr[l].w, blurred.px.data(), blurred.w, blur_tmp);
       const float s = scale[l];
       for (const orc_keypoint& src : kps) {
         orb_descriptor(src, blurred, d);
@@ -632,7 +636,8 @@ int orc_fast(const uint8_t* img, int w, int h, int step, int threshold, int nonm
   return (int)v.size();
 }
 void orc_gaussian_blur7(const uint8_t* src, int w, int h, int sstep, uint8_t* dst, int dstep) {
-  gaussian_blur7(src, w, h, sstep, dst, dstep);
+  std::vector<uint16_t> tmp;
+  gaussian_blur7(src, w, h, sstep, dst, dstep, tmp);
 }
 float orc_fast_atan2(float y, float x) { return fast_atan2(y, x); }
 void orc_cos_sin_deg(float angle_deg, float* c, float* s) {
@@ -656,6 +661,38 @@ int orc_distribute(const int* xys, int n, int band_w, int band_h, int N, int* ou
     out_xys[3 * i] = (int)r[i].x; out_xys[3 * i + 1] = (int)r[i].y; out_xys[3 * i + 2] = (int)r[i].response;
   }
   return (int)r.size();
+}
+
+// CPU baseline: `nthreads` std::threads, one extractor instance each (the
+// reference runs one thread per extractor, Frame.cc:122-125), each extracting
+// `iters` frames round-robin from `frames` (nframes x rows x cols, dense).
+// Returns elapsed seconds; *total_kp accumulates keypoints so nothing is elided.
+double orc_extract_throughput(int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh,
+                              const uint8_t* frames, int nframes, int rows, int cols, int nthreads,
+                              int iters, long long* total_kp) {
+  std::vector<Extractor*> ex(nthreads);
+  for (auto& e : ex) e = new Extractor(nfeatures, scaleFactor, nlevels, iniTh, minTh);
+  std::vector<long long> kp(nthreads, 0);
+  const int cap = nfeatures * 2 + 64 * nlevels;
+  auto t0 = std::chrono::steady_clock::now();
+  std::vector<std::thread> th;
+  for (int t = 0; t < nthreads; t++)
+    th.emplace_back([&, t]() {
+      std::vector<orc_keypoint> k(cap);
+      std::vector<uint8_t> d((size_t)cap * 32);
+      for (int i = 0; i < iters; i++) {
+        int n = 0;
+        const uint8_t* img = frames + (size_t)((t + i) % nframes) * rows * cols;
+        ex[t]->extract(img, rows, cols, cols, 0, 0, k.data(), d.data(), cap, &n);
+        kp[t] += n;
+      }
+    });
+  for (auto& x : th) x.join();
+  double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  long long tot = 0;
+  for (int t = 0; t < nthreads; t++) { tot += kp[t]; delete ex[t]; }
+  if (total_kp) *total_kp = tot;
+  return dt;
 }
 
 // std::sort with the reference's comparator on (count, ulx) pairs; returns the

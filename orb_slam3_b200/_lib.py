@@ -43,8 +43,21 @@ SIGNATURES = {
     "orb_extract_batch_device": (_i, [_vp, _i, _vp, _sz, _i, _i, _sz, _vp, _vp]),
     "orb_device_results": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp),
                                 C.POINTER(_i)]),
+    "orb_download_results": (_i, [_vp, _i, _vp, _vp, _i, C.POINTER(_i)]),
     "orb_synchronize": (_i, [_vp]),
     "orb_pyramid": (_i, [_vp, _i, _i, C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), C.POINTER(_sz)]),
+    "ham_distance": (_i, [_vp, _vp]),
+    "match_create": (_i, [_i, C.POINTER(_vp)]),
+    "match_destroy": (None, [_vp]),
+    "match_project_local": (_i, [_vp, _vp, _vp, _f, _f, _i, _f, _vp]),
+    "match_project_last": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp]),
+    "match_triangulate": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i]),
+    "match_project_last_batch": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _f, _i, _vp, _vp, _i]),
+    "match_project_local_batch": (_i, [_vp, _i, _vp, _vp, _f, _f, _i, _f, _vp, _vp, _i]),
+    "match_triangulate_batch": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _i]),
+    "match_synchronize": (_i, [_vp]),
+    "match_kernel_launches": (C.c_longlong, [_vp]),
+    "match_last_ms": (C.c_double, [_vp]),
     "orb_set_profiling": (_i, [_vp, _i]),
     "orb_stage_times": (_i, [_vp, _vp, _vp, _i]),
     "orb_stage_name": (C.c_char_p, [_i]),

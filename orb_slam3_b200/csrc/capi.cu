@@ -89,6 +89,29 @@ int orb_device_results(orb_extractor* h, const orb_keypoint** d_kps, const uint8
   return ORB_OK;
 }
 
+int orb_download_results(orb_extractor* h, int frame, orb_keypoint* kps, uint8_t* desc, int cap, int* n) {
+  if (!h || !h->e.initialized || frame < 0 || frame >= h->e.last_batch || !kps || !desc || !n) return ORB_E_ARG;
+  Engine& e = h->e;
+  cudaSetDevice(e.device);
+  cudaStream_t s = e.last_stream ? e.last_stream : e.stream;
+  int cnt[2] = {0, 0};
+  if (cudaMemcpyAsync(&cnt[0], e.d_n + frame, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+      cudaMemcpyAsync(&cnt[1], e.d_mono + frame, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+      cudaStreamSynchronize(s) != cudaSuccess) {
+    orbb200::set_last_error(cudaGetErrorString(cudaGetLastError()));
+    return ORB_E_CUDA;
+  }
+  *n = cnt[0];
+  if (cnt[0] > cap) { orbb200::set_last_error("keypoint buffer too small"); return ORB_E_CAPACITY; }
+  if (cudaMemcpyAsync(kps, e.d_kps + (size_t)frame * e.out_cap, sizeof(orb_keypoint) * cnt[0], cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+      cudaMemcpyAsync(desc, e.d_desc + (size_t)frame * e.out_cap * 32, (size_t)32 * cnt[0], cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+      cudaStreamSynchronize(s) != cudaSuccess) {
+    orbb200::set_last_error(cudaGetErrorString(cudaGetLastError()));
+    return ORB_E_CUDA;
+  }
+  return cnt[1];
+}
+
 int orb_synchronize(orb_extractor* h) {
   if (!h || !h->e.initialized) return ORB_E_ARG;
   cudaSetDevice(h->e.device);

@@ -381,7 +381,7 @@ layout_kernel(const int* __restrict__ sel, size_t sel_frame_stride, const int* _
     const int m = sel_count[f * nlevels + l];
     int* ls = fslot + L.sel_off;
     for (int i = threadIdx.x; i < m; i += blockDim.x) {
-      float x = (float)fsel[3 * (L.sel_off + i)];
+      float x = (float)(fsel[3 * (L.sel_off + i)] + 16);  // minBorder added back (:884)
       if (l != 0) x = __fmul_rn(x, L.scale);
       ls[i] = (x >= lap0 && x <= lap1) ? 1 : 0;
     }
@@ -389,7 +389,7 @@ layout_kernel(const int* __restrict__ sel, size_t sel_frame_stride, const int* _
     // ls[i] <- number of lapped points before i; then slot
     const int nlap = be.exclusive_scan(ls, m);
     for (int i = threadIdx.x; i < m; i += blockDim.x) {
-      float x = (float)fsel[3 * (L.sel_off + i)];
+      float x = (float)(fsel[3 * (L.sel_off + i)] + 16);  // minBorder added back (:884)
       if (l != 0) x = __fmul_rn(x, L.scale);
       const bool lapped = (x >= lap0 && x <= lap1);
       const int before = ls[i];

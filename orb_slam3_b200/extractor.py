@@ -115,6 +115,13 @@ class ORBextractor:
                                            C.byref(cap)))
         return k.value, d.value, n.value, m.value, cap.value
 
+    def download_results(self, frame):
+        kps = np.empty(self.cap, dtype=KP_DTYPE)
+        desc = np.empty((self.cap, 32), dtype=np.uint8)
+        n = C.c_int(0)
+        mono = check(self._lib.orb_download_results(self._h, frame, ptr(kps), ptr(desc), self.cap, C.byref(n)))
+        return mono, kps[:n.value], desc[:n.value]
+
     def synchronize(self):
         check(self._lib.orb_synchronize(self._h))
 

@@ -1,0 +1,125 @@
+"""ctypes mirrors of the flat view structs of include/orb_b200.h.
+
+A view only borrows memory: every numpy array handed in is kept alive on the
+Python object (`_keep`)."""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import KP_DTYPE
+
+_f, _i = C.c_float, C.c_int32
+_vp = C.c_void_p
+
+FRAME_GRID_COLS, FRAME_GRID_ROWS = 64, 48  # include/Frame.h:44-45
+
+
+class orb_frame_view(C.Structure):
+    _fields_ = [("n", _i), ("keys", _vp), ("u_right", _vp), ("desc", _vp),
+                ("min_x", _f), ("min_y", _f), ("max_x", _f), ("max_y", _f),
+                ("grid_w_inv", _f), ("grid_h_inv", _f),
+                ("n_levels", _i), ("scale_factors", _vp), ("level_sigma2", _vp),
+                ("fx", _f), ("fy", _f), ("cx", _f), ("cy", _f), ("bf", _f), ("b", _f),
+                ("kp_taken", _vp)]
+
+
+class orb_mappoint_view(C.Structure):
+    _fields_ = [("n", _i), ("track_in_view", _vp), ("is_bad", _vp), ("has_obs", _vp),
+                ("proj_x", _vp), ("proj_y", _vp), ("proj_xr", _vp), ("scale_level", _vp),
+                ("view_cos", _vp), ("depth", _vp), ("desc", _vp)]
+
+
+class orb_lastframe_view(C.Structure):
+    _fields_ = [("n", _i), ("has_mp", _vp), ("has_obs", _vp), ("world_pos", _vp), ("desc", _vp),
+                ("octave", _vp), ("angle", _vp)]
+
+
+class orb_featvec_view(C.Structure):
+    _fields_ = [("n_nodes", _i), ("node_ids", _vp), ("ptr", _vp), ("idx", _vp)]
+
+
+def _arr(a, dtype):
+    if a is None:
+        return None
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data
+
+
+def make_frame_view(keys, desc, width, height, scale_factors, u_right=None, kp_taken=None,
+                    fx=700.0, fy=700.0, cx=None, cy=None, bf=0.0, b=0.0, level_sigma2=None):
+    """Frame fields as the Frame constructor derives them for an undistorted pinhole
+    image: mnMinX=0, mnMaxX=cols, grid inverse = 64/(maxX-minX) (Frame.cc:ComputeImageBounds,
+    :181-182)."""
+    keys = _arr(keys, KP_DTYPE)
+    desc = _arr(desc, np.uint8)
+    sf = _arr(scale_factors, np.float32)
+    s2 = _arr(level_sigma2 if level_sigma2 is not None else sf * sf, np.float32)
+    ur = _arr(u_right, np.float32)
+    tk = _arr(kp_taken, np.uint8)
+    v = orb_frame_view()
+    v.n = len(keys)
+    v.keys, v.u_right, v.desc, v.kp_taken = _p(keys), _p(ur), _p(desc), _p(tk)
+    v.min_x, v.min_y, v.max_x, v.max_y = 0.0, 0.0, float(width), float(height)
+    v.grid_w_inv = np.float32(FRAME_GRID_COLS) / np.float32(v.max_x - v.min_x)
+    v.grid_h_inv = np.float32(FRAME_GRID_ROWS) / np.float32(v.max_y - v.min_y)
+    v.n_levels = len(sf)
+    v.scale_factors, v.level_sigma2 = _p(sf), _p(s2)
+    v.fx, v.fy = fx, fy
+    v.cx = width / 2.0 if cx is None else cx
+    v.cy = height / 2.0 if cy is None else cy
+    v.bf, v.b = bf, b
+    v._keep = (keys, desc, sf, s2, ur, tk)
+    return v
+
+
+def make_mappoint_view(proj_x, proj_y, scale_level, desc, view_cos=None, proj_xr=None, depth=None,
+                       track_in_view=None, is_bad=None, has_obs=None):
+    n = len(proj_x)
+    a = dict(
+        track_in_view=_arr(np.ones(n) if track_in_view is None else track_in_view, np.uint8),
+        is_bad=_arr(np.zeros(n) if is_bad is None else is_bad, np.uint8),
+        has_obs=_arr(np.ones(n) if has_obs is None else has_obs, np.uint8),
+        proj_x=_arr(proj_x, np.float32), proj_y=_arr(proj_y, np.float32),
+        proj_xr=_arr(np.full(n, -1.0) if proj_xr is None else proj_xr, np.float32),
+        scale_level=_arr(scale_level, np.int32),
+        view_cos=_arr(np.ones(n) if view_cos is None else view_cos, np.float32),
+        depth=_arr(np.ones(n) if depth is None else depth, np.float32),
+        desc=_arr(desc, np.uint8))
+    v = orb_mappoint_view()
+    v.n = n
+    for k, arr in a.items():
+        setattr(v, k, _p(arr))
+    v._keep = a
+    return v
+
+
+def make_lastframe_view(world_pos, desc, octave, angle, has_mp=None, has_obs=None):
+    n = len(octave)
+    a = dict(has_mp=_arr(np.ones(n) if has_mp is None else has_mp, np.uint8),
+             has_obs=_arr(np.ones(n) if has_obs is None else has_obs, np.uint8),
+             world_pos=_arr(world_pos, np.float32), desc=_arr(desc, np.uint8),
+             octave=_arr(octave, np.int32), angle=_arr(angle, np.float32))
+    v = orb_lastframe_view()
+    v.n = n
+    for k, arr in a.items():
+        setattr(v, k, _p(arr))
+    v._keep = a
+    return v
+
+
+def make_featvec_view(node_of_feature):
+    """DBoW2::FeatureVector from a per-feature node id (-1 = feature not in the vector)."""
+    node_of_feature = np.asarray(node_of_feature, dtype=np.int64)
+    valid = np.nonzero(node_of_feature >= 0)[0]
+    order = valid[np.argsort(node_of_feature[valid], kind="stable")]  # ascending index inside a node
+    ids, counts = np.unique(node_of_feature[order], return_counts=True)
+    a = dict(node_ids=_arr(ids, np.uint32), ptr=_arr(np.concatenate([[0], np.cumsum(counts)]), np.int32),
+             idx=_arr(order, np.int32))
+    v = orb_featvec_view()
+    v.n_nodes = len(ids)
+    v.node_ids, v.ptr, v.idx = _p(a["node_ids"]), _p(a["ptr"]), _p(a["idx"])
+    v._keep = a
+    return v
