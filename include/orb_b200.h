@@ -223,6 +223,64 @@ long long match_kernel_launches(const orb_matcher* m);
 /* Device time of the last batch (CUDA events on the matcher's stream), ms. */
 double match_last_ms(orb_matcher* m);
 
+/* ------------------------------------------------------------------------
+ * Optimizer::LocalBundleAdjustment (src/Optimizer.cc:1116-1498): the g2o
+ * Levenberg-Marquardt loop `optimizer.optimize(10)` (:1410-1411) on a flat graph.
+ * The shim keeps steps 1-4 (collecting KFs/MPs/edges, :1119-1400) and 6-7
+ * (outlier erase, write-back under Map::mMutexMapUpdate, :1413-1497).
+ * Pinhole mono (EdgeSE3ProjectXYZ) and stereo (g2o::EdgeStereoSE3ProjectXYZ)
+ * edges; EdgeSE3ProjectXYZToBody (second camera) is out of scope.
+ * ---------------------------------------------------------------------- */
+typedef struct lba_graph_view {
+  int32_t n_kf;               /* local + fixed keyframes */
+  const double* kf_pose;      /* n_kf x 7: g2o::SE3Quat(Tcw): quaternion x,y,z,w then translation (:1217, :1236) */
+  const uint8_t* kf_fixed;    /* vSE3->setFixed() (:1219, :1238) */
+  const float* kf_cam;        /* n_kf x 5: fx, fy, cx, cy, mbf of the KF's Pinhole camera */
+  int32_t n_mp;
+  const double* mp_pos;       /* n_mp x 3, VertexSBAPointXYZ estimates (:1285) */
+  int32_t n_edges;
+  const int32_t* e_kf;        /* index into kf arrays */
+  const int32_t* e_mp;        /* index into mp arrays */
+  const uint8_t* e_stereo;    /* 0: mono 2-D edge (:1305-1331), 1: stereo 3-D edge (:1332-1364) */
+  const double* e_obs;        /* n_edges x 3: kpUn.pt.x, kpUn.pt.y, mvuRight (ignored for mono) */
+  const float* e_inv_sigma2;  /* mvInvLevelSigma2[kpUn.octave] */
+} lba_graph_view;
+
+typedef struct lba_stats {
+  int32_t iterations;         /* outer LM iterations executed (return value of optimize()) */
+  int32_t trials;             /* total lambda trials (linear solves), incl. rejected ones */
+  int32_t stopped;            /* 1 when *stop ended the loop */
+  double chi2_initial, chi2_final, lambda_final;
+  double ms_total;            /* device time of the whole solve (CUDA events) */
+  double ms_linearize, ms_schur, ms_solve, ms_update;   /* accumulated per stage */
+  int32_t n_free_kf, n_pairs;
+  double schur_flops;         /* block-sparse useful flops per trial */
+} lba_stats;
+
+typedef struct lba_solver lba_solver;
+int lba_create(int device, lba_solver** out);
+void lba_destroy(lba_solver* s);
+/* Multi-GPU: landmarks (with their edges) are sharded over `world` ranks, poses
+ * replicated; one ncclAllReduce(sum, fp64) of [S, b_schur, chi2] per trial.
+ * unique_id = the 128 bytes of ncclGetUniqueId from rank 0 (lba_nccl_unique_id). */
+int lba_nccl_unique_id(void* out128);
+int lba_comm_init(lba_solver* s, int rank, int world, const void* unique_id128);
+
+/* Runs optimize(max_iters) (reference: 10).  lambda_init <= 0 selects g2o's
+ * tau*max(diag H) (tau = 1e-5); > 0 is setUserLambdaInit (100 for inertial maps,
+ * Optimizer.cc:1197-1198).  `stop` is polled between trials like
+ * SparseOptimizer::terminate(); NULL = never.  Outputs (caller buffers):
+ *   kf_pose_out n_kf x 7, mp_pos_out n_mp x 3,
+ *   chi2_out n_edges      e->chi2() as the reference reads it after optimize()
+ *                          (errors of the last evaluated trial, :1423-1460),
+ *   depth_pos_out n_edges  e->isDepthPositive() at the final estimates.
+ * With a communicator, the graph view holds this rank's landmark shard and all
+ * keyframes; outputs cover the shard.  Returns iterations or < 0. */
+int lba_solve(lba_solver* s, const lba_graph_view* g, const volatile uint8_t* stop, int max_iters,
+              double lambda_init, double* kf_pose_out, double* mp_pos_out, double* chi2_out,
+              uint8_t* depth_pos_out, lba_stats* stats);
+long long lba_kernel_launches(const lba_solver* s);
+
 /* Per-stage device timing (CUDA events on the launching stream).  Stages:
  * 0 h2d, 1 pyramid, 2 fast, 3 octree, 4 blur, 5 layout, 6 orient+describe,
  * 7 d2h.  orb_stage_times fills ms[8] (accumulated) and launches[8]. */

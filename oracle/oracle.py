@@ -67,6 +67,10 @@ def lib():
                                              C.c_int, C.c_void_p]
         L.orc_match_triangulate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.orc_lba_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_lba_reduced_system.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.POINTER(C.c_double)]
         L.orc_sort_nodes.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _lib = L
     return _lib
@@ -226,3 +230,32 @@ def match_triangulate(kf1, kf2, fv1, fv2, F12, ep, only_stereo=False, coarse=Fal
     n = lib().orc_match_triangulate(C.byref(kf1), C.byref(kf2), C.byref(fv1), C.byref(fv2), _ptr(F12), _ptr(ep),
                                     int(only_stereo), int(coarse), int(check_ori), _ptr(out), cap)
     return n, out[:n]
+
+
+# ---- local BA (views: orb_slam3_b200/views.py lba_graph_view / lba_stats, interface types)
+def lba_solve(g, max_iters=10, lambda_init=0.0, stop=None):
+    """optimize(max_iters) on the flat graph view g.  Returns dict(kf_pose, mp_pos, chi2, depth_pos, stats, trace)."""
+    from orb_slam3_b200.views import lba_stats
+    kf = np.zeros((g.n_kf, 7))
+    mp = np.zeros((g.n_mp, 3))
+    chi2 = np.zeros(g.n_edges)
+    dp = np.zeros(g.n_edges, np.uint8)
+    st = lba_stats()
+    trace = np.zeros((128, 4))
+    sp = _ptr(stop) if stop is not None else None
+    it = lib().orc_lba_solve(C.byref(g), sp, max_iters, lambda_init, _ptr(kf), _ptr(mp), _ptr(chi2), _ptr(dp),
+                             C.byref(st), _ptr(trace))
+    return dict(iterations=it, kf_pose=kf, mp_pos=mp, chi2=chi2, depth_pos=dp, stats=st.as_dict(),
+                trace=trace[:st.trials].copy())
+
+
+def lba_reduced_system(g, lam, lm_mask=None):
+    nf = int((np.ctypeslib.as_array(C.cast(g.kf_fixed, C.POINTER(C.c_uint8)), (g.n_kf,)) == 0).sum())
+    n = 6 * nf
+    S = np.zeros((n, n))
+    bs = np.zeros(n)
+    chi = C.c_double()
+    m = None if lm_mask is None else np.ascontiguousarray(lm_mask, np.uint8)
+    lib().orc_lba_reduced_system(C.byref(g), lam, _ptr(m) if m is not None else None, _ptr(S), _ptr(bs),
+                                 C.byref(chi))
+    return S, bs, chi.value

@@ -1,0 +1,564 @@
+// TEST INFRASTRUCTURE ONLY (see orc_common.h).  fp64 CPU restatement of the g2o
+// Levenberg-Marquardt loop that Optimizer::LocalBundleAdjustment runs
+// (src/Optimizer.cc:1410-1411 `optimizer.optimize(10)`), on the flat graph of
+// include/orb_b200.h (interface types only).
+//
+// Restates (paths relative to /root/reference):
+//   Thirdparty/g2o/g2o/core/sparse_optimizer.cpp:354-419   optimize()
+//   Thirdparty/g2o/g2o/core/optimization_algorithm_levenberg.cpp:61-194  solve(), lambda init, scale
+//   Thirdparty/g2o/g2o/core/block_solver.hpp:354-486 (Schur solve), :502-560 (buildSystem), :564-604
+//   Thirdparty/g2o/g2o/core/base_binary_edge.hpp:55-120     constructQuadraticForm
+//   Thirdparty/g2o/g2o/core/robust_kernel_impl.cpp:65-91    RobustKernelHuber (float dsqr)
+//   Thirdparty/g2o/g2o/types/se3quat.h:98-120, 217-285       SE3Quat map / * / exp / normalizeRotation
+//   Thirdparty/g2o/g2o/types/types_six_dof_expmap.cpp:190-197, 228-274  stereo edge
+//   Thirdparty/g2o/g2o/types/types_six_dof_expmap.h:73-76    VertexSE3Expmap::oplusImpl
+//   src/OptimizableTypes.cpp:139-160, include/OptimizableTypes.h:99-104   mono edge
+//   src/CameraModels/Pinhole.cpp:42-48, 71-81                project / projectJac (float parameters)
+//   src/Optimizer.cc:1275-1276, 1305-1364                    Huber deltas, information, edge set-up
+// The reduced system is solved with a skyline LDL^T on the dense S instead of
+// Eigen's SimplicialLDLT (un-vendored); same solution up to rounding.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+#include "../include/orb_b200.h"
+
+namespace {
+
+struct Quat { double x, y, z, w; };
+struct SE3 { Quat r; double t[3]; };
+
+inline void quat_normalize(Quat& q) {  // se3quat.h:280-285
+  if (q.w < 0) { q.x = -q.x; q.y = -q.y; q.z = -q.z; q.w = -q.w; }
+  const double n = std::sqrt(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+  q.x /= n; q.y /= n; q.z /= n; q.w /= n;
+}
+inline Quat quat_mul(const Quat& a, const Quat& b) {
+  return Quat{a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y, a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z,
+              a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x, a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z};
+}
+inline void quat_rot(const Quat& q, const double v[3], double out[3]) {  // Eigen _transformVector
+  double ux = q.y * v[2] - q.z * v[1], uy = q.z * v[0] - q.x * v[2], uz = q.x * v[1] - q.y * v[0];
+  ux += ux; uy += uy; uz += uz;
+  out[0] = v[0] + q.w * ux + (q.y * uz - q.z * uy);
+  out[1] = v[1] + q.w * uy + (q.z * ux - q.x * uz);
+  out[2] = v[2] + q.w * uz + (q.x * uy - q.y * ux);
+}
+inline void quat_to_R(const Quat& q, double R[9]) {  // Eigen toRotationMatrix
+  const double tx = 2 * q.x, ty = 2 * q.y, tz = 2 * q.z;
+  const double twx = tx * q.w, twy = ty * q.w, twz = tz * q.w;
+  const double txx = tx * q.x, txy = ty * q.x, txz = tz * q.x;
+  const double tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
+  R[0] = 1 - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
+  R[3] = txy + twz; R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+  R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1 - (txx + tyy);
+}
+inline Quat R_to_quat(const double R[9]) {  // Eigen quaternion from rotation matrix
+  Quat q;
+  double t = R[0] + R[4] + R[8];
+  if (t > 0) {
+    t = std::sqrt(t + 1.0);
+    q.w = 0.5 * t;
+    t = 0.5 / t;
+    q.x = (R[7] - R[5]) * t; q.y = (R[2] - R[6]) * t; q.z = (R[3] - R[1]) * t;
+  } else {
+    int i = 0;
+    if (R[4] > R[0]) i = 1;
+    if (R[8] > R[i * 4]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = std::sqrt(R[i * 4] - R[j * 4] - R[k * 4] + 1.0);
+    double v[3];
+    v[i] = 0.5 * t;
+    t = 0.5 / t;
+    q.w = (R[k * 3 + j] - R[j * 3 + k]) * t;
+    v[j] = (R[j * 3 + i] + R[i * 3 + j]) * t;
+    v[k] = (R[k * 3 + i] + R[i * 3 + k]) * t;
+    q.x = v[0]; q.y = v[1]; q.z = v[2];
+  }
+  return q;
+}
+inline void se3_map(const SE3& T, const double p[3], double out[3]) {
+  quat_rot(T.r, p, out);
+  out[0] += T.t[0]; out[1] += T.t[1]; out[2] += T.t[2];
+}
+// SE3Quat::exp(update) * T   (se3quat.h:223-257, :98-104; oplusImpl)
+inline SE3 se3_exp_mul(const double u[6], const SE3& T) {
+  const double w[3] = {u[0], u[1], u[2]}, ups[3] = {u[3], u[4], u[5]};
+  const double theta = std::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+  const double Om[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0};
+  double Om2[9];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      double s = 0;
+      for (int k = 0; k < 3; k++) s += Om[i * 3 + k] * Om[k * 3 + j];
+      Om2[i * 3 + j] = s;
+    }
+  double R[9], V[9];
+  if (theta < 0.00001) {
+    for (int i = 0; i < 9; i++) { R[i] = (i % 4 == 0 ? 1.0 : 0.0) + Om[i] + Om2[i]; V[i] = R[i]; }
+  } else {
+    const double a = std::sin(theta) / theta, b = (1 - std::cos(theta)) / (theta * theta);
+    const double c = (theta - std::sin(theta)) / std::pow(theta, 3);
+    for (int i = 0; i < 9; i++) {
+      const double I = (i % 4 == 0 ? 1.0 : 0.0);
+      R[i] = I + a * Om[i] + b * Om2[i];
+      V[i] = I + b * Om[i] + c * Om2[i];
+    }
+  }
+  SE3 E;
+  E.r = R_to_quat(R);
+  for (int i = 0; i < 3; i++) E.t[i] = V[i * 3] * ups[0] + V[i * 3 + 1] * ups[1] + V[i * 3 + 2] * ups[2];
+  quat_normalize(E.r);  // SE3Quat(q,t) ctor
+  SE3 out;
+  double rt[3];
+  quat_rot(E.r, T.t, rt);
+  for (int i = 0; i < 3; i++) out.t[i] = E.t[i] + rt[i];
+  out.r = quat_mul(E.r, T.r);
+  quat_normalize(out.r);
+  return out;
+}
+
+struct Huber {
+  double delta; float dsqr;
+  explicit Huber(float th) : delta(th), dsqr((float)((double)th * (double)th)) {}
+  // robust_kernel_impl.cpp:78-91: rho[0], rho[1]
+  inline void robustify(double e, double& rho0, double& rho1) const {
+    if (e <= dsqr) { rho0 = e; rho1 = 1.; }
+    else { const double s = std::sqrt(e); rho0 = 2 * s * delta - dsqr; rho1 = delta / s; }
+  }
+};
+
+struct Problem {
+  const lba_graph_view* g;
+  std::vector<SE3> pose;
+  std::vector<double> pt;
+  std::vector<int> free_idx;  // kf -> free pose index or -1
+  int nf = 0;
+  std::vector<double> err;    // per edge, 3 comps
+  Huber hm, hs;
+  // system
+  std::vector<double> Hpp, Hll, W, b;  // Hpp nf*36, Hll nmp*9, W nedges*18 (6x3), b (6nf+3nmp)
+  std::vector<double> x;
+  std::vector<std::vector<int>> lm_edges;
+
+  explicit Problem(const lba_graph_view* gv)
+      : g(gv), hm((float)std::sqrt(5.991)), hs((float)std::sqrt(7.815)) {  // Optimizer.cc:1275-1276
+    pose.resize(g->n_kf);
+    free_idx.assign(g->n_kf, -1);
+    for (int k = 0; k < g->n_kf; k++) {
+      const double* p = g->kf_pose + 7 * k;
+      pose[k].r = Quat{p[0], p[1], p[2], p[3]};
+      quat_normalize(pose[k].r);
+      pose[k].t[0] = p[4]; pose[k].t[1] = p[5]; pose[k].t[2] = p[6];
+      if (!g->kf_fixed[k]) free_idx[k] = nf++;
+    }
+    pt.assign(g->mp_pos, g->mp_pos + 3 * (size_t)g->n_mp);
+    err.assign(3 * (size_t)g->n_edges, 0.0);
+    lm_edges.resize(g->n_mp);
+    for (int e = 0; e < g->n_edges; e++) lm_edges[g->e_mp[e]].push_back(e);
+    Hpp.resize((size_t)nf * 36); Hll.resize((size_t)g->n_mp * 9); W.resize((size_t)g->n_edges * 18);
+    b.resize((size_t)6 * nf + 3 * (size_t)g->n_mp);
+    x.assign(b.size(), 0.0);
+  }
+
+  inline int dim(int e) const { return g->e_stereo[e] ? 3 : 2; }
+
+  // computeError of both edge types
+  void compute_errors() {
+    for (int e = 0; e < g->n_edges; e++) {
+      const int k = g->e_kf[e];
+      double Xc[3];
+      se3_map(pose[k], &pt[3 * (size_t)g->e_mp[e]], Xc);
+      const float* cam = g->kf_cam + 5 * k;
+      const double* obs = g->e_obs + 3 * (size_t)e;
+      double* r = &err[3 * (size_t)e];
+      if (g->e_stereo[e]) {
+        // types_six_dof_expmap.cpp:190-197: invz in float; fx.. are doubles set from floats
+        const double fx = cam[0], fy = cam[1], cx = cam[2], cy = cam[3];
+        const float bf = (float)(double)cam[4];
+        const float invz = 1.0f / (float)Xc[2];
+        const double u = Xc[0] * invz * fx + cx;
+        const double v = Xc[1] * invz * fy + cy;
+        r[0] = obs[0] - u; r[1] = obs[1] - v; r[2] = obs[2] - (u - bf * invz);
+      } else {
+        // Pinhole::project(Vector3d): float parameters promoted
+        r[0] = obs[0] - (cam[0] * Xc[0] / Xc[2] + cam[2]);
+        r[1] = obs[1] - (cam[1] * Xc[1] / Xc[2] + cam[3]);
+        r[2] = 0;
+      }
+    }
+  }
+  inline double chi2(int e) const {
+    const double s = g->e_inv_sigma2[e];
+    const double* r = &err[3 * (size_t)e];
+    double c = r[0] * (s * r[0]) + r[1] * (s * r[1]);
+    if (g->e_stereo[e]) c += r[2] * (s * r[2]);
+    return c;
+  }
+  double robust_chi2() const {  // sparse_optimizer.cpp:100-114
+    double chi = 0, r0, r1;
+    for (int e = 0; e < g->n_edges; e++) {
+      (g->e_stereo[e] ? hs : hm).robustify(chi2(e), r0, r1);
+      chi += r0;
+    }
+    return chi;
+  }
+
+  // linearizeOplus + constructQuadraticForm for every edge, copyB
+  void build_system() {
+    std::fill(Hpp.begin(), Hpp.end(), 0.0);
+    std::fill(Hll.begin(), Hll.end(), 0.0);
+    std::fill(b.begin(), b.end(), 0.0);
+    for (int e = 0; e < g->n_edges; e++) {
+      const int k = g->e_kf[e], l = g->e_mp[e], d = dim(e);
+      double Xc[3], R[9];
+      se3_map(pose[k], &pt[3 * (size_t)l], Xc);
+      quat_to_R(pose[k].r, R);
+      const float* cam = g->kf_cam + 5 * k;
+      const double x = Xc[0], y = Xc[1], z = Xc[2];
+      double A[9], B[18];  // d x 3, d x 6 row-major
+      if (g->e_stereo[e]) {
+        const double fx = cam[0], fy = cam[1], bf = cam[4];
+        const double z_2 = z * z;
+        for (int c = 0; c < 3; c++) {
+          A[0 * 3 + c] = -fx * R[0 * 3 + c] / z + fx * x * R[2 * 3 + c] / z_2;
+          A[1 * 3 + c] = -fy * R[1 * 3 + c] / z + fy * y * R[2 * 3 + c] / z_2;
+          A[2 * 3 + c] = A[0 * 3 + c] - bf * R[2 * 3 + c] / z_2;
+        }
+        B[0] = x * y / z_2 * fx; B[1] = -(1 + (x * x / z_2)) * fx; B[2] = y / z * fx;
+        B[3] = -1. / z * fx; B[4] = 0; B[5] = x / z_2 * fx;
+        B[6] = (1 + y * y / z_2) * fy; B[7] = -x * y / z_2 * fy; B[8] = -x / z * fy;
+        B[9] = 0; B[10] = -1. / z * fy; B[11] = y / z_2 * fy;
+        B[12] = B[0] - bf * y / z_2; B[13] = B[1] + bf * x / z_2; B[14] = B[2];
+        B[15] = B[3]; B[16] = 0; B[17] = B[5] - bf / z_2;
+      } else {
+        // -projectJac (Pinhole.cpp:71-81), times R / SE3deriv (OptimizableTypes.cpp:139-160)
+        const double J[6] = {-(cam[0] / z), -0., -(-cam[0] * x / (z * z)), -0., -(cam[1] / z), -(-cam[1] * y / (z * z))};
+        for (int r = 0; r < 2; r++)
+          for (int c = 0; c < 3; c++)
+            A[r * 3 + c] = J[r * 3] * R[c] + J[r * 3 + 1] * R[3 + c] + J[r * 3 + 2] * R[6 + c];
+        const double D[18] = {0, z, -y, 1, 0, 0, -z, 0, x, 0, 1, 0, y, -x, 0, 0, 0, 1};
+        for (int r = 0; r < 2; r++)
+          for (int c = 0; c < 6; c++)
+            B[r * 6 + c] = J[r * 3] * D[c] + J[r * 3 + 1] * D[6 + c] + J[r * 3 + 2] * D[12 + c];
+      }
+      double rho0, rho1;
+      (g->e_stereo[e] ? hs : hm).robustify(chi2(e), rho0, rho1);
+      const double s = g->e_inv_sigma2[e];
+      const double ws = rho1 * s;  // weightedOmega = rho[1] * information
+      const double* r = &err[3 * (size_t)e];
+      double omega_r[3];
+      for (int i = 0; i < d; i++) omega_r[i] = -(s * r[i]) * rho1;
+      // landmark (from) part
+      double* Hl = &Hll[9 * (size_t)l];
+      double* bl = &b[(size_t)6 * nf + 3 * (size_t)l];
+      for (int i = 0; i < 3; i++) {
+        for (int j = 0; j < 3; j++) {
+          double acc = 0;
+          for (int q = 0; q < d; q++) acc += A[q * 3 + i] * ws * A[q * 3 + j];
+          Hl[i * 3 + j] += acc;
+        }
+        double acc = 0;
+        for (int q = 0; q < d; q++) acc += A[q * 3 + i] * omega_r[q];
+        bl[i] += acc;
+      }
+      const int f = free_idx[k];
+      double* We = &W[18 * (size_t)e];
+      if (f >= 0) {
+        double* Hp = &Hpp[36 * (size_t)f];
+        double* bp = &b[6 * (size_t)f];
+        for (int i = 0; i < 6; i++) {
+          for (int j = 0; j < 6; j++) {
+            double acc = 0;
+            for (int q = 0; q < d; q++) acc += B[q * 6 + i] * ws * B[q * 6 + j];
+            Hp[i * 6 + j] += acc;
+          }
+          double acc = 0;
+          for (int q = 0; q < d; q++) acc += B[q * 6 + i] * omega_r[q];
+          bp[i] += acc;
+          for (int j = 0; j < 3; j++) {  // Hpl block (pose rows, landmark cols) = B^T wOmega A
+            double a2 = 0;
+            for (int q = 0; q < d; q++) a2 += B[q * 6 + i] * ws * A[q * 3 + j];
+            We[i * 3 + j] = a2;
+          }
+        }
+      } else {
+        for (int i = 0; i < 18; i++) We[i] = 0;
+      }
+    }
+  }
+};
+
+// Skyline LDL^T of a dense symmetric matrix (lower triangle, row-major n x n),
+// in place; returns false on a zero pivot (Eigen SimplicialLDLT reports failure
+// only then).  first[i] = first structurally non-zero column of row i.
+bool skyline_ldlt(std::vector<double>& A, int n, std::vector<int>& first, std::vector<double>& D) {
+  first.resize(n);
+  D.resize(n);
+  for (int i = 0; i < n; i++) {
+    int f = 0;
+    while (f < i && A[(size_t)i * n + f] == 0.0) f++;
+    first[i] = f;
+  }
+  for (int i = 0; i < n; i++) {
+    double* Li = &A[(size_t)i * n];
+    for (int j = first[i]; j < i; j++) {
+      const double* Lj = &A[(size_t)j * n];
+      double s = Li[j];
+      for (int k = std::max(first[i], first[j]); k < j; k++) s -= Li[k] * Lj[k];  // Li[k] still holds L*D
+      Li[j] = s;  // = L_ij * D_j
+    }
+    double d = Li[i];
+    for (int j = first[i]; j < i; j++) {
+      const double ld = Li[j];
+      const double l = ld / D[j];
+      d -= ld * l;
+      Li[j] = l;
+    }
+    if (d == 0.0) return false;
+    D[i] = d;
+  }
+  return true;
+}
+
+void skyline_solve(const std::vector<double>& L, const std::vector<int>& first, const std::vector<double>& D,
+                   int n, double* x /* in: rhs, out: solution */) {
+  for (int i = 0; i < n; i++) {
+    double s = x[i];
+    for (int k = first[i]; k < i; k++) s -= L[(size_t)i * n + k] * x[k];
+    x[i] = s;
+  }
+  for (int i = 0; i < n; i++) x[i] /= D[i];
+  for (int i = n - 1; i >= 0; i--) {
+    const double xi = x[i];
+    for (int k = first[i]; k < i; k++) x[k] -= L[(size_t)i * n + k] * xi;
+  }
+}
+
+inline bool inv3(const double* m, double* o) {  // Eigen 3x3 inverse (cofactors)
+  const double c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8], c02 = m[3] * m[7] - m[4] * m[6];
+  const double det = m[0] * c00 + m[1] * c01 + m[2] * c02;
+  const double id = 1.0 / det;
+  o[0] = c00 * id; o[1] = (m[2] * m[7] - m[1] * m[8]) * id; o[2] = (m[1] * m[5] - m[2] * m[4]) * id;
+  o[3] = c01 * id; o[4] = (m[0] * m[8] - m[2] * m[6]) * id; o[5] = (m[2] * m[3] - m[0] * m[5]) * id;
+  o[6] = c02 * id; o[7] = (m[1] * m[6] - m[0] * m[7]) * id; o[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+  return true;
+}
+
+// Schur complement for damping lambda: S (n x n dense, n = 6 nf), bs, Dinv
+void schur(const Problem& P, double lambda, std::vector<double>& S, std::vector<double>& bs,
+           std::vector<double>& Dinv, const uint8_t* lm_mask) {
+  const int nf = P.nf, n = 6 * nf;
+  S.assign((size_t)n * n, 0.0);
+  bs.assign(P.b.begin(), P.b.begin() + n);
+  for (int f = 0; f < nf; f++)
+    for (int i = 0; i < 6; i++)
+      for (int j = 0; j < 6; j++)
+        S[(size_t)(6 * f + i) * n + 6 * f + j] = P.Hpp[36 * (size_t)f + i * 6 + j] + (i == j ? lambda : 0.0);
+  Dinv.assign((size_t)P.g->n_mp * 9, 0.0);
+  for (int l = 0; l < P.g->n_mp; l++) {
+    if (lm_mask && !lm_mask[l]) continue;
+    double Dm[9];
+    for (int i = 0; i < 9; i++) Dm[i] = P.Hll[9 * (size_t)l + i] + ((i % 4 == 0) ? lambda : 0.0);
+    double* Di = &Dinv[9 * (size_t)l];
+    inv3(Dm, Di);
+    const double* bl = &P.b[(size_t)n + 3 * (size_t)l];
+    double db[3];
+    for (int i = 0; i < 3; i++) db[i] = Di[i * 3] * bl[0] + Di[i * 3 + 1] * bl[1] + Di[i * 3 + 2] * bl[2];
+    const std::vector<int>& es = P.lm_edges[l];
+    for (int e1 : es) {
+      const int f1 = P.free_idx[P.g->e_kf[e1]];
+      if (f1 < 0) continue;
+      const double* W1 = &P.W[18 * (size_t)e1];
+      double Y[18];
+      for (int i = 0; i < 6; i++)
+        for (int j = 0; j < 3; j++)
+          Y[i * 3 + j] = W1[i * 3] * Di[j] + W1[i * 3 + 1] * Di[3 + j] + W1[i * 3 + 2] * Di[6 + j];
+      for (int i = 0; i < 6; i++) bs[6 * f1 + i] -= W1[i * 3] * db[0] + W1[i * 3 + 1] * db[1] + W1[i * 3 + 2] * db[2];
+      for (int e2 : es) {
+        const int f2 = P.free_idx[P.g->e_kf[e2]];
+        if (f2 < 0) continue;
+        const double* W2 = &P.W[18 * (size_t)e2];
+        for (int i = 0; i < 6; i++)
+          for (int j = 0; j < 6; j++)
+            S[(size_t)(6 * f1 + i) * n + 6 * f2 + j] -= Y[i * 3] * W2[j * 3] + Y[i * 3 + 1] * W2[j * 3 + 1] + Y[i * 3 + 2] * W2[j * 3 + 2];
+      }
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+// Full optimize(max_iters).  Outputs as lba_solve of include/orb_b200.h.
+int orc_lba_solve(const lba_graph_view* g, const volatile uint8_t* stop, int max_iters, double lambda_init,
+                  double* kf_pose_out, double* mp_pos_out, double* chi2_out, uint8_t* depth_pos_out,
+                  lba_stats* stats, double* trace /* per trial: lambda, tempChi, rho, accepted; cap 4*128 */) {
+  auto t_begin = std::chrono::steady_clock::now();
+  Problem P(g);
+  const int nf = P.nf, n = 6 * nf;
+  const size_t nvec = P.b.size();
+  double lambda = -1, ni = 2;
+  int nBad = 0, trials = 0, iters = 0, stopped = 0;
+  double chi_first = 0, currentChi = 0;
+  std::vector<double> S, bs, Dinv, D;
+  std::vector<int> first;
+  std::vector<SE3> pose_bak;
+  std::vector<double> pt_bak;
+  auto terminate = [&]() { return stop && *stop; };
+  for (int it = 0; it < max_iters && !terminate(); it++) {
+    P.compute_errors();
+    currentChi = P.robust_chi2();
+    double tempChi = currentChi;
+    const double iniChi = currentChi;
+    if (it == 0) chi_first = currentChi;
+    P.build_system();
+    if (it == 0) {
+      if (lambda_init > 0) lambda = lambda_init;
+      else {  // computeLambdaInit: tau * max diagonal over all free vertices
+        double mx = 0;
+        for (int f = 0; f < nf; f++)
+          for (int j = 0; j < 6; j++) mx = std::max(std::fabs(P.Hpp[36 * (size_t)f + j * 7]), mx);
+        for (int l = 0; l < g->n_mp; l++)
+          for (int j = 0; j < 3; j++) mx = std::max(std::fabs(P.Hll[9 * (size_t)l + j * 4]), mx);
+        lambda = 1e-5 * mx;
+      }
+      ni = 2; nBad = 0;
+    }
+    double rho = 0;
+    int qmax = 0;
+    do {
+      pose_bak = P.pose; pt_bak = P.pt;  // push
+      schur(P, lambda, S, bs, Dinv, nullptr);
+      bool ok2 = skyline_ldlt(S, n, first, D);
+      if (ok2) {
+        for (int i = 0; i < n; i++) P.x[i] = bs[i];
+        skyline_solve(S, first, D, n, P.x.data());
+        for (int l = 0; l < g->n_mp; l++) {  // xl = Dinv (bl - W^T xp)
+          double c[3] = {P.b[(size_t)n + 3 * (size_t)l], P.b[(size_t)n + 3 * (size_t)l + 1], P.b[(size_t)n + 3 * (size_t)l + 2]};
+          for (int e : P.lm_edges[l]) {
+            const int f = P.free_idx[g->e_kf[e]];
+            if (f < 0) continue;
+            const double* We = &P.W[18 * (size_t)e];
+            for (int j = 0; j < 3; j++)
+              for (int i = 0; i < 6; i++) c[j] -= We[i * 3 + j] * P.x[6 * f + i];
+          }
+          const double* Di = &Dinv[9 * (size_t)l];
+          for (int i = 0; i < 3; i++) P.x[(size_t)n + 3 * (size_t)l + i] = Di[i * 3] * c[0] + Di[i * 3 + 1] * c[1] + Di[i * 3 + 2] * c[2];
+        }
+      }
+      // update (oplus) -- g2o updates even when the solve failed; x then holds stale values
+      for (int k = 0; k < g->n_kf; k++)
+        if (P.free_idx[k] >= 0) P.pose[k] = se3_exp_mul(&P.x[6 * (size_t)P.free_idx[k]], P.pose[k]);
+      for (size_t i = 0; i < 3 * (size_t)g->n_mp; i++) P.pt[i] += P.x[(size_t)n + i];
+      P.compute_errors();
+      tempChi = P.robust_chi2();
+      if (!ok2) tempChi = std::numeric_limits<double>::max();
+      rho = currentChi - tempChi;
+      double scale = 0;
+      for (size_t j = 0; j < nvec; j++) scale += P.x[j] * (lambda * P.x[j] + P.b[j]);
+      scale += 1e-3;
+      rho /= scale;
+      const bool accept = rho > 0 && std::isfinite(tempChi);
+      if (trace && trials < 128) {
+        trace[4 * trials] = lambda; trace[4 * trials + 1] = tempChi; trace[4 * trials + 2] = rho;
+        trace[4 * trials + 3] = accept ? 1 : 0;
+      }
+      if (accept) {
+        double alpha = 1. - std::pow((2 * rho - 1), 3);
+        alpha = std::min(alpha, 2. / 3.);
+        const double scaleFactor = std::max(1. / 3., alpha);
+        lambda *= scaleFactor;
+        ni = 2;
+        currentChi = tempChi;
+      } else {
+        lambda *= ni;
+        ni *= 2;
+        P.pose = pose_bak; P.pt = pt_bak;  // pop
+      }
+      qmax++;
+      trials++;
+    } while (rho < 0 && qmax < 10 && !terminate());
+    iters++;
+    if (qmax == 10 || rho == 0) break;  // Terminate
+    if ((iniChi - currentChi) * 1e3 < iniChi) nBad++;
+    else nBad = 0;
+    if (nBad >= 3) break;
+  }
+  if (terminate()) stopped = 1;
+  for (int k = 0; k < g->n_kf; k++) {
+    double* o = kf_pose_out + 7 * k;
+    o[0] = P.pose[k].r.x; o[1] = P.pose[k].r.y; o[2] = P.pose[k].r.z; o[3] = P.pose[k].r.w;
+    o[4] = P.pose[k].t[0]; o[5] = P.pose[k].t[1]; o[6] = P.pose[k].t[2];
+  }
+  memcpy(mp_pos_out, P.pt.data(), sizeof(double) * 3 * (size_t)g->n_mp);
+  for (int e = 0; e < g->n_edges; e++) {
+    if (chi2_out) chi2_out[e] = P.chi2(e);  // errors of the last evaluated trial
+    if (depth_pos_out) {
+      double Xc[3];
+      se3_map(P.pose[g->e_kf[e]], &P.pt[3 * (size_t)g->e_mp[e]], Xc);
+      depth_pos_out[e] = Xc[2] > 0.0;
+    }
+  }
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    stats->iterations = iters; stats->trials = trials; stats->stopped = stopped;
+    stats->chi2_initial = chi_first; stats->chi2_final = currentChi; stats->lambda_final = lambda;
+    stats->n_free_kf = nf;
+    stats->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+  }
+  return iters;
+}
+
+// One linearisation at the input estimates: robust chi2, and for damping
+// `lambda` the reduced system restricted to landmarks with lm_mask != 0 (NULL =
+// all).  H_pp/b_p of edges whose landmark is masked out are excluded too, so
+// shard results add up to the full system.  S is 6nf x 6nf row-major.
+int orc_lba_reduced_system(const lba_graph_view* g, double lambda, const uint8_t* lm_mask, double* S_out,
+                           double* bs_out, double* chi2_robust) {
+  Problem P(g);
+  P.compute_errors();
+  if (chi2_robust) {
+    double chi = 0, r0, r1;
+    for (int e = 0; e < g->n_edges; e++) {
+      if (lm_mask && !lm_mask[g->e_mp[e]]) continue;
+      (g->e_stereo[e] ? P.hs : P.hm).robustify(P.chi2(e), r0, r1);
+      chi += r0;
+    }
+    *chi2_robust = chi;
+  }
+  if (lm_mask) {
+    // rebuild with masked-out edges removed: emulate by zero weight
+    std::vector<float> w(g->e_inv_sigma2, g->e_inv_sigma2 + g->n_edges);
+    lba_graph_view g2 = *g;
+    for (int e = 0; e < g->n_edges; e++)
+      if (!lm_mask[g->e_mp[e]]) w[e] = 0.f;
+    g2.e_inv_sigma2 = w.data();
+    Problem Q(&g2);
+    Q.compute_errors();
+    Q.build_system();
+    std::vector<double> S, bs, Dinv;
+    schur(Q, lambda, S, bs, Dinv, lm_mask);
+    const int n = 6 * Q.nf;
+    // lambda on the pose diagonal is added once per call: remove it so shards sum, caller adds it back
+    for (int i = 0; i < n; i++) S[(size_t)i * n + i] -= lambda;
+    memcpy(S_out, S.data(), sizeof(double) * (size_t)n * n);
+    memcpy(bs_out, bs.data(), sizeof(double) * n);
+    return n;
+  }
+  P.build_system();
+  std::vector<double> S, bs, Dinv;
+  schur(P, lambda, S, bs, Dinv, nullptr);
+  const int n = 6 * P.nf;
+  for (int i = 0; i < n; i++) S[(size_t)i * n + i] -= lambda;
+  memcpy(S_out, S.data(), sizeof(double) * (size_t)n * n);
+  memcpy(bs_out, bs.data(), sizeof(double) * n);
+  return n;
+}
+
+}  // extern "C"

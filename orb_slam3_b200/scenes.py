@@ -117,3 +117,132 @@ def triangulation_scene(kps1, desc1, kps2, desc2, width, height, seed, n_nodes=1
     F12 = (np.linalg.inv(K).T @ tx @ R @ np.linalg.inv(K)).astype(np.float32)
     ep = np.array([FX * t[0] / t[2] + cx, FY * t[1] / t[2] + cy], np.float32)
     return k1, k2, make_featvec_view(node1), make_featvec_view(node2), F12.reshape(9), ep
+
+
+# ---------------------------------------------------------------- local BA graphs
+def _quat_from_yaw_pitch(yaw, pitch):
+    cy, sy, cp, sp = np.cos(yaw / 2), np.sin(yaw / 2), np.cos(pitch / 2), np.sin(pitch / 2)
+    # R = Ry(yaw) * Rx(pitch)
+    return np.array([cy * sp, sy * cp, -sy * sp, cy * cp])
+
+
+def _quat_mul(a, b):
+    ax, ay, az, aw = a
+    bx, by, bz, bw = b
+    return np.array([aw * bx + ax * bw + ay * bz - az * by, aw * by + ay * bw + az * bx - ax * bz,
+                     aw * bz + az * bw + ax * by - ay * bx, aw * bw - ax * bx - ay * by - az * bz])
+
+
+def _quat_rot(q, v):
+    u = np.cross(q[:3], v)
+    u = u + u
+    return v + q[3] * u + np.cross(q[:3], u)
+
+
+def lba_graph(n_kf_opt, n_mp, seed=0, fixed_frac=0.1, stereo_frac=0.8, outlier_frac=0.02,
+              width=1280, height=720, fx=700.0, bf=386.0):
+    """Synthetic LocalBundleAdjustment graph: K optimisable
+    KFs on a smooth trajectory (1 m spacing, yaw drift) + ceil(K/10) fixed ones,
+    landmarks seen by 3..10 KFs of a sliding window, 80% stereo edges, octave noise
+    model, 2% gross outliers, perturbed initial estimates.  Returns (graph dict, truth)."""
+    rng = np.random.default_rng(seed)
+    n_fixed = int(np.ceil(n_kf_opt * fixed_frac))
+    K = n_kf_opt + n_fixed
+    cx, cy = width / 2.0, height / 2.0
+    # world-from-camera poses along +z with yaw drift; Tcw = inverse
+    Twc_q, Twc_t = [], []
+    for k in range(K):
+        yaw = 0.01 * k + 0.05 * np.sin(0.3 * k)
+        Twc_q.append(_quat_from_yaw_pitch(yaw, 0.01 * np.cos(0.2 * k)))
+        Twc_t.append(np.array([0.3 * np.sin(0.1 * k), 0.02 * k % 0.3, 1.0 * k]))
+    Tcw = np.zeros((K, 7))
+    for k in range(K):
+        qi = Twc_q[k] * np.array([-1, -1, -1, 1])
+        Tcw[k, :4] = qi
+        Tcw[k, 4:] = -_quat_rot(qi, Twc_t[k])
+    # fixed KFs are the oldest ones (they see local points but are not local KFs)
+    fixed = np.zeros(K, np.uint8)
+    fixed[:n_fixed] = 1
+    e_kf, e_mp, e_st, e_obs, e_is2 = [], [], [], [], []
+    pts = np.zeros((n_mp, 3))
+    inv_sigma2 = (1.0 / (scale_factors() ** 2)).astype(np.float32)
+    l = 0
+    attempts = 0
+    while l < n_mp and attempts < 50 * n_mp:
+        attempts += 1
+        k0 = int(rng.integers(0, K))
+        depth = rng.uniform(4, 40)
+        u, v = rng.uniform(40, width - 40), rng.uniform(40, height - 40)
+        Xc = np.array([(u - cx) / fx * depth, (v - cy) / fx * depth, depth])
+        Xw = _quat_rot(Twc_q[k0], Xc) + Twc_t[k0]
+        m = int(rng.integers(3, 11))
+        obs = []
+        for k in range(max(0, k0 - 7), min(K, k0 + 8)):
+            Xk = _quat_rot(Tcw[k, :4], Xw) + Tcw[k, 4:]
+            if Xk[2] < 1.0:
+                continue
+            uu, vv = fx * Xk[0] / Xk[2] + cx, fx * Xk[1] / Xk[2] + cy
+            if 0 <= uu < width and 0 <= vv < height:
+                obs.append((k, uu, vv, Xk[2]))
+        if len(obs) < 3 or all(fixed[o[0]] for o in obs):
+            continue
+        if len(obs) > m:
+            sel = sorted(rng.choice(len(obs), m, replace=False))
+            obs = [obs[i] for i in sel]
+        pts[l] = Xw
+        for (k, uu, vv, zz) in obs:
+            octv = int(rng.integers(0, 8))
+            sig = 1.2 ** octv
+            nu, nv, nr = rng.normal(0, 1, 3) * sig
+            if rng.random() < outlier_frac:
+                nu += rng.choice([-50, 50])
+            st = rng.random() < stereo_frac
+            e_kf.append(k); e_mp.append(l); e_st.append(1 if st else 0)
+            e_obs.append((np.float32(uu + nu), np.float32(vv + nv), np.float32(uu - bf / zz + nr) if st else -1.0))
+            e_is2.append(inv_sigma2[octv])
+        l += 1
+    n_mp = l
+    pts = pts[:n_mp]
+    truth = dict(kf_pose=Tcw.copy(), mp_pos=pts.copy())
+    # initial perturbation: poses 2 cm / 0.5 deg (free KFs only), points 5 cm
+    pose0 = Tcw.copy()
+    for k in range(K):
+        if fixed[k]:
+            continue
+        w = rng.normal(0, np.deg2rad(0.5) / np.sqrt(3), 3)
+        th = np.linalg.norm(w)
+        dq = np.concatenate([np.sin(th / 2) * w / max(th, 1e-12), [np.cos(th / 2)]])
+        pose0[k, :4] = _quat_mul(dq, Tcw[k, :4])
+        pose0[k, 4:] = _quat_rot(dq, Tcw[k, 4:]) + rng.normal(0, 0.02 / np.sqrt(3), 3)
+    # Sophus stores float poses; LocalBundleAdjustment casts them to double (:1216-1217)
+    pose0 = pose0.astype(np.float32).astype(np.float64)
+    pts0 = (pts + rng.normal(0, 0.05 / np.sqrt(3), pts.shape)).astype(np.float32).astype(np.float64)
+    cam = np.tile(np.array([fx, fx, cx, cy, bf], np.float32), (K, 1))
+    g = dict(kf_pose=pose0, kf_fixed=fixed, kf_cam=cam, mp_pos=pts0, e_kf=np.array(e_kf, np.int32),
+             e_mp=np.array(e_mp, np.int32), e_stereo=np.array(e_st, np.uint8),
+             e_obs=np.array(e_obs, np.float64), e_inv_sigma2=np.array(e_is2, np.float32))
+    return g, truth
+
+
+def lba_view(g):
+    from .views import make_lba_graph_view
+    return make_lba_graph_view(**g)
+
+
+def shard_graph(g, rank, world):
+    """Landmark shard of a graph for rank `rank` of `world`: landmarks
+    l with l % world == rank, with all their edges; keyframes replicated.  Returns
+    (sub-graph dict, landmark ids, edge ids)."""
+    n_mp = len(g["mp_pos"])
+    lm = np.arange(rank, n_mp, world)
+    new_id = -np.ones(n_mp, np.int64)
+    new_id[lm] = np.arange(len(lm))
+    ed = np.nonzero(new_id[g["e_mp"]] >= 0)[0]
+    sub = dict(g)
+    sub["mp_pos"] = g["mp_pos"][lm]
+    sub["e_kf"] = g["e_kf"][ed]
+    sub["e_mp"] = new_id[g["e_mp"][ed]].astype(np.int32)
+    sub["e_stereo"] = g["e_stereo"][ed]
+    sub["e_obs"] = g["e_obs"][ed]
+    sub["e_inv_sigma2"] = g["e_inv_sigma2"][ed]
+    return sub, lm, ed

@@ -123,3 +123,34 @@ def make_featvec_view(node_of_feature):
     v.node_ids, v.ptr, v.idx = _p(a["node_ids"]), _p(a["ptr"]), _p(a["idx"])
     v._keep = a
     return v
+
+
+class lba_graph_view(C.Structure):
+    _fields_ = [("n_kf", _i), ("kf_pose", _vp), ("kf_fixed", _vp), ("kf_cam", _vp),
+                ("n_mp", _i), ("mp_pos", _vp),
+                ("n_edges", _i), ("e_kf", _vp), ("e_mp", _vp), ("e_stereo", _vp), ("e_obs", _vp),
+                ("e_inv_sigma2", _vp)]
+
+
+class lba_stats(C.Structure):
+    _fields_ = [("iterations", _i), ("trials", _i), ("stopped", _i),
+                ("chi2_initial", C.c_double), ("chi2_final", C.c_double), ("lambda_final", C.c_double),
+                ("ms_total", C.c_double), ("ms_linearize", C.c_double), ("ms_schur", C.c_double),
+                ("ms_solve", C.c_double), ("ms_update", C.c_double),
+                ("n_free_kf", _i), ("n_pairs", _i), ("schur_flops", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def make_lba_graph_view(kf_pose, kf_fixed, kf_cam, mp_pos, e_kf, e_mp, e_stereo, e_obs, e_inv_sigma2):
+    a = dict(kf_pose=_arr(kf_pose, np.float64), kf_fixed=_arr(kf_fixed, np.uint8), kf_cam=_arr(kf_cam, np.float32),
+             mp_pos=_arr(mp_pos, np.float64), e_kf=_arr(e_kf, np.int32), e_mp=_arr(e_mp, np.int32),
+             e_stereo=_arr(e_stereo, np.uint8), e_obs=_arr(e_obs, np.float64),
+             e_inv_sigma2=_arr(e_inv_sigma2, np.float32))
+    v = lba_graph_view()
+    v.n_kf, v.n_mp, v.n_edges = len(a["kf_fixed"]), len(a["mp_pos"]), len(a["e_kf"])
+    for k, arr in a.items():
+        setattr(v, k, _p(arr))
+    v._keep = a
+    return v
