@@ -58,6 +58,12 @@ SIGNATURES = {
     "match_synchronize": (_i, [_vp]),
     "match_kernel_launches": (C.c_longlong, [_vp]),
     "match_last_ms": (C.c_double, [_vp]),
+    "lba_create": (_i, [_i, C.POINTER(_vp)]),
+    "lba_destroy": (None, [_vp]),
+    "lba_nccl_unique_id": (_i, [_vp]),
+    "lba_comm_init": (_i, [_vp, _i, _i, _vp]),
+    "lba_solve": (_i, [_vp, _vp, _vp, _i, C.c_double, _vp, _vp, _vp, _vp, _vp]),
+    "lba_kernel_launches": (C.c_longlong, [_vp]),
     "orb_set_profiling": (_i, [_vp, _i]),
     "orb_stage_times": (_i, [_vp, _vp, _vp, _i]),
     "orb_stage_name": (C.c_char_p, [_i]),

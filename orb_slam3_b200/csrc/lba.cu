@@ -1,0 +1,1103 @@
+// Local bundle adjustment LM engine for B200 (sm_100a) behind include/orb_b200.h
+// (lba_solve): the g2o loop that Optimizer::LocalBundleAdjustment runs
+// (reference src/Optimizer.cc:1410-1411 -> Thirdparty/g2o optimization_algorithm_
+// levenberg.cpp:61-169, block_solver.hpp:354-604), all in fp64.
+//
+// Data layout (HBM, SoA, fp64): poses K x 7 (quaternion xyzw + t), points L x 3,
+// edges sorted by landmark (CSR lm_ptr) so one thread owns a landmark and its
+// H_ll / b_l sums are deterministic; a second CSR (by free pose) and a pair list
+// (pose i1 <= i2 -> the landmarks they share) are built once per solve on the
+// host -- the analogue of g2o's buildStructure (block_solver.hpp:143-295).
+//
+// Kernels per LM trial:
+//   lin_kernel          residuals, Huber weights, Jacobians, H_ll, b_l, W (6x3 per edge)
+//   pose_reduce_kernel  H_pp, b_p per free pose (fixed-order tree sum)
+//   lm_prepare_kernel   (H_ll + lambda I)^-1, D^-1 b_l, Y = W D^-1
+//   schur_pairs_kernel  S_{i1 i2} = [H_pp] - sum_l Y_{i1 l} W_{i2 l}^T : the dense contraction,
+//                       on the tensor cores as fp64 DMMA (mma.sync.m8n8k4.f64), one CTA per pose pair
+//   bschur_kernel       b_s = b_p - sum W D^-1 b_l          (stored as an extra row of S)
+//   [ncclAllReduce of (S | b_s) when landmarks are sharded over GPUs]
+//   ldlt_kernel         blocked right-looking LDL^T of S (+rhs row), all SMs, own grid barrier
+//   backsub_kernel      L^T x_p = z
+//   lm_update_kernel    x_l = D^-1 (b_l - W^T x_p), state backup, oplus (SE3 exp), scale terms
+//   err_kernel          robust chi2 of the trial state
+// The LM control law (lambda, rho, accept/reject, stop rules) runs on the host
+// between trials, reading three doubles back per trial; *stop is polled there.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <float.h>
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/orb_b200.h"
+#include "orb_engine.h"
+
+namespace orbb200 {
+
+#define CUDA_TRYL(expr)                                                                \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      set_last_error(std::string(#expr) + ": " + cudaGetErrorString(_e));              \
+      return ORB_E_CUDA;                                                               \
+    }                                                                                  \
+  } while (0)
+
+// ------------------------------------------------------------ device helpers
+struct DQuat { double x, y, z, w; };
+
+__device__ __forceinline__ void q_normalize(DQuat& q) {  // se3quat.h:280-285
+  if (q.w < 0) { q.x = -q.x; q.y = -q.y; q.z = -q.z; q.w = -q.w; }
+  const double n = sqrt(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+  q.x /= n; q.y /= n; q.z /= n; q.w /= n;
+}
+__device__ __forceinline__ DQuat q_mul(const DQuat& a, const DQuat& b) {
+  DQuat r;
+  r.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
+  r.y = a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z;
+  r.z = a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x;
+  r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
+  return r;
+}
+__device__ __forceinline__ void q_rot(const DQuat& q, const double* v, double* o) {
+  double ux = q.y * v[2] - q.z * v[1], uy = q.z * v[0] - q.x * v[2], uz = q.x * v[1] - q.y * v[0];
+  ux += ux; uy += uy; uz += uz;
+  o[0] = v[0] + q.w * ux + (q.y * uz - q.z * uy);
+  o[1] = v[1] + q.w * uy + (q.z * ux - q.x * uz);
+  o[2] = v[2] + q.w * uz + (q.x * uy - q.y * ux);
+}
+__device__ __forceinline__ void q_to_R(const DQuat& q, double* R) {
+  const double tx = 2 * q.x, ty = 2 * q.y, tz = 2 * q.z;
+  const double twx = tx * q.w, twy = ty * q.w, twz = tz * q.w;
+  const double txx = tx * q.x, txy = ty * q.x, txz = tz * q.x;
+  const double tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
+  R[0] = 1 - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
+  R[3] = txy + twz; R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+  R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1 - (txx + tyy);
+}
+__device__ __forceinline__ DQuat R_to_q(const double* R) {
+  DQuat q;
+  double t = R[0] + R[4] + R[8];
+  if (t > 0) {
+    t = sqrt(t + 1.0);
+    q.w = 0.5 * t;
+    t = 0.5 / t;
+    q.x = (R[7] - R[5]) * t; q.y = (R[2] - R[6]) * t; q.z = (R[3] - R[1]) * t;
+  } else {
+    int i = 0;
+    if (R[4] > R[0]) i = 1;
+    if (R[8] > R[i * 4]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = sqrt(R[i * 4] - R[j * 4] - R[k * 4] + 1.0);
+    double v[3];
+    v[i] = 0.5 * t;
+    t = 0.5 / t;
+    q.w = (R[k * 3 + j] - R[j * 3 + k]) * t;
+    v[j] = (R[j * 3 + i] + R[i * 3 + j]) * t;
+    v[k] = (R[k * 3 + i] + R[i * 3 + k]) * t;
+    q.x = v[0]; q.y = v[1]; q.z = v[2];
+  }
+  return q;
+}
+
+struct HuberD { double delta, dsqr; };
+__device__ __forceinline__ void robustify(const HuberD& h, double e, double& rho0, double& rho1) {
+  if (e <= h.dsqr) { rho0 = e; rho1 = 1.; }
+  else { const double s = sqrt(e); rho0 = 2 * s * h.delta - h.dsqr; rho1 = h.delta / s; }
+}
+
+struct LbaDev {
+  int n_kf, n_free, n_mp, n_edges, n;  // n = 6*n_free
+  // graph (edges sorted by landmark)
+  const int* lm_ptr; const int* e_kf; const int* e_free; const uint8_t* e_stereo;
+  const double* e_obs; const float* e_is2; const float* kf_cam; const int* free_kf;
+  const int* pose_ptr; const int* pose_edges;
+  const int* pair_i1; const int* pair_i2; const int* pair_ptr; const int* pair_ea; const int* pair_eb;
+  int n_pairs;
+  // state
+  double* pose; double* pts; double* pose_bak; double* pts_bak;
+  // system
+  double *Hll, *bl, *W, *Y, *Hpp_e, *bp_e, *Hpp, *bp, *Dinv, *db, *S, *x, *chi_lm, *chi2_e, *scale_part;
+  double* scalars;  // [0] chi, [1] scale, [2] maxdiag, [3] pivot_fail
+  HuberD hm, hs;
+};
+
+// residual of one edge; returns chi2 (r^T Omega r)
+__device__ __forceinline__ double edge_residual(const LbaDev& D, int e, const double* Xc, double* r) {
+  const float* cam = D.kf_cam + 5 * D.e_kf[e];
+  const double* obs = D.e_obs + 3 * (size_t)e;
+  const double s = (double)D.e_is2[e];
+  if (D.e_stereo[e]) {
+    // types_six_dof_expmap.cpp:190-197: invz is a float
+    const double fx = cam[0], fy = cam[1], cx = cam[2], cy = cam[3];
+    const float bf = cam[4];
+    const float invz = __fdiv_rn(1.0f, (float)Xc[2]);
+    const double u = Xc[0] * (double)invz * fx + cx;
+    const double v = Xc[1] * (double)invz * fy + cy;
+    r[0] = obs[0] - u; r[1] = obs[1] - v; r[2] = obs[2] - (u - (double)__fmul_rn(bf, invz));
+    return r[0] * (s * r[0]) + r[1] * (s * r[1]) + r[2] * (s * r[2]);
+  }
+  r[0] = obs[0] - ((double)cam[0] * Xc[0] / Xc[2] + (double)cam[2]);
+  r[1] = obs[1] - ((double)cam[1] * Xc[1] / Xc[2] + (double)cam[3]);
+  r[2] = 0;
+  return r[0] * (s * r[0]) + r[1] * (s * r[1]);
+}
+
+// One thread per landmark: linearise all its edges (base_binary_edge.hpp:55-120).
+template <bool LINEARIZE>
+__global__ void __launch_bounds__(128) lin_kernel(LbaDev D) {
+  const int l = blockIdx.x * 128 + threadIdx.x;
+  if (l >= D.n_mp) return;
+  const double X[3] = {D.pts[3 * (size_t)l], D.pts[3 * (size_t)l + 1], D.pts[3 * (size_t)l + 2]};
+  double Hl[6] = {0, 0, 0, 0, 0, 0}, bl[3] = {0, 0, 0}, chi = 0;
+  for (int e = D.lm_ptr[l]; e < D.lm_ptr[l + 1]; e++) {
+    const int k = D.e_kf[e];
+    const double* P = D.pose + 7 * (size_t)k;
+    DQuat q = {P[0], P[1], P[2], P[3]};
+    double Xc[3], r[3];
+    q_rot(q, X, Xc);
+    Xc[0] += P[4]; Xc[1] += P[5]; Xc[2] += P[6];
+    const double e2 = edge_residual(D, e, Xc, r);
+    D.chi2_e[e] = e2;
+    double rho0, rho1;
+    robustify(D.e_stereo[e] ? D.hs : D.hm, e2, rho0, rho1);
+    chi += rho0;
+    if (!LINEARIZE) continue;
+    const int d = D.e_stereo[e] ? 3 : 2;
+    const float* cam = D.kf_cam + 5 * k;
+    double R[9], A[9], B[18];
+    q_to_R(q, R);
+    const double x = Xc[0], y = Xc[1], z = Xc[2];
+    if (d == 3) {  // types_six_dof_expmap.cpp:228-274
+      const double fx = cam[0], fy = cam[1], bf = cam[4];
+      const double z_2 = z * z;
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        A[c] = -fx * R[c] / z + fx * x * R[6 + c] / z_2;
+        A[3 + c] = -fy * R[3 + c] / z + fy * y * R[6 + c] / z_2;
+        A[6 + c] = A[c] - bf * R[6 + c] / z_2;
+      }
+      B[0] = x * y / z_2 * fx; B[1] = -(1 + (x * x / z_2)) * fx; B[2] = y / z * fx;
+      B[3] = -1. / z * fx; B[4] = 0; B[5] = x / z_2 * fx;
+      B[6] = (1 + y * y / z_2) * fy; B[7] = -x * y / z_2 * fy; B[8] = -x / z * fy;
+      B[9] = 0; B[10] = -1. / z * fy; B[11] = y / z_2 * fy;
+      B[12] = B[0] - bf * y / z_2; B[13] = B[1] + bf * x / z_2; B[14] = B[2];
+      B[15] = B[3]; B[16] = 0; B[17] = B[5] - bf / z_2;
+    } else {  // OptimizableTypes.cpp:139-160 with Pinhole::projectJac
+      const double fx = cam[0], fy = cam[1];
+      const double J0 = -(fx / z), J2 = fx * x / (z * z), J4 = -(fy / z), J5 = fy * y / (z * z);
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        A[c] = J0 * R[c] + J2 * R[6 + c];
+        A[3 + c] = J4 * R[3 + c] + J5 * R[6 + c];
+        A[6 + c] = 0;
+      }
+      // SE3deriv rows: (0,z,-y,1,0,0) (-z,0,x,0,1,0) (y,-x,0,0,0,1)
+      B[0] = J2 * y;          B[1] = J0 * z - J2 * x; B[2] = -J0 * y; B[3] = J0; B[4] = 0;  B[5] = J2;
+      B[6] = -J4 * z + J5 * y; B[7] = -J5 * x;        B[8] = J4 * x;  B[9] = 0;  B[10] = J4; B[11] = J5;
+#pragma unroll
+      for (int c = 12; c < 18; c++) B[c] = 0;
+    }
+    const double s = (double)D.e_is2[e];
+    const double ws = rho1 * s;
+    double orr[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) orr[i] = -(s * r[i]) * rho1;
+    // landmark block (upper: 00 01 02 11 12 22)
+    int t = 0;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+#pragma unroll
+      for (int j = i; j < 3; j++) {
+        Hl[t++] += ws * (A[i] * A[j] + A[3 + i] * A[3 + j] + A[6 + i] * A[6 + j]);
+      }
+      bl[i] += A[i] * orr[0] + A[3 + i] * orr[1] + A[6 + i] * orr[2];
+    }
+    if (D.e_free[e] >= 0) {
+      double* We = D.W + 18 * (size_t)e;
+      double* He = D.Hpp_e + 21 * (size_t)e;
+      double* be = D.bp_e + 6 * (size_t)e;
+      t = 0;
+#pragma unroll
+      for (int i = 0; i < 6; i++) {
+#pragma unroll
+        for (int j = i; j < 6; j++) He[t++] = ws * (B[i] * B[j] + B[6 + i] * B[6 + j] + B[12 + i] * B[12 + j]);
+        be[i] = B[i] * orr[0] + B[6 + i] * orr[1] + B[12 + i] * orr[2];
+#pragma unroll
+        for (int j = 0; j < 3; j++) We[i * 3 + j] = ws * (B[i] * A[j] + B[6 + i] * A[3 + j] + B[12 + i] * A[6 + j]);
+      }
+    }
+  }
+  D.chi_lm[l] = chi;
+  if (LINEARIZE) {
+    double* H = D.Hll + 6 * (size_t)l;
+#pragma unroll
+    for (int i = 0; i < 6; i++) H[i] = Hl[i];
+    D.bl[3 * (size_t)l] = bl[0]; D.bl[3 * (size_t)l + 1] = bl[1]; D.bl[3 * (size_t)l + 2] = bl[2];
+  }
+}
+
+__device__ __forceinline__ double block_sum(double v, double* sm) {
+  // fixed-order reduction: warp shuffles then warp partials in order
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (lane == 0) sm[warp] = v;
+  __syncthreads();
+  double t = 0;
+  for (int w = 0; w < nw; w++) t += sm[w];
+  return t;
+}
+
+// One CTA per free pose: H_pp (full symmetric 6x6) and b_p.
+__global__ void __launch_bounds__(128) pose_reduce_kernel(LbaDev D) {
+  __shared__ double sm[4];
+  const int f = blockIdx.x;
+  double acc[27];
+#pragma unroll
+  for (int i = 0; i < 27; i++) acc[i] = 0;
+  for (int p = D.pose_ptr[f] + threadIdx.x; p < D.pose_ptr[f + 1]; p += 128) {
+    const int e = D.pose_edges[p];
+    const double* He = D.Hpp_e + 21 * (size_t)e;
+    const double* be = D.bp_e + 6 * (size_t)e;
+#pragma unroll
+    for (int i = 0; i < 21; i++) acc[i] += He[i];
+#pragma unroll
+    for (int i = 0; i < 6; i++) acc[21 + i] += be[i];
+  }
+  double tot[27];
+#pragma unroll
+  for (int i = 0; i < 27; i++) tot[i] = block_sum(acc[i], sm);
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int i = 0; i < 6; i++)
+      for (int j = i; j < 6; j++) {
+        D.Hpp[36 * (size_t)f + i * 6 + j] = tot[t];
+        D.Hpp[36 * (size_t)f + j * 6 + i] = tot[t];
+        t++;
+      }
+    for (int i = 0; i < 6; i++) D.bp[6 * (size_t)f + i] = tot[21 + i];
+  }
+}
+
+// Deterministic sum of an array by one CTA; optional max of |diag| entries.
+__global__ void __launch_bounds__(1024) reduce_kernel(const double* a, int n, double* out) {
+  __shared__ double sm[32];
+  double v = 0;
+  for (int i = threadIdx.x; i < n; i += 1024) v += a[i];
+  const double t = block_sum(v, sm);
+  if (threadIdx.x == 0) *out = t;
+}
+__global__ void __launch_bounds__(1024) maxdiag_kernel(LbaDev D, const double* Hpp, int with_landmarks, double* out) {
+  __shared__ double sm[32];
+  double m = 0;
+  if (Hpp)
+    for (int i = threadIdx.x; i < D.n_free * 6; i += 1024) m = fmax(m, fabs(Hpp[36 * (size_t)(i / 6) + (i % 6) * 7]));
+  for (int l = threadIdx.x; with_landmarks && l < D.n_mp; l += 1024) {
+    const double* H = D.Hll + 6 * (size_t)l;
+    m = fmax(m, fmax(fabs(H[0]), fmax(fabs(H[3]), fabs(H[5]))));
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) { for (int w = 0; w < 32; w++) m = fmax(m, sm[w]); *out = m; }
+}
+
+// Per landmark: D^-1 = (H_ll + lambda I)^-1 (cofactors), D^-1 b_l, Y_e = W_e D^-1.
+__global__ void __launch_bounds__(128) lm_prepare_kernel(LbaDev D, double lambda) {
+  const int l = blockIdx.x * 128 + threadIdx.x;
+  if (l >= D.n_mp) return;
+  const double* H = D.Hll + 6 * (size_t)l;
+  const double m0 = H[0] + lambda, m1 = H[1], m2 = H[2], m4 = H[3] + lambda, m5 = H[4], m8 = H[5] + lambda;
+  const double c00 = m4 * m8 - m5 * m5, c01 = m5 * m2 - m1 * m8, c02 = m1 * m5 - m4 * m2;
+  const double id = 1.0 / (m0 * c00 + m1 * c01 + m2 * c02);
+  double Di[9];
+  Di[0] = c00 * id; Di[1] = (m2 * m5 - m1 * m8) * id; Di[2] = (m1 * m5 - m2 * m4) * id;
+  Di[3] = c01 * id; Di[4] = (m0 * m8 - m2 * m2) * id; Di[5] = (m2 * m1 - m0 * m5) * id;
+  Di[6] = c02 * id; Di[7] = (m1 * m2 - m0 * m5) * id; Di[8] = (m0 * m4 - m1 * m1) * id;
+  double* Do = D.Dinv + 9 * (size_t)l;
+#pragma unroll
+  for (int i = 0; i < 9; i++) Do[i] = Di[i];
+  const double* b = D.bl + 3 * (size_t)l;
+#pragma unroll
+  for (int i = 0; i < 3; i++) D.db[3 * (size_t)l + i] = Di[i * 3] * b[0] + Di[i * 3 + 1] * b[1] + Di[i * 3 + 2] * b[2];
+  for (int e = D.lm_ptr[l]; e < D.lm_ptr[l + 1]; e++) {
+    if (D.e_free[e] < 0) continue;
+    const double* We = D.W + 18 * (size_t)e;
+    double* Ye = D.Y + 18 * (size_t)e;
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) Ye[i * 3 + j] = We[i * 3] * Di[j] + We[i * 3 + 1] * Di[3 + j] + We[i * 3 + 2] * Di[6 + j];
+  }
+}
+
+// The Schur contraction on the tensor cores: one CTA (4 warps) per pose pair
+// (i1 <= i2); every shared landmark contributes a 6x3 * 3x6 product, issued as an
+// fp64 DMMA m8n8k4 (A = Y_{i1,l} padded to 8x4, B = W_{i2,l}^T padded to 4x8).
+__global__ void __launch_bounds__(128) schur_pairs_kernel(LbaDev D) {
+  __shared__ double part[4][64];
+  const int p = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const bool live = (g < 6) && (t < 3);
+  const int off = g * 3 + t;
+  double c0 = 0, c1 = 0;
+  const int beg = D.pair_ptr[p], end = D.pair_ptr[p + 1];
+  for (int i = beg + warp; i < end; i += 4) {
+    const double a = live ? D.Y[18 * (size_t)D.pair_ea[i] + off] : 0.0;
+    const double b = live ? D.W[18 * (size_t)D.pair_eb[i] + off] : 0.0;
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+  }
+  part[warp][g * 8 + 2 * t] = c0;
+  part[warp][g * 8 + 2 * t + 1] = c1;
+  __syncthreads();
+  if (threadIdx.x < 36) {
+    const int r = threadIdx.x / 6, c = threadIdx.x % 6;  // r: dims of pose i1, c: dims of pose i2
+    const double v = part[0][r * 8 + c] + part[1][r * 8 + c] + part[2][r * 8 + c] + part[3][r * 8 + c];
+    const int i1 = D.pair_i1[p], i2 = D.pair_i2[p];
+    double out = -v;
+    if (i1 == i2) out += D.Hpp[36 * (size_t)i1 + r * 6 + c];
+    // lower triangle of S: block row i2, block column i1
+    D.S[(size_t)(6 * i2 + c) * D.n + 6 * i1 + r] = out;
+  }
+}
+
+// b_s = b_p - sum_e W_e (D^-1 b_l): row n of the S buffer.  One CTA per free pose.
+__global__ void __launch_bounds__(128) bschur_kernel(LbaDev D) {
+  __shared__ double sm[4];
+  const int f = blockIdx.x;
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  for (int p = D.pose_ptr[f] + threadIdx.x; p < D.pose_ptr[f + 1]; p += 128) {
+    const int e = D.pose_edges[p];
+    // landmark of edge e: binary search in lm_ptr is avoided by storing db per edge landmark via e_mp
+    const double* We = D.W + 18 * (size_t)e;
+    const double* d = D.db + 3 * (size_t)D.e_free[D.n_edges + e];  // second half of e_free = landmark id
+#pragma unroll
+    for (int i = 0; i < 6; i++) acc[i] += We[i * 3] * d[0] + We[i * 3 + 1] * d[1] + We[i * 3 + 2] * d[2];
+  }
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    const double t = block_sum(acc[i], sm);
+    if (threadIdx.x == 0) D.S[(size_t)D.n * D.n + 6 * f + i] = D.bp[6 * (size_t)f + i] - t;
+  }
+}
+
+__global__ void add_lambda_kernel(LbaDev D, double lambda) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < D.n) D.S[(size_t)i * D.n + i] += lambda;
+}
+
+// ---------------------------------------------------------------- dense LDL^T
+// (n+1) x n row-major buffer, lower triangle of S in rows 0..n-1, rhs in row n.
+// Blocked right-looking LDL^T over all SMs; every CTA factors the 32x32 diagonal
+// block redundantly in shared memory (saves a grid barrier), owns a slice of the
+// rows below for the panel solve, then a slice of the trailing tiles.
+constexpr int NB = 32;
+
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nblocks, unsigned& gen) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned target = (++gen) * nblocks;
+    atomicAdd(bar, 1u);
+    while (*(volatile unsigned*)bar < target) { }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) ldlt_kernel(double* __restrict__ M, int n, unsigned* bar, double* fail) {
+  __shared__ double L11[NB][NB + 1];
+  __shared__ double Dd[NB];
+  __shared__ double Ti[NB][NB + 1];
+  __shared__ double Tj[NB][NB + 1];
+  const int rows = n + 1;  // including the rhs row
+  unsigned gen = 0;
+  const unsigned nblk = gridDim.x;
+  for (int k0 = 0; k0 < n; k0 += NB) {
+    const int nb = min(NB, n - k0);
+    // ---- diagonal block (redundant per CTA)
+    for (int i = threadIdx.x; i < NB * NB; i += 256) {
+      const int r = i / NB, c = i % NB;
+      L11[r][c] = (r < nb && c <= r) ? M[(size_t)(k0 + r) * n + k0 + c] : 0.0;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const int r = threadIdx.x;
+      for (int c = 0; c < nb; c++) {
+        const double d = L11[c][c];
+        if (r == 0) { Dd[c] = d; if (d == 0.0) *fail = 1.0; }
+        double l = 0;
+        if (r > c && r < nb) {
+          l = L11[r][c] / d;
+          // update the rest of row r: A[r][m] -= l * d * L[m][c] for c < m <= r
+          for (int m = c + 1; m <= r; m++) L11[r][m] -= l * L11[m][c];  // L11[m][c] still holds A (= L*d)
+        }
+        __syncwarp();
+        if (r > c && r < nb) L11[r][c] = l;
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    // ---- panel: rows below the block, one thread per row
+    const int r0 = k0 + nb;
+    for (int i = r0 + blockIdx.x * 256 + threadIdx.x; i < rows; i += 256 * nblk) {
+      double* Mi = M + (size_t)i * n + k0;
+      double ld[NB];
+#pragma unroll 4
+      for (int j = 0; j < nb; j++) {
+        double s = Mi[j];
+        for (int m = 0; m < j; m++) s -= ld[m] * L11[j][m];
+        ld[j] = s;  // = L_ij * D_j
+      }
+      for (int j = 0; j < nb; j++) Mi[j] = ld[j] / Dd[j];
+    }
+    grid_barrier(bar, nblk, gen);
+    // every CTA has loaded the diagonal block by now: publish its factor
+    if (blockIdx.x == 0) {
+      for (int i = threadIdx.x; i < nb * nb; i += 256) {
+        const int r = i / nb, c = i % nb;
+        if (c < r) M[(size_t)(k0 + r) * n + k0 + c] = L11[r][c];
+        else if (c == r) M[(size_t)(k0 + r) * n + k0 + c] = Dd[r];
+      }
+    }
+    // ---- trailing update, 32x32 tiles (bi >= bj), rhs row is the last partial tile row
+    const int T = (rows - r0 + NB - 1) / NB;
+    const int ntiles = T * (T + 1) / 2;
+    for (int tile = blockIdx.x; tile < ntiles; tile += nblk) {
+      // tile -> (bi, bj), bi >= bj
+      int bi = (int)((sqrt(8.0 * tile + 1.0) - 1.0) * 0.5);
+      while ((bi + 1) * (bi + 2) / 2 <= tile) bi++;
+      while (bi * (bi + 1) / 2 > tile) bi--;
+      const int bj = tile - bi * (bi + 1) / 2;
+      const int i0 = r0 + bi * NB, j0 = r0 + bj * NB;
+      if (j0 >= n) continue;  // column block beyond the matrix (only the rhs row exists there)
+      __syncthreads();
+      for (int i = threadIdx.x; i < NB * NB; i += 256) {
+        const int r = i / NB, c = i % NB;
+        Ti[r][c] = (i0 + r < rows && c < nb) ? M[(size_t)(i0 + r) * n + k0 + c] : 0.0;
+        Tj[r][c] = (j0 + r < n && c < nb) ? M[(size_t)(j0 + r) * n + k0 + c] * Dd[c] : 0.0;
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < NB * NB; i += 256) {
+        const int r = i / NB, c = i % NB;
+        const int gi = i0 + r, gj = j0 + c;
+        if (gi >= rows || gj >= n || gj > gi) continue;
+        double s = 0;
+#pragma unroll 8
+        for (int m = 0; m < NB; m++) s += Ti[r][m] * Tj[c][m];
+        M[(size_t)gi * n + gj] -= s;
+      }
+    }
+    grid_barrier(bar, nblk, gen);
+  }
+}
+
+// L^T x = z  (z = row n of M after ldlt_kernel).  Single CTA, right-looking.
+__global__ void __launch_bounds__(1024) backsub_kernel(const double* __restrict__ M, int n, double* __restrict__ x) {
+  extern __shared__ double acc[];  // n entries
+  __shared__ double xb[NB];
+  for (int i = threadIdx.x; i < n; i += 1024) acc[i] = M[(size_t)n * n + i];
+  __syncthreads();
+  const int nblocks = (n + NB - 1) / NB;
+  for (int b = nblocks - 1; b >= 0; b--) {
+    const int k0 = b * NB, nb = min(NB, n - k0);
+    if (threadIdx.x < 32) {
+      // unit upper-triangular solve inside the block, last row first
+      const int r = threadIdx.x;
+      double v = (r < nb) ? acc[k0 + r] : 0.0;
+      for (int c = nb - 1; c >= 0; c--) {
+        const double xc = __shfl_sync(0xffffffffu, v, c);
+        if (r < c) v -= M[(size_t)(k0 + c) * n + k0 + r] * xc;
+      }
+      if (r < nb) { xb[r] = v; x[k0 + r] = v; }
+    }
+    __syncthreads();
+    // acc[j] -= sum_{i in block} L[i][j] x_i for j < k0 (rows are contiguous: coalesced)
+    for (int j = threadIdx.x; j < k0; j += 1024) {
+      double s = 0;
+      for (int i = 0; i < nb; i++) s += M[(size_t)(k0 + i) * n + j] * xb[i];
+      acc[j] -= s;
+    }
+    __syncthreads();
+  }
+}
+
+// x_l = D^-1 (b_l - W^T x_p); scale terms x.(lambda x + b); backup + update points.
+__global__ void __launch_bounds__(128) lm_update_points_kernel(LbaDev D, double lambda) {
+  const int l = blockIdx.x * 128 + threadIdx.x;
+  if (l >= D.n_mp) return;
+  const double* b = D.bl + 3 * (size_t)l;
+  double c[3] = {b[0], b[1], b[2]};
+  for (int e = D.lm_ptr[l]; e < D.lm_ptr[l + 1]; e++) {
+    const int f = D.e_free[e];
+    if (f < 0) continue;
+    const double* We = D.W + 18 * (size_t)e;
+    const double* xp = D.x + 6 * (size_t)f;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      c[0] -= We[i * 3] * xp[i]; c[1] -= We[i * 3 + 1] * xp[i]; c[2] -= We[i * 3 + 2] * xp[i];
+    }
+  }
+  const double* Di = D.Dinv + 9 * (size_t)l;
+  double sc = 0;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const double xl = Di[i * 3] * c[0] + Di[i * 3 + 1] * c[1] + Di[i * 3 + 2] * c[2];
+    D.x[(size_t)D.n + 3 * (size_t)l + i] = xl;
+    sc += xl * (lambda * xl + b[i]);
+    const double old = D.pts[3 * (size_t)l + i];
+    D.pts_bak[3 * (size_t)l + i] = old;
+    D.pts[3 * (size_t)l + i] = old + xl;
+  }
+  D.scale_part[D.n_free + l] = sc;
+}
+
+// VertexSE3Expmap::oplusImpl: T <- exp(delta) * T   (se3quat.h:223-257)
+__global__ void __launch_bounds__(64) lm_update_poses_kernel(LbaDev D, double lambda) {
+  const int f = blockIdx.x * 64 + threadIdx.x;
+  if (f >= D.n_free) return;
+  const int k = D.free_kf[f];
+  double* P = D.pose + 7 * (size_t)k;
+  double* Pb = D.pose_bak + 7 * (size_t)k;
+  const double* u = D.x + 6 * (size_t)f;
+  double sc = 0;
+  for (int i = 0; i < 6; i++) sc += u[i] * (lambda * u[i] + D.bp[6 * (size_t)f + i]);
+  D.scale_part[f] = sc;
+  for (int i = 0; i < 7; i++) Pb[i] = P[i];
+  const double w0 = u[0], w1 = u[1], w2 = u[2];
+  const double theta = sqrt(w0 * w0 + w1 * w1 + w2 * w2);
+  const double Om[9] = {0, -w2, w1, w2, 0, -w0, -w1, w0, 0};
+  double Om2[9];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) Om2[i * 3 + j] = Om[i * 3] * Om[j] + Om[i * 3 + 1] * Om[3 + j] + Om[i * 3 + 2] * Om[6 + j];
+  double R[9], V[9];
+  if (theta < 0.00001) {
+    for (int i = 0; i < 9; i++) { R[i] = ((i % 4 == 0) ? 1.0 : 0.0) + Om[i] + Om2[i]; V[i] = R[i]; }
+  } else {
+    const double a = sin(theta) / theta, b = (1 - cos(theta)) / (theta * theta);
+    const double c = (theta - sin(theta)) / pow(theta, 3.0);
+    for (int i = 0; i < 9; i++) {
+      const double I = (i % 4 == 0) ? 1.0 : 0.0;
+      R[i] = I + a * Om[i] + b * Om2[i];
+      V[i] = I + b * Om[i] + c * Om2[i];
+    }
+  }
+  DQuat qe = R_to_q(R);
+  q_normalize(qe);
+  double te[3];
+  for (int i = 0; i < 3; i++) te[i] = V[i * 3] * u[3] + V[i * 3 + 1] * u[4] + V[i * 3 + 2] * u[5];
+  DQuat q0 = {P[0], P[1], P[2], P[3]};
+  const double t0[3] = {P[4], P[5], P[6]};
+  double rt[3];
+  q_rot(qe, t0, rt);
+  DQuat qn = q_mul(qe, q0);
+  q_normalize(qn);
+  P[0] = qn.x; P[1] = qn.y; P[2] = qn.z; P[3] = qn.w;
+  P[4] = te[0] + rt[0]; P[5] = te[1] + rt[1]; P[6] = te[2] + rt[2];
+}
+
+__global__ void restore_kernel(LbaDev D) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 3 * D.n_mp) D.pts[i] = D.pts_bak[i];
+  if (i < D.n_free * 7) {
+    const int k = D.free_kf[i / 7];
+    D.pose[7 * (size_t)k + i % 7] = D.pose_bak[7 * (size_t)k + i % 7];
+  }
+}
+
+__global__ void normalize_poses_kernel(LbaDev D) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= D.n_kf) return;
+  double* P = D.pose + 7 * (size_t)k;
+  DQuat q = {P[0], P[1], P[2], P[3]};
+  q_normalize(q);  // SE3Quat(q, t) constructor (Optimizer.cc:1217)
+  P[0] = q.x; P[1] = q.y; P[2] = q.z; P[3] = q.w;
+}
+
+__global__ void depth_kernel(LbaDev D, uint8_t* out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= D.n_edges) return;
+  const int l = D.e_free[D.n_edges + e];
+  const double* P = D.pose + 7 * (size_t)D.e_kf[e];
+  DQuat q = {P[0], P[1], P[2], P[3]};
+  double Xc[3];
+  q_rot(q, D.pts + 3 * (size_t)l, Xc);
+  out[e] = (Xc[2] + P[6]) > 0.0;
+}
+
+// ------------------------------------------------------------------- NCCL (dlopen)
+struct Uid { char internal[128]; };
+struct Nccl {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, /*ncclUniqueId by value*/ Uid, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static Nccl g_nccl;
+
+static int nccl_load() {
+  if (g_nccl.lib) return 0;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) {
+    g_nccl.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.lib) break;
+  }
+  if (!g_nccl.lib) { set_last_error(std::string("dlopen libnccl.so.2: ") + dlerror()); return ORB_E_NCCL; }
+  *(void**)&g_nccl.GetUniqueId = dlsym(g_nccl.lib, "ncclGetUniqueId");
+  *(void**)&g_nccl.CommInitRank = dlsym(g_nccl.lib, "ncclCommInitRank");
+  *(void**)&g_nccl.AllReduce = dlsym(g_nccl.lib, "ncclAllReduce");
+  *(void**)&g_nccl.CommDestroy = dlsym(g_nccl.lib, "ncclCommDestroy");
+  *(void**)&g_nccl.GetErrorString = dlsym(g_nccl.lib, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce) {
+    set_last_error("libnccl: missing symbols");
+    return ORB_E_NCCL;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------- solver
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = bytes + bytes / 8 + 256;
+    CUDA_TRYL(cudaMalloc(&p, cap));
+    return 0;
+  }
+};
+
+struct Solver {
+  int device = 0;
+  bool initialized = false;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[8];
+  DevBuf graph, work;
+  double* h_scalars = nullptr;  // pinned
+  unsigned* d_bar = nullptr;
+  int sm_count = 0, ldlt_blocks = 0;
+  long long launches = 0;
+  void* comm = nullptr;
+  int rank = 0, world = 1;
+
+  int init() {
+    if (initialized) return 0;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+      set_last_error("no CUDA device: orb_slam3_b200 has no CPU path");
+      return ORB_E_NODEVICE;
+    }
+    CUDA_TRYL(cudaSetDevice(device));
+    CUDA_TRYL(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    for (auto& e : ev) CUDA_TRYL(cudaEventCreate(&e));
+    CUDA_TRYL(cudaHostAlloc((void**)&h_scalars, 8 * sizeof(double), cudaHostAllocDefault));
+    CUDA_TRYL(cudaMalloc((void**)&d_bar, 256));
+    cudaDeviceProp prop;
+    CUDA_TRYL(cudaGetDeviceProperties(&prop, device));
+    sm_count = prop.multiProcessorCount;
+    int per_sm = 0;
+    CUDA_TRYL(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ldlt_kernel, 256, 0));
+    ldlt_blocks = sm_count * std::max(1, std::min(per_sm, 1));
+    initialized = true;
+    return 0;
+  }
+  ~Solver() {
+    if (!initialized) return;
+    cudaSetDevice(device);
+    if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
+    if (graph.p) cudaFree(graph.p);
+    if (work.p) cudaFree(work.p);
+    cudaFreeHost(h_scalars);
+    cudaFree(d_bar);
+    for (auto& e : ev) cudaEventDestroy(e);
+    cudaStreamDestroy(stream);
+  }
+};
+
+template <class T>
+static T* carve(uint8_t*& p, size_t count) {
+  T* r = (T*)p;
+  p += (count * sizeof(T) + 255) & ~(size_t)255;
+  return r;
+}
+
+static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t* stop, int max_iters,
+                      double lambda_init, double* kf_pose_out, double* mp_pos_out, double* chi2_out,
+                      uint8_t* depth_pos_out, lba_stats* stats) {
+  if (!g || !kf_pose_out || !mp_pos_out || g->n_kf <= 0 || g->n_mp < 0 || g->n_edges < 0) {
+    set_last_error("lba_solve: bad argument");
+    return ORB_E_ARG;
+  }
+  int rc = S.init();
+  if (rc) return rc;
+  CUDA_TRYL(cudaSetDevice(S.device));
+  const int K = g->n_kf, L = g->n_mp, E = g->n_edges;
+  // ---- structure (host): free poses, landmark CSR, pose CSR, pose-pair lists
+  std::vector<int> free_idx(K, -1), free_kf;
+  for (int k = 0; k < K; k++)
+    if (!g->kf_fixed[k]) { free_idx[k] = (int)free_kf.size(); free_kf.push_back(k); }
+  const int nf = (int)free_kf.size(), n = 6 * nf;
+  if (nf == 0) { set_last_error("lba_solve: no free keyframe"); return ORB_E_ARG; }
+  std::vector<int> lm_ptr(L + 1, 0);
+  for (int e = 0; e < E; e++) {
+    if (g->e_mp[e] < 0 || g->e_mp[e] >= L || g->e_kf[e] < 0 || g->e_kf[e] >= K) { set_last_error("edge index"); return ORB_E_ARG; }
+    lm_ptr[g->e_mp[e] + 1]++;
+  }
+  for (int l = 0; l < L; l++) lm_ptr[l + 1] += lm_ptr[l];
+  std::vector<int> perm(E), cursor(lm_ptr.begin(), lm_ptr.end() - 1);
+  for (int e = 0; e < E; e++) perm[cursor[g->e_mp[e]]++] = e;   // sorted position -> original edge
+  std::vector<int> se_kf(E), se_free(2 * (size_t)E);
+  std::vector<uint8_t> se_st(E);
+  std::vector<double> se_obs(3 * (size_t)E);
+  std::vector<float> se_is2(E);
+  std::vector<int> pose_cnt(nf + 1, 0);
+  for (int s = 0; s < E; s++) {
+    const int e = perm[s];
+    se_kf[s] = g->e_kf[e];
+    se_free[s] = free_idx[g->e_kf[e]];
+    se_free[(size_t)E + s] = g->e_mp[e];
+    se_st[s] = g->e_stereo[e] ? 1 : 0;
+    memcpy(&se_obs[3 * (size_t)s], g->e_obs + 3 * (size_t)e, 3 * sizeof(double));
+    se_is2[s] = g->e_inv_sigma2[e];
+    if (se_free[s] >= 0) pose_cnt[se_free[s] + 1]++;
+  }
+  std::vector<int> pose_ptr(nf + 1, 0);
+  for (int f = 0; f < nf; f++) pose_ptr[f + 1] = pose_ptr[f] + pose_cnt[f + 1];
+  std::vector<int> pose_edges(pose_ptr[nf]), pcur(pose_ptr.begin(), pose_ptr.end() - 1);
+  for (int s = 0; s < E; s++)
+    if (se_free[s] >= 0) pose_edges[pcur[se_free[s]]++] = s;
+  // pairs: for every landmark, every (a <= b) of its free-pose edges
+  std::vector<long long> pair_count((size_t)nf * nf, 0);
+  std::vector<int> tmp;
+  double schur_flops = 0;
+  for (int l = 0; l < L; l++) {
+    tmp.clear();
+    for (int s = lm_ptr[l]; s < lm_ptr[l + 1]; s++)
+      if (se_free[s] >= 0) tmp.push_back(s);
+    const double m = (double)tmp.size();
+    schur_flops += 50 + m * (108 + 36) + m * (m + 1) / 2 * 216;
+    for (size_t a = 0; a < tmp.size(); a++)
+      for (size_t b = 0; b < tmp.size(); b++) {
+        const int fa = se_free[tmp[a]], fb = se_free[tmp[b]];
+        if (fa < fb || (fa == fb && a <= b)) pair_count[(size_t)fa * nf + fb]++;
+      }
+  }
+  std::vector<int> pair_i1, pair_i2, pair_ptr(1, 0);
+  std::vector<long long> pair_slot((size_t)nf * nf, -1);
+  for (int a = 0; a < nf; a++)
+    for (int b = a; b < nf; b++) {
+      const long long c = pair_count[(size_t)a * nf + b];
+      if (c == 0 && a != b) continue;
+      pair_slot[(size_t)a * nf + b] = (long long)pair_i1.size();
+      pair_i1.push_back(a); pair_i2.push_back(b);
+      pair_ptr.push_back(pair_ptr.back() + (int)c);
+    }
+  const int n_pairs = (int)pair_i1.size();
+  std::vector<int> pair_ea(pair_ptr.back()), pair_eb(pair_ptr.back()), pair_cur(pair_ptr.begin(), pair_ptr.end() - 1);
+  for (int l = 0; l < L; l++) {
+    tmp.clear();
+    for (int s = lm_ptr[l]; s < lm_ptr[l + 1]; s++)
+      if (se_free[s] >= 0) tmp.push_back(s);
+    for (size_t a = 0; a < tmp.size(); a++)
+      for (size_t b = 0; b < tmp.size(); b++) {
+        const int fa = se_free[tmp[a]], fb = se_free[tmp[b]];
+        if (fa < fb || (fa == fb && a <= b)) {
+          const int slot = (int)pair_slot[(size_t)fa * nf + fb];
+          const int pos = pair_cur[slot]++;
+          pair_ea[pos] = tmp[a]; pair_eb[pos] = tmp[b];
+        }
+      }
+  }
+  // ---- device memory
+  size_t gbytes = 256 * 20 + sizeof(int) * ((size_t)L + 1 + 3 * (size_t)E + nf + (nf + 1) + pose_edges.size() +
+                                            2 * (size_t)n_pairs + pair_ptr.size() + 2 * pair_ea.size()) +
+                  (size_t)E * (1 + 24 + 4) + (size_t)K * 20;
+  if (S.graph.reserve(gbytes)) return ORB_E_CUDA;
+  uint8_t* gp = (uint8_t*)S.graph.p;
+  LbaDev D;
+  memset(&D, 0, sizeof(D));
+  D.n_kf = K; D.n_free = nf; D.n_mp = L; D.n_edges = E; D.n = n; D.n_pairs = n_pairs;
+  cudaStream_t st = S.stream;
+#define UPLOAD(field, type, vec, count)                                                              \
+  do {                                                                                               \
+    type* dptr = carve<type>(gp, std::max<size_t>(count, 1));                                        \
+    if ((count) > 0) CUDA_TRYL(cudaMemcpyAsync(dptr, (vec), sizeof(type) * (count), cudaMemcpyHostToDevice, st)); \
+    D.field = dptr;                                                                                  \
+  } while (0)
+  UPLOAD(lm_ptr, int, lm_ptr.data(), (size_t)L + 1);
+  UPLOAD(e_kf, int, se_kf.data(), (size_t)E);
+  UPLOAD(e_free, int, se_free.data(), 2 * (size_t)E);
+  UPLOAD(e_stereo, uint8_t, se_st.data(), (size_t)E);
+  UPLOAD(e_obs, double, se_obs.data(), 3 * (size_t)E);
+  UPLOAD(e_is2, float, se_is2.data(), (size_t)E);
+  UPLOAD(kf_cam, float, g->kf_cam, 5 * (size_t)K);
+  UPLOAD(free_kf, int, free_kf.data(), (size_t)nf);
+  UPLOAD(pose_ptr, int, pose_ptr.data(), (size_t)nf + 1);
+  UPLOAD(pose_edges, int, pose_edges.data(), pose_edges.size());
+  UPLOAD(pair_i1, int, pair_i1.data(), (size_t)n_pairs);
+  UPLOAD(pair_i2, int, pair_i2.data(), (size_t)n_pairs);
+  UPLOAD(pair_ptr, int, pair_ptr.data(), pair_ptr.size());
+  UPLOAD(pair_ea, int, pair_ea.data(), pair_ea.size());
+  UPLOAD(pair_eb, int, pair_eb.data(), pair_eb.size());
+#undef UPLOAD
+  const size_t nS = (size_t)(n + 1) * n;
+  size_t wbytes = 256 * 24 + sizeof(double) * (14 * (size_t)K + 6 * (size_t)L + (size_t)L * (6 + 3 + 9 + 3 + 1) +
+                                               (size_t)E * (18 + 18 + 21 + 6 + 1) + (size_t)nf * 42 + nS +
+                                               (size_t)n + 3 * (size_t)L + (size_t)nf + L + 16) + (size_t)E;
+  if (S.work.reserve(wbytes)) return ORB_E_CUDA;
+  uint8_t* wp = (uint8_t*)S.work.p;
+  D.pose = carve<double>(wp, 7 * (size_t)K); D.pose_bak = carve<double>(wp, 7 * (size_t)K);
+  D.pts = carve<double>(wp, 3 * (size_t)L + 1); D.pts_bak = carve<double>(wp, 3 * (size_t)L + 1);
+  D.Hll = carve<double>(wp, 6 * (size_t)L + 1); D.bl = carve<double>(wp, 3 * (size_t)L + 1);
+  D.Dinv = carve<double>(wp, 9 * (size_t)L + 1); D.db = carve<double>(wp, 3 * (size_t)L + 1);
+  D.chi_lm = carve<double>(wp, (size_t)L + 1);
+  D.W = carve<double>(wp, 18 * (size_t)E + 1); D.Y = carve<double>(wp, 18 * (size_t)E + 1);
+  D.Hpp_e = carve<double>(wp, 21 * (size_t)E + 1); D.bp_e = carve<double>(wp, 6 * (size_t)E + 1);
+  D.chi2_e = carve<double>(wp, (size_t)E + 1);
+  D.Hpp = carve<double>(wp, 36 * (size_t)nf); D.bp = carve<double>(wp, 6 * (size_t)nf);
+  D.S = carve<double>(wp, nS);
+  D.x = carve<double>(wp, (size_t)n + 3 * (size_t)L + 1);
+  D.scale_part = carve<double>(wp, (size_t)nf + L + 1);
+  D.scalars = carve<double>(wp, 16);
+  uint8_t* d_depth = carve<uint8_t>(wp, (size_t)E + 1);
+  const float thm = (float)sqrt(5.991), ths = (float)sqrt(7.815);  // Optimizer.cc:1275-1276
+  D.hm.delta = thm; D.hm.dsqr = (double)(float)((double)thm * (double)thm);
+  D.hs.delta = ths; D.hs.dsqr = (double)(float)((double)ths * (double)ths);
+  CUDA_TRYL(cudaMemcpyAsync(D.pose, g->kf_pose, sizeof(double) * 7 * (size_t)K, cudaMemcpyHostToDevice, st));
+  if (L) CUDA_TRYL(cudaMemcpyAsync(D.pts, g->mp_pos, sizeof(double) * 3 * (size_t)L, cudaMemcpyHostToDevice, st));
+  CUDA_TRYL(cudaMemsetAsync(D.chi2_e, 0, sizeof(double) * ((size_t)E + 1), st));
+  CUDA_TRYL(cudaMemsetAsync(D.x, 0, sizeof(double) * ((size_t)n + 3 * (size_t)L + 1), st));
+  CUDA_TRYL(cudaMemsetAsync(D.scalars, 0, sizeof(double) * 16, st));
+  CUDA_TRYL(cudaMemsetAsync(D.W, 0, sizeof(double) * (18 * (size_t)E + 1), st));
+  CUDA_TRYL(cudaEventRecord(S.ev[0], st));
+  normalize_poses_kernel<<<(K + 127) / 128, 128, 0, st>>>(D);
+  S.launches++;
+
+  const int lm_blocks = (L + 127) / 128;
+  auto terminate = [&]() { return stop && *stop; };
+  auto allreduce = [&](double* buf, size_t count) -> int {
+    if (S.world <= 1) return 0;
+    int r = g_nccl.AllReduce(buf, buf, count, /*ncclFloat64*/ 8, /*ncclSum*/ 0, S.comm, st);
+    if (r != 0) { set_last_error(std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?")); return ORB_E_NCCL; }
+    return 0;
+  };
+  // chi (robust) of the current state -> h_scalars[0]; all ranks see the global value
+  auto eval_chi = [&](bool linearize) -> int {
+    if (L) {
+      if (linearize) lin_kernel<true><<<lm_blocks, 128, 0, st>>>(D);
+      else lin_kernel<false><<<lm_blocks, 128, 0, st>>>(D);
+    }
+    reduce_kernel<<<1, 1024, 0, st>>>(D.chi_lm, L, D.scalars);
+    S.launches += 2;
+    return 0;
+  };
+  double lambda = -1, ni = 2, chi_first = 0, currentChi = 0;
+  int nBad = 0, trials = 0, iters = 0;
+  float ms_lin = 0, ms_schur = 0, ms_solve = 0, ms_upd = 0;
+  auto lap = [&](int a, int b, float& acc) {
+    float t = 0;
+    if (cudaEventElapsedTime(&t, S.ev[a], S.ev[b]) == cudaSuccess) acc += t;
+  };
+  for (int it = 0; it < max_iters && !terminate(); it++) {
+    CUDA_TRYL(cudaEventRecord(S.ev[1], st));
+    eval_chi(true);
+    pose_reduce_kernel<<<nf, 128, 0, st>>>(D);
+    S.launches++;
+    if (S.world > 1 && (rc = allreduce(D.scalars, 1))) return rc;  // global robust chi2
+    if (it == 0 && !(lambda_init > 0)) {
+      // computeLambdaInit: max |diag| over all free vertices of the *global* Hessian
+      if (S.world == 1) {
+        maxdiag_kernel<<<1, 1024, 0, st>>>(D, D.Hpp, 1, D.scalars + 2);
+      } else {
+        maxdiag_kernel<<<1, 1024, 0, st>>>(D, nullptr, 1, D.scalars + 2);
+        int r = g_nccl.AllReduce(D.scalars + 2, D.scalars + 2, 1, 8, /*ncclMax*/ 2, S.comm, st);
+        if (r) { set_last_error("ncclAllReduce(max)"); return ORB_E_NCCL; }
+        CUDA_TRYL(cudaMemcpyAsync(D.S, D.Hpp, sizeof(double) * 36 * (size_t)nf, cudaMemcpyDeviceToDevice, st));
+        if ((rc = allreduce(D.S, 36 * (size_t)nf))) return rc;
+        maxdiag_kernel<<<1, 1024, 0, st>>>(D, D.S, 0, D.scalars + 4);
+      }
+      S.launches++;
+    }
+    CUDA_TRYL(cudaMemcpyAsync(S.h_scalars, D.scalars, 5 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRYL(cudaEventRecord(S.ev[2], st));
+    CUDA_TRYL(cudaStreamSynchronize(st));
+    lap(1, 2, ms_lin);
+    currentChi = S.h_scalars[0];
+    double tempChi = currentChi;
+    const double iniChi = currentChi;
+    if (it == 0) {
+      chi_first = currentChi;
+      if (lambda_init > 0) lambda = lambda_init;
+      else lambda = 1e-5 * std::max(S.h_scalars[2], S.world > 1 ? S.h_scalars[4] : 0.0);  // tau = 1e-5
+      ni = 2; nBad = 0;
+    }
+    double rho = 0;
+    int qmax = 0;
+    do {
+      CUDA_TRYL(cudaEventRecord(S.ev[3], st));
+      // Schur complement
+      CUDA_TRYL(cudaMemsetAsync(D.S, 0, sizeof(double) * nS, st));
+      if (L) lm_prepare_kernel<<<lm_blocks, 128, 0, st>>>(D, lambda);
+      schur_pairs_kernel<<<n_pairs, 128, 0, st>>>(D);
+      bschur_kernel<<<nf, 128, 0, st>>>(D);
+      S.launches += 3;
+      // landmark shards: every rank holds its partial H_pp, b_p and Schur terms; one sum gives (S | b_s)
+      if (S.world > 1 && (rc = allreduce(D.S, nS))) return rc;
+      add_lambda_kernel<<<(n + 255) / 256, 256, 0, st>>>(D, lambda);
+      CUDA_TRYL(cudaEventRecord(S.ev[4], st));
+      // reduced solve
+      CUDA_TRYL(cudaMemsetAsync(S.d_bar, 0, 256, st));
+      CUDA_TRYL(cudaMemsetAsync(D.scalars + 3, 0, sizeof(double), st));
+      {
+        double* Mp = D.S;
+        int nn = n;
+        unsigned* bar = S.d_bar;
+        double* failp = D.scalars + 3;
+        void* args[] = {&Mp, &nn, &bar, &failp};
+        const int blocks = std::min(S.ldlt_blocks, std::max(1, (n + 1 + NB - 1) / NB * ((n + 1 + NB - 1) / NB)));
+        CUDA_TRYL(cudaLaunchCooperativeKernel((void*)ldlt_kernel, dim3(blocks), dim3(256), args, 0, st));
+      }
+      backsub_kernel<<<1, 1024, sizeof(double) * n, st>>>(D.S, n, D.x);
+      S.launches += 3;
+      CUDA_TRYL(cudaEventRecord(S.ev[5], st));
+      // update + evaluate
+      if (L) lm_update_points_kernel<<<lm_blocks, 128, 0, st>>>(D, lambda);
+      lm_update_poses_kernel<<<(nf + 63) / 64, 64, 0, st>>>(D, S.rank == 0 ? lambda : 0.0);
+      eval_chi(false);
+      reduce_kernel<<<1, 1024, 0, st>>>(D.scale_part, nf + L, D.scalars + 1);
+      S.launches += 3;
+      if (S.world > 1) {
+        if ((rc = allreduce(D.scalars, 2))) return rc;
+      }
+      CUDA_TRYL(cudaMemcpyAsync(S.h_scalars, D.scalars, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+      CUDA_TRYL(cudaEventRecord(S.ev[6], st));
+      CUDA_TRYL(cudaStreamSynchronize(st));
+      lap(3, 4, ms_schur); lap(4, 5, ms_solve); lap(5, 6, ms_upd);
+      const bool ok2 = S.h_scalars[3] == 0.0;
+      tempChi = S.h_scalars[0];
+      if (!ok2) tempChi = DBL_MAX;
+      rho = currentChi - tempChi;
+      double scale = S.h_scalars[1];
+      scale += 1e-3;
+      rho /= scale;
+      if (rho > 0 && std::isfinite(tempChi)) {
+        double alpha = 1. - pow((2 * rho - 1), 3);
+        alpha = std::min(alpha, 2. / 3.);
+        const double scaleFactor = std::max(1. / 3., alpha);
+        lambda *= scaleFactor;
+        ni = 2;
+        currentChi = tempChi;
+      } else {
+        lambda *= ni;
+        ni *= 2;
+        restore_kernel<<<(std::max(3 * L, 7 * nf) + 255) / 256, 256, 0, st>>>(D);  // pop
+        S.launches++;
+      }
+      qmax++;
+      trials++;
+    } while (rho < 0 && qmax < 10 && !terminate());
+    iters++;
+    if (qmax == 10 || rho == 0) break;
+    if ((iniChi - currentChi) * 1e3 < iniChi) nBad++;
+    else nBad = 0;
+    if (nBad >= 3) break;
+  }
+  // ---- outputs
+  if (E) depth_kernel<<<(E + 255) / 256, 256, 0, st>>>(D, d_depth);
+  S.launches++;
+  CUDA_TRYL(cudaEventRecord(S.ev[7], st));
+  std::vector<double> chi_sorted(E);
+  std::vector<uint8_t> dep_sorted(E);
+  CUDA_TRYL(cudaMemcpyAsync(kf_pose_out, D.pose, sizeof(double) * 7 * (size_t)K, cudaMemcpyDeviceToHost, st));
+  if (L) CUDA_TRYL(cudaMemcpyAsync(mp_pos_out, D.pts, sizeof(double) * 3 * (size_t)L, cudaMemcpyDeviceToHost, st));
+  if (E) {
+    CUDA_TRYL(cudaMemcpyAsync(chi_sorted.data(), D.chi2_e, sizeof(double) * E, cudaMemcpyDeviceToHost, st));
+    CUDA_TRYL(cudaMemcpyAsync(dep_sorted.data(), d_depth, E, cudaMemcpyDeviceToHost, st));
+  }
+  CUDA_TRYL(cudaStreamSynchronize(st));
+  for (int s = 0; s < E; s++) {
+    if (chi2_out) chi2_out[perm[s]] = chi_sorted[s];
+    if (depth_pos_out) depth_pos_out[perm[s]] = dep_sorted[s];
+  }
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    stats->iterations = iters; stats->trials = trials; stats->stopped = terminate() ? 1 : 0;
+    stats->chi2_initial = chi_first; stats->chi2_final = currentChi; stats->lambda_final = lambda;
+    float tot = 0;
+    cudaEventElapsedTime(&tot, S.ev[0], S.ev[7]);
+    stats->ms_total = tot; stats->ms_linearize = ms_lin; stats->ms_schur = ms_schur; stats->ms_solve = ms_solve;
+    stats->ms_update = ms_upd; stats->n_free_kf = nf; stats->n_pairs = n_pairs; stats->schur_flops = schur_flops;
+  }
+  return iters;
+}
+
+}  // namespace orbb200
+
+using orbb200::Solver;
+struct lba_solver { Solver s; };
+
+extern "C" {
+
+int lba_create(int device, lba_solver** out) {
+  if (!out || device < 0) return ORB_E_ARG;
+  *out = new lba_solver();
+  (*out)->s.device = device;
+  return ORB_OK;
+}
+void lba_destroy(lba_solver* s) { delete s; }
+
+int lba_nccl_unique_id(void* out128) {
+  if (!out128) return ORB_E_ARG;
+  int rc = orbb200::nccl_load();
+  if (rc) return rc;
+  orbb200::Uid id;
+  memset(&id, 0, sizeof(id));
+  if (orbb200::g_nccl.GetUniqueId(&id) != 0) { orbb200::set_last_error("ncclGetUniqueId failed"); return ORB_E_NCCL; }
+  memcpy(out128, &id, 128);
+  return ORB_OK;
+}
+
+int lba_comm_init(lba_solver* s, int rank, int world, const void* unique_id128) {
+  if (!s || !unique_id128 || world < 1 || rank < 0 || rank >= world) return ORB_E_ARG;
+  int rc = s->s.init();
+  if (rc) return rc;
+  if (world == 1) { s->s.rank = 0; s->s.world = 1; return ORB_OK; }
+  rc = orbb200::nccl_load();
+  if (rc) return rc;
+  cudaSetDevice(s->s.device);
+  orbb200::Uid id;
+  memcpy(&id, unique_id128, 128);
+  void* comm = nullptr;
+  int r = orbb200::g_nccl.CommInitRank(&comm, world, id, rank);
+  if (r != 0) {
+    orbb200::set_last_error(std::string("ncclCommInitRank: ") +
+                            (orbb200::g_nccl.GetErrorString ? orbb200::g_nccl.GetErrorString(r) : "?"));
+    return ORB_E_NCCL;
+  }
+  s->s.comm = comm; s->s.rank = rank; s->s.world = world;
+  return ORB_OK;
+}
+
+int lba_solve(lba_solver* s, const lba_graph_view* g, const volatile uint8_t* stop, int max_iters,
+              double lambda_init, double* kf_pose_out, double* mp_pos_out, double* chi2_out,
+              uint8_t* depth_pos_out, lba_stats* stats) {
+  if (!s) return ORB_E_ARG;
+  return orbb200::solve_impl(s->s, g, stop, max_iters, lambda_init, kf_pose_out, mp_pos_out, chi2_out,
+                             depth_pos_out, stats);
+}
+
+long long lba_kernel_launches(const lba_solver* s) { return s ? s->s.launches : 0; }
+
+}  // extern "C"

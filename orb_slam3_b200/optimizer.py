@@ -1,0 +1,66 @@
+"""Host-side mirror of Optimizer::LocalBundleAdjustment's optimisation core
+(src/Optimizer.cc:1116-1498, the part between graph set-up and write-back) over
+the C ABI: lba_solve runs g2o's `optimizer.optimize(10)` equivalent on the GPU.
+No CPU fallback."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, ptr
+from .views import lba_stats
+
+
+class LocalBundleAdjustment:
+    """One solver handle (CUDA stream + scratch) reusable across calls."""
+
+    CHI2_MONO = 5.991     # Optimizer.cc:1423
+    CHI2_STEREO = 7.815   # Optimizer.cc:1455
+
+    def __init__(self, device=0):
+        self._lib = _lib.lib()
+        h = C.c_void_p()
+        check(self._lib.lba_create(int(device), C.byref(h)))
+        self._h = h
+        self.rank, self.world = 0, 1
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._lib.lba_destroy(h)
+            self._h = None
+
+    def init_comm(self, rank, world, unique_id):
+        """Landmark-sharded multi-GPU mode; unique_id = bytes from nccl_unique_id() of rank 0."""
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
+        check(self._lib.lba_comm_init(self._h, int(rank), int(world), buf))
+        self.rank, self.world = rank, world
+
+    @staticmethod
+    def nccl_unique_id():
+        buf = (C.c_char * 128)()
+        check(_lib.lib().lba_nccl_unique_id(buf))
+        return bytes(buf)
+
+    def __call__(self, graph, pbStopFlag=None, max_iters=10, lambda_init=0.0):
+        """graph: lba_graph_view.  Returns dict(iterations, kf_pose, mp_pos, chi2, depth_pos, stats);
+        the caller applies the chi2 / depth tests (:1413-1460) and writes poses back."""
+        kf = np.empty((graph.n_kf, 7))
+        mp = np.empty((graph.n_mp, 3))
+        chi2 = np.empty(graph.n_edges)
+        dp = np.empty(graph.n_edges, np.uint8)
+        st = lba_stats()
+        sp = ptr(pbStopFlag) if pbStopFlag is not None else None
+        it = check(self._lib.lba_solve(self._h, C.byref(graph), sp, int(max_iters), float(lambda_init), ptr(kf),
+                                       ptr(mp), ptr(chi2), ptr(dp), C.byref(st)))
+        return dict(iterations=it, kf_pose=kf, mp_pos=mp, chi2=chi2, depth_pos=dp, stats=st.as_dict())
+
+    def kernel_launches(self):
+        return int(self._lib.lba_kernel_launches(self._h))
+
+    @classmethod
+    def outliers(cls, graph_dict, result):
+        """Edges the reference erases after optimize(): chi2 > 5.991 (mono) / 7.815 (stereo) or depth <= 0."""
+        st = np.asarray(graph_dict["e_stereo"]).astype(bool)
+        th = np.where(st, cls.CHI2_STEREO, cls.CHI2_MONO)
+        return (result["chi2"] > th) | (result["depth_pos"] == 0)

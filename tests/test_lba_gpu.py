@@ -1,0 +1,93 @@
+"""GPU parity of lba_solve (C ABI) against the fp64 CPU oracle: pose / landmark
+deltas within 1e-4 relative (BASELINE.json north_star), same number of LM
+iterations and lambda trials, same outlier classification."""
+import numpy as np
+import pytest
+
+from orb_slam3_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _compare(g, ref, got, ctx=""):
+    assert got["iterations"] == ref["iterations"], (ctx, got["iterations"], ref["iterations"])
+    assert got["stats"]["trials"] == ref["stats"]["trials"], ctx
+    for key in ("kf_pose", "mp_pos"):
+        d_ref = ref[key] - (g[key] if key == "mp_pos" else ref[key] * 0)
+        scale = max(np.abs(ref[key] - g[key]).max(), 1e-9) if key == "mp_pos" else 1.0
+        err = np.abs(got[key] - ref[key]).max()
+        assert err <= TOL * scale, (ctx, key, err, scale)
+    # relative error on the deltas themselves
+    dref = ref["mp_pos"] - g["mp_pos"]
+    dgot = got["mp_pos"] - g["mp_pos"]
+    rel = np.linalg.norm(dgot - dref) / max(np.linalg.norm(dref), 1e-30)
+    assert rel < TOL, (ctx, "delta points rel", rel)
+    tref = ref["kf_pose"][:, 4:] - g["kf_pose"][:, 4:]
+    tgot = got["kf_pose"][:, 4:] - g["kf_pose"][:, 4:]
+    rel = np.linalg.norm(tgot - tref) / max(np.linalg.norm(tref), 1e-30)
+    assert rel < TOL, (ctx, "delta translation rel", rel)
+    assert abs(got["stats"]["chi2_final"] - ref["stats"]["chi2_final"]) <= 1e-8 * ref["stats"]["chi2_final"]
+    assert np.allclose(got["chi2"], ref["chi2"], rtol=1e-6, atol=1e-6)
+    assert np.array_equal(got["depth_pos"], ref["depth_pos"])
+
+
+@pytest.fixture(scope="module")
+def lba():
+    from orb_slam3_b200.optimizer import LocalBundleAdjustment
+    return LocalBundleAdjustment()
+
+
+@pytest.mark.parametrize("K,L,seed", [(5, 60, 0), (10, 500, 1), (20, 3000, 2), (37, 2000, 3)])
+def test_lba_matches_oracle(oracle, lba, K, L, seed):
+    g, _ = scenes.lba_graph(K, L, seed=seed)
+    gv = scenes.lba_view(g)
+    _compare(g, oracle.lba_solve(gv), lba(gv), "K%d" % K)
+
+
+def test_lba_config4_50kf_20k_landmarks(oracle, lba):
+    g, _ = scenes.lba_graph(50, 20000, seed=0)
+    gv = scenes.lba_view(g)
+    ref, got = oracle.lba_solve(gv), lba(gv)
+    _compare(g, ref, got, "config4")
+    from orb_slam3_b200.optimizer import LocalBundleAdjustment as LBA
+    assert np.array_equal(LBA.outliers(g, ref), LBA.outliers(g, got))
+
+
+def test_lba_rejected_trials_and_user_lambda(oracle, lba):
+    g, _ = scenes.lba_graph(5, 60, seed=3)
+    rng = np.random.default_rng(3)
+    g["mp_pos"] = g["mp_pos"] + rng.normal(0, 5.0, g["mp_pos"].shape)
+    g["kf_pose"][:, 4:] += rng.normal(0, 0.3, (len(g["kf_pose"]), 3)) * (g["kf_fixed"][:, None] == 0)
+    gv = scenes.lba_view(g)
+    ref = oracle.lba_solve(gv, max_iters=4, lambda_init=1e-8)
+    got = lba(gv, max_iters=4, lambda_init=1e-8)
+    assert (ref["trace"][:, 3] == 0).any()
+    assert got["stats"]["trials"] == ref["stats"]["trials"] and got["iterations"] == ref["iterations"]
+    assert abs(got["stats"]["chi2_final"] - ref["stats"]["chi2_final"]) <= 1e-5 * ref["stats"]["chi2_final"]
+    # inertial maps: setUserLambdaInit(100) (Optimizer.cc:1197-1198)
+    g2, _ = scenes.lba_graph(8, 300, seed=5)
+    gv2 = scenes.lba_view(g2)
+    _compare(g2, oracle.lba_solve(gv2, lambda_init=100.0), lba(gv2, lambda_init=100.0), "lambda100")
+
+
+def test_lba_stop_flag_and_fixed_poses(oracle, lba):
+    g, _ = scenes.lba_graph(8, 200, seed=3)
+    gv = scenes.lba_view(g)
+    stop = np.ones(1, np.uint8)
+    r = lba(gv, pbStopFlag=stop)
+    assert r["iterations"] == 0 and r["stats"]["stopped"] == 1
+    assert np.allclose(r["mp_pos"], g["mp_pos"])
+    r = lba(gv)
+    fixed = g["kf_fixed"] == 1
+    q0 = g["kf_pose"][fixed].copy()
+    q0[:, :4] /= np.linalg.norm(q0[:, :4], axis=1, keepdims=True)
+    assert np.allclose(r["kf_pose"][fixed], q0, atol=1e-14)
+    # edge order must not matter: shuffle the edges, same result (deterministic reductions aside)
+    perm = np.random.default_rng(0).permutation(len(g["e_kf"]))
+    g2 = dict(g)
+    for k in ("e_kf", "e_mp", "e_stereo", "e_obs", "e_inv_sigma2"):
+        g2[k] = g[k][perm]
+    r2 = lba(scenes.lba_view(g2))
+    assert np.allclose(r2["mp_pos"], r["mp_pos"], rtol=0, atol=1e-9)
+    assert np.allclose(r2["chi2"], r["chi2"][perm], rtol=1e-9, atol=1e-9)
