@@ -4,17 +4,24 @@
 python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 A "step" is one pass of the front-end hot path over one batch of synthetic
-1280x720 frames (8 levels, 2000 features): ORB extract (+ projection match once
-the matcher stage is enabled).  One process per GPU (torchrun for N>1), frames
-are independent so ranks share nothing: weak scaling, no data-path collective.
+1280x720 frames (BASELINE.json configs[1]: 8 levels, 2000 features): per frame
+ORB extract -> SearchByProjection against the previous frame (th 15, rotation
+check) -> SearchByProjection against ~3000 local map points (th 3).  One
+process per GPU (torchrun for N>1); frames are independent so ranks share
+nothing on this path: weak scaling, no data-path collective.
 
   value : frames/s with the batch already resident in HBM (CUDA events on the
           launching stream, max over ranks)
-  e2e   : frames/s through the host-buffer C ABI (pinned host frames -> H2D ->
-          kernels -> D2H keypoints+descriptors), same batches
+  e2e   : frames/s through the host-buffer C ABI: pinned host frames -> H2D ->
+          kernels -> D2H keypoints + descriptors, then host views -> match ->
+          D2H assignments
+  lba   : LocalBA LM iterations/s (optimize(10) incl. rejected trials) on the
+          synthetic config-4 graph (N=1) / config-5 graph sharded by landmark
+          with one NCCL all-reduce per trial (N>1)
   roofline / cpu_baseline : see DESIGN.md "Measurement"
 """
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -28,7 +35,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 H, W, NFEAT, NLEVELS = 720, 1280, 2000, 8
+N_LOCAL_EXTRA = 1000          # random map points on top of one per keypoint (~3000 total)
+TH_LAST, TH_LOCAL = 15.0, 3.0
 METRIC = "frames/sec ORB extract+match 1280x720x8lvl"
+WORKLOAD = ("configs[1]: 1280x720 8-level 2000-feature ORB extract + SearchByProjection "
+            "(last frame th=15 + ~3000 local map points th=3), synthetic stream")
 
 
 def level_pixels():
@@ -41,13 +52,15 @@ def level_pixels():
 
 
 def make_frames(n, seed0):
+    """A synthetic stream: frame t+1 = frame t shifted by (dx,dy) in [-8,8]^2."""
     from orb_slam3_b200.synth import synth_frame, shifted_frame
     rng = np.random.default_rng(seed0)
-    frames = [synth_frame(H, W, seed0)]
+    frames, shifts = [synth_frame(H, W, seed0)], [(0, 0)]
     for t in range(1, n):
-        dx, dy = rng.integers(-8, 9, size=2)
-        frames.append(shifted_frame(frames[-1], int(dx), int(dy), seed0 * 1000 + t))
-    return np.stack(frames)
+        dx, dy = (int(v) for v in rng.integers(-8, 9, size=2))
+        frames.append(shifted_frame(frames[-1], dx, dy, seed0 * 1000 + t))
+        shifts.append((dx, dy))
+    return np.stack(frames), shifts
 
 
 class ClockSampler(threading.Thread):
@@ -73,11 +86,16 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.1)
 
     def summary(self):
-        sm = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        def num(v):
+            try:
+                return float(v)
+            except ValueError:
+                return None
+        sm = [num(r[1]) for r in self.rows if num(r[1]) is not None]
+        mx = [num(r[2]) for r in self.rows if num(r[2]) is not None]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
@@ -88,44 +106,264 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
-def cpu_reference_fps(frames, threads, seconds_budget=20.0):
-    """The oracle (CPU restatement of the reference path) on the host cores:
-    one extractor instance per std::thread, frames are independent (the
-    reference runs one thread per extractor, Frame.cc:122-125)."""
+# --------------------------------------------------------------------------- CPU arm
+def cpu_extract_fps(frames, threads, seconds_budget):
     from oracle import oracle as O
-    O.build()
-    fps1, _, dt1 = O.extract_throughput(frames, NFEAT, 1, 2)
+    fps1, _, _ = O.extract_throughput(frames, NFEAT, 1, 2)
     iters = int(min(64, max(2, seconds_budget * fps1)))
     return O.extract_throughput(frames, NFEAT, threads, iters)
 
 
+def cpu_match_seconds_per_frame(frames, shifts, n_pairs=3):
+    """Oracle matchers (one thread, like the Tracking thread) on a few frame pairs."""
+    from oracle import oracle as O
+    from orb_slam3_b200 import scenes
+    ex = O.OracleExtractor(NFEAT)
+    feats = [ex.extract(f)[:2] for f in frames[:n_pairs + 1]]
+    t_m = 0.0
+    for t in range(1, n_pairs + 1):
+        (ka, da), (kb, db) = feats[t - 1], feats[t]
+        cur, last, Tcw = scenes.last_frame_scene(ka, da, kb, db, W, H, shifts[t], seed=2 * t)
+        F, mps = scenes.local_map_scene(kb, db, W, H, N_LOCAL_EXTRA, seed=7 * t)
+        t1 = time.perf_counter()
+        O.match_project_last(cur, last, Tcw, TH_LAST)
+        O.match_project_local(F, mps, TH_LOCAL, 0.8)
+        t_m += time.perf_counter() - t1
+    return t_m / n_pairs
+
+
+def cpu_lba(K, L, seed=0):
+    from oracle import oracle as O
+    from orb_slam3_b200 import scenes
+    g, _ = scenes.lba_graph(K, L, seed=seed)
+    r = O.lba_solve(scenes.lba_view(g))
+    st = r["stats"]
+    return {"config": "%d KF x %d landmarks, %d edges" % (K, L, len(g["e_kf"])), "iterations": st["iterations"],
+            "trials": st["trials"], "seconds": st["ms_total"] / 1e3,
+            "value": st["trials"] / (st["ms_total"] / 1e3), "unit": "LM iterations/s", "threads": 1}
+
+
 def run_reference(args):
+    """The reference's own CPU implementation of the path: the oracle port (the
+    reference cannot be compiled here), all host threads for the per-frame work
+    (one extractor instance per thread), single thread for LBA like g2o."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from oracle import oracle as O
+    O.build()
     threads = os.cpu_count() or 1
-    frames = make_frames(8, 1)
+    frames, shifts = make_frames(8, 1)
     K, Wm = args.steps, args.warmup
-    # one step = a bounded sample: `threads` x per_thread frames
+    t_match = cpu_match_seconds_per_frame(frames, shifts)
     vals = []
     for i in range(Wm + K):
-        fps, done, dt = cpu_reference_fps(frames, threads, seconds_budget=1.0)
+        fps, done, dt = cpu_extract_fps(frames, threads, seconds_budget=1.0)
         if i >= Wm:
-            vals.append((fps, done, dt))
-    fps = sum(v[1] for v in vals) / sum(v[2] for v in vals)
+            vals.append((done, dt))
+    done = sum(v[0] for v in vals)
+    secs = sum(v[1] for v in vals)
+    # matching runs on the same threads: add its per-frame cost to each thread's frame time
+    t_ext_frame_thread = secs * threads / max(done, 1)
+    fps = threads / (t_ext_frame_thread + t_match)
+    lba = cpu_lba(50, 20000)
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
-        "steps": K, "warmup": Wm, "ms_per_step": 1e3 * sum(v[2] for v in vals) / K,
+        "steps": K, "warmup": Wm, "ms_per_step": 1e3 * secs / max(K, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
         "data": "synthetic",
-        "config": {"workload": "configs[1]: 1280x720 8-level 2000-feature ORB extract, synthetic stream",
-                   "frames_per_step": int(vals[0][1]), "stages": "extract"},
+        "config": {"workload": WORKLOAD, "frames_per_step": int(vals[0][0]) if vals else 0},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-                         "sample": "%d frames/step over %d threads (oracle C++ port, -O3 x86-64-v3)"
-                                   % (vals[0][1], threads)},
+                         "sample": "%d frames/step over %d std::threads (oracle C++ port, -O3 x86-64-v3); "
+                                   "extract %.2f ms + match %.2f ms per frame per thread"
+                                   % (vals[0][0] if vals else 0, threads, 1e3 * t_ext_frame_thread, 1e3 * t_match)},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "lba": lba,
     }
     print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- GPU arm
+class Workload:
+    """POOL distinct batches of B frames with everything the matchers need."""
+
+    def __init__(self, B, POOL, rank, device, stream):
+        import torch
+        from orb_slam3_b200 import scenes
+        from orb_slam3_b200.extractor import ORBextractor
+        from orb_slam3_b200.matcher import ORBmatcher
+        self.torch, self.B, self.POOL = torch, B, POOL
+        self.ext = ORBextractor(NFEAT, 1.2, NLEVELS, 20, 7, device=device)
+        self.m_last = ORBmatcher(0.9, True, device=device)
+        self.m_local = ORBmatcher(0.8, True, device=device)
+        self.stream = stream
+        for m in (self.m_last, self.m_local):
+            m.set_stream(stream)
+        cap = self.ext.cap
+        self.cap = cap
+        uniq, shifts = make_frames(min(B, 16) + 1, 1000 * rank + 1)
+        self.uniq = uniq
+        nu = len(uniq) - 1
+        self.host_pool, self.dev_pool, self.meta = [], [], []
+        self.sf = scenes.scale_factors()
+        self.sf2 = (self.sf * self.sf).astype(np.float32)
+        # one untimed extraction of the distinct frames (GPU) to build the match inputs
+        res = self.ext.extract_batch(list(uniq))
+        for p in range(POOL):
+            t = torch.empty((B, H, W), dtype=torch.uint8).pin_memory()
+            idx = [1 + (b + p) % nu for b in range(B)]        # frame idx[b]; its predecessor is idx[b]-1
+            for b in range(B):
+                t[b] = torch.from_numpy(uniq[idx[b]])
+            self.host_pool.append(t)
+            self.dev_pool.append(t.cuda())
+            entry = {"n": [], "cur": [], "last": [], "T": [], "F": [], "mps": [], "d_last": [], "d_mps": [],
+                     "d_taken": []}
+            for b in range(B):
+                i = idx[b]
+                _, kb, db = res[i]
+                _, ka, da = res[i - 1]
+                cur, last, Tcw = scenes.last_frame_scene(ka, da, kb, db, W, H, shifts[i], seed=2 * i)
+                F, mps = scenes.local_map_scene(kb, db, W, H, N_LOCAL_EXTRA, seed=7 * i)
+                entry["n"].append(len(kb))
+                entry["cur"].append(cur); entry["last"].append(last); entry["T"].append(Tcw)
+                entry["F"].append(F); entry["mps"].append(mps)
+                entry["d_last"].append({k: torch.from_numpy(np.ascontiguousarray(v)).cuda()
+                                        for k, v in last._keep.items()})
+                entry["d_mps"].append({k: torch.from_numpy(np.ascontiguousarray(v)).cuda()
+                                       for k, v in mps._keep.items()})
+                entry["d_taken"].append((torch.from_numpy(cur._keep[5]).cuda(), torch.from_numpy(F._keep[5]).cuda()))
+            entry["T"] = np.stack(entry["T"])
+            self.meta.append(entry)
+        self.d_assign_last = torch.empty((B, cap), dtype=torch.int32, device="cuda")
+        self.d_assign_local = torch.empty((B, cap), dtype=torch.int32, device="cuda")
+        self.out_k = torch.empty((B, cap * 28), dtype=torch.uint8).pin_memory()
+        self.out_d = torch.empty((B, cap * 32), dtype=torch.uint8).pin_memory()
+        self.out_n = np.zeros(B, np.int32)
+        self.out_m = np.zeros(B, np.int32)
+        self.nmatch_last = np.zeros(B, np.int32)
+        self.nmatch_local = np.zeros(B, np.int32)
+        self._dev_views = {}
+
+    # views whose frame side points at the extractor's device results (built once per pool entry)
+    def _device_views(self, p):
+        if p in self._dev_views:
+            return self._dev_views[p]
+        from orb_slam3_b200.views import orb_frame_view, orb_lastframe_view, orb_mappoint_view
+        kp, ds, _, _, cap = self.ext.device_results()
+        e = self.meta[p]
+        curs, lasts, Fs, Ms = [], [], [], []
+        for b in range(self.B):
+            for which, src, lst in ((0, e["cur"][b], curs), (1, e["F"][b], Fs)):
+                v = orb_frame_view()
+                C.memmove(C.byref(v), C.byref(src), C.sizeof(v))
+                v.n = e["n"][b]
+                v.keys = kp + b * cap * 28
+                v.desc = ds + b * cap * 32
+                v.u_right = None
+                v.kp_taken = e["d_taken"][b][which].data_ptr()
+                v.scale_factors, v.level_sigma2 = self.sf.ctypes.data, self.sf2.ctypes.data
+                lst.append(v)
+            lv = orb_lastframe_view()
+            lv.n = e["last"][b].n
+            for k in ("has_mp", "has_obs", "world_pos", "desc", "octave", "angle"):
+                setattr(lv, k, e["d_last"][b][k].data_ptr())
+            lasts.append(lv)
+            mv = orb_mappoint_view()
+            mv.n = e["mps"][b].n
+            for k in ("track_in_view", "is_bad", "has_obs", "proj_x", "proj_y", "proj_xr", "scale_level",
+                      "view_cos", "depth", "desc"):
+                setattr(mv, k, e["d_mps"][b][k].data_ptr())
+            Ms.append(mv)
+        a1 = [self.d_assign_last.data_ptr() + 4 * b * self.cap for b in range(self.B)]
+        a2 = [self.d_assign_local.data_ptr() + 4 * b * self.cap for b in range(self.B)]
+        self._dev_views[p] = (curs, lasts, Fs, Ms, a1, a2)
+        return self._dev_views[p]
+
+    def step_device(self, i):
+        p = i % self.POOL
+        d = self.dev_pool[p]
+        self.ext.extract_batch_device(d.data_ptr(), self.B, H, W, W, H * W, stream=self.stream)
+        curs, lasts, Fs, Ms, a1, a2 = self._device_views(p)
+        r1, _ = self.m_last.project_last_batch(curs, lasts, self.meta[p]["T"], TH_LAST, on_device=True,
+                                               assign_ptrs=a1)
+        r2, _ = self.m_local.project_local_batch(Fs, Ms, TH_LOCAL, on_device=True, assign_ptrs=a2)
+        self.nmatch_last, self.nmatch_local = r1, r2
+
+    def step_host(self, i):
+        from orb_slam3_b200._lib import check, ptr
+        from orb_slam3_b200.views import orb_frame_view
+        p = i % self.POOL
+        t = self.host_pool[p]
+        B, cap = self.B, self.cap
+        arr = (C.c_void_p * B)(*[t.data_ptr() + b * H * W for b in range(B)])
+        check(self.ext._lib.orb_extract_batch(self.ext._h, B, arr, H, W, W, None, C.c_void_p(self.out_k.data_ptr()),
+                                              C.c_void_p(self.out_d.data_ptr()), cap, ptr(self.out_n),
+                                              ptr(self.out_m)))
+        e = self.meta[p]
+        curs, Fs = [], []
+        for b in range(B):
+            for src, lst in ((e["cur"][b], curs), (e["F"][b], Fs)):
+                v = orb_frame_view()
+                C.memmove(C.byref(v), C.byref(src), C.sizeof(v))
+                v.n = int(self.out_n[b])
+                v.keys = self.out_k.data_ptr() + b * cap * 28      # the keypoints just downloaded
+                v.desc = self.out_d.data_ptr() + b * cap * 32
+                lst.append(v)
+        r1, _ = self.m_last.project_last_batch(curs, e["last"], e["T"], TH_LAST)
+        r2, _ = self.m_local.project_local_batch(Fs, e["mps"], TH_LOCAL)
+        self.nmatch_last, self.nmatch_local = r1, r2
+
+    def e2e_bytes(self):
+        e = self.meta[0]
+        h2d = self.B * H * W
+        d2h = int(self.B * (NFEAT + 4 * NLEVELS) * 60 + 8 * self.B)
+        for b in range(self.B):
+            n = e["n"][b]
+            h2d += 2 * n * 61 + e["last"][b].n * 50 + e["mps"][b].n * 59
+            d2h += 2 * n * 4
+        return h2d, d2h
+
+
+def run_lba_gpu(rank, world, device):
+    """LocalBA on the GPU: configs 4 and 5 at N=1, config 5 sharded by landmark for N>1."""
+    import torch
+    import torch.distributed as dist
+    from orb_slam3_b200 import scenes
+    from orb_slam3_b200.optimizer import LocalBundleAdjustment
+    out = {}
+    lba = LocalBundleAdjustment(device=device)
+    configs = [("config4", 50, 20000), ("config5", 200, 80000)] if world == 1 else [("config5", 200, 80000)]
+    if world > 1:
+        uid = [LocalBundleAdjustment.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        lba.init_comm(rank, world, uid[0])
+    for name, K, L in configs:
+        g, _ = scenes.lba_graph(K, L, seed=0)
+        sub = g if world == 1 else scenes.shard_graph(g, rank, world)[0]
+        gv = scenes.lba_view(sub)
+        best = None
+        for rep in range(4):  # the first run warms up allocations
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            st = lba(gv)["stats"]
+            if rep > 0 and (best is None or st["ms_total"] < best["ms_total"]):
+                best = st
+        ms = torch.tensor([best["ms_total"]], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms_total = float(ms.item())
+        out[name] = {
+            "config": "%d KF x %d landmarks, %d edges%s" % (K, L, len(g["e_kf"]),
+                                                            "" if world == 1 else ", landmark shards + ncclAllReduce"),
+            "iterations": best["iterations"], "trials": best["trials"], "ms_total": ms_total,
+            "value": best["trials"] / (ms_total * 1e-3), "unit": "LM iterations/s",
+            "chi2_initial": best["chi2_initial"], "chi2_final": best["chi2_final"],
+            "stage_ms": {k: best[k] for k in ("ms_linearize", "ms_schur", "ms_solve", "ms_update")},
+            "schur_gflops_sparse": best["schur_flops"] * best["trials"] / max(best["ms_schur"], 1e-9) / 1e6,
+            "n_pose_pairs": best["n_pairs"],
+        }
+    return out
 
 
 def main():
@@ -135,14 +373,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--batch", type=int, default=64, help="frames per step per GPU")
-    ap.add_argument("--pool", type=int, default=4, help="distinct batches rotated through (L2 defeat)")
+    ap.add_argument("--pool", type=int, default=3, help="distinct batches rotated through (L2 defeat)")
+    ap.add_argument("--no-lba", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
     import torch
     import torch.distributed as dist
-    from orb_slam3_b200.extractor import ORBextractor
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -154,39 +393,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     B, K, Wm, POOL = args.batch, args.steps, max(args.warmup, 3), args.pool
 
-    # ---- synthetic streams: POOL distinct batches of B frames (this rank's cameras)
-    uniq = make_frames(min(B, 16), 1000 * rank + 1)
-    host_pool = []
-    for p in range(POOL):
-        t = torch.empty((B, H, W), dtype=torch.uint8).pin_memory()
-        for b in range(B):
-            src = uniq[(b + p) % len(uniq)]
-            t[b] = torch.from_numpy(np.roll(src, (p * 7 + b // len(uniq), b // len(uniq) * 3), (0, 1)).copy())
-        host_pool.append(t)
-    dev_pool = [t.cuda() for t in host_pool]
-    ext = ORBextractor(NFEAT, 1.2, NLEVELS, 20, 7, device=local_rank)
-    ext._lib.orb_extract_batch_device  # noqa: B018  (fail early if the ABI is missing)
-    tstream = torch.cuda.Stream()  # non-default stream so the engine launches where the events are recorded
+    tstream = torch.cuda.Stream()  # non-default stream: the engines launch where the events are recorded
     torch.cuda.set_stream(tstream)
-    stream = tstream.cuda_stream
-
-    def step_device(i):
-        d = dev_pool[i % POOL]
-        ext.extract_batch_device(d.data_ptr(), B, H, W, W, H * W, stream=stream)
-
-    cap = ext.cap
-    from orb_slam3_b200._lib import KP_DTYPE, check, ptr
-    import ctypes as C
-    out_k = torch.empty((B, cap * 28), dtype=torch.uint8).pin_memory()
-    out_d = torch.empty((B, cap * 32), dtype=torch.uint8).pin_memory()
-    out_n = np.zeros(B, np.int32)
-    out_m = np.zeros(B, np.int32)
-
-    def step_host(i):
-        t = host_pool[i % POOL]
-        arr = (C.c_void_p * B)(*[t.data_ptr() + b * H * W for b in range(B)])
-        check(ext._lib.orb_extract_batch(ext._h, B, arr, H, W, W, None, C.c_void_p(out_k.data_ptr()),
-                                         C.c_void_p(out_d.data_ptr()), cap, ptr(out_n), ptr(out_m)))
+    wl = Workload(B, POOL, rank, local_rank, tstream.cuda_stream)
 
     def barrier():
         torch.cuda.synchronize()
@@ -194,52 +403,58 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, k):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(k):
-            fn(i)
-        e1.record()
-        ext.synchronize()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        return ms
+    def launches_now():
+        return wl.ext.kernel_launches() + wl.m_last.kernel_launches() + wl.m_local.kernel_launches()
 
     # ---- device-resident metric
     for i in range(Wm):
-        step_device(i)
-    launches0 = ext.kernel_launches()
+        wl.step_device(i)
+    launches0 = launches_now()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ms_dev = timed(step_device, K)
-    launches = ext.kernel_launches() - launches0
-    # ---- end to end through the host-buffer ABI (wall clock brackets the D2H sync)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        wl.step_device(i)
+    e1.record()
+    barrier()
+    ms_dev = e0.elapsed_time(e1)
+    launches = launches_now() - launches0
+    nm_last, nm_local = int(wl.nmatch_last.sum()), int(wl.nmatch_local.sum())
+    # ---- end to end through the host-buffer ABI (wall clock brackets every copy and sync)
     for i in range(Wm):
-        step_host(i)
+        wl.step_host(i)
     barrier()
     t0 = time.perf_counter()
     for i in range(K):
-        step_host(i)
+        wl.step_host(i)
     barrier()
     ms_e2e = (time.perf_counter() - t0) * 1e3
     sampler.stop_flag = True
     sampler.join(timeout=2)
-    nkp = int(out_n.sum())
+    nkp = int(wl.out_n.sum())
 
     # ---- per-kernel times for the roofline (events around each launch; separate pass)
-    ext.set_profiling(True)
-    ext.stage_times(reset=True)
+    wl.ext.set_profiling(True)
+    wl.ext.stage_times(reset=True)
+    ms_match = [0.0, 0.0]
     for i in range(K):
-        step_device(i)
-    ext.synchronize()
-    st = ext.stage_times(reset=True)
-    ext.set_profiling(False)
+        wl.step_device(i)
+        ms_match[0] += wl.m_last.last_ms()
+        ms_match[1] += wl.m_local.last_ms()
+    wl.ext.synchronize()
+    st = wl.ext.stage_times(reset=True)
+    wl.ext.set_profiling(False)
 
     tens = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tens, op=dist.ReduceOp.MAX)
     ms_dev, ms_e2e = tens.tolist()
+
+    lba = None
+    if not args.no_lba:
+        lba = run_lba_gpu(rank, world, local_rank)
 
     if rank == 0:
         peaks = {}
@@ -248,50 +463,72 @@ def main():
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback"
+        peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
         P = sum(level_pixels())
+        n_mp = NFEAT + N_LOCAL_EXTRA
         # algorithmic bytes per frame and per kernel (DESIGN.md "Kernels")
         alg = {
-            "pyramid": W * H + (P - W * H),          # read level 0, write levels 1..7
-            "fast": P + 0,                           # one read of the pyramid
-            "blur": 2 * P,                           # read + write blurred pyramid
-            "octree": 38000 * 8,                     # candidate records
+            "pyramid": W * H + (P - W * H),           # read level 0, write levels 1..7
+            "fast": P,                                # one read of the pyramid
+            "blur": 2 * P,                            # read + write blurred pyramid
+            "octree": 38000 * 8,                      # candidate records in
             "describe": NFEAT * (28 + 32) + NFEAT * (31 * 31 + 512),
         }
         kern = {k: v for k, v in st.items() if k in alg and v[1] > 0}
+
+        def per_launch_ms(k):
+            n_l = kern[k][1] if k != "pyramid" else kern[k][1] / (NLEVELS - 1)
+            return kern[k][0] / n_l
+
         dom = max(kern, key=lambda k: kern[k][0])
-        dom_ms_per_launch = kern[dom][0] / (kern[dom][1] if dom != "pyramid" else kern[dom][1] / (NLEVELS - 1))
-        achieved = alg[dom] * B / (dom_ms_per_launch * 1e-3) / 1e9
-        total_ms = sum(v[0] for v in kern.values())
+        achieved = alg[dom] * B / (per_launch_ms(dom) * 1e-3) / 1e9
+        total_ms = sum(v[0] for v in kern.values()) + sum(ms_match)
         fps_dev = world * B * K / (ms_dev * 1e-3)
         fps_e2e = world * B * K / (ms_e2e * 1e-3)
-        # bounded CPU sample on rank 0 at N=1
+        stage = {k: v[0] / K for k, v in st.items()}
+        stage["match_last(th15)"] = ms_match[0] / K
+        stage["match_local(th3)"] = ms_match[1] / K
+        per_kernel = {}
+        for k in kern:
+            gbs = alg[k] * B / (per_launch_ms(k) * 1e-3) / 1e9
+            per_kernel[k] = {"GB/s": gbs, "frac_of_hbm": gbs / hbm_peak}
+        b_match = (NFEAT + n_mp) * 32 + NFEAT * 16 + n_mp * 24 + 64 * 48 * 4 + NFEAT * 4
+        gbs = b_match * B / (max(ms_match[1], 1e-9) / K * 1e-3) / 1e9
+        per_kernel["match_local"] = {"GB/s": gbs, "frac_of_hbm": gbs / hbm_peak}
         cpu = None
-        if world == 1:
+        if world == 1 and not args.no_cpu:
+            from oracle import oracle as O
+            O.build()
             threads = os.cpu_count() or 1
-            fps_cpu, done, dt = cpu_reference_fps(uniq, threads, seconds_budget=10.0)
-            fps_1, done1, dt1 = cpu_reference_fps(uniq, 1, seconds_budget=4.0)
-            cpu = {"value": fps_cpu, "unit": "frames/s", "cores": threads, "kind": "port",
-                   "sample": "%d frames over %d threads in %.1fs; single thread: %.1f frames/s"
-                             % (done, threads, dt, fps_1)}
+            fps_cpu, done, dt = cpu_extract_fps(wl.uniq[:8], threads, seconds_budget=8.0)
+            fps_1, _, _ = cpu_extract_fps(wl.uniq[:8], 1, seconds_budget=3.0)
+            t_match = cpu_match_seconds_per_frame(*make_frames(4, 1))
+            t_ext = threads / fps_cpu
+            cpu = {"value": threads / (t_ext + t_match), "unit": "frames/s", "cores": threads, "kind": "port",
+                   "sample": "extract: %d frames over %d std::threads in %.1fs (%.1f frames/s; 1 thread %.1f frames/s); "
+                             "match: %.2f ms/frame/thread (oracle C++ port)" % (done, threads, dt, fps_cpu, fps_1,
+                                                                               1e3 * t_match)}
+            if lba is not None:
+                lba["cpu_baseline_config4"] = cpu_lba(50, 20000)
+        h2d, d2h = wl.e2e_bytes()
         line = {
             "metric": METRIC, "value": fps_dev, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "configs[1]: 1280x720 8-level 2000-feature ORB extract, synthetic stream",
-                       "frames_per_step_per_gpu": B, "stages": "extract",
+            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B,
                        "l2": "inputs+pyramids %.0f MB per rotation > 126 MB L2 (%d batches rotated)"
                              % (POOL * B * (W * H + 2 * P) / 1e6, POOL),
-                       "keypoints_last_step": nkp},
-            "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": B * H * W,
-                    "d2h_bytes_per_step": int(B * (NFEAT + 4 * NLEVELS) * 60 + 8 * B)},
+                       "keypoints_last_step": nkp, "matches_last_step": {"last": nm_last, "local": nm_local}},
+            "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                         "share_of_step": kern[dom][0] / total_ms,
-                         "stage_ms_per_step": {k: v[0] / K for k, v in st.items()}},
+                         "share_of_step": kern[dom][0] / total_ms, "stage_ms_per_step": stage,
+                         "per_kernel": per_kernel},
             "cpu_baseline": cpu,
+            "lba": lba,
         }
         print(json.dumps(line))
     if world > 1:

@@ -218,6 +218,9 @@ int match_triangulate_batch(orb_matcher* m, int count, const orb_frame_view* kf1
                             const orb_featvec_view* fv1, const orb_featvec_view* fv2, const float* F12_rowmajor9,
                             const float* ep2, int only_stereo, int coarse, int check_orientation,
                             int32_t* const* pairs_out, int cap, int32_t* results, int on_device);
+/* Submit subsequent batches on `cuda_stream` (a cudaStream_t) instead of the
+ * matcher's own stream, e.g. the stream an extractor ran on; NULL restores it. */
+int match_set_stream(orb_matcher* m, void* cuda_stream);
 int match_synchronize(orb_matcher* m);
 long long match_kernel_launches(const orb_matcher* m);
 /* Device time of the last batch (CUDA events on the matcher's stream), ms. */

@@ -570,7 +570,7 @@ struct Pinned {
 struct Matcher {
   int device = 0;
   bool initialized = false;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, user_stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   Arena in_arena, scratch, out_arena;
   Pinned h_in, h_out;
@@ -735,7 +735,7 @@ static int run_projection(Matcher& M, int count, int kind, const orb_frame_view*
         p.assign = carve_dev<int>(M.out_arena, nk);
       }
     }
-    cudaStream_t s = M.stream;
+    cudaStream_t s = M.user_stream ? M.user_stream : M.stream;
     CUDA_TRYM(cudaEventRecord(M.ev0, s));
     if (!on_device && in_bytes)
       CUDA_TRYM(cudaMemcpyAsync(M.in_arena.d, M.h_in.h, in_bytes, cudaMemcpyHostToDevice, s));
@@ -841,7 +841,7 @@ static int run_triangulate(Matcher& M, int count, const orb_frame_view* kf1, con
     if (on_device) p.pairs = pairs_out[k];
     else { pair_off[k] = M.out_arena.used; p.pairs = carve_dev<int>(M.out_arena, 2 * (size_t)cap); }
   }
-  cudaStream_t s = M.stream;
+  cudaStream_t s = M.user_stream ? M.user_stream : M.stream;
   CUDA_TRYM(cudaEventRecord(M.ev0, s));
   if (in_bytes) CUDA_TRYM(cudaMemcpyAsync(M.in_arena.d, M.h_in.h, in_bytes, cudaMemcpyHostToDevice, s));
   CUDA_TRYM(cudaMemcpyAsync(d_probs, P.data(), sizeof(TriProblem) * count, cudaMemcpyHostToDevice, s));
@@ -951,10 +951,16 @@ int match_triangulate_batch(orb_matcher* m, int count, const orb_frame_view* kf1
                                   check_orientation, pairs_out, cap, results, on_device);
 }
 
+int match_set_stream(orb_matcher* m, void* cuda_stream) {
+  if (!m) return ORB_E_ARG;
+  m->m.user_stream = (cudaStream_t)cuda_stream;
+  return ORB_OK;
+}
+
 int match_synchronize(orb_matcher* m) {
   if (!m || !m->m.initialized) return ORB_E_ARG;
   cudaSetDevice(m->m.device);
-  return cudaStreamSynchronize(m->m.stream) == cudaSuccess ? ORB_OK : ORB_E_CUDA;
+  return cudaStreamSynchronize(m->m.user_stream ? m->m.user_stream : m->m.stream) == cudaSuccess ? ORB_OK : ORB_E_CUDA;
 }
 long long match_kernel_launches(const orb_matcher* m) { return m ? m->m.launches : 0; }
 double match_last_ms(orb_matcher* m) { return m ? m->m.last_ms : 0.0; }

@@ -115,6 +115,9 @@ class ORBmatcher:
                                                 int(bCoarse), int(self.mbCheckOrientation), arr, cap, ptr(res), 0))
         return res, [o[:r] for o, r in zip(outs, res)]
 
+    def set_stream(self, cuda_stream):
+        check(self._lib.match_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
+
     def last_ms(self):
         return float(self._lib.match_last_ms(self._h))
 

@@ -139,6 +139,14 @@ def _quat_rot(q, v):
     return v + q[3] * u + np.cross(q[:3], u)
 
 
+def _qrot_many(q, v):
+    """Rotate v[...,3] by quaternions q[...,4] (x,y,z,w), broadcasting."""
+    qv = q[..., :3]
+    u = np.cross(qv, v)
+    u = u + u
+    return v + q[..., 3:4] * u + np.cross(qv, u)
+
+
 def lba_graph(n_kf_opt, n_mp, seed=0, fixed_frac=0.1, stereo_frac=0.8, outlier_frac=0.02,
               width=1280, height=720, fx=700.0, bf=386.0):
     """Synthetic LocalBundleAdjustment graph: K optimisable
@@ -149,60 +157,65 @@ def lba_graph(n_kf_opt, n_mp, seed=0, fixed_frac=0.1, stereo_frac=0.8, outlier_f
     n_fixed = int(np.ceil(n_kf_opt * fixed_frac))
     K = n_kf_opt + n_fixed
     cx, cy = width / 2.0, height / 2.0
-    # world-from-camera poses along +z with yaw drift; Tcw = inverse
-    Twc_q, Twc_t = [], []
-    for k in range(K):
-        yaw = 0.01 * k + 0.05 * np.sin(0.3 * k)
-        Twc_q.append(_quat_from_yaw_pitch(yaw, 0.01 * np.cos(0.2 * k)))
-        Twc_t.append(np.array([0.3 * np.sin(0.1 * k), 0.02 * k % 0.3, 1.0 * k]))
+    k_idx = np.arange(K)
+    Twc_q = np.stack([_quat_from_yaw_pitch(0.01 * k + 0.05 * np.sin(0.3 * k), 0.01 * np.cos(0.2 * k)) for k in k_idx])
+    Twc_t = np.stack([0.3 * np.sin(0.1 * k_idx), (0.02 * k_idx) % 0.3, 1.0 * k_idx], 1)
     Tcw = np.zeros((K, 7))
-    for k in range(K):
-        qi = Twc_q[k] * np.array([-1, -1, -1, 1])
-        Tcw[k, :4] = qi
-        Tcw[k, 4:] = -_quat_rot(qi, Twc_t[k])
-    # fixed KFs are the oldest ones (they see local points but are not local KFs)
+    Tcw[:, :4] = Twc_q * np.array([-1, -1, -1, 1])
+    Tcw[:, 4:] = -_qrot_many(Tcw[:, :4], Twc_t)
     fixed = np.zeros(K, np.uint8)
-    fixed[:n_fixed] = 1
-    e_kf, e_mp, e_st, e_obs, e_is2 = [], [], [], [], []
-    pts = np.zeros((n_mp, 3))
+    fixed[:n_fixed] = 1  # the oldest KFs see local points but are not local KFs
     inv_sigma2 = (1.0 / (scale_factors() ** 2)).astype(np.float32)
-    l = 0
-    attempts = 0
-    while l < n_mp and attempts < 50 * n_mp:
-        attempts += 1
-        k0 = int(rng.integers(0, K))
-        depth = rng.uniform(4, 40)
-        u, v = rng.uniform(40, width - 40), rng.uniform(40, height - 40)
-        Xc = np.array([(u - cx) / fx * depth, (v - cy) / fx * depth, depth])
-        Xw = _quat_rot(Twc_q[k0], Xc) + Twc_t[k0]
-        m = int(rng.integers(3, 11))
-        obs = []
-        for k in range(max(0, k0 - 7), min(K, k0 + 8)):
-            Xk = _quat_rot(Tcw[k, :4], Xw) + Tcw[k, 4:]
-            if Xk[2] < 1.0:
-                continue
-            uu, vv = fx * Xk[0] / Xk[2] + cx, fx * Xk[1] / Xk[2] + cy
-            if 0 <= uu < width and 0 <= vv < height:
-                obs.append((k, uu, vv, Xk[2]))
-        if len(obs) < 3 or all(fixed[o[0]] for o in obs):
-            continue
-        if len(obs) > m:
-            sel = sorted(rng.choice(len(obs), m, replace=False))
-            obs = [obs[i] for i in sel]
-        pts[l] = Xw
-        for (k, uu, vv, zz) in obs:
-            octv = int(rng.integers(0, 8))
-            sig = 1.2 ** octv
-            nu, nv, nr = rng.normal(0, 1, 3) * sig
-            if rng.random() < outlier_frac:
-                nu += rng.choice([-50, 50])
-            st = rng.random() < stereo_frac
-            e_kf.append(k); e_mp.append(l); e_st.append(1 if st else 0)
-            e_obs.append((np.float32(uu + nu), np.float32(vv + nv), np.float32(uu - bf / zz + nr) if st else -1.0))
-            e_is2.append(inv_sigma2[octv])
-        l += 1
-    n_mp = l
-    pts = pts[:n_mp]
+
+    pts_l, ekf_l, emp_l = [], [], []
+    have = 0
+    while have < n_mp:
+        m_try = int((n_mp - have) * 1.3) + 64
+        k0 = rng.integers(0, K, m_try)
+        depth = rng.uniform(4, 40, m_try)
+        u = rng.uniform(40, width - 40, m_try)
+        v = rng.uniform(40, height - 40, m_try)
+        Xc = np.stack([(u - cx) / fx * depth, (v - cy) / fx * depth, depth], 1)
+        Xw = _qrot_many(Twc_q[k0], Xc) + Twc_t[k0]
+        offs = np.arange(-7, 8)
+        kk = k0[:, None] + offs[None, :]                      # candidate observers (window)
+        inb = (kk >= 0) & (kk < K)
+        kc = np.clip(kk, 0, K - 1)
+        Xk = _qrot_many(Tcw[kc, :4], Xw[:, None, :]) + Tcw[kc, 4:]
+        zz = Xk[..., 2]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            uu = fx * Xk[..., 0] / zz + cx
+            vv = fx * Xk[..., 1] / zz + cy
+        vis = inb & (zz >= 1.0) & (uu >= 0) & (uu < width) & (vv >= 0) & (vv < height)
+        want = rng.integers(3, 11, m_try)
+        pri = np.where(vis, rng.random(vis.shape), 2.0)        # keep `want` random visible observers
+        rank = np.argsort(np.argsort(pri, axis=1), axis=1)
+        keep = vis & (rank < want[:, None])
+        nobs = keep.sum(1)
+        free_seen = (keep & (fixed[kc] == 0)).any(1)
+        ok = np.nonzero((nobs >= 3) & free_seen)[0][: n_mp - have]
+        for j, l_src in enumerate(ok):
+            ks = kc[l_src][keep[l_src]]
+            ekf_l.append(ks)
+            emp_l.append(np.full(len(ks), have + j))
+        pts_l.append(Xw[ok])
+        have += len(ok)
+    pts = np.concatenate(pts_l)
+    e_kf = np.concatenate(ekf_l).astype(np.int32)
+    e_mp = np.concatenate(emp_l).astype(np.int32)
+    E = len(e_kf)
+    Xk = _qrot_many(Tcw[e_kf, :4], pts[e_mp]) + Tcw[e_kf, 4:]
+    uu = fx * Xk[:, 0] / Xk[:, 2] + cx
+    vv = fx * Xk[:, 1] / Xk[:, 2] + cy
+    octv = rng.integers(0, 8, E)
+    sig = 1.2 ** octv
+    noise = rng.normal(0, 1, (E, 3)) * sig[:, None]
+    out = rng.random(E) < outlier_frac
+    noise[out, 0] += rng.choice([-50.0, 50.0], out.sum())
+    e_st = (rng.random(E) < stereo_frac).astype(np.uint8)
+    ur = np.where(e_st == 1, (uu - bf / Xk[:, 2] + noise[:, 2]).astype(np.float32), np.float32(-1.0))
+    e_obs = np.stack([(uu + noise[:, 0]).astype(np.float32), (vv + noise[:, 1]).astype(np.float32), ur], 1).astype(np.float64)
+    e_is2 = inv_sigma2[octv]
     truth = dict(kf_pose=Tcw.copy(), mp_pos=pts.copy())
     # initial perturbation: poses 2 cm / 0.5 deg (free KFs only), points 5 cm
     pose0 = Tcw.copy()
@@ -218,9 +231,17 @@ def lba_graph(n_kf_opt, n_mp, seed=0, fixed_frac=0.1, stereo_frac=0.8, outlier_f
     pose0 = pose0.astype(np.float32).astype(np.float64)
     pts0 = (pts + rng.normal(0, 0.05 / np.sqrt(3), pts.shape)).astype(np.float32).astype(np.float64)
     cam = np.tile(np.array([fx, fx, cx, cy, bf], np.float32), (K, 1))
-    g = dict(kf_pose=pose0, kf_fixed=fixed, kf_cam=cam, mp_pos=pts0, e_kf=np.array(e_kf, np.int32),
-             e_mp=np.array(e_mp, np.int32), e_stereo=np.array(e_st, np.uint8),
-             e_obs=np.array(e_obs, np.float64), e_inv_sigma2=np.array(e_is2, np.float32))
+    g = dict(kf_pose=pose0, kf_fixed=fixed, kf_cam=cam, mp_pos=pts0, e_kf=e_kf, e_mp=e_mp, e_stereo=e_st,
+             e_obs=e_obs, e_inv_sigma2=e_is2.astype(np.float32))
+    return g, truth
+
+
+def lba_rough_graph(seed=4):
+    """Small graph with a wild start and almost no damping: forces rejected LM trials."""
+    g, truth = lba_graph(5, 60, seed=seed)
+    rng = np.random.default_rng(seed)
+    g["mp_pos"] = g["mp_pos"] + rng.normal(0, 5.0, g["mp_pos"].shape)
+    g["kf_pose"][:, 4:] += rng.normal(0, 0.3, (len(g["kf_pose"]), 3)) * (g["kf_fixed"][:, None] == 0)
     return g, truth
 
 

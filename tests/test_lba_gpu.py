@@ -55,10 +55,7 @@ def test_lba_config4_50kf_20k_landmarks(oracle, lba):
 
 
 def test_lba_rejected_trials_and_user_lambda(oracle, lba):
-    g, _ = scenes.lba_graph(5, 60, seed=3)
-    rng = np.random.default_rng(3)
-    g["mp_pos"] = g["mp_pos"] + rng.normal(0, 5.0, g["mp_pos"].shape)
-    g["kf_pose"][:, 4:] += rng.normal(0, 0.3, (len(g["kf_pose"]), 3)) * (g["kf_fixed"][:, None] == 0)
+    g, _ = scenes.lba_rough_graph(4)
     gv = scenes.lba_view(g)
     ref = oracle.lba_solve(gv, max_iters=4, lambda_init=1e-8)
     got = lba(gv, max_iters=4, lambda_init=1e-8)
