@@ -88,3 +88,19 @@ def test_lba_stop_flag_and_fixed_poses(oracle, lba):
     r2 = lba(scenes.lba_view(g2))
     assert np.allclose(r2["mp_pos"], r["mp_pos"], rtol=0, atol=1e-9)
     assert np.allclose(r2["chi2"], r["chi2"][perm], rtol=1e-9, atol=1e-9)
+
+
+def test_lba_landmark_shards_over_nccl_match_single_gpu():
+    """Needs >= 2 GPUs: the sharded solve (one ncclAllReduce of [S | b_s] per trial) equals the 1-GPU solve."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs 2 GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(here, "multi_gpu_lba_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "MULTI_GPU_LBA_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
