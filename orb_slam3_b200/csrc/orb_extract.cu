@@ -184,44 +184,84 @@ __device__ __forceinline__ int fast_best(const uint8_t* __restrict__ c, int pitc
 // One CTA per FAST cell of ComputeKeyPointsOctTree (ORBextractor.cc:805-872):
 // score map at minTh in shared memory, 3x3 strict NMS inside the cell's band,
 // keep score>=iniTh survivors, or all survivors when there is none.
+//   1. the cell tile comes in as aligned 32-bit words (one warp per row);
+//   2. every band pixel takes the cheap two-diameter rejection test; the few that
+//      pass are compacted into a shared-memory queue (ballot + popc), so
+//   3. the full 16-ring score and 4. the NMS / emission only ever run on dense
+//      queues -- no warp drags 31 rejected lanes through the expensive path.
 constexpr int FAST_THREADS = 128;
-constexpr int FAST_TILE_MAX = 80;  // wCell+6 <= 75
+constexpr int FAST_TILE_MAX = 80;    // rows: hCell+6 <= 76
+constexpr int FAST_TILE_PITCH = 84;  // bytes, 21 words: (x0&3) + wCell+6 <= 79
+constexpr int FAST_BAND_MAX = 70;
 
 __global__ void __launch_bounds__(FAST_THREADS)
 fast_cells_kernel(const uint8_t* __restrict__ pyr, size_t frame_stride,
                   const CellDesc* __restrict__ cells, const LevelDev* __restrict__ lv, int ini_th,
                   int min_th, Cand* __restrict__ cand, size_t cand_frame_stride,
                   int* __restrict__ cand_count, int nlevels) {
-  __shared__ uint8_t tile[FAST_TILE_MAX * FAST_TILE_MAX];
-  __shared__ uint8_t smap[(FAST_TILE_MAX - 4) * (FAST_TILE_MAX - 4)];
-  __shared__ int s_cnt_ini, s_cnt_all, s_base;
+  __shared__ __align__(16) uint8_t tile[FAST_TILE_MAX * FAST_TILE_PITCH];
+  __shared__ __align__(16) uint8_t smap[(FAST_BAND_MAX + 2) * (FAST_BAND_MAX + 2) + 8];
+  __shared__ unsigned short queue[FAST_BAND_MAX * FAST_BAND_MAX];
+  __shared__ int s_qn, s_cnt_ini, s_cnt_all, s_base;
   const CellDesc cd = cells[blockIdx.x];
   const LevelDev L = lv[cd.level];
   const int f = blockIdx.y;
   const uint8_t* img = pyr + (size_t)f * frame_stride + L.img_off;
   const int tw = cd.x1 - cd.x0, th = cd.y1 - cd.y0;
   const int bw = tw - 6, bh = th - 6;
-  const int sw = bw + 2;
-  if (threadIdx.x == 0) { s_cnt_ini = 0; s_cnt_all = 0; }
-  for (int i = threadIdx.x; i < tw * th; i += FAST_THREADS) {
-    const int y = i / tw, x = i - y * tw;
-    tile[y * FAST_TILE_MAX + x] = img[(size_t)(cd.y0 + y) * L.pitch + cd.x0 + x];
-  }
-  for (int i = threadIdx.x; i < (bw + 2) * (bh + 2); i += FAST_THREADS) smap[i] = 0;
-  __syncthreads();
   if (bw <= 0 || bh <= 0) return;
-  for (int i = threadIdx.x; i < bw * bh; i += FAST_THREADS) {
-    const int y = i / bw, x = i - y * bw;
-    const int best = fast_best(&tile[(y + 3) * FAST_TILE_MAX + x + 3], FAST_TILE_MAX, min_th);
+  const int sw = bw + 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { s_qn = 0; s_cnt_ini = 0; s_cnt_all = 0; }
+  // 1. tile load, aligned words
+  const int ox = cd.x0 & 3;
+  const int nw = (ox + tw + 3) >> 2;
+  {
+    const uint8_t* src = img + (size_t)cd.y0 * L.pitch + (cd.x0 & ~3);
+    for (int r = warp; r < th; r += FAST_THREADS / 32)
+      if (lane < nw)
+        reinterpret_cast<uint32_t*>(tile)[r * (FAST_TILE_PITCH / 4) + lane] =
+            *reinterpret_cast<const uint32_t*>(src + (size_t)r * L.pitch + 4 * lane);
+    const int nz = ((bw + 2) * (bh + 2) + 3) >> 2;
+    for (int i = threadIdx.x; i < nz; i += FAST_THREADS) reinterpret_cast<uint32_t*>(smap)[i] = 0;
+  }
+  __syncthreads();
+  // 2. cheap rejection + compaction (a 9-arc contains one end of every diameter)
+  for (int y = warp; y < bh; y += FAST_THREADS / 32) {
+    for (int x0 = 0; x0 < bw; x0 += 32) {
+      const int x = x0 + lane;
+      bool pass = false;
+      if (x < bw) {
+        const uint8_t* c = &tile[(y + 3) * FAST_TILE_PITCH + ox + x + 3];
+        const int v = c[0], hi = v + min_th, lo = v - min_th;
+        const int r0 = c[3 * FAST_TILE_PITCH], r8 = c[-3 * FAST_TILE_PITCH], r4 = c[3], r12 = c[-3];
+        const bool bp = ((r0 > hi) | (r8 > hi)) & ((r4 > hi) | (r12 > hi));
+        const bool dp = ((r0 < lo) | (r8 < lo)) & ((r4 < lo) | (r12 < lo));
+        pass = bp | dp;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, pass);
+      if (m) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&s_qn, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (pass) queue[base + __popc(m & ((1u << lane) - 1))] = (unsigned short)((y << 8) | x);
+      }
+    }
+  }
+  __syncthreads();
+  const int qn = s_qn;
+  // 3. full FAST-9/16 score of the queued pixels
+  for (int q = threadIdx.x; q < qn; q += FAST_THREADS) {
+    const int e = queue[q], y = e >> 8, x = e & 255;
+    const int best = fast_best(&tile[(y + 3) * FAST_TILE_PITCH + ox + x + 3], FAST_TILE_PITCH, min_th);
     smap[(y + 1) * sw + x + 1] = (uint8_t)best;
   }
   __syncthreads();
-  // NMS; a thread remembers its survivors as one bit per visited pixel
-  // (<= 70*70/128 = 39 visits)
+  // 4. NMS on the queue; a thread remembers its survivors as one bit per visit (<= 4900/128 = 39)
   unsigned long long keep_bits = 0, ini_bits = 0;
   int it = 0;
-  for (int i = threadIdx.x; i < bw * bh; i += FAST_THREADS, it++) {
-    const int y = i / bw, x = i - y * bw;
+  for (int q = threadIdx.x; q < qn; q += FAST_THREADS, it++) {
+    const int e = queue[q], y = e >> 8, x = e & 255;
     const uint8_t* p = &smap[(y + 1) * sw + x + 1];
     const int s = p[0];
     if (s && s > p[-1] && s > p[1] && s > p[-sw - 1] && s > p[-sw] && s > p[-sw + 1] &&
@@ -244,9 +284,9 @@ fast_cells_kernel(const uint8_t* __restrict__ pyr, size_t frame_stride,
   // the order inside the level's list is irrelevant (the octree uses order keys)
   Cand* out = cand + (size_t)f * cand_frame_stride + L.cand_off;
   it = 0;
-  for (int i = threadIdx.x; i < bw * bh; i += FAST_THREADS, it++) {
+  for (int q = threadIdx.x; q < qn; q += FAST_THREADS, it++) {
     if (!(bits & (1ull << it))) continue;
-    const int y = i / bw, x = i - y * bw;
+    const int e = queue[q], y = e >> 8, x = e & 255;
     const int pos = atomicAdd(&s_base, 1);
     if (pos < L.cand_cap) {
       Cand c;
@@ -312,44 +352,79 @@ octree_kernel(const Cand* __restrict__ cand, size_t cand_frame_stride, const int
 }
 
 // GaussianBlur 7x7 sigma 2 over every level of every frame.
-constexpr int BLUR_TW = 128, BLUR_TH = 16;
+// 128x32 output tile per CTA; aligned 32-bit loads, 4 pixels per thread in both
+// passes, one coalesced 32-bit store per thread.
+constexpr int BLUR_TW = 128, BLUR_TH = 32;
+constexpr int BLUR_IW = BLUR_TW + 8;  // bytes per staged input row: [x0-4, x0+TW+4)
+
+__device__ __forceinline__ int reflect101(int p, int n) {
+  if (p < 0) p = -p;
+  if (p >= n) p = 2 * n - 2 - p;
+  return min(max(p, 0), n - 1);
+}
 
 __global__ void __launch_bounds__(256)
 blur_kernel(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blr, size_t frame_stride,
             const BlurTile* __restrict__ tiles, const LevelDev* __restrict__ lv) {
-  __shared__ uint8_t in[(BLUR_TH + 6) * (BLUR_TW + 8)];
-  __shared__ uint16_t hb[(BLUR_TH + 6) * BLUR_TW];
+  __shared__ __align__(16) uint8_t in[(BLUR_TH + 6) * BLUR_IW];
+  __shared__ __align__(16) uint16_t hb[(BLUR_TH + 6) * BLUR_TW];
   const BlurTile t = tiles[blockIdx.x];
   const LevelDev L = lv[t.level];
   const uint8_t* src = pyr + (size_t)blockIdx.y * frame_stride + L.img_off;
   uint8_t* dst = blr + (size_t)blockIdx.y * frame_stride + L.img_off;
   const int w = L.w, h = L.h;
-  const int IW = BLUR_TW + 8;
-  for (int i = threadIdx.x; i < (BLUR_TH + 6) * (BLUR_TW + 6); i += 256) {
-    const int ly = i / (BLUR_TW + 6), lx = i - ly * (BLUR_TW + 6);
-    int gx = t.x0 + lx - 3, gy = t.y0 + ly - 3;
-    // BORDER_REFLECT_101 at the true image edge
-    if (gx < 0) gx = -gx; if (gx >= w) gx = 2 * w - 2 - gx;
-    if (gy < 0) gy = -gy; if (gy >= h) gy = 2 * h - 2 - gy;
-    gx = min(max(gx, 0), w - 1);  // tiles past the right/bottom edge: value unused
-    gy = min(max(gy, 0), h - 1);
-    in[ly * IW + lx] = src[(size_t)gy * L.pitch + gx];
+  const bool interior = t.x0 >= 4 && t.x0 + BLUR_TW + 4 <= w && t.y0 >= 3 && t.y0 + BLUR_TH + 3 <= h;
+  if (interior) {
+    const uint8_t* base = src + (size_t)(t.y0 - 3) * L.pitch + (t.x0 - 4);
+    for (int i = threadIdx.x; i < (BLUR_TH + 6) * (BLUR_IW / 4); i += 256) {
+      const int r = i / (BLUR_IW / 4), c = i - r * (BLUR_IW / 4);
+      reinterpret_cast<uint32_t*>(in)[i] = *reinterpret_cast<const uint32_t*>(base + (size_t)r * L.pitch + 4 * c);
+    }
+  } else {
+    for (int i = threadIdx.x; i < (BLUR_TH + 6) * BLUR_IW; i += 256) {
+      const int r = i / BLUR_IW, c = i - r * BLUR_IW;
+      // BORDER_REFLECT_101 at the true image edge (values past the right/bottom edge are unused)
+      const int gx = reflect101(t.x0 - 4 + c, w), gy = reflect101(t.y0 - 3 + r, h);
+      in[i] = src[(size_t)gy * L.pitch + gx];
+    }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < (BLUR_TH + 6) * BLUR_TW; i += 256) {
-    const int ly = i / BLUR_TW, lx = i - ly * BLUR_TW;
-    const uint8_t* p = &in[ly * IW + lx];
-    hb[i] = (uint16_t)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
+  // horizontal pass: 4 outputs per thread from bytes [4q+1, 4q+11) of the staged row
+  for (int i = threadIdx.x; i < (BLUR_TH + 6) * (BLUR_TW / 4); i += 256) {
+    const int r = i / (BLUR_TW / 4), q = i - r * (BLUR_TW / 4);
+    const uint32_t* row = reinterpret_cast<const uint32_t*>(in + r * BLUR_IW) + q;
+    const uint32_t w0 = row[0], w1 = row[1], w2 = row[2];
+    int p[12];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { p[k] = (w0 >> (8 * k)) & 255; p[4 + k] = (w1 >> (8 * k)) & 255; p[8 + k] = (w2 >> (8 * k)) & 255; }
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++)  // output x = 4q+k is centred on staged byte 4q+k+4
+      o[k] = 18 * (p[k + 1] + p[k + 7]) + 34 * (p[k + 2] + p[k + 6]) + 48 * (p[k + 3] + p[k + 5]) + 56 * p[k + 4];
+    uint2 packed;
+    packed.x = o[0] | (o[1] << 16);
+    packed.y = o[2] | (o[3] << 16);
+    reinterpret_cast<uint2*>(hb + r * BLUR_TW)[q] = packed;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < BLUR_TH * BLUR_TW; i += 256) {
-    const int ly = i / BLUR_TW, lx = i - ly * BLUR_TW;
-    const int gx = t.x0 + lx, gy = t.y0 + ly;
-    if (gx >= w || gy >= h) continue;
-    const uint16_t* p = &hb[ly * BLUR_TW + lx];
-    const uint32_t acc = 18u * (p[0] + p[6 * BLUR_TW]) + 34u * (p[BLUR_TW] + p[5 * BLUR_TW]) +
-                         48u * (p[2 * BLUR_TW] + p[4 * BLUR_TW]) + 56u * p[3 * BLUR_TW];
-    dst[(size_t)gy * L.pitch + gx] = (uint8_t)((acc + (1u << 15)) >> 16);
+  // vertical pass + final rounding, one 32-bit store per thread
+  for (int i = threadIdx.x; i < BLUR_TH * (BLUR_TW / 4); i += 256) {
+    const int r = i / (BLUR_TW / 4), q = i - r * (BLUR_TW / 4);
+    const int gy = t.y0 + r, gx = t.x0 + 4 * q;
+    if (gy >= h || gx >= w) continue;
+    uint32_t acc[4] = {0, 0, 0, 0};
+    const uint32_t kk[7] = {18, 34, 48, 56, 48, 34, 18};
+#pragma unroll
+    for (int k = 0; k < 7; k++) {
+      const uint2 v = reinterpret_cast<const uint2*>(hb + (r + k) * BLUR_TW)[q];
+      acc[0] += kk[k] * (v.x & 0xffff); acc[1] += kk[k] * (v.x >> 16);
+      acc[2] += kk[k] * (v.y & 0xffff); acc[3] += kk[k] * (v.y >> 16);
+    }
+    uint32_t out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) out |= ((acc[k] + (1u << 15)) >> 16) << (8 * k);
+    // the pitch is a multiple of 64, so the (rare) partial last word stays inside the row
+    *reinterpret_cast<uint32_t*>(dst + (size_t)gy * L.pitch + gx) = out;
   }
 }
 
@@ -600,7 +675,7 @@ int Engine::ensure(int rows, int cols, int batch) {
     const float width = (float)(maxBX - minB), height = (float)(maxBY - minB);
     const int nCols = (int)(width / 35.f), nRows = (int)(height / 35.f);
     const int wCell = (int)ceilf(width / nCols), hCell = (int)ceilf(height / nRows);
-    if (wCell + 6 > FAST_TILE_MAX - 4 || hCell + 6 > FAST_TILE_MAX - 4 || wCell >= 128 || hCell >= 128) {
+    if (wCell > FAST_BAND_MAX || hCell > FAST_BAND_MAX) {
       set_last_error("unsupported FAST cell size");
       return ORB_E_ARG;
     }
