@@ -430,34 +430,37 @@ __global__ void __launch_bounds__(256) ldlt_kernel(double* __restrict__ M, int n
     }
     __syncthreads();
     if (threadIdx.x < 32) {
+      // left-looking LDL^T of the 32x32 block by one warp: lane r owns row r.
+      // Ti holds (L*D) so column j costs one dot product of length j per lane.
       const int r = threadIdx.x;
-      for (int c = 0; c < nb; c++) {
-        const double d = L11[c][c];
-        if (r == 0) { Dd[c] = d; if (d == 0.0) *fail = 1.0; }
-        double l = 0;
-        if (r > c && r < nb) {
-          l = L11[r][c] / d;
-          // update the rest of row r: A[r][m] -= l * d * L[m][c] for c < m <= r
-          for (int m = c + 1; m <= r; m++) L11[r][m] -= l * L11[m][c];  // L11[m][c] still holds A (= L*d)
+      for (int j = 0; j < nb; j++) {
+        double sacc = 0;
+        if (r >= j && r < nb) {
+          sacc = L11[r][j];
+          for (int m = 0; m < j; m++) sacc -= Ti[r][m] * L11[j][m];
         }
+        const double d = __shfl_sync(0xffffffffu, sacc, j);
+        if (r == j) { Dd[j] = d; if (d == 0.0) *fail = 1.0; }
         __syncwarp();
-        if (r > c && r < nb) L11[r][c] = l;
+        if (r > j && r < nb) { Ti[r][j] = sacc; L11[r][j] = sacc / d; }
         __syncwarp();
       }
     }
     __syncthreads();
-    // ---- panel: rows below the block, one thread per row
+    // ---- panel: rows below the block, one warp per row (lane j owns column j of the row);
+    //      forward substitution with the running value broadcast by shuffle
     const int r0 = k0 + nb;
-    for (int i = r0 + blockIdx.x * 256 + threadIdx.x; i < rows; i += 256 * nblk) {
-      double* Mi = M + (size_t)i * n + k0;
-      double ld[NB];
-#pragma unroll 4
-      for (int j = 0; j < nb; j++) {
-        double s = Mi[j];
-        for (int m = 0; m < j; m++) s -= ld[m] * L11[j][m];
-        ld[j] = s;  // = L_ij * D_j
+    {
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+      for (int i = r0 + blockIdx.x * 8 + warp; i < rows; i += 8 * nblk) {
+        double* Mi = M + (size_t)i * n + k0;
+        double a = (lane < nb) ? Mi[lane] : 0.0;
+        for (int m = 0; m < nb; m++) {
+          const double ldm = __shfl_sync(0xffffffffu, a, m);  // (L*D)_im is final once m steps are done
+          if (lane > m) a -= ldm * L11[lane][m];
+        }
+        if (lane < nb) Mi[lane] = a / Dd[lane];
       }
-      for (int j = 0; j < nb; j++) Mi[j] = ld[j] / Dd[j];
     }
     grid_barrier(bar, nblk, gen);
     // every CTA has loaded the diagonal block by now: publish its factor

@@ -58,7 +58,8 @@ struct Engine {
 
   // device state
   bool initialized = false;
-  cudaStream_t stream = nullptr, last_stream = nullptr;
+  cudaStream_t stream = nullptr, last_stream = nullptr, stream_in = nullptr, stream_out = nullptr;
+  std::vector<cudaEvent_t> chunk_events;
   std::vector<void*> dev_allocs, host_allocs;
   uint8_t *d_pyr = nullptr, *d_blur = nullptr, *d_scratch = nullptr, *d_desc = nullptr, *d_stage = nullptr;
   Cand* d_cand = nullptr;
@@ -90,7 +91,7 @@ struct Engine {
   void stage_begin(int st, cudaStream_t s);
   void stage_end(int st, cudaStream_t s, int launches);
   int collect_times(double* ms, long long* launches, bool reset);
-  int run_device(int batch, const int* lap_host, cudaStream_t s);
+  int run_device(int f0, int batch, const int* lap_host, cudaStream_t s);
   int extract_batch_host(int batch, const uint8_t* const* imgs, int rows, int cols, size_t step, const int* lap,
                          orb_keypoint* kps, uint8_t* desc, int cap, int* n, int* mono);
   int extract_batch_device(int batch, const uint8_t* d_imgs, size_t frame_stride, int rows, int cols, size_t step,

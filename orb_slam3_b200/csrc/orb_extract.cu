@@ -226,7 +226,8 @@ fast_cells_kernel(const uint8_t* __restrict__ pyr, size_t frame_stride,
     for (int i = threadIdx.x; i < nz; i += FAST_THREADS) reinterpret_cast<uint32_t*>(smap)[i] = 0;
   }
   __syncthreads();
-  // 2. cheap rejection + compaction (a 9-arc contains one end of every diameter)
+  // 2. cheap rejection + compaction: a 9-arc contains one end of every diameter, so a
+  //    corner needs (k or k+8) brighter -- or darker -- for each of the 8 diameters; 4 are tested here
   for (int y = warp; y < bh; y += FAST_THREADS / 32) {
     for (int x0 = 0; x0 < bw; x0 += 32) {
       const int x = x0 + lane;
@@ -235,9 +236,15 @@ fast_cells_kernel(const uint8_t* __restrict__ pyr, size_t frame_stride,
         const uint8_t* c = &tile[(y + 3) * FAST_TILE_PITCH + ox + x + 3];
         const int v = c[0], hi = v + min_th, lo = v - min_th;
         const int r0 = c[3 * FAST_TILE_PITCH], r8 = c[-3 * FAST_TILE_PITCH], r4 = c[3], r12 = c[-3];
-        const bool bp = ((r0 > hi) | (r8 > hi)) & ((r4 > hi) | (r12 > hi));
-        const bool dp = ((r0 < lo) | (r8 < lo)) & ((r4 < lo) | (r12 < lo));
-        pass = bp | dp;
+        bool bp = ((r0 > hi) | (r8 > hi)) & ((r4 > hi) | (r12 > hi));
+        bool dp = ((r0 < lo) | (r8 < lo)) & ((r4 < lo) | (r12 < lo));
+        if (bp | dp) {
+          const int r2 = c[2 * FAST_TILE_PITCH + 2], r10 = c[-2 * FAST_TILE_PITCH - 2];
+          const int r6 = c[-2 * FAST_TILE_PITCH + 2], r14 = c[2 * FAST_TILE_PITCH - 2];
+          bp = bp & ((r2 > hi) | (r10 > hi)) & ((r6 > hi) | (r14 > hi));
+          dp = dp & ((r2 < lo) | (r10 < lo)) & ((r6 < lo) | (r14 < lo));
+          pass = bp | dp;
+        }
       }
       const unsigned m = __ballot_sync(0xffffffffu, pass);
       if (m) {
@@ -246,6 +253,54 @@ fast_cells_kernel(const uint8_t* __restrict__ pyr, size_t frame_stride,
         base = __shfl_sync(0xffffffffu, base, 0);
         if (pass) queue[base + __popc(m & ((1u << lane) - 1))] = (unsigned short)((y << 8) | x);
       }
+    }
+  }
+  __syncthreads();
+  // 2b. exact segment test on the queue (16-bit brighter/darker masks, run of >= 9), second compaction
+  {
+    const int qn1 = s_qn;
+    __syncthreads();
+    if (threadIdx.x == 0) s_qn = 0;
+    __syncthreads();
+    for (int q0 = 0; q0 < qn1; q0 += FAST_THREADS) {
+      const int q = q0 + threadIdx.x;
+      bool corner = false;
+      int e = 0;
+      if (q < qn1) {
+        e = queue[q];
+        const int y = e >> 8, x = e & 255;
+        const uint8_t* c = &tile[(y + 3) * FAST_TILE_PITCH + ox + x + 3];
+        const int v = c[0], hi = v + min_th, lo = v - min_th;
+        constexpr int P = FAST_TILE_PITCH;
+        const int off[16] = {3 * P, 3 * P + 1, 2 * P + 2, P + 3, 3, -P + 3, -2 * P + 2, -3 * P + 1,
+                             -3 * P, -3 * P - 1, -2 * P - 2, -P - 3, -3, P - 3, 2 * P - 2, 3 * P - 1};
+        unsigned mb = 0, md = 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+          const int r = c[off[k]];
+          mb |= (unsigned)(r > hi) << k;
+          md |= (unsigned)(r < lo) << k;
+        }
+        auto run9 = [](unsigned m) {
+          const unsigned m2 = m | (m << 16);
+          unsigned t = m2 & (m2 >> 1);
+          t &= t >> 2;
+          t &= t >> 4;
+          t &= m2 >> 8;
+          return t != 0;
+        };
+        corner = run9(mb) | run9(md);
+      }
+      __syncthreads();  // every thread has read its queue[q] before the compacted entries overwrite it
+      const unsigned m = __ballot_sync(0xffffffffu, corner);
+      if (m) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&s_qn, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        // base + rank <= q0 + threadIdx.x: never overwrites an entry a later pass still needs
+        if (corner) queue[base + __popc(m & ((1u << lane) - 1))] = (unsigned short)e;
+      }
+      __syncthreads();
     }
   }
   __syncthreads();
@@ -527,13 +582,14 @@ describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blr
   if (lane < 31) {
     const int u = lane - 15, au = abs(u);
     const uint8_t* c = img + (size_t)y * L.pitch + x + u;
-    for (int v = -15; v <= 15; v++) {
-      if (au <= c_umax[abs(v)]) {
-        const int val = c[v * L.pitch];
-        m10 += u * val;
-        m01 += v * val;
-      }
-    }
+    // circular patch: column u spans rows |v| <= vmax(u); all 31 loads are issued back to back
+    int vals[31];
+#pragma unroll
+    for (int v = -15; v <= 15; v++) vals[v + 15] = (au <= c_umax[v < 0 ? -v : v]) ? (int)c[v * L.pitch] : 0;
+    int colsum = 0;
+#pragma unroll
+    for (int v = -15; v <= 15; v++) { colsum += vals[v + 15]; m01 += v * vals[v + 15]; }
+    m10 = u * colsum;
   }
   m10 = __reduce_add_sync(0xffffffffu, m10);
   m01 = __reduce_add_sync(0xffffffffu, m01);
@@ -620,8 +676,12 @@ void Engine::release() {
   host_allocs.clear();
   for (int i = 0; i < ORB_NUM_STAGES + 1; i++)
     for (auto& e : ev_pool[i]) cudaEventDestroy(e);
+  for (auto& e : chunk_events) cudaEventDestroy(e);
+  chunk_events.clear();
   if (stream) cudaStreamDestroy(stream);
-  stream = nullptr;
+  if (stream_in) cudaStreamDestroy(stream_in);
+  if (stream_out) cudaStreamDestroy(stream_out);
+  stream = stream_in = stream_out = nullptr;
   initialized = false;
   cap_rows = cap_cols = cap_batch = 0;
 }
@@ -645,6 +705,8 @@ int Engine::ensure(int rows, int cols, int batch) {
   release();
   CUDA_TRY(cudaSetDevice(device));
   CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&stream_in, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&stream_out, cudaStreamNonBlocking));
   initialized = true;
   CUDA_TRY(cudaMemcpyToSymbol(c_pattern, h_pattern, sizeof(h_pattern)));
   CUDA_TRY(cudaMemcpyToSymbol(c_umax, umax, sizeof(umax)));
@@ -827,13 +889,20 @@ int Engine::collect_times(double* ms, long long* launches, bool reset) {
 }
 
 // Everything between "level 0 is in the pyramid slab" and "results are in
-// d_kps/d_desc/d_n/d_mono", on stream s.
-int Engine::run_device(int batch, const int* lap_host, cudaStream_t s) {
+// d_kps/d_desc/d_n/d_mono" for frames [f0, f0+batch) of the slabs, on stream s.
+int Engine::run_device(int f0, int batch, const int* lap_host, cudaStream_t s) {
   const int B = batch;
   pyramid_fetched = false;
-  last_batch = batch;
+  uint8_t* pyr = d_pyr + (size_t)f0 * pyr_frame_bytes;
+  uint8_t* blr = d_blur + (size_t)f0 * pyr_frame_bytes;
+  Cand* cand = d_cand + (size_t)f0 * cand_frame_elems;
+  uint8_t* scratch = d_scratch + (size_t)f0 * scratch_frame_bytes;
+  int* sel = d_sel + 3 * (size_t)f0 * sel_frame_elems;
+  int* slot = d_slot + (size_t)f0 * sel_frame_elems;
+  int* cand_count = d_cand_count + (size_t)f0 * nlevels;
+  int* sel_count = d_sel_count + (size_t)f0 * nlevels;
   if (lap_host) {
-    CUDA_TRY(cudaMemcpyAsync(d_lap, lap_host, sizeof(int) * 2 * B, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_lap + 2 * f0, lap_host + 2 * f0, sizeof(int) * 2 * B, cudaMemcpyHostToDevice, s));
   }
   // 1. pyramid
   stage_begin(1, s);
@@ -841,43 +910,45 @@ int Engine::run_device(int batch, const int* lap_host, cudaStream_t s) {
     const LevelDev& S = levels[l - 1];
     const LevelDev& D = levels[l];
     dim3 grid((D.w + 4 * 256 - 1) / (4 * 256), D.h, B);
-    resize_level_kernel<<<grid, 256, 0, s>>>(d_pyr, pyr_frame_bytes, S.img_off, S.w, S.h, S.pitch, D.img_off,
+    resize_level_kernel<<<grid, 256, 0, s>>>(pyr, pyr_frame_bytes, S.img_off, S.w, S.h, S.pitch, D.img_off,
                                             D.w, D.h, D.pitch, d_xofs + rs[l].x_off, d_alpha + rs[l].x_off,
                                             d_yofs + rs[l].y_off, d_beta + rs[l].y_off);
   }
   stage_end(1, s, nlevels - 1);
   // 2. FAST cells
   stage_begin(2, s);
-  CUDA_TRY(cudaMemsetAsync(d_cand_count, 0, sizeof(int) * nlevels * B, s));
-  fast_cells_kernel<<<dim3(num_cells, B), FAST_THREADS, 0, s>>>(d_pyr, pyr_frame_bytes, d_cells, d_levels, ini_th,
-                                                                min_th, d_cand, cand_frame_elems, d_cand_count,
-                                                                nlevels);
+  CUDA_TRY(cudaMemsetAsync(cand_count, 0, sizeof(int) * nlevels * B, s));
+  fast_cells_kernel<<<dim3(num_cells, B), FAST_THREADS, 0, s>>>(pyr, pyr_frame_bytes, d_cells, d_levels, ini_th,
+                                                                min_th, cand, cand_frame_elems, cand_count, nlevels);
   stage_end(2, s, 1);
   // 3. octree
   stage_begin(3, s);
-  octree_kernel<<<dim3(nlevels, B), OCT_THREADS, 0, s>>>(d_cand, cand_frame_elems, d_cand_count, d_levels, d_scratch,
-                                                         scratch_frame_bytes, d_sel, 3 * sel_frame_elems, d_sel_count,
+  octree_kernel<<<dim3(nlevels, B), OCT_THREADS, 0, s>>>(cand, cand_frame_elems, cand_count, d_levels, scratch,
+                                                         scratch_frame_bytes, sel, 3 * sel_frame_elems, sel_count,
                                                          nlevels);
   stage_end(3, s, 1);
   // 4. blur
   stage_begin(4, s);
-  blur_kernel<<<dim3(num_tiles, B), 256, 0, s>>>(d_pyr, d_blur, pyr_frame_bytes, d_tiles, d_levels);
+  blur_kernel<<<dim3(num_tiles, B), 256, 0, s>>>(pyr, blr, pyr_frame_bytes, d_tiles, d_levels);
   stage_end(4, s, 1);
   // 5. output layout
   stage_begin(5, s);
-  layout_kernel<<<B, 256, 0, s>>>(d_sel, 3 * sel_frame_elems, d_sel_count, d_levels, nlevels,
-                                  lap_host ? d_lap : nullptr, d_slot, d_n, d_mono, out_cap);
+  layout_kernel<<<B, 256, 0, s>>>(sel, 3 * sel_frame_elems, sel_count, d_levels, nlevels,
+                                  lap_host ? d_lap + 2 * f0 : nullptr, slot, d_n + f0, d_mono + f0, out_cap);
   stage_end(5, s, 1);
   // 6. orientation + descriptors
   stage_begin(6, s);
   describe_kernel<<<dim3((unsigned)(sel_frame_elems / 8), B), 256, 0, s>>>(
-      d_pyr, d_blur, pyr_frame_bytes, d_sel, 3 * sel_frame_elems, d_sel_count, d_slot, d_levels, nlevels,
-      d_warp_level, d_kps, d_desc, out_cap);
+      pyr, blr, pyr_frame_bytes, sel, 3 * sel_frame_elems, sel_count, slot, d_levels, nlevels, d_warp_level,
+      d_kps + (size_t)f0 * out_cap, d_desc + (size_t)f0 * out_cap * 32, out_cap);
   stage_end(6, s, 1);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
+// Host-buffer path.  The batch is cut into chunks that flow through three
+// streams (H2D | kernels | D2H) so the PCIe copies overlap the compute of the
+// neighbouring chunks.
 int Engine::extract_batch_host(int batch, const uint8_t* const* imgs, int rows, int cols, size_t step,
                                const int* lap, orb_keypoint* kps, uint8_t* desc, int cap, int* n, int* mono) {
   if (batch <= 0 || !imgs || !kps || !desc || !n || !mono) { set_last_error("bad argument"); return ORB_E_ARG; }
@@ -887,32 +958,56 @@ int Engine::extract_batch_host(int batch, const uint8_t* const* imgs, int rows, 
   int rc = ensure(rows, cols, std::max(batch, cap_batch_hint));
   if (rc) return rc;
   CUDA_TRY(cudaSetDevice(device));
+  last_batch = batch;
+  last_stream = stream;
   cudaStream_t s = stream;
-  stage_begin(0, s);
   const LevelDev& L0 = levels[0];
-  for (int b = 0; b < batch; b++)
-    CUDA_TRY(cudaMemcpy2DAsync(d_pyr + (size_t)b * pyr_frame_bytes, L0.pitch, imgs[b], step, cols, rows,
-                               cudaMemcpyHostToDevice, s));
-  stage_end(0, s, 0);
-  rc = run_device(batch, lap, s);
-  if (rc) return rc;
-  stage_begin(7, s);
-  CUDA_TRY(cudaMemcpyAsync(h_counts, d_n, sizeof(int) * batch, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaMemcpyAsync(h_counts + batch, d_mono, sizeof(int) * batch, cudaMemcpyDeviceToHost, s));
-  // keypoints are dense from slot 0; copy the quota-sized prefix now, the rare
-  // overshoot (<= 3 per level) after the counts are known
-  const int guess = std::min(std::min(cap, out_cap), nfeatures + 4 * nlevels);
-  for (int b = 0; b < batch; b++) {
-    CUDA_TRY(cudaMemcpyAsync(kps + (size_t)b * cap, d_kps + (size_t)b * out_cap, sizeof(orb_keypoint) * guess,
-                             cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(desc + (size_t)b * cap * 32, d_desc + (size_t)b * out_cap * 32, (size_t)32 * guess,
-                             cudaMemcpyDeviceToHost, s));
+  const int chunk = batch <= 8 ? batch : std::max(8, (batch + 3) / 4);
+  const int nchunks = (batch + chunk - 1) / chunk;
+  if ((int)chunk_events.size() < 2 * nchunks) {
+    const size_t old = chunk_events.size();
+    chunk_events.resize(2 * nchunks);
+    for (size_t i = old; i < chunk_events.size(); i++)
+      CUDA_TRY(cudaEventCreateWithFlags(&chunk_events[i], cudaEventDisableTiming));
   }
+  // keypoints are dense from slot 0; copy the quota-sized prefix as each chunk finishes,
+  // the rare overshoot (<= 3 per level) after the counts are known
+  const int guess = std::min(std::min(cap, out_cap), nfeatures + 4 * nlevels);
+  stage_begin(0, s);
+  for (int c = 0; c < nchunks; c++) {
+    const int f0 = c * chunk, fb = std::min(chunk, batch - f0);
+    for (int b = f0; b < f0 + fb; b++)
+      CUDA_TRY(cudaMemcpy2DAsync(d_pyr + (size_t)b * pyr_frame_bytes, L0.pitch, imgs[b], step, cols, rows,
+                                 cudaMemcpyHostToDevice, nchunks > 1 ? stream_in : s));
+    if (nchunks > 1) CUDA_TRY(cudaEventRecord(chunk_events[2 * c], stream_in));
+  }
+  stage_end(0, s, 0);
+  for (int c = 0; c < nchunks; c++) {
+    const int f0 = c * chunk, fb = std::min(chunk, batch - f0);
+    if (nchunks > 1) CUDA_TRY(cudaStreamWaitEvent(s, chunk_events[2 * c], 0));
+    rc = run_device(f0, fb, lap, s);
+    if (rc) return rc;
+    cudaStream_t so = nchunks > 1 ? stream_out : s;
+    if (nchunks > 1) {
+      CUDA_TRY(cudaEventRecord(chunk_events[2 * c + 1], s));
+      CUDA_TRY(cudaStreamWaitEvent(so, chunk_events[2 * c + 1], 0));
+    }
+    CUDA_TRY(cudaMemcpyAsync(h_counts + f0, d_n + f0, sizeof(int) * fb, cudaMemcpyDeviceToHost, so));
+    CUDA_TRY(cudaMemcpyAsync(h_counts + cap_batch + f0, d_mono + f0, sizeof(int) * fb, cudaMemcpyDeviceToHost, so));
+    for (int b = f0; b < f0 + fb; b++) {
+      CUDA_TRY(cudaMemcpyAsync(kps + (size_t)b * cap, d_kps + (size_t)b * out_cap, sizeof(orb_keypoint) * guess,
+                               cudaMemcpyDeviceToHost, so));
+      CUDA_TRY(cudaMemcpyAsync(desc + (size_t)b * cap * 32, d_desc + (size_t)b * out_cap * 32, (size_t)32 * guess,
+                               cudaMemcpyDeviceToHost, so));
+    }
+  }
+  stage_begin(7, s);
+  if (nchunks > 1) CUDA_TRY(cudaStreamSynchronize(stream_out));
   CUDA_TRY(cudaStreamSynchronize(s));
   int worst = 0;
   for (int b = 0; b < batch; b++) {
     n[b] = h_counts[b];
-    mono[b] = h_counts[batch + b];
+    mono[b] = h_counts[cap_batch + b];
     worst = std::max(worst, n[b]);
   }
   if (worst > cap) { set_last_error("keypoint buffer too small"); return ORB_E_CAPACITY; }
@@ -948,7 +1043,8 @@ int Engine::extract_batch_device(int batch, const uint8_t* d_imgs, size_t frame_
                                  step, cols, rows, cudaMemcpyDeviceToDevice, s));
   }
   stage_end(0, s, 0);
-  return run_device(batch, lap, s) ? ORB_E_CUDA : batch;
+  last_batch = batch;
+  return run_device(0, batch, lap, s) ? ORB_E_CUDA : batch;
 }
 
 int Engine::fetch_pyramid() {
