@@ -226,81 +226,80 @@ fast_cells_kernel(const uint8_t* __restrict__ pyr, size_t frame_stride,
     for (int i = threadIdx.x; i < nz; i += FAST_THREADS) reinterpret_cast<uint32_t*>(smap)[i] = 0;
   }
   __syncthreads();
-  // 2. cheap rejection + compaction: a 9-arc contains one end of every diameter, so a
-  //    corner needs (k or k+8) brighter -- or darker -- for each of the 8 diameters; 4 are tested here
-  for (int y = warp; y < bh; y += FAST_THREADS / 32) {
-    for (int x0 = 0; x0 < bw; x0 += 32) {
-      const int x = x0 + lane;
-      bool pass = false;
-      if (x < bw) {
-        const uint8_t* c = &tile[(y + 3) * FAST_TILE_PITCH + ox + x + 3];
-        const int v = c[0], hi = v + min_th, lo = v - min_th;
-        const int r0 = c[3 * FAST_TILE_PITCH], r8 = c[-3 * FAST_TILE_PITCH], r4 = c[3], r12 = c[-3];
-        bool bp = ((r0 > hi) | (r8 > hi)) & ((r4 > hi) | (r12 > hi));
-        bool dp = ((r0 < lo) | (r8 < lo)) & ((r4 < lo) | (r12 < lo));
-        if (bp | dp) {
-          const int r2 = c[2 * FAST_TILE_PITCH + 2], r10 = c[-2 * FAST_TILE_PITCH - 2];
-          const int r6 = c[-2 * FAST_TILE_PITCH + 2], r14 = c[2 * FAST_TILE_PITCH - 2];
-          bp = bp & ((r2 > hi) | (r10 > hi)) & ((r6 > hi) | (r14 > hi));
-          dp = dp & ((r2 < lo) | (r10 < lo)) & ((r6 < lo) | (r14 < lo));
-          pass = bp | dp;
-        }
-      }
-      const unsigned m = __ballot_sync(0xffffffffu, pass);
-      if (m) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&s_qn, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (pass) queue[base + __popc(m & ((1u << lane) - 1))] = (unsigned short)((y << 8) | x);
+  // 2. cheap rejection on every band pixel (linear index, full warps): a 9-arc contains one
+  //    end of every diameter, so a corner needs (k or k+8) brighter -- or darker -- for each
+  //    of the 8 diameters; 4 are tested here.  Survivors stay as one bit per visit (<= 39).
+  const unsigned magic = ((1u << 20) + bw - 1) / bw;  // idx / bw for idx < 70*70
+  const int npx = bw * bh;
+  unsigned long long pass_bits = 0;
+  {
+    int it = 0;
+    for (int idx = threadIdx.x; idx < npx; idx += FAST_THREADS, it++) {
+      const int y = (int)(((unsigned)idx * magic) >> 20), x = idx - y * bw;
+      const uint8_t* c = &tile[(y + 3) * FAST_TILE_PITCH + ox + x + 3];
+      const int v = c[0], hi = v + min_th, lo = v - min_th;
+      const int r0 = c[3 * FAST_TILE_PITCH], r8 = c[-3 * FAST_TILE_PITCH], r4 = c[3], r12 = c[-3];
+      bool bp = ((r0 > hi) | (r8 > hi)) & ((r4 > hi) | (r12 > hi));
+      bool dp = ((r0 < lo) | (r8 < lo)) & ((r4 < lo) | (r12 < lo));
+      if (bp | dp) {
+        const int r2 = c[2 * FAST_TILE_PITCH + 2], r10 = c[-2 * FAST_TILE_PITCH - 2];
+        const int r6 = c[-2 * FAST_TILE_PITCH + 2], r14 = c[2 * FAST_TILE_PITCH - 2];
+        bp = bp & ((r2 > hi) | (r10 > hi)) & ((r6 > hi) | (r14 > hi));
+        dp = dp & ((r2 < lo) | (r10 < lo)) & ((r6 < lo) | (r14 < lo));
+        if (bp | dp) pass_bits |= 1ull << it;
       }
     }
   }
-  __syncthreads();
-  // 2b. exact segment test on the queue (16-bit brighter/darker masks, run of >= 9), second compaction
-  {
-    const int qn1 = s_qn;
-    __syncthreads();
-    if (threadIdx.x == 0) s_qn = 0;
-    __syncthreads();
-    for (int q0 = 0; q0 < qn1; q0 += FAST_THREADS) {
-      const int q = q0 + threadIdx.x;
-      bool corner = false;
-      int e = 0;
-      if (q < qn1) {
-        e = queue[q];
-        const int y = e >> 8, x = e & 255;
-        const uint8_t* c = &tile[(y + 3) * FAST_TILE_PITCH + ox + x + 3];
-        const int v = c[0], hi = v + min_th, lo = v - min_th;
-        constexpr int P = FAST_TILE_PITCH;
-        const int off[16] = {3 * P, 3 * P + 1, 2 * P + 2, P + 3, 3, -P + 3, -2 * P + 2, -3 * P + 1,
-                             -3 * P, -3 * P - 1, -2 * P - 2, -P - 3, -3, P - 3, 2 * P - 2, 3 * P - 1};
-        unsigned mb = 0, md = 0;
+  // 2b. exact segment test (16-bit brighter/darker masks, run of >= 9) on the thread's own survivors
+  unsigned long long corner_bits = 0;
+  while (pass_bits) {
+    const int it = __ffsll((long long)pass_bits) - 1;
+    pass_bits &= pass_bits - 1;
+    const int idx = threadIdx.x + it * FAST_THREADS;
+    const int y = (int)(((unsigned)idx * magic) >> 20), x = idx - y * bw;
+    const uint8_t* c = &tile[(y + 3) * FAST_TILE_PITCH + ox + x + 3];
+    const int v = c[0], hi = v + min_th, lo = v - min_th;
+    constexpr int P = FAST_TILE_PITCH;
+    const int off[16] = {3 * P, 3 * P + 1, 2 * P + 2, P + 3, 3, -P + 3, -2 * P + 2, -3 * P + 1,
+                         -3 * P, -3 * P - 1, -2 * P - 2, -P - 3, -3, P - 3, 2 * P - 2, 3 * P - 1};
+    unsigned mb = 0, md = 0;
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
-          const int r = c[off[k]];
-          mb |= (unsigned)(r > hi) << k;
-          md |= (unsigned)(r < lo) << k;
-        }
-        auto run9 = [](unsigned m) {
-          const unsigned m2 = m | (m << 16);
-          unsigned t = m2 & (m2 >> 1);
-          t &= t >> 2;
-          t &= t >> 4;
-          t &= m2 >> 8;
-          return t != 0;
-        };
-        corner = run9(mb) | run9(md);
-      }
-      __syncthreads();  // every thread has read its queue[q] before the compacted entries overwrite it
-      const unsigned m = __ballot_sync(0xffffffffu, corner);
-      if (m) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&s_qn, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        // base + rank <= q0 + threadIdx.x: never overwrites an entry a later pass still needs
-        if (corner) queue[base + __popc(m & ((1u << lane) - 1))] = (unsigned short)e;
-      }
-      __syncthreads();
+    for (int k = 0; k < 16; k++) {
+      const int r = c[off[k]];
+      mb |= (unsigned)(r > hi) << k;
+      md |= (unsigned)(r < lo) << k;
+    }
+    auto run9 = [](unsigned m) {
+      const unsigned m2 = m | (m << 16);
+      unsigned t = m2 & (m2 >> 1);
+      t &= t >> 2;
+      t &= t >> 4;
+      t &= m2 >> 8;
+      return t != 0;
+    };
+    if (run9(mb) | run9(md)) corner_bits |= 1ull << it;
+  }
+  // compaction of the corners into the queue: one block-wide exclusive scan
+  {
+    __shared__ int s_warp_tot[FAST_THREADS / 32];
+    const int cnt = __popcll(corner_bits);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp_tot[warp] = incl;
+    __syncthreads();
+    int base = incl - cnt;
+    for (int w = 0; w < warp; w++) base += s_warp_tot[w];
+    if (threadIdx.x == FAST_THREADS - 1) s_qn = base + cnt;
+    while (corner_bits) {
+      const int it = __ffsll((long long)corner_bits) - 1;
+      corner_bits &= corner_bits - 1;
+      const int idx = threadIdx.x + it * FAST_THREADS;
+      const int y = (int)(((unsigned)idx * magic) >> 20), x = idx - y * bw;
+      queue[base++] = (unsigned short)((y << 8) | x);
     }
   }
   __syncthreads();
@@ -558,7 +557,7 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 // One warp per selected keypoint: IC_Angle (ORBextractor.cc:76-103) on the raw
 // level, computeOrbDescriptor (:107-146) on the blurred level, final
 // KeyPoint fields (:880-890, :1149-1151), written to its output slot.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blr, size_t frame_stride,
                 const int* __restrict__ sel, size_t sel_frame_stride, const int* __restrict__ sel_count,
                 const int* __restrict__ slot, const LevelDev* __restrict__ lv, int nlevels,

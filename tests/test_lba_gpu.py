@@ -86,8 +86,12 @@ def test_lba_stop_flag_and_fixed_poses(oracle, lba):
     for k in ("e_kf", "e_mp", "e_stereo", "e_obs", "e_inv_sigma2"):
         g2[k] = g[k][perm]
     r2 = lba(scenes.lba_view(g2))
-    assert np.allclose(r2["mp_pos"], r["mp_pos"], rtol=0, atol=1e-9)
-    assert np.allclose(r2["chi2"], r["chi2"][perm], rtol=1e-9, atol=1e-9)
+    # (summation order inside a landmark changes -> last-bit differences, amplified by 10 LM steps)
+    assert np.abs(r2["mp_pos"] - r["mp_pos"]).max() < 1e-6, np.abs(r2["mp_pos"] - r["mp_pos"]).max()
+    assert np.allclose(r2["chi2"], r["chi2"][perm], rtol=1e-6, atol=1e-6)
+    # same input twice: bitwise identical (all reductions are fixed-order; detects races)
+    r3 = lba(gv)
+    assert np.array_equal(r3["mp_pos"], r["mp_pos"]) and np.array_equal(r3["kf_pose"], r["kf_pose"])
 
 
 def test_lba_landmark_shards_over_nccl_match_single_gpu():
