@@ -54,7 +54,7 @@ struct Engine {
   std::vector<ResizeTab> rs;
   size_t pyr_frame_bytes = 0, cand_frame_elems = 0, scratch_frame_bytes = 0, sel_frame_elems = 0;
   int out_cap = 0, num_cells = 0, num_tiles = 0;
-  int cap_rows = 0, cap_cols = 0, cap_batch = 0, cap_batch_hint = 1;
+  int cap_rows = 0, cap_cols = 0, cap_batch = 0, cap_batch_hint = 1, chunk_override = 0;
 
   // device state
   bool initialized = false;
@@ -96,6 +96,7 @@ struct Engine {
                          orb_keypoint* kps, uint8_t* desc, int cap, int* n, int* mono);
   int extract_batch_device(int batch, const uint8_t* d_imgs, size_t frame_stride, int rows, int cols, size_t step,
                            const int* lap, cudaStream_t user);
+  int l2_chunk_frames(int batch) const;
   int fetch_pyramid();
   int debug_candidates(int frame, int level, int* xys, int cap);
 };

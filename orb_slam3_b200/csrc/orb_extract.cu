@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -202,7 +203,8 @@ fast_cells_kernel(const uint8_t* __restrict__ pyr, size_t frame_stride,
   __shared__ __align__(16) uint8_t tile[FAST_TILE_MAX * FAST_TILE_PITCH];
   __shared__ __align__(16) uint8_t smap[(FAST_BAND_MAX + 2) * (FAST_BAND_MAX + 2) + 8];
   __shared__ unsigned short queue[FAST_BAND_MAX * FAST_BAND_MAX];
-  __shared__ int s_qn, s_cnt_ini, s_cnt_all, s_base;
+  __shared__ int s_qn, s_cnt_all, s_base;
+  __shared__ int s_warp_tot[FAST_THREADS / 32];
   const CellDesc cd = cells[blockIdx.x];
   const LevelDev L = lv[cd.level];
   const int f = blockIdx.y;
@@ -212,7 +214,7 @@ fast_cells_kernel(const uint8_t* __restrict__ pyr, size_t frame_stride,
   if (bw <= 0 || bh <= 0) return;
   const int sw = bw + 2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) { s_qn = 0; s_cnt_ini = 0; s_cnt_all = 0; }
+  if (threadIdx.x == 0) { s_qn = 0; s_cnt_all = 0; }
   // 1. tile load, aligned words
   const int ox = cd.x0 & 3;
   const int nw = (ox + tw + 3) >> 2;
@@ -226,120 +228,99 @@ fast_cells_kernel(const uint8_t* __restrict__ pyr, size_t frame_stride,
     for (int i = threadIdx.x; i < nz; i += FAST_THREADS) reinterpret_cast<uint32_t*>(smap)[i] = 0;
   }
   __syncthreads();
-  // 2. cheap rejection on every band pixel (linear index, full warps): a 9-arc contains one
-  //    end of every diameter, so a corner needs (k or k+8) brighter -- or darker -- for each
-  //    of the 8 diameters; 4 are tested here.  Survivors stay as one bit per visit (<= 39).
+  // The reference calls cv::FAST(cell, iniThFAST) and only when that returns nothing
+  // cv::FAST(cell, minThFAST) (:826-846).  Same here: pass 0 at iniTh (few pixels survive the
+  // cheap test), pass 1 at minTh only for the rare cells that came out empty.
   const unsigned magic = ((1u << 20) + bw - 1) / bw;  // idx / bw for idx < 70*70
   const int npx = bw * bh;
-  unsigned long long pass_bits = 0;
-  {
-    int it = 0;
-    for (int idx = threadIdx.x; idx < npx; idx += FAST_THREADS, it++) {
-      const int y = (int)(((unsigned)idx * magic) >> 20), x = idx - y * bw;
-      const uint8_t* c = &tile[(y + 3) * FAST_TILE_PITCH + ox + x + 3];
-      const int v = c[0], hi = v + min_th, lo = v - min_th;
-      const int r0 = c[3 * FAST_TILE_PITCH], r8 = c[-3 * FAST_TILE_PITCH], r4 = c[3], r12 = c[-3];
-      bool bp = ((r0 > hi) | (r8 > hi)) & ((r4 > hi) | (r12 > hi));
-      bool dp = ((r0 < lo) | (r8 < lo)) & ((r4 < lo) | (r12 < lo));
-      if (bp | dp) {
-        const int r2 = c[2 * FAST_TILE_PITCH + 2], r10 = c[-2 * FAST_TILE_PITCH - 2];
-        const int r6 = c[-2 * FAST_TILE_PITCH + 2], r14 = c[2 * FAST_TILE_PITCH - 2];
-        bp = bp & ((r2 > hi) | (r10 > hi)) & ((r6 > hi) | (r14 > hi));
-        dp = dp & ((r2 < lo) | (r10 < lo)) & ((r6 < lo) | (r14 < lo));
-        if (bp | dp) pass_bits |= 1ull << it;
+  unsigned long long keep_bits = 0;
+  int qn = 0;
+  for (int pass = 0; pass < 2; pass++) {
+    const int th_fast = pass == 0 ? ini_th : min_th;
+    if (pass == 1) {
+      const int nz = ((bw + 2) * (bh + 2) + 3) >> 2;
+      for (int i = threadIdx.x; i < nz; i += FAST_THREADS) reinterpret_cast<uint32_t*>(smap)[i] = 0;
+    }
+    // 2. cheap rejection on every band pixel (linear index, full warps): a 9-arc contains one
+    //    end of every diameter, so a corner needs (k or k+8) brighter -- or darker -- for each
+    //    of the 8 diameters; 4 are tested here.  Survivors stay as one bit per visit (<= 39).
+    unsigned long long pass_bits = 0;
+    {
+      int it = 0;
+      for (int idx = threadIdx.x; idx < npx; idx += FAST_THREADS, it++) {
+        const int y = (int)(((unsigned)idx * magic) >> 20), x = idx - y * bw;
+        const uint8_t* c = &tile[(y + 3) * FAST_TILE_PITCH + ox + x + 3];
+        const int v = c[0], hi = v + th_fast, lo = v - th_fast;
+        const int r0 = c[3 * FAST_TILE_PITCH], r8 = c[-3 * FAST_TILE_PITCH], r4 = c[3], r12 = c[-3];
+        bool bp = ((r0 > hi) | (r8 > hi)) & ((r4 > hi) | (r12 > hi));
+        bool dp = ((r0 < lo) | (r8 < lo)) & ((r4 < lo) | (r12 < lo));
+        if (bp | dp) {
+          const int r2 = c[2 * FAST_TILE_PITCH + 2], r10 = c[-2 * FAST_TILE_PITCH - 2];
+          const int r6 = c[-2 * FAST_TILE_PITCH + 2], r14 = c[2 * FAST_TILE_PITCH - 2];
+          bp = bp & ((r2 > hi) | (r10 > hi)) & ((r6 > hi) | (r14 > hi));
+          dp = dp & ((r2 < lo) | (r10 < lo)) & ((r6 < lo) | (r14 < lo));
+          if (bp | dp) pass_bits |= 1ull << it;
+        }
       }
     }
-  }
-  // 2b. exact segment test (16-bit brighter/darker masks, run of >= 9) on the thread's own survivors
-  unsigned long long corner_bits = 0;
-  while (pass_bits) {
-    const int it = __ffsll((long long)pass_bits) - 1;
-    pass_bits &= pass_bits - 1;
-    const int idx = threadIdx.x + it * FAST_THREADS;
-    const int y = (int)(((unsigned)idx * magic) >> 20), x = idx - y * bw;
-    const uint8_t* c = &tile[(y + 3) * FAST_TILE_PITCH + ox + x + 3];
-    const int v = c[0], hi = v + min_th, lo = v - min_th;
-    constexpr int P = FAST_TILE_PITCH;
-    const int off[16] = {3 * P, 3 * P + 1, 2 * P + 2, P + 3, 3, -P + 3, -2 * P + 2, -3 * P + 1,
-                         -3 * P, -3 * P - 1, -2 * P - 2, -P - 3, -3, P - 3, 2 * P - 2, 3 * P - 1};
-    unsigned mb = 0, md = 0;
+    // compaction of the survivors into the queue: one block-wide exclusive scan
+    {
+      const int cnt = __popcll(pass_bits);
+      int incl = cnt;
 #pragma unroll
-    for (int k = 0; k < 16; k++) {
-      const int r = c[off[k]];
-      mb |= (unsigned)(r > hi) << k;
-      md |= (unsigned)(r < lo) << k;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      __syncthreads();  // previous pass is done with s_warp_tot / queue / smap zeroing is visible
+      if (lane == 31) s_warp_tot[warp] = incl;
+      if (threadIdx.x == 0) { s_cnt_all = 0; }
+      __syncthreads();
+      int base = incl - cnt;
+      for (int w = 0; w < warp; w++) base += s_warp_tot[w];
+      if (threadIdx.x == FAST_THREADS - 1) s_qn = base + cnt;
+      while (pass_bits) {
+        const int it = __ffsll((long long)pass_bits) - 1;
+        pass_bits &= pass_bits - 1;
+        const int idx = threadIdx.x + it * FAST_THREADS;
+        const int y = (int)(((unsigned)idx * magic) >> 20), x = idx - y * bw;
+        queue[base++] = (unsigned short)((y << 8) | x);
+      }
     }
-    auto run9 = [](unsigned m) {
-      const unsigned m2 = m | (m << 16);
-      unsigned t = m2 & (m2 >> 1);
-      t &= t >> 2;
-      t &= t >> 4;
-      t &= m2 >> 8;
-      return t != 0;
-    };
-    if (run9(mb) | run9(md)) corner_bits |= 1ull << it;
-  }
-  // compaction of the corners into the queue: one block-wide exclusive scan
-  {
-    __shared__ int s_warp_tot[FAST_THREADS / 32];
-    const int cnt = __popcll(corner_bits);
-    int incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
-    }
-    if (lane == 31) s_warp_tot[warp] = incl;
     __syncthreads();
-    int base = incl - cnt;
-    for (int w = 0; w < warp; w++) base += s_warp_tot[w];
-    if (threadIdx.x == FAST_THREADS - 1) s_qn = base + cnt;
-    while (corner_bits) {
-      const int it = __ffsll((long long)corner_bits) - 1;
-      corner_bits &= corner_bits - 1;
-      const int idx = threadIdx.x + it * FAST_THREADS;
-      const int y = (int)(((unsigned)idx * magic) >> 20), x = idx - y * bw;
-      queue[base++] = (unsigned short)((y << 8) | x);
+    qn = s_qn;
+    // 3. exact segment test + score (max arc threshold) of the queued pixels, dense lanes
+    for (int q = threadIdx.x; q < qn; q += FAST_THREADS) {
+      const int e = queue[q], y = e >> 8, x = e & 255;
+      const int best = fast_best(&tile[(y + 3) * FAST_TILE_PITCH + ox + x + 3], FAST_TILE_PITCH, th_fast);
+      smap[(y + 1) * sw + x + 1] = (uint8_t)best;
     }
-  }
-  __syncthreads();
-  const int qn = s_qn;
-  // 3. full FAST-9/16 score of the queued pixels
-  for (int q = threadIdx.x; q < qn; q += FAST_THREADS) {
-    const int e = queue[q], y = e >> 8, x = e & 255;
-    const int best = fast_best(&tile[(y + 3) * FAST_TILE_PITCH + ox + x + 3], FAST_TILE_PITCH, min_th);
-    smap[(y + 1) * sw + x + 1] = (uint8_t)best;
-  }
-  __syncthreads();
-  // 4. NMS on the queue; a thread remembers its survivors as one bit per visit (<= 4900/128 = 39)
-  unsigned long long keep_bits = 0, ini_bits = 0;
-  int it = 0;
-  for (int q = threadIdx.x; q < qn; q += FAST_THREADS, it++) {
-    const int e = queue[q], y = e >> 8, x = e & 255;
-    const uint8_t* p = &smap[(y + 1) * sw + x + 1];
-    const int s = p[0];
-    if (s && s > p[-1] && s > p[1] && s > p[-sw - 1] && s > p[-sw] && s > p[-sw + 1] &&
-        s > p[sw - 1] && s > p[sw] && s > p[sw + 1]) {
-      keep_bits |= 1ull << it;
-      if (s - 1 >= ini_th) ini_bits |= 1ull << it;
+    __syncthreads();
+    // 4. strict 3x3 NMS on the queue; a thread remembers its survivors as one bit per visit
+    keep_bits = 0;
+    int it = 0;
+    for (int q = threadIdx.x; q < qn; q += FAST_THREADS, it++) {
+      const int e = queue[q], y = e >> 8, x = e & 255;
+      const uint8_t* p = &smap[(y + 1) * sw + x + 1];
+      const int s = p[0];
+      if (s && s > p[-1] && s > p[1] && s > p[-sw - 1] && s > p[-sw] && s > p[-sw + 1] &&
+          s > p[sw - 1] && s > p[sw] && s > p[sw + 1])
+        keep_bits |= 1ull << it;
     }
+    if (keep_bits) atomicAdd(&s_cnt_all, __popcll(keep_bits));
+    __syncthreads();
+    if (s_cnt_all > 0 || ini_th == min_th) break;
   }
-  if (keep_bits) atomicAdd(&s_cnt_all, __popcll(keep_bits));
-  if (ini_bits) atomicAdd(&s_cnt_ini, __popcll(ini_bits));
-  __syncthreads();
-  // cv::FAST(cell, iniTh) first, cv::FAST(cell, minTh) only when that is empty (:826-846)
-  const bool use_ini = s_cnt_ini > 0;
-  const int total = use_ini ? s_cnt_ini : s_cnt_all;
+  const int total = s_cnt_all;
   if (total == 0) return;
   if (threadIdx.x == 0) s_base = atomicAdd(&cand_count[f * nlevels + cd.level], total);
   __syncthreads();
-  const unsigned long long bits = use_ini ? ini_bits : keep_bits;
-  if (!bits) return;
+  if (!keep_bits) return;
   // the order inside the level's list is irrelevant (the octree uses order keys)
   Cand* out = cand + (size_t)f * cand_frame_stride + L.cand_off;
-  it = 0;
+  int it = 0;
   for (int q = threadIdx.x; q < qn; q += FAST_THREADS, it++) {
-    if (!(bits & (1ull << it))) continue;
+    if (!(keep_bits & (1ull << it))) continue;
     const int e = queue[q], y = e >> 8, x = e & 255;
     const int pos = atomicAdd(&s_base, 1);
     if (pos < L.cand_cap) {
@@ -557,7 +538,7 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 // One warp per selected keypoint: IC_Angle (ORBextractor.cc:76-103) on the raw
 // level, computeOrbDescriptor (:107-146) on the blurred level, final
 // KeyPoint fields (:880-890, :1149-1151), written to its output slot.
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256)
 describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blr, size_t frame_stride,
                 const int* __restrict__ sel, size_t sel_frame_stride, const int* __restrict__ sel_count,
                 const int* __restrict__ slot, const LevelDev* __restrict__ lv, int nlevels,
@@ -961,7 +942,7 @@ int Engine::extract_batch_host(int batch, const uint8_t* const* imgs, int rows, 
   last_stream = stream;
   cudaStream_t s = stream;
   const LevelDev& L0 = levels[0];
-  const int chunk = batch <= 8 ? batch : std::max(8, (batch + 3) / 4);
+  const int chunk = batch <= 8 ? batch : std::min(l2_chunk_frames(batch), std::max(8, (batch + 3) / 4));
   const int nchunks = (batch + chunk - 1) / chunk;
   if ((int)chunk_events.size() < 2 * nchunks) {
     const size_t old = chunk_events.size();
@@ -1043,7 +1024,21 @@ int Engine::extract_batch_device(int batch, const uint8_t* d_imgs, size_t frame_
   }
   stage_end(0, s, 0);
   last_batch = batch;
-  return run_device(0, batch, lap, s) ? ORB_E_CUDA : batch;
+  // L2-sized sub-batches: a chunk's pyramid, blurred pyramid and candidates stay in the
+  // 126 MB L2 between resize -> FAST -> blur -> describe instead of round-tripping through HBM
+  const int chunk = l2_chunk_frames(batch);
+  for (int f0 = 0; f0 < batch; f0 += chunk)
+    if (run_device(f0, std::min(chunk, batch - f0), lap, s)) return ORB_E_CUDA;
+  return batch;
+}
+
+int Engine::l2_chunk_frames(int batch) const {
+  if (chunk_override > 0) return std::min(chunk_override, batch);
+  const char* env = getenv("ORB_B200_CHUNK");
+  if (env && atoi(env) > 0) return std::min(atoi(env), batch);
+  // measured on B200 (profiles/r1_summary.md): sub-batching does not help -- no stage is HBM bound and
+  // the latency-bound octree wants as many (frame, level) CTAs in flight as possible
+  return batch;
 }
 
 int Engine::fetch_pyramid() {
