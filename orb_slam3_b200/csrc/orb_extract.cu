@@ -10,6 +10,7 @@
 // explicit _rn intrinsics).
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -135,15 +136,20 @@ resize_level_kernel(uint8_t* __restrict__ pyr, size_t frame_stride, size_t src_o
   *reinterpret_cast<uint32_t*>(base + dst_off + (size_t)y * dpitch + x4) = packed;
 }
 
-// Copy the caller's level-0 image (arbitrary pitch) into the pyramid slab.
-__global__ void copy_level0_kernel(const uint8_t* __restrict__ src, size_t src_frame_stride,
-                                   size_t src_step, uint8_t* __restrict__ pyr, size_t frame_stride,
-                                   int w, int h, int pitch) {
-  const int x = (blockIdx.x * blockDim.x + threadIdx.x);
+// Copy the caller's level-0 images (arbitrary pitch / frame stride, device memory) into the
+// pyramid slabs: one launch for the whole batch, 16-byte accesses when the layout allows.
+__global__ void __launch_bounds__(256)
+copy_level0_kernel(const uint8_t* __restrict__ src, size_t src_frame_stride, size_t src_step,
+                   uint8_t* __restrict__ pyr, size_t frame_stride, int w, int h, int pitch, int vec16) {
   const int y = blockIdx.y;
-  if (x >= w) return;
-  pyr[(size_t)blockIdx.z * frame_stride + (size_t)y * pitch + x] =
-      src[(size_t)blockIdx.z * src_frame_stride + (size_t)y * src_step + x];
+  const uint8_t* s = src + (size_t)blockIdx.z * src_frame_stride + (size_t)y * src_step;
+  uint8_t* d = pyr + (size_t)blockIdx.z * frame_stride + (size_t)y * pitch;
+  if (vec16) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i * 16 < w) reinterpret_cast<uint4*>(d)[i] = reinterpret_cast<const uint4*>(s)[i];
+  } else {
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < w; x += gridDim.x * blockDim.x) d[x] = s[x];
+  }
 }
 
 // FAST-9/16 score of the centre pixel from its ring; returns best (=score+1) or
@@ -535,15 +541,15 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
   return a;
 }
 
-// One warp per selected keypoint: IC_Angle (ORBextractor.cc:76-103) on the raw
-// level, computeOrbDescriptor (:107-146) on the blurred level, final
-// KeyPoint fields (:880-890, :1149-1151), written to its output slot.
+// One warp per selected keypoint: IC_Angle (ORBextractor.cc:76-103) on the raw level, the
+// final KeyPoint fields (:880-890, :1149-1151) and the rotation (cos, sin) for the descriptor.
+// Kept separate from the descriptor kernel so both run at full occupancy (each is a chain of
+// dependent long-latency gathers).
 __global__ void __launch_bounds__(256)
-describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blr, size_t frame_stride,
-                const int* __restrict__ sel, size_t sel_frame_stride, const int* __restrict__ sel_count,
-                const int* __restrict__ slot, const LevelDev* __restrict__ lv, int nlevels,
-                const int* __restrict__ warp_level, orb_keypoint* __restrict__ kps,
-                uint8_t* __restrict__ desc, int out_cap) {
+orient_kernel(const uint8_t* __restrict__ pyr, size_t frame_stride, const int* __restrict__ sel,
+              size_t sel_frame_stride, const int* __restrict__ sel_count, const int* __restrict__ slot,
+              const LevelDev* __restrict__ lv, int nlevels, const int* __restrict__ warp_level,
+              orb_keypoint* __restrict__ kps, float2* __restrict__ rot, int out_cap) {
   const int lane = threadIdx.x & 31;
   const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // index in the sel slab
   const int f = blockIdx.y;
@@ -557,12 +563,11 @@ describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blr
   const int pos = slot[(size_t)f * sel_frame_stride / 3 + gw];
   if (pos < 0) return;
   const uint8_t* img = pyr + (size_t)f * frame_stride + L.img_off;
-  // ---- IC_Angle: lane <-> u = lane-15
+  // lane <-> u = lane-15; column u spans rows |v| <= vmax(u); all 31 loads are issued back to back
   int m10 = 0, m01 = 0;
   if (lane < 31) {
     const int u = lane - 15, au = abs(u);
     const uint8_t* c = img + (size_t)y * L.pitch + x + u;
-    // circular patch: column u spans rows |v| <= vmax(u); all 31 loads are issued back to back
     int vals[31];
 #pragma unroll
     for (int v = -15; v <= 15; v++) vals[v + 15] = (au <= c_umax[v < 0 ? -v : v]) ? (int)c[v * L.pitch] : 0;
@@ -573,14 +578,47 @@ describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blr
   }
   m10 = __reduce_add_sync(0xffffffffu, m10);
   m01 = __reduce_add_sync(0xffffffffu, m01);
+  if (lane != 0) return;
   const float angle = fast_atan2_deg((float)m01, (float)m10);
-  // ---- steered BRIEF: lane <-> descriptor byte
   const float factorPI = 0.017453292519943295f;  // (float)(CV_PI/180.f)
   const float ang = __fmul_rn(angle, factorPI);
-  const float a = (float)cos((double)ang), b = (float)sin((double)ang);
+  rot[(size_t)f * sel_frame_stride / 3 + gw] = make_float2((float)cos((double)ang), (float)sin((double)ang));
+  orb_keypoint kp;
+  float fx = (float)x, fy = (float)y;
+  if (level != 0) { fx = __fmul_rn(fx, L.scale); fy = __fmul_rn(fy, L.scale); }
+  kp.x = fx; kp.y = fy;
+  kp.size = (float)L.patch_size;
+  kp.angle = angle;
+  kp.response = (float)score;
+  kp.octave = level;
+  kp.class_id = -1;
+  kps[(size_t)f * out_cap + pos] = kp;
+}
+
+// One warp per selected keypoint, lane <-> descriptor byte: computeOrbDescriptor (:107-146) on
+// the blurred level.
+__global__ void __launch_bounds__(256)
+brief_kernel(const uint8_t* __restrict__ blr, size_t frame_stride, const int* __restrict__ sel,
+             size_t sel_frame_stride, const int* __restrict__ sel_count, const int* __restrict__ slot,
+             const LevelDev* __restrict__ lv, int nlevels, const int* __restrict__ warp_level,
+             const float2* __restrict__ rot, uint8_t* __restrict__ desc, int out_cap) {
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int f = blockIdx.y;
+  const int level = warp_level[gw];
+  if (level < 0) return;
+  const LevelDev L = lv[level];
+  const int i = gw - L.sel_off;
+  if (i >= sel_count[f * nlevels + level]) return;
+  const int* rec = sel + (size_t)f * sel_frame_stride + 3 * (size_t)gw;
+  const int x = rec[0] + 16, y = rec[1] + 16;
+  const int pos = slot[(size_t)f * sel_frame_stride / 3 + gw];
+  if (pos < 0) return;
+  const float2 ab = rot[(size_t)f * sel_frame_stride / 3 + gw];
+  const float a = ab.x, b = ab.y;
   const uint8_t* bc = blr + (size_t)f * frame_stride + L.img_off + (size_t)y * L.pitch + x;
   const int* pat = c_pattern + 32 * lane;
-  int val = 0;
+  int t0[8], t1[8];
 #pragma unroll
   for (int k = 0; k < 8; k++) {
     const float x0 = (float)pat[4 * k], y0 = (float)pat[4 * k + 1];
@@ -589,22 +627,13 @@ describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blr
     const int rx0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
     const int ry1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
     const int rx1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-    const int t0 = bc[ry0 * L.pitch + rx0], t1 = bc[ry1 * L.pitch + rx1];
-    val |= (t0 < t1) << k;
+    t0[k] = bc[ry0 * L.pitch + rx0];
+    t1[k] = bc[ry1 * L.pitch + rx1];
   }
+  int val = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) val |= (t0[k] < t1[k]) << k;
   desc[((size_t)f * out_cap + pos) * 32 + lane] = (uint8_t)val;
-  if (lane == 0) {
-    orb_keypoint kp;
-    float fx = (float)x, fy = (float)y;
-    if (level != 0) { fx = __fmul_rn(fx, L.scale); fy = __fmul_rn(fy, L.scale); }
-    kp.x = fx; kp.y = fy;
-    kp.size = (float)L.patch_size;
-    kp.angle = angle;
-    kp.response = (float)score;
-    kp.octave = level;
-    kp.class_id = -1;
-    kps[(size_t)f * out_cap + pos] = kp;
-  }
 }
 
 // ------------------------------------------------------------------- engine
@@ -661,6 +690,10 @@ void Engine::release() {
   if (stream) cudaStreamDestroy(stream);
   if (stream_in) cudaStreamDestroy(stream_in);
   if (stream_out) cudaStreamDestroy(stream_out);
+  if (stream_side) cudaStreamDestroy(stream_side);
+  if (ev_pyr_done) cudaEventDestroy(ev_pyr_done);
+  if (ev_blur_done) cudaEventDestroy(ev_blur_done);
+  stream_side = nullptr; ev_pyr_done = ev_blur_done = nullptr;
   stream = stream_in = stream_out = nullptr;
   initialized = false;
   cap_rows = cap_cols = cap_batch = 0;
@@ -687,6 +720,9 @@ int Engine::ensure(int rows, int cols, int batch) {
   CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaStreamCreateWithFlags(&stream_in, cudaStreamNonBlocking));
   CUDA_TRY(cudaStreamCreateWithFlags(&stream_out, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&stream_side, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreateWithFlags(&ev_pyr_done, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&ev_blur_done, cudaEventDisableTiming));
   initialized = true;
   CUDA_TRY(cudaMemcpyToSymbol(c_pattern, h_pattern, sizeof(h_pattern)));
   CUDA_TRY(cudaMemcpyToSymbol(c_umax, umax, sizeof(umax)));
@@ -800,6 +836,7 @@ int Engine::ensure(int rows, int cols, int batch) {
   if (dalloc(&d_scratch, scratch_frame_bytes * B)) return ORB_E_CUDA;
   if (dalloc(&d_sel, 3 * sel_frame_elems * B)) return ORB_E_CUDA;
   if (dalloc(&d_slot, sel_frame_elems * B)) return ORB_E_CUDA;
+  if (dalloc(&d_rot, sel_frame_elems * B)) return ORB_E_CUDA;
   if (dalloc(&d_cand_count, (size_t)nlevels * B)) return ORB_E_CUDA;
   if (dalloc(&d_sel_count, (size_t)nlevels * B)) return ORB_E_CUDA;
   if (dalloc(&d_n, B)) return ORB_E_CUDA;
@@ -895,6 +932,20 @@ int Engine::run_device(int f0, int batch, const int* lap_host, cudaStream_t s) {
                                             d_yofs + rs[l].y_off, d_beta + rs[l].y_off);
   }
   stage_end(1, s, nlevels - 1);
+  // 4. blur: needs only the pyramid, so it runs on a side stream next to FAST + octree (the
+  //    octree is a latency-bound 8-CTA-per-frame kernel that leaves most SMs idle)
+  const bool side_stream_used = !profiling;
+  if (side_stream_used) {
+    CUDA_TRY(cudaEventRecord(ev_pyr_done, s));
+    CUDA_TRY(cudaStreamWaitEvent(stream_side, ev_pyr_done, 0));
+    blur_kernel<<<dim3(num_tiles, B), 256, 0, stream_side>>>(pyr, blr, pyr_frame_bytes, d_tiles, d_levels);
+    CUDA_TRY(cudaEventRecord(ev_blur_done, stream_side));
+    stage_launches[4] += 1; total_launches += 1;
+  } else {
+    stage_begin(4, s);
+    blur_kernel<<<dim3(num_tiles, B), 256, 0, s>>>(pyr, blr, pyr_frame_bytes, d_tiles, d_levels);
+    stage_end(4, s, 1);
+  }
   // 2. FAST cells
   stage_begin(2, s);
   CUDA_TRY(cudaMemsetAsync(cand_count, 0, sizeof(int) * nlevels * B, s));
@@ -907,21 +958,22 @@ int Engine::run_device(int f0, int batch, const int* lap_host, cudaStream_t s) {
                                                          scratch_frame_bytes, sel, 3 * sel_frame_elems, sel_count,
                                                          nlevels);
   stage_end(3, s, 1);
-  // 4. blur
-  stage_begin(4, s);
-  blur_kernel<<<dim3(num_tiles, B), 256, 0, s>>>(pyr, blr, pyr_frame_bytes, d_tiles, d_levels);
-  stage_end(4, s, 1);
   // 5. output layout
   stage_begin(5, s);
   layout_kernel<<<B, 256, 0, s>>>(sel, 3 * sel_frame_elems, sel_count, d_levels, nlevels,
                                   lap_host ? d_lap + 2 * f0 : nullptr, slot, d_n + f0, d_mono + f0, out_cap);
   stage_end(5, s, 1);
-  // 6. orientation + descriptors
+  // 6. orientation, then descriptors
   stage_begin(6, s);
-  describe_kernel<<<dim3((unsigned)(sel_frame_elems / 8), B), 256, 0, s>>>(
-      pyr, blr, pyr_frame_bytes, sel, 3 * sel_frame_elems, sel_count, slot, d_levels, nlevels, d_warp_level,
-      d_kps + (size_t)f0 * out_cap, d_desc + (size_t)f0 * out_cap * 32, out_cap);
-  stage_end(6, s, 1);
+  float2* rot = d_rot + (size_t)f0 * sel_frame_elems;
+  orient_kernel<<<dim3((unsigned)(sel_frame_elems / 8), B), 256, 0, s>>>(
+      pyr, pyr_frame_bytes, sel, 3 * sel_frame_elems, sel_count, slot, d_levels, nlevels, d_warp_level,
+      d_kps + (size_t)f0 * out_cap, rot, out_cap);
+  if (side_stream_used) CUDA_TRY(cudaStreamWaitEvent(s, ev_blur_done, 0));
+  brief_kernel<<<dim3((unsigned)(sel_frame_elems / 8), B), 256, 0, s>>>(
+      blr, pyr_frame_bytes, sel, 3 * sel_frame_elems, sel_count, slot, d_levels, nlevels, d_warp_level, rot,
+      d_desc + (size_t)f0 * out_cap * 32, out_cap);
+  stage_end(6, s, 2);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -1016,13 +1068,18 @@ int Engine::extract_batch_device(int batch, const uint8_t* d_imgs, size_t frame_
   last_stream = s;
   const LevelDev& L0 = levels[0];
   stage_begin(0, s);
-  CUDA_TRY(cudaMemcpy2DAsync(d_pyr, L0.pitch, d_imgs, step, cols, rows, cudaMemcpyDeviceToDevice, s));
-  if (batch > 1) {
-    for (int b = 1; b < batch; b++)
-      CUDA_TRY(cudaMemcpy2DAsync(d_pyr + (size_t)b * pyr_frame_bytes, L0.pitch, d_imgs + (size_t)b * frame_stride,
-                                 step, cols, rows, cudaMemcpyDeviceToDevice, s));
+  {
+    // rows are 16-byte copyable when pointers/pitches are 16-aligned (the slab pitch is a multiple
+    // of 64, so the tail of the last vector stays inside the destination row)
+    const int vec16 = ((uintptr_t)d_imgs % 16 == 0) && (step % 16 == 0) && (frame_stride % 16 == 0) &&
+                      ((size_t)((cols + 15) / 16) * 16 <= step);
+    const int per_row = vec16 ? (cols + 15) / 16 : cols;
+    dim3 grid((per_row + 255) / 256, rows, batch);
+    if (!vec16) grid.x = std::min<unsigned>(grid.x, 8);
+    copy_level0_kernel<<<grid, 256, 0, s>>>(d_imgs, frame_stride, step, d_pyr, pyr_frame_bytes, cols, rows, L0.pitch,
+                                            vec16);
   }
-  stage_end(0, s, 0);
+  stage_end(0, s, 1);
   last_batch = batch;
   // L2-sized sub-batches: a chunk's pyramid, blurred pyramid and candidates stay in the
   // 126 MB L2 between resize -> FAST -> blur -> describe instead of round-tripping through HBM
