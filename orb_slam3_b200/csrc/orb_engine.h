@@ -61,7 +61,6 @@ struct Engine {
   cudaStream_t stream = nullptr, last_stream = nullptr, stream_in = nullptr, stream_out = nullptr;
   cudaStream_t stream_side = nullptr;
   cudaEvent_t ev_pyr_done = nullptr, ev_blur_done = nullptr;
-  float2* d_rot = nullptr;
   std::vector<cudaEvent_t> chunk_events;
   std::vector<void*> dev_allocs, host_allocs;
   uint8_t *d_pyr = nullptr, *d_blur = nullptr, *d_scratch = nullptr, *d_desc = nullptr, *d_stage = nullptr;

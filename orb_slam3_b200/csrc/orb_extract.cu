@@ -541,15 +541,15 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
   return a;
 }
 
-// One warp per selected keypoint: IC_Angle (ORBextractor.cc:76-103) on the raw level, the
-// final KeyPoint fields (:880-890, :1149-1151) and the rotation (cos, sin) for the descriptor.
-// Kept separate from the descriptor kernel so both run at full occupancy (each is a chain of
-// dependent long-latency gathers).
+// One warp per selected keypoint: IC_Angle (ORBextractor.cc:76-103) on the raw
+// level, computeOrbDescriptor (:107-146) on the blurred level, final
+// KeyPoint fields (:880-890, :1149-1151), written to its output slot.
 __global__ void __launch_bounds__(256)
-orient_kernel(const uint8_t* __restrict__ pyr, size_t frame_stride, const int* __restrict__ sel,
-              size_t sel_frame_stride, const int* __restrict__ sel_count, const int* __restrict__ slot,
-              const LevelDev* __restrict__ lv, int nlevels, const int* __restrict__ warp_level,
-              orb_keypoint* __restrict__ kps, float2* __restrict__ rot, int out_cap) {
+describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blr, size_t frame_stride,
+                const int* __restrict__ sel, size_t sel_frame_stride, const int* __restrict__ sel_count,
+                const int* __restrict__ slot, const LevelDev* __restrict__ lv, int nlevels,
+                const int* __restrict__ warp_level, orb_keypoint* __restrict__ kps,
+                uint8_t* __restrict__ desc, int out_cap) {
   const int lane = threadIdx.x & 31;
   const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // index in the sel slab
   const int f = blockIdx.y;
@@ -563,11 +563,12 @@ orient_kernel(const uint8_t* __restrict__ pyr, size_t frame_stride, const int* _
   const int pos = slot[(size_t)f * sel_frame_stride / 3 + gw];
   if (pos < 0) return;
   const uint8_t* img = pyr + (size_t)f * frame_stride + L.img_off;
-  // lane <-> u = lane-15; column u spans rows |v| <= vmax(u); all 31 loads are issued back to back
+  // ---- IC_Angle: lane <-> u = lane-15
   int m10 = 0, m01 = 0;
   if (lane < 31) {
     const int u = lane - 15, au = abs(u);
     const uint8_t* c = img + (size_t)y * L.pitch + x + u;
+    // circular patch: column u spans rows |v| <= vmax(u); all 31 loads are issued back to back
     int vals[31];
 #pragma unroll
     for (int v = -15; v <= 15; v++) vals[v + 15] = (au <= c_umax[v < 0 ? -v : v]) ? (int)c[v * L.pitch] : 0;
@@ -578,47 +579,14 @@ orient_kernel(const uint8_t* __restrict__ pyr, size_t frame_stride, const int* _
   }
   m10 = __reduce_add_sync(0xffffffffu, m10);
   m01 = __reduce_add_sync(0xffffffffu, m01);
-  if (lane != 0) return;
   const float angle = fast_atan2_deg((float)m01, (float)m10);
+  // ---- steered BRIEF: lane <-> descriptor byte
   const float factorPI = 0.017453292519943295f;  // (float)(CV_PI/180.f)
   const float ang = __fmul_rn(angle, factorPI);
-  rot[(size_t)f * sel_frame_stride / 3 + gw] = make_float2((float)cos((double)ang), (float)sin((double)ang));
-  orb_keypoint kp;
-  float fx = (float)x, fy = (float)y;
-  if (level != 0) { fx = __fmul_rn(fx, L.scale); fy = __fmul_rn(fy, L.scale); }
-  kp.x = fx; kp.y = fy;
-  kp.size = (float)L.patch_size;
-  kp.angle = angle;
-  kp.response = (float)score;
-  kp.octave = level;
-  kp.class_id = -1;
-  kps[(size_t)f * out_cap + pos] = kp;
-}
-
-// One warp per selected keypoint, lane <-> descriptor byte: computeOrbDescriptor (:107-146) on
-// the blurred level.
-__global__ void __launch_bounds__(256)
-brief_kernel(const uint8_t* __restrict__ blr, size_t frame_stride, const int* __restrict__ sel,
-             size_t sel_frame_stride, const int* __restrict__ sel_count, const int* __restrict__ slot,
-             const LevelDev* __restrict__ lv, int nlevels, const int* __restrict__ warp_level,
-             const float2* __restrict__ rot, uint8_t* __restrict__ desc, int out_cap) {
-  const int lane = threadIdx.x & 31;
-  const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int f = blockIdx.y;
-  const int level = warp_level[gw];
-  if (level < 0) return;
-  const LevelDev L = lv[level];
-  const int i = gw - L.sel_off;
-  if (i >= sel_count[f * nlevels + level]) return;
-  const int* rec = sel + (size_t)f * sel_frame_stride + 3 * (size_t)gw;
-  const int x = rec[0] + 16, y = rec[1] + 16;
-  const int pos = slot[(size_t)f * sel_frame_stride / 3 + gw];
-  if (pos < 0) return;
-  const float2 ab = rot[(size_t)f * sel_frame_stride / 3 + gw];
-  const float a = ab.x, b = ab.y;
+  const float a = (float)cos((double)ang), b = (float)sin((double)ang);
   const uint8_t* bc = blr + (size_t)f * frame_stride + L.img_off + (size_t)y * L.pitch + x;
   const int* pat = c_pattern + 32 * lane;
-  int t0[8], t1[8];
+  int val = 0;
 #pragma unroll
   for (int k = 0; k < 8; k++) {
     const float x0 = (float)pat[4 * k], y0 = (float)pat[4 * k + 1];
@@ -627,13 +595,22 @@ brief_kernel(const uint8_t* __restrict__ blr, size_t frame_stride, const int* __
     const int rx0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
     const int ry1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
     const int rx1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-    t0[k] = bc[ry0 * L.pitch + rx0];
-    t1[k] = bc[ry1 * L.pitch + rx1];
+    const int t0 = bc[ry0 * L.pitch + rx0], t1 = bc[ry1 * L.pitch + rx1];
+    val |= (t0 < t1) << k;
   }
-  int val = 0;
-#pragma unroll
-  for (int k = 0; k < 8; k++) val |= (t0[k] < t1[k]) << k;
   desc[((size_t)f * out_cap + pos) * 32 + lane] = (uint8_t)val;
+  if (lane == 0) {
+    orb_keypoint kp;
+    float fx = (float)x, fy = (float)y;
+    if (level != 0) { fx = __fmul_rn(fx, L.scale); fy = __fmul_rn(fy, L.scale); }
+    kp.x = fx; kp.y = fy;
+    kp.size = (float)L.patch_size;
+    kp.angle = angle;
+    kp.response = (float)score;
+    kp.octave = level;
+    kp.class_id = -1;
+    kps[(size_t)f * out_cap + pos] = kp;
+  }
 }
 
 // ------------------------------------------------------------------- engine
@@ -836,7 +813,6 @@ int Engine::ensure(int rows, int cols, int batch) {
   if (dalloc(&d_scratch, scratch_frame_bytes * B)) return ORB_E_CUDA;
   if (dalloc(&d_sel, 3 * sel_frame_elems * B)) return ORB_E_CUDA;
   if (dalloc(&d_slot, sel_frame_elems * B)) return ORB_E_CUDA;
-  if (dalloc(&d_rot, sel_frame_elems * B)) return ORB_E_CUDA;
   if (dalloc(&d_cand_count, (size_t)nlevels * B)) return ORB_E_CUDA;
   if (dalloc(&d_sel_count, (size_t)nlevels * B)) return ORB_E_CUDA;
   if (dalloc(&d_n, B)) return ORB_E_CUDA;
@@ -963,17 +939,13 @@ int Engine::run_device(int f0, int batch, const int* lap_host, cudaStream_t s) {
   layout_kernel<<<B, 256, 0, s>>>(sel, 3 * sel_frame_elems, sel_count, d_levels, nlevels,
                                   lap_host ? d_lap + 2 * f0 : nullptr, slot, d_n + f0, d_mono + f0, out_cap);
   stage_end(5, s, 1);
-  // 6. orientation, then descriptors
+  // 6. orientation + descriptors (one fused kernel measured faster than an orient/brief split)
   stage_begin(6, s);
-  float2* rot = d_rot + (size_t)f0 * sel_frame_elems;
-  orient_kernel<<<dim3((unsigned)(sel_frame_elems / 8), B), 256, 0, s>>>(
-      pyr, pyr_frame_bytes, sel, 3 * sel_frame_elems, sel_count, slot, d_levels, nlevels, d_warp_level,
-      d_kps + (size_t)f0 * out_cap, rot, out_cap);
   if (side_stream_used) CUDA_TRY(cudaStreamWaitEvent(s, ev_blur_done, 0));
-  brief_kernel<<<dim3((unsigned)(sel_frame_elems / 8), B), 256, 0, s>>>(
-      blr, pyr_frame_bytes, sel, 3 * sel_frame_elems, sel_count, slot, d_levels, nlevels, d_warp_level, rot,
-      d_desc + (size_t)f0 * out_cap * 32, out_cap);
-  stage_end(6, s, 2);
+  describe_kernel<<<dim3((unsigned)(sel_frame_elems / 8), B), 256, 0, s>>>(
+      pyr, blr, pyr_frame_bytes, sel, 3 * sel_frame_elems, sel_count, slot, d_levels, nlevels, d_warp_level,
+      d_kps + (size_t)f0 * out_cap, d_desc + (size_t)f0 * out_cap * 32, out_cap);
+  stage_end(6, s, 1);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
