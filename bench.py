@@ -208,7 +208,7 @@ def run_reference(args):
 class Workload:
     """POOL distinct batches of B frames with everything the matchers need."""
 
-    def __init__(self, B, POOL, rank, device, stream):
+    def __init__(self, B, POOL, rank, device, stream, share=None):
         import torch
         from orb_slam3_b200 import scenes
         from orb_slam3_b200.extractor import ORBextractor
@@ -222,6 +222,12 @@ class Workload:
             m.set_stream(stream)
         cap = self.ext.cap
         self.cap = cap
+        if share is not None:
+            # extra e2e worker: same inputs, own engine handles and output buffers
+            self.uniq, self.host_pool, self.dev_pool, self.meta = share.uniq, share.host_pool, None, share.meta
+            self.sf, self.sf2 = share.sf, share.sf2
+            self._alloc_outputs(torch, B, cap)
+            return
         uniq, shifts = make_frames(min(B, 16) + 1, 1000 * rank + 1)
         self.uniq = uniq
         nu = len(uniq) - 1
@@ -257,6 +263,9 @@ class Workload:
             self.meta.append(entry)
         self.d_assign_last = torch.empty((B, cap), dtype=torch.int32, device="cuda")
         self.d_assign_local = torch.empty((B, cap), dtype=torch.int32, device="cuda")
+        self._alloc_outputs(torch, B, cap)
+
+    def _alloc_outputs(self, torch, B, cap):
         self.out_k = torch.empty((B, cap * 28), dtype=torch.uint8).pin_memory()
         self.out_d = torch.empty((B, cap * 32), dtype=torch.uint8).pin_memory()
         self.out_n = np.zeros(B, np.int32)
@@ -395,6 +404,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--batch", type=int, default=64, help="frames per step per GPU")
     ap.add_argument("--pool", type=int, default=3, help="distinct batches rotated through (L2 defeat)")
+    ap.add_argument("--e2e-workers", type=int, default=3, help="host threads feeding the GPU in the e2e leg")
     ap.add_argument("--no-lba", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -443,15 +453,34 @@ def main():
     ms_dev = e0.elapsed_time(e1)
     launches = launches_now() - launches0
     nm_last, nm_local = int(wl.nmatch_last.sum()), int(wl.nmatch_local.sum())
-    # ---- end to end through the host-buffer ABI (wall clock brackets every copy and sync)
-    for i in range(Wm):
-        wl.step_host(i)
+    # ---- end to end through the host-buffer ABI (wall clock brackets every copy and sync).
+    # Batches come from independent camera streams, so `--e2e-workers` host threads (each with its
+    # own extractor + matcher handles, i.e. its own CUDA streams) work on different batches at once:
+    # one batch's PCIe copies and host staging overlap another batch's kernels.
+    from concurrent.futures import ThreadPoolExecutor
+    workers = [wl] + [Workload(B, POOL, rank, local_rank, None, share=wl) for _ in range(args.e2e_workers - 1)]
+    for w in workers[1:]:
+        for m in (w.m_last, w.m_local):
+            m.set_stream(None)
+    for m in (wl.m_last, wl.m_local):
+        m.set_stream(None)
+    pool_exec = ThreadPoolExecutor(len(workers))
+
+    def run_host_steps(k):
+        def work(widx):
+            torch.cuda.set_device(local_rank)
+            for i in range(widx, k, len(workers)):
+                workers[widx].step_host(i)
+        list(pool_exec.map(work, range(len(workers))))
+
+    run_host_steps(max(Wm, len(workers)))
     barrier()
     t0 = time.perf_counter()
-    for i in range(K):
-        wl.step_host(i)
+    run_host_steps(K)
     barrier()
     ms_e2e = (time.perf_counter() - t0) * 1e3
+    for m in (wl.m_last, wl.m_local):
+        m.set_stream(tstream.cuda_stream)
     sampler.stop_flag = True
     sampler.join(timeout=2)
     nkp = int(wl.out_n.sum())
@@ -541,7 +570,7 @@ def main():
                              % (POOL * B * (W * H + 2 * P) / 1e6, POOL),
                        "keypoints_last_step": nkp, "matches_last_step": {"last": nm_last, "local": nm_local}},
             "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h)},
+                    "d2h_bytes_per_step": int(d2h), "host_threads": args.e2e_workers},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
