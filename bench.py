@@ -236,6 +236,7 @@ class Workload:
         self.sf2 = (self.sf * self.sf).astype(np.float32)
         # one untimed extraction of the distinct frames (GPU) to build the match inputs
         res = self.ext.extract_batch(list(uniq))
+        scene_cache = {}
         for p in range(POOL):
             t = torch.empty((B, H, W), dtype=torch.uint8).pin_memory()
             idx = [1 + (b + p) % nu for b in range(B)]        # frame idx[b]; its predecessor is idx[b]-1
@@ -247,18 +248,21 @@ class Workload:
                      "d_taken": []}
             for b in range(B):
                 i = idx[b]
-                _, kb, db = res[i]
-                _, ka, da = res[i - 1]
-                cur, last, Tcw = scenes.last_frame_scene(ka, da, kb, db, W, H, shifts[i], seed=2 * i)
-                F, mps = scenes.local_map_scene(kb, db, W, H, N_LOCAL_EXTRA, seed=7 * i)
-                entry["n"].append(len(kb))
+                if i not in scene_cache:  # only len(uniq)-1 distinct frames exist
+                    _, kb, db = res[i]
+                    _, ka, da = res[i - 1]
+                    cur, last, Tcw = scenes.last_frame_scene(ka, da, kb, db, W, H, shifts[i], seed=2 * i)
+                    F, mps = scenes.local_map_scene(kb, db, W, H, N_LOCAL_EXTRA, seed=7 * i)
+                    scene_cache[i] = (
+                        len(kb), cur, last, Tcw, F, mps,
+                        {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in last._keep.items()},
+                        {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in mps._keep.items()},
+                        (torch.from_numpy(cur._keep[5]).cuda(), torch.from_numpy(F._keep[5]).cuda()))
+                n_i, cur, last, Tcw, F, mps, dl, dm, dtk = scene_cache[i]
+                entry["n"].append(n_i)
                 entry["cur"].append(cur); entry["last"].append(last); entry["T"].append(Tcw)
                 entry["F"].append(F); entry["mps"].append(mps)
-                entry["d_last"].append({k: torch.from_numpy(np.ascontiguousarray(v)).cuda()
-                                        for k, v in last._keep.items()})
-                entry["d_mps"].append({k: torch.from_numpy(np.ascontiguousarray(v)).cuda()
-                                       for k, v in mps._keep.items()})
-                entry["d_taken"].append((torch.from_numpy(cur._keep[5]).cuda(), torch.from_numpy(F._keep[5]).cuda()))
+                entry["d_last"].append(dl); entry["d_mps"].append(dm); entry["d_taken"].append(dtk)
             entry["T"] = np.stack(entry["T"])
             self.meta.append(entry)
         self.d_assign_last = torch.empty((B, cap), dtype=torch.int32, device="cuda")
@@ -404,7 +408,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--batch", type=int, default=64, help="frames per step per GPU")
     ap.add_argument("--pool", type=int, default=3, help="distinct batches rotated through (L2 defeat)")
-    ap.add_argument("--e2e-workers", type=int, default=3, help="host threads feeding the GPU in the e2e leg")
+    ap.add_argument("--e2e-workers", type=int, default=4, help="host threads feeding the GPU in the e2e leg")
     ap.add_argument("--no-lba", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -436,17 +436,8 @@ __global__ void __launch_bounds__(256) ldlt_kernel(double* __restrict__ M, int n
       for (int j = 0; j < nb; j++) {
         double sacc = 0;
         if (r >= j && r < nb) {
-          // four independent partial sums: the fp64 FMA chain is the critical path of the whole solve
-          double s0 = L11[r][j], s1 = 0, s2 = 0, s3 = 0;
-          int m = 0;
-          for (; m + 4 <= j; m += 4) {
-            s0 -= Ti[r][m] * L11[j][m];
-            s1 -= Ti[r][m + 1] * L11[j][m + 1];
-            s2 -= Ti[r][m + 2] * L11[j][m + 2];
-            s3 -= Ti[r][m + 3] * L11[j][m + 3];
-          }
-          for (; m < j; m++) s0 -= Ti[r][m] * L11[j][m];
-          sacc = (s0 + s1) + (s2 + s3);
+          sacc = L11[r][j];
+          for (int m = 0; m < j; m++) sacc -= Ti[r][m] * L11[j][m];
         }
         const double d = __shfl_sync(0xffffffffu, sacc, j);
         if (r == j) { Dd[j] = d; if (d == 0.0) *fail = 1.0; }
@@ -978,9 +969,7 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
         unsigned* bar = S.d_bar;
         double* failp = D.scalars + 3;
         void* args[] = {&Mp, &nn, &bar, &failp};
-        // as few CTAs as the first panel can use: the grid barrier cost grows with the CTA count
-        const int tb = (n + 1 + NB - 1) / NB;
-        const int blocks = std::min(S.ldlt_blocks, std::max(std::max(1, tb * (tb + 1) / 2), (n + 1 + 7) / 8));
+        const int blocks = std::min(S.ldlt_blocks, std::max(1, (n + 1 + NB - 1) / NB * ((n + 1 + NB - 1) / NB)));
         CUDA_TRYL(cudaLaunchCooperativeKernel((void*)ldlt_kernel, dim3(blocks), dim3(256), args, 0, st));
       }
       backsub_kernel<<<1, 1024, sizeof(double) * n, st>>>(D.S, n, D.x);
