@@ -140,14 +140,24 @@ int octree_select(BE& be, const Cand* cand, int n, const OctreeLevelParams& p,
       // 1. children point counts of every node that could be split
       for (int j = tid; j < 4 * M; j += nt) s.childcnt[j] = 0;
       be.sync();
-      for (int i = tid; i < n; i += nt) {
-        const int node = s.pt_node[i];
-        if (cnt[node] > 1) {
-          const uint32_t xy = cand[i].xy;
-          const int q = quadrant_of((int)(xy & 0xffffu), (int)(xy >> 16), ulx[node], uly[node],
-                                    brx[node], bry[node]);
-          s.pt_q[i] = (uint8_t)q;
-          be.atomic_add(&s.childcnt[4 * node + q], 1);
+      // 4 points per trip: the four independent (pt_node, xy) loads are issued together, which is
+      // what bounds this latency-bound kernel (one CTA walks ~10^4 points a dozen times)
+      for (int i0 = tid; i0 < n; i0 += 4 * nt) {
+        int node[4];
+        uint32_t xy[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int i = i0 + u * nt;
+          node[u] = i < n ? s.pt_node[i] : -1;
+          xy[u] = i < n ? cand[i].xy : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          if (node[u] < 0 || cnt[node[u]] <= 1) continue;
+          const int q = quadrant_of((int)(xy[u] & 0xffffu), (int)(xy[u] >> 16), ulx[node[u]], uly[node[u]],
+                                    brx[node[u]], bry[node[u]]);
+          s.pt_q[i0 + u * nt] = (uint8_t)q;
+          be.atomic_add(&s.childcnt[4 * node[u] + q], 1);
         }
       }
       be.sync();
@@ -246,9 +256,17 @@ int octree_select(BE& be, const Cand* cand, int n, const OctreeLevelParams& p,
         }
       }
       be.sync();
-      for (int i = tid; i < n; i += nt) {
-        const int node = s.pt_node[i];
-        s.pt_node[i] = s.remap[4 * node + (s.rank[node] >= 0 ? (int)s.pt_q[i] : 0)];
+      for (int i0 = tid; i0 < n; i0 += 4 * nt) {
+        int node[4], q[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int i = i0 + u * nt;
+          node[u] = i < n ? s.pt_node[i] : -1;
+          q[u] = i < n ? (int)s.pt_q[i] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (node[u] >= 0) s.pt_node[i0 + u * nt] = s.remap[4 * node[u] + (s.rank[node[u]] >= 0 ? q[u] : 0)];
       }
       be.sync();
 

@@ -396,6 +396,7 @@ octree_kernel(const Cand* __restrict__ cand, size_t cand_frame_stride, const int
       for (int k = 0; k < 5; k++) { s.nd[b][k] = q; q += nc; }
     s.childcnt = q; q += 4 * nc;
     s.remap = q; q += 4 * nc;
+    s.rank = q; q += nc;
   }
   const int n = min(cand_count[f * nlevels + level], L.cand_cap);
   const Cand* c = cand + (size_t)f * cand_frame_stride + L.cand_off;
@@ -810,7 +811,7 @@ int Engine::ensure(int rows, int cols, int batch) {
   {
     int max_nc = 0;
     for (int l = 0; l < nlevels; l++) max_nc = std::max(max_nc, levels[l].oct.node_cap);
-    const size_t need = (size_t)18 * max_nc * sizeof(int);
+    const size_t need = (size_t)19 * max_nc * sizeof(int);
     if (need <= 96 * 1024) {
       oct_smem_node_cap = max_nc;
       oct_smem_bytes = need;
