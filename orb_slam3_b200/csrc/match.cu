@@ -347,7 +347,8 @@ __device__ __forceinline__ int rot_bin(float a1, float a2) {
 }
 
 // Phase 2+3: resolution rounds, one CTA per problem.
-__global__ void __launch_bounds__(1024) proj_resolve_kernel(ProjProblem* probs) {
+__global__ void __launch_bounds__(1024) proj_resolve_kernel(ProjProblem* probs, int smem_nk) {
+  extern __shared__ int rs_dyn[];
   __shared__ int s_unresolved, s_nmatch;
   __shared__ int s_hist[HISTO_LENGTH];
   __shared__ int s_ind[3];
@@ -355,19 +356,27 @@ __global__ void __launch_bounds__(1024) proj_resolve_kernel(ProjProblem* probs) 
   if (P.result[1]) return;  // candidate buffer overflow: host re-runs with a larger one
   const DevFrame& F = P.F;
   const int nq = P.nq, nk = F.n;
+  // per-keypoint state of the rounds (owner index, taken flag, octave) in shared memory when it
+  // fits: every round is a chain of dependent look-ups into these arrays
+  const bool in_smem = nk <= smem_nk;
+  int* minidx = in_smem ? rs_dyn : P.minidx;
+  uint8_t* taken = in_smem ? reinterpret_cast<uint8_t*>(rs_dyn + smem_nk) : P.taken;
+  uint8_t* oct8 = taken + smem_nk;
+  if (in_smem)
+    for (int i = threadIdx.x; i < nk; i += 1024) { taken[i] = P.taken[i]; oct8[i] = (uint8_t)F.keys[i].octave; }
   if (threadIdx.x == 0) s_nmatch = 0;
   for (int b = threadIdx.x; b < HISTO_LENGTH; b += 1024) s_hist[b] = 0;
   for (int j = threadIdx.x; j < nq; j += 1024) P.acc_kp[j] = -1;
   __syncthreads();
   while (true) {
     if (threadIdx.x == 0) s_unresolved = 0;
-    for (int i = threadIdx.x; i < nk; i += 1024) P.minidx[i] = 0x7fffffff;
+    for (int i = threadIdx.x; i < nk; i += 1024) minidx[i] = 0x7fffffff;
     __syncthreads();
     for (int j = threadIdx.x; j < nq; j += 1024) {
       if (!P.q_state[j]) continue;
       for (int e = P.q_off[j]; e < P.q_off[j + 1]; e++) {
         const int c = P.cand_idx[e];
-        if (!P.taken[c]) atomicMin(&P.minidx[c], j);
+        if (!taken[c]) atomicMin(&minidx[c], j);
       }
     }
     __syncthreads();
@@ -376,7 +385,7 @@ __global__ void __launch_bounds__(1024) proj_resolve_kernel(ProjProblem* probs) 
       bool mine = true;
       for (int e = P.q_off[j]; e < P.q_off[j + 1] && mine; e++) {
         const int c = P.cand_idx[e];
-        if (P.minidx[c] != j && !((volatile uint8_t*)P.taken)[c]) mine = false;
+        if (minidx[c] != j && !((volatile uint8_t*)taken)[c]) mine = false;
       }
       if (!mine) { atomicAdd(&s_unresolved, 1); continue; }
       // replay the reference scan on the current flags
@@ -385,13 +394,13 @@ __global__ void __launch_bounds__(1024) proj_resolve_kernel(ProjProblem* probs) 
         const int c = P.cand_idx[e];
         // free candidates of a finalising point all carry minidx == j; anything else
         // was taken before this round or by a lower-index point in this round
-        if (P.minidx[c] != j) continue;
+        if (minidx[c] != j) continue;
         const int dist = P.cand_dist[e];
         if (dist < bestDist) {
           bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel;
-          bestLevel = F.keys[c].octave; bestIdx = c;
+          bestLevel = in_smem ? (int)oct8[c] : F.keys[c].octave; bestIdx = c;
         } else if (P.kind == 0 && dist < bestDist2) {
-          bestLevel2 = F.keys[c].octave; bestDist2 = dist;
+          bestLevel2 = in_smem ? (int)oct8[c] : F.keys[c].octave; bestDist2 = dist;
         }
       }
       bool accept = bestDist <= TH_HIGH;
@@ -403,7 +412,7 @@ __global__ void __launch_bounds__(1024) proj_resolve_kernel(ProjProblem* probs) 
       }
       if (accept) {
         P.assign[bestIdx] = j;
-        P.taken[bestIdx] = P.has_obs[j] ? 1 : 0;
+        taken[bestIdx] = P.has_obs[j] ? 1 : 0;
         P.acc_kp[j] = bestIdx;
         atomicAdd(&s_nmatch, 1);
         if (P.kind == 1 && P.check_ori) {
@@ -577,6 +586,7 @@ struct Matcher {
   long long launches = 0;
   double last_ms = 0;
   size_t cand_per_query = 48;  // initial candidate budget, grows on overflow
+  size_t resolve_smem_attr = 48 * 1024;
 
   int init() {
     if (initialized) return 0;
@@ -747,7 +757,19 @@ static int run_projection(Matcher& M, int count, int kind, const orb_frame_view*
     if (max_nq > 0) proj_setup_kernel<<<qgrid, 128, 0, s>>>(d_probs);
     proj_scan_kernel<<<count, 1024, 0, s>>>(d_probs);
     if (max_nq > 0) proj_fill_kernel<<<qgrid, 128, 0, s>>>(d_probs);
-    proj_resolve_kernel<<<count, 1024, 0, s>>>(d_probs);
+    {
+      int max_nk = 0;
+      for (int k = 0; k < count; k++) max_nk = std::max(max_nk, P[k].F.n);
+      int smem_nk = (max_nk + 3) & ~3;
+      size_t smem_bytes = (size_t)smem_nk * 6;
+      if (smem_bytes > 160 * 1024) { smem_nk = 0; smem_bytes = 0; }
+      if (smem_bytes > M.resolve_smem_attr) {
+        CUDA_TRYM(cudaFuncSetAttribute(proj_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem_bytes));
+        M.resolve_smem_attr = smem_bytes;
+      }
+      proj_resolve_kernel<<<count, 1024, smem_bytes, s>>>(d_probs, smem_nk);
+    }
     M.launches += 5;
     const size_t out_bytes = M.out_arena.used;
     CUDA_TRYM(cudaMemcpyAsync(M.h_out.h, M.out_arena.d, out_bytes, cudaMemcpyDeviceToHost, s));
