@@ -537,6 +537,13 @@ def main():
         dom = max(kern, key=lambda k: kern[k][0])
         achieved = alg[dom] * B / (per_launch_ms(dom) * 1e-3) / 1e9
         total_ms = sum(v[0] for v in kern.values()) + sum(ms_match)
+        traffic = None
+        try:  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+            tr = json.load(open(os.path.join(ROOT, "profiles", "fast_cells_traffic_r1.json")))
+            if dom == "fast":
+                traffic = tr["dram_bytes_per_launch"] * B / tr["batch"]
+        except Exception:
+            pass
         fps_dev = world * B * K / (ms_dev * 1e-3)
         fps_e2e = world * B * K / (ms_e2e * 1e-3)
         stage = {k: v[0] / K for k, v in st.items()}
@@ -578,7 +585,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / hbm_peak, "traffic": traffic, "algorithmic_bytes_per_launch": alg[dom] * B,
+                         "peak_source": peak_src,
                          "share_of_step": kern[dom][0] / total_ms, "stage_ms_per_step": stage,
                          "per_kernel": per_kernel},
             "cpu_baseline": cpu,
