@@ -1,0 +1,92 @@
+"""Committed golden vectors (tests/golden/, made by scripts/make_golden.py in the build
+container): cv2's own outputs pin the oracle's OpenCV primitives where cv2 is absent; the oracle's
+outputs on seeded inputs pin both the oracle (regression) and the GPU path."""
+import os
+
+import numpy as np
+import pytest
+
+from orb_slam3_b200 import scenes
+from orb_slam3_b200.synth import synth_frame, shifted_frame
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _load(name):
+    return np.load(os.path.join(G, name), allow_pickle=False)
+
+
+def test_oracle_primitives_match_cv2_golden(oracle):
+    z = _load("primitives_cv2.npz")
+    assert np.array_equal(oracle.resize_linear_u8(z["img"], 133, 100), z["resize_img"])
+    assert np.array_equal(oracle.resize_linear_u8(z["rnd"], 109, 81), z["resize_rnd"])
+    assert np.array_equal(oracle.gaussian_blur7(z["img"]), z["blur_img"])
+    assert np.array_equal(oracle.gaussian_blur7(z["rnd"]), z["blur_rnd"])
+    assert np.array_equal(oracle.fast(z["img"], 20), z["fast20"])
+    assert np.array_equal(oracle.fast(z["img"], 7), z["fast7"])
+    got = np.array([oracle.fast_atan2(y, x) for y, x in zip(z["atan_y"], z["atan_x"])], np.float32)
+    assert np.array_equal(got, z["atan"])
+    assert np.array_equal(synth_frame(120, 160, 3), z["img"])  # the generator itself is pinned too
+
+
+def _scene():
+    z = _load("extract_640x480.npz")
+    f0 = synth_frame(480, 640, 1)
+    f1 = shifted_frame(f0, 5, -3, 2)
+    return z, f0, f1
+
+
+def test_oracle_reproduces_golden(oracle):
+    z, f0, f1 = _scene()
+    k, d, mono = oracle.OracleExtractor(1000).extract(f0)
+    assert mono == int(z["mono"]) and np.array_equal(d, z["desc"])
+    for f in k.dtype.names:
+        assert np.array_equal(k[f], z["kps"][f]), f
+    k1, d1, _ = oracle.OracleExtractor(1000).extract(f1)
+    m = _load("match_scene.npz")
+    cur, last, Tcw = scenes.last_frame_scene(k, d, k1, d1, 640, 480, (5, -3), seed=3, stereo=True)
+    n, a = oracle.match_project_last(cur, last, Tcw, 15.0)
+    assert n == int(m["n_last"]) and np.array_equal(a, m["a_last"])
+    F, mps = scenes.local_map_scene(k1, d1, 640, 480, 400, seed=4)
+    n, a = oracle.match_project_local(F, mps, 3.0, 0.8)
+    assert n == int(m["n_loc"]) and np.array_equal(a, m["a_loc"])
+    kf1, kf2, fv1, fv2, F12, ep = scenes.triangulation_scene(k, d, k1, d1, 640, 480, seed=5, n_nodes=60)
+    n, p = oracle.match_triangulate(kf1, kf2, fv1, fv2, F12, ep)
+    assert n == int(m["n_tri"]) and np.array_equal(p, m["pairs"])
+    g, _ = scenes.lba_graph(8, 300, seed=1)
+    r = oracle.lba_solve(scenes.lba_view(g))
+    zl = _load("lba_small.npz")
+    assert r["iterations"] == int(zl["iterations"]) and r["stats"]["trials"] == int(zl["trials"])
+    assert np.allclose(r["kf_pose"], zl["kf_pose"], rtol=0, atol=1e-9)
+    assert np.allclose(r["mp_pos"], zl["mp_pos"], rtol=0, atol=1e-7)
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_golden():
+    from orb_slam3_b200.extractor import ORBextractor
+    from orb_slam3_b200.matcher import ORBmatcher
+    from orb_slam3_b200.optimizer import LocalBundleAdjustment
+    z, f0, f1 = _scene()
+    ext = ORBextractor(1000, 1.2, 8, 20, 7)
+    mono, k, d = ext(f0)
+    assert mono == int(z["mono"]) and np.array_equal(d, z["desc"])
+    for f in k.dtype.names:
+        assert np.array_equal(k[f], z["kps"][f]), f
+    _, k1, d1 = ext(f1)
+    m = _load("match_scene.npz")
+    cur, last, Tcw = scenes.last_frame_scene(k, d, k1, d1, 640, 480, (5, -3), seed=3, stereo=True)
+    n, a = ORBmatcher(0.9, True).SearchByProjectionLast(cur, last, Tcw, 15.0)
+    assert n == int(m["n_last"]) and np.array_equal(a, m["a_last"])
+    F, mps = scenes.local_map_scene(k1, d1, 640, 480, 400, seed=4)
+    n, a = ORBmatcher(0.8).SearchByProjection(F, mps, 3.0)
+    assert n == int(m["n_loc"]) and np.array_equal(a, m["a_loc"])
+    kf1, kf2, fv1, fv2, F12, ep = scenes.triangulation_scene(k, d, k1, d1, 640, 480, seed=5, n_nodes=60)
+    n, p = ORBmatcher(0.6, True).SearchForTriangulation(kf1, kf2, fv1, fv2, F12, ep)
+    assert n == int(m["n_tri"]) and np.array_equal(p, m["pairs"])
+    g, _ = scenes.lba_graph(8, 300, seed=1)
+    r = LocalBundleAdjustment()(scenes.lba_view(g))
+    zl = _load("lba_small.npz")
+    assert r["iterations"] == int(zl["iterations"]) and r["stats"]["trials"] == int(zl["trials"])
+    step = np.abs(zl["mp_pos"] - g["mp_pos"]).max()
+    assert np.abs(r["mp_pos"] - zl["mp_pos"]).max() < 1e-4 * step
+    assert np.abs(r["kf_pose"] - zl["kf_pose"]).max() < 1e-6
