@@ -339,28 +339,50 @@ __global__ void __launch_bounds__(128) lm_prepare_kernel(LbaDev D, double lambda
 // The Schur contraction on the tensor cores: one CTA (4 warps) per pose pair
 // (i1 <= i2); every shared landmark contributes a 6x3 * 3x6 product, issued as an
 // fp64 DMMA m8n8k4 (A = Y_{i1,l} padded to 8x4, B = W_{i2,l}^T padded to 4x8).
-__global__ void __launch_bounds__(128) schur_pairs_kernel(LbaDev D) {
-  __shared__ double part[4][64];
+__global__ void __launch_bounds__(256) schur_pairs_kernel(LbaDev D) {
+  __shared__ double part[8][64];
   const int p = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   const bool live = (g < 6) && (t < 3);
   const int off = g * 3 + t;
-  double c0 = 0, c1 = 0;
+  // two accumulator pairs so consecutive DMMAs do not serialise on the C operand
+  double c0 = 0, c1 = 0, e0 = 0, e1 = 0;
   const int beg = D.pair_ptr[p], end = D.pair_ptr[p + 1];
-  for (int i = beg + warp; i < end; i += 4) {
-    const double a = live ? D.Y[18 * (size_t)D.pair_ea[i] + off] : 0.0;
-    const double b = live ? D.W[18 * (size_t)D.pair_eb[i] + off] : 0.0;
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
+  for (int i0 = beg + warp * 4; i0 < end; i0 += 8 * 4) {
+    // 4 entries per trip: all index loads, then all operand loads, then the DMMAs (the loop is a
+    // chain of dependent L2 accesses otherwise)
+    int ea[4], eb[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = i0 + u;
+      ea[u] = i < end ? D.pair_ea[i] : -1;
+      eb[u] = i < end ? D.pair_eb[i] : -1;
+    }
+    double a[4], b[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      a[u] = (live && ea[u] >= 0) ? D.Y[18 * (size_t)ea[u] + off] : 0.0;
+      b[u] = (live && eb[u] >= 0) ? D.W[18 * (size_t)eb[u] + off] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u += 2) {
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                   : "+d"(c0), "+d"(c1)
+                   : "d"(a[u]), "d"(b[u]));
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                   : "+d"(e0), "+d"(e1)
+                   : "d"(a[u + 1]), "d"(b[u + 1]));
+    }
   }
-  part[warp][g * 8 + 2 * t] = c0;
-  part[warp][g * 8 + 2 * t + 1] = c1;
+  part[warp][g * 8 + 2 * t] = c0 + e0;
+  part[warp][g * 8 + 2 * t + 1] = c1 + e1;
   __syncthreads();
   if (threadIdx.x < 36) {
     const int r = threadIdx.x / 6, c = threadIdx.x % 6;  // r: dims of pose i1, c: dims of pose i2
-    const double v = part[0][r * 8 + c] + part[1][r * 8 + c] + part[2][r * 8 + c] + part[3][r * 8 + c];
+    double v = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) v += part[w][r * 8 + c];
     const int i1 = D.pair_i1[p], i2 = D.pair_i2[p];
     double out = -v;
     if (i1 == i2) out += D.Hpp[36 * (size_t)i1 + r * 6 + c];
@@ -503,31 +525,46 @@ __global__ void __launch_bounds__(256) ldlt_kernel(double* __restrict__ M, int n
   }
 }
 
-// L^T x = z  (z = row n of M after ldlt_kernel).  Single CTA, right-looking.
+// L^T x = z  (z = row n of M after ldlt_kernel).  Single CTA, right-looking: solve the last
+// 32 unknowns from a shared-memory copy of their diagonal block, then subtract their
+// contribution from every earlier right-hand side (rows of L are contiguous: coalesced).
 __global__ void __launch_bounds__(1024) backsub_kernel(const double* __restrict__ M, int n, double* __restrict__ x) {
   extern __shared__ double acc[];  // n entries
   __shared__ double xb[NB];
+  __shared__ double Lb[NB][NB + 1];
   for (int i = threadIdx.x; i < n; i += 1024) acc[i] = M[(size_t)n * n + i];
-  __syncthreads();
   const int nblocks = (n + NB - 1) / NB;
   for (int b = nblocks - 1; b >= 0; b--) {
     const int k0 = b * NB, nb = min(NB, n - k0);
+    {
+      const int r = threadIdx.x >> 5, c = threadIdx.x & 31;  // 1024 threads = 32 x 32
+      Lb[r][c] = (r < nb && c < r) ? M[(size_t)(k0 + r) * n + k0 + c] : 0.0;
+    }
+    __syncthreads();
     if (threadIdx.x < 32) {
       // unit upper-triangular solve inside the block, last row first
       const int r = threadIdx.x;
       double v = (r < nb) ? acc[k0 + r] : 0.0;
       for (int c = nb - 1; c >= 0; c--) {
         const double xc = __shfl_sync(0xffffffffu, v, c);
-        if (r < c) v -= M[(size_t)(k0 + c) * n + k0 + r] * xc;
+        if (r < c) v -= Lb[c][r] * xc;
       }
       if (r < nb) { xb[r] = v; x[k0 + r] = v; }
     }
     __syncthreads();
-    // acc[j] -= sum_{i in block} L[i][j] x_i for j < k0 (rows are contiguous: coalesced)
+    // acc[j] -= sum_{i in block} L[i][j] x_i for j < k0
     for (int j = threadIdx.x; j < k0; j += 1024) {
-      double s = 0;
-      for (int i = 0; i < nb; i++) s += M[(size_t)(k0 + i) * n + j] * xb[i];
-      acc[j] -= s;
+      const double* col = M + (size_t)k0 * n + j;
+      double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+      int i = 0;
+      for (; i + 4 <= nb; i += 4) {  // four independent loads in flight
+        s0 += col[(size_t)i * n] * xb[i];
+        s1 += col[(size_t)(i + 1) * n] * xb[i + 1];
+        s2 += col[(size_t)(i + 2) * n] * xb[i + 2];
+        s3 += col[(size_t)(i + 3) * n] * xb[i + 3];
+      }
+      for (; i < nb; i++) s0 += col[(size_t)i * n] * xb[i];
+      acc[j] -= (s0 + s1) + (s2 + s3);
     }
     __syncthreads();
   }
@@ -953,7 +990,7 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
       // Schur complement
       CUDA_TRYL(cudaMemsetAsync(D.S, 0, sizeof(double) * nS, st));
       if (L) lm_prepare_kernel<<<lm_blocks, 128, 0, st>>>(D, lambda);
-      schur_pairs_kernel<<<n_pairs, 128, 0, st>>>(D);
+      schur_pairs_kernel<<<n_pairs, 256, 0, st>>>(D);
       bschur_kernel<<<nf, 128, 0, st>>>(D);
       S.launches += 3;
       // landmark shards: every rank holds its partial H_pp, b_p and Schur terms; one sum gives (S | b_s)
