@@ -321,7 +321,11 @@ class Workload:
         r1, _ = self.m_last.project_last_batch(curs, lasts, self.meta[p]["T"], TH_LAST, on_device=True,
                                                assign_ptrs=a1)
         r2, _ = self.m_local.project_local_batch(Fs, Ms, TH_LOCAL, on_device=True, assign_ptrs=a2)
-        self.nmatch_last, self.nmatch_local = r1, r2
+        self.nmatch_last, self.nmatch_local = r1, r2  # filled when the asynchronous batches complete
+
+    def finish_device(self):
+        self.m_last.synchronize()
+        self.m_local.synchronize()
 
     def step_host(self, i):
         from orb_slam3_b200._lib import check, ptr
@@ -441,9 +445,13 @@ def main():
     def launches_now():
         return wl.ext.kernel_launches() + wl.m_last.kernel_launches() + wl.m_local.kernel_launches()
 
-    # ---- device-resident metric
+    # ---- device-resident metric (matcher batches are asynchronous: the host prepares the next
+    # submission while the GPU works; everything is ordered on one stream)
+    for m in (wl.m_last, wl.m_local):
+        m.set_async(True)
     for i in range(Wm):
         wl.step_device(i)
+    wl.finish_device()
     launches0 = launches_now()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -453,6 +461,7 @@ def main():
     for i in range(K):
         wl.step_device(i)
     e1.record()
+    wl.finish_device()
     barrier()
     ms_dev = e0.elapsed_time(e1)
     launches = launches_now() - launches0
@@ -462,6 +471,8 @@ def main():
     # own extractor + matcher handles, i.e. its own CUDA streams) work on different batches at once:
     # one batch's PCIe copies and host staging overlap another batch's kernels.
     from concurrent.futures import ThreadPoolExecutor
+    for m in (wl.m_last, wl.m_local):
+        m.set_async(False)
     workers = [wl] + [Workload(B, POOL, rank, local_rank, None, share=wl) for _ in range(args.e2e_workers - 1)]
     for w in workers[1:]:
         for m in (w.m_last, w.m_local):
@@ -493,6 +504,8 @@ def main():
     wl.ext.set_profiling(True)
     wl.ext.stage_times(reset=True)
     ms_match = [0.0, 0.0]
+    for m in (wl.m_last, wl.m_local):
+        m.set_async(False)
     for i in range(K):
         wl.step_device(i)
         ms_match[0] += wl.m_last.last_ms()

@@ -221,6 +221,11 @@ int match_triangulate_batch(orb_matcher* m, int count, const orb_frame_view* kf1
 /* Submit subsequent batches on `cuda_stream` (a cudaStream_t) instead of the
  * matcher's own stream, e.g. the stream an extractor ran on; NULL restores it. */
 int match_set_stream(orb_matcher* m, void* cuda_stream);
+/* Asynchronous mode for device-resident batches (on_device != 0): the *_batch call returns after
+ * enqueueing; `results` (which must stay valid) and the device outputs are complete after
+ * match_synchronize() or the next batch on the same handle.  A candidate-buffer overflow is then
+ * reported by that call as ORB_E_CAPACITY (the budget has been grown: re-submit the batch). */
+int match_set_async(orb_matcher* m, int enabled);
 int match_synchronize(orb_matcher* m);
 long long match_kernel_launches(const orb_matcher* m);
 /* Device time of the last batch (CUDA events on the matcher's stream), ms. */

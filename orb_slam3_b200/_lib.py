@@ -56,6 +56,7 @@ SIGNATURES = {
     "match_project_local_batch": (_i, [_vp, _i, _vp, _vp, _f, _f, _i, _f, _vp, _vp, _i]),
     "match_triangulate_batch": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _i]),
     "match_set_stream": (_i, [_vp, _vp]),
+    "match_set_async": (_i, [_vp, _i]),
     "match_synchronize": (_i, [_vp]),
     "match_kernel_launches": (C.c_longlong, [_vp]),
     "match_last_ms": (C.c_double, [_vp]),

@@ -587,6 +587,12 @@ struct Matcher {
   double last_ms = 0;
   size_t cand_per_query = 48;  // initial candidate budget, grows on overflow
   size_t resolve_smem_attr = 48 * 1024;
+  // asynchronous mode (device-resident problems only): one batch may be in flight per handle
+  bool async_mode = false, pending = false;
+  int pending_count = 0;
+  std::vector<size_t> pending_off;
+  int32_t* pending_results = nullptr;
+  int finish_pending();
 
   int init() {
     if (initialized) return 0;
@@ -654,6 +660,26 @@ static void stage_frame(Stager& st, const orb_frame_view& v, DevFrame& d) {
 template <class T>
 static T* carve_dev(Arena& a, size_t count) { return (T*)(a.d + a.take(count * sizeof(T))); }
 
+int Matcher::finish_pending() {
+  if (!pending) return 0;
+  pending = false;
+  cudaStream_t s = user_stream ? user_stream : stream;
+  CUDA_TRYM(cudaStreamSynchronize(s));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ev0, ev1);
+  last_ms = ms;
+  for (int k = 0; k < pending_count; k++) {
+    const int* r = (const int*)(h_out.h + pending_off[k]);
+    if (r[1]) {
+      cand_per_query *= 4;
+      set_last_error("candidate buffer overflow in an asynchronous batch: re-submit it");
+      return ORB_E_CAPACITY;
+    }
+  }
+  for (int k = 0; k < pending_count; k++) pending_results[k] = ((const int*)(h_out.h + pending_off[k]))[0];
+  return 0;
+}
+
 static int run_projection(Matcher& M, int count, int kind, const orb_frame_view* F, const orb_mappoint_view* mps,
                           const orb_lastframe_view* last, const float* Tcw, const int32_t* forward,
                           const int32_t* backward, float th, float ratio, int far_points, float th_far,
@@ -662,6 +688,7 @@ static int run_projection(Matcher& M, int count, int kind, const orb_frame_view*
   int rc = M.init();
   if (rc) return rc;
   CUDA_TRYM(cudaSetDevice(M.device));
+  if ((rc = M.finish_pending())) return rc;  // the arenas are about to be reused
   std::vector<ProjProblem> P(count);
   for (int attempt = 0; attempt < 6; attempt++) {
     // ---- stage inputs (sizing pass, then copy pass)
@@ -774,6 +801,11 @@ static int run_projection(Matcher& M, int count, int kind, const orb_frame_view*
     const size_t out_bytes = M.out_arena.used;
     CUDA_TRYM(cudaMemcpyAsync(M.h_out.h, M.out_arena.d, out_bytes, cudaMemcpyDeviceToHost, s));
     CUDA_TRYM(cudaEventRecord(M.ev1, s));
+    if (M.async_mode && on_device) {
+      // results land in `results` at match_synchronize() / the next batch on this handle
+      M.pending = true; M.pending_count = count; M.pending_off = out_off; M.pending_results = results;
+      return count;
+    }
     CUDA_TRYM(cudaStreamSynchronize(s));
     float ms = 0;
     cudaEventElapsedTime(&ms, M.ev0, M.ev1);
@@ -809,6 +841,7 @@ static int run_triangulate(Matcher& M, int count, const orb_frame_view* kf1, con
   int rc = M.init();
   if (rc) return rc;
   CUDA_TRYM(cudaSetDevice(M.device));
+  if ((rc = M.finish_pending())) return rc;
   std::vector<TriProblem> P(count);
   Stager st{on_device != 0};
   std::vector<int> nfeat(count);
@@ -979,9 +1012,16 @@ int match_set_stream(orb_matcher* m, void* cuda_stream) {
   return ORB_OK;
 }
 
+int match_set_async(orb_matcher* m, int enabled) {
+  if (!m) return ORB_E_ARG;
+  m->m.async_mode = enabled != 0;
+  return ORB_OK;
+}
+
 int match_synchronize(orb_matcher* m) {
   if (!m || !m->m.initialized) return ORB_E_ARG;
   cudaSetDevice(m->m.device);
+  if (m->m.pending) return m->m.finish_pending();
   return cudaStreamSynchronize(m->m.user_stream ? m->m.user_stream : m->m.stream) == cudaSuccess ? ORB_OK : ORB_E_CUDA;
 }
 long long match_kernel_launches(const orb_matcher* m) { return m ? m->m.launches : 0; }

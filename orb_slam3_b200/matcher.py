@@ -72,6 +72,7 @@ class ORBmatcher:
         fw = np.ascontiguousarray(np.zeros(B) if forward is None else forward, np.int32)
         bw = np.ascontiguousarray(np.zeros(B) if backward is None else backward, np.int32)
         res = np.zeros(B, np.int32)
+        self._last_res = res  # must outlive an asynchronous batch
         if on_device:
             outs = None
             arr = (C.c_void_p * B)(*assign_ptrs)
@@ -89,6 +90,7 @@ class ORBmatcher:
         fa = (orb_frame_view * B)(*frames)
         ma = (orb_mappoint_view * B)(*mps)
         res = np.zeros(B, np.int32)
+        self._last_res = res
         if on_device:
             outs = None
             arr = (C.c_void_p * B)(*assign_ptrs)
@@ -117,6 +119,12 @@ class ORBmatcher:
 
     def set_stream(self, cuda_stream):
         check(self._lib.match_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
+
+    def set_async(self, on):
+        check(self._lib.match_set_async(self._h, int(on)))
+
+    def synchronize(self):
+        check(self._lib.match_synchronize(self._h))
 
     def last_ms(self):
         return float(self._lib.match_last_ms(self._h))
