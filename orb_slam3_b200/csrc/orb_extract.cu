@@ -380,7 +380,9 @@ octree_kernel(const Cand* __restrict__ cand, size_t cand_frame_stride, const int
               int smem_node_cap) {
   __shared__ int smem_ints[48];
   extern __shared__ int oct_dyn[];
-  const int level = blockIdx.x, f = blockIdx.y;
+  // level-major launch order (blockIdx.x = frame): all the heavy level-0 CTAs start in the first
+  // wave and the light high levels back-fill the SMs as they drain
+  const int level = blockIdx.y, f = blockIdx.x;
   const LevelDev L = lv[level];
   CtaBackend be;
   be.smem_ints = smem_ints;
@@ -956,7 +958,7 @@ int Engine::run_device(int f0, int batch, const int* lap_host, cudaStream_t s) {
   stage_end(2, s, 1);
   // 3. octree
   stage_begin(3, s);
-  octree_kernel<<<dim3(nlevels, B), OCT_THREADS, oct_smem_bytes, s>>>(cand, cand_frame_elems, cand_count, d_levels,
+  octree_kernel<<<dim3(B, nlevels), OCT_THREADS, oct_smem_bytes, s>>>(cand, cand_frame_elems, cand_count, d_levels,
                                                                       scratch, scratch_frame_bytes, sel,
                                                                       3 * sel_frame_elems, sel_count, nlevels,
                                                                       oct_smem_node_cap);
