@@ -599,7 +599,22 @@ describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blr
   const float factorPI = 0.017453292519943295f;  // (float)(CV_PI/180.f)
   const float ang = __fmul_rn(angle, factorPI);
   const float a = (float)cos((double)ang), b = (float)sin((double)ang);
-  const uint8_t* bc = blr + (size_t)f * frame_stride + L.img_off + (size_t)y * L.pitch + x;
+  // stage the 37x37 blurred patch (rotated pattern offsets are within +-18) in shared memory with
+  // coalesced aligned word loads; the 512 samples then gather from shared memory instead of
+  // issuing ~25 L1 wavefronts per load instruction
+  constexpr int PR = 18, PW = 11, PP = PW * 4;  // 11 words = 44 bytes cover [x-18, x+18] from an aligned start
+  __shared__ __align__(16) uint8_t s_patch[8][(2 * PR + 1) * PP];
+  uint8_t* patch = s_patch[threadIdx.x >> 5];
+  const int a0 = (x - PR) & ~3;
+  {
+    const uint8_t* bsrc = blr + (size_t)f * frame_stride + L.img_off + (size_t)(y - PR) * L.pitch + a0;
+    for (int idx = lane; idx < (2 * PR + 1) * PW; idx += 32) {
+      const int r = idx / PW, w = idx - r * PW;
+      reinterpret_cast<uint32_t*>(patch)[idx] = *reinterpret_cast<const uint32_t*>(bsrc + (size_t)r * L.pitch + 4 * w);
+    }
+  }
+  __syncwarp();
+  const uint8_t* bc = patch + PR * PP + (x - a0);
   const int* pat = c_pattern + 32 * lane;
   int val = 0;
 #pragma unroll
@@ -610,7 +625,7 @@ describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blr
     const int rx0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
     const int ry1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
     const int rx1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-    const int t0 = bc[ry0 * L.pitch + rx0], t1 = bc[ry1 * L.pitch + rx1];
+    const int t0 = bc[ry0 * PP + rx0], t1 = bc[ry1 * PP + rx1];
     val |= (t0 < t1) << k;
   }
   desc[((size_t)f * out_cap + pos) * 32 + lane] = (uint8_t)val;
@@ -836,7 +851,7 @@ int Engine::ensure(int rows, int cols, int batch) {
 
   const size_t B = batch;
   if (dalloc(&d_pyr, pyr_frame_bytes * B)) return ORB_E_CUDA;
-  if (dalloc(&d_blur, pyr_frame_bytes * B)) return ORB_E_CUDA;
+  if (dalloc(&d_blur, pyr_frame_bytes * B + 256)) return ORB_E_CUDA;
   if (dalloc(&d_cand, cand_frame_elems * B)) return ORB_E_CUDA;
   if (dalloc(&d_scratch, scratch_frame_bytes * B)) return ORB_E_CUDA;
   if (dalloc(&d_sel, 3 * sel_frame_elems * B)) return ORB_E_CUDA;
