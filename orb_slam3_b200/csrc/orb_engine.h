@@ -68,7 +68,7 @@ struct Engine {
   Cand* d_cand = nullptr;
   int *d_sel = nullptr, *d_slot = nullptr, *d_cand_count = nullptr, *d_sel_count = nullptr;
   int *d_n = nullptr, *d_mono = nullptr, *d_lap = nullptr, *d_warp_level = nullptr;
-  int *d_xofs = nullptr, *d_yofs = nullptr;
+  int *d_xofs = nullptr, *d_yofs = nullptr, *d_pattern_t = nullptr;
   short2 *d_alpha = nullptr, *d_beta = nullptr;
   orb_keypoint* d_kps = nullptr;
   LevelDev* d_levels = nullptr;

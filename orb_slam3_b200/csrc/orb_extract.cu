@@ -26,7 +26,7 @@
 namespace orbb200 {
 
 // ----------------------------------------------------------------- constants
-__constant__ int c_pattern[1024];
+__constant__ int c_pattern[1024];  // (kept for reference; the kernels read the lane-transposed copy below)
 __constant__ int c_umax[16];
 static const int h_pattern[1024] = {
 #include "pattern_31.inc"
@@ -563,8 +563,13 @@ __global__ void __launch_bounds__(256)
 describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blr, size_t frame_stride,
                 const int* __restrict__ sel, size_t sel_frame_stride, const int* __restrict__ sel_count,
                 const int* __restrict__ slot, const LevelDev* __restrict__ lv, int nlevels,
-                const int* __restrict__ warp_level, orb_keypoint* __restrict__ kps,
-                uint8_t* __restrict__ desc, int out_cap) {
+                const int* __restrict__ warp_level, const int* __restrict__ pattern_t,
+                orb_keypoint* __restrict__ kps, uint8_t* __restrict__ desc, int out_cap) {
+  // rBRIEF pattern, lane-transposed ([word j][lane]): lane-dependent indexing of __constant__
+  // memory would serialise into 32 replays per load
+  __shared__ int s_pat[1024];
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_pat[i] = pattern_t[i];
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // index in the sel slab
   const int f = blockIdx.y;
@@ -615,12 +620,11 @@ describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blr
   }
   __syncwarp();
   const uint8_t* bc = patch + PR * PP + (x - a0);
-  const int* pat = c_pattern + 32 * lane;
   int val = 0;
 #pragma unroll
   for (int k = 0; k < 8; k++) {
-    const float x0 = (float)pat[4 * k], y0 = (float)pat[4 * k + 1];
-    const float x1 = (float)pat[4 * k + 2], y1 = (float)pat[4 * k + 3];
+    const float x0 = (float)s_pat[(4 * k) * 32 + lane], y0 = (float)s_pat[(4 * k + 1) * 32 + lane];
+    const float x1 = (float)s_pat[(4 * k + 2) * 32 + lane], y1 = (float)s_pat[(4 * k + 3) * 32 + lane];
     const int ry0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
     const int rx0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
     const int ry1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
@@ -867,6 +871,13 @@ int Engine::ensure(int rows, int cols, int batch) {
   if (dalloc(&d_cells, cells.size())) return ORB_E_CUDA;
   if (dalloc(&d_tiles, tiles.size())) return ORB_E_CUDA;
   if (dalloc(&d_warp_level, warp_level.size())) return ORB_E_CUDA;
+  if (dalloc(&d_pattern_t, (size_t)1024)) return ORB_E_CUDA;
+  {
+    std::vector<int> pt(1024);
+    for (int lane = 0; lane < 32; lane++)
+      for (int j = 0; j < 32; j++) pt[j * 32 + lane] = h_pattern[32 * lane + j];
+    CUDA_TRY(cudaMemcpy(d_pattern_t, pt.data(), sizeof(int) * 1024, cudaMemcpyHostToDevice));
+  }
   if (dalloc(&d_xofs, h_xofs.size())) return ORB_E_CUDA;
   if (dalloc(&d_yofs, h_yofs.size())) return ORB_E_CUDA;
   if (dalloc(&d_alpha, h_alpha.size())) return ORB_E_CUDA;
@@ -988,7 +999,7 @@ int Engine::run_device(int f0, int batch, const int* lap_host, cudaStream_t s) {
   if (side_stream_used) CUDA_TRY(cudaStreamWaitEvent(s, ev_blur_done, 0));
   describe_kernel<<<dim3((unsigned)(sel_frame_elems / 8), B), 256, 0, s>>>(
       pyr, blr, pyr_frame_bytes, sel, 3 * sel_frame_elems, sel_count, slot, d_levels, nlevels, d_warp_level,
-      d_kps + (size_t)f0 * out_cap, d_desc + (size_t)f0 * out_cap * 32, out_cap);
+      d_pattern_t, d_kps + (size_t)f0 * out_cap, d_desc + (size_t)f0 * out_cap * 32, out_cap);
   stage_end(6, s, 1);
   CUDA_TRY(cudaGetLastError());
   return 0;
