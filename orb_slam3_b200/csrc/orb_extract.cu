@@ -237,8 +237,10 @@ fast_cells_kernel(const uint8_t* __restrict__ pyr, size_t frame_stride,
   // The reference calls cv::FAST(cell, iniThFAST) and only when that returns nothing
   // cv::FAST(cell, minThFAST) (:826-846).  Same here: pass 0 at iniTh (few pixels survive the
   // cheap test), pass 1 at minTh only for the rare cells that came out empty.
-  const unsigned magic = ((1u << 20) + bw - 1) / bw;  // idx / bw for idx < 70*70
-  const int npx = bw * bh;
+  // 4-pixel groups = aligned words of a tile row that overlap the band columns [ox+3, ox+3+bw)
+  const int g0 = (ox + 3) >> 2, ng = ((ox + 3 + bw + 3) >> 2) - g0;
+  const int nitems = bh * ng;                           // <= 70 * 19
+  const unsigned magic_g = ((1u << 20) + ng - 1) / ng;  // idx / ng for idx < 70*19
   unsigned long long keep_bits = 0;
   int qn = 0;
   for (int pass = 0; pass < 2; pass++) {
@@ -247,25 +249,39 @@ fast_cells_kernel(const uint8_t* __restrict__ pyr, size_t frame_stride,
       const int nz = ((bw + 2) * (bh + 2) + 3) >> 2;
       for (int i = threadIdx.x; i < nz; i += FAST_THREADS) reinterpret_cast<uint32_t*>(smap)[i] = 0;
     }
-    // 2. cheap rejection on every band pixel (linear index, full warps): a 9-arc contains one
-    //    end of every diameter, so a corner needs (k or k+8) brighter -- or darker -- for each
-    //    of the 8 diameters; 4 are tested here.  Survivors stay as one bit per visit (<= 39).
+    // 2. cheap rejection, 4 pixels per thread on packed bytes: a 9-arc contains one end of every
+    //    diameter, so a corner needs |ring - centre| > t at one end of each of the 8 diameters; 4
+    //    diameters are tested with VABSDIFF4 + a SWAR compare on aligned 32-bit shared-memory
+    //    words (sign consistency is left to the exact test: the filter only has to be a superset).
+    //    Survivors stay as one bit per (visit, byte): <= 11 visits x 4.
     unsigned long long pass_bits = 0;
     {
+      const uint32_t* tw32 = reinterpret_cast<const uint32_t*>(tile);
+      constexpr int PWD = FAST_TILE_PITCH / 4;
+      const uint32_t t4 = 0x01010101u * (uint32_t)th_fast;
       int it = 0;
-      for (int idx = threadIdx.x; idx < npx; idx += FAST_THREADS, it++) {
-        const int y = (int)(((unsigned)idx * magic) >> 20), x = idx - y * bw;
-        const uint8_t* c = &tile[(y + 3) * FAST_TILE_PITCH + ox + x + 3];
-        const int v = c[0], hi = v + th_fast, lo = v - th_fast;
-        const int r0 = c[3 * FAST_TILE_PITCH], r8 = c[-3 * FAST_TILE_PITCH], r4 = c[3], r12 = c[-3];
-        bool bp = ((r0 > hi) | (r8 > hi)) & ((r4 > hi) | (r12 > hi));
-        bool dp = ((r0 < lo) | (r8 < lo)) & ((r4 < lo) | (r12 < lo));
-        if (bp | dp) {
-          const int r2 = c[2 * FAST_TILE_PITCH + 2], r10 = c[-2 * FAST_TILE_PITCH - 2];
-          const int r6 = c[-2 * FAST_TILE_PITCH + 2], r14 = c[2 * FAST_TILE_PITCH - 2];
-          bp = bp & ((r2 > hi) | (r10 > hi)) & ((r6 > hi) | (r14 > hi));
-          dp = dp & ((r2 < lo) | (r10 < lo)) & ((r6 < lo) | (r14 < lo));
-          if (bp | dp) pass_bits |= 1ull << it;
+      for (int idx = threadIdx.x; idx < nitems; idx += FAST_THREADS, it++) {
+        const int y = (int)(((unsigned)idx * magic_g) >> 20), g = g0 + (idx - y * ng);
+        const uint32_t* rc = tw32 + (y + 3) * PWD + g;  // centre row, word g
+        const uint32_t v = rc[0];
+        const uint32_t r0 = rc[3 * PWD], r8 = rc[-3 * PWD];
+        const uint32_t r4 = __funnelshift_r(rc[0], rc[1], 24), r12 = __funnelshift_r(rc[-1], rc[0], 8);
+        const uint32_t* rp = rc + 2 * PWD;
+        const uint32_t* rm = rc - 2 * PWD;
+        const uint32_t r2 = __funnelshift_r(rp[0], rp[1], 16), r14 = __funnelshift_r(rp[-1], rp[0], 16);
+        const uint32_t r6 = __funnelshift_r(rm[0], rm[1], 16), r10 = __funnelshift_r(rm[-1], rm[0], 16);
+        uint32_t m = __vcmpgtu4(__vabsdiffu4(r0, v), t4) | __vcmpgtu4(__vabsdiffu4(r8, v), t4);
+        m &= __vcmpgtu4(__vabsdiffu4(r4, v), t4) | __vcmpgtu4(__vabsdiffu4(r12, v), t4);
+        m &= __vcmpgtu4(__vabsdiffu4(r2, v), t4) | __vcmpgtu4(__vabsdiffu4(r10, v), t4);
+        m &= __vcmpgtu4(__vabsdiffu4(r6, v), t4) | __vcmpgtu4(__vabsdiffu4(r14, v), t4);
+        if (m) {
+          // keep bytes whose column lies inside the band [ox+3, ox+3+bw)
+          unsigned nib = ((m >> 7) & 1u) | ((m >> 14) & 2u) | ((m >> 21) & 4u) | ((m >> 28) & 8u);
+          const int c0 = 4 * g - (ox + 3);  // band x of byte 0
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            if ((unsigned)(c0 + k) >= (unsigned)bw) nib &= ~(1u << k);
+          pass_bits |= (unsigned long long)nib << (4 * it);
         }
       }
     }
@@ -286,10 +302,11 @@ fast_cells_kernel(const uint8_t* __restrict__ pyr, size_t frame_stride,
       for (int w = 0; w < warp; w++) base += s_warp_tot[w];
       if (threadIdx.x == FAST_THREADS - 1) s_qn = base + cnt;
       while (pass_bits) {
-        const int it = __ffsll((long long)pass_bits) - 1;
+        const int bit = __ffsll((long long)pass_bits) - 1;
         pass_bits &= pass_bits - 1;
-        const int idx = threadIdx.x + it * FAST_THREADS;
-        const int y = (int)(((unsigned)idx * magic) >> 20), x = idx - y * bw;
+        const int idx = threadIdx.x + (bit >> 2) * FAST_THREADS;
+        const int y = (int)(((unsigned)idx * magic_g) >> 20), g = g0 + (idx - y * ng);
+        const int x = 4 * g + (bit & 3) - (ox + 3);
         queue[base++] = (unsigned short)((y << 8) | x);
       }
     }
