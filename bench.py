@@ -313,14 +313,30 @@ class Workload:
         self._dev_views[p] = (curs, lasts, Fs, Ms, a1, a2)
         return self._dev_views[p]
 
+    def enable_side_streams(self, main_stream):
+        """The two projection matchers only depend on the extraction, not on each other: give each
+        its own stream so their latency-bound kernels overlap (joined back before the next step)."""
+        torch = self.torch
+        self.main_stream = main_stream
+        self.side = (torch.cuda.Stream(), torch.cuda.Stream())
+        self.m_last.set_stream(self.side[0].cuda_stream)
+        self.m_local.set_stream(self.side[1].cuda_stream)
+
     def step_device(self, i):
         p = i % self.POOL
         d = self.dev_pool[p]
         self.ext.extract_batch_device(d.data_ptr(), self.B, H, W, W, H * W, stream=self.stream)
         curs, lasts, Fs, Ms, a1, a2 = self._device_views(p)
+        side = getattr(self, "side", None)
+        if side:
+            for st in side:
+                st.wait_stream(self.main_stream)
         r1, _ = self.m_last.project_last_batch(curs, lasts, self.meta[p]["T"], TH_LAST, on_device=True,
                                                assign_ptrs=a1)
         r2, _ = self.m_local.project_local_batch(Fs, Ms, TH_LOCAL, on_device=True, assign_ptrs=a2)
+        if side:  # the next extraction overwrites the keypoints/descriptors the matchers read
+            for st in side:
+                self.main_stream.wait_stream(st)
         self.nmatch_last, self.nmatch_local = r1, r2  # filled when the asynchronous batches complete
 
     def finish_device(self):
@@ -449,6 +465,7 @@ def main():
     # submission while the GPU works; everything is ordered on one stream)
     for m in (wl.m_last, wl.m_local):
         m.set_async(True)
+    wl.enable_side_streams(tstream)
     for i in range(Wm):
         wl.step_device(i)
     wl.finish_device()
@@ -506,6 +523,8 @@ def main():
     ms_match = [0.0, 0.0]
     for m in (wl.m_last, wl.m_local):
         m.set_async(False)
+        m.set_stream(tstream.cuda_stream)
+    wl.side = None
     for i in range(K):
         wl.step_device(i)
         ms_match[0] += wl.m_last.last_ms()
