@@ -26,6 +26,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <float.h>
+#include <stdlib.h>
 #include <math.h>
 #include <string.h>
 
@@ -435,7 +436,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nblocks, un
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) ldlt_kernel(double* __restrict__ M, int n, unsigned* bar, double* fail) {
+__global__ void __launch_bounds__(256) ldlt_kernel(double* __restrict__ M, int n, unsigned* bar, double* fail, int dbg) {
   __shared__ double L11[NB][NB + 1];
   __shared__ double Dd[NB];
   __shared__ double Ti[NB][NB + 1];
@@ -451,7 +452,7 @@ __global__ void __launch_bounds__(256) ldlt_kernel(double* __restrict__ M, int n
       L11[r][c] = (r < nb && c <= r) ? M[(size_t)(k0 + r) * n + k0 + c] : 0.0;
     }
     __syncthreads();
-    if (threadIdx.x < 32) {
+    if (threadIdx.x < 32 && !(dbg & 1)) {
       // left-looking LDL^T of the 32x32 block by one warp: lane r owns row r.
       // Ti holds (L*D) so column j costs one dot product of length j per lane.
       const int r = threadIdx.x;
@@ -474,7 +475,7 @@ __global__ void __launch_bounds__(256) ldlt_kernel(double* __restrict__ M, int n
     const int r0 = k0 + nb;
     {
       const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-      for (int i = r0 + blockIdx.x * 8 + warp; i < rows; i += 8 * nblk) {
+      for (int i = r0 + blockIdx.x * 8 + warp; i < rows && !(dbg & 2); i += 8 * nblk) {
         double* Mi = M + (size_t)i * n + k0;
         double a = (lane < nb) ? Mi[lane] : 0.0;
         for (int m = 0; m < nb; m++) {
@@ -496,7 +497,7 @@ __global__ void __launch_bounds__(256) ldlt_kernel(double* __restrict__ M, int n
     // ---- trailing update, 32x32 tiles (bi >= bj), rhs row is the last partial tile row
     const int T = (rows - r0 + NB - 1) / NB;
     const int ntiles = T * (T + 1) / 2;
-    for (int tile = blockIdx.x; tile < ntiles; tile += nblk) {
+    for (int tile = blockIdx.x; tile < ntiles && !(dbg & 4); tile += nblk) {
       // tile -> (bi, bj), bi >= bj
       int bi = (int)((sqrt(8.0 * tile + 1.0) - 1.0) * 0.5);
       while ((bi + 1) * (bi + 2) / 2 <= tile) bi++;
@@ -1005,7 +1006,9 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
         int nn = n;
         unsigned* bar = S.d_bar;
         double* failp = D.scalars + 3;
-        void* args[] = {&Mp, &nn, &bar, &failp};
+        static const int dbg_env = getenv("ORB_B200_LDLT_DEBUG") ? atoi(getenv("ORB_B200_LDLT_DEBUG")) : 0;
+        int dbg = dbg_env;  // timing experiments only (bit0: no diagonal factor, bit1: no panel, bit2: no trailing)
+        void* args[] = {&Mp, &nn, &bar, &failp, &dbg};
         const int blocks = std::min(S.ldlt_blocks, std::max(1, (n + 1 + NB - 1) / NB * ((n + 1 + NB - 1) / NB)));
         CUDA_TRYL(cudaLaunchCooperativeKernel((void*)ldlt_kernel, dim3(blocks), dim3(256), args, 0, st));
       }
