@@ -17,7 +17,7 @@ def run(*a):
 
 d = json.load(open(os.path.join(P, "bench_r1_n1.json")))
 r = json.load(open(os.path.join(P, "bench_r1_reference_arm.json")))
-n2 = json.load(open(os.path.join(P, "bench_r1_n2_early.json")))
+n2 = json.load(open(os.path.join(P, "bench_r1_n2.json")))
 extract_raw = run("raw", os.path.join(P, "extract_r1.ncu-rep"))
 lba_raw = run("raw", os.path.join(P, "lba_r1.ncu-rep"))
 launch = run("launches", os.path.join(P, "launches_r1.csv"))
@@ -44,7 +44,7 @@ o.append(f"| CPU port of the reference path, same box (`--impl reference`) | {r[
 c4, c5 = d["lba"]["config4"], d["lba"]["config5"]
 o.append(f"| LocalBA config 4 ({c4['config']}) | **{c4['value']:.0f}** LM iterations/s ({c4['ms_total']:.1f} ms for optimize(10), {c4['trials']} trials) vs {d['lba']['cpu_baseline_config4']['value']:.1f} on one CPU thread (g2o is single-threaded) |")
 o.append(f"| LocalBA config 5 ({c5['config']}), 1 GPU | {c5['value']:.0f} LM iterations/s ({c5['ms_total']:.1f} ms) |")
-o.append(f"| 2xB200 (earlier build of the round, `bench_r1_n2_early.json`) | {n2['value']:.0f} frames/s resident; config 5 sharded by landmark + ncclAllReduce: {n2['lba']['config5']['value']:.0f} LM iterations/s |")
+o.append(f"| 2xB200 (`bench_r1_n2.json`) | {n2['value']:.0f} frames/s resident; config 5 sharded by landmark + ncclAllReduce: {n2['lba']['config5']['value']:.0f} LM iterations/s |")
 o.append("\n## Where a step goes (CUDA events per stage, ms per 64-frame step)\n")
 o.append("| stage | ms/step | us/frame | algorithmic GB/s | frac of HBM peak (6556 GB/s measured) |\n|---|---|---|---|---|")
 for k in ["pyramid", "fast", "octree", "blur", "describe", "layout", "match_last(th15)", "match_local(th3)"]:
