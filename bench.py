@@ -3,7 +3,7 @@
 
 python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-A "step" is one pass of the front-end hot path over one batch of synthetic
+A "step" is one pass of the front-end hot path over one batch (128 per GPU) of synthetic
 1280x720 frames (BASELINE.json configs[1]: 8 levels, 2000 features): per frame
 ORB extract -> SearchByProjection against the previous frame (th 15, rotation
 check) -> SearchByProjection against ~3000 local map points (th 3).  One
@@ -426,7 +426,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--batch", type=int, default=64, help="frames per step per GPU")
+    ap.add_argument("--batch", type=int, default=128, help="frames per step per GPU")
     ap.add_argument("--pool", type=int, default=3, help="distinct batches rotated through (L2 defeat)")
     ap.add_argument("--e2e-workers", type=int, default=4, help="host threads feeding the GPU in the e2e leg")
     ap.add_argument("--no-lba", action="store_true")
