@@ -30,33 +30,34 @@ json.dump({"kernel": "fast_cells_kernel", "batch": 64, "dram_bytes_per_launch": 
            "source": "profiles/extract_r1.ncu-rep (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"},
           open(os.path.join(P, "fast_cells_traffic_r1.json"), "w"), indent=1)
 st = d["roofline"]["stage_ms_per_step"]
+B = d["config"]["frames_per_step_per_gpu"]
 pk = d["roofline"]["per_kernel"]
 o = []
 o.append("# Round 1 -- measured on 1xB200 (gpurun box, 128 logical host CPUs), synthetic data\n")
 o.append("Numbers come from `bench.py` (CUDA events on the launching stream, 20 timed steps after 3 warm-ups, three\n"
-         "batches rotated = 1.27 GB of inputs + pyramids per rotation >> 126 MB L2) and from ncu captures of the same\n"
+         "batches rotated = 2.5 GB of inputs + pyramids per rotation >> 126 MB L2) and from ncu captures of the same\n"
          "code taken under `gpurun` (files in this directory).  SM clock 1965 MHz throughout, no throttle reason active.\n")
 o.append("## Headline (`bench_r1_n1.json`, reference arm `bench_r1_reference_arm.json`)\n")
 o.append("| quantity | value |\n|---|---|")
-o.append(f"| frames/s, inputs resident in HBM (`value`) | **{d['value']:.0f}** ({d['ms_per_step']:.2f} ms per 64-frame step, {d['gpu_launches']} kernel launches / 20 steps) |")
+o.append(f"| frames/s, inputs resident in HBM (`value`) | **{d['value']:.0f}** ({d['ms_per_step']:.2f} ms per {B}-frame step, {d['gpu_launches']} kernel launches / 20 steps) |")
 o.append(f"| frames/s end to end through the host-buffer C ABI (`e2e`, {d['e2e']['host_threads']} host threads, {d['e2e']['h2d_bytes_per_step']/1e6:.0f} MB H2D + {d['e2e']['d2h_bytes_per_step']/1e6:.1f} MB D2H per step) | **{d['e2e']['value']:.0f}** |")
 o.append(f"| CPU port of the reference path, same box (`--impl reference`) | {r['value']:.0f} frames/s on {r['cpu_baseline']['cores']} std::threads (best of 4..128; 1 thread = 25 frames/s) |")
 c4, c5 = d["lba"]["config4"], d["lba"]["config5"]
 o.append(f"| LocalBA config 4 ({c4['config']}) | **{c4['value']:.0f}** LM iterations/s ({c4['ms_total']:.1f} ms for optimize(10), {c4['trials']} trials) vs {d['lba']['cpu_baseline_config4']['value']:.1f} on one CPU thread (g2o is single-threaded) |")
 o.append(f"| LocalBA config 5 ({c5['config']}), 1 GPU | {c5['value']:.0f} LM iterations/s ({c5['ms_total']:.1f} ms) |")
 o.append(f"| 2xB200 (`bench_r1_n2.json`) | {n2['value']:.0f} frames/s resident; config 5 sharded by landmark + ncclAllReduce: {n2['lba']['config5']['value']:.0f} LM iterations/s |")
-o.append("\n## Where a step goes (CUDA events per stage, ms per 64-frame step)\n")
+o.append(f"\n## Where a step goes (CUDA events per stage, ms per {B}-frame step)\n")
 o.append("| stage | ms/step | us/frame | algorithmic GB/s | frac of HBM peak (6556 GB/s measured) |\n|---|---|---|---|---|")
 for k in ["pyramid", "fast", "octree", "blur", "describe", "layout", "match_last(th15)", "match_local(th3)"]:
     key = k if k in pk else ("match_local" if k.startswith("match_local") else None)
     g = pk[key]["GB/s"] if key in pk else None
-    o.append(f"| {k} | {st[k]:.3f} | {st[k]*1000/64:.1f} | {'' if g is None else '%.0f' % g} | {'' if g is None else '%.3f' % pk[key]['frac_of_hbm']} |")
+    o.append(f"| {k} | {st[k]:.3f} | {st[k]*1000/B:.1f} | {'' if g is None else '%.0f' % g} | {'' if g is None else '%.3f' % pk[key]['frac_of_hbm']} |")
 o.append("\n(per-stage events are taken with everything on one stream; in the timed `value` run the blur and the two\n"
          "matchers run on side streams, which is why the stages add up to more than `ms_per_step`.)\n")
 rf = d["roofline"]
 o.append(f"`roofline` of the bench line: dominant kernel = `{rf['kernel']}` ({rf['share_of_step']*100:.0f} % of the step), "
          f"{rf['achieved']:.0f} GB/s of algorithmic traffic = **{rf['frac']*100:.1f} % of the measured HBM peak**; DRAM traffic "
-         f"{traffic/1e6:.0f} MB per 64-frame launch (ncu) vs {rf['algorithmic_bytes_per_launch']/1e6:.0f} MB algorithmic: no re-reads. "
+         f"{traffic/1e6:.0f} MB per 64-frame launch (ncu capture at batch 64) vs {rf['algorithmic_bytes_per_launch']/1e6*64/B:.0f} MB algorithmic: no re-reads. "
          "ncu explains the gap to the HBM roofline: the kernel is instruction-issue bound (70 % of issue slots busy, <3 % DRAM throughput).\n")
 o.append("## ncu launch list (`launches_r1.csv`, `--metrics gpu__time_duration.sum --clock-control none`, one `bench.py --steps 2` run)\n")
 o.append(launch)
