@@ -41,6 +41,8 @@ struct ResizeTab {
   int x_off = 0, y_off = 0;
 };
 
+struct LevelTensorMaps;
+
 struct Engine {
   // parameters and tables (ORBextractor.cc:409-469)
   int nfeatures, nlevels, ini_th, min_th, device;
@@ -99,6 +101,8 @@ struct Engine {
                          orb_keypoint* kps, uint8_t* desc, int cap, int* n, int* mono);
   int extract_batch_device(int batch, const uint8_t* d_imgs, size_t frame_stride, int rows, int cols, size_t step,
                            const int* lap, cudaStream_t user);
+  LevelTensorMaps* tmaps = nullptr;  // host copy of the per-level TMA descriptors (passed by value to the kernel)
+  int encode_tensor_maps(int batch);
   int l2_chunk_frames(int batch) const;
   int fetch_pyramid();
   int debug_candidates(int frame, int level, int* xys, int cap);

@@ -8,6 +8,7 @@
 // per-cell NMS band + minTh fallback, libstdc++-ordered octree, strict-IEEE
 // fastAtan2 and rBRIEF rotation (no FMA contraction: built with -fmad=false and
 // explicit _rn intrinsics).
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -197,16 +198,21 @@ __device__ __forceinline__ int fast_best(const uint8_t* __restrict__ c, int pitc
 //   3. the full 16-ring score and 4. the NMS / emission only ever run on dense
 //      queues -- no warp drags 31 rejected lanes through the expensive path.
 constexpr int FAST_THREADS = 128;
-constexpr int FAST_TILE_MAX = 80;    // rows: hCell+6 <= 76
-constexpr int FAST_TILE_PITCH = 84;  // bytes, 21 words: (x0&3) + wCell+6 <= 79
+constexpr int FAST_TILE_MAX = 76;    // TMA box rows: hCell+6 <= 76
+constexpr int FAST_TILE_PITCH = 80;  // TMA box columns (bytes): wCell+6 <= 76, multiple of 16
 constexpr int FAST_BAND_MAX = 70;
 
+struct LevelTensorMaps {
+  CUtensorMap m[16];  // one 3-D (x, y, frame) uint8 map per pyramid level
+};
+
 __global__ void __launch_bounds__(FAST_THREADS)
-fast_cells_kernel(const uint8_t* __restrict__ pyr, size_t frame_stride,
+fast_cells_kernel(const __grid_constant__ LevelTensorMaps maps, int frame0,
                   const CellDesc* __restrict__ cells, const LevelDev* __restrict__ lv, int ini_th,
                   int min_th, Cand* __restrict__ cand, size_t cand_frame_stride,
                   int* __restrict__ cand_count, int nlevels) {
-  __shared__ __align__(16) uint8_t tile[FAST_TILE_MAX * FAST_TILE_PITCH];
+  __shared__ __align__(128) uint8_t tile[FAST_TILE_MAX * FAST_TILE_PITCH];
+  __shared__ __align__(8) unsigned long long tma_bar;
   __shared__ __align__(16) uint8_t smap[(FAST_BAND_MAX + 2) * (FAST_BAND_MAX + 2) + 8];
   __shared__ unsigned short queue[FAST_BAND_MAX * FAST_BAND_MAX];
   __shared__ int s_qn, s_cnt_all, s_base;
@@ -214,26 +220,49 @@ fast_cells_kernel(const uint8_t* __restrict__ pyr, size_t frame_stride,
   const CellDesc cd = cells[blockIdx.x];
   const LevelDev L = lv[cd.level];
   const int f = blockIdx.y;
-  const uint8_t* img = pyr + (size_t)f * frame_stride + L.img_off;
   const int tw = cd.x1 - cd.x0, th = cd.y1 - cd.y0;
   const int bw = tw - 6, bh = th - 6;
   if (bw <= 0 || bh <= 0) return;
   const int sw = bw + 2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) { s_qn = 0; s_cnt_all = 0; }
-  // 1. tile load, aligned words
-  const int ox = cd.x0 & 3;
-  const int nw = (ox + tw + 3) >> 2;
+  // 1. the cell tile arrives through TMA: one 80x76 box of the (x, y, frame) tensor of this level,
+  //    issued by one thread, completion signalled on an mbarrier (out-of-image bytes are zero-filled
+  //    and never read by a band pixel)
+  const unsigned bar_addr = (unsigned)__cvta_generic_to_shared(&tma_bar);
+  if (threadIdx.x == 0) {
+    s_qn = 0; s_cnt_all = 0;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(tile);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr),
+                 "r"(FAST_TILE_MAX * FAST_TILE_PITCH)
+                 : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(&maps.m[cd.level]), "r"(bar_addr), "r"(cd.x0), "r"(cd.y0), "r"(frame0 + f)
+        : "memory");
+  }
   {
-    const uint8_t* src = img + (size_t)cd.y0 * L.pitch + (cd.x0 & ~3);
-    for (int r = warp; r < th; r += FAST_THREADS / 32)
-      if (lane < nw)
-        reinterpret_cast<uint32_t*>(tile)[r * (FAST_TILE_PITCH / 4) + lane] =
-            *reinterpret_cast<const uint32_t*>(src + (size_t)r * L.pitch + 4 * lane);
     const int nz = ((bw + 2) * (bh + 2) + 3) >> 2;
     for (int i = threadIdx.x; i < nz; i += FAST_THREADS) reinterpret_cast<uint32_t*>(smap)[i] = 0;
   }
+  {
+    unsigned done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n.reg .pred p;\n"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n"
+          "selp.u32 %0, 1, 0, p;\n}"
+          : "=r"(done)
+          : "r"(bar_addr)
+          : "memory");
+    }
+  }
   __syncthreads();
+  constexpr int ox = 0;  // the box starts exactly at the cell's first column
   // The reference calls cv::FAST(cell, iniThFAST) and only when that returns nothing
   // cv::FAST(cell, minThFAST) (:826-846).  Same here: pass 0 at iniTh (few pixels survive the
   // cheap test), pass 1 at minTh only for the rare cells that came out empty.
@@ -781,7 +810,7 @@ int Engine::ensure(int rows, int cols, int batch) {
     const float width = (float)(maxBX - minB), height = (float)(maxBY - minB);
     const int nCols = (int)(width / 35.f), nRows = (int)(height / 35.f);
     const int wCell = (int)ceilf(width / nCols), hCell = (int)ceilf(height / nRows);
-    if (wCell > FAST_BAND_MAX || hCell > FAST_BAND_MAX) {
+    if (wCell > FAST_BAND_MAX || hCell > FAST_BAND_MAX || wCell + 6 > FAST_TILE_PITCH || hCell + 6 > FAST_TILE_MAX) {
       set_last_error("unsupported FAST cell size");
       return ORB_E_ARG;
     }
@@ -873,6 +902,7 @@ int Engine::ensure(int rows, int cols, int batch) {
   const size_t B = batch;
   if (dalloc(&d_pyr, pyr_frame_bytes * B)) return ORB_E_CUDA;
   if (dalloc(&d_blur, pyr_frame_bytes * B + 256)) return ORB_E_CUDA;
+  if (encode_tensor_maps((int)B)) return ORB_E_CUDA;
   if (dalloc(&d_cand, cand_frame_elems * B)) return ORB_E_CUDA;
   if (dalloc(&d_scratch, scratch_frame_bytes * B)) return ORB_E_CUDA;
   if (dalloc(&d_sel, 3 * sel_frame_elems * B)) return ORB_E_CUDA;
@@ -996,8 +1026,8 @@ int Engine::run_device(int f0, int batch, const int* lap_host, cudaStream_t s) {
   // 2. FAST cells
   stage_begin(2, s);
   CUDA_TRY(cudaMemsetAsync(cand_count, 0, sizeof(int) * nlevels * B, s));
-  fast_cells_kernel<<<dim3(num_cells, B), FAST_THREADS, 0, s>>>(pyr, pyr_frame_bytes, d_cells, d_levels, ini_th,
-                                                                min_th, cand, cand_frame_elems, cand_count, nlevels);
+  fast_cells_kernel<<<dim3(num_cells, B), FAST_THREADS, 0, s>>>(*tmaps, f0, d_cells, d_levels, ini_th, min_th, cand,
+                                                                cand_frame_elems, cand_count, nlevels);
   stage_end(2, s, 1);
   // 3. octree
   stage_begin(3, s);
@@ -1131,6 +1161,34 @@ int Engine::extract_batch_device(int batch, const uint8_t* d_imgs, size_t frame_
   for (int f0 = 0; f0 < batch; f0 += chunk)
     if (run_device(f0, std::min(chunk, batch - f0), lap, s)) return ORB_E_CUDA;
   return batch;
+}
+
+// TMA descriptors of the pyramid levels: uint8 tensor (x = level width, y = level height, z = frame)
+// with byte strides (pitch, slab stride); box = the FAST tile.  cuTensorMapEncodeTiled is taken from
+// the driver through the runtime so the library does not link libcuda.
+int Engine::encode_tensor_maps(int batch) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess) { set_last_error("cuTensorMapEncodeTiled not available"); return ORB_E_CUDA; }
+  if (!tmaps) tmaps = new LevelTensorMaps();
+  memset(tmaps, 0, sizeof(LevelTensorMaps));
+  if (nlevels > 16) { set_last_error("more than 16 pyramid levels"); return ORB_E_ARG; }
+  for (int l = 0; l < nlevels; l++) {
+    const LevelDev& L = levels[l];
+    const cuuint64_t dims[3] = {(cuuint64_t)L.w, (cuuint64_t)L.h, (cuuint64_t)batch};
+    const cuuint64_t strides[2] = {(cuuint64_t)L.pitch, (cuuint64_t)pyr_frame_bytes};
+    const cuuint32_t box[3] = {(cuuint32_t)FAST_TILE_PITCH, (cuuint32_t)FAST_TILE_MAX, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = ((EncodeFn)fn)(&tmaps->m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, d_pyr + L.img_off, dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled failed, level " + std::to_string(l) + " rc " + std::to_string((int)r)); return ORB_E_CUDA; }
+  }
+  return 0;
 }
 
 int Engine::l2_chunk_frames(int batch) const {
