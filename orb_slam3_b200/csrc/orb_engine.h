@@ -101,7 +101,8 @@ struct Engine {
                          orb_keypoint* kps, uint8_t* desc, int cap, int* n, int* mono);
   int extract_batch_device(int batch, const uint8_t* d_imgs, size_t frame_stride, int rows, int cols, size_t step,
                            const int* lap, cudaStream_t user);
-  LevelTensorMaps* tmaps = nullptr;  // host copy of the per-level TMA descriptors (passed by value to the kernel)
+  LevelTensorMaps* tmaps = nullptr;  // host copy of the per-level TMA descriptors
+  void* d_tmaps_raw = nullptr;       // device copy read by cp.async.bulk.tensor
   int encode_tensor_maps(int batch);
   int l2_chunk_frames(int batch) const;
   int fetch_pyramid();

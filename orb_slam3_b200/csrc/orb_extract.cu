@@ -199,7 +199,7 @@ __device__ __forceinline__ int fast_best(const uint8_t* __restrict__ c, int pitc
 //      queues -- no warp drags 31 rejected lanes through the expensive path.
 constexpr int FAST_THREADS = 128;
 constexpr int FAST_TILE_MAX = 76;    // TMA box rows: hCell+6 <= 76
-constexpr int FAST_TILE_PITCH = 80;  // TMA box columns (bytes): wCell+6 <= 76, multiple of 16
+constexpr int FAST_TILE_PITCH = 96;  // TMA box columns (bytes): (x0 & 15) + wCell+6 <= 91, multiple of 16
 constexpr int FAST_BAND_MAX = 70;
 
 struct LevelTensorMaps {
@@ -207,7 +207,7 @@ struct LevelTensorMaps {
 };
 
 __global__ void __launch_bounds__(FAST_THREADS)
-fast_cells_kernel(const __grid_constant__ LevelTensorMaps maps, int frame0,
+fast_cells_kernel(const CUtensorMap* __restrict__ maps, int frame0,
                   const CellDesc* __restrict__ cells, const LevelDev* __restrict__ lv, int ini_th,
                   int min_th, Cand* __restrict__ cand, size_t cand_frame_stride,
                   int* __restrict__ cand_count, int nlevels) {
@@ -225,7 +225,7 @@ fast_cells_kernel(const __grid_constant__ LevelTensorMaps maps, int frame0,
   if (bw <= 0 || bh <= 0) return;
   const int sw = bw + 2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // 1. the cell tile arrives through TMA: one 80x76 box of the (x, y, frame) tensor of this level,
+  // 1. the cell tile arrives through TMA: one 96x76 box of the (x, y, frame) tensor of this level,
   //    issued by one thread, completion signalled on an mbarrier (out-of-image bytes are zero-filled
   //    and never read by a band pixel)
   const unsigned bar_addr = (unsigned)__cvta_generic_to_shared(&tma_bar);
@@ -242,7 +242,7 @@ fast_cells_kernel(const __grid_constant__ LevelTensorMaps maps, int frame0,
                  : "memory");
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(dst), "l"(&maps.m[cd.level]), "r"(bar_addr), "r"(cd.x0), "r"(cd.y0), "r"(frame0 + f)
+        ::"r"(dst), "l"(maps + cd.level), "r"(bar_addr), "r"(cd.x0 & ~15), "r"(cd.y0), "r"(frame0 + f)
         : "memory");
   }
   {
@@ -262,7 +262,8 @@ fast_cells_kernel(const __grid_constant__ LevelTensorMaps maps, int frame0,
     }
   }
   __syncthreads();
-  constexpr int ox = 0;  // the box starts exactly at the cell's first column
+  const int ox = cd.x0 & 15;  // the box starts at the 16-byte aligned column left of the cell (TMA needs
+                              // 16-byte aligned global row starts)
   // The reference calls cv::FAST(cell, iniThFAST) and only when that returns nothing
   // cv::FAST(cell, minThFAST) (:826-846).  Same here: pass 0 at iniTh (few pixels survive the
   // cheap test), pass 1 at minTh only for the rare cells that came out empty.
@@ -810,7 +811,7 @@ int Engine::ensure(int rows, int cols, int batch) {
     const float width = (float)(maxBX - minB), height = (float)(maxBY - minB);
     const int nCols = (int)(width / 35.f), nRows = (int)(height / 35.f);
     const int wCell = (int)ceilf(width / nCols), hCell = (int)ceilf(height / nRows);
-    if (wCell > FAST_BAND_MAX || hCell > FAST_BAND_MAX || wCell + 6 > FAST_TILE_PITCH || hCell + 6 > FAST_TILE_MAX) {
+    if (wCell > FAST_BAND_MAX || hCell > FAST_BAND_MAX || wCell + 6 + 15 > FAST_TILE_PITCH || hCell + 6 > FAST_TILE_MAX) {
       set_last_error("unsupported FAST cell size");
       return ORB_E_ARG;
     }
@@ -1026,7 +1027,7 @@ int Engine::run_device(int f0, int batch, const int* lap_host, cudaStream_t s) {
   // 2. FAST cells
   stage_begin(2, s);
   CUDA_TRY(cudaMemsetAsync(cand_count, 0, sizeof(int) * nlevels * B, s));
-  fast_cells_kernel<<<dim3(num_cells, B), FAST_THREADS, 0, s>>>(*tmaps, f0, d_cells, d_levels, ini_th, min_th, cand,
+  fast_cells_kernel<<<dim3(num_cells, B), FAST_THREADS, 0, s>>>((const CUtensorMap*)d_tmaps_raw, f0, d_cells, d_levels, ini_th, min_th, cand,
                                                                 cand_frame_elems, cand_count, nlevels);
   stage_end(2, s, 1);
   // 3. octree
@@ -1188,6 +1189,14 @@ int Engine::encode_tensor_maps(int batch) {
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled failed, level " + std::to_string(l) + " rc " + std::to_string((int)r)); return ORB_E_CUDA; }
   }
+  // the descriptors live in global memory (cudaMalloc is 256-byte aligned; TMA needs 64)
+  {
+    void* q = nullptr;  // (re)allocated with the other slabs: release() frees dev_allocs
+    CUDA_TRY(cudaMalloc(&q, sizeof(LevelTensorMaps)));
+    dev_allocs.push_back(q);
+    d_tmaps_raw = q;
+  }
+  CUDA_TRY(cudaMemcpy(d_tmaps_raw, tmaps, sizeof(LevelTensorMaps), cudaMemcpyHostToDevice));
   return 0;
 }
 

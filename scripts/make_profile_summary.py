@@ -72,7 +72,7 @@ o.append("""
 
 | kernel | first correct version | end of round | what did it |
 |---|---|---|---|
-| FAST cells | 36 | 12.9 | compaction queue instead of divergent heavy path; iniTh pass first and minTh pass only for empty cells (the reference's own two cv::FAST calls); packed-byte VABSDIFF4 pre-test |
+| FAST cells | 36 | 10.4 | compaction queue instead of divergent heavy path; iniTh pass first and minTh pass only for empty cells (the reference's own two cv::FAST calls); packed-byte VABSDIFF4 pre-test; tile through TMA (UTMALDG.3D + mbarrier) |
 | describe (IC angle + rBRIEF) | 15 | 4.7 | **pattern table moved from `__constant__` (lane-divergent index = 32 replays per load) to a lane-transposed shared-memory copy** (ncu source view: 45 % of samples on `LDC.64`) |
 | blur | 11.5 | 6.3 | 4 pixels / thread, aligned word loads and stores |
 | octree | 8.5 | 6.5 | node arrays in shared memory, 4-way batched point loops, level-major launch order |
