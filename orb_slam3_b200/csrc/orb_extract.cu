@@ -457,8 +457,10 @@ octree_kernel(const Cand* __restrict__ cand, size_t cand_frame_stride, const int
 // GaussianBlur 7x7 sigma 2 over every level of every frame.
 // 128x32 output tile per CTA; aligned 32-bit loads, 4 pixels per thread in both
 // passes, one coalesced 32-bit store per thread.
-constexpr int BLUR_TW = 128, BLUR_TH = 32;
-constexpr int BLUR_IW = BLUR_TW + 8;  // bytes per staged input row: [x0-4, x0+TW+4)
+constexpr int BLUR_TW = 128, BLUR_TH = 58;  // TH + 6 staged rows = 32 row pairs
+constexpr int BLUR_IW = BLUR_TW + 8;          // bytes per staged input row: [x0-4, x0+TW+4)
+constexpr int BLUR_PAIRS = (BLUR_TH + 6) / 2;
+static_assert(BLUR_TH % 2 == 0 && BLUR_TW % 4 == 0, "row pairs / 4-pixel groups");
 
 __device__ __forceinline__ int reflect101(int p, int n) {
   if (p < 0) p = -p;
@@ -466,68 +468,89 @@ __device__ __forceinline__ int reflect101(int p, int n) {
   return min(max(p, 0), n - 1);
 }
 
+// 8.8 fixed-point taps of cv::GaussianBlur(7x7, sigma 2) (oracle orc_extract.cpp, reference call
+// ORBextractor.cc:1110) as byte vectors for the integer dot-product instructions:
+// horizontal: 7 u8 taps = IDP.4A over bytes [c-3, c] and [c+1, c+4) (8th weight 0);
+// vertical:   rows are stored in pairs (row 2j | row 2j+1 << 16), 7 u16 taps = 4 IDP.2A.
+constexpr uint32_t BLUR_K_LO = 18u | (34u << 8) | (48u << 16) | (56u << 24);
+constexpr uint32_t BLUR_K_HI = 48u | (34u << 8) | (18u << 16);
+constexpr uint32_t BLUR_K_ODD_A = (18u << 8) | (34u << 16) | (48u << 24);             // (0,18 | 34,48)
+constexpr uint32_t BLUR_K_ODD_B = 56u | (48u << 8) | (34u << 16) | (18u << 24);      // (56,48 | 34,18)
+
+__device__ __forceinline__ void blur_h4(const uint32_t* __restrict__ row, uint32_t o[4]) {
+  const uint32_t w0 = row[0], w1 = row[1], w2 = row[2];
+  // output k is centred on staged byte 4q+k+4: taps cover bytes 4q+k+1 .. 4q+k+7
+  o[0] = __dp4a(__funnelshift_r(w0, w1, 8), BLUR_K_LO, __dp4a(__funnelshift_r(w1, w2, 8), BLUR_K_HI, 0u));
+  o[1] = __dp4a(__funnelshift_r(w0, w1, 16), BLUR_K_LO, __dp4a(__funnelshift_r(w1, w2, 16), BLUR_K_HI, 0u));
+  o[2] = __dp4a(__funnelshift_r(w0, w1, 24), BLUR_K_LO, __dp4a(__funnelshift_r(w1, w2, 24), BLUR_K_HI, 0u));
+  o[3] = __dp4a(w1, BLUR_K_LO, __dp4a(w2, BLUR_K_HI, 0u));
+}
+
 __global__ void __launch_bounds__(256)
 blur_kernel(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blr, size_t frame_stride,
             const BlurTile* __restrict__ tiles, const LevelDev* __restrict__ lv) {
   __shared__ __align__(16) uint8_t in[(BLUR_TH + 6) * BLUR_IW];
-  __shared__ __align__(16) uint16_t hb[(BLUR_TH + 6) * BLUR_TW];
+  __shared__ __align__(16) uint32_t hp[BLUR_PAIRS * BLUR_TW];  // horizontal sums, two rows per word
   const BlurTile t = tiles[blockIdx.x];
   const LevelDev L = lv[t.level];
   const uint8_t* src = pyr + (size_t)blockIdx.y * frame_stride + L.img_off;
   uint8_t* dst = blr + (size_t)blockIdx.y * frame_stride + L.img_off;
   const int w = L.w, h = L.h;
-  const bool interior = t.x0 >= 4 && t.x0 + BLUR_TW + 4 <= w && t.y0 >= 3 && t.y0 + BLUR_TH + 3 <= h;
-  if (interior) {
-    const uint8_t* base = src + (size_t)(t.y0 - 3) * L.pitch + (t.x0 - 4);
-    for (int i = threadIdx.x; i < (BLUR_TH + 6) * (BLUR_IW / 4); i += 256) {
-      const int r = i / (BLUR_IW / 4), c = i - r * (BLUR_IW / 4);
-      reinterpret_cast<uint32_t*>(in)[i] = *reinterpret_cast<const uint32_t*>(base + (size_t)r * L.pitch + 4 * c);
+  const int out_rows = min(BLUR_TH, h - t.y0);           // rows of this tile inside the image
+  const int in_rows = out_rows + 6;
+  // stage [y0-3, y0+out_rows+3) x [x0-4, x0+TW+4) word by word; BORDER_REFLECT_101 at the true image
+  // edge (bytes past the right edge feed only outputs that are never stored)
+  for (int i = threadIdx.x; i < in_rows * (BLUR_IW / 4); i += 256) {
+    const int r = i / (BLUR_IW / 4), c = i - r * (BLUR_IW / 4);
+    const int gy = reflect101(t.y0 - 3 + r, h), gx = t.x0 - 4 + 4 * c;
+    const uint8_t* rowp = src + (size_t)gy * L.pitch;
+    uint32_t v;
+    if (gx >= 0 && gx + 3 < w) {
+      v = *reinterpret_cast<const uint32_t*>(rowp + gx);
+    } else {
+      v = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) v |= (uint32_t)rowp[reflect101(gx + k, w)] << (8 * k);
     }
-  } else {
-    for (int i = threadIdx.x; i < (BLUR_TH + 6) * BLUR_IW; i += 256) {
-      const int r = i / BLUR_IW, c = i - r * BLUR_IW;
-      // BORDER_REFLECT_101 at the true image edge (values past the right/bottom edge are unused)
-      const int gx = reflect101(t.x0 - 4 + c, w), gy = reflect101(t.y0 - 3 + r, h);
-      in[i] = src[(size_t)gy * L.pitch + gx];
-    }
+    reinterpret_cast<uint32_t*>(in)[i] = v;
   }
   __syncthreads();
-  // horizontal pass: 4 outputs per thread from bytes [4q+1, 4q+11) of the staged row
-  for (int i = threadIdx.x; i < (BLUR_TH + 6) * (BLUR_TW / 4); i += 256) {
-    const int r = i / (BLUR_TW / 4), q = i - r * (BLUR_TW / 4);
-    const uint32_t* row = reinterpret_cast<const uint32_t*>(in + r * BLUR_IW) + q;
-    const uint32_t w0 = row[0], w1 = row[1], w2 = row[2];
-    int p[12];
-#pragma unroll
-    for (int k = 0; k < 4; k++) { p[k] = (w0 >> (8 * k)) & 255; p[4 + k] = (w1 >> (8 * k)) & 255; p[8 + k] = (w2 >> (8 * k)) & 255; }
-    uint32_t o[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++)  // output x = 4q+k is centred on staged byte 4q+k+4
-      o[k] = 18 * (p[k + 1] + p[k + 7]) + 34 * (p[k + 2] + p[k + 6]) + 48 * (p[k + 3] + p[k + 5]) + 56 * p[k + 4];
-    uint2 packed;
-    packed.x = o[0] | (o[1] << 16);
-    packed.y = o[2] | (o[3] << 16);
-    reinterpret_cast<uint2*>(hb + r * BLUR_TW)[q] = packed;
+  // horizontal pass: one thread = 4 columns of one row pair, stored as (even row | odd row << 16)
+  const int in_pairs = (in_rows + 1) >> 1;
+  for (int i = threadIdx.x; i < in_pairs * (BLUR_TW / 4); i += 256) {
+    const int j = i / (BLUR_TW / 4), q = i - j * (BLUR_TW / 4);
+    uint32_t a[4], b[4];
+    blur_h4(reinterpret_cast<const uint32_t*>(in + (2 * j) * BLUR_IW) + q, a);
+    blur_h4(reinterpret_cast<const uint32_t*>(in + (2 * j + 1) * BLUR_IW) + q, b);  // row in_rows (odd count) is unused slack
+    uint4 pk;
+    pk.x = a[0] | (b[0] << 16); pk.y = a[1] | (b[1] << 16); pk.z = a[2] | (b[2] << 16); pk.w = a[3] | (b[3] << 16);
+    reinterpret_cast<uint4*>(hp + j * BLUR_TW)[q] = pk;
   }
   __syncthreads();
-  // vertical pass + final rounding, one 32-bit store per thread
-  for (int i = threadIdx.x; i < BLUR_TH * (BLUR_TW / 4); i += 256) {
-    const int r = i / (BLUR_TW / 4), q = i - r * (BLUR_TW / 4);
-    const int gy = t.y0 + r, gx = t.x0 + 4 * q;
-    if (gy >= h || gx >= w) continue;
-    uint32_t acc[4] = {0, 0, 0, 0};
-    const uint32_t kk[7] = {18, 34, 48, 56, 48, 34, 18};
-#pragma unroll
-    for (int k = 0; k < 7; k++) {
-      const uint2 v = reinterpret_cast<const uint2*>(hb + (r + k) * BLUR_TW)[q];
-      acc[0] += kk[k] * (v.x & 0xffff); acc[1] += kk[k] * (v.x >> 16);
-      acc[2] += kk[k] * (v.y & 0xffff); acc[3] += kk[k] * (v.y >> 16);
-    }
-    uint32_t out = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) out |= ((acc[k] + (1u << 15)) >> 16) << (8 * k);
+  // vertical pass + rounding: one thread = 4 columns x 2 output rows (2jo, 2jo+1) from pairs jo..jo+3
+  const int out_pairs = (out_rows + 1) >> 1;
+  for (int i = threadIdx.x; i < out_pairs * (BLUR_TW / 4); i += 256) {
+    const int jo = i / (BLUR_TW / 4), q = i - jo * (BLUR_TW / 4);
+    const int gy = t.y0 + 2 * jo, gx = t.x0 + 4 * q;
+    if (gx >= w) continue;
+    const uint4 p0 = reinterpret_cast<const uint4*>(hp + (jo + 0) * BLUR_TW)[q];
+    const uint4 p1 = reinterpret_cast<const uint4*>(hp + (jo + 1) * BLUR_TW)[q];
+    const uint4 p2 = reinterpret_cast<const uint4*>(hp + (jo + 2) * BLUR_TW)[q];
+    const uint4 p3 = reinterpret_cast<const uint4*>(hp + (jo + 3) * BLUR_TW)[q];
+    uint32_t e[4], o[4];
+#define BLUR_V(c, k)                                                                                       \
+    e[k] = __dp2a_hi(p3.c, BLUR_K_HI, __dp2a_lo(p2.c, BLUR_K_HI, __dp2a_hi(p1.c, BLUR_K_LO,               \
+             __dp2a_lo(p0.c, BLUR_K_LO, 1u << 15))));                                                      \
+    o[k] = __dp2a_hi(p3.c, BLUR_K_ODD_B, __dp2a_lo(p2.c, BLUR_K_ODD_B, __dp2a_hi(p1.c, BLUR_K_ODD_A,      \
+             __dp2a_lo(p0.c, BLUR_K_ODD_A, 1u << 15))));
+    BLUR_V(x, 0) BLUR_V(y, 1) BLUR_V(z, 2) BLUR_V(w, 3)
+#undef BLUR_V
+    // (acc + 2^15) >> 16 < 256: the result is byte 2 of each accumulator
+    const uint32_t oe = __byte_perm(__byte_perm(e[0], e[1], 0x0062), __byte_perm(e[2], e[3], 0x0062), 0x5410);
+    const uint32_t oo = __byte_perm(__byte_perm(o[0], o[1], 0x0062), __byte_perm(o[2], o[3], 0x0062), 0x5410);
     // the pitch is a multiple of 64, so the (rare) partial last word stays inside the row
-    *reinterpret_cast<uint32_t*>(dst + (size_t)gy * L.pitch + gx) = out;
+    *reinterpret_cast<uint32_t*>(dst + (size_t)gy * L.pitch + gx) = oe;
+    if (gy + 1 < h) *reinterpret_cast<uint32_t*>(dst + (size_t)(gy + 1) * L.pitch + gx) = oo;
   }
 }
 
