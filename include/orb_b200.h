@@ -289,6 +289,35 @@ int lba_solve(lba_solver* s, const lba_graph_view* g, const volatile uint8_t* st
               uint8_t* depth_pos_out, lba_stats* stats);
 long long lba_kernel_launches(const lba_solver* s);
 
+/* ------------------------------------------------------------------------
+ * void Frame::ComputeStereoMatches() (src/Frame.cc:811-981), SURVEY.md 8(f-1).
+ * Works on what the two extractor handles left on the device after their last
+ * extract (mvKeys / mDescriptors / mvImagePyramid of mpORBextractorLeft and
+ * mpORBextractorRight): frame i of the left batch is matched against frame i of
+ * the right batch.  bf = Frame::mbf, b = Frame::mb.  Outputs per frame:
+ * u_right[cap] = mvuRight, depth[cap] = mvDepth (-1 where there is no stereo
+ * match), for the left handle's keypoints in their output order.
+ * Where the reference is undefined (no left keypoint survives to the median
+ * test, Frame.cc:969) every output is -1.
+ * ---------------------------------------------------------------------- */
+typedef struct orb_stereo orb_stereo;
+int stereo_create(int device, orb_stereo** out);
+void stereo_destroy(orb_stereo* h);
+/* One stereo pair (frame 0 of both handles), host outputs.  Returns the number of
+ * keypoints with a stereo match, or ORB_E_*. */
+int stereo_match(orb_stereo* h, orb_extractor* left, orb_extractor* right, float bf, float b, float* u_right,
+                 float* depth, int cap);
+/* `batch` pairs.  on_device = 0: u_right / depth are host arrays of batch x cap floats, kept[batch]
+ * (optional) receives the match counts, the call returns after the copy.  on_device = 1: results stay
+ * on the device (stereo_device_results), the call only enqueues work on cuda_stream (NULL = the left
+ * handle's stream) after both extractions.  Returns batch or ORB_E_*. */
+int stereo_match_batch(orb_stereo* h, orb_extractor* left, orb_extractor* right, int batch, float bf, float b,
+                       float* u_right, float* depth, int cap, int* kept, int on_device, void* cuda_stream);
+int stereo_device_results(orb_stereo* h, const float** d_u_right, const float** d_depth, const int** d_kept,
+                          int* stride);
+long long stereo_kernel_launches(const orb_stereo* h);
+float stereo_last_ms(orb_stereo* h); /* device time of the last call (CUDA events), waits for it */
+
 /* Per-stage device timing (CUDA events on the launching stream).  Stages:
  * 0 h2d, 1 pyramid, 2 fast, 3 octree, 4 blur, 5 layout, 6 orient+describe,
  * 7 d2h.  orb_stage_times fills ms[8] (accumulated) and launches[8]. */

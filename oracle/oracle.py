@@ -72,6 +72,10 @@ def lib():
         L.orc_lba_reduced_system.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.POINTER(C.c_double)]
         L.orc_sort_nodes.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_stereo_match.restype = C.c_int
+        L.orc_stereo_match.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -259,3 +263,29 @@ def lba_reduced_system(g, lam, lm_mask=None):
     lib().orc_lba_reduced_system(C.byref(g), lam, _ptr(m) if m is not None else None, _ptr(S), _ptr(bs),
                                  C.byref(chi))
     return S, bs, chi.value
+
+
+def stereo_match(kl, dl, kr, dr, pyr_l, pyr_r, bf, b, scale_factor=1.2):
+    """Frame::ComputeStereoMatches (Frame.cc:811-981).  pyr_l / pyr_r: lists of un-blurred level images
+    (mvImagePyramid of the two extractors).  Returns (n_kept, mvuRight, mvDepth, sad)."""
+    nl = len(pyr_l)
+    L = [np.ascontiguousarray(a, np.uint8) for a in pyr_l]
+    R = [np.ascontiguousarray(a, np.uint8) for a in pyr_r]
+    assert all(a.shape == c.shape for a, c in zip(L, R))
+    pl = (C.c_void_p * nl)(*[a.ctypes.data for a in L])
+    pr = (C.c_void_p * nl)(*[a.ctypes.data for a in R])
+    lw = np.array([a.shape[1] for a in L], np.int32)
+    lh = np.array([a.shape[0] for a in L], np.int32)
+    ls = np.array([a.strides[0] for a in L], np.int32)
+    scale = np.ones(nl, np.float32)
+    for i in range(1, nl):  # ORBextractor.cc:414-420
+        scale[i] = np.float32(scale[i - 1] * np.float32(scale_factor))
+    inv = (np.float32(1.0) / scale).astype(np.float32)
+    kl = np.ascontiguousarray(kl); kr = np.ascontiguousarray(kr)
+    dl = np.ascontiguousarray(dl, np.uint8); dr = np.ascontiguousarray(dr, np.uint8)
+    ur = np.zeros(len(kl), np.float32)
+    dp = np.zeros(len(kl), np.float32)
+    sad = np.zeros(len(kl), np.int32)
+    n = lib().orc_stereo_match(len(kl), _ptr(kl), _ptr(dl), len(kr), _ptr(kr), _ptr(dr), nl, pl, pr, _ptr(lw), _ptr(lh),
+                               _ptr(ls), _ptr(scale), _ptr(inv), float(bf), float(b), _ptr(ur), _ptr(dp), _ptr(sad))
+    return n, ur, dp, sad

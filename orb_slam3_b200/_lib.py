@@ -66,6 +66,13 @@ SIGNATURES = {
     "lba_comm_init": (_i, [_vp, _i, _i, _vp]),
     "lba_solve": (_i, [_vp, _vp, _vp, _i, C.c_double, _vp, _vp, _vp, _vp, _vp]),
     "lba_kernel_launches": (C.c_longlong, [_vp]),
+    "stereo_create": (_i, [_i, _vp]),
+    "stereo_destroy": (None, [_vp]),
+    "stereo_match": (_i, [_vp, _vp, _vp, C.c_float, C.c_float, _vp, _vp, _i]),
+    "stereo_match_batch": (_i, [_vp, _vp, _vp, _i, C.c_float, C.c_float, _vp, _vp, _i, _vp, _i, _vp]),
+    "stereo_device_results": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "stereo_kernel_launches": (C.c_longlong, [_vp]),
+    "stereo_last_ms": (C.c_float, [_vp]),
     "orb_set_profiling": (_i, [_vp, _i]),
     "orb_stage_times": (_i, [_vp, _vp, _vp, _i]),
     "orb_stage_name": (C.c_char_p, [_i]),

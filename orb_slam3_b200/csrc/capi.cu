@@ -10,11 +10,6 @@
 
 using orbb200::Engine;
 
-struct orb_extractor {
-  Engine e;
-  orb_extractor(int nf, float sf, int nl, int ini, int mn, int dev) : e(nf, sf, nl, ini, mn, dev) {}
-};
-
 extern "C" {
 
 const char* orb_version(void) { return "orb_slam3_b200 0.1 (sm_100a)"; }

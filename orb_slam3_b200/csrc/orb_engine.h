@@ -110,3 +110,9 @@ struct Engine {
 };
 
 }  // namespace orbb200
+
+// The opaque handle of include/orb_b200.h.
+struct orb_extractor {
+  orbb200::Engine e;
+  orb_extractor(int nf, float sf, int nl, int ini, int mn, int dev) : e(nf, sf, nl, ini, mn, dev) {}
+};

@@ -54,3 +54,25 @@ def shifted_frame(img, dx, dy, seed):
     elif dx < 0:
         out[:, dx:] = rng.integers(0, 256, size=(h, -dx))
     return np.ascontiguousarray(out)
+
+
+def stereo_right(left, seed, disparities=(12,), noise=3):
+    """Right image of a rectified pair: the left image cut into len(disparities) horizontal bands, band k
+    moved left by disparities[k] px (right[y, x] = left[y, x + d]), fresh noise in the uncovered strip and
+    +-`noise` grey levels of sensor noise so that the L1 window distances are not all zero."""
+    rng = np.random.default_rng(seed)
+    h, w = left.shape
+    out = np.empty_like(left)
+    edges = np.linspace(0, h, len(disparities) + 1).astype(int)
+    for k, d in enumerate(disparities):
+        y0, y1 = edges[k], edges[k + 1]
+        band = np.roll(left[y0:y1], -int(d), axis=1).copy()
+        if d > 0:
+            band[:, w - d:] = rng.integers(0, 256, size=(y1 - y0, d))
+        elif d < 0:
+            band[:, :-d] = rng.integers(0, 256, size=(y1 - y0, -d))
+        out[y0:y1] = band
+    if noise:
+        n = rng.integers(-noise, noise + 1, size=(h, w))
+        out = np.clip(out.astype(np.int32) + n, 0, 255).astype(np.uint8)
+    return np.ascontiguousarray(out)
