@@ -449,6 +449,69 @@ def run_lba_gpu(rank, world, device):
     return out
 
 
+def run_stereo_gpu(device, tstream, pairs=64, reps=5, cpu=True):
+    """SURVEY.md 8(f-1), config 3 shape: `pairs` rectified 1280x720 stereo pairs per step; both eyes
+    extracted by their own handle, then Frame::ComputeStereoMatches on the device-resident results."""
+    import torch
+    from orb_slam3_b200.extractor import ORBextractor
+    from orb_slam3_b200.stereo import StereoMatcher
+    from orb_slam3_b200.synth import synth_frame, stereo_right
+    bf, b = 386.0, 386.0 / 700.0
+    uniq = 4
+    lefts = [synth_frame(H, W, 9000 + i) for i in range(uniq)]
+    rights = [stereo_right(l, 9100 + i, disparities=(6, 24, 12)) for i, l in enumerate(lefts)]
+    dl = torch.from_numpy(np.stack([lefts[i % uniq] for i in range(pairs)])).cuda()
+    dr = torch.from_numpy(np.stack([rights[i % uniq] for i in range(pairs)])).cuda()
+    el = ORBextractor(NFEAT, 1.2, NLEVELS, 20, 7, device=device)
+    er = ORBextractor(NFEAT, 1.2, NLEVELS, 20, 7, device=device)
+    sm = StereoMatcher(device)
+    cs = tstream.cuda_stream
+
+    def step():
+        el.extract_batch_device(dl.data_ptr(), pairs, H, W, W, H * W, stream=cs)
+        er.extract_batch_device(dr.data_ptr(), pairs, H, W, W, H * W, stream=cs)
+        sm.compute_batch(el, er, pairs, bf, b, on_device=True, cuda_stream=cs)
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ms_match = 0.0
+    for _ in range(reps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_all = e0.elapsed_time(e1) / reps
+    for _ in range(reps):  # the matcher alone, device time between its own events
+        sm.compute_batch(el, er, pairs, bf, b, on_device=True, cuda_stream=cs)
+        ms_match += sm.last_ms()
+    ms_match /= reps
+    kept, ur, dp = sm.compute_batch(el, er, pairs, bf, b)
+    out = {"config": "%d stereo pairs 1280x720, 2000 features per eye, disparity bands 6/24/12 px" % pairs,
+           "pairs_per_s": pairs / (ms_all * 1e-3), "ms_per_step": ms_all, "unit": "stereo pairs/s (2 x extract + ComputeStereoMatches)",
+           "stereo_match_us_per_pair": 1e3 * ms_match / pairs, "matches_per_pair": float(kept.mean()),
+           "gpu_launches_per_step": 3}
+    if cpu:
+        from oracle import oracle as O
+        exl, exr = O.OracleExtractor(NFEAT), O.OracleExtractor(NFEAT)
+        t0 = time.perf_counter()
+        kl, d1, _ = exl.extract(lefts[0])
+        kr, d2, _ = exr.extract(rights[0])
+        t_ext = time.perf_counter() - t0
+        pl = [exl.level_image(l) for l in range(NLEVELS)]
+        pr = [exr.level_image(l) for l in range(NLEVELS)]
+        t0 = time.perf_counter()
+        for _ in range(5):
+            n_ref, ur_ref, dp_ref, _ = O.stereo_match(kl, d1, kr, d2, pl, pr, bf, b)
+        t_sm = (time.perf_counter() - t0) / 5
+        n0 = len(kl)
+        out["cpu_baseline"] = {"stereo_match_ms_per_pair": 1e3 * t_sm, "extract2_ms_per_pair": 1e3 * t_ext, "threads": 1,
+                               "kind": "port", "parity_pair0": bool(np.array_equal(ur[0, :n0], ur_ref) and
+                                                                    np.array_equal(dp[0, :n0], dp_ref))}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -460,6 +523,7 @@ def main():
     ap.add_argument("--e2e-workers", type=int, default=4, help="host threads feeding the GPU in the e2e leg")
     ap.add_argument("--no-lba", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-stereo", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -570,6 +634,11 @@ def main():
     lba = None
     if not args.no_lba:
         lba = run_lba_gpu(rank, world, local_rank)
+    stereo = None
+    if rank == 0 and not args.no_stereo:
+        stereo = run_stereo_gpu(local_rank, tstream, cpu=(world == 1 and not args.no_cpu))
+    if world > 1:
+        dist.barrier()
 
     if rank == 0:
         peaks = {}
@@ -652,6 +721,7 @@ def main():
                          "per_kernel": per_kernel},
             "cpu_baseline": cpu,
             "lba": lba,
+            "stereo": stereo,
         }
         print(json.dumps(line))
     if world > 1:

@@ -31,6 +31,9 @@ orb_extractor* handle_of(const ORBextractor* self) {
 }
 }  // namespace
 
+// Used by shim/Frame_ComputeStereoMatches.cc: the engine handle behind a reference extractor object.
+orb_extractor* orbb200_handle_of(const ORBextractor* self) { return handle_of(self); }
+
 ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int _iniThFAST, int _minThFAST)
     : nfeatures(_nfeatures), scaleFactor(_scaleFactor), nlevels(_nlevels), iniThFAST(_iniThFAST),
       minThFAST(_minThFAST) {
