@@ -586,7 +586,6 @@ struct Matcher {
   long long launches = 0;
   double last_ms = 0;
   size_t cand_per_query = 48;  // initial candidate budget, grows on overflow
-  size_t resolve_smem_attr = 48 * 1024;
   // asynchronous mode (device-resident problems only): one batch may be in flight per handle
   bool async_mode = false, pending = false;
   int pending_count = 0;
@@ -790,11 +789,7 @@ static int run_projection(Matcher& M, int count, int kind, const orb_frame_view*
       int smem_nk = (max_nk + 3) & ~3;
       size_t smem_bytes = (size_t)smem_nk * 6;
       if (smem_bytes > 160 * 1024) { smem_nk = 0; smem_bytes = 0; }
-      if (smem_bytes > M.resolve_smem_attr) {
-        CUDA_TRYM(cudaFuncSetAttribute(proj_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem_bytes));
-        M.resolve_smem_attr = smem_bytes;
-      }
+      CUDA_TRYM(raise_dynamic_smem((const void*)proj_resolve_kernel, smem_bytes, M.device));
       proj_resolve_kernel<<<count, 1024, smem_bytes, s>>>(d_probs, smem_nk);
     }
     M.launches += 5;

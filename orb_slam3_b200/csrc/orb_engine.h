@@ -3,7 +3,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <map>
+#include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/orb_b200.h"
@@ -13,6 +16,20 @@ namespace orbb200 {
 
 void set_last_error(const std::string& s);
 const char* last_error();
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the kernel (per device), not to a handle:
+// several handles with different sizes share it, so it is only ever raised, process-wide.
+inline cudaError_t raise_dynamic_smem(const void* kernel, size_t bytes, int device) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, size_t> cur;
+  std::lock_guard<std::mutex> lk(mu);
+  size_t& c = cur[std::make_pair(kernel, device)];
+  if (c == 0) c = 48 * 1024;  // what every kernel may use without the attribute
+  if (bytes <= c) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) c = bytes;
+  return e;
+}
 
 // Per pyramid level; lives in host and device memory.
 struct LevelDev {

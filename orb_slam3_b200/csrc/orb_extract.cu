@@ -906,7 +906,7 @@ int Engine::ensure(int rows, int cols, int batch) {
     if (need <= 96 * 1024) {
       oct_smem_node_cap = max_nc;
       oct_smem_bytes = need;
-      CUDA_TRY(cudaFuncSetAttribute(octree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+      CUDA_TRY(raise_dynamic_smem((const void*)octree_kernel, need, device));
     } else {
       oct_smem_node_cap = 0;  // huge quotas: keep the node arrays in global memory
       oct_smem_bytes = 0;

@@ -110,3 +110,17 @@ def test_device_resident_path(oracle):
     orc = oracle.OracleExtractor(1000)
     for b in range(3):
         _assert_same(orc.extract(frames[b]), ext.download_results(b), "dev%d" % b)
+
+
+def test_handles_with_different_parameters_interleave(oracle):
+    """Kernel attributes (dynamic shared memory of the octree / resolve kernels) are per kernel, not per
+    handle: a smaller handle used in between must not break a larger one."""
+    from orb_slam3_b200.extractor import ORBextractor
+    img = synth_frame(480, 640, 6)
+    big, small = ORBextractor(2000, 1.2, 8, 20, 7), ORBextractor(300, 1.2, 8, 20, 7)
+    ref_big = oracle.OracleExtractor(2000).extract(img)
+    ref_small = oracle.OracleExtractor(300).extract(img)
+    _assert_same(ref_big, big(img), "big first")
+    _assert_same(ref_small, small(img), "small")
+    _assert_same(ref_big, big(img), "big again")
+    _assert_same(ref_small, small(img), "small again")
