@@ -318,6 +318,39 @@ int stereo_device_results(orb_stereo* h, const float** d_u_right, const float** 
 long long stereo_kernel_launches(const orb_stereo* h);
 float stereo_last_ms(orb_stereo* h); /* device time of the last call (CUDA events), waits for it */
 
+/* ------------------------------------------------------------------------
+ * int Optimizer::PoseOptimization(Frame* pFrame) (src/Optimizer.cc:814-1115),
+ * motion-only bundle adjustment of one frame pose against its
+ * matched MapPoints -- 4 rounds of g2o Levenberg-Marquardt optimize(10), each
+ * restarted from the frame pose, with chi2 re-classification (5.991 / 7.815)
+ * between rounds and the Huber kernel dropped for the last round.  fp64.
+ * Only the Pinhole single-camera layout (!pFrame->mpCamera2) is covered.
+ * One edge per keypoint i with mvpMapPoints[i] != NULL, in keypoint order.
+ * ---------------------------------------------------------------------- */
+typedef struct pose_opt_view {
+  int32_t n;               /* number of edges (nInitialCorrespondences) */
+  const float* xw;         /* n x 3: pMP->GetWorldPos() */
+  const float* obs;        /* n x 3: mvKeysUn[i].pt.x, .pt.y, mvuRight[i] (< 0: monocular edge) */
+  const float* inv_sigma2; /* n: mvInvLevelSigma2[mvKeysUn[i].octave] */
+  float fx, fy, cx, cy, bf;/* Frame::fx, fy, cx, cy, mbf */
+  double pose[7];          /* pFrame->GetPose(): unit quaternion (x,y,z,w) + translation */
+} pose_opt_view;
+
+typedef struct orb_poseopt orb_poseopt;
+int poseopt_create(int device, orb_poseopt** out);
+void poseopt_destroy(orb_poseopt* h);
+/* pose_out[7]: optimised Tcw (quaternion xyzw + translation; the shim casts to float for
+ * Frame::SetPose); outlier_out[n] = mvbOutlier of the edges.  Returns
+ * nInitialCorrespondences - nBad (0 and an untouched pose when n < 3), or ORB_E_*. */
+int pose_optimize(orb_poseopt* h, const pose_opt_view* v, double* pose_out, uint8_t* outlier_out);
+/* `batch` independent frames, one CTA each, one kernel launch.  pose_out: batch x 7;
+ * outlier_out[k]: n_k flags; inliers_out[batch].  stats_out (optional): batch x 3 ints =
+ * rounds run, LM iterations, LM trials.  Returns batch or ORB_E_*. */
+int pose_optimize_batch(orb_poseopt* h, int batch, const pose_opt_view* views, double* pose_out,
+                        uint8_t* const* outlier_out, int* inliers_out, int* stats_out);
+long long poseopt_kernel_launches(const orb_poseopt* h);
+float poseopt_last_ms(orb_poseopt* h); /* device time of the last call (CUDA events) */
+
 /* Per-stage device timing (CUDA events on the launching stream).  Stages:
  * 0 h2d, 1 pyramid, 2 fast, 3 octree, 4 blur, 5 layout, 6 orient+describe,
  * 7 d2h.  orb_stage_times fills ms[8] (accumulated) and launches[8]. */

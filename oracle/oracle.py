@@ -72,6 +72,8 @@ def lib():
         L.orc_lba_reduced_system.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.POINTER(C.c_double)]
         L.orc_sort_nodes.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_pose_optimize.restype = C.c_int
+        L.orc_pose_optimize.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_stereo_match.restype = C.c_int
         L.orc_stereo_match.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -289,3 +291,14 @@ def stereo_match(kl, dl, kr, dr, pyr_l, pyr_r, bf, b, scale_factor=1.2):
     n = lib().orc_stereo_match(len(kl), _ptr(kl), _ptr(dl), len(kr), _ptr(kr), _ptr(dr), nl, pl, pr, _ptr(lw), _ptr(lh),
                                _ptr(ls), _ptr(scale), _ptr(inv), float(bf), float(b), _ptr(ur), _ptr(dp), _ptr(sad))
     return n, ur, dp, sad
+
+
+def pose_optimize(view):
+    """Optimizer::PoseOptimization (Optimizer.cc:814-1115) on a pose_opt_view.
+    Returns dict(inliers, pose[7], outlier[n] bool, chi2[n], stats = rounds / LM iterations / LM trials)."""
+    pose = np.zeros(7)
+    out = np.zeros(max(view.n, 1), np.uint8)
+    chi2 = np.zeros(max(view.n, 1))
+    stats = np.zeros(3, np.int32)
+    n = lib().orc_pose_optimize(C.byref(view), _ptr(pose), _ptr(out), _ptr(chi2), _ptr(stats))
+    return dict(inliers=n, pose=pose, outlier=out[:view.n].astype(bool), chi2=chi2[:view.n], stats=stats)

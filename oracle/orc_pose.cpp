@@ -1,0 +1,262 @@
+// TEST INFRASTRUCTURE ONLY (see orc_common.h).  fp64 CPU restatement of
+// Optimizer::PoseOptimization (reference src/Optimizer.cc:814-1115; SURVEY.md
+// 8(f-2)) for the Pinhole single-camera layout (`!pFrame->mpCamera2`): one
+// VertexSE3Expmap, unary EdgeSE3ProjectXYZOnlyPose / EdgeStereoSE3ProjectXYZOnlyPose
+// edges, BlockSolver_6_3 + LinearSolverDense + g2o's Levenberg-Marquardt.
+// PARITY UNPINNED BY THE REFERENCE (no tests ship with it); pinned by an
+// independent numpy/scipy check of the normal equations and a finite-difference
+// check of the Jacobians in tests/test_pose_oracle.py.
+//
+// Restates (paths relative to /root/reference):
+//   src/Optimizer.cc:814-1115                                   edge set-up, 4 rounds, chi2 classification
+//   include/OptimizableTypes.h:41-45, src/OptimizableTypes.cpp:49-63   mono edge error / Jacobian
+//   src/CameraModels/Pinhole.cpp:42-48, 71-81                    project / projectJac (float parameters)
+//   Thirdparty/g2o/g2o/types/types_six_dof_expmap.cpp:339-346, 375-404  stereo edge (float invz in the error)
+//   Thirdparty/g2o/g2o/core/base_unary_edge.hpp:44-70            constructQuadraticForm
+//   Thirdparty/g2o/g2o/core/optimization_algorithm_levenberg.cpp:61-194  LM control
+//   Thirdparty/g2o/g2o/core/sparse_optimizer.cpp:354-419         optimize()
+//   Thirdparty/g2o/g2o/solvers/linear_solver_dense.h:64-112      dense LDLT, isPositive()
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+#include "../include/orb_b200.h"
+#include "orc_se3.h"
+
+namespace {
+
+// Eigen::LDLT (diagonal pivoting) of a 6x6 SPD matrix; false when a pivot is negative
+// (isPositive() == false -> LinearSolverDense::solve fails) or vanishes.
+bool ldlt6_solve(const double Hin[36], const double b[6], double x[6]) {
+  double A[36];
+  memcpy(A, Hin, sizeof(A));
+  int perm[6] = {0, 1, 2, 3, 4, 5};
+  double D[6];
+  for (int k = 0; k < 6; k++) {
+    int piv = k;
+    for (int i = k + 1; i < 6; i++)
+      if (std::fabs(A[i * 6 + i]) > std::fabs(A[piv * 6 + piv])) piv = i;
+    if (piv != k) {  // symmetric row/column swap
+      for (int j = 0; j < 6; j++) std::swap(A[k * 6 + j], A[piv * 6 + j]);
+      for (int j = 0; j < 6; j++) std::swap(A[j * 6 + k], A[j * 6 + piv]);
+      std::swap(perm[k], perm[piv]);
+    }
+    const double d = A[k * 6 + k];
+    if (!(d > 0)) return false;
+    D[k] = d;
+    for (int i = k + 1; i < 6; i++) A[i * 6 + k] /= d;
+    for (int i = k + 1; i < 6; i++)
+      for (int j = k + 1; j < 6; j++) A[i * 6 + j] -= A[i * 6 + k] * d * A[j * 6 + k];
+  }
+  double y[6];
+  for (int i = 0; i < 6; i++) y[i] = b[perm[i]];
+  for (int i = 0; i < 6; i++)
+    for (int j = 0; j < i; j++) y[i] -= A[i * 6 + j] * y[j];
+  for (int i = 0; i < 6; i++) y[i] /= D[i];
+  for (int i = 5; i >= 0; i--)
+    for (int j = i + 1; j < 6; j++) y[i] -= A[j * 6 + i] * y[j];
+  for (int i = 0; i < 6; i++) x[perm[i]] = y[i];
+  return true;
+}
+
+struct PoseProblem {
+  const pose_opt_view* v;
+  SE3 T;
+  std::vector<uint8_t> level;   // 0 active, 1 excluded (setLevel)
+  std::vector<double> err;      // 3 per edge; what e->chi2() reads
+  bool robust = true;
+  Huber hm, hs;
+  double H[36], b[6];
+
+  explicit PoseProblem(const pose_opt_view* pv)
+      : v(pv), hm((float)std::sqrt(5.991)), hs((float)std::sqrt(7.815)) {  // Optimizer.cc:851-852
+    level.assign(v->n, 0);
+    err.assign(3 * (size_t)v->n, 0.0);
+  }
+  bool stereo(int e) const { return v->obs[3 * e + 2] >= 0; }  // mvuRight[i] < 0 -> monocular (:867)
+
+  void compute_error(int e) {
+    const double Xw[3] = {v->xw[3 * e], v->xw[3 * e + 1], v->xw[3 * e + 2]};  // GetWorldPos().cast<double>()
+    double Xc[3];
+    se3_map(T, Xw, Xc);
+    double* r = &err[3 * (size_t)e];
+    const double ou = v->obs[3 * e], ov = v->obs[3 * e + 1];
+    if (stereo(e)) {
+      const double fx = v->fx, fy = v->fy, cx = v->cx, cy = v->cy, bf = v->bf;  // e->fx = pFrame->fx ... (:906-910)
+      const float invz = 1.0f / (float)Xc[2];
+      const double pu = Xc[0] * invz * fx + cx;
+      const double pv = Xc[1] * invz * fy + cy;
+      r[0] = ou - pu; r[1] = ov - pv; r[2] = (double)v->obs[3 * e + 2] - (pu - bf * invz);
+    } else {
+      r[0] = ou - (v->fx * Xc[0] / Xc[2] + v->cx);
+      r[1] = ov - (v->fy * Xc[1] / Xc[2] + v->cy);
+      r[2] = 0;
+    }
+  }
+  void compute_active_errors() {
+    for (int e = 0; e < v->n; e++) if (!level[e]) compute_error(e);
+  }
+  double chi2(int e) const {
+    const double s = v->inv_sigma2[e];
+    const double* r = &err[3 * (size_t)e];
+    double c = r[0] * (s * r[0]) + r[1] * (s * r[1]);
+    if (stereo(e)) c += r[2] * (s * r[2]);
+    return c;
+  }
+  double active_robust_chi2() const {
+    double chi = 0, r0, r1;
+    for (int e = 0; e < v->n; e++) {
+      if (level[e]) continue;
+      if (robust) { (stereo(e) ? hs : hm).robustify(chi2(e), r0, r1); chi += r0; }
+      else chi += chi2(e);
+    }
+    return chi;
+  }
+  void jacobian(int e, double B[18]) const {  // d x 6 row-major
+    const double Xw[3] = {v->xw[3 * e], v->xw[3 * e + 1], v->xw[3 * e + 2]};
+    double Xc[3];
+    se3_map(T, Xw, Xc);
+    const double x = Xc[0], y = Xc[1];
+    if (stereo(e)) {
+      const double fx = v->fx, fy = v->fy, bf = v->bf;
+      const double invz = 1.0 / Xc[2], invz_2 = invz * invz;
+      B[0] = x * y * invz_2 * fx; B[1] = -(1 + (x * x * invz_2)) * fx; B[2] = y * invz * fx;
+      B[3] = -invz * fx; B[4] = 0; B[5] = x * invz_2 * fx;
+      B[6] = (1 + y * y * invz_2) * fy; B[7] = -x * y * invz_2 * fy; B[8] = -x * invz * fy;
+      B[9] = 0; B[10] = -invz * fy; B[11] = y * invz_2 * fy;
+      B[12] = B[0] - bf * y * invz_2; B[13] = B[1] + bf * x * invz_2; B[14] = B[2];
+      B[15] = B[3]; B[16] = 0; B[17] = B[5] - bf * invz_2;
+    } else {
+      const double z = Xc[2];
+      const double J[6] = {-(v->fx / z), -0., -(-v->fx * x / (z * z)), -0., -(v->fy / z), -(-v->fy * y / (z * z))};
+      const double D[18] = {0, z, -y, 1, 0, 0, -z, 0, x, 0, 1, 0, y, -x, 0, 0, 0, 1};
+      for (int r = 0; r < 2; r++)
+        for (int c = 0; c < 6; c++) B[r * 6 + c] = J[r * 3] * D[c] + J[r * 3 + 1] * D[6 + c] + J[r * 3 + 2] * D[12 + c];
+    }
+  }
+  void build_system() {
+    std::fill(H, H + 36, 0.0);
+    std::fill(b, b + 6, 0.0);
+    for (int e = 0; e < v->n; e++) {
+      if (level[e]) continue;
+      const int d = stereo(e) ? 3 : 2;
+      double B[18];
+      jacobian(e, B);
+      double rho0 = 0, rho1 = 1;
+      if (robust) (stereo(e) ? hs : hm).robustify(chi2(e), rho0, rho1);
+      const double s = v->inv_sigma2[e];
+      const double ws = rho1 * s;
+      const double* r = &err[3 * (size_t)e];
+      for (int i = 0; i < 6; i++) {
+        for (int j = 0; j < 6; j++) {
+          double acc = 0;
+          for (int q = 0; q < d; q++) acc += B[q * 6 + i] * ws * B[q * 6 + j];
+          H[i * 6 + j] += acc;
+        }
+        double acc = 0;
+        for (int q = 0; q < d; q++) acc += B[q * 6 + i] * (s * r[q]);
+        b[i] -= rho1 * acc;
+      }
+    }
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+// Returns nInitialCorrespondences - nBad (Optimizer.cc:1114).  pose_out: quaternion xyzw + translation
+// (SE3quat_recov before the cast to float); outlier_out[n] = mvbOutlier of the edges; chi2_out[n] (optional)
+// = the chi2 each edge was last classified with; stats_out (optional) = {rounds run, LM iterations, LM trials}.
+int orc_pose_optimize(const pose_opt_view* v, double* pose_out, uint8_t* outlier_out, double* chi2_out,
+                      int* stats_out) {
+  const int n = v->n;
+  if (stats_out) stats_out[0] = stats_out[1] = stats_out[2] = 0;
+  SE3 T0;
+  T0.r = Quat{v->pose[0], v->pose[1], v->pose[2], v->pose[3]};
+  quat_normalize(T0.r);  // SE3Quat(q, t) constructor
+  T0.t[0] = v->pose[4]; T0.t[1] = v->pose[5]; T0.t[2] = v->pose[6];
+  auto write_pose = [&](const SE3& T) {
+    pose_out[0] = T.r.x; pose_out[1] = T.r.y; pose_out[2] = T.r.z; pose_out[3] = T.r.w;
+    pose_out[4] = T.t[0]; pose_out[5] = T.t[1]; pose_out[6] = T.t[2];
+  };
+  for (int e = 0; e < n; e++) outlier_out[e] = 0;  // mvbOutlier[i] = false (:869, :903)
+  if (n < 3) { write_pose(T0); return 0; }         // :1000-1001 (the frame pose is left untouched)
+  PoseProblem P(v);
+  const float chi2Mono = 5.991, chi2Stereo = 7.815;  // :1005-1006
+  int nBad = 0;
+  for (int round = 0; round < 4; round++) {
+    P.T = T0;  // every round restarts from the frame pose (:1012-1013)
+    // ---- optimizer.optimize(10)
+    double lambda = -1, ni = 2;
+    int nBadLM = 0;
+    double x[6] = {0, 0, 0, 0, 0, 0};  // the solver's _x survives a failed solve
+    for (int it = 0; it < 10; it++) {
+      P.compute_active_errors();
+      double currentChi = P.active_robust_chi2();
+      double tempChi = currentChi;
+      const double iniChi = currentChi;
+      P.build_system();
+      if (it == 0) {
+        double mx = 0;
+        for (int j = 0; j < 6; j++) mx = std::max(std::fabs(P.H[j * 7]), mx);
+        lambda = 1e-5 * mx;
+        ni = 2; nBadLM = 0;
+      }
+      double rho = 0;
+      int qmax = 0;
+      do {
+        const SE3 backup = P.T;  // push
+        double Hl[36];
+        memcpy(Hl, P.H, sizeof(Hl));
+        for (int j = 0; j < 6; j++) Hl[j * 7] += lambda;
+        const bool ok2 = ldlt6_solve(Hl, P.b, x);  // a failed solve leaves x as it was
+        P.T = se3_exp_mul(x, P.T);
+        P.compute_active_errors();
+        tempChi = P.active_robust_chi2();
+        if (!ok2) tempChi = std::numeric_limits<double>::max();
+        rho = currentChi - tempChi;
+        double scale = 1e-3;
+        for (int j = 0; j < 6; j++) scale += x[j] * (lambda * x[j] + P.b[j]);
+        rho /= scale;
+        if (rho > 0 && std::isfinite(tempChi)) {
+          double alpha = 1. - std::pow((2 * rho - 1), 3);
+          alpha = std::min(alpha, 2. / 3.);
+          lambda *= std::max(1. / 3., alpha);
+          ni = 2;
+          currentChi = tempChi;
+        } else {
+          lambda *= ni;
+          ni *= 2;
+          P.T = backup;  // pop
+        }
+        qmax++;
+        if (stats_out) stats_out[2]++;
+      } while (rho < 0 && qmax < 10);
+      if (stats_out) stats_out[1]++;
+      if (qmax == 10 || rho == 0) break;
+      if ((iniChi - currentChi) * 1e3 < iniChi) nBadLM++;
+      else nBadLM = 0;
+      if (nBadLM >= 3) break;
+    }
+    // ---- classification (:1018-1096)
+    nBad = 0;
+    for (int e = 0; e < n; e++) {
+      if (outlier_out[e]) P.compute_error(e);  // excluded edges carry a stale error
+      const float chi2 = (float)P.chi2(e);
+      if (chi2_out) chi2_out[e] = P.chi2(e);
+      if (chi2 > (P.stereo(e) ? chi2Stereo : chi2Mono)) { outlier_out[e] = 1; P.level[e] = 1; nBad++; }
+      else { outlier_out[e] = 0; P.level[e] = 0; }
+    }
+    if (round == 2) P.robust = false;  // e->setRobustKernel(0) (:1041-1042)
+    if (stats_out) stats_out[0]++;
+    if (n < 10) break;                 // optimizer.edges().size() < 10 (:1098-1099)
+  }
+  write_pose(P.T);
+  return n - nBad;
+}
+
+}  // extern "C"

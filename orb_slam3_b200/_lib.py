@@ -73,6 +73,12 @@ SIGNATURES = {
     "stereo_device_results": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "stereo_kernel_launches": (C.c_longlong, [_vp]),
     "stereo_last_ms": (C.c_float, [_vp]),
+    "poseopt_create": (_i, [_i, _vp]),
+    "poseopt_destroy": (None, [_vp]),
+    "pose_optimize": (_i, [_vp, _vp, _vp, _vp]),
+    "pose_optimize_batch": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "poseopt_kernel_launches": (C.c_longlong, [_vp]),
+    "poseopt_last_ms": (C.c_float, [_vp]),
     "orb_set_profiling": (_i, [_vp, _i]),
     "orb_stage_times": (_i, [_vp, _vp, _vp, _i]),
     "orb_stage_name": (C.c_char_p, [_i]),

@@ -35,6 +35,7 @@
 #include <vector>
 
 #include "../../include/orb_b200.h"
+#include "se3_dev.cuh"
 #include "orb_engine.h"
 
 namespace orbb200 {
@@ -47,69 +48,6 @@ namespace orbb200 {
       return ORB_E_CUDA;                                                               \
     }                                                                                  \
   } while (0)
-
-// ------------------------------------------------------------ device helpers
-struct DQuat { double x, y, z, w; };
-
-__device__ __forceinline__ void q_normalize(DQuat& q) {  // se3quat.h:280-285
-  if (q.w < 0) { q.x = -q.x; q.y = -q.y; q.z = -q.z; q.w = -q.w; }
-  const double n = sqrt(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
-  q.x /= n; q.y /= n; q.z /= n; q.w /= n;
-}
-__device__ __forceinline__ DQuat q_mul(const DQuat& a, const DQuat& b) {
-  DQuat r;
-  r.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
-  r.y = a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z;
-  r.z = a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x;
-  r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
-  return r;
-}
-__device__ __forceinline__ void q_rot(const DQuat& q, const double* v, double* o) {
-  double ux = q.y * v[2] - q.z * v[1], uy = q.z * v[0] - q.x * v[2], uz = q.x * v[1] - q.y * v[0];
-  ux += ux; uy += uy; uz += uz;
-  o[0] = v[0] + q.w * ux + (q.y * uz - q.z * uy);
-  o[1] = v[1] + q.w * uy + (q.z * ux - q.x * uz);
-  o[2] = v[2] + q.w * uz + (q.x * uy - q.y * ux);
-}
-__device__ __forceinline__ void q_to_R(const DQuat& q, double* R) {
-  const double tx = 2 * q.x, ty = 2 * q.y, tz = 2 * q.z;
-  const double twx = tx * q.w, twy = ty * q.w, twz = tz * q.w;
-  const double txx = tx * q.x, txy = ty * q.x, txz = tz * q.x;
-  const double tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
-  R[0] = 1 - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
-  R[3] = txy + twz; R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
-  R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1 - (txx + tyy);
-}
-__device__ __forceinline__ DQuat R_to_q(const double* R) {
-  DQuat q;
-  double t = R[0] + R[4] + R[8];
-  if (t > 0) {
-    t = sqrt(t + 1.0);
-    q.w = 0.5 * t;
-    t = 0.5 / t;
-    q.x = (R[7] - R[5]) * t; q.y = (R[2] - R[6]) * t; q.z = (R[3] - R[1]) * t;
-  } else {
-    int i = 0;
-    if (R[4] > R[0]) i = 1;
-    if (R[8] > R[i * 4]) i = 2;
-    const int j = (i + 1) % 3, k = (j + 1) % 3;
-    t = sqrt(R[i * 4] - R[j * 4] - R[k * 4] + 1.0);
-    double v[3];
-    v[i] = 0.5 * t;
-    t = 0.5 / t;
-    q.w = (R[k * 3 + j] - R[j * 3 + k]) * t;
-    v[j] = (R[j * 3 + i] + R[i * 3 + j]) * t;
-    v[k] = (R[k * 3 + i] + R[i * 3 + k]) * t;
-    q.x = v[0]; q.y = v[1]; q.z = v[2];
-  }
-  return q;
-}
-
-struct HuberD { double delta, dsqr; };
-__device__ __forceinline__ void robustify(const HuberD& h, double e, double& rho0, double& rho1) {
-  if (e <= h.dsqr) { rho0 = e; rho1 = 1.; }
-  else { const double s = sqrt(e); rho0 = 2 * s * h.delta - h.dsqr; rho1 = h.delta / s; }
-}
 
 struct LbaDev {
   int n_kf, n_free, n_mp, n_edges, n;  // n = 6*n_free

@@ -64,3 +64,49 @@ class LocalBundleAdjustment:
         st = np.asarray(graph_dict["e_stereo"]).astype(bool)
         th = np.where(st, cls.CHI2_STEREO, cls.CHI2_MONO)
         return (result["chi2"] > th) | (result["depth_pos"] == 0)
+
+
+class PoseOptimization:
+    """Optimizer::PoseOptimization (src/Optimizer.cc:814-1115) over the C ABI: one frame or a batch of
+    independent frames per call, one CTA per frame in a single kernel launch.  No CPU fallback."""
+
+    CHI2_MONO = 5.991
+    CHI2_STEREO = 7.815
+
+    def __init__(self, device=0):
+        self._lib = _lib.lib()
+        h = C.c_void_p()
+        check(self._lib.poseopt_create(int(device), C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._lib.poseopt_destroy(h)
+            self._h = None
+
+    def __call__(self, view):
+        """view: pose_opt_view.  Returns (nInitialCorrespondences - nBad, pose[7], mvbOutlier[n])."""
+        pose = np.empty(7)
+        out = np.empty(max(view.n, 1), np.uint8)
+        n = check(self._lib.pose_optimize(self._h, C.byref(view), ptr(pose), ptr(out)))
+        return n, pose, out[:view.n].astype(bool)
+
+    def batch(self, views):
+        """Returns (inliers[B], poses[B,7], [mvbOutlier_k], stats[B,3] = rounds, LM iterations, LM trials)."""
+        from .views import pose_opt_view
+        B = len(views)
+        arr = (pose_opt_view * B)(*views)
+        pose = np.empty((B, 7))
+        outs = [np.empty(max(v.n, 1), np.uint8) for v in views]
+        optr = (C.c_void_p * B)(*[o.ctypes.data for o in outs])
+        inl = np.empty(B, np.int32)
+        stats = np.empty((B, 3), np.int32)
+        check(self._lib.pose_optimize_batch(self._h, B, arr, ptr(pose), optr, ptr(inl), ptr(stats)))
+        return inl, pose, [o[:v.n].astype(bool) for o, v in zip(outs, views)], stats
+
+    def last_ms(self):
+        return float(self._lib.poseopt_last_ms(self._h))
+
+    def kernel_launches(self):
+        return int(self._lib.poseopt_kernel_launches(self._h))

@@ -267,3 +267,42 @@ def shard_graph(g, rank, world):
     sub["e_obs"] = g["e_obs"][ed]
     sub["e_inv_sigma2"] = g["e_inv_sigma2"][ed]
     return sub, lm, ed
+
+
+def pose_scene(n, seed=0, stereo_frac=0.8, outlier_frac=0.1, rot_deg=1.0, trans=0.05, width=1280, height=720,
+               fx=700.0, bf=386.0, wild=False):
+    """One frame for Optimizer::PoseOptimization (SURVEY.md 8(f-2)): n matched MapPoints in the frustum
+    (depth 2..30 m), observations with the octave noise model, `outlier_frac` gross mismatches (random
+    positions), and an initial pose off the truth by `rot_deg` / `trans` (a constant-velocity prediction).
+    `wild=True` starts far enough away to force rejected LM trials.  Returns (pose_opt_view, truth dict)."""
+    from .views import make_pose_opt_view
+    rng = np.random.default_rng(seed)
+    cx, cy = width / 2.0, height / 2.0
+    q_true = _quat_from_yaw_pitch(0.3 + 0.01 * seed, -0.05)
+    t_true = np.array([0.4, -0.1, 2.0]) + 0.1 * rng.normal(size=3)
+    depth = rng.uniform(2, 30, n)
+    u = rng.uniform(30, width - 30, n)
+    v = rng.uniform(30, height - 30, n)
+    Xc = np.stack([(u - cx) / fx * depth, (v - cy) / fx * depth, depth], 1)
+    qi = q_true * np.array([-1, -1, -1, 1])
+    Xw = _qrot_many(np.tile(qi, (n, 1)), Xc - t_true)               # Tcw^-1 * Xc
+    octv = rng.integers(0, 8, n)
+    sig = 1.2 ** octv
+    noise = rng.normal(0, 1, (n, 3)) * sig[:, None]
+    ur = u - bf / depth + noise[:, 2]
+    st = rng.random(n) < stereo_frac
+    obs = np.stack([u + noise[:, 0], v + noise[:, 1], np.where(st, ur, -1.0)], 1)
+    out = rng.random(n) < outlier_frac
+    obs[out, 0] = rng.uniform(0, width, out.sum())
+    obs[out, 1] = rng.uniform(0, height, out.sum())
+    obs[out & st, 2] = obs[out & st, 0] - rng.uniform(2, 60, (out & st).sum())
+    inv_sigma2 = (1.0 / (scale_factors() ** 2)).astype(np.float32)[octv]
+    scale = 20.0 if wild else 1.0
+    w = rng.normal(0, np.deg2rad(rot_deg * scale) / np.sqrt(3), 3)
+    th = np.linalg.norm(w)
+    dq = np.concatenate([np.sin(th / 2) * w / max(th, 1e-12), [np.cos(th / 2)]])
+    q0 = _quat_mul(dq, q_true)
+    t0 = _quat_rot(dq, t_true) + rng.normal(0, trans * scale / np.sqrt(3), 3)
+    pose0 = np.concatenate([q0, t0]).astype(np.float32).astype(np.float64)  # Sophus::SE3f cast to double (:830-831)
+    view = make_pose_opt_view(Xw.astype(np.float32), obs.astype(np.float32), inv_sigma2, (fx, fx, cx, cy, bf), pose0)
+    return view, dict(pose=np.concatenate([q_true, t_true]), outlier=out, stereo=st)

@@ -154,3 +154,24 @@ def make_lba_graph_view(kf_pose, kf_fixed, kf_cam, mp_pos, e_kf, e_mp, e_stereo,
         setattr(v, k, _p(arr))
     v._keep = a
     return v
+
+
+class pose_opt_view(C.Structure):
+    _fields_ = [("n", _i), ("xw", _vp), ("obs", _vp), ("inv_sigma2", _vp),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("bf", C.c_float),
+                ("pose", C.c_double * 7)]
+
+
+def make_pose_opt_view(xw, obs, inv_sigma2, cam, pose):
+    """xw [n,3] f32 world points, obs [n,3] f32 (u, v, uRight or -1), inv_sigma2 [n] f32,
+    cam = (fx, fy, cx, cy, bf), pose = quaternion xyzw + translation."""
+    a = dict(xw=_arr(xw, np.float32), obs=_arr(obs, np.float32), inv_sigma2=_arr(inv_sigma2, np.float32))
+    v = pose_opt_view()
+    v.n = len(a["inv_sigma2"])
+    for k, arr in a.items():
+        setattr(v, k, _p(arr))
+    v.fx, v.fy, v.cx, v.cy, v.bf = (float(c) for c in cam)
+    for i in range(7):
+        v.pose[i] = float(pose[i])
+    v._keep = a
+    return v
