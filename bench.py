@@ -512,6 +512,46 @@ def run_stereo_gpu(device, tstream, pairs=64, reps=5, cpu=True):
     return out
 
 
+def run_pose_gpu(device, frames=128, edges=1000, reps=5, cpu=True):
+    """SURVEY.md 8(f-2): `frames` independent Optimizer::PoseOptimization problems (one per tracked frame,
+    `edges` matched MapPoints each, 80 % stereo, 10 % gross mismatches) per step, one kernel launch."""
+    from orb_slam3_b200 import scenes
+    from orb_slam3_b200.optimizer import PoseOptimization
+    po = PoseOptimization(device)
+    uniq = 16
+    base = [scenes.pose_scene(edges, seed=100 + i)[0] for i in range(uniq)]
+    views = [base[i % uniq] for i in range(frames)]
+    po.batch(views)
+    ms_dev, t0 = 0.0, time.perf_counter()
+    for _ in range(reps):
+        inl, pose, outs, stats = po.batch(views)
+        ms_dev += po.last_ms()
+    ms_wall = (time.perf_counter() - t0) * 1e3 / reps
+    ms_dev /= reps
+    out = {"config": "%d frames x %d edges (80%% stereo, 10%% mismatches), 4 rounds x optimize(10)" % (frames, edges),
+           "value": frames / (ms_dev * 1e-3), "unit": "PoseOptimization calls/s (kernel, CUDA events)",
+           "e2e_value": frames / (ms_wall * 1e-3), "e2e_unit": "calls/s through the host-buffer C ABI (H2D + kernel + D2H)",
+           "ms_per_step": ms_dev, "gpu_launches_per_step": 1,
+           "lm_trials_per_frame": float(stats[:, 2].mean()), "inliers_per_frame": float(inl.mean())}
+    if cpu:
+        from oracle import oracle as O
+        t0 = time.perf_counter()
+        refs = [O.pose_optimize(v) for v in base]
+        t_cpu = (time.perf_counter() - t0) / uniq
+        ok = all(np.array_equal(outs[i], refs[i]["outlier"]) and
+                 np.abs(pose[i] - refs[i]["pose"]).max() < 1e-7 for i in range(uniq))
+        out["cpu_baseline"] = {"ms_per_call": 1e3 * t_cpu, "threads": 1, "kind": "port", "parity_first_%d" % uniq: bool(ok)}
+    return out
+
+
+def _guarded(fn, *a, **k):
+    """The extra legs must never cost the headline line."""
+    try:
+        return fn(*a, **k)
+    except Exception as e:  # noqa: BLE001
+        return {"error": "%s: %s" % (type(e).__name__, e)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -523,7 +563,7 @@ def main():
     ap.add_argument("--e2e-workers", type=int, default=4, help="host threads feeding the GPU in the e2e leg")
     ap.add_argument("--no-lba", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-stereo", action="store_true")
+    ap.add_argument("--no-stereo", action="store_true", help="skip the 8(f) legs (ComputeStereoMatches, PoseOptimization)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -636,7 +676,10 @@ def main():
         lba = run_lba_gpu(rank, world, local_rank)
     stereo = None
     if rank == 0 and not args.no_stereo:
-        stereo = run_stereo_gpu(local_rank, tstream, cpu=(world == 1 and not args.no_cpu))
+        stereo = _guarded(run_stereo_gpu, local_rank, tstream, cpu=(world == 1 and not args.no_cpu))
+    pose = None
+    if rank == 0 and not args.no_stereo:
+        pose = _guarded(run_pose_gpu, local_rank, cpu=(world == 1 and not args.no_cpu))
     if world > 1:
         dist.barrier()
 
@@ -722,6 +765,7 @@ def main():
             "cpu_baseline": cpu,
             "lba": lba,
             "stereo": stereo,
+            "pose_optimization": pose,
         }
         print(json.dumps(line))
     if world > 1:
