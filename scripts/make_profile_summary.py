@@ -46,6 +46,13 @@ c4, c5 = d["lba"]["config4"], d["lba"]["config5"]
 o.append(f"| LocalBA config 4 ({c4['config']}) | **{c4['value']:.0f}** LM iterations/s ({c4['ms_total']:.1f} ms for optimize(10), {c4['trials']} trials) vs {d['lba']['cpu_baseline_config4']['value']:.1f} on one CPU thread (g2o is single-threaded) |")
 o.append(f"| LocalBA config 5 ({c5['config']}), 1 GPU | {c5['value']:.0f} LM iterations/s ({c5['ms_total']:.1f} ms) |")
 o.append(f"| 2xB200 (`bench_r1_n2.json`) | {n2['value']:.0f} frames/s resident; config 5 sharded by landmark + ncclAllReduce: {n2['lba']['config5']['value']:.0f} LM iterations/s |")
+if d.get("stereo") and "error" not in d["stereo"]:
+    sx = d["stereo"]
+    o.append(f"| SURVEY 8(f-1) `Frame::ComputeStereoMatches`, {sx['config']} | **{sx['stereo_match_us_per_pair']:.1f} us per pair** on the device-resident extractor outputs (3 launches per 64 pairs, {sx['matches_per_pair']:.0f} matches/pair) vs {sx['cpu_baseline']['stereo_match_ms_per_pair']:.2f} ms on one CPU thread; whole stereo frame (2 x extract + match): {sx['pairs_per_s']:.0f} pairs/s; bench-time parity vs oracle: {sx['cpu_baseline']['parity_pair0']} |")
+if d.get("pose_optimization") and "error" not in d["pose_optimization"]:
+    px = d["pose_optimization"]
+    pc = px["cpu_baseline"]
+    o.append(f"| SURVEY 8(f-2) `Optimizer::PoseOptimization`, {px['config']} | **{px['value']:.0f} calls/s** in one kernel launch ({px['ms_per_step']:.2f} ms per 128 frames, {px['lm_trials_per_frame']:.0f} LM trials per frame); {px['e2e_value']:.0f} calls/s through the host-buffer ABI; CPU port {pc['ms_per_call']:.2f} ms per call on one thread; bench-time parity vs oracle: {[v for k, v in pc.items() if k.startswith('parity')][0]} |")
 o.append(f"\n## Where a step goes (CUDA events per stage, ms per {B}-frame step)\n")
 o.append("| stage | ms/step | us/frame | algorithmic GB/s | frac of HBM peak (6556 GB/s measured) |\n|---|---|---|---|---|")
 for k in ["pyramid", "fast", "octree", "blur", "describe", "layout", "match_last(th15)", "match_local(th3)"]:
@@ -61,8 +68,10 @@ o.append(f"`roofline` of the bench line: dominant kernel = `{rf['kernel']}` ({rf
          "ncu explains the gap to the HBM roofline: the kernel is instruction-issue bound (70 % of issue slots busy, <3 % DRAM throughput).\n")
 o.append("## ncu launch list (`launches_r1.csv`, `--metrics gpu__time_duration.sum --clock-control none`, one `bench.py --steps 2` run)\n")
 o.append(launch)
-o.append("\nShares agree with the event-based stage table within the cold-cache / serialisation caveat (ncu serialises the side\n"
-         "streams): FAST 26 % vs 28 %, octree 21 % vs 14 %, blur 13 % vs 14 %, describe 9 % vs 10 %.\n")
+tot = sum(st[k] for k in ["pyramid", "fast", "octree", "blur", "describe", "layout", "match_last(th15)", "match_local(th3)"])
+o.append("\nEvent-based shares of the same stages for comparison (the launch list is cold-cache and serialises the side "
+         "streams, so the shares must agree, not the absolute times): "
+         + ", ".join(f"{k} {100 * st[k] / tot:.0f} %" for k in ["fast", "octree", "blur", "pyramid", "describe"]) + ".\n")
 o.append("## ncu `--set full`, extractor kernels at batch 64 (`extract_r1.ncu-rep`)\n")
 o.append(extract_raw)
 o.append("\n## ncu `--set full`, LBA kernels on config 4 (`lba_r1.ncu-rep`)\n")
@@ -74,7 +83,7 @@ o.append("""
 |---|---|---|---|
 | FAST cells | 36 | 10.4 | compaction queue instead of divergent heavy path; iniTh pass first and minTh pass only for empty cells (the reference's own two cv::FAST calls); packed-byte VABSDIFF4 pre-test; tile through TMA (UTMALDG.3D + mbarrier) |
 | describe (IC angle + rBRIEF) | 15 | 4.7 | **pattern table moved from `__constant__` (lane-divergent index = 32 replays per load) to a lane-transposed shared-memory copy** (ncu source view: 45 % of samples on `LDC.64`) |
-| blur | 11.5 | 6.3 | 4 pixels / thread, aligned word loads and stores |
+| blur | 11.5 | 3.2 | 4 pixels / thread, aligned word loads and stores (6.3); then the taps as byte vectors on the integer dot-product unit: IDP.4A horizontal, IDP.2A vertical on row-pair words, PRMT packing (68 -> ~16 lane instructions per pixel) |
 | octree | 8.5 | 6.5 | node arrays in shared memory, 4-way batched point loops, level-major launch order |
 | level-0 copy | 4.1 | 0.5 | one vectorised kernel instead of 64 cudaMemcpy2DAsync |
 | matchers (both) | 12.2 | 10.5 (overlapped on two side streams) | per-keypoint state of the resolution rounds in shared memory |
@@ -83,7 +92,9 @@ o.append("""
 
 Tried and reverted (measured slower or no gain): L2-sized sub-batches (no stage is HBM bound), orient/brief kernel
 split, forcing 64 registers on describe, fewer CTAs / 4-accumulator ILP in the LDLT diagonal block, staging the
-describe patch in shared memory before the constant-memory fix.
+describe patch in shared memory before the constant-memory fix, running two to four sub-batches on concurrent
+(also prioritised) stream lanes to hide the latency-bound octree under the other lanes' FAST grids (27.5 k -> 27.7 k fps
+plain, 25.4 k with priorities).
 """)
 open(os.path.join(P, "r1_summary.md"), "w").write("\n".join(o))
 print("written", len(o))
