@@ -9,6 +9,8 @@
                        (BASELINE.json configs[0]).
   match_scene.npz    : oracle results of the three matchers on a seeded scene.
   lba_small.npz      : oracle optimize(10) result on lba_graph(8, 300, seed=1).
+  stereo_640x480.npz : oracle Frame::ComputeStereoMatches on synth_frame(480,640,5) / stereo_right(.., 6, (5,30,17)).
+  pose_small.npz     : oracle Optimizer::PoseOptimization on pose_scene(400, seed=7).
 """
 import os
 import sys
@@ -20,7 +22,7 @@ sys.path.insert(0, ROOT)
 import cv2  # noqa: E402
 from oracle import oracle as O  # noqa: E402
 from orb_slam3_b200 import scenes  # noqa: E402
-from orb_slam3_b200.synth import synth_frame, shifted_frame  # noqa: E402
+from orb_slam3_b200.synth import synth_frame, shifted_frame, stereo_right  # noqa: E402
 
 out = os.path.join(ROOT, "tests", "golden")
 os.makedirs(out, exist_ok=True)
@@ -66,4 +68,19 @@ g, _ = scenes.lba_graph(8, 300, seed=1)
 r = O.lba_solve(scenes.lba_view(g))
 np.savez_compressed(os.path.join(out, "lba_small.npz"), kf_pose=r["kf_pose"], mp_pos=r["mp_pos"], chi2=r["chi2"],
                     iterations=r["iterations"], trials=r["stats"]["trials"], chi2_final=r["stats"]["chi2_final"])
+# ---- ComputeStereoMatches
+sl = synth_frame(480, 640, 5)
+sr = stereo_right(sl, 6, disparities=(5, 30, 17))
+el, er = O.OracleExtractor(1000), O.OracleExtractor(1000)
+kl, dl, _ = el.extract(sl)
+kr, dr, _ = er.extract(sr)
+n_st, ur, dp, sad = O.stereo_match(kl, dl, kr, dr, [el.level_image(l) for l in range(8)],
+                                   [er.level_image(l) for l in range(8)], 386.0, 0.5514)
+np.savez_compressed(os.path.join(out, "stereo_640x480.npz"), n=n_st, u_right=ur, depth=dp, sad=sad)
+
+# ---- PoseOptimization
+pv, _ = scenes.pose_scene(400, seed=7)
+pr = O.pose_optimize(pv)
+np.savez_compressed(os.path.join(out, "pose_small.npz"), inliers=pr["inliers"], pose=pr["pose"], outlier=pr["outlier"],
+                    stats=pr["stats"])
 print("golden fixtures written to", out)

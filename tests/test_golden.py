@@ -61,6 +61,48 @@ def test_oracle_reproduces_golden(oracle):
     assert np.allclose(r["mp_pos"], zl["mp_pos"], rtol=0, atol=1e-7)
 
 
+def _stereo_inputs():
+    from orb_slam3_b200.synth import stereo_right
+    sl = synth_frame(480, 640, 5)
+    return sl, stereo_right(sl, 6, disparities=(5, 30, 17))
+
+
+def test_oracle_reproduces_stereo_and_pose_golden(oracle):
+    sl, sr = _stereo_inputs()
+    el, er = oracle.OracleExtractor(1000), oracle.OracleExtractor(1000)
+    kl, dl, _ = el.extract(sl)
+    kr, dr, _ = er.extract(sr)
+    n, ur, dp, sad = oracle.stereo_match(kl, dl, kr, dr, [el.level_image(l) for l in range(8)],
+                                         [er.level_image(l) for l in range(8)], 386.0, 0.5514)
+    z = _load("stereo_640x480.npz")
+    assert n == int(z["n"]) and np.array_equal(ur, z["u_right"]) and np.array_equal(dp, z["depth"])
+    assert np.array_equal(sad, z["sad"])
+    pv, _ = scenes.pose_scene(400, seed=7)
+    r = oracle.pose_optimize(pv)
+    zp = _load("pose_small.npz")
+    assert r["inliers"] == int(zp["inliers"]) and np.array_equal(r["outlier"], zp["outlier"])
+    assert np.array_equal(r["stats"], zp["stats"]) and np.allclose(r["pose"], zp["pose"], rtol=0, atol=1e-11)
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_stereo_and_pose_golden():
+    from orb_slam3_b200.extractor import ORBextractor
+    from orb_slam3_b200.optimizer import PoseOptimization
+    from orb_slam3_b200.stereo import StereoMatcher
+    sl, sr = _stereo_inputs()
+    el, er = ORBextractor(1000, 1.2, 8, 20, 7), ORBextractor(1000, 1.2, 8, 20, 7)
+    _, kl, _ = el(sl)
+    er(sr)
+    n, ur, dp = StereoMatcher().ComputeStereoMatches(el, er, len(kl), 386.0, 0.5514)
+    z = _load("stereo_640x480.npz")
+    assert n == int(z["n"]) and np.array_equal(ur, z["u_right"]) and np.array_equal(dp, z["depth"])
+    pv, _ = scenes.pose_scene(400, seed=7)
+    inl, pose, out = PoseOptimization()(pv)
+    zp = _load("pose_small.npz")
+    assert inl == int(zp["inliers"]) and np.array_equal(out, zp["outlier"])
+    assert np.allclose(pose, zp["pose"], rtol=0, atol=1e-8)
+
+
 @pytest.mark.gpu
 def test_gpu_reproduces_golden():
     from orb_slam3_b200.extractor import ORBextractor
