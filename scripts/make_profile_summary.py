@@ -76,6 +76,10 @@ o.append("## ncu `--set full`, extractor kernels at batch 64 (`extract_r1.ncu-re
 o.append(extract_raw)
 o.append("\n## ncu `--set full`, LBA kernels on config 4 (`lba_r1.ncu-rep`)\n")
 o.append(lba_raw)
+if os.path.exists(os.path.join(P, "f_rows_r1.ncu-rep")):
+    o.append("\n## ncu `--set full`, SURVEY 8(f) kernels (`f_rows_r1.ncu-rep`: ComputeStereoMatches on 64 pairs, "
+             "PoseOptimization on 128 frames x 1000 edges; `scripts/profile_f.py`)\n")
+    o.append(run("raw", os.path.join(P, "f_rows_r1.ncu-rep")))
 o.append("""
 ## What moved during the round (us per 720p frame at batch 64, CUDA events)
 
