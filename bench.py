@@ -574,6 +574,11 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # stdout carries exactly one JSON line: libraries that write to fd 1 (NCCL prints its version banner
+    # there) are pointed at stderr, the line itself goes to a duplicate of the original stdout
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: orb_slam3_b200 has no CPU path")
     torch.cuda.set_device(local_rank)
@@ -767,7 +772,7 @@ def main():
             "stereo": stereo,
             "pose_optimization": pose,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
