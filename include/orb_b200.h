@@ -351,6 +351,53 @@ int pose_optimize_batch(orb_poseopt* h, int batch, const pose_opt_view* views, d
 long long poseopt_kernel_launches(const orb_poseopt* h);
 float poseopt_last_ms(orb_poseopt* h); /* device time of the last call (CUDA events) */
 
+/* ------------------------------------------------------------------------
+ * bool Frame::isInFrustum(MapPoint* pMP, float viewingCosLimit) (src/Frame.cc:512-570,
+ * the Nleft == -1 branch) with MapPoint::PredictScale (src/MapPoint.cc:531-546),
+ * the producer of the mbTrackInView / mTrackProj* / mnTrackScaleLevel /
+ * mTrackViewCos / mTrackDepth fields that SearchByProjection(Frame&, vector<MapPoint*>&)
+ * consumes (orb_mappoint_view above).  One call tests all local map points of a frame
+ * (Tracking::SearchLocalPoints, src/Tracking.cc:3367-3390).
+ * ---------------------------------------------------------------------- */
+typedef struct orb_frustum_view {
+  int32_t n;               /* map points */
+  const float* world_pos;  /* n x 3: GetWorldPos() */
+  const float* normal;     /* n x 3: GetNormal() */
+  const float* min_dist;   /* n: mfMinDistance (GetMinDistanceInvariance() = 0.8f * this) */
+  const float* max_dist;   /* n: mfMaxDistance (GetMaxDistanceInvariance() = 1.2f * this) */
+  float Rcw[9];            /* Frame::mRcw, row-major */
+  float tcw[3];            /* Frame::mtcw */
+  float Ow[3];             /* Frame::mOw */
+  float fx, fy, cx, cy, bf;
+  float min_x, max_x, min_y, max_y; /* Frame::mnMinX .. mnMaxY */
+  float log_scale_factor;  /* Frame::mfLogScaleFactor = log(mfScaleFactor) as float */
+  int32_t n_levels;        /* Frame::mnScaleLevels */
+} orb_frustum_view;
+
+typedef struct orb_frustum orb_frustum;
+int frustum_create(int device, orb_frustum** out);
+void frustum_destroy(orb_frustum* h);
+/* Host outputs, n entries each.  track_in_view, proj_x, proj_y are always written (the reference
+ * resets mTrackProjX/Y to -1 and overwrites them once the projection is inside the image);
+ * proj_xr, scale_level, view_cos, depth are written only where track_in_view = 1 -- elsewhere the
+ * caller's values stay, like the stale MapPoint members of the reference.  Returns the number of
+ * points in view, or ORB_E_*. */
+int frame_is_in_frustum(orb_frustum* h, const orb_frustum_view* v, float viewing_cos_limit, uint8_t* track_in_view,
+                        float* proj_x, float* proj_y, float* proj_xr, int32_t* scale_level, float* view_cos,
+                        float* depth);
+/* Enqueue-only variant for device-resident chaining: the SoA results stay on the device in the layout
+ * of orb_mappoint_view's fields (frustum_device_results), on cuda_stream (NULL = the handle's). */
+int frame_is_in_frustum_device(orb_frustum* h, const orb_frustum_view* v, float viewing_cos_limit, void* cuda_stream);
+int frustum_device_results(orb_frustum* h, const uint8_t** d_track_in_view, const float** d_proj_x,
+                           const float** d_proj_y, const float** d_proj_xr, const int32_t** d_scale_level,
+                           const float** d_view_cos, const float** d_depth, const int32_t** d_count);
+long long frustum_kernel_launches(const orb_frustum* h);
+float frustum_last_ms(orb_frustum* h);
+/* The kernel's per-point body executed on the host (same source, csrc/frustum_core.h) -- a debug hook
+ * for the CPU tests, not a product path: needs no device and is not used by any caller of this library. */
+int frustum_debug_host(const orb_frustum_view* v, float viewing_cos_limit, uint8_t* track_in_view, float* proj_x,
+                       float* proj_y, float* proj_xr, int32_t* scale_level, float* view_cos, float* depth);
+
 /* Per-stage device timing (CUDA events on the launching stream).  Stages:
  * 0 h2d, 1 pyramid, 2 fast, 3 octree, 4 blur, 5 layout, 6 orient+describe,
  * 7 d2h.  orb_stage_times fills ms[8] (accumulated) and launches[8]. */

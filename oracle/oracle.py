@@ -72,6 +72,8 @@ def lib():
         L.orc_lba_reduced_system.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.POINTER(C.c_double)]
         L.orc_sort_nodes.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_is_in_frustum.restype = C.c_int
+        L.orc_is_in_frustum.argtypes = [C.c_void_p, C.c_float] + [C.c_void_p] * 7
         L.orc_pose_optimize.restype = C.c_int
         L.orc_pose_optimize.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_stereo_match.restype = C.c_int
@@ -302,3 +304,17 @@ def pose_optimize(view):
     stats = np.zeros(3, np.int32)
     n = lib().orc_pose_optimize(C.byref(view), _ptr(pose), _ptr(out), _ptr(chi2), _ptr(stats))
     return dict(inliers=n, pose=pose, outlier=out[:view.n].astype(bool), chi2=chi2[:view.n], stats=stats)
+
+
+def is_in_frustum(view, viewing_cos_limit=0.5, out=None):
+    """Frame::isInFrustum (Frame.cc:512-570) over all points of an orb_frustum_view.  Returns (n_in_view, out);
+    out keeps stale members for points that are not in view, like the reference."""
+    if out is None:
+        n = view.n
+        out = dict(track_in_view=np.zeros(n, np.uint8), proj_x=np.zeros(n, np.float32), proj_y=np.zeros(n, np.float32),
+                   proj_xr=np.zeros(n, np.float32), scale_level=np.zeros(n, np.int32),
+                   view_cos=np.zeros(n, np.float32), depth=np.zeros(n, np.float32))
+    k = lib().orc_is_in_frustum(C.byref(view), float(viewing_cos_limit),
+                                *[_ptr(out[f]) for f in ("track_in_view", "proj_x", "proj_y", "proj_xr",
+                                                         "scale_level", "view_cos", "depth")])
+    return k, out

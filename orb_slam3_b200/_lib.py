@@ -79,6 +79,14 @@ SIGNATURES = {
     "pose_optimize_batch": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "poseopt_kernel_launches": (C.c_longlong, [_vp]),
     "poseopt_last_ms": (C.c_float, [_vp]),
+    "frustum_create": (_i, [_i, _vp]),
+    "frustum_destroy": (None, [_vp]),
+    "frame_is_in_frustum": (_i, [_vp, _vp, C.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "frame_is_in_frustum_device": (_i, [_vp, _vp, C.c_float, _vp]),
+    "frustum_device_results": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "frustum_kernel_launches": (C.c_longlong, [_vp]),
+    "frustum_last_ms": (C.c_float, [_vp]),
+    "frustum_debug_host": (_i, [_vp, C.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "orb_set_profiling": (_i, [_vp, _i]),
     "orb_stage_times": (_i, [_vp, _vp, _vp, _i]),
     "orb_stage_name": (C.c_char_p, [_i]),

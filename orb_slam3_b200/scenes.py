@@ -306,3 +306,31 @@ def pose_scene(n, seed=0, stereo_frac=0.8, outlier_frac=0.1, rot_deg=1.0, trans=
     pose0 = np.concatenate([q0, t0]).astype(np.float32).astype(np.float64)  # Sophus::SE3f cast to double (:830-831)
     view = make_pose_opt_view(Xw.astype(np.float32), obs.astype(np.float32), inv_sigma2, (fx, fx, cx, cy, bf), pose0)
     return view, dict(pose=np.concatenate([q_true, t_true]), outlier=out, stereo=st)
+
+
+def frustum_scene(n, seed=0, width=1280, height=720, fx=700.0, bf=386.0):
+    """Local map points around one frame for Frame::isInFrustum (SURVEY.md 8(f-3)): a mix that takes every
+    exit of the function -- behind the camera, outside the image bounds, outside the scale-invariance
+    distance band, seen from too steep an angle, and in view.  Returns (orb_frustum_view, truth dict)."""
+    from .views import make_frustum_view
+    rng = np.random.default_rng(seed)
+    cx, cy = width / 2.0, height / 2.0
+    q = _quat_from_yaw_pitch(0.4 + 0.1 * seed, 0.1)                      # Rwc
+    twc = np.array([1.0, -0.5, 2.0]) + rng.normal(0, 0.3, 3)
+    qi = q * np.array([-1, -1, -1, 1])
+    R = np.stack([_quat_rot(qi, e) for e in np.eye(3)], 1)               # Rcw
+    tcw = -R @ twc
+    depth = rng.uniform(-5, 40, n)                                       # ~11 % behind the camera
+    u = rng.uniform(-200, width + 200, n)                                # some outside the image
+    v = rng.uniform(-120, height + 120, n)
+    Xc = np.stack([(u - cx) / fx * depth, (v - cy) / fx * depth, depth], 1)
+    Xw = (Xc - tcw) @ R                                                  # Rcw^T (Xc - tcw)
+    # reference keyframe of each point: somewhere else, sets the normal and the distance band
+    ref = twc + rng.normal(0, 6.0, (n, 3))
+    d_ref = np.linalg.norm(Xw - ref, axis=1)
+    normal = (Xw - ref) / d_ref[:, None]
+    level = rng.integers(0, 8, n)
+    max_dist = d_ref * (1.2 ** level)
+    min_dist = max_dist / (1.2 ** 7)
+    view = make_frustum_view(Xw, normal, min_dist, max_dist, R, tcw, (fx, fx, cx, cy, bf), (0.0, width, 0.0, height))
+    return view, dict(depth=depth, u=u, v=v)

@@ -175,3 +175,36 @@ def make_pose_opt_view(xw, obs, inv_sigma2, cam, pose):
         v.pose[i] = float(pose[i])
     v._keep = a
     return v
+
+
+class orb_frustum_view(C.Structure):
+    _fields_ = [("n", _i), ("world_pos", _vp), ("normal", _vp), ("min_dist", _vp), ("max_dist", _vp),
+                ("Rcw", C.c_float * 9), ("tcw", C.c_float * 3), ("Ow", C.c_float * 3),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("bf", C.c_float),
+                ("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float),
+                ("log_scale_factor", C.c_float), ("n_levels", _i)]
+
+
+def make_frustum_view(world_pos, normal, min_dist, max_dist, Rcw, tcw, cam, bounds, scale_factor=1.2, n_levels=8):
+    """Frame side: Rcw [3,3], tcw [3] (Ow = -Rcw^T tcw in float like Frame::UpdatePoseMatrices),
+    cam = (fx, fy, cx, cy, bf), bounds = (min_x, max_x, min_y, max_y)."""
+    a = dict(world_pos=_arr(world_pos, np.float32), normal=_arr(normal, np.float32),
+             min_dist=_arr(min_dist, np.float32), max_dist=_arr(max_dist, np.float32))
+    v = orb_frustum_view()
+    v.n = len(a["min_dist"])
+    for k, arr in a.items():
+        setattr(v, k, _p(arr))
+    R = np.asarray(Rcw, np.float32).reshape(3, 3)
+    t = np.asarray(tcw, np.float32).reshape(3)
+    Ow = (-(R.T @ t)).astype(np.float32)
+    for i in range(9):
+        v.Rcw[i] = float(R.reshape(9)[i])
+    for i in range(3):
+        v.tcw[i] = float(t[i])
+        v.Ow[i] = float(Ow[i])
+    v.fx, v.fy, v.cx, v.cy, v.bf = (float(c) for c in cam)
+    v.min_x, v.max_x, v.min_y, v.max_y = (float(b) for b in bounds)
+    v.log_scale_factor = float(np.log(np.float32(scale_factor)))  # std::log(float) (Frame.cc:112)
+    v.n_levels = int(n_levels)
+    v._keep = a
+    return v
