@@ -544,6 +544,35 @@ def run_pose_gpu(device, frames=128, edges=1000, reps=5, cpu=True):
     return out
 
 
+def run_frustum_gpu(device, cpu=True):
+    """SURVEY.md 8(f-3): Frame::isInFrustum over the local map of one frame (5000 points, the
+    Tracking::SearchLocalPoints shape) and over 2^20 points (streaming rate of the kernel)."""
+    from orb_slam3_b200 import scenes
+    from orb_slam3_b200.frustum import FrustumCuller
+    fc = FrustumCuller(device)
+    out = {}
+    for name, n, reps in (("local_map_5000", 5000, 20), ("stream_1M", 1 << 20, 5)):
+        v, _ = scenes.frustum_scene(n, seed=3)
+        k, o = fc.isInFrustum(v)
+        ms_dev, t0 = 0.0, time.perf_counter()
+        for _ in range(reps):
+            k, o = fc.isInFrustum(v, out=o)
+            ms_dev += fc.last_ms()
+        ms_wall = (time.perf_counter() - t0) * 1e3 / reps
+        ms_dev /= reps
+        e = {"points": n, "in_view": int(k), "kernel_us": 1e3 * ms_dev, "host_call_us": 1e3 * ms_wall,
+             "kernel_GBps_algorithmic": n * 57 / (ms_dev * 1e-3) / 1e9, "bytes_per_point": 57}
+        if cpu:
+            from oracle import oracle as O
+            t0 = time.perf_counter()
+            for _ in range(3):
+                k_ref, ref = O.is_in_frustum(v)
+            e["cpu_port_us"] = (time.perf_counter() - t0) / 3 * 1e6
+            e["parity"] = bool(k_ref == k and all(np.array_equal(o[f], ref[f]) for f in ref))
+        out[name] = e
+    return out
+
+
 def _guarded(fn, *a, **k):
     """The extra legs must never cost the headline line."""
     try:
@@ -563,7 +592,7 @@ def main():
     ap.add_argument("--e2e-workers", type=int, default=4, help="host threads feeding the GPU in the e2e leg")
     ap.add_argument("--no-lba", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-stereo", action="store_true", help="skip the 8(f) legs (ComputeStereoMatches, PoseOptimization)")
+    ap.add_argument("--no-stereo", action="store_true", help="skip the 8(f) legs (ComputeStereoMatches, PoseOptimization, isInFrustum)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -685,6 +714,9 @@ def main():
     pose = None
     if rank == 0 and not args.no_stereo:
         pose = _guarded(run_pose_gpu, local_rank, cpu=(world == 1 and not args.no_cpu))
+    frustum = None
+    if rank == 0 and not args.no_stereo:
+        frustum = _guarded(run_frustum_gpu, local_rank, cpu=(world == 1 and not args.no_cpu))
     if world > 1:
         dist.barrier()
 
@@ -771,6 +803,7 @@ def main():
             "lba": lba,
             "stereo": stereo,
             "pose_optimization": pose,
+            "is_in_frustum": frustum,
         }
         print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:
