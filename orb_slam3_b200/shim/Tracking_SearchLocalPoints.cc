@@ -40,8 +40,11 @@ void Tracking::SearchLocalPoints() {
   for (int i = 0; i < n; i++) {
     const Eigen::Vector3f P = cand[i]->GetWorldPos(), N = cand[i]->GetNormal();
     for (int k = 0; k < 3; k++) { pos[3 * i + k] = P[k]; nrm[3 * i + k] = N[k]; }
-    dmin[i] = cand[i]->GetMinDistanceInvariance() / 0.8f;  // the view carries mfMinDistance / mfMaxDistance;
-    dmax[i] = cand[i]->GetMaxDistanceInvariance() / 1.2f;  // a 2-line accessor pair on MapPoint avoids the round trip
+    // the view carries the raw mfMinDistance / mfMaxDistance (PredictScale divides the raw maximum by the
+    // distance, MapPoint.cc:531-546): two one-line public getters added to include/MapPoint.h,
+    // because dividing Get{Min,Max}DistanceInvariance() by 0.8f / 1.2f does not round-trip in float
+    dmin[i] = cand[i]->GetMinDistanceRaw();
+    dmax[i] = cand[i]->GetMaxDistanceRaw();
   }
   orb_frustum_view v;
   v.n = n;
