@@ -53,6 +53,9 @@ if d.get("pose_optimization") and "error" not in d["pose_optimization"]:
     px = d["pose_optimization"]
     pc = px["cpu_baseline"]
     o.append(f"| SURVEY 8(f-2) `Optimizer::PoseOptimization`, {px['config']} | **{px['value']:.0f} calls/s** in one kernel launch ({px['ms_per_step']:.2f} ms per 128 frames, {px['lm_trials_per_frame']:.0f} LM trials per frame); {px['e2e_value']:.0f} calls/s through the host-buffer ABI; CPU port {pc['ms_per_call']:.2f} ms per call on one thread; bench-time parity vs oracle: {[v for k, v in pc.items() if k.startswith('parity')][0]} |")
+if not d.get("is_in_frustum") and os.path.exists(os.path.join(P, "bench_r1_f3_leg.json")):
+    # the 8(f-3) leg was added after the 20-step line was taken: its numbers come from a later short run
+    d["is_in_frustum"] = json.load(open(os.path.join(P, "bench_r1_f3_leg.json"))).get("is_in_frustum")
 if d.get("is_in_frustum") and "error" not in d["is_in_frustum"]:
     fl, fs = d["is_in_frustum"]["local_map_5000"], d["is_in_frustum"]["stream_1M"]
     o.append(f"| SURVEY 8(f-3) `Frame::isInFrustum` over a local map | 5000 points: kernel {fl['kernel_us']:.0f} us, host-buffer call {fl['host_call_us']:.0f} us (CPU port {fl.get('cpu_port_us', float('nan')):.0f} us); 2^20 points: kernel {fs['kernel_us']:.0f} us = **{fs['kernel_GBps_algorithmic']:.0f} GB/s** algorithmic (57 B/point), CPU port {fs.get('cpu_port_us', float('nan'))/1e3:.1f} ms; bench-time parity vs oracle: {fl.get('parity')} / {fs.get('parity')} |")
