@@ -334,3 +334,43 @@ def frustum_scene(n, seed=0, width=1280, height=720, fx=700.0, bf=386.0):
     min_dist = max_dist / (1.2 ** 7)
     view = make_frustum_view(Xw, normal, min_dist, max_dist, R, tcw, (fx, fx, cx, cy, bf), (0.0, width, 0.0, height))
     return view, dict(depth=depth, u=u, v=v)
+
+
+def frustum_match_scene(kps, desc, width, height, seed, n_extra=500, th_noise=1.0):
+    """3-D local map behind SearchByProjection(F, vpMapPoints): one MapPoint per keypoint, placed so that it
+    projects within ~th_noise px of the keypoint and PredictScale gives the keypoint's octave, plus n_extra
+    random points (some outside the frustum).  Returns (orb_frame_view, orb_frustum_view, desc[n,32],
+    is_bad, has_obs): Frame::isInFrustum on the frustum view yields the orb_mappoint_view fields."""
+    from .views import make_frame_view, make_frustum_view
+    rng = np.random.default_rng(seed)
+    sf = scale_factors()
+    cx, cy = width / 2.0, height / 2.0
+    q = _quat_from_yaw_pitch(0.2, -0.05)
+    twc = np.array([0.5, 0.2, -1.0])
+    qi = q * np.array([-1, -1, -1, 1])
+    R = np.stack([_quat_rot(qi, e) for e in np.eye(3)], 1)               # Rcw
+    tcw = -R @ twc
+    n = len(kps)
+    u = np.concatenate([kps["x"] + rng.normal(0, th_noise, n), rng.uniform(-100, width + 100, n_extra)])
+    v = np.concatenate([kps["y"] + rng.normal(0, th_noise, n), rng.uniform(-60, height + 60, n_extra)])
+    m = n + n_extra
+    z = rng.uniform(3, 30, m)
+    Xc = np.stack([(u - cx) / FX * z, (v - cy) / FY * z, z], 1)
+    Xw = (Xc - tcw) @ R
+    octv = np.concatenate([kps["octave"], rng.integers(0, 8, n_extra)])
+    dist = np.linalg.norm(Xw - twc, axis=1)
+    max_dist = dist * 1.2 ** (octv - 0.5)                                # ceil(log(max/dist)/log 1.2) = octave
+    min_dist = max_dist / 1.2 ** 7
+    view_dir = (Xw - twc) / dist[:, None]
+    tilt = rng.normal(0, 0.02, (m, 3)) + (rng.random(m) < 0.3)[:, None] * rng.normal(0, 0.2, (m, 3))
+    normal = view_dir + tilt
+    normal /= np.linalg.norm(normal, axis=1)[:, None]
+    d = np.concatenate([flip_bits(desc, 6, rng), rng.integers(0, 256, (n_extra, 32), dtype=np.uint8)])
+    order = rng.permutation(m)
+    fv = make_frustum_view(Xw[order], normal[order], min_dist[order], max_dist[order], R, tcw,
+                           (FX, FY, cx, cy, 386.0), (0.0, width, 0.0, height))
+    taken = (rng.random(n) < 0.2).astype(np.uint8)
+    F = make_frame_view(kps, desc, width, height, sf, kp_taken=taken, fx=FX, fy=FY, bf=0.0)
+    is_bad = (rng.random(m) < 0.02).astype(np.uint8)
+    has_obs = (rng.random(m) > 0.1).astype(np.uint8)
+    return F, fv, np.ascontiguousarray(d[order]), is_bad, has_obs
