@@ -398,6 +398,49 @@ float frustum_last_ms(orb_frustum* h);
 int frustum_debug_host(const orb_frustum_view* v, float viewing_cos_limit, uint8_t* track_in_view, float* proj_x,
                        float* proj_y, float* proj_xr, int32_t* scale_level, float* view_cos, float* depth);
 
+/* ------------------------------------------------------------------------
+ * void Frame::ComputeBoW() / KeyFrame::ComputeBoW() (src/Frame.cc:738-745): DBoW2's
+ * TemplatedVocabulary<FORB::TDescriptor, FORB>::transform(features, BowVector&, FeatureVector&,
+ * levelsup = 4) (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1127-1195, :1218-1258; FORB::distance
+ * FORB.cpp:81-101; BowVector.cpp:34-84; FeatureVector.cpp:31-45), SURVEY.md 8(f-4).
+ * Covered: the ORB vocabulary's configuration -- TF_IDF (or TF) weighting with L1 scoring.
+ * The vocabulary is uploaded once and stays resident.  Outputs are the two std::maps flattened in
+ * key order; the FeatureVector comes out as the CSR that match_triangulate reads (orb_featvec_view).
+ * ---------------------------------------------------------------------- */
+typedef struct orb_vocab_view {
+  int32_t n_nodes;          /* m_nodes.size(); node 0 is the root */
+  int32_t L;                /* m_L, depth levels */
+  const int32_t* child_ptr; /* n_nodes + 1: CSR over m_nodes[i].children, in that vector's order */
+  const int32_t* child_ids; /* child node ids */
+  const uint8_t* desc;      /* n_nodes x 32: m_nodes[i].descriptor (the root's row is unused) */
+  const double* weight;     /* n_nodes: m_nodes[i].weight */
+  const int32_t* word_id;   /* n_nodes: m_nodes[i].word_id for leaves (nodes without children) */
+} orb_vocab_view;
+
+typedef struct orb_vocab orb_vocab;
+int vocab_create(int device, const orb_vocab_view* v, orb_vocab** out);
+void vocab_destroy(orb_vocab* h);
+/* desc: n x 32 host descriptors (Converter::toDescriptorVector(mDescriptors)).
+ * BowVector:     bow_ids[cap_words] ascending WordId, bow_vals[cap_words] (L1-normalised), *n_words.
+ * FeatureVector: fv_node_ids[cap_words] ascending NodeId, fv_ptr[cap_words + 1], fv_idx[n] feature indices
+ *                (ascending inside a node), *n_fv_nodes.  cap_words >= n is always enough.
+ * Returns the number of features that contributed (weight > 0), or ORB_E_*. */
+int bow_transform(orb_vocab* h, const uint8_t* desc, int n, int levelsup, int32_t* bow_ids, double* bow_vals,
+                  int32_t* n_words, int32_t* fv_node_ids, int32_t* fv_ptr, int32_t* fv_idx, int32_t* n_fv_nodes,
+                  int cap_words);
+/* Same, for frame `frame` of what an extractor handle left on the device after its last extract
+ * (no descriptor upload). */
+int bow_transform_extracted(orb_vocab* h, orb_extractor* ex, int frame, int levelsup, int32_t* bow_ids,
+                            double* bow_vals, int32_t* n_words, int32_t* fv_node_ids, int32_t* fv_ptr,
+                            int32_t* fv_idx, int32_t* n_fv_nodes, int cap_words);
+long long bow_kernel_launches(const orb_vocab* h);
+float bow_last_ms(orb_vocab* h);
+/* The kernels' source (csrc/bow_core.h) executed single-threaded on the host -- a debug hook for the
+ * CPU tests, not a product path. */
+int bow_debug_host(const orb_vocab_view* v, const uint8_t* desc, int n, int levelsup, int32_t* bow_ids,
+                   double* bow_vals, int32_t* n_words, int32_t* fv_node_ids, int32_t* fv_ptr, int32_t* fv_idx,
+                   int32_t* n_fv_nodes, int cap_words);
+
 /* Per-stage device timing (CUDA events on the launching stream).  Stages:
  * 0 h2d, 1 pyramid, 2 fast, 3 octree, 4 blur, 5 layout, 6 orient+describe,
  * 7 d2h.  orb_stage_times fills ms[8] (accumulated) and launches[8]. */

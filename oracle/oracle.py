@@ -72,6 +72,8 @@ def lib():
         L.orc_lba_reduced_system.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.POINTER(C.c_double)]
         L.orc_sort_nodes.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_bow_transform.restype = C.c_int
+        L.orc_bow_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 7 + [C.c_int]
         L.orc_is_in_frustum.restype = C.c_int
         L.orc_is_in_frustum.argtypes = [C.c_void_p, C.c_float] + [C.c_void_p] * 7
         L.orc_pose_optimize.restype = C.c_int
@@ -318,3 +320,19 @@ def is_in_frustum(view, viewing_cos_limit=0.5, out=None):
                                 *[_ptr(out[f]) for f in ("track_in_view", "proj_x", "proj_y", "proj_xr",
                                                          "scale_level", "view_cos", "depth")])
     return k, out
+
+
+def bow_transform(vocab_view, desc, levelsup=4):
+    """DBoW2 transform(features, BowVector, FeatureVector, levelsup) (TemplatedVocabulary.h:1127-1195).
+    Returns dict(used, bow_ids, bow_vals, fv_node_ids, fv_ptr, fv_idx)."""
+    desc = np.ascontiguousarray(desc, np.uint8)
+    n = len(desc)
+    cap = max(n, 1)
+    ids, vals = np.zeros(cap, np.int32), np.zeros(cap)
+    fn, fp, fi = np.zeros(cap, np.int32), np.zeros(cap + 1, np.int32), np.zeros(cap, np.int32)
+    nw, nn = C.c_int(0), C.c_int(0)
+    used = lib().orc_bow_transform(C.byref(vocab_view), _ptr(desc), n, int(levelsup), _ptr(ids), _ptr(vals),
+                                   C.byref(nw), _ptr(fn), _ptr(fp), _ptr(fi), C.byref(nn), cap)
+    assert used >= 0
+    return dict(used=used, bow_ids=ids[:nw.value].copy(), bow_vals=vals[:nw.value].copy(),
+                fv_node_ids=fn[:nn.value].copy(), fv_ptr=fp[:nn.value + 1].copy(), fv_idx=fi[:used].copy())

@@ -87,6 +87,13 @@ SIGNATURES = {
     "frustum_kernel_launches": (C.c_longlong, [_vp]),
     "frustum_last_ms": (C.c_float, [_vp]),
     "frustum_debug_host": (_i, [_vp, C.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vocab_create": (_i, [_i, _vp, _vp]),
+    "vocab_destroy": (None, [_vp]),
+    "bow_transform": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
+    "bow_transform_extracted": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
+    "bow_kernel_launches": (C.c_longlong, [_vp]),
+    "bow_last_ms": (C.c_float, [_vp]),
+    "bow_debug_host": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
     "orb_set_profiling": (_i, [_vp, _i]),
     "orb_stage_times": (_i, [_vp, _vp, _vp, _i]),
     "orb_stage_name": (C.c_char_p, [_i]),

@@ -374,3 +374,47 @@ def frustum_match_scene(kps, desc, width, height, seed, n_extra=500, th_noise=1.
     is_bad = (rng.random(m) < 0.02).astype(np.uint8)
     has_obs = (rng.random(m) > 0.1).astype(np.uint8)
     return F, fv, np.ascontiguousarray(d[order]), is_bad, has_obs
+
+
+def synth_vocabulary(k=10, L=4, seed=0, irregular=True, stop_frac=0.02):
+    """A DBoW2-shaped ORB vocabulary: a k-ary tree of depth L built top-down, node
+    descriptors = parent's with ~40 bits flipped (so a descriptor's descent is decided by real Hamming
+    distances, with ties), idf-like word weights, `stop_frac` of the words stopped (weight 0), and --
+    `irregular` -- a few nodes with fewer children and a few leaves above the last level, like k-means
+    trees that run out of points.  Returns an orb_vocab_view."""
+    from .views import make_vocab_view
+    rng = np.random.default_rng(seed)
+    desc = [rng.integers(0, 256, 32, dtype=np.uint8)]      # node 0: root (its descriptor is never read)
+    children = [[]]
+    level = [0]
+    frontier = [0]
+    for lv in range(1, L + 1):
+        nxt = []
+        for p in frontier:
+            if irregular and lv > 1 and rng.random() < 0.03:
+                continue                                   # an early leaf
+            kk = k if not irregular or rng.random() > 0.1 else int(rng.integers(2, k + 1))
+            for _ in range(kk):
+                bits = np.unpackbits(desc[p])
+                flip = rng.choice(256, 40, replace=False)
+                bits[flip] ^= 1
+                desc.append(np.packbits(bits))
+                children.append([])
+                level.append(lv)
+                children[p].append(len(desc) - 1)
+                nxt.append(len(desc) - 1)
+        frontier = nxt
+    n = len(desc)
+    child_ptr = np.zeros(n + 1, np.int32)
+    child_ids = []
+    for i in range(n):
+        child_ids.extend(children[i])
+        child_ptr[i + 1] = len(child_ids)
+    is_leaf = np.array([len(c) == 0 for c in children])
+    word_id = -np.ones(n, np.int32)
+    word_id[is_leaf] = np.arange(is_leaf.sum())            # m_words order = node order (create_words, :905-925)
+    weight = np.zeros(n)
+    weight[is_leaf] = np.log(rng.uniform(1.5, 400.0, is_leaf.sum()))
+    stopped = is_leaf & (rng.random(n) < stop_frac)
+    weight[stopped] = 0.0
+    return make_vocab_view(L, child_ptr, np.array(child_ids, np.int32), np.stack(desc), weight, word_id)

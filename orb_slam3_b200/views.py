@@ -208,3 +208,19 @@ def make_frustum_view(world_pos, normal, min_dist, max_dist, Rcw, tcw, cam, boun
     v.n_levels = int(n_levels)
     v._keep = a
     return v
+
+
+class orb_vocab_view(C.Structure):
+    _fields_ = [("n_nodes", _i), ("L", _i), ("child_ptr", _vp), ("child_ids", _vp), ("desc", _vp), ("weight", _vp),
+                ("word_id", _vp)]
+
+
+def make_vocab_view(L, child_ptr, child_ids, desc, weight, word_id):
+    a = dict(child_ptr=_arr(child_ptr, np.int32), child_ids=_arr(child_ids, np.int32), desc=_arr(desc, np.uint8),
+             weight=_arr(weight, np.float64), word_id=_arr(word_id, np.int32))
+    v = orb_vocab_view()
+    v.n_nodes, v.L = len(a["weight"]), int(L)
+    for k, arr in a.items():
+        setattr(v, k, _p(arr))
+    v._keep = a
+    return v
