@@ -573,6 +573,36 @@ def run_frustum_gpu(device, cpu=True):
     return out
 
 
+def run_bow_gpu(device, cpu=True):
+    """SURVEY.md 8(f-4): Frame::ComputeBoW = DBoW2 transform(levelsup 4) of one frame's 2000 descriptors
+    against a resident synthetic 10-ary depth-5 vocabulary (the ORB vocabulary is 10-ary, depth 6)."""
+    from orb_slam3_b200 import scenes
+    from orb_slam3_b200.bow import ORBVocabulary
+    from orb_slam3_b200.extractor import ORBextractor
+    from orb_slam3_b200.synth import synth_frame
+    voc = scenes.synth_vocabulary(10, 5, seed=3)
+    gv = ORBVocabulary(voc, device)
+    ext = ORBextractor(NFEAT, 1.2, NLEVELS, 20, 7, device=device)
+    _, kps, desc = ext(synth_frame(H, W, 4242))
+    got = gv.transform_extracted(ext, 0, 4)
+    reps, ms_dev, t0 = 20, 0.0, time.perf_counter()
+    for _ in range(reps):
+        got = gv.transform_extracted(ext, 0, 4)
+        ms_dev += gv.last_ms()
+    ms_wall = (time.perf_counter() - t0) * 1e3 / reps
+    out = {"config": "%d descriptors, vocabulary %d nodes (k=10, L=5), levelsup 4" % (len(desc), voc.n_nodes),
+           "kernels_us": 1e3 * ms_dev / reps, "call_us_descriptors_on_device": 1e3 * ms_wall, "gpu_launches_per_call": 2,
+           "words": int(len(got["bow_ids"])), "fv_nodes": int(len(got["fv_node_ids"]))}
+    if cpu:
+        from oracle import oracle as O
+        t0 = time.perf_counter()
+        for _ in range(3):
+            ref = O.bow_transform(voc, desc, 4)
+        out["cpu_port_us"] = (time.perf_counter() - t0) / 3 * 1e6
+        out["parity"] = bool(all(np.array_equal(got[k], ref[k]) for k in ("bow_ids", "bow_vals", "fv_node_ids", "fv_ptr", "fv_idx")))
+    return out
+
+
 def _guarded(fn, *a, **k):
     """The extra legs must never cost the headline line."""
     try:
@@ -592,7 +622,7 @@ def main():
     ap.add_argument("--e2e-workers", type=int, default=4, help="host threads feeding the GPU in the e2e leg")
     ap.add_argument("--no-lba", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-stereo", action="store_true", help="skip the 8(f) legs (ComputeStereoMatches, PoseOptimization, isInFrustum)")
+    ap.add_argument("--no-stereo", action="store_true", help="skip the 8(f) legs (ComputeStereoMatches, PoseOptimization, isInFrustum, ComputeBoW)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -717,6 +747,9 @@ def main():
     frustum = None
     if rank == 0 and not args.no_stereo:
         frustum = _guarded(run_frustum_gpu, local_rank, cpu=(world == 1 and not args.no_cpu))
+    bow = None
+    if rank == 0 and not args.no_stereo:
+        bow = _guarded(run_bow_gpu, local_rank, cpu=(world == 1 and not args.no_cpu))
     if world > 1:
         dist.barrier()
 
@@ -804,6 +837,7 @@ def main():
             "stereo": stereo,
             "pose_optimization": pose,
             "is_in_frustum": frustum,
+            "compute_bow": bow,
         }
         print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:

@@ -59,6 +59,9 @@ if not d.get("is_in_frustum") and os.path.exists(os.path.join(P, "bench_r1_f3_le
 if d.get("is_in_frustum") and "error" not in d["is_in_frustum"]:
     fl, fs = d["is_in_frustum"]["local_map_5000"], d["is_in_frustum"]["stream_1M"]
     o.append(f"| SURVEY 8(f-3) `Frame::isInFrustum` over a local map | 5000 points: kernel {fl['kernel_us']:.0f} us, host-buffer call {fl['host_call_us']:.0f} us (CPU port {fl.get('cpu_port_us', float('nan')):.0f} us); 2^20 points: kernel {fs['kernel_us']:.0f} us = **{fs['kernel_GBps_algorithmic']:.0f} GB/s** algorithmic (57 B/point), CPU port {fs.get('cpu_port_us', float('nan'))/1e3:.1f} ms; bench-time parity vs oracle: {fl.get('parity')} / {fs.get('parity')} |")
+if d.get("compute_bow") and "error" not in d["compute_bow"]:
+    bw = d["compute_bow"]
+    o.append(f"| SURVEY 8(f-4) `Frame::ComputeBoW` (DBoW2 transform), {bw['config']} | kernels {bw['kernels_us']:.0f} us, call with descriptors already on the device {bw['call_us_descriptors_on_device']:.0f} us, CPU port {bw.get('cpu_port_us', float('nan')):.0f} us; bench-time parity vs oracle: {bw.get('parity')} |")
 o.append(f"\n## Where a step goes (CUDA events per stage, ms per {B}-frame step)\n")
 o.append("| stage | ms/step | us/frame | algorithmic GB/s | frac of HBM peak (6556 GB/s measured) |\n|---|---|---|---|---|")
 for k in ["pyramid", "fast", "octree", "blur", "describe", "layout", "match_last(th15)", "match_local(th3)"]:
