@@ -109,16 +109,21 @@ struct Vocab {
       if (v->child_ptr[i + 1] < v->child_ptr[i]) { set_last_error("vocabulary view: child_ptr not monotone"); return ORB_E_ARG; }
     for (int c = 0; c < n_children; c++)
       if (v->child_ids[c] <= 0 || v->child_ids[c] >= v->n_nodes) { set_last_error("vocabulary view: child id out of range"); return ORB_E_ARG; }
+    // every allocation is handed to V at once, so that ~Vocab() frees it if a later step fails
     int *cp = nullptr, *ci = nullptr, *wi = nullptr;
     uint8_t* ds = nullptr;
     double* wt = nullptr;
-    CUDA_TRYB(cudaMalloc(&cp, sizeof(int) * (nn + 1)));
-    CUDA_TRYB(cudaMalloc(&ci, sizeof(int) * std::max(n_children, 1)));
-    CUDA_TRYB(cudaMalloc(&ds, 32 * nn));
-    CUDA_TRYB(cudaMalloc(&wt, sizeof(double) * nn));
-    CUDA_TRYB(cudaMalloc(&wi, sizeof(int) * nn));
     V.n_nodes = v->n_nodes; V.L = v->L;
-    V.child_ptr = cp; V.child_ids = ci; V.desc = ds; V.weight = wt; V.word_id = wi;
+    CUDA_TRYB(cudaMalloc(&cp, sizeof(int) * (nn + 1)));
+    V.child_ptr = cp;
+    CUDA_TRYB(cudaMalloc(&ci, sizeof(int) * std::max(n_children, 1)));
+    V.child_ids = ci;
+    CUDA_TRYB(cudaMalloc(&ds, 32 * nn));
+    V.desc = ds;
+    CUDA_TRYB(cudaMalloc(&wt, sizeof(double) * nn));
+    V.weight = wt;
+    CUDA_TRYB(cudaMalloc(&wi, sizeof(int) * nn));
+    V.word_id = wi;
     CUDA_TRYB(cudaMemcpy(cp, v->child_ptr, sizeof(int) * (nn + 1), cudaMemcpyHostToDevice));
     CUDA_TRYB(cudaMemcpy(ci, v->child_ids, sizeof(int) * n_children, cudaMemcpyHostToDevice));
     CUDA_TRYB(cudaMemcpy(ds, v->desc, 32 * nn, cudaMemcpyHostToDevice));

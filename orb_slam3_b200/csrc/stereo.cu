@@ -267,7 +267,12 @@ struct Stereo {
   long long launches = 0;
 
   explicit Stereo(int dev) : device(dev) {}
-  ~Stereo() { release(); }
+  ~Stereo() {
+    release();
+    if (ev) cudaEventDestroy(ev);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+  }
   void release() {
     cudaFree(d_row_off); cudaFree(d_row_items); cudaFree(d_sad); cudaFree(d_kept); cudaFree(d_u); cudaFree(d_depth);
     if (h_kept) cudaFreeHost(h_kept);
