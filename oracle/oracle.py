@@ -72,6 +72,10 @@ def lib():
         L.orc_lba_reduced_system.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.POINTER(C.c_double)]
         L.orc_sort_nodes.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_lia_solve.restype = C.c_int
+        L.orc_lia_solve.argtypes = [C.c_void_p] * 6
+        L.orc_lia_linearize.restype = C.c_int
+        L.orc_lia_linearize.argtypes = [C.c_void_p] * 5
         L.orc_bow_transform.restype = C.c_int
         L.orc_bow_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 7 + [C.c_int]
         L.orc_is_in_frustum.restype = C.c_int
@@ -336,3 +340,70 @@ def bow_transform(vocab_view, desc, levelsup=4):
     assert used >= 0
     return dict(used=used, bow_ids=ids[:nw.value].copy(), bow_vals=vals[:nw.value].copy(),
                 fv_node_ids=fn[:nn.value].copy(), fv_ptr=fp[:nn.value + 1].copy(), fv_idx=fi[:used].copy())
+
+
+# ---- Optimizer::LocalInertialBA (oracle only so far; the view mirrors oracle/orc_lia.h)
+class lia_graph_view(C.Structure):
+    _vp, _i = C.c_void_p, C.c_int32
+    _fields_ = [("n_kf", _i), ("kf_Rwb", _vp), ("kf_twb", _vp), ("kf_Rcw", _vp), ("kf_tcw", _vp), ("kf_fixed", _vp),
+                ("kf_has_imu", _vp), ("kf_vel", _vp), ("kf_bg", _vp), ("kf_ba", _vp),
+                ("Rcb", C.c_double * 9), ("tcb", C.c_double * 3), ("tbc", C.c_double * 3),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("bf", C.c_float),
+                ("n_mp", _i), ("mp_pos", _vp),
+                ("n_edges", _i), ("e_kf", _vp), ("e_mp", _vp), ("e_stereo", _vp), ("e_obs", _vp), ("e_inv_sigma2", _vp),
+                ("n_inertial", _i), ("i_kf1", _vp), ("i_kf2", _vp), ("i_dR", _vp), ("i_dV", _vp), ("i_dP", _vp),
+                ("i_JRg", _vp), ("i_JVg", _vp), ("i_JVa", _vp), ("i_JPg", _vp), ("i_JPa", _vp), ("i_bias", _vp),
+                ("i_dT", _vp), ("i_C", _vp), ("i_last", _vp),
+                ("lambda_init", C.c_double), ("iterations", _i)]
+
+
+_LIA_TYPES = dict(kf_Rwb=np.float64, kf_twb=np.float64, kf_Rcw=np.float64, kf_tcw=np.float64, kf_fixed=np.uint8,
+                  kf_has_imu=np.uint8, kf_vel=np.float64, kf_bg=np.float64, kf_ba=np.float64, mp_pos=np.float64,
+                  e_kf=np.int32, e_mp=np.int32, e_stereo=np.uint8, e_obs=np.float64, e_inv_sigma2=np.float32,
+                  i_kf1=np.int32, i_kf2=np.int32, i_dR=np.float32, i_dV=np.float32, i_dP=np.float32, i_JRg=np.float32,
+                  i_JVg=np.float32, i_JVa=np.float32, i_JPg=np.float32, i_JPa=np.float32, i_bias=np.float32,
+                  i_dT=np.float32, i_C=np.float32, i_last=np.uint8)
+
+
+def make_lia_view(d):
+    """d: dict with the arrays of lia_graph_view plus Rcb[3,3], tcb[3], tbc[3], cam=(fx,fy,cx,cy,bf),
+    lambda_init, iterations."""
+    v = lia_graph_view()
+    keep = {}
+    for k, t in _LIA_TYPES.items():
+        keep[k] = np.ascontiguousarray(d[k], t)
+        setattr(v, k, keep[k].ctypes.data)
+    v.n_kf, v.n_mp, v.n_edges, v.n_inertial = len(keep["kf_fixed"]), len(keep["mp_pos"]), len(keep["e_kf"]), len(keep["i_kf1"])
+    for i, x in enumerate(np.asarray(d["Rcb"], np.float64).reshape(9)):
+        v.Rcb[i] = x
+    for i in range(3):
+        v.tcb[i] = float(d["tcb"][i])
+        v.tbc[i] = float(d["tbc"][i])
+    v.fx, v.fy, v.cx, v.cy, v.bf = (float(c) for c in d["cam"])
+    v.lambda_init, v.iterations = float(d.get("lambda_init", 1.0)), int(d.get("iterations", 10))
+    v._keep = keep
+    return v
+
+
+def lia_solve(v):
+    kf = np.zeros((v.n_kf, 21))
+    mp = np.zeros((v.n_mp, 3))
+    chi2 = np.zeros(max(v.n_edges, 1))
+    dp = np.zeros(max(v.n_edges, 1), np.uint8)
+    st = np.zeros(6)
+    it = lib().orc_lia_solve(C.byref(v), _ptr(kf), _ptr(mp), _ptr(chi2), _ptr(dp), _ptr(st))
+    return dict(iterations=it, Rcw=kf[:, :9].reshape(-1, 3, 3), tcw=kf[:, 9:12], vel=kf[:, 12:15], bg=kf[:, 15:18],
+                ba=kf[:, 18:21], mp_pos=mp, chi2=chi2[:v.n_edges], depth_pos=dp[:v.n_edges],
+                stats=dict(iterations=int(st[0]), trials=int(st[1]), err=st[2], err_end=st[3], lambda_final=st[4],
+                           dim=int(st[5])))
+
+
+def lia_linearize(v, delta=None):
+    """(robust chi2, b) at the input state, and robust chi2 after oplus(delta)."""
+    chi, chid = C.c_double(), C.c_double()
+    np_ = lib().orc_lia_linearize(C.byref(v), None, C.byref(chi), None, None)
+    b = np.zeros(np_ + 3 * v.n_mp)
+    d = None if delta is None else np.ascontiguousarray(delta, np.float64)
+    lib().orc_lia_linearize(C.byref(v), _ptr(d) if d is not None else None, C.byref(chi), _ptr(b),
+                            C.byref(chid) if d is not None else None)
+    return chi.value, b, (chid.value if d is not None else None), np_

@@ -418,3 +418,172 @@ def synth_vocabulary(k=10, L=4, seed=0, irregular=True, stop_frac=0.02):
     stopped = is_leaf & (rng.random(n) < stop_frac)
     weight[stopped] = 0.0
     return make_vocab_view(L, child_ptr, np.array(child_ids, np.int32), np.stack(desc), weight, word_id)
+
+
+# ------------------------------------------------------------------ visual-inertial local window
+def _so3_exp(w):
+    th = np.linalg.norm(w)
+    W = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    if th < 1e-8:
+        return np.eye(3) + W
+    return np.eye(3) + W * np.sin(th) / th + W @ W * (1 - np.cos(th)) / th ** 2
+
+
+def _so3_right_jac(w):
+    th = np.linalg.norm(w)
+    W = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    if th < 1e-8:
+        return np.eye(3)
+    return np.eye(3) - W * (1 - np.cos(th)) / th ** 2 + W @ W * (th - np.sin(th)) / th ** 3
+
+
+def imu_preintegrate(acc, gyr, dt, ba, bg, Nga, NgaWalk):
+    """IMU::Preintegrated::IntegrateNewMeasurement over a run of samples (reference src/ImuTypes.cc:176-237):
+    returns dict(dR, dV, dP, JRg, JVg, JVa, JPg, JPa, C[15,15], dT).  float64 here; the caller casts."""
+    dR, dV, dP = np.eye(3), np.zeros(3), np.zeros(3)
+    JRg, JVg, JVa, JPg, JPa = (np.zeros((3, 3)) for _ in range(5))
+    C = np.zeros((15, 15))
+    dT = 0.0
+    for a_m, w_m in zip(acc, gyr):
+        a, w = a_m - ba, w_m - bg
+        Wacc = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+        A, B = np.eye(9), np.zeros((9, 6))
+        dP = dP + dV * dt + 0.5 * dR @ a * dt * dt
+        dV = dV + dR @ a * dt
+        A[3:6, 0:3] = -dR * dt @ Wacc
+        A[6:9, 0:3] = -0.5 * dR * dt * dt @ Wacc
+        A[6:9, 3:6] = np.eye(3) * dt
+        B[3:6, 3:6] = dR * dt
+        B[6:9, 3:6] = 0.5 * dR * dt * dt
+        JPa = JPa + JVa * dt - 0.5 * dR * dt * dt
+        JPg = JPg + JVg * dt - 0.5 * dR * dt * dt @ Wacc @ JRg
+        JVa = JVa - dR * dt
+        JVg = JVg - dR * dt @ Wacc @ JRg
+        dRi, rJ = _so3_exp(w * dt), _so3_right_jac(w * dt)
+        U, _, Vt = np.linalg.svd(dR @ dRi)
+        dR = U @ Vt
+        A[0:3, 0:3] = dRi.T
+        B[0:3, 0:3] = rJ * dt
+        C[0:9, 0:9] = A @ C[0:9, 0:9] @ A.T + B @ Nga @ B.T
+        C[9:15, 9:15] += NgaWalk
+        JRg = dRi.T @ JRg - rJ * dt
+        dT += dt
+    return dict(dR=dR, dV=dV, dP=dP, JRg=JRg, JVg=JVg, JVa=JVa, JPg=JPg, JPa=JPa, C=C, dT=dT)
+
+
+def lia_scene(n_opt=6, n_mp=300, seed=0, n_fixed_visual=2, imu_rate=200, kf_dt=0.5, width=1280, height=720,
+              fx=700.0, bf=386.0, perturb=1.0, outlier_frac=0.02):
+    """A visual-inertial local window for Optimizer::LocalInertialBA: n_opt optimisable keyframes (newest
+    first) with velocity and biases, the fixed keyframe before the window, n_fixed_visual extra fixed
+    keyframes without IMU vertices, map points seen from several of them, and the IMU preintegrated between
+    consecutive keyframes with the reference's own scheme.  The true trajectory is the discrete integral of
+    the simulated IMU samples, so the preintegration constraints hold exactly at the truth.
+    Returns (dict for oracle.make_lia_view, truth dict)."""
+    rng = np.random.default_rng(seed)
+    g = np.array([0.0, 0.0, -9.81])
+    dt = 1.0 / imu_rate
+    m = int(round(kf_dt * imu_rate))
+    nk = n_opt + 1                                   # chronological keyframes 0 (fixed) .. n_opt
+    R = np.array([[0.0, 0.0, 1.0], [-1.0, 0.0, 0.0], [0.0, -1.0, 0.0]])  # body = camera axes: z forward (world +x), y down
+    p, v = np.zeros(3), np.array([1.2, 0.0, 0.0])
+    ba_true, bg_true = rng.normal(0, 0.02, 3), rng.normal(0, 0.002, 3)
+    sf = np.sqrt(imu_rate)
+    ng, na, ngw, naw = 1.7e-4 * sf, 2.0e-3 * sf, 1.9e-5 / sf, 3.0e-3 / sf
+    Nga = np.diag([ng ** 2] * 3 + [na ** 2] * 3)
+    NgaWalk = np.diag([ngw ** 2] * 3 + [naw ** 2] * 3)
+    states, acc_all, gyr_all = [(R.copy(), p.copy(), v.copy())], [], []
+    for s in range((nk - 1) * m):
+        t = s * dt
+        a_w = np.array([0.3 * np.sin(0.9 * t), 0.5 * np.cos(0.7 * t), 0.2 * np.sin(1.3 * t)])
+        w_b = np.array([0.05 * np.sin(1.1 * t), 0.08 * np.cos(0.8 * t), 0.04 * np.sin(0.5 * t)])
+        a_b = R.T @ (a_w - g)
+        acc_all.append(a_b + ba_true)
+        gyr_all.append(w_b + bg_true)
+        p = p + v * dt + 0.5 * (R @ a_b + g) * dt * dt
+        v = v + (R @ a_b + g) * dt
+        U, _, Vt = np.linalg.svd(R @ _so3_exp(w_b * dt))
+        R = U @ Vt
+        if (s + 1) % m == 0:
+            states.append((R.copy(), p.copy(), v.copy()))
+    acc_all, gyr_all = np.array(acc_all), np.array(gyr_all)
+    # camera rig
+    Rcb = _so3_exp(np.array([0.01, -0.02, 0.015]))
+    tcb = np.array([0.05, 0.02, -0.01])
+    tbc = -Rcb.T @ tcb
+    cx, cy = width / 2.0, height / 2.0
+
+    def cam_of(Rwb, twb):
+        Rcw = Rcb @ Rwb.T
+        return Rcw, Rcb @ (-Rwb.T @ twb) + tcb
+
+    # extra fixed visual keyframes: older poses next to the start
+    extra = []
+    for j in range(n_fixed_visual):
+        Re = states[0][0] @ _so3_exp(rng.normal(0, 0.03, 3))
+        extra.append((Re, states[0][1] + np.array([-0.6 * (j + 1), 0.2 * (-1) ** j, 0.05]), np.zeros(3)))
+    # view order: newest optimisable first ... oldest optimisable, the fixed one before the window, extras
+    order = list(range(nk - 1, 0, -1)) + [0]
+    all_states = [states[c] for c in order] + extra
+    K = len(all_states)
+    fixed = np.array([0] * n_opt + [1] * (1 + n_fixed_visual), np.uint8)
+    has_imu = np.array([1] * (n_opt + 1) + [0] * n_fixed_visual, np.uint8)
+    Rwb_t = np.stack([s[0] for s in all_states]); twb_t = np.stack([s[1] for s in all_states])
+    vel_t = np.stack([s[2] for s in all_states])
+    # map points ahead of the trajectory, observed where they project inside the image
+    pts = np.stack([rng.uniform(3, 30, n_mp), rng.uniform(-7, 7, n_mp), rng.uniform(-3, 3, n_mp)], 1) + states[0][1]
+    e_kf, e_mp, e_obs, e_st, e_is2 = [], [], [], [], []
+    inv_sigma2 = (1.0 / (scale_factors() ** 2)).astype(np.float32)
+    for l in range(n_mp):
+        for k in range(K):
+            Rcw, tcw = cam_of(Rwb_t[k], twb_t[k])
+            Xc = Rcw @ pts[l] + tcw
+            if Xc[2] < 0.5:
+                continue
+            u, w_ = fx * Xc[0] / Xc[2] + cx, fx * Xc[1] / Xc[2] + cy
+            if not (20 < u < width - 20 and 20 < w_ < height - 20) or rng.random() < 0.25:
+                continue
+            o = int(rng.integers(0, 8))
+            sig = 1.2 ** o
+            st = rng.random() < 0.7
+            n3 = rng.normal(0, 1, 3) * sig
+            if rng.random() < outlier_frac:
+                n3[0] += 40.0
+            e_kf.append(k); e_mp.append(l); e_st.append(st); e_is2.append(inv_sigma2[o])
+            e_obs.append([np.float32(u + n3[0]), np.float32(w_ + n3[1]), np.float32(u - bf / Xc[2] + n3[2]) if st else -1.0])
+    # preintegration between consecutive keyframes (edge i: kf2 = view i, kf1 = view i + 1)
+    lin_off = 1e-3
+    pre = []
+    for i in range(n_opt):
+        c2 = order[i]
+        seg = slice((c2 - 1) * m, c2 * m)
+        pre.append(imu_preintegrate(acc_all[seg], gyr_all[seg], dt, ba_true + lin_off, bg_true - lin_off, Nga, NgaWalk))
+    # initial estimates: truth + perturbation on the free vertices
+    Rwb0, twb0, vel0 = Rwb_t.copy(), twb_t.copy(), vel_t.copy()
+    bg0 = np.tile(bg_true, (K, 1)); ba0 = np.tile(ba_true, (K, 1))
+    for k in range(n_opt):
+        Rwb0[k] = Rwb_t[k] @ _so3_exp(rng.normal(0, np.deg2rad(0.3) * perturb, 3))
+        twb0[k] = twb_t[k] + rng.normal(0, 0.01 * perturb, 3)
+        vel0[k] = vel_t[k] + rng.normal(0, 0.02 * perturb, 3)
+        bg0[k] = bg_true + rng.normal(0, 2e-4 * perturb, 3)
+        ba0[k] = ba_true + rng.normal(0, 5e-3 * perturb, 3)
+    # Sophus::SE3f / Vector3f storage of the reference: float, cast to double by the optimiser
+    f32 = lambda a: np.asarray(a, np.float32).astype(np.float64)
+    Rwb0, twb0, vel0, bg0, ba0 = f32(Rwb0), f32(twb0), f32(vel0), f32(bg0), f32(ba0)
+    Rcw0 = np.stack([cam_of(Rwb0[k], twb0[k])[0] for k in range(K)])
+    tcw0 = np.stack([cam_of(Rwb0[k], twb0[k])[1] for k in range(K)])
+    pts0 = f32(pts + rng.normal(0, 0.03 * perturb, pts.shape))
+    d = dict(kf_Rwb=Rwb0.reshape(K, 9), kf_twb=twb0, kf_Rcw=f32(Rcw0).reshape(K, 9), kf_tcw=f32(tcw0), kf_fixed=fixed,
+             kf_has_imu=has_imu, kf_vel=vel0, kf_bg=bg0, kf_ba=ba0, Rcb=Rcb, tcb=tcb, tbc=tbc,
+             cam=(fx, fx, cx, cy, bf), mp_pos=pts0, e_kf=e_kf, e_mp=e_mp, e_stereo=e_st,
+             e_obs=np.array(e_obs, np.float64).reshape(-1, 3), e_inv_sigma2=e_is2,
+             i_kf1=np.arange(1, n_opt + 1), i_kf2=np.arange(0, n_opt),
+             i_dR=np.stack([q["dR"] for q in pre]).reshape(n_opt, 9), i_dV=np.stack([q["dV"] for q in pre]),
+             i_dP=np.stack([q["dP"] for q in pre]),
+             i_JRg=np.stack([q["JRg"] for q in pre]).reshape(n_opt, 9), i_JVg=np.stack([q["JVg"] for q in pre]).reshape(n_opt, 9),
+             i_JVa=np.stack([q["JVa"] for q in pre]).reshape(n_opt, 9), i_JPg=np.stack([q["JPg"] for q in pre]).reshape(n_opt, 9),
+             i_JPa=np.stack([q["JPa"] for q in pre]).reshape(n_opt, 9),
+             i_bias=np.tile(np.concatenate([ba_true + lin_off, bg_true - lin_off]), (n_opt, 1)),
+             i_dT=np.array([q["dT"] for q in pre]), i_C=np.stack([q["C"] for q in pre]).reshape(n_opt, 225),
+             i_last=np.array([0] * (n_opt - 1) + [1], np.uint8), lambda_init=1.0, iterations=10)
+    truth = dict(Rwb=Rwb_t, twb=twb_t, vel=vel_t, bg=bg_true, ba=ba_true, mp_pos=pts, cam_of=cam_of)
+    return d, truth
