@@ -442,6 +442,74 @@ int bow_debug_host(const orb_vocab_view* v, const uint8_t* desc, int n, int leve
                    double* bow_vals, int32_t* n_words, int32_t* fv_node_ids, int32_t* fv_ptr, int32_t* fv_idx,
                    int32_t* n_fv_nodes, int cap_words);
 
+/* ------------------------------------------------------------------------
+ * void Optimizer::LocalInertialBA(KeyFrame*, bool* pbStopFlag, Map*, ..., bool bLarge, bool bRecInit)
+ * (src/Optimizer.cc:2383-2958), SURVEY.md 8(f-4b): the optimizer.optimize(opt_it) in the middle --
+ * g2o Levenberg-Marquardt (user lambda) over VertexPose (ImuCamPose) / VertexVelocity / VertexGyroBias /
+ * VertexAccBias and marginalised map points with EdgeMono / EdgeStereo / EdgeInertial / EdgeGyroRW /
+ * EdgeAccRW (src/G2oTypes.cc).  Graph set-up, outlier erasure and write-back stay in the shim, like for
+ * LocalBundleAdjustment.  One camera per keyframe (no mpCamera2).  fp64.
+ * STATUS: the per-window source (csrc/lia_core.h) is held against the oracle on the host
+ * (lia_debug_host); the single-launch device path has not been run on hardware yet.
+ * ---------------------------------------------------------------------- */
+typedef struct lia_graph_view {
+  /* keyframes: vpOptimizableKFs (newest first), then lFixedKeyFrames */
+  int32_t n_kf;
+  const double* kf_Rwb;      /* n_kf x 9 row-major: GetImuRotation().cast<double>() */
+  const double* kf_twb;      /* n_kf x 3: GetImuPosition() */
+  const double* kf_Rcw;      /* n_kf x 9: GetRotation() (left camera) */
+  const double* kf_tcw;      /* n_kf x 3: GetTranslation() */
+  const uint8_t* kf_fixed;   /* VertexPose (and the IMU vertices) fixed */
+  const uint8_t* kf_has_imu; /* KeyFrame::bImu: velocity / gyro-bias / acc-bias vertices exist */
+  const double* kf_vel;      /* n_kf x 3: GetVelocity() */
+  const double* kf_bg;       /* n_kf x 3: GetGyroBias() */
+  const double* kf_ba;       /* n_kf x 3: GetAccBias() */
+  double Rcb[9], tcb[3], tbc[3]; /* mImuCalib.mTcb / mTbc (one rig) */
+  float fx, fy, cx, cy, bf;
+  /* map points and visual edges (EdgeMono / EdgeStereo, left camera) */
+  int32_t n_mp;
+  const double* mp_pos;      /* n_mp x 3 */
+  int32_t n_edges;
+  const int32_t* e_kf;
+  const int32_t* e_mp;
+  const uint8_t* e_stereo;
+  const double* e_obs;       /* n_edges x 3: u, v, uRight */
+  const float* e_inv_sigma2; /* mvInvLevelSigma2[octave] / uncertainty2 */
+  /* inertial edges: EdgeInertial + EdgeGyroRW + EdgeAccRW between kf1 (previous) and kf2 */
+  int32_t n_inertial;
+  const int32_t* i_kf1;
+  const int32_t* i_kf2;
+  const float* i_dR;         /* x 9: IMU::Preintegrated::dR, then dV, dP (x 3 each) */
+  const float* i_dV;
+  const float* i_dP;
+  const float* i_JRg;        /* x 9 each: bias Jacobians of the preintegration */
+  const float* i_JVg;
+  const float* i_JVa;
+  const float* i_JPg;
+  const float* i_JPa;
+  const float* i_bias;       /* x 6: linearisation bias b = (bax, bay, baz, bwx, bwy, bwz) */
+  const float* i_dT;         /* integrated time */
+  const float* i_C;          /* x 225: 15x15 covariance, row-major */
+  const uint8_t* i_last;     /* i == N-1: Huber(sqrt(16.92)) and information * 1e-2 (:2585-2596) */
+  double lambda_init;        /* setUserLambdaInit: 1e0, or 1e-2 when bLarge */
+  int32_t iterations;        /* opt_it: 10, or 4 when bLarge */
+} lia_graph_view;
+
+typedef struct orb_lia orb_lia;
+int lia_create(int device, orb_lia** out);
+void lia_destroy(orb_lia* h);
+/* kf_out: n_kf x 21 doubles (Rcw 9 row-major, tcw 3, velocity 3, gyro bias 3, acc bias 3); mp_out: n_mp x 3;
+ * chi2_out / depth_pos_out: per visual edge (e->chi2(), isDepthPositive()); stats[8]: iterations, trials,
+ * activeRobustChi2 before (err) and after (err_end), final lambda, pose-side dimension, 2 reserved.
+ * Returns the number of LM iterations or ORB_E_*. */
+int lia_solve(orb_lia* h, const lia_graph_view* g, double* kf_out, double* mp_out, double* chi2_out,
+              uint8_t* depth_pos_out, double* stats);
+long long lia_kernel_launches(const orb_lia* h);
+float lia_last_ms(orb_lia* h);
+/* csrc/lia_core.h executed single-threaded on the host -- a debug hook for the CPU tests, not a product path. */
+int lia_debug_host(const lia_graph_view* g, double* kf_out, double* mp_out, double* chi2_out,
+                   uint8_t* depth_pos_out, double* stats);
+
 /* Per-stage device timing (CUDA events on the launching stream).  Stages:
  * 0 h2d, 1 pyramid, 2 fast, 3 octree, 4 blur, 5 layout, 6 orient+describe,
  * 7 d2h.  orb_stage_times fills ms[8] (accumulated) and launches[8]. */

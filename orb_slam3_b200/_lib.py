@@ -94,6 +94,12 @@ SIGNATURES = {
     "bow_kernel_launches": (C.c_longlong, [_vp]),
     "bow_last_ms": (C.c_float, [_vp]),
     "bow_debug_host": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
+    "lia_create": (_i, [_i, _vp]),
+    "lia_destroy": (None, [_vp]),
+    "lia_solve": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lia_kernel_launches": (C.c_longlong, [_vp]),
+    "lia_last_ms": (C.c_float, [_vp]),
+    "lia_debug_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "orb_set_profiling": (_i, [_vp, _i]),
     "orb_stage_times": (_i, [_vp, _vp, _vp, _i]),
     "orb_stage_name": (C.c_char_p, [_i]),

@@ -110,3 +110,55 @@ class PoseOptimization:
 
     def kernel_launches(self):
         return int(self._lib.poseopt_kernel_launches(self._h))
+
+
+def _lia_outputs(view):
+    kf = np.zeros((view.n_kf, 21))
+    mp = np.zeros((max(view.n_mp, 1), 3))
+    chi2 = np.zeros(max(view.n_edges, 1))
+    dp = np.zeros(max(view.n_edges, 1), np.uint8)
+    st = np.zeros(8)
+    return kf, mp, chi2, dp, st
+
+
+def _lia_pack(view, it, kf, mp, chi2, dp, st):
+    return dict(iterations=it, Rcw=kf[:, :9].reshape(-1, 3, 3), tcw=kf[:, 9:12], vel=kf[:, 12:15], bg=kf[:, 15:18],
+                ba=kf[:, 18:21], mp_pos=mp[:view.n_mp], chi2=chi2[:view.n_edges], depth_pos=dp[:view.n_edges],
+                stats=dict(iterations=int(st[0]), trials=int(st[1]), err=st[2], err_end=st[3], lambda_final=st[4],
+                           dim=int(st[5])))
+
+
+class LocalInertialBA:
+    """Optimizer::LocalInertialBA's optimizer.optimize(opt_it) (src/Optimizer.cc:2383-2958) over the C ABI: the whole
+    LM loop in one kernel launch.  No CPU fallback (`lia_debug_host` runs the kernel's source on the host for the
+    CPU tests).  The device path has not been run on hardware yet."""
+
+    def __init__(self, device=0):
+        self._lib = _lib.lib()
+        h = C.c_void_p()
+        check(self._lib.lia_create(int(device), C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._lib.lia_destroy(h)
+            self._h = None
+
+    def __call__(self, view):
+        kf, mp, chi2, dp, st = _lia_outputs(view)
+        it = check(self._lib.lia_solve(self._h, C.byref(view), ptr(kf), ptr(mp), ptr(chi2), ptr(dp), ptr(st)))
+        return _lia_pack(view, it, kf, mp, chi2, dp, st)
+
+    def last_ms(self):
+        return float(self._lib.lia_last_ms(self._h))
+
+    def kernel_launches(self):
+        return int(self._lib.lia_kernel_launches(self._h))
+
+
+def lia_debug_host(view):
+    """csrc/lia_core.h on the host (CPU tests): same source as the kernel."""
+    kf, mp, chi2, dp, st = _lia_outputs(view)
+    it = check(_lib.lib().lia_debug_host(C.byref(view), ptr(kf), ptr(mp), ptr(chi2), ptr(dp), ptr(st)))
+    return _lia_pack(view, it, kf, mp, chi2, dp, st)

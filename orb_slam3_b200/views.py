@@ -224,3 +224,45 @@ def make_vocab_view(L, child_ptr, child_ids, desc, weight, word_id):
         setattr(v, k, _p(arr))
     v._keep = a
     return v
+
+
+# ---- Optimizer::LocalInertialBA graph (include/orb_b200.h: lia_graph_view)
+class lia_graph_view(C.Structure):
+    _fields_ = [("n_kf", _i), ("kf_Rwb", _vp), ("kf_twb", _vp), ("kf_Rcw", _vp), ("kf_tcw", _vp), ("kf_fixed", _vp),
+                ("kf_has_imu", _vp), ("kf_vel", _vp), ("kf_bg", _vp), ("kf_ba", _vp),
+                ("Rcb", C.c_double * 9), ("tcb", C.c_double * 3), ("tbc", C.c_double * 3),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("bf", C.c_float),
+                ("n_mp", _i), ("mp_pos", _vp),
+                ("n_edges", _i), ("e_kf", _vp), ("e_mp", _vp), ("e_stereo", _vp), ("e_obs", _vp), ("e_inv_sigma2", _vp),
+                ("n_inertial", _i), ("i_kf1", _vp), ("i_kf2", _vp), ("i_dR", _vp), ("i_dV", _vp), ("i_dP", _vp),
+                ("i_JRg", _vp), ("i_JVg", _vp), ("i_JVa", _vp), ("i_JPg", _vp), ("i_JPa", _vp), ("i_bias", _vp),
+                ("i_dT", _vp), ("i_C", _vp), ("i_last", _vp),
+                ("lambda_init", C.c_double), ("iterations", _i)]
+
+
+_LIA_TYPES = dict(kf_Rwb=np.float64, kf_twb=np.float64, kf_Rcw=np.float64, kf_tcw=np.float64, kf_fixed=np.uint8,
+                  kf_has_imu=np.uint8, kf_vel=np.float64, kf_bg=np.float64, kf_ba=np.float64, mp_pos=np.float64,
+                  e_kf=np.int32, e_mp=np.int32, e_stereo=np.uint8, e_obs=np.float64, e_inv_sigma2=np.float32,
+                  i_kf1=np.int32, i_kf2=np.int32, i_dR=np.float32, i_dV=np.float32, i_dP=np.float32, i_JRg=np.float32,
+                  i_JVg=np.float32, i_JVa=np.float32, i_JPg=np.float32, i_JPa=np.float32, i_bias=np.float32,
+                  i_dT=np.float32, i_C=np.float32, i_last=np.uint8)
+
+
+def make_lia_view(d):
+    """d: dict with the arrays of lia_graph_view plus Rcb[3,3], tcb[3], tbc[3], cam=(fx,fy,cx,cy,bf),
+    lambda_init, iterations."""
+    v = lia_graph_view()
+    keep = {}
+    for k, t in _LIA_TYPES.items():
+        keep[k] = np.ascontiguousarray(d[k], t)
+        setattr(v, k, keep[k].ctypes.data)
+    v.n_kf, v.n_mp, v.n_edges, v.n_inertial = len(keep["kf_fixed"]), len(keep["mp_pos"]), len(keep["e_kf"]), len(keep["i_kf1"])
+    for i, x in enumerate(np.asarray(d["Rcb"], np.float64).reshape(9)):
+        v.Rcb[i] = x
+    for i in range(3):
+        v.tcb[i] = float(d["tcb"][i])
+        v.tbc[i] = float(d["tbc"][i])
+    v.fx, v.fy, v.cx, v.cy, v.bf = (float(c) for c in d["cam"])
+    v.lambda_init, v.iterations = float(d.get("lambda_init", 1.0)), int(d.get("iterations", 10))
+    v._keep = keep
+    return v

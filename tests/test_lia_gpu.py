@@ -1,0 +1,33 @@
+"""GPU parity of lia_solve (C ABI, Optimizer::LocalInertialBA's optimize(), Optimizer.cc:2383-2958) against the
+fp64 CPU oracle.  The kernel's source is already held against the oracle on the host
+(tests/test_lia_core_host.py); this file is the hardware run of the same comparison.
+
+SKIPPED for now: the single-launch device path was finished after the round's GPU budget was spent and has
+not been on a B200 yet.  Remove the skip in the first GPU call of the next round."""
+import numpy as np
+import pytest
+
+from orb_slam3_b200 import scenes
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skip(reason="lia_kernel has not been run on hardware yet (row 8f-4b)")]
+
+
+@pytest.mark.parametrize("n_opt,n_mp,seed,perturb", [(4, 80, 2, 1.0), (6, 300, 1, 1.0), (10, 400, 3, 1.0), (5, 150, 5, 6.0),
+                                                      (25, 1500, 9, 1.0)])
+def test_device_run_matches_the_oracle(oracle, n_opt, n_mp, seed, perturb):
+    from orb_slam3_b200.optimizer import LocalInertialBA
+    from test_lia_core_host import _compare
+    d, _ = scenes.lia_scene(n_opt, n_mp, seed=seed, perturb=perturb)
+    if n_opt == 25:
+        d["lambda_init"], d["iterations"] = 1e-2, 4               # bLarge
+    v = oracle.make_lia_view(d)
+    ref = oracle.lia_solve(v)
+    lia = LocalInertialBA()
+    got = lia(v)
+    # fp64 atomics change the summation order: LM counts may differ once a trial is at the rounding level
+    assert abs(got["stats"]["iterations"] - ref["stats"]["iterations"]) <= 1
+    if got["stats"]["iterations"] == ref["stats"]["iterations"] and got["stats"]["trials"] == ref["stats"]["trials"]:
+        _compare(d, ref, got, tol=1e-6)
+    else:
+        assert abs(got["stats"]["err_end"] - ref["stats"]["err_end"]) <= 1e-3 * ref["stats"]["err_end"]
+    assert lia.kernel_launches() == 1 and lia.last_ms() > 0
