@@ -45,3 +45,20 @@ def test_large_window_settings_and_bad_views(oracle):
     v.lambda_init = 0.0
     with pytest.raises(OrbError):
         lia_debug_host(v)
+
+
+def test_window_without_inertial_edges(oracle):
+    """Keyframes without IMU vertices and no inertial edges: the ImuCamPose parametrisation alone (the visual
+    part of the window) -- the degenerate input the core must still handle."""
+    from orb_slam3_b200.optimizer import lia_debug_host
+    d, _ = scenes.lia_scene(5, 200, seed=11)
+    for k in ("i_kf1", "i_kf2", "i_dT", "i_last"):
+        d[k] = d[k][:0]
+    for k in ("i_dR", "i_dV", "i_dP", "i_JRg", "i_JVg", "i_JVa", "i_JPg", "i_JPa", "i_bias", "i_C"):
+        d[k] = np.asarray(d[k])[:0]
+    d["kf_has_imu"] = np.zeros_like(d["kf_has_imu"])
+    v = oracle.make_lia_view(d)
+    ref, got = oracle.lia_solve(v), lia_debug_host(v)
+    assert ref["stats"]["dim"] == 6 * 5
+    _compare(d, ref, got)
+    assert np.array_equal(got["vel"], d["kf_vel"]) and np.array_equal(got["bg"], d["kf_bg"])
