@@ -11,6 +11,9 @@
   lba_small.npz      : oracle optimize(10) result on lba_graph(8, 300, seed=1).
   stereo_640x480.npz : oracle Frame::ComputeStereoMatches on synth_frame(480,640,5) / stereo_right(.., 6, (5,30,17)).
   pose_small.npz     : oracle Optimizer::PoseOptimization on pose_scene(400, seed=7).
+  frustum_small.npz  : oracle Frame::isInFrustum on frustum_scene(3000, seed=2).
+  bow_small.npz      : oracle DBoW2 transform of the extract_640x480 descriptors on synth_vocabulary(10, 4, seed=2).
+  lia_small.npz      : oracle Optimizer::LocalInertialBA optimize() on lia_scene(5, 150, seed=6).
 """
 import os
 import sys
@@ -83,4 +86,20 @@ pv, _ = scenes.pose_scene(400, seed=7)
 pr = O.pose_optimize(pv)
 np.savez_compressed(os.path.join(out, "pose_small.npz"), inliers=pr["inliers"], pose=pr["pose"], outlier=pr["outlier"],
                     stats=pr["stats"])
+# ---- isInFrustum
+fv, _ = scenes.frustum_scene(3000, seed=2)
+n_in, fo = O.is_in_frustum(fv, 0.5)
+np.savez_compressed(os.path.join(out, "frustum_small.npz"), n_in=n_in, **fo)
+
+# ---- ComputeBoW
+voc = scenes.synth_vocabulary(10, 4, seed=2)
+bw = O.bow_transform(voc, d, 2)
+np.savez_compressed(os.path.join(out, "bow_small.npz"), **bw)
+
+# ---- LocalInertialBA
+ld, _ = scenes.lia_scene(5, 150, seed=6)
+lr = O.lia_solve(O.make_lia_view(ld))
+np.savez_compressed(os.path.join(out, "lia_small.npz"), tcw=lr["tcw"], Rcw=lr["Rcw"], vel=lr["vel"], bg=lr["bg"], ba=lr["ba"],
+                    mp_pos=lr["mp_pos"], chi2=lr["chi2"], iterations=lr["stats"]["iterations"], trials=lr["stats"]["trials"],
+                    err_end=lr["stats"]["err_end"])
 print("golden fixtures written to", out)

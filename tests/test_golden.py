@@ -84,6 +84,45 @@ def test_oracle_reproduces_stereo_and_pose_golden(oracle):
     assert np.array_equal(r["stats"], zp["stats"]) and np.allclose(r["pose"], zp["pose"], rtol=0, atol=1e-11)
 
 
+def test_oracle_reproduces_frustum_bow_and_lia_golden(oracle):
+    fv, _ = scenes.frustum_scene(3000, seed=2)
+    n_in, fo = oracle.is_in_frustum(fv, 0.5)
+    z = _load("frustum_small.npz")
+    assert n_in == int(z["n_in"])
+    for k in fo:
+        assert np.array_equal(fo[k], z[k]), k
+    zs, f0, _ = _scene()
+    voc = scenes.synth_vocabulary(10, 4, seed=2)
+    bw = oracle.bow_transform(voc, zs["desc"], 2)
+    zb = _load("bow_small.npz")
+    for k in ("bow_ids", "bow_vals", "fv_node_ids", "fv_ptr", "fv_idx"):
+        assert np.array_equal(bw[k], zb[k]), k
+    ld, _ = scenes.lia_scene(5, 150, seed=6)
+    lr = oracle.lia_solve(oracle.make_lia_view(ld))
+    zl = _load("lia_small.npz")
+    assert lr["stats"]["iterations"] == int(zl["iterations"]) and lr["stats"]["trials"] == int(zl["trials"])
+    for k in ("tcw", "Rcw", "vel", "bg", "ba", "mp_pos"):
+        assert np.allclose(lr[k], zl[k], rtol=0, atol=1e-9), k
+    assert np.allclose(lr["chi2"], zl["chi2"], rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_frustum_and_bow_golden():
+    from orb_slam3_b200.bow import ORBVocabulary
+    from orb_slam3_b200.frustum import FrustumCuller
+    fv, _ = scenes.frustum_scene(3000, seed=2)
+    n_in, fo = FrustumCuller().isInFrustum(fv, 0.5)
+    z = _load("frustum_small.npz")
+    assert n_in == int(z["n_in"])
+    for k in fo:
+        assert np.array_equal(fo[k], z[k]), k
+    zs = _load("extract_640x480.npz")
+    bw = ORBVocabulary(scenes.synth_vocabulary(10, 4, seed=2)).transform(zs["desc"], 2)
+    zb = _load("bow_small.npz")
+    for k in ("bow_ids", "bow_vals", "fv_node_ids", "fv_ptr", "fv_idx"):
+        assert np.array_equal(bw[k], zb[k]), k
+
+
 @pytest.mark.gpu
 def test_gpu_reproduces_stereo_and_pose_golden():
     from orb_slam3_b200.extractor import ORBextractor
