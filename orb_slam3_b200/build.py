@@ -1,45 +1,84 @@
-"""Build liborbb200.so in-tree with nvcc for sm_100a (no torch involved)."""
+"""Build liborbb200.so in-tree with nvcc for sm_100a (no torch involved).
+
+Every csrc/*.cu is compiled to its own object (in parallel, cached under build/ by content hash of the
+translation unit's sources + flags) and linked into one shared library."""
+import concurrent.futures
+import hashlib
 import os
 import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "liborbb200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-fmad=false",  # canonical float semantics: no FMA contraction
-         "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
+         "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
 
 def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
+def _headers():
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if not f.endswith(".cu"))
+    deps.append(os.path.join(HERE, "..", "include", "orb_b200.h"))
+    return deps
+
+
+def _digest(src):
+    h = hashlib.sha256(" ".join([NVCC] + FLAGS).encode())
+    for p in [src] + _headers():
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:20]
+
+
 def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
-    deps.append(os.path.join(HERE, "..", "include", "orb_b200.h"))
-    return any(os.path.getmtime(d) > t for d in deps)
+    return any(os.path.getmtime(d) > t for d in sources() + _headers())
+
+
+def _compile(src, force):
+    name = os.path.splitext(os.path.basename(src))[0]
+    obj = os.path.join(OBJ, "%s.%s.o" % (name, _digest(src)))
+    if os.path.exists(obj) and not force:
+        return obj, "cached %s\n" % os.path.basename(obj), 0
+    for f in os.listdir(OBJ):  # drop stale objects of this translation unit
+        if f.startswith(name + ".") and f.endswith(".o"):
+            os.remove(os.path.join(OBJ, f))
+    cmd = [NVCC] + FLAGS + ["-c", "-o", obj, src]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    return obj, " ".join(cmd) + "\n" + r.stdout, r.returncode
 
 
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
-    cmd = [NVCC] + FLAGS + ["-o", LIB] + sources() + ["-ldl"]
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    os.makedirs(OBJ, exist_ok=True)
+    with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        results = list(ex.map(lambda s: _compile(s, force), sources()))
+    log_text = "".join(r[1] for r in results)
+    rc = max(r[2] for r in results)
+    if rc == 0:
+        cmd = [NVCC, "-shared", "-o", LIB] + [r[0] for r in results] + ["-ldl"]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        log_text += " ".join(cmd) + "\n" + r.stdout
+        rc = r.returncode
     log = os.path.join(HERE, "build.log")
     with open(log, "w") as f:
-        f.write(" ".join(cmd) + "\n" + r.stdout)
-    if verbose or r.returncode:
-        sys.stderr.write(r.stdout)
-    if r.returncode:
+        f.write(log_text)
+    if verbose or rc:
+        sys.stderr.write(log_text)
+    if rc:
         raise RuntimeError("nvcc failed, see %s" % log)
     return LIB
 
 
 if __name__ == "__main__":
-    build(force=True, verbose="-v" in sys.argv)
+    build(force="-f" in sys.argv, verbose="-v" in sys.argv)
     print(LIB)

@@ -195,4 +195,15 @@ int orb_debug_introsort(const int* count, const int* ulx, int n, int* perm_out) 
   return n;
 }
 
+int orb_debug_sincos_device(int device, const float* x, size_t n, float* cos_out, float* sin_out) {
+  if (!x || !cos_out || !sin_out || n == 0) return ORB_E_ARG;
+  return orbb200::debug_sincos_device(device, x, n, cos_out, sin_out);
+}
+
+int orb_debug_sincos_host(const float* x, size_t n, float* cos_out, float* sin_out, int fused) {
+  if (!x || !cos_out || !sin_out) return ORB_E_ARG;
+  orbb200::debug_sincos_host(x, n, cos_out, sin_out, fused);
+  return 0;
+}
+
 }  // extern "C"

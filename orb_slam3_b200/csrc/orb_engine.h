@@ -126,6 +126,9 @@ struct Engine {
   int debug_candidates(int frame, int level, int* xys, int cap);
 };
 
+int debug_sincos_device(int device, const float* x, size_t n, float* c, float* s);
+void debug_sincos_host(const float* x, size_t n, float* c, float* s, int fused);
+
 }  // namespace orbb200
 
 // The opaque handle of include/orb_b200.h.

@@ -24,6 +24,7 @@
 #include "octree_core.h"
 #include "orb_engine.h"
 #include "cta_backend.cuh"
+#include "glibc_sincosf.h"
 
 namespace orbb200 {
 
@@ -623,7 +624,9 @@ describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blr
   // ---- steered BRIEF: lane <-> descriptor byte
   const float factorPI = 0.017453292519943295f;  // (float)(CV_PI/180.f)
   const float ang = __fmul_rn(angle, factorPI);
-  const float a = (float)cos((double)ang), b = (float)sin((double)ang);
+  // glibc's cosf / sinf bit for bit (csrc/glibc_sincosf.h): the reference's `(float)cos(angle)` resolves to
+  // std::cos(float) = cosf (ORBextractor.cc:111-112); (float)cos((double)x) differs for 0.13 % of the floats
+  const float a = glibc_sincosf::cosf_exact<true>(ang), b = glibc_sincosf::sinf_exact<true>(ang);
   // stage the 37x37 blurred patch (rotated pattern offsets are within +-18) in shared memory with
   // coalesced aligned word loads; the 512 samples then gather from shared memory instead of
   // issuing ~25 L1 wavefronts per load instruction
@@ -664,6 +667,43 @@ describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blr
     kp.octave = level;
     kp.class_id = -1;
     kps[(size_t)f * out_cap + pos] = kp;
+  }
+}
+
+// cosf / sinf of csrc/glibc_sincosf.h on the device (debug hook of the parity tests)
+__global__ void sincos_debug_kernel(const float* __restrict__ x, float* __restrict__ c, float* __restrict__ s, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    c[i] = glibc_sincosf::cosf_exact<true>(x[i]);
+    s[i] = glibc_sincosf::sinf_exact<true>(x[i]);
+  }
+}
+
+int debug_sincos_device(int device, const float* x, size_t n, float* c, float* s) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_last_error("no CUDA device: orb_slam3_b200 has no CPU path");
+    return ORB_E_NODEVICE;
+  }
+  CUDA_TRY(cudaSetDevice(device));
+  float *dx = nullptr, *dc = nullptr, *ds = nullptr;
+  CUDA_TRY(cudaMalloc(&dx, n * 4));
+  CUDA_TRY(cudaMalloc(&dc, n * 4));
+  CUDA_TRY(cudaMalloc(&ds, n * 4));
+  cudaError_t e = cudaMemcpy(dx, x, n * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    sincos_debug_kernel<<<148 * 8, 256>>>(dx, dc, ds, n);
+    e = cudaMemcpy(c, dc, n * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(s, ds, n * 4, cudaMemcpyDeviceToHost);
+  }
+  cudaFree(dx); cudaFree(dc); cudaFree(ds);
+  if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); return ORB_E_CUDA; }
+  return 0;
+}
+
+void debug_sincos_host(const float* x, size_t n, float* c, float* s, int fused) {
+  for (size_t i = 0; i < n; i++) {
+    c[i] = fused ? glibc_sincosf::cosf_exact<true>(x[i]) : glibc_sincosf::cosf_exact<false>(x[i]);
+    s[i] = fused ? glibc_sincosf::sinf_exact<true>(x[i]) : glibc_sincosf::sinf_exact<false>(x[i]);
   }
 }
 

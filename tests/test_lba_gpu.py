@@ -54,6 +54,17 @@ def test_lba_config4_50kf_20k_landmarks(oracle, lba):
     assert np.array_equal(LBA.outliers(g, ref), LBA.outliers(g, got))
 
 
+def test_lba_config5_200kf_80k_landmarks(oracle, lba):
+    """BASELINE.json configs[4] at full size against the oracle (the reference's own iteration budget:
+    optimize(10), Optimizer.cc:1410-1411)."""
+    g, _ = scenes.lba_graph(200, 80000, seed=0)
+    gv = scenes.lba_view(g)
+    ref, got = oracle.lba_solve(gv), lba(gv)
+    _compare(g, ref, got, "config5")
+    from orb_slam3_b200.optimizer import LocalBundleAdjustment as LBA
+    assert np.array_equal(LBA.outliers(g, ref), LBA.outliers(g, got))
+
+
 def test_lba_rejected_trials_and_user_lambda(oracle, lba):
     g, _ = scenes.lba_rough_graph(4)
     gv = scenes.lba_view(g)

@@ -1,15 +1,13 @@
 """GPU parity of lia_solve (C ABI, Optimizer::LocalInertialBA's optimize(), Optimizer.cc:2383-2958) against the
 fp64 CPU oracle.  The kernel's source is already held against the oracle on the host
 (tests/test_lia_core_host.py); this file is the hardware run of the same comparison.
-
-SKIPPED for now: the single-launch device path was finished after the round's GPU budget was spent and has
-not been on a B200 yet.  Remove the skip in the first GPU call of the next round."""
+"""
 import numpy as np
 import pytest
 
 from orb_slam3_b200 import scenes
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skip(reason="lia_kernel has not been run on hardware yet (row 8f-4b)")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("n_opt,n_mp,seed,perturb", [(4, 80, 2, 1.0), (6, 300, 1, 1.0), (10, 400, 3, 1.0), (5, 150, 5, 6.0),
