@@ -216,6 +216,14 @@ def extract_throughput(frames, nfeatures, nthreads, iters, scale_factor=1.2, nle
 
 
 # ---- matchers: the views are the ctypes structs of orb_slam3_b200/views.py (interface types)
+def three_maxima(sizes, init=(-1, -1, -1)):
+    sizes = np.ascontiguousarray(sizes, np.int32)
+    ind = np.array(init, np.int32)
+    lib().orc_three_maxima.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    lib().orc_three_maxima(_ptr(sizes), len(sizes), _ptr(ind))
+    return tuple(int(v) for v in ind)
+
+
 def ham_distance(a, b):
     a = np.ascontiguousarray(a, np.uint8)
     b = np.ascontiguousarray(b, np.uint8)

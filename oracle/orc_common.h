@@ -5,14 +5,17 @@
 // cpu_baseline / --impl reference legs of bench.py use it, as the checker and
 // as the timed CPU baseline.
 //
-// PARITY UNPINNED BY THE REFERENCE: ORB_SLAM3 ships no tests, golden vectors or
-// known-answer fixtures for this path and the
-// reference itself cannot be compiled in this image (OpenCV C++, Eigen,
-// Pangolin and Boost headers are absent).  The oracle is therefore pinned to
-//   * cv2 4.13 (Python) for the un-vendored OpenCV arithmetic (resize, FAST,
-//     GaussianBlur, fastAtan2) -- tests/test_oracle_vs_cv2.py + tests/golden/
-//   * the reference sources it restates, cited per function as file:line
-//     relative to /root/reference.
+// PARITY PINNING.  ORB_SLAM3 ships no tests, golden vectors or known-answer fixtures for this path
+// (SURVEY.md section 4, 8c), and the whole reference cannot be built in this image (OpenCV C++, Eigen,
+// Pangolin and Boost headers are absent).  What pins the oracle:
+//   * extractor rows (a1-a9): the REFERENCE's own object code -- /root/reference/src/ORBextractor.cc compiled
+//     UNMODIFIED against oracle/cvcompat/ (`make ref` -> oracle/_ref/), plus ORBmatcher::DescriptorDistance /
+//     ComputeThreeMaxima -- compared with this restatement by tests/test_ref_parity.py, and reference vectors
+//     generated from it under tests/golden/ref_*.npz (scripts/make_golden_ref.py);
+//   * the un-vendored OpenCV arithmetic underneath (resize, FAST, GaussianBlur, fastAtan2): cv2 4.13 (Python),
+//     bit-exact -- tests/test_oracle_vs_cv2.py + tests/golden/primitives_cv2.npz;
+//   * matchers / g2o / DBoW2 rows: "parity unpinned" by the reference (their translation units need Eigen /
+//     Sophus); pinned by independent numpy restatements and the reference sources cited per function.
 #pragma once
 #include <stdint.h>
 

@@ -108,6 +108,10 @@ inline int rot_bin(float a1, float a2) {
 extern "C" {
 
 int orc_ham_distance(const uint8_t* a, const uint8_t* b) { return descriptor_distance(a, b); }
+// ComputeThreeMaxima alone (pinned against the reference's object code by tests/test_ref_parity.py)
+void orc_three_maxima(const int* sizes, int L, int* ind /*3, in: initial values*/) {
+  three_maxima(sizes, L, ind[0], ind[1], ind[2]);
+}
 
 // ORBmatcher.cc:43-141
 int orc_match_project_local(const orb_frame_view* F, const orb_mappoint_view* mps, float th, float nn_ratio,

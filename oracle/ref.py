@@ -1,0 +1,127 @@
+"""ctypes binding of oracle/_ref/libref_orb.so (TEST INFRASTRUCTURE ONLY): the REFERENCE's own object code --
+/root/reference/src/ORBextractor.cc compiled unmodified against oracle/cvcompat/ plus ORBmatcher's
+DescriptorDistance / ComputeThreeMaxima -- used to pin the restated oracle (and through it the CUDA path) to
+the reference itself.  Built by `make -C oracle ref` where /root/reference exists; shipped prebuilt to the GPU box."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from . import oracle as _o
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libref_orb.so")
+REFERENCE = os.environ.get("ORB_REFERENCE_DIR", "/root/reference")
+KP_DTYPE = _o.KP_DTYPE
+
+
+def build(force=False):
+    """Compile oracle/_ref from the reference sources where they lie (needs /root/reference)."""
+    if not os.path.exists(os.path.join(REFERENCE, "src", "ORBextractor.cc")):
+        return None
+    _o.build()
+    cmd = ["make", "-C", _HERE, "REF=" + REFERENCE] + (["-B"] if force else []) + ["_ref/libref_orb.so"]
+    subprocess.check_call(cmd, stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+def available():
+    return os.path.exists(LIB_PATH) or build() is not None
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH) and build() is None:
+            raise FileNotFoundError("oracle/_ref is not built and %s is absent" % REFERENCE)
+        _o.lib()  # liborb_oracle.so first: _ref's image primitives resolve against it
+        L = C.CDLL(LIB_PATH)
+        ip, fp = C.POINTER(C.c_int), C.POINTER(C.c_float)
+        L.ref_extractor_create.restype = C.c_void_p
+        L.ref_extractor_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.ref_extractor_destroy.argtypes = [C.c_void_p]
+        L.ref_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                  C.c_void_p, C.c_int, ip]
+        L.ref_level_info.argtypes = [C.c_void_p, C.c_int, ip, ip, ip, ip, fp]
+        L.ref_level_ptr.restype = C.POINTER(C.c_uint8)
+        L.ref_level_ptr.argtypes = [C.c_void_p, C.c_int]
+        L.ref_tables.argtypes = [C.c_void_p] * 8
+        L.ref_descriptor_distance.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref_three_maxima.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_extract_throughput.restype = C.c_double
+        L.ref_extract_throughput.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                             C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class RefExtractor:
+    """ORB_SLAM3::ORBextractor itself (reference object code)."""
+
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+        self.nlevels, self.nfeatures = nlevels, nfeatures
+        self._h = lib().ref_extractor_create(nfeatures, scale_factor, nlevels, ini_th, min_th)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().ref_extractor_destroy(self._h)
+            self._h = None
+
+    def extract(self, img, lap=(0, 0)):
+        """Returns (keypoints, descriptors, monoIndex) of operator() (ORBextractor.cc:1086-1168)."""
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        cap = self.nfeatures * 2 + 64 * self.nlevels
+        kps = np.zeros(cap, dtype=KP_DTYPE)
+        desc = np.zeros((cap, 32), dtype=np.uint8)
+        n = C.c_int(0)
+        mono = lib().ref_extract(self._h, _ptr(img), img.shape[0], img.shape[1], img.strides[0], int(lap[0]), int(lap[1]),
+                                 _ptr(kps), _ptr(desc), cap, C.byref(n))
+        assert n.value <= cap
+        return kps[:n.value].copy(), desc[:n.value].copy(), mono
+
+    def level_image(self, level, border=0):
+        """mvImagePyramid[level]; border = 19 also returns the EDGE_THRESHOLD frame around it."""
+        w, h, step, q = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        s = C.c_float()
+        assert lib().ref_level_info(self._h, level, C.byref(w), C.byref(h), C.byref(step), C.byref(q), C.byref(s)) == 0
+        p = lib().ref_level_ptr(self._h, level)
+        base = C.cast(p, C.c_void_p).value - border * step.value - border
+        buf = (C.c_uint8 * ((h.value + 2 * border) * step.value)).from_address(base)
+        a = np.frombuffer(buf, np.uint8).reshape(h.value + 2 * border, step.value)
+        return a[:, :w.value + 2 * border].copy()
+
+    def tables(self):
+        nl = self.nlevels
+        sc, isc, s2, is2 = (np.zeros(nl, np.float32) for _ in range(4))
+        q, um, pat = np.zeros(nl, np.int32), np.zeros(16, np.int32), np.zeros(1024, np.int32)
+        lib().ref_tables(self._h, _ptr(sc), _ptr(isc), _ptr(s2), _ptr(is2), _ptr(q), _ptr(um), _ptr(pat))
+        return dict(scale=sc, inv_scale=isc, sigma2=s2, inv_sigma2=is2, quota=q, umax=um, pattern=pat)
+
+
+def descriptor_distance(a, b):
+    a, b = np.ascontiguousarray(a, np.uint8), np.ascontiguousarray(b, np.uint8)
+    return lib().ref_descriptor_distance(_ptr(a), _ptr(b))
+
+
+def three_maxima(sizes, init=(-1, -1, -1)):
+    sizes = np.ascontiguousarray(sizes, np.int32)
+    ind = np.array(init, np.int32)
+    lib().ref_three_maxima(_ptr(sizes), len(sizes), _ptr(ind))
+    return tuple(int(v) for v in ind)
+
+
+def extract_throughput(frames, nfeatures, nthreads, iters):
+    """Seconds for nthreads x iters calls of the reference extractor (one instance per std::thread)."""
+    frames = np.ascontiguousarray(frames, np.uint8)
+    tot = C.c_longlong(0)
+    dt = lib().ref_extract_throughput(nfeatures, 1.2, 8, 20, 7, _ptr(frames), frames.shape[0], frames.shape[1],
+                                      frames.shape[2], nthreads, iters, C.byref(tot))
+    return dt, tot.value
