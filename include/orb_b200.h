@@ -263,6 +263,11 @@ typedef struct lba_stats {
   double ms_linearize, ms_schur, ms_solve, ms_update;   /* accumulated per stage */
   int32_t n_free_kf, n_pairs;
   double schur_flops;         /* block-sparse useful flops per trial */
+  int32_t solver_kind;        /* reduced solve: 0 = dense cooperative LDL^T (all SMs), 1 = envelope LDL^T (one CTA) */
+  int32_t envelope_rows_max;  /* tallest panel window of the row envelope of S (rows) */
+  double ms_host_prep;        /* host wall time before the first kernel: edge sort, CSRs, pair lists, ordering, uploads queued */
+  double ms_wall;             /* host wall time of the whole call (prep + H2D + kernels + D2H + un-sort) */
+  double allreduce_bytes_per_trial; /* bytes each rank contributes to the per-trial ncclAllReduce (0 on one GPU) */
 } lba_stats;
 
 typedef struct lba_solver lba_solver;

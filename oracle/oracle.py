@@ -18,7 +18,8 @@ def build(force=False):
     srcs = [f for f in os.listdir(_HERE) if f.startswith("orc_") or f.endswith(".inc")]
     if not force and os.path.exists(_LIB_PATH):
         so_m = os.path.getmtime(_LIB_PATH)
-        if all(os.path.getmtime(os.path.join(_HERE, f)) <= so_m for f in srcs):
+        deps = [os.path.join(_HERE, f) for f in srcs] + [os.path.join(_HERE, "..", "include", "orb_b200.h")]
+        if all(os.path.getmtime(f) <= so_m for f in deps):
             return _LIB_PATH
     subprocess.check_call(["make", "-C", _HERE, "-B", "liborb_oracle.so"],
                           stdout=subprocess.DEVNULL)

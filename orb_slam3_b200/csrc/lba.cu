@@ -31,6 +31,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -350,6 +351,20 @@ __global__ void __launch_bounds__(128) bschur_kernel(LbaDev D) {
   }
 }
 
+// Landmark shards exchange only the row envelope of (S | b_s): rows are packed back to back for the
+// ncclAllReduce (dir 0) and scattered into the dense buffer again afterwards (dir 1).  Row n = rhs.
+__global__ void __launch_bounds__(256) env_pack_kernel(double* __restrict__ S, int n, const int* __restrict__ first,
+                                                       const long long* __restrict__ rowp, double* __restrict__ buf, int dir) {
+  const int i = blockIdx.x;
+  const int f = i < n ? first[i] : 0, len = i < n ? i - f + 1 : n;
+  double* row = S + (size_t)i * n + f;
+  double* b = buf + rowp[i];
+  for (int j = threadIdx.x; j < len; j += 256) {
+    if (dir == 0) b[j] = row[j];
+    else row[j] = b[j];
+  }
+}
+
 __global__ void add_lambda_kernel(LbaDev D, double lambda) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < D.n) D.S[(size_t)i * D.n + i] += lambda;
@@ -522,6 +537,155 @@ __global__ void __launch_bounds__(1024) backsub_kernel(const double* __restrict_
       }
       for (; i < nb; i++) s0 += col[(size_t)i * n] * xb[i];
       acc[j] -= (s0 + s1) + (s2 + s3);
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------- envelope (skyline) LDL^T
+// The reduced system of a local window is block-banded once the keyframes are ordered along the
+// covisibility chain (g2o hands Eigen's SimplicialLDLT a sparse matrix for the same reason,
+// linear_solver_eigen.h:94-124): without pivoting the factor never leaves the row envelope of S.  This
+// kernel factors S inside its envelope with ONE CTA -- no grid barriers -- and solves for x in the same
+// launch.  Per 32-column panel: (1) the 32x32 diagonal block by the 1024 threads (one register each, the
+// pivot column broadcast through shared memory: ~32 x (barrier + reciprocal) on the critical path),
+// (2) the rows of the envelope below it (<= SKY_WMAX, one warp per row, forward substitution by shuffles),
+// their L and L*D kept in shared memory, (3) the trailing update of the window's lower triangle in 4x4
+// register micro-tiles straight from those two shared arrays.  `reach[c]` = last row whose envelope
+// contains a column <= c (prefix maximum, host-built from the pose-pair list); row n is the right-hand side.
+constexpr int SKY_THREADS = 1024;
+constexpr int SKY_WMAX = 320;  // rows of one panel window incl. the rhs row (dynamic shared memory: 2 x 32 x WMAX doubles)
+
+__global__ void __launch_bounds__(SKY_THREADS) ldlt_sky_kernel(double* __restrict__ M, int n, const int* __restrict__ reach,
+                                                             const int* __restrict__ first, double* fail,
+                                                             double* __restrict__ x) {
+  extern __shared__ __align__(16) double sky_dyn[];
+  double* Alt = sky_dyn;                         // [32][SKY_WMAX]  L   of the window rows, transposed (m major)
+  double* Aldt = sky_dyn + 32 * SKY_WMAX;        // [32][SKY_WMAX]  L*D of the window rows
+  __shared__ double L11[NB][NB + 1];
+  __shared__ double colb[NB];
+  __shared__ double Dd[NB], Di[NB];
+  __shared__ double xb[NB];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int k0 = 0; k0 < n; k0 += NB) {
+    const int nb = min(NB, n - k0);
+    // ---- (1) diagonal block: thread (r, c) owns a[r][c], r = warp, c = lane
+    {
+      const int r = warp, c = lane;
+      double a = (r < nb && c <= r) ? M[(size_t)(k0 + r) * n + k0 + c] : 0.0;
+      for (int k = 0; k < nb; k++) {
+        if (c == k && r >= k) colb[r] = a;  // column k of L*D (pivot included)
+        __syncthreads();
+        const double d = colb[k];
+        // 1/d: fp32 seed + two Newton steps in fp64 (~1 ulp), redundantly per thread
+        double inv = (double)__frcp_rn((float)d);
+        inv = inv * (2.0 - d * inv);
+        inv = inv * (2.0 - d * inv);
+        if (r == k && c == k) { Dd[k] = d; Di[k] = inv; if (d == 0.0) *fail = 1.0; }
+        if (r > k && c > k && c <= r) a -= (colb[r] * inv) * colb[c];
+        if (c == k && r > k) a = colb[r] * inv;  // L[r][k]
+        __syncthreads();
+      }
+      L11[r][c] = a;  // strictly lower part = L, diagonal = D
+      if (r < nb && c <= r) M[(size_t)(k0 + r) * n + k0 + c] = a;
+    }
+    __syncthreads();
+    // ---- (2) panel rows: the envelope rows below the block, then the rhs row (window index w)
+    const int r0 = k0 + nb;
+    const int rend = min(max(reach[k0 + nb - 1] + 1, r0), n);  // envelope rows are [r0, rend)
+    const int nw = rend - r0 + 1;                               // + rhs
+    for (int w = warp; w < nw; w += SKY_THREADS / 32) {
+      const int i = (w < nw - 1) ? r0 + w : n;
+      double* Mi = M + (size_t)i * n + k0;
+      double a = (lane < nb) ? Mi[lane] : 0.0;
+      for (int m = 0; m < nb; m++) {
+        const double ldm = __shfl_sync(0xffffffffu, a, m);  // (L*D)_im is final once m steps are done
+        if (lane > m) a -= ldm * L11[lane][m];
+      }
+      const double l = (lane < nb) ? a * Di[lane] : 0.0;
+      if (lane < nb) Mi[lane] = l;
+      Alt[lane * SKY_WMAX + w] = l;
+      Aldt[lane * SKY_WMAX + w] = (lane < nb) ? a : 0.0;
+    }
+    __syncthreads();
+    // ---- (3) trailing update inside the window: M[i][j] -= sum_m L[i][m] (L*D)[j][m], j <= i, 4x4 micro-tiles
+    {
+      const int T = (nw + 3) >> 2;           // micro-tile rows
+      const int ntile = T * (T + 1) / 2;
+      for (int t = tid; t < ntile; t += SKY_THREADS) {
+        int ti = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
+        while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
+        while (ti * (ti + 1) / 2 > t) ti--;
+        const int tj = t - ti * (ti + 1) / 2;
+        double acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+          for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
+#pragma unroll 4
+        for (int m = 0; m < NB; m++) {
+          const double2 li0 = *reinterpret_cast<const double2*>(&Alt[m * SKY_WMAX + 4 * ti]);
+          const double2 li1 = *reinterpret_cast<const double2*>(&Alt[m * SKY_WMAX + 4 * ti + 2]);
+          const double2 lj0 = *reinterpret_cast<const double2*>(&Aldt[m * SKY_WMAX + 4 * tj]);
+          const double2 lj1 = *reinterpret_cast<const double2*>(&Aldt[m * SKY_WMAX + 4 * tj + 2]);
+          const double li[4] = {li0.x, li0.y, li1.x, li1.y}, lj[4] = {lj0.x, lj0.y, lj1.x, lj1.y};
+#pragma unroll
+          for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) acc[a][b] += li[a] * lj[b];
+        }
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+          const int wi = 4 * ti + a;
+          if (wi >= nw) continue;
+          const int gi = (wi < nw - 1) ? r0 + wi : n;
+#pragma unroll
+          for (int b = 0; b < 4; b++) {
+            const int wj = 4 * tj + b;
+            if (wj >= nw - 1 || wj > wi) continue;  // the rhs row has no column; lower triangle only
+            M[(size_t)gi * n + r0 + wj] -= acc[a][b];
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // ---- L^T x = z, z = row n (already scaled by 1/D).  Blocks from the last to the first; the running
+  //      right-hand side lives in shared memory (Alt is free now), contributions of a solved block are
+  //      gathered row-wise (coalesced) into Aldt and summed per column.
+  double* acc = Alt;  // n <= 32 * SKY_WMAX
+  for (int i = tid; i < n; i += SKY_THREADS) acc[i] = M[(size_t)n * n + i];
+  __syncthreads();
+  const int nblocks = (n + NB - 1) / NB;
+  for (int b = nblocks - 1; b >= 0; b--) {
+    const int k0 = b * NB, nb = min(NB, n - k0);
+    L11[warp][lane] = (warp < nb && lane < warp) ? M[(size_t)(k0 + warp) * n + k0 + lane] : 0.0;
+    __syncthreads();
+    if (warp == 0) {
+      double v = (lane < nb) ? acc[k0 + lane] : 0.0;
+      for (int c = nb - 1; c >= 0; c--) {
+        const double xc = __shfl_sync(0xffffffffu, v, c);
+        if (lane < c) v -= L11[c][lane] * xc;
+      }
+      if (lane < nb) { xb[lane] = v; x[k0 + lane] = v; }
+    }
+    __syncthreads();
+    // columns [jmin, k0) can hold non-zeros of the block's rows
+    int jmin = k0;
+    for (int r = 0; r < nb; r++) jmin = min(jmin, first[k0 + r]);
+    const int wcols = k0 - jmin;  // <= SKY_WMAX - 1 (host-checked)
+    if (wcols > 0) {
+      if (warp < nb) {
+        const double xi = xb[warp];
+        const double* Li = M + (size_t)(k0 + warp) * n + jmin;
+        for (int j = lane; j < wcols; j += 32) Aldt[warp * SKY_WMAX + j] = Li[j] * xi;
+      }
+      __syncthreads();
+      for (int j = tid; j < wcols; j += SKY_THREADS) {
+        double s = 0;
+        for (int r = 0; r < nb; r++) s += Aldt[r * SKY_WMAX + j];
+        acc[jmin + j] -= s;
+      }
     }
     __syncthreads();
   }
@@ -742,6 +906,7 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
   CUDA_TRYL(cudaSetDevice(S.device));
   const int K = g->n_kf, L = g->n_mp, E = g->n_edges;
   // ---- structure (host): free poses, landmark CSR, pose CSR, pose-pair lists
+  const auto t_host0 = std::chrono::steady_clock::now();
   std::vector<int> free_idx(K, -1), free_kf;
   for (int k = 0; k < K; k++)
     if (!g->kf_fixed[k]) { free_idx[k] = (int)free_kf.size(); free_kf.push_back(k); }
@@ -755,6 +920,79 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
   for (int l = 0; l < L; l++) lm_ptr[l + 1] += lm_ptr[l];
   std::vector<int> perm(E), cursor(lm_ptr.begin(), lm_ptr.end() - 1);
   for (int e = 0; e < E; e++) perm[cursor[g->e_mp[e]]++] = e;   // sorted position -> original edge
+  // Elimination order of the free poses.  The envelope solver's cost is the profile of S, so when the
+  // caller's keyframe order is not already chain-like (Optimizer.cc:1135-1160 lists the current keyframe
+  // first, then its covisibles) the poses are renumbered by reverse Cuthill-McKee on the covisibility
+  // pattern; the natural order is kept when it is at least as good (what Eigen's AMD ordering does for g2o).
+  // covisibility pattern of the free poses (block pattern of S); with landmark shards every rank only sees
+  // its own landmarks, so the patterns are OR-ed over the ranks: ordering, envelope and the choice of the
+  // solver kernel must be identical everywhere (all ranks factor the same matrix)
+  std::vector<uint8_t> adj((size_t)nf * nf, 0);
+  {
+    std::vector<int> fl;
+    for (int l = 0; l < L; l++) {
+      fl.clear();
+      for (int s = lm_ptr[l]; s < lm_ptr[l + 1]; s++) {
+        const int f = free_idx[g->e_kf[perm[s]]];
+        if (f >= 0) fl.push_back(f);
+      }
+      for (int a : fl)
+        for (int b : fl) adj[(size_t)a * nf + b] = 1;
+    }
+    for (int a = 0; a < nf; a++) adj[(size_t)a * nf + a] = 1;
+    if (S.world > 1) {
+      if (S.graph.reserve(adj.size() + 256)) return ORB_E_CUDA;
+      CUDA_TRYL(cudaMemcpyAsync(S.graph.p, adj.data(), adj.size(), cudaMemcpyHostToDevice, S.stream));
+      const int r = g_nccl.AllReduce(S.graph.p, S.graph.p, adj.size(), /*ncclUint8*/ 1, /*ncclMax*/ 2, S.comm, S.stream);
+      if (r) { set_last_error("ncclAllReduce(covisibility pattern)"); return ORB_E_NCCL; }
+      CUDA_TRYL(cudaMemcpyAsync(adj.data(), S.graph.p, adj.size(), cudaMemcpyDeviceToHost, S.stream));
+      CUDA_TRYL(cudaStreamSynchronize(S.stream));
+    }
+  }
+  if (nf > 2 && !getenv("ORB_B200_LBA_NO_REORDER")) {
+    auto profile = [&](const std::vector<int>& pos) {  // pos[f] = position of pose f
+      long long p = 0;
+      std::vector<int> lo(nf);
+      for (int i = 0; i < nf; i++) lo[i] = i;
+      for (int a = 0; a < nf; a++)
+        for (int b = 0; b < nf; b++)
+          if (adj[(size_t)a * nf + b] && pos[b] < pos[a]) lo[pos[a]] = std::min(lo[pos[a]], pos[b]);
+      for (int i = 0; i < nf; i++) p += i - lo[i] + 1;
+      return p;
+    };
+    std::vector<int> deg(nf, 0), nat(nf), order, pos(nf, -1);
+    for (int a = 0; a < nf; a++) { nat[a] = a; for (int b = 0; b < nf; b++) deg[a] += adj[(size_t)a * nf + b] && a != b; }
+    std::vector<uint8_t> seen(nf, 0);
+    while ((int)order.size() < nf) {
+      int start = -1;  // lowest-degree unvisited node of the next component
+      for (int a = 0; a < nf; a++)
+        if (!seen[a] && (start < 0 || deg[a] < deg[start])) start = a;
+      seen[start] = 1;
+      size_t head = order.size();
+      order.push_back(start);
+      while (head < order.size()) {
+        const int a = order[head++];
+        std::vector<int> nb;
+        for (int b = 0; b < nf; b++)
+          if (adj[(size_t)a * nf + b] && !seen[b]) { nb.push_back(b); seen[b] = 1; }
+        std::stable_sort(nb.begin(), nb.end(), [&](int x, int y) { return deg[x] < deg[y]; });
+        order.insert(order.end(), nb.begin(), nb.end());
+      }
+    }
+    std::reverse(order.begin(), order.end());
+    for (int i = 0; i < nf; i++) pos[order[i]] = i;
+    if (profile(pos) * 10 < profile(nat) * 9) {  // renumber only for a >= 10 % smaller profile
+      std::vector<int> nk(nf);
+      for (int i = 0; i < nf; i++) nk[i] = free_kf[order[i]];
+      free_kf = nk;
+      for (int i = 0; i < nf; i++) free_idx[free_kf[i]] = i;
+      std::vector<uint8_t> adj2((size_t)nf * nf, 0);  // the pattern in the new numbering
+      for (int a = 0; a < nf; a++)
+        for (int b = 0; b < nf; b++)
+          if (adj[(size_t)a * nf + b]) adj2[(size_t)pos[a] * nf + pos[b]] = 1;
+      adj.swap(adj2);
+    }
+  }
   std::vector<int> se_kf(E), se_free(2 * (size_t)E);
   std::vector<uint8_t> se_st(E);
   std::vector<double> se_obs(3 * (size_t)E);
@@ -817,8 +1055,41 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
         }
       }
   }
+  // ---- row envelope of S (scalar rows): first[i] = first non-zero column, reach[c] = last row whose
+  //      envelope holds a column <= c; feasibility / cost of the single-CTA envelope solver
+  std::vector<int> env_first(n), env_reach(n, 0);
+  {
+    std::vector<int> bfirst(nf);
+    for (int i = 0; i < nf; i++) {
+      bfirst[i] = i;
+      for (int j = 0; j < i; j++)
+        if (adj[(size_t)i * nf + j]) { bfirst[i] = j; break; }
+    }
+    for (int i = 0; i < n; i++) env_first[i] = 6 * bfirst[i / 6];
+    for (int i = 0; i < n; i++) env_reach[env_first[i]] = std::max(env_reach[env_first[i]], i);
+    for (int c = 1; c < n; c++) env_reach[c] = std::max(env_reach[c], env_reach[c - 1]);
+  }
+  std::vector<long long> env_rowp(n + 2, 0);
+  for (int i = 0; i < n; i++) env_rowp[i + 1] = env_rowp[i] + (i - env_first[i] + 1);
+  env_rowp[n + 1] = env_rowp[n] + n;
+  const size_t env_total = (size_t)env_rowp[n + 1];
+  int sky_rows_max = 0;
+  double sky_flops = 0;
+  for (int k0 = 0; k0 < n; k0 += NB) {
+    const int nb = std::min(NB, n - k0), r0 = k0 + nb;
+    const int rend = std::min(std::max(env_reach[k0 + nb - 1] + 1, r0), n);
+    const int nw = rend - r0 + 1;
+    int jmin = k0;
+    for (int r = 0; r < nb; r++) jmin = std::min(jmin, env_first[k0 + r]);
+    sky_rows_max = std::max(sky_rows_max, std::max(nw, k0 - jmin));
+    sky_flops += (double)nw * nw * nb;
+  }
+  static const char* ldlt_env = getenv("ORB_B200_LDLT");  // "dense" | "sky" | unset = automatic
+  bool use_sky = sky_rows_max <= SKY_WMAX - 4 && n <= 32 * SKY_WMAX && sky_flops <= 6.0e7;
+  if (ldlt_env && !strcmp(ldlt_env, "dense")) use_sky = false;
+  if (ldlt_env && !strcmp(ldlt_env, "sky")) use_sky = sky_rows_max <= SKY_WMAX - 4 && n <= 32 * SKY_WMAX;
   // ---- device memory
-  size_t gbytes = 256 * 20 + sizeof(int) * ((size_t)L + 1 + 3 * (size_t)E + nf + (nf + 1) + pose_edges.size() +
+  size_t gbytes = 256 * 24 + sizeof(int) * 2 * (size_t)n + sizeof(long long) * ((size_t)n + 2) + sizeof(int) * ((size_t)L + 1 + 3 * (size_t)E + nf + (nf + 1) + pose_edges.size() +
                                             2 * (size_t)n_pairs + pair_ptr.size() + 2 * pair_ea.size()) +
                   (size_t)E * (1 + 24 + 4) + (size_t)K * 20;
   if (S.graph.reserve(gbytes)) return ORB_E_CUDA;
@@ -848,10 +1119,25 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
   UPLOAD(pair_ptr, int, pair_ptr.data(), pair_ptr.size());
   UPLOAD(pair_ea, int, pair_ea.data(), pair_ea.size());
   UPLOAD(pair_eb, int, pair_eb.data(), pair_eb.size());
+  const int *d_env_first = nullptr, *d_env_reach = nullptr;
+  {
+    int* dptr = carve<int>(gp, (size_t)n);
+    CUDA_TRYL(cudaMemcpyAsync(dptr, env_first.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
+    d_env_first = dptr;
+    dptr = carve<int>(gp, (size_t)n);
+    CUDA_TRYL(cudaMemcpyAsync(dptr, env_reach.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
+    d_env_reach = dptr;
+  }
+  const long long* d_env_rowp = nullptr;
+  {
+    long long* dptr = carve<long long>(gp, (size_t)n + 2);
+    CUDA_TRYL(cudaMemcpyAsync(dptr, env_rowp.data(), sizeof(long long) * (n + 2), cudaMemcpyHostToDevice, st));
+    d_env_rowp = dptr;
+  }
 #undef UPLOAD
   const size_t nS = (size_t)(n + 1) * n;
-  size_t wbytes = 256 * 24 + sizeof(double) * (14 * (size_t)K + 6 * (size_t)L + (size_t)L * (6 + 3 + 9 + 3 + 1) +
-                                               (size_t)E * (18 + 18 + 21 + 6 + 1) + (size_t)nf * 42 + nS +
+  size_t wbytes = 256 * 32 + sizeof(double) * (14 * (size_t)K + 6 * (size_t)L + (size_t)L * (6 + 3 + 9 + 3 + 1) +
+                                               (size_t)E * (18 + 18 + 21 + 6 + 1) + (size_t)nf * 42 + nS + (S.world > 1 ? env_total : 1) +
                                                (size_t)n + 3 * (size_t)L + (size_t)nf + L + 16) + (size_t)E;
   if (S.work.reserve(wbytes)) return ORB_E_CUDA;
   uint8_t* wp = (uint8_t*)S.work.p;
@@ -865,6 +1151,7 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
   D.chi2_e = carve<double>(wp, (size_t)E + 1);
   D.Hpp = carve<double>(wp, 36 * (size_t)nf); D.bp = carve<double>(wp, 6 * (size_t)nf);
   D.S = carve<double>(wp, nS);
+  double* d_env_pack = carve<double>(wp, S.world > 1 ? env_total : 1);
   D.x = carve<double>(wp, (size_t)n + 3 * (size_t)L + 1);
   D.scale_part = carve<double>(wp, (size_t)nf + L + 1);
   D.scalars = carve<double>(wp, 16);
@@ -878,6 +1165,7 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
   CUDA_TRYL(cudaMemsetAsync(D.x, 0, sizeof(double) * ((size_t)n + 3 * (size_t)L + 1), st));
   CUDA_TRYL(cudaMemsetAsync(D.scalars, 0, sizeof(double) * 16, st));
   CUDA_TRYL(cudaMemsetAsync(D.W, 0, sizeof(double) * (18 * (size_t)E + 1), st));
+  const double ms_host_prep = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
   CUDA_TRYL(cudaEventRecord(S.ev[0], st));
   normalize_poses_kernel<<<(K + 127) / 128, 128, 0, st>>>(D);
   S.launches++;
@@ -951,13 +1239,23 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
       bschur_kernel<<<nf, 128, 0, st>>>(D);
       S.launches += 3;
       // landmark shards: every rank holds its partial H_pp, b_p and Schur terms; one sum gives (S | b_s)
-      if (S.world > 1 && (rc = allreduce(D.S, nS))) return rc;
+      if (S.world > 1) {
+        env_pack_kernel<<<n + 1, 256, 0, st>>>(D.S, n, d_env_first, d_env_rowp, d_env_pack, 0);
+        if ((rc = allreduce(d_env_pack, env_total))) return rc;
+        env_pack_kernel<<<n + 1, 256, 0, st>>>(D.S, n, d_env_first, d_env_rowp, d_env_pack, 1);
+        S.launches += 2;
+      }
       add_lambda_kernel<<<(n + 255) / 256, 256, 0, st>>>(D, lambda);
       CUDA_TRYL(cudaEventRecord(S.ev[4], st));
       // reduced solve
       CUDA_TRYL(cudaMemsetAsync(S.d_bar, 0, 256, st));
       CUDA_TRYL(cudaMemsetAsync(D.scalars + 3, 0, sizeof(double), st));
-      {
+      if (use_sky) {
+        const size_t smem = sizeof(double) * 2 * 32 * SKY_WMAX;
+        CUDA_TRYL(raise_dynamic_smem((const void*)ldlt_sky_kernel, smem, S.device));
+        ldlt_sky_kernel<<<1, SKY_THREADS, smem, st>>>(D.S, n, d_env_reach, d_env_first, D.scalars + 3, D.x);
+        S.launches += 1;
+      } else {
         double* Mp = D.S;
         int nn = n;
         unsigned* bar = S.d_bar;
@@ -967,9 +1265,10 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
         void* args[] = {&Mp, &nn, &bar, &failp, &dbg};
         const int blocks = std::min(S.ldlt_blocks, std::max(1, (n + 1 + NB - 1) / NB * ((n + 1 + NB - 1) / NB)));
         CUDA_TRYL(cudaLaunchCooperativeKernel((void*)ldlt_kernel, dim3(blocks), dim3(256), args, 0, st));
+        backsub_kernel<<<1, 1024, sizeof(double) * n, st>>>(D.S, n, D.x);
+        S.launches += 2;
       }
-      backsub_kernel<<<1, 1024, sizeof(double) * n, st>>>(D.S, n, D.x);
-      S.launches += 3;
+      S.launches += 1;
       CUDA_TRYL(cudaEventRecord(S.ev[5], st));
       // update + evaluate
       if (L) lm_update_points_kernel<<<lm_blocks, 128, 0, st>>>(D, lambda);
@@ -1038,6 +1337,10 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
     cudaEventElapsedTime(&tot, S.ev[0], S.ev[7]);
     stats->ms_total = tot; stats->ms_linearize = ms_lin; stats->ms_schur = ms_schur; stats->ms_solve = ms_solve;
     stats->ms_update = ms_upd; stats->n_free_kf = nf; stats->n_pairs = n_pairs; stats->schur_flops = schur_flops;
+    stats->solver_kind = use_sky ? 1 : 0; stats->envelope_rows_max = sky_rows_max;
+    stats->ms_host_prep = ms_host_prep;
+    stats->ms_wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
+    stats->allreduce_bytes_per_trial = S.world > 1 ? (double)env_total * sizeof(double) : 0.0;
   }
   return iters;
 }

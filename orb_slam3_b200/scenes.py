@@ -245,6 +245,19 @@ def lba_rough_graph(seed=4):
     return g, truth
 
 
+def permute_keyframes(g, perm):
+    """The same graph with its keyframes listed in another order (new index i = old keyframe perm[i]):
+    LocalBundleAdjustment collects the local keyframes from covisibility lists, not along the trajectory."""
+    perm = np.asarray(perm)
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(len(perm))
+    h = dict(g)
+    for k in ("kf_pose", "kf_fixed", "kf_cam"):
+        h[k] = np.ascontiguousarray(g[k][perm])
+    h["e_kf"] = inv[g["e_kf"]].astype(np.int32)
+    return h
+
+
 def lba_view(g):
     from .views import make_lba_graph_view
     return make_lba_graph_view(**g)

@@ -137,7 +137,9 @@ class lba_stats(C.Structure):
                 ("chi2_initial", C.c_double), ("chi2_final", C.c_double), ("lambda_final", C.c_double),
                 ("ms_total", C.c_double), ("ms_linearize", C.c_double), ("ms_schur", C.c_double),
                 ("ms_solve", C.c_double), ("ms_update", C.c_double),
-                ("n_free_kf", _i), ("n_pairs", _i), ("schur_flops", C.c_double)]
+                ("n_free_kf", _i), ("n_pairs", _i), ("schur_flops", C.c_double),
+                ("solver_kind", _i), ("envelope_rows_max", _i), ("ms_host_prep", C.c_double), ("ms_wall", C.c_double),
+                ("allreduce_bytes_per_trial", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

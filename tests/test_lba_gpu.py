@@ -65,6 +65,34 @@ def test_lba_config5_200kf_80k_landmarks(oracle, lba):
     assert np.array_equal(LBA.outliers(g, ref), LBA.outliers(g, got))
 
 
+def test_lba_envelope_solver_and_keyframe_order(oracle, lba):
+    """The reduced solve runs inside the row envelope of S (one CTA) when the window is chain-like; a shuffled
+    keyframe list is renumbered (reverse Cuthill-McKee) back to a narrow profile.  Both equal the oracle."""
+    g, _ = scenes.lba_graph(50, 4000, seed=4)
+    got = lba(scenes.lba_view(g))
+    assert got["stats"]["solver_kind"] == 1 and got["stats"]["envelope_rows_max"] <= 6 * 16 + 32
+    _compare(g, oracle.lba_solve(scenes.lba_view(g)), got, "natural order")
+    gs = scenes.permute_keyframes(g, np.random.default_rng(3).permutation(len(g["kf_fixed"])))
+    got_s = lba(scenes.lba_view(gs))
+    assert got_s["stats"]["solver_kind"] == 1 and got_s["stats"]["envelope_rows_max"] <= 6 * 24 + 32, got_s["stats"]
+    _compare(gs, oracle.lba_solve(scenes.lba_view(gs)), got_s, "shuffled keyframes")
+    # a window in which every keyframe sees every landmark: the envelope is the whole triangle (still one CTA at n = 72)
+    gd, _ = scenes.lba_graph(12, 800, seed=6)
+    rng = np.random.default_rng(0)
+    free = np.nonzero(gd["kf_fixed"] == 0)[0]
+    extra_kf = rng.choice(free, 400)
+    extra_mp = rng.integers(0, len(gd["mp_pos"]), 400)
+    pair = set(zip(gd["e_kf"].tolist(), gd["e_mp"].tolist()))
+    sel = [i for i, (k, m) in enumerate(zip(extra_kf.tolist(), extra_mp.tolist())) if (k, m) not in pair]
+    k2, m2 = extra_kf[sel].astype(np.int32), extra_mp[sel].astype(np.int32)
+    gd["e_kf"] = np.concatenate([gd["e_kf"], k2]); gd["e_mp"] = np.concatenate([gd["e_mp"], m2])
+    gd["e_stereo"] = np.concatenate([gd["e_stereo"], np.zeros(len(k2), np.uint8)])
+    gd["e_obs"] = np.concatenate([gd["e_obs"], np.column_stack([rng.uniform(100, 1100, len(k2)), rng.uniform(100, 600, len(k2)),
+                                                                -np.ones(len(k2))])])
+    gd["e_inv_sigma2"] = np.concatenate([gd["e_inv_sigma2"], np.ones(len(k2), np.float32)])
+    _compare(gd, oracle.lba_solve(scenes.lba_view(gd)), lba(scenes.lba_view(gd)), "dense coupling")
+
+
 def test_lba_rejected_trials_and_user_lambda(oracle, lba):
     g, _ = scenes.lba_rough_graph(4)
     gv = scenes.lba_view(g)
