@@ -263,7 +263,8 @@ typedef struct lba_stats {
   double ms_linearize, ms_schur, ms_solve, ms_update;   /* accumulated per stage */
   int32_t n_free_kf, n_pairs;
   double schur_flops;         /* block-sparse useful flops per trial */
-  int32_t solver_kind;        /* reduced solve: 0 = dense cooperative LDL^T (all SMs), 1 = envelope LDL^T (one CTA) */
+  int32_t solver_kind;        /* reduced solve: 0 = dense cooperative LDL^T (all SMs), 1 = envelope LDL^T, 32-column panels
+                               * (one CTA), 2 = window-resident envelope LDL^T, 8-column panels (one CTA, shared memory) */
   int32_t envelope_rows_max;  /* tallest panel window of the row envelope of S (rows) */
   double ms_host_prep;        /* host wall time before the first kernel: edge sort, CSRs, pair lists, ordering, uploads queued */
   double ms_wall;             /* host wall time of the whole call (prep + H2D + kernels + D2H + un-sort) */

@@ -691,6 +691,213 @@ __global__ void __launch_bounds__(SKY_THREADS) ldlt_sky_kernel(double* __restric
   }
 }
 
+// ---------------------------------------------------------------- window-resident envelope LDL^T
+// Third formulation of the reduced solve, for narrow envelopes (a keyframe chain: <= WIN_ROWS rows under a
+// pivot).  What bounded ldlt_sky_kernel was not arithmetic but a chain of ~1200 pivots at ~1 us each: every
+// 32-column panel paid global-memory round trips (diagonal block in, panel rows in/out, trailing tiles in/out)
+// and 64 block-wide barriers.  Here the active part of the matrix -- the rows of the envelope under the current
+// pivots, a (<= 120)^2 lower triangle -- LIVES in shared memory as a ring (row i, column j at [i % WIN][j % WIN]);
+// rows enter it once, from global memory, when the envelope first reaches them (independent loads, off the
+// critical path), are updated in place panel after panel, and leave as finished columns of L.  Panels are 8
+// columns wide: the 8x8 pivot block is factored by one thread entirely in registers (no communication on the
+// chain), the panel rows by one thread each, the rank-8 update of the window in 4x4 register micro-tiles;
+// three barriers per 8 pivots instead of 64 per 32.  The back-substitution runs in the same launch, 8 unknowns
+// per step, with the next step's rows of L already in flight.
+constexpr int WIN = 128, WIN_P = WIN + 1, WIN_ROWS = WIN - 8, WPB = 8, WIN_THREADS = 512;
+
+__global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restrict__ M, int n, const int* __restrict__ reach,
+                                                             const int* __restrict__ first, double* fail,
+                                                             double* __restrict__ x) {
+  extern __shared__ __align__(16) double win_dyn[];
+  double* A = win_dyn;                       // [WIN][WIN_P] ring of the trailing window
+  double* zr = A + WIN * WIN_P;              // [WIN] right-hand side entries of the window columns
+  double* Lt = zr + WIN;                     // [8][WIN] L   of the panel rows, m-major; slot nr = rhs row
+  double* LDt = Lt + WPB * WIN;              // [8][WIN] L*D of the panel rows
+  __shared__ double Lb[WPB][WPB];            // pivot block: strict lower = L
+  __shared__ double Dib[WPB];                // 1 / D
+  __shared__ double xb[WPB];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int loaded = 0;  // rows (and rhs columns) [0, loaded) have entered the window
+  for (int k0 = 0; k0 < n; k0 += WPB) {
+    const int nb = min(WPB, n - k0);
+    const int R = min(max(reach[k0 + nb - 1], k0 + nb - 1), n - 1);  // last row of the window
+    // ---- (0) rows entering the window: columns [k0, i], zero left of the envelope (the ring slot is stale)
+    for (int i = max(loaded, k0) + warp; i <= R; i += WIN_THREADS / 32) {
+      const int f = first[i];
+      const double* Mi = M + (size_t)i * n;
+      double* Ai = A + (i % WIN) * WIN_P;
+      for (int j = k0 + lane; j <= i; j += 32) Ai[j % WIN] = j >= f ? Mi[j] : 0.0;
+      if (lane == 0) zr[i % WIN] = M[(size_t)n * n + i];
+    }
+    loaded = max(loaded, R + 1);
+    __syncthreads();
+    // ---- (1) pivot block, one thread, registers only
+    if (tid == 0) {
+      double a[WPB][WPB];
+#pragma unroll
+      for (int r = 0; r < WPB; r++)
+#pragma unroll
+        for (int c = 0; c < WPB; c++)
+          a[r][c] = (r < nb && c <= r) ? A[((k0 + r) % WIN) * WIN_P + (k0 + c) % WIN] : (r == c ? 1.0 : 0.0);
+#pragma unroll
+      for (int k = 0; k < WPB; k++) {
+        const double d = a[k][k];
+        if (d == 0.0) *fail = 1.0;
+        double inv = (double)__frcp_rn((float)d);
+        inv = inv * (2.0 - d * inv);
+        inv = inv * (2.0 - d * inv);
+        Dib[k] = inv;
+        double l[WPB];
+#pragma unroll
+        for (int r = k + 1; r < WPB; r++) l[r] = a[r][k] * inv;
+#pragma unroll
+        for (int r = k + 1; r < WPB; r++)
+#pragma unroll
+          for (int m = k + 1; m <= r; m++) a[r][m] -= l[r] * a[m][k];
+#pragma unroll
+        for (int r = k + 1; r < WPB; r++) a[r][k] = l[r];
+      }
+#pragma unroll
+      for (int r = 0; r < WPB; r++)
+#pragma unroll
+        for (int c = 0; c < WPB; c++) {
+          Lb[r][c] = c < r ? a[r][c] : 0.0;
+          if (r < nb && c <= r) M[(size_t)(k0 + r) * n + k0 + c] = a[r][c];  // L below, D on the diagonal
+        }
+    }
+    __syncthreads();
+    // ---- (2) panel rows [k0+nb, R] and the rhs row: forward substitution, one thread per row
+    const int r0 = k0 + nb, nr = R - r0 + 1;  // nr rows under the pivot block; slot nr = rhs
+    if (tid <= nr) {
+      const bool rhs = tid == nr;
+      const int i = r0 + tid;
+      double* src = rhs ? zr : A + (i % WIN) * WIN_P;
+      double ld[WPB], l[WPB];
+#pragma unroll
+      for (int m = 0; m < WPB; m++) ld[m] = m < nb ? src[(k0 + m) % WIN] : 0.0;
+#pragma unroll
+      for (int m = 1; m < WPB; m++)
+#pragma unroll
+        for (int p2 = 0; p2 < m; p2++) ld[m] -= ld[p2] * Lb[m][p2];
+#pragma unroll
+      for (int m = 0; m < WPB; m++) {
+        l[m] = m < nb ? ld[m] * Dib[m] : 0.0;
+        Lt[m * WIN + tid] = l[m];
+        LDt[m * WIN + tid] = m < nb ? ld[m] : 0.0;
+      }
+      double* dst = M + (size_t)(rhs ? n : i) * n + k0;
+#pragma unroll
+      for (int m = 0; m < WPB; m++)
+        if (m < nb) dst[m] = l[m];
+    }
+    __syncthreads();
+    // ---- (3) rank-nb update of the window rows / columns [r0, R] (+ rhs), 4x4 micro-tiles over window slots
+    {
+      const int T = (nr + 1 + 3) >> 2;
+      const int ntile = T * (T + 1) / 2;
+      for (int t = tid; t < ntile; t += WIN_THREADS) {
+        int ti = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
+        while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
+        while (ti * (ti + 1) / 2 > t) ti--;
+        const int tj = t - ti * (ti + 1) / 2;
+        double acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+          for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
+#pragma unroll
+        for (int m = 0; m < WPB; m++) {
+          const double2 li0 = *reinterpret_cast<const double2*>(&Lt[m * WIN + 4 * ti]);
+          const double2 li1 = *reinterpret_cast<const double2*>(&Lt[m * WIN + 4 * ti + 2]);
+          const double2 lj0 = *reinterpret_cast<const double2*>(&LDt[m * WIN + 4 * tj]);
+          const double2 lj1 = *reinterpret_cast<const double2*>(&LDt[m * WIN + 4 * tj + 2]);
+          const double li[4] = {li0.x, li0.y, li1.x, li1.y}, lj[4] = {lj0.x, lj0.y, lj1.x, lj1.y};
+#pragma unroll
+          for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) acc[a][b] += li[a] * lj[b];
+        }
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+          const int wi = 4 * ti + a;
+          if (wi > nr) continue;
+          const bool rhs = wi == nr;
+          double* row = rhs ? zr : A + ((r0 + wi) % WIN) * WIN_P;
+#pragma unroll
+          for (int b = 0; b < 4; b++) {
+            const int wj = 4 * tj + b;
+            if (wj >= nr || wj > wi) continue;  // the rhs row has no column of its own; lower triangle only
+            row[(r0 + wj) % WIN] -= acc[a][b];
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // ---- L^T x = z (z = row n of M, already scaled by 1/D).  8 unknowns per step; a thread owns a column of
+  //      the step's window and has the next step's 8 entries of L in flight while this step is solved.
+  double* acc = A;  // n <= WIN * WIN_P (host-checked)
+  for (int i = tid; i < n; i += WIN_THREADS) acc[i] = M[(size_t)n * n + i];
+  const int nblk = (n + WPB - 1) / WPB;
+  auto jmin_of = [&](int b) {
+    const int k0 = b * WPB, nb = min(WPB, n - k0);
+    int jm = k0;
+    for (int r = 0; r < nb; r++) jm = min(jm, first[k0 + r]);
+    return jm;
+  };
+  double nxt[WPB];
+  int jm_next = nblk > 0 ? jmin_of(nblk - 1) : 0;
+  {
+    const int k0 = (nblk - 1) * WPB, nb = min(WPB, n - k0), j = jm_next + tid;
+#pragma unroll
+    for (int r = 0; r < WPB; r++) nxt[r] = (r < nb && j < k0 + r) ? M[(size_t)(k0 + r) * n + j] : 0.0;
+  }
+  __syncthreads();
+  for (int b = nblk - 1; b >= 0; b--) {
+    const int k0 = b * WPB, nb = min(WPB, n - k0), jm = jm_next;
+    double cur[WPB];
+#pragma unroll
+    for (int r = 0; r < WPB; r++) cur[r] = nxt[r];
+    if (b > 0) {  // next step's loads: independent of everything below
+      jm_next = jmin_of(b - 1);
+      const int k1 = k0 - WPB, j = jm_next + tid;
+#pragma unroll
+      for (int r = 0; r < WPB; r++) nxt[r] = (j < k1 + r) ? M[(size_t)(k1 + r) * n + j] : 0.0;
+    }
+    // in-block solve: the thread that owns column k0 + c holds L[k0+r][k0+c] in cur[r]; gather them first
+    if (tid >= k0 - jm && tid < k0 - jm + nb) {
+      const int c = tid - (k0 - jm);
+#pragma unroll
+      for (int r = 0; r < WPB; r++) Lb[r][c] = r > c ? cur[r] : 0.0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double v[WPB];
+#pragma unroll
+      for (int r = 0; r < WPB; r++) v[r] = r < nb ? acc[k0 + r] : 0.0;
+#pragma unroll
+      for (int c = WPB - 1; c >= 0; c--)
+#pragma unroll
+        for (int r = 0; r < c; r++) v[r] -= Lb[c][r] * v[c];
+#pragma unroll
+      for (int r = 0; r < WPB; r++)
+        if (r < nb) { xb[r] = v[r]; x[k0 + r] = v[r]; }
+    }
+    __syncthreads();
+    {
+      const int j = jm + tid;
+      if (j < k0) {
+        double sdot = 0;
+#pragma unroll
+        for (int r = 0; r < WPB; r++)
+          if (r < nb) sdot += cur[r] * xb[r];
+        acc[j] -= sdot;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // x_l = D^-1 (b_l - W^T x_p); scale terms x.(lambda x + b); backup + update points.
 __global__ void __launch_bounds__(128) lm_update_points_kernel(LbaDev D, double lambda) {
   const int l = blockIdx.x * 128 + threadIdx.x;
@@ -1084,10 +1291,20 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
     sky_rows_max = std::max(sky_rows_max, std::max(nw, k0 - jmin));
     sky_flops += (double)nw * nw * nb;
   }
-  static const char* ldlt_env = getenv("ORB_B200_LDLT");  // "dense" | "sky" | unset = automatic
+  int win_rows_max = 0;  // 8-column panels of the window-resident kernel
+  for (int k0 = 0; k0 < n; k0 += WPB) {
+    const int nb = std::min(WPB, n - k0);
+    const int R = std::min(std::max(env_reach[k0 + nb - 1], k0 + nb - 1), n - 1);
+    int jmin = k0;
+    for (int r = 0; r < nb; r++) jmin = std::min(jmin, env_first[k0 + r]);
+    win_rows_max = std::max(win_rows_max, std::max(R - k0 + 1, k0 - jmin + nb));
+  }
+  const bool win_ok = win_rows_max <= WIN_ROWS && n <= WIN * WIN_P;
+  static const char* ldlt_env = getenv("ORB_B200_LDLT");  // "dense" | "sky" | "win" | unset = automatic
   bool use_sky = sky_rows_max <= SKY_WMAX - 4 && n <= 32 * SKY_WMAX && sky_flops <= 6.0e7;
   if (ldlt_env && !strcmp(ldlt_env, "dense")) use_sky = false;
   if (ldlt_env && !strcmp(ldlt_env, "sky")) use_sky = sky_rows_max <= SKY_WMAX - 4 && n <= 32 * SKY_WMAX;
+  bool use_win = win_ok && !(ldlt_env && (!strcmp(ldlt_env, "sky") || !strcmp(ldlt_env, "dense")));
   // ---- device memory
   size_t gbytes = 256 * 24 + sizeof(int) * 2 * (size_t)n + sizeof(long long) * ((size_t)n + 2) + sizeof(int) * ((size_t)L + 1 + 3 * (size_t)E + nf + (nf + 1) + pose_edges.size() +
                                             2 * (size_t)n_pairs + pair_ptr.size() + 2 * pair_ea.size()) +
@@ -1250,7 +1467,12 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
       // reduced solve
       CUDA_TRYL(cudaMemsetAsync(S.d_bar, 0, 256, st));
       CUDA_TRYL(cudaMemsetAsync(D.scalars + 3, 0, sizeof(double), st));
-      if (use_sky) {
+      if (use_win) {
+        const size_t smem = sizeof(double) * (WIN * WIN_P + WIN + 2 * WPB * WIN);
+        CUDA_TRYL(raise_dynamic_smem((const void*)ldlt_win_kernel, smem, S.device));
+        ldlt_win_kernel<<<1, WIN_THREADS, smem, st>>>(D.S, n, d_env_reach, d_env_first, D.scalars + 3, D.x);
+        S.launches += 1;
+      } else if (use_sky) {
         const size_t smem = sizeof(double) * 2 * 32 * SKY_WMAX;
         CUDA_TRYL(raise_dynamic_smem((const void*)ldlt_sky_kernel, smem, S.device));
         ldlt_sky_kernel<<<1, SKY_THREADS, smem, st>>>(D.S, n, d_env_reach, d_env_first, D.scalars + 3, D.x);
@@ -1337,7 +1559,7 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
     cudaEventElapsedTime(&tot, S.ev[0], S.ev[7]);
     stats->ms_total = tot; stats->ms_linearize = ms_lin; stats->ms_schur = ms_schur; stats->ms_solve = ms_solve;
     stats->ms_update = ms_upd; stats->n_free_kf = nf; stats->n_pairs = n_pairs; stats->schur_flops = schur_flops;
-    stats->solver_kind = use_sky ? 1 : 0; stats->envelope_rows_max = sky_rows_max;
+    stats->solver_kind = use_win ? 2 : (use_sky ? 1 : 0); stats->envelope_rows_max = use_win ? win_rows_max : sky_rows_max;
     stats->ms_host_prep = ms_host_prep;
     stats->ms_wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
     stats->allreduce_bytes_per_trial = S.world > 1 ? (double)env_total * sizeof(double) : 0.0;

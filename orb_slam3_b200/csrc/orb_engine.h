@@ -119,7 +119,12 @@ struct Engine {
   int extract_batch_device(int batch, const uint8_t* d_imgs, size_t frame_stride, int rows, int cols, size_t step,
                            const int* lap, cudaStream_t user);
   LevelTensorMaps* tmaps = nullptr;  // host copy of the per-level TMA descriptors
-  void* d_tmaps_raw = nullptr;       // device copy read by cp.async.bulk.tensor
+  void* d_tmaps_raw = nullptr;       // device copy read by cp.async.bulk.tensor (first 16: CTA-per-cell boxes,
+                                     // next 16: the warp-per-cell boxes)
+  // warp-per-cell FAST (fast_warp_kernel): tile / score map / queue geometry, persistent grid size
+  int fw_tile_pitch = 0, fw_tile_rows = 0, fw_smap_pitch = 0, fw_smap_bytes = 0, fw_queue_cap = 0, fw_per_warp = 0;
+  int fw_grid = 0;
+  bool fw_enabled = false;
   int encode_tensor_maps(int batch);
   int l2_chunk_frames(int batch) const;
   int fetch_pyramid();

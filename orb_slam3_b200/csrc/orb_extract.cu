@@ -154,7 +154,8 @@ constexpr int FAST_TILE_PITCH = 96;  // TMA box columns (bytes): (x0 & 15) + wCe
 constexpr int FAST_BAND_MAX = 70;
 
 struct LevelTensorMaps {
-  CUtensorMap m[16];  // one 3-D (x, y, frame) uint8 map per pyramid level
+  CUtensorMap m[32];  // one 3-D (x, y, frame) uint8 map per pyramid level: [0,16) box of fast_cells_kernel,
+                      // [16,32) box of fast_warp_kernel
 };
 
 __global__ void __launch_bounds__(FAST_THREADS)
@@ -333,6 +334,219 @@ fast_cells_kernel(const CUtensorMap* __restrict__ maps, int frame0,
       c.score = (uint32_t)(smap[(y + 1) * sw + x + 1] - 1);
       out[pos] = c;
     }
+  }
+}
+
+// ---- FAST, second formulation: ONE WARP PER CELL, persistent, TMA ring ----------------------------------------
+// Same per-cell semantics as fast_cells_kernel above, reorganised around what the profile of that kernel showed
+// (profiles/r1_fast_breakdown.md): a quarter of its stall samples sat in a prologue that waits for the CTA's own
+// tile, a fifth of its instructions were a block-wide scan with two barriers per pass, and its packed `d > t`
+// compare cost five instructions.  Here every warp owns a cell at a time and walks the (cell, frame) list with
+// stride = warps in the grid; the tile of its NEXT cell is already in flight (cp.async.bulk.tensor into the other
+// half of a two-slot ring, one mbarrier per slot) while it works on the current one; all hand-offs inside the
+// cell are warp-synchronous (ballot / shuffle prefix sums, __syncwarp) -- there is no __syncthreads in the
+// kernel; the packed threshold test is ((d & 0x7f..) + K | d) on the byte MSBs (3 instructions per sample).
+// The box starts at the 4-byte aligned column left of the cell, so its row pitch is 48 bytes at 1280x720
+// (2.1 KB per cell instead of 7.3 KB through L2) and the three rows a warp touches per load instruction fall
+// into different shared-memory banks.
+struct FastGeom {
+  int tile_pitch, tile_rows, tile_bytes;  // TMA box = tile_pitch x tile_rows bytes (pitch multiple of 16)
+  int smap_pitch, smap_bytes;             // score map with a one-pixel zero frame
+  int queue_cap;                          // pre-test survivors of one cell (<= band pixels)
+  int per_warp_bytes;
+};
+constexpr int FASTW_WARPS = 8;
+
+__device__ __forceinline__ uint32_t fast_gt4_msb(uint32_t d, uint32_t K, bool hi) {
+  // byte-wise d > t, result in bit 7 of every byte (other bits are garbage): t < 128: ((d & 0x7f) + 127 - t) | d,
+  // t >= 128: ((d & 0x7f) + 255 - t) & d
+  const uint32_t s = (d & 0x7f7f7f7fu) + K;
+  return hi ? (s & d) : (s | d);
+}
+
+__global__ void __launch_bounds__(FASTW_WARPS * 32)
+fast_warp_kernel(const CUtensorMap* __restrict__ maps, int frame0, int nframes, const CellDesc* __restrict__ cells,
+                 int num_cells, const LevelDev* __restrict__ lv, int ini_th, int min_th, Cand* __restrict__ cand,
+                 size_t cand_frame_stride, int* __restrict__ cand_count, int nlevels, FastGeom G) {
+  extern __shared__ __align__(128) uint8_t fw_dyn[];
+  __shared__ __align__(8) unsigned long long bars[FASTW_WARPS][2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint8_t* wbase = fw_dyn + (size_t)warp * G.per_warp_bytes;
+  uint8_t* smap = wbase + 2 * G.tile_bytes;
+  unsigned short* queue = reinterpret_cast<unsigned short*>(smap + G.smap_bytes);
+  const unsigned bar0 = (unsigned)__cvta_generic_to_shared(&bars[warp][0]);
+  const unsigned tile0 = (unsigned)__cvta_generic_to_shared(wbase);
+  const int SW = G.smap_pitch, TP = G.tile_pitch;
+  const long long total = (long long)num_cells * nframes;
+  const long long gw = (long long)blockIdx.x * FASTW_WARPS + warp, NW = (long long)gridDim.x * FASTW_WARPS;
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  for (int i = lane; i < G.smap_bytes / 4; i += 32) reinterpret_cast<uint32_t*>(smap)[i] = 0;
+  __syncwarp();
+  auto issue = [&](long long item, int slot) {  // lane 0 only
+    const int f = (int)(item / num_cells), c = (int)(item - (long long)f * num_cells);
+    const CellDesc cd = cells[c];
+    const unsigned bar = bar0 + 8 * slot, dst = tile0 + slot * G.tile_bytes;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(G.tile_bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(maps + cd.level), "r"(bar), "r"(cd.x0 & ~3), "r"(cd.y0), "r"(frame0 + f)
+        : "memory");
+  };
+  if (gw < total && lane == 0) issue(gw, 0);
+  const uint32_t hi_ini = ini_th >= 128, hi_min = min_th >= 128;
+  const uint32_t K_ini = 0x01010101u * (uint32_t)(hi_ini ? 255 - ini_th : 127 - ini_th);
+  const uint32_t K_min = 0x01010101u * (uint32_t)(hi_min ? 255 - min_th : 127 - min_th);
+  int n = 0;
+  for (long long item = gw; item < total; item += NW, n++) {
+    const int slot = n & 1;
+    // the other slot was read during the previous iteration; every lane is past it (the __syncwarp that ends
+    // an iteration), so its refill can start now and overlaps this whole cell
+    if (item + NW < total && lane == 0) issue(item + NW, slot ^ 1);
+    {
+      const unsigned bar = bar0 + 8 * slot, parity = (unsigned)(n >> 1) & 1u;
+      unsigned done = 0;
+      while (!done) {
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+      }
+    }
+    const int f = (int)(item / num_cells), ci = (int)(item - (long long)f * num_cells);
+    const CellDesc cd = cells[ci];
+    const uint8_t* tile = wbase + slot * G.tile_bytes;
+    const int bw = cd.x1 - cd.x0 - 6, bh = cd.y1 - cd.y0 - 6;
+    if (bw > 0 && bh > 0) {
+      const int ox = cd.x0 & 3;
+      // 4-pixel groups = aligned words of a tile row that overlap the band columns [ox+3, ox+3+bw)
+      const int g0 = (ox + 3) >> 2, ng = ((ox + 3 + bw + 3) >> 2) - g0;
+      const int nitems = bh * ng;
+      const unsigned magic_g = ((1u << 20) + ng - 1) / ng;  // idx / ng for idx < 2^20 / ng
+      const uint32_t* tw32 = reinterpret_cast<const uint32_t*>(tile);
+      const int PWD = TP >> 2;
+      int qn = 0, total_keep = 0;
+      for (int pass = 0; pass < 2; pass++) {
+        const int th_fast = pass == 0 ? ini_th : min_th;
+        const uint32_t K = pass == 0 ? K_ini : K_min;
+        const bool hi = pass == 0 ? hi_ini : hi_min;
+        qn = 0;
+        // 2. packed 4-diameter rejection test, 16 visits (512 groups) per chunk, survivors appended to the queue
+        for (int base = 0; base < nitems; base += 512) {
+          unsigned long long pass_bits = 0;
+#pragma unroll 2
+          for (int it = 0; it < 16; it++) {
+            const int idx = base + it * 32 + lane;
+            if (idx >= nitems) break;
+            const int y = (int)(((unsigned)idx * magic_g) >> 20), g = g0 + (idx - y * ng);
+            const uint32_t* rc = tw32 + (y + 3) * PWD + g;
+            const uint32_t v = rc[0];
+            const uint32_t r0 = rc[3 * PWD], r8 = rc[-3 * PWD];
+            const uint32_t r4 = __funnelshift_r(rc[0], rc[1], 24), r12 = __funnelshift_r(rc[-1], rc[0], 8);
+            const uint32_t* rp = rc + 2 * PWD;
+            const uint32_t* rm = rc - 2 * PWD;
+            const uint32_t r2 = __funnelshift_r(rp[0], rp[1], 16), r14 = __funnelshift_r(rp[-1], rp[0], 16);
+            const uint32_t r6 = __funnelshift_r(rm[0], rm[1], 16), r10 = __funnelshift_r(rm[-1], rm[0], 16);
+            uint32_t m = fast_gt4_msb(__vabsdiffu4(r0, v), K, hi) | fast_gt4_msb(__vabsdiffu4(r8, v), K, hi);
+            m &= fast_gt4_msb(__vabsdiffu4(r4, v), K, hi) | fast_gt4_msb(__vabsdiffu4(r12, v), K, hi);
+            m &= fast_gt4_msb(__vabsdiffu4(r2, v), K, hi) | fast_gt4_msb(__vabsdiffu4(r10, v), K, hi);
+            m &= fast_gt4_msb(__vabsdiffu4(r6, v), K, hi) | fast_gt4_msb(__vabsdiffu4(r14, v), K, hi);
+            m &= 0x80808080u;
+            if (m) {
+              unsigned nib = ((m >> 7) & 1u) | ((m >> 14) & 2u) | ((m >> 21) & 4u) | ((m >> 28) & 8u);
+              const int c0 = 4 * g - (ox + 3);  // band x of byte 0; keep bytes whose column lies inside the band
+              if (c0 < 0) nib &= ~((1u << (-c0)) - 1u);
+              if (c0 + 3 >= bw) nib &= (1u << max(bw - c0, 0)) - 1u;
+              pass_bits |= (unsigned long long)nib << (4 * it);
+            }
+          }
+          const int cnt = __popcll(pass_bits);
+          int incl = cnt;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+          }
+          int qpos = qn + incl - cnt;
+          qn += __shfl_sync(0xffffffffu, incl, 31);
+          while (pass_bits) {
+            const int bit = __ffsll((long long)pass_bits) - 1;
+            pass_bits &= pass_bits - 1;
+            const int idx = base + (bit >> 2) * 32 + lane;
+            const int y = (int)(((unsigned)idx * magic_g) >> 20), g = g0 + (idx - y * ng);
+            const int x = 4 * g + (bit & 3) - (ox + 3);
+            queue[qpos++] = (unsigned short)((y << 7) | x);
+          }
+        }
+        __syncwarp();
+        // 3. exact segment test + score of the queued pixels on dense lanes
+        for (int q = lane; q < qn; q += 32) {
+          const int e = queue[q], y = e >> 7, x = e & 127;
+          const int best = fast_best(&tile[(y + 3) * TP + ox + x + 3], TP, th_fast);
+          smap[(y + 1) * SW + x + 1] = (uint8_t)best;
+        }
+        __syncwarp();
+        // 4. strict 3x3 NMS; survivors are marked in bit 15 of their queue entry
+        total_keep = 0;
+        for (int q0 = 0; q0 < qn; q0 += 32) {
+          const int q = q0 + lane;
+          bool keep = false;
+          if (q < qn) {
+            const int e = queue[q], y = e >> 7, x = e & 127;
+            const uint8_t* p = &smap[(y + 1) * SW + x + 1];
+            const int sc = p[0];
+            keep = sc && sc > p[-1] && sc > p[1] && sc > p[-SW - 1] && sc > p[-SW] && sc > p[-SW + 1] &&
+                   sc > p[SW - 1] && sc > p[SW] && sc > p[SW + 1];
+            if (keep) queue[q] = (unsigned short)(e | 0x8000);
+          }
+          total_keep += __popc(__ballot_sync(0xffffffffu, keep));
+        }
+        if (total_keep > 0 || ini_th == min_th || pass == 1) break;
+        // empty at iniTh (ORBextractor.cc:843-846): forget this pass' scores, try again at minTh
+        for (int q = lane; q < qn; q += 32) {
+          const int e = queue[q];
+          smap[((e >> 7) + 1) * SW + (e & 127) + 1] = 0;
+        }
+        __syncwarp();
+      }
+      if (total_keep > 0) {
+        const LevelDev L = lv[cd.level];
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&cand_count[f * nlevels + cd.level], total_keep);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        Cand* out = cand + (size_t)f * cand_frame_stride + L.cand_off;
+        for (int q0 = 0; q0 < qn; q0 += 32) {
+          const int q = q0 + lane;
+          const int e = q < qn ? queue[q] : 0;
+          const bool keep = (e & 0x8000) != 0;
+          const unsigned bal = __ballot_sync(0xffffffffu, keep);
+          if (keep) {
+            const int y = (e >> 7) & 127, x = e & 127;
+            const int pos = base + __popc(bal & ((1u << lane) - 1u));
+            if (pos < L.cand_cap) {
+              Cand c;
+              c.xy = (uint32_t)(x + 3 + cd.shift_x) | ((uint32_t)(y + 3 + cd.shift_y) << 16);
+              c.score = (uint32_t)(smap[(y + 1) * SW + x + 1] - 1);
+              out[pos] = c;
+            }
+          }
+          base += __popc(bal);
+        }
+      }
+      // the score map goes back to all-zero for the next cell: only the entries this cell wrote
+      __syncwarp();
+      for (int q = lane; q < qn; q += 32) {
+        const int e = queue[q];
+        smap[(((e >> 7) & 127) + 1) * SW + (e & 127) + 1] = 0;
+      }
+    }
+    __syncwarp();
   }
 }
 
@@ -913,6 +1127,29 @@ int Engine::ensure(int rows, int cols, int batch) {
   for (int l = 0; l < nlevels; l++)
     for (int i = 0; i < levels[l].oct.node_cap; i++) warp_level[levels[l].sel_off + i] = l;
 
+  {
+    // warp-per-cell FAST geometry: box = (3 + widest cell + 6, rounded to 16) x (tallest cell + 6)
+    int max_tw = 0, max_th = 0;
+    for (const CellDesc& c : cells) { max_tw = std::max(max_tw, c.x1 - c.x0); max_th = std::max(max_th, c.y1 - c.y0); }
+    fw_tile_pitch = (int)align_up(3 + max_tw, 16);
+    fw_tile_rows = (int)align_up(max_th, 8);  // pitch % 16 == 0 and rows % 8 == 0: every slot is 128-byte aligned for TMA
+    fw_smap_pitch = max_tw - 6 + 2;
+    fw_smap_bytes = (int)align_up((size_t)fw_smap_pitch * (max_th - 6 + 2) + 4, 16);
+    fw_queue_cap = (max_tw - 6) * (max_th - 6);
+    const int tile_bytes = (int)align_up((size_t)fw_tile_pitch * fw_tile_rows, 128);
+    fw_per_warp = (int)align_up((size_t)2 * tile_bytes + fw_smap_bytes + 2 * (size_t)fw_queue_cap, 128);
+    const size_t smem = (size_t)fw_per_warp * FASTW_WARPS;
+    const char* env = getenv("ORB_B200_FAST");  // "cta": the CTA-per-cell kernel
+    fw_enabled = !(env && !strcmp(env, "cta")) && fw_tile_pitch <= 256 && fw_tile_rows <= 256 && smem <= 200 * 1024 &&
+                 max_tw - 6 <= 127 && max_th - 6 <= 127 && (size_t)fw_tile_pitch * fw_tile_rows == (size_t)tile_bytes;
+    if (fw_enabled) {
+      CUDA_TRY(raise_dynamic_smem((const void*)fast_warp_kernel, smem, device));
+      int per_sm = 0, sms = 0;
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fast_warp_kernel, FASTW_WARPS * 32, smem));
+      CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+      fw_grid = sms * std::max(per_sm, 1);
+    }
+  }
   const size_t B = batch;
   if (dalloc(&d_pyr, pyr_frame_bytes * B)) return ORB_E_CUDA;
   if (dalloc(&d_blur, pyr_frame_bytes * B + 256)) return ORB_E_CUDA;
@@ -1040,8 +1277,19 @@ int Engine::run_device(int f0, int batch, const int* lap_host, cudaStream_t s) {
   // 2. FAST cells
   stage_begin(2, s);
   CUDA_TRY(cudaMemsetAsync(cand_count, 0, sizeof(int) * nlevels * B, s));
-  fast_cells_kernel<<<dim3(num_cells, B), FAST_THREADS, 0, s>>>((const CUtensorMap*)d_tmaps_raw, f0, d_cells, d_levels, ini_th, min_th, cand,
-                                                                cand_frame_elems, cand_count, nlevels);
+  if (fw_enabled) {
+    FastGeom G;
+    G.tile_pitch = fw_tile_pitch; G.tile_rows = fw_tile_rows; G.tile_bytes = fw_tile_pitch * fw_tile_rows;
+    G.smap_pitch = fw_smap_pitch; G.smap_bytes = fw_smap_bytes; G.queue_cap = fw_queue_cap; G.per_warp_bytes = fw_per_warp;
+    const long long items = (long long)num_cells * B;
+    const int grid = (int)std::min<long long>(fw_grid, (items + FASTW_WARPS - 1) / FASTW_WARPS);
+    fast_warp_kernel<<<grid, FASTW_WARPS * 32, (size_t)fw_per_warp * FASTW_WARPS, s>>>(
+        (const CUtensorMap*)d_tmaps_raw + 16, f0, B, d_cells, num_cells, d_levels, ini_th, min_th, cand, cand_frame_elems,
+        cand_count, nlevels, G);
+  } else {
+    fast_cells_kernel<<<dim3(num_cells, B), FAST_THREADS, 0, s>>>((const CUtensorMap*)d_tmaps_raw, f0, d_cells, d_levels, ini_th, min_th, cand,
+                                                                  cand_frame_elems, cand_count, nlevels);
+  }
   stage_end(2, s, 1);
   // 3. octree
   stage_begin(3, s);
@@ -1201,6 +1449,13 @@ int Engine::encode_tensor_maps(int batch) {
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled failed, level " + std::to_string(l) + " rc " + std::to_string((int)r)); return ORB_E_CUDA; }
+    if (fw_enabled) {
+      const cuuint32_t box2[3] = {(cuuint32_t)fw_tile_pitch, (cuuint32_t)fw_tile_rows, 1};
+      r = ((EncodeFn)fn)(&tmaps->m[16 + l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, d_pyr + L.img_off, dims, strides, box2, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled (warp box) failed, level " + std::to_string(l) + " rc " + std::to_string((int)r)); return ORB_E_CUDA; }
+    }
   }
   // the descriptors live in global memory (cudaMalloc is 256-byte aligned; TMA needs 64)
   {

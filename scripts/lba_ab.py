@@ -31,7 +31,7 @@ cfgs = [(50, 20000), (200, 80000)]
 if len(sys.argv) > 2:
     cfgs = [(int(sys.argv[i]), int(sys.argv[i + 1])) for i in range(1, len(sys.argv) - 1, 2)]
 for K, L in cfgs:
-    for mode, shuffle in (("dense", 0), ("sky", 0), ("auto", 1)):
+    for mode, shuffle in (("dense", 0), ("sky", 0), ("win", 0), ("auto", 1)):
         env = dict(os.environ)
         if mode != "auto":
             env["ORB_B200_LDLT"] = mode
