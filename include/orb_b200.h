@@ -294,6 +294,9 @@ int lba_solve(lba_solver* s, const lba_graph_view* g, const volatile uint8_t* st
               double lambda_init, double* kf_pose_out, double* mp_pos_out, double* chi2_out,
               uint8_t* depth_pos_out, lba_stats* stats);
 long long lba_kernel_launches(const lba_solver* s);
+/* Measurement helper: dense fp64 tensor-pipe peak (DMMA m8n8k4 issued from registers by a full grid, best of
+ * `reps` launches, CUDA events) in TFLOP/s -- the denominator of the Schur roofline in bench.py. */
+int lba_measure_fp64_mma_peak(int device, int reps, double* tflops_out);
 
 /* ------------------------------------------------------------------------
  * void Frame::ComputeStereoMatches() (src/Frame.cc:811-981), SURVEY.md 8(f-1).

@@ -1001,6 +1001,60 @@ __global__ void depth_kernel(LbaDev D, uint8_t* out) {
   out[e] = (Xc[2] + P[6]) > 0.0;
 }
 
+// ------------------------------------------------------------------- fp64 tensor-pipe peak (measurement)
+// The denominator of the Schur roofline ("record the fp64 peak measured the same way" as
+// MEASURED_PEAKS.json): every warp of a full grid issues independent DMMA m8n8k4 chains from registers, best of
+// `reps` launches between CUDA events.  2 * 8 * 8 * 4 = 512 flop per instruction.
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) {
+  double c[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { c[i][0] = 0.0; c[i][1] = 0.0; }
+  const double a = 1.0 + 1e-9 * threadIdx.x, b = 1.0 - 1e-9 * threadIdx.x;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                   : "+d"(c[i][0]), "+d"(c[i][1])
+                   : "d"(a), "d"(b));
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += c[i][0] + c[i][1];
+  if (s == 12345.678) out[0] = s;  // keep the chains alive
+}
+
+int measure_fp64_mma_peak(int device, int reps, double* tflops_out) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_last_error("no CUDA device: orb_slam3_b200 has no CPU path");
+    return ORB_E_NODEVICE;
+  }
+  CUDA_TRYL(cudaSetDevice(device));
+  int sms = 0;
+  CUDA_TRYL(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  double* d = nullptr;
+  CUDA_TRYL(cudaMalloc(&d, 64));
+  cudaEvent_t e0, e1;
+  CUDA_TRYL(cudaEventCreate(&e0));
+  CUDA_TRYL(cudaEventCreate(&e1));
+  const int iters = 20000, grid = sms * 8;
+  double best = 0;
+  for (int r = 0; r < reps + 2; r++) {
+    cudaEventRecord(e0);
+    dmma_peak_kernel<<<grid, 256>>>(d, iters);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double tf = 512.0 * 8 * iters * (256 / 32) * (double)grid / (ms * 1e-3) / 1e12;
+    if (r >= 2) best = std::max(best, tf);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  CUDA_TRYL(cudaGetLastError());
+  *tflops_out = best;
+  return 0;
+}
+
 // ------------------------------------------------------------------- NCCL (dlopen)
 struct Uid { char internal[128]; };
 struct Nccl {
@@ -1623,5 +1677,10 @@ int lba_solve(lba_solver* s, const lba_graph_view* g, const volatile uint8_t* st
 }
 
 long long lba_kernel_launches(const lba_solver* s) { return s ? s->s.launches : 0; }
+
+int lba_measure_fp64_mma_peak(int device, int reps, double* tflops_out) {
+  if (!tflops_out || reps < 1) return ORB_E_ARG;
+  return orbb200::measure_fp64_mma_peak(device, reps, tflops_out);
+}
 
 }  // extern "C"

@@ -354,6 +354,7 @@ struct FastGeom {
   int smap_pitch, smap_bytes;             // score map with a one-pixel zero frame
   int queue_cap;                          // pre-test survivors of one cell (<= band pixels)
   int per_warp_bytes;
+  int align_mask;                         // the box starts at x0 & ~align_mask (3 or 15)
 };
 constexpr int FASTW_WARPS = 8;
 
@@ -393,7 +394,7 @@ fast_warp_kernel(const CUtensorMap* __restrict__ maps, int frame0, int nframes, 
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(G.tile_bytes) : "memory");
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(dst), "l"(maps + cd.level), "r"(bar), "r"(cd.x0 & ~3), "r"(cd.y0), "r"(frame0 + f)
+        ::"r"(dst), "l"(maps + cd.level), "r"(bar), "r"(cd.x0 & ~G.align_mask), "r"(cd.y0), "r"(frame0 + f)
         : "memory");
   };
   if (gw < total && lane == 0) issue(gw, 0);
@@ -424,7 +425,7 @@ fast_warp_kernel(const CUtensorMap* __restrict__ maps, int frame0, int nframes, 
     const uint8_t* tile = wbase + slot * G.tile_bytes;
     const int bw = cd.x1 - cd.x0 - 6, bh = cd.y1 - cd.y0 - 6;
     if (bw > 0 && bh > 0) {
-      const int ox = cd.x0 & 3;
+      const int ox = cd.x0 & G.align_mask;
       // 4-pixel groups = aligned words of a tile row that overlap the band columns [ox+3, ox+3+bw)
       const int g0 = (ox + 3) >> 2, ng = ((ox + 3 + bw + 3) >> 2) - g0;
       const int nitems = bh * ng;
@@ -1131,7 +1132,9 @@ int Engine::ensure(int rows, int cols, int batch) {
     // warp-per-cell FAST geometry: box = (3 + widest cell + 6, rounded to 16) x (tallest cell + 6)
     int max_tw = 0, max_th = 0;
     for (const CellDesc& c : cells) { max_tw = std::max(max_tw, c.x1 - c.x0); max_th = std::max(max_th, c.y1 - c.y0); }
-    fw_tile_pitch = (int)align_up(3 + max_tw, 16);
+    const char* al = getenv("ORB_B200_FAST_ALIGN");  // 4: box starts at the 4-byte aligned column (48-byte rows at 720p)
+    fw_align_mask = (al && atoi(al) == 4) ? 3 : 15;
+    fw_tile_pitch = (int)align_up(fw_align_mask + max_tw, 16);
     fw_tile_rows = (int)align_up(max_th, 8);  // pitch % 16 == 0 and rows % 8 == 0: every slot is 128-byte aligned for TMA
     fw_smap_pitch = max_tw - 6 + 2;
     fw_smap_bytes = (int)align_up((size_t)fw_smap_pitch * (max_th - 6 + 2) + 4, 16);
@@ -1281,6 +1284,7 @@ int Engine::run_device(int f0, int batch, const int* lap_host, cudaStream_t s) {
     FastGeom G;
     G.tile_pitch = fw_tile_pitch; G.tile_rows = fw_tile_rows; G.tile_bytes = fw_tile_pitch * fw_tile_rows;
     G.smap_pitch = fw_smap_pitch; G.smap_bytes = fw_smap_bytes; G.queue_cap = fw_queue_cap; G.per_warp_bytes = fw_per_warp;
+    G.align_mask = fw_align_mask;
     const long long items = (long long)num_cells * B;
     const int grid = (int)std::min<long long>(fw_grid, (items + FASTW_WARPS - 1) / FASTW_WARPS);
     fast_warp_kernel<<<grid, FASTW_WARPS * 32, (size_t)fw_per_warp * FASTW_WARPS, s>>>(
