@@ -51,6 +51,23 @@ def level_pixels():
     return [int(np.rint(np.float32(W) * s)) * int(np.rint(np.float32(H) * s)) for s in inv]
 
 
+N_STREAMS, STREAM_LEN = 8, 32      # 8 camera streams x 32 frames = 256 distinct frames (+ the 8 stream heads)
+
+
+def make_streams(rank, n_streams=N_STREAMS, length=STREAM_LEN):
+    """stream s of this rank = synth frame seed 1000*(rank*n_streams+s), then `length` frames each the
+    previous one shifted by (dx,dy) in [-8,8]^2.  Returns (frames[n_streams*(length+1)], shifts, index of the
+    predecessor of every frame or -1 for a stream head)."""
+    frames, shifts, prev = [], [], []
+    for s in range(n_streams):
+        f, sh = make_frames(length + 1, 1000 * (rank * n_streams + s) + 1)
+        base = len(frames)
+        frames.extend(f)
+        shifts.extend(sh)
+        prev.extend([-1] + [base + t - 1 for t in range(1, length + 1)])
+    return np.stack(frames), shifts, prev
+
+
 def make_frames(n, seed0):
     """A synthetic stream: frame t+1 = frame t shifted by (dx,dy) in [-8,8]^2."""
     from orb_slam3_b200.synth import synth_frame, shifted_frame
@@ -136,11 +153,25 @@ class ClockSampler(threading.Thread):
 
 
 # --------------------------------------------------------------------------- CPU arm
-def cpu_extract_fps(frames, threads, seconds_budget):
+def cpu_extractor():
+    """(extract_throughput(frames, nfeatures, threads, iters) -> (fps, done, seconds), kind).  kind "reference": the
+    reference's own ORBextractor.cc as object code (oracle/_ref, built in the container that has /root/reference and
+    shipped prebuilt) over cv2-pinned image primitives; "port": the restated oracle when that library is absent."""
     from oracle import oracle as O
-    fps1, _, _ = O.extract_throughput(frames, NFEAT, 1, 2)
+    from oracle import ref as R
+    if os.path.exists(R.LIB_PATH):
+        def thr(frames, nfeatures, threads, iters):
+            dt, _ = R.extract_throughput(frames, nfeatures, threads, iters)
+            return threads * iters / dt, threads * iters, dt
+        return thr, "reference"
+    return O.extract_throughput, "port"
+
+
+def cpu_extract_fps(frames, threads, seconds_budget):
+    thr, _ = cpu_extractor()
+    fps1, _, _ = thr(frames, NFEAT, 1, 2)
     iters = int(min(64, max(2, seconds_budget * fps1)))
-    return O.extract_throughput(frames, NFEAT, threads, iters)
+    return thr(frames, NFEAT, threads, iters)
 
 
 _BEST_THREADS = {}
@@ -151,13 +182,13 @@ def best_cpu_threads():
     shared boxes often expose more logical CPUs than the process can really use."""
     if "n" in _BEST_THREADS:
         return _BEST_THREADS["n"]
-    from oracle import oracle as O
+    thr, _ = cpu_extractor()
     ncpu = os.cpu_count() or 1
     frames, _ = make_frames(4, 1)
     cands = sorted({c for c in (4, 8, 16, 32, 64, ncpu) if c <= ncpu})
     best, best_fps = ncpu, 0.0
     for c in cands:
-        fps, _, _ = O.extract_throughput(frames, NFEAT, c, 3)
+        fps, _, _ = thr(frames, NFEAT, c, 3)
         if fps > best_fps:
             best, best_fps = c, fps
     _BEST_THREADS["n"] = best
@@ -194,9 +225,10 @@ def cpu_lba(K, L, seed=0):
 
 
 def run_reference(args):
-    """The reference's own CPU implementation of the path: the oracle port (the
-    reference cannot be compiled here), all host threads for the per-frame work
-    (one extractor instance per thread), single thread for LBA like g2o."""
+    """The reference's own CPU implementation of the path: ORBextractor.cc compiled unmodified (oracle/_ref) when
+    that library was built (kind "reference"), else the oracle port; matchers and LBA are the oracle port (their
+    translation units need Eigen).  All host threads for the per-frame work (one extractor instance per thread),
+    single thread for LBA like g2o."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -223,10 +255,16 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "frames_per_step": int(vals[0][0]) if vals else 0},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-                         "sample": "%d frames/step over %d std::threads (best of 4..nproc; oracle C++ port, -O3 x86-64-v3); "
-                                   "extract %.2f ms + match %.2f ms per frame per thread"
-                                   % (vals[0][0] if vals else 0, threads, 1e3 * t_ext_frame_thread, 1e3 * t_match)},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": cpu_extractor()[1],
+                         "sample": "%d frames/step over %d std::threads (best of 4..nproc); extract = %s, -O3 x86-64-v3, "
+                                   "%.2f ms/frame/thread measured with all threads busy; SearchByProjection x2 = oracle port, "
+                                   "%.2f ms/frame measured on one thread; value = threads / (extract + match) -- a composition "
+                                   "of two measurements, not one loop"
+                                   % (vals[0][0] if vals else 0, threads,
+                                      "the reference's ORBextractor.cc object code (oracle/_ref) over scalar cv2-pinned "
+                                      "resize/FAST/blur (OpenCV's SIMD versions would be faster)"
+                                      if cpu_extractor()[1] == "reference" else "oracle C++ port",
+                                      1e3 * t_ext_frame_thread, 1e3 * t_match)},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "lba": lba,
     }
@@ -257,9 +295,11 @@ class Workload:
             self.sf, self.sf2 = share.sf, share.sf2
             self._alloc_outputs(torch, B, cap)
             return
-        uniq, shifts = make_frames(min(B, 16) + 1, 1000 * rank + 1)
+        uniq, shifts, prev = make_streams(rank)
         self.uniq = uniq
-        nu = len(uniq) - 1
+        succ = [i for i in range(len(uniq)) if prev[i] >= 0]   # the 256 frames that have a predecessor
+        nu = len(succ)
+        self.n_distinct = nu
         self.host_pool, self.dev_pool, self.meta = [], [], []
         self.sf = scenes.scale_factors()
         self.sf2 = (self.sf * self.sf).astype(np.float32)
@@ -268,7 +308,7 @@ class Workload:
         scene_cache = {}
         for p in range(POOL):
             t = torch.empty((B, H, W), dtype=torch.uint8).pin_memory()
-            idx = [1 + (b + p) % nu for b in range(B)]        # frame idx[b]; its predecessor is idx[b]-1
+            idx = [succ[(b + p * B) % nu] for b in range(B)]  # frame idx[b]; its predecessor is prev[idx[b]]
             for b in range(B):
                 t[b] = torch.from_numpy(uniq[idx[b]])
             self.host_pool.append(t)
@@ -279,7 +319,7 @@ class Workload:
                 i = idx[b]
                 if i not in scene_cache:  # only len(uniq)-1 distinct frames exist
                     _, kb, db = res[i]
-                    _, ka, da = res[i - 1]
+                    _, ka, da = res[prev[i]]
                     cur, last, Tcw = scenes.last_frame_scene(ka, da, kb, db, W, H, shifts[i], seed=2 * i)
                     F, mps = scenes.local_map_scene(kb, db, W, H, N_LOCAL_EXTRA, seed=7 * i)
                     scene_cache[i] = (
@@ -408,10 +448,14 @@ class Workload:
 
 
 def run_lba_gpu(rank, world, device):
-    """LocalBA on the GPU: configs 4 and 5 at N=1, config 5 sharded by landmark for N>1."""
+    """LocalBA on the GPU: configs 4 and 5 at N=1, config 5 sharded by landmark for N>1 (one ncclAllReduce of the
+    envelope of [S | b_s] per LM trial).  `value` = LM trials / device time of optimize(10); `e2e` = the same count
+    over the host wall time of the C-ABI call (edge sort, CSR / pair lists, ordering, H2D, kernels, D2H).  At N>1
+    rank 0 also solves the unsharded graph and reports whether the sharded solve reproduces it."""
+    import ctypes as C
     import torch
     import torch.distributed as dist
-    from orb_slam3_b200 import scenes
+    from orb_slam3_b200 import _lib, scenes
     from orb_slam3_b200.optimizer import LocalBundleAdjustment
     out = {}
     lba = LocalBundleAdjustment(device=device)
@@ -420,52 +464,108 @@ def run_lba_gpu(rank, world, device):
         uid = [LocalBundleAdjustment.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         lba.init_comm(rank, world, uid[0])
+    peak = C.c_double(0.0)
+    fp64_peak = None
+    if rank == 0 and _lib.lib().lba_measure_fp64_mma_peak(device, 10, C.byref(peak)) == 0:
+        fp64_peak = peak.value
+    tensor_pct = None
+    try:
+        tensor_pct = json.load(open(os.path.join(ROOT, "profiles", "schur_pairs_r2.json")))["sm__pipe_tensor_cycles_active_pct"]
+    except Exception:
+        pass
     for name, K, L in configs:
         g, _ = scenes.lba_graph(K, L, seed=0)
-        sub = g if world == 1 else scenes.shard_graph(g, rank, world)[0]
+        sub, lm_ids, _ = (g, None, None) if world == 1 else scenes.shard_graph(g, rank, world)
         gv = scenes.lba_view(sub)
-        best = None
+        best, res = None, None
         for rep in range(4):  # the first run warms up allocations
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
-            st = lba(gv)["stats"]
+            r = lba(gv)
+            st = r["stats"]
             if rep > 0 and (best is None or st["ms_total"] < best["ms_total"]):
-                best = st
-        ms = torch.tensor([best["ms_total"]], dtype=torch.float64, device="cuda")
+                best, res = st, r
+        ms = torch.tensor([best["ms_total"], best["ms_wall"]], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        ms_total = float(ms.item())
-        out[name] = {
+        ms_total, ms_wall = (float(v) for v in ms.tolist())
+        schur_tf = best["schur_flops"] * best["trials"] / max(best["ms_schur"], 1e-9) / 1e9   # TFLOP/s (useful, block-sparse)
+        entry = {
             "config": "%d KF x %d landmarks, %d edges%s" % (K, L, len(g["e_kf"]),
                                                             "" if world == 1 else ", landmark shards + ncclAllReduce"),
             "iterations": best["iterations"], "trials": best["trials"], "ms_total": ms_total,
             "value": best["trials"] / (ms_total * 1e-3), "unit": "LM iterations/s",
+            "e2e": {"value": best["trials"] / (ms_wall * 1e-3), "unit": "LM iterations/s", "ms_wall": ms_wall,
+                    "ms_host_prep": best["ms_host_prep"],
+                    "h2d_bytes": int(len(sub["e_kf"]) * 45 + len(sub["mp_pos"]) * 24 + len(g["kf_fixed"]) * 77),
+                    "d2h_bytes": int(len(sub["e_kf"]) * 9 + len(sub["mp_pos"]) * 24 + len(g["kf_fixed"]) * 56)},
             "chi2_initial": best["chi2_initial"], "chi2_final": best["chi2_final"],
             "stage_ms": {k: best[k] for k in ("ms_linearize", "ms_schur", "ms_solve", "ms_update")},
-            "schur_gflops_sparse": best["schur_flops"] * best["trials"] / max(best["ms_schur"], 1e-9) / 1e6,
+            "reduced_solver": {0: "dense cooperative LDLT", 1: "envelope LDLT (32-column panels, one CTA)",
+                               2: "window-resident envelope LDLT (8-column panels, one CTA)"}[best["solver_kind"]],
+            "envelope_rows_max": best["envelope_rows_max"],
+            "schur_gflops_sparse": 1e3 * schur_tf,
+            "roofline": {"bound": "tensor", "kernel": "schur_pairs_kernel (fp64 DMMA m8n8k4)", "achieved": schur_tf,
+                         "peak": fp64_peak, "unit": "TFLOP/s", "frac": (schur_tf / fp64_peak) if fp64_peak else None,
+                         "peak_source": "measured in this run: DMMA m8n8k4 from registers, full grid, best of 10 (lba_measure_fp64_mma_peak)",
+                         "tensor_pipe_pct": tensor_pct,
+                         "flops": "block-sparse useful flops per trial (SURVEY.md 8d) x trials / time between the Schur events"},
             "n_pose_pairs": best["n_pairs"],
+            "allreduce_bytes_per_trial": best["allreduce_bytes_per_trial"],
         }
+        if world > 1:
+            # NCCL parity carried by the scaling run itself: rank 0 solves the unsharded graph on its own GPU
+            flag = torch.zeros(3, dtype=torch.float64, device="cuda")
+            if rank == 0:
+                single = LocalBundleAdjustment(device=device)(scenes.lba_view(g))
+                dpose = float(np.abs(single["kf_pose"] - res["kf_pose"]).max())
+                dpts = float(np.abs(single["mp_pos"][lm_ids] - res["mp_pos"]).max())
+                same_counts = (single["iterations"] == res["iterations"] and
+                               single["stats"]["trials"] == res["stats"]["trials"])
+                flag = torch.tensor([1.0 if (same_counts and dpose < 1e-7 and dpts < 1e-6) else 0.0, dpose, dpts],
+                                    dtype=torch.float64, device="cuda")
+            dist.broadcast(flag, src=0)
+            entry["sharded_equals_single"] = bool(flag[0].item() == 1.0)
+            entry["max_abs_dpose_vs_single"] = float(flag[1].item())
+            entry["max_abs_dpoint_vs_single"] = float(flag[2].item())
+        out[name] = entry
     return out
 
 
-def run_stereo_gpu(device, tstream, pairs=64, reps=5, cpu=True):
-    """SURVEY.md 8(f-1), config 3 shape: `pairs` rectified 1280x720 stereo pairs per step; both eyes
-    extracted by their own handle, then Frame::ComputeStereoMatches on the device-resident results."""
+def run_stereo_gpu(rank, world, device, tstream, pairs=64, reps=5, cpu=True):
+    """BASELINE.json configs[2] (SURVEY.md 8d config 3, rows 8f-1 + a12): one stereo camera stream per rank / GPU.
+    A step = `pairs` rectified 1280x720 stereo pairs of this rank's stream: both eyes extracted by their own
+    handle, Frame::ComputeStereoMatches on the device-resident results, then SearchForTriangulation between
+    consecutive left keyframes (synthetic FeatureVectors, ~1000 nodes) through the host-buffer batch call.
+    Weak scaling: every rank runs its own stream; value = all pairs / max-over-ranks time."""
     import torch
+    import torch.distributed as dist
+    from orb_slam3_b200 import scenes
     from orb_slam3_b200.extractor import ORBextractor
+    from orb_slam3_b200.matcher import ORBmatcher
     from orb_slam3_b200.stereo import StereoMatcher
-    from orb_slam3_b200.synth import synth_frame, stereo_right
+    from orb_slam3_b200.synth import stereo_right
     bf, b = 386.0, 386.0 / 700.0
-    uniq = 4
-    lefts = [synth_frame(H, W, 9000 + i) for i in range(uniq)]
-    rights = [stereo_right(l, 9100 + i, disparities=(6, 24, 12)) for i, l in enumerate(lefts)]
-    dl = torch.from_numpy(np.stack([lefts[i % uniq] for i in range(pairs)])).cuda()
-    dr = torch.from_numpy(np.stack([rights[i % uniq] for i in range(pairs)])).cuda()
+    uniq = 16
+    lefts, shifts = make_frames(uniq + 1, 9000 + 1000 * rank)
+    rights = [stereo_right(l, 9100 + 17 * rank + i, disparities=(6, 24, 12)) for i, l in enumerate(lefts)]
+    idx = [1 + i % uniq for i in range(pairs)]
+    dl = torch.from_numpy(np.stack([lefts[i] for i in idx])).cuda()
+    dr = torch.from_numpy(np.stack([rights[i] for i in idx])).cuda()
     el = ORBextractor(NFEAT, 1.2, NLEVELS, 20, 7, device=device)
     er = ORBextractor(NFEAT, 1.2, NLEVELS, 20, 7, device=device)
     sm = StereoMatcher(device)
+    tri = ORBmatcher(0.6, False, device=device)      # LocalMapping.cc:466: ORBmatcher matcher(0.6, false)
     cs = tstream.cuda_stream
+    # triangulation inputs: keyframe pairs (frame i, its predecessor) from one untimed extraction of the left stream
+    feats = el.extract_batch(list(lefts))
+    tri_in = {}
+    for i in range(1, uniq + 1):
+        _, k2, d2 = feats[i]
+        _, k1, d1 = feats[i - 1]
+        tri_in[i] = scenes.triangulation_scene(k1, d1, k2, d2, W, H, seed=31 * i, n_nodes=1000, shift=shifts[i])
+    targs = [[tri_in[i][j] for i in idx] for j in range(6)]
 
     def step():
         el.extract_batch_device(dl.data_ptr(), pairs, H, W, W, H * W, stream=cs)
@@ -474,30 +574,51 @@ def run_stereo_gpu(device, tstream, pairs=64, reps=5, cpu=True):
 
     for _ in range(3):
         step()
+    n_tri, _ = tri.triangulate_batch(*targs)
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
     e0.record()
-    ms_match = 0.0
     for _ in range(reps):
         step()
     e1.record()
+    ms_tri_dev = 0.0
+    for _ in range(reps):   # SearchForTriangulation of the same keyframes (host views -> H2D -> kernels -> D2H pair lists)
+        n_tri, _ = tri.triangulate_batch(*targs)
+        ms_tri_dev += tri.last_ms()
     torch.cuda.synchronize()
+    ms_wall = (time.perf_counter() - t0) * 1e3 / reps
     ms_all = e0.elapsed_time(e1) / reps
-    for _ in range(reps):  # the matcher alone, device time between its own events
+    ms_tri_dev /= reps
+    ms_match = 0.0
+    for _ in range(reps):  # the stereo matcher alone, device time between its own events
         sm.compute_batch(el, er, pairs, bf, b, on_device=True, cuda_stream=cs)
         ms_match += sm.last_ms()
     ms_match /= reps
     kept, ur, dp = sm.compute_batch(el, er, pairs, bf, b)
-    out = {"config": "%d stereo pairs 1280x720, 2000 features per eye, disparity bands 6/24/12 px" % pairs,
-           "pairs_per_s": pairs / (ms_all * 1e-3), "ms_per_step": ms_all, "unit": "stereo pairs/s (2 x extract + ComputeStereoMatches)",
+    t = torch.tensor([ms_all + ms_tri_dev, ms_wall], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev_max, ms_wall_max = (float(v) for v in t.tolist())
+    out = {"config": "configs[2]: %d stereo streams (one per GPU) x %d pairs 1280x720 per step, 2000 features per eye, "
+                     "disparity bands 6/24/12 px, %d distinct pairs per stream; + SearchForTriangulation per keyframe pair"
+                     % (world, pairs, uniq),
+           "value": world * pairs / (ms_dev_max * 1e-3), "unit": "stereo pairs/s (2 x extract + ComputeStereoMatches + SearchForTriangulation), device time, max over ranks",
+           "e2e_value": world * pairs / (ms_wall_max * 1e-3),
+           "e2e_unit": "stereo pairs/s, host wall clock (frames resident; triangulation through host buffers)",
+           "n_gpus": world, "scaling": "weak",
+           "pairs_per_s": pairs / (ms_all * 1e-3), "ms_per_step": ms_all,
            "stereo_match_us_per_pair": 1e3 * ms_match / pairs, "matches_per_pair": float(kept.mean()),
-           "gpu_launches_per_step": 3}
-    if cpu:
+           "triangulate_us_per_kf_pair": 1e3 * ms_tri_dev / pairs, "triangulation_pairs_per_kf_pair": float(n_tri.mean()),
+           "gpu_launches_per_step": 3 + int(tri.kernel_launches() // (reps + 1))}
+    if cpu and rank == 0:
         from oracle import oracle as O
         exl, exr = O.OracleExtractor(NFEAT), O.OracleExtractor(NFEAT)
         t0 = time.perf_counter()
-        kl, d1, _ = exl.extract(lefts[0])
-        kr, d2, _ = exr.extract(rights[0])
+        kl, d1, _ = exl.extract(lefts[1])
+        kr, d2, _ = exr.extract(rights[1])
         t_ext = time.perf_counter() - t0
         pl = [exl.level_image(l) for l in range(NLEVELS)]
         pr = [exr.level_image(l) for l in range(NLEVELS)]
@@ -505,10 +626,17 @@ def run_stereo_gpu(device, tstream, pairs=64, reps=5, cpu=True):
         for _ in range(5):
             n_ref, ur_ref, dp_ref, _ = O.stereo_match(kl, d1, kr, d2, pl, pr, bf, b)
         t_sm = (time.perf_counter() - t0) / 5
+        a1 = tri_in[1]
+        t0 = time.perf_counter()
+        for _ in range(5):
+            n_tref, p_tref = O.match_triangulate(*a1, False, False, False)
+        t_tri = (time.perf_counter() - t0) / 5
         n0 = len(kl)
-        out["cpu_baseline"] = {"stereo_match_ms_per_pair": 1e3 * t_sm, "extract2_ms_per_pair": 1e3 * t_ext, "threads": 1,
-                               "kind": "port", "parity_pair0": bool(np.array_equal(ur[0, :n0], ur_ref) and
-                                                                    np.array_equal(dp[0, :n0], dp_ref))}
+        got_n, got_p = tri.triangulate_batch(*[[a1[j]] for j in range(6)])
+        out["cpu_baseline"] = {"stereo_match_ms_per_pair": 1e3 * t_sm, "extract2_ms_per_pair": 1e3 * t_ext,
+                               "triangulate_ms_per_kf_pair": 1e3 * t_tri, "threads": 1, "kind": "port",
+                               "parity_pair0": bool(np.array_equal(ur[0, :n0], ur_ref) and np.array_equal(dp[0, :n0], dp_ref)),
+                               "parity_triangulation0": bool(int(got_n[0]) == n_tref and np.array_equal(got_p[0], p_tref))}
     return out
 
 
@@ -603,6 +731,62 @@ def run_bow_gpu(device, cpu=True):
     return out
 
 
+def run_latency_gpu(device, cpu=True, reps=30):
+    """Batch-1 latency of the calls the Tracking thread makes once per frame, through the host-buffer C ABI
+    (wall clock around the call: H2D + kernels + D2H + sync), median of `reps`, beside the CPU port on one thread."""
+    from orb_slam3_b200 import scenes
+    from orb_slam3_b200.extractor import ORBextractor
+    from orb_slam3_b200.matcher import ORBmatcher
+    from orb_slam3_b200.optimizer import PoseOptimization
+    from orb_slam3_b200.stereo import StereoMatcher
+    from orb_slam3_b200.synth import stereo_right
+    frames, shifts = make_frames(3, 777)
+    right = stereo_right(frames[1], 778, disparities=(6, 24, 12))
+    ext = ORBextractor(NFEAT, 1.2, NLEVELS, 20, 7, device=device)
+    ext_r = ORBextractor(NFEAT, 1.2, NLEVELS, 20, 7, device=device)
+    m_last, m_local = ORBmatcher(0.9, True, device=device), ORBmatcher(0.8, True, device=device)
+    po, sm = PoseOptimization(device), StereoMatcher(device)
+    _, ka, da = ext(frames[0])
+    _, kb, db = ext(frames[1])
+    cur, last, Tcw = scenes.last_frame_scene(ka, da, kb, db, W, H, shifts[1], seed=5)
+    F, mps = scenes.local_map_scene(kb, db, W, H, N_LOCAL_EXTRA, seed=6)
+    pv, _ = scenes.pose_scene(1000, seed=8)
+    ext_r(right)
+    bf, b = 386.0, 386.0 / 700.0
+
+    def med(fn):
+        fn(); fn()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        return 1e6 * float(np.median(ts))
+
+    out = {"unit": "microseconds per call, batch 1, host buffers in and out (median of %d)" % reps,
+           "orb_extract_1280x720": {"gpu_us": med(lambda: ext(frames[1]))},
+           "match_project_last": {"gpu_us": med(lambda: m_last.SearchByProjectionLast(cur, last, Tcw, TH_LAST))},
+           "match_project_local": {"gpu_us": med(lambda: m_local.SearchByProjection(F, mps, TH_LOCAL))},
+           "pose_optimize_1000_edges": {"gpu_us": med(lambda: po(pv))},
+           "stereo_match": {"gpu_us": med(lambda: sm.ComputeStereoMatches(ext, ext_r, len(kb), bf, b))}}
+    if cpu:
+        from oracle import oracle as O
+        ex, exr = O.OracleExtractor(NFEAT), O.OracleExtractor(NFEAT)
+        out["orb_extract_1280x720"]["cpu_port_us"] = med(lambda: ex.extract(frames[1]))
+        out["match_project_last"]["cpu_port_us"] = med(lambda: O.match_project_last(cur, last, Tcw, TH_LAST))
+        out["match_project_local"]["cpu_port_us"] = med(lambda: O.match_project_local(F, mps, TH_LOCAL, 0.8))
+        out["pose_optimize_1000_edges"]["cpu_port_us"] = med(lambda: O.pose_optimize(pv))
+        kl, dl_, _ = ex.extract(frames[1])
+        kr, dr_, _ = exr.extract(right)
+        pl = [ex.level_image(l) for l in range(NLEVELS)]
+        pr = [exr.level_image(l) for l in range(NLEVELS)]
+        out["stereo_match"]["cpu_port_us"] = med(lambda: O.stereo_match(kl, dl_, kr, dr_, pl, pr, bf, b))
+        for v in out.values():
+            if isinstance(v, dict) and "cpu_port_us" in v:
+                v["speedup_vs_one_cpu_thread"] = v["cpu_port_us"] / v["gpu_us"]
+    return out
+
+
 def _guarded(fn, *a, **k):
     """The extra legs must never cost the headline line."""
     try:
@@ -618,7 +802,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--batch", type=int, default=128, help="frames per step per GPU")
-    ap.add_argument("--pool", type=int, default=3, help="distinct batches rotated through (L2 defeat)")
+    ap.add_argument("--pool", type=int, default=2, help="distinct batches rotated through (L2 defeat); 2 x 128 = the 256 distinct frames")
     ap.add_argument("--e2e-workers", type=int, default=4, help="host threads feeding the GPU in the e2e leg")
     ap.add_argument("--no-lba", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -739,8 +923,8 @@ def main():
     if not args.no_lba:
         lba = run_lba_gpu(rank, world, local_rank)
     stereo = None
-    if rank == 0 and not args.no_stereo:
-        stereo = _guarded(run_stereo_gpu, local_rank, tstream, cpu=(world == 1 and not args.no_cpu))
+    if not args.no_stereo:   # configs[2]: every rank runs its own stereo stream
+        stereo = run_stereo_gpu(rank, world, local_rank, tstream, cpu=(world == 1 and not args.no_cpu))
     pose = None
     if rank == 0 and not args.no_stereo:
         pose = _guarded(run_pose_gpu, local_rank, cpu=(world == 1 and not args.no_cpu))
@@ -750,6 +934,9 @@ def main():
     bow = None
     if rank == 0 and not args.no_stereo:
         bow = _guarded(run_bow_gpu, local_rank, cpu=(world == 1 and not args.no_cpu))
+    latency = None
+    if rank == 0 and not args.no_stereo:
+        latency = _guarded(run_latency_gpu, local_rank, cpu=(world == 1 and not args.no_cpu))
     if world > 1:
         dist.barrier()
 
@@ -782,7 +969,8 @@ def main():
         total_ms = sum(v[0] for v in kern.values()) + sum(ms_match)
         traffic = None
         try:  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
-            tr = json.load(open(os.path.join(ROOT, "profiles", "fast_cells_traffic_r1.json")))
+            tp = os.path.join(ROOT, "profiles", "fast_traffic_r2.json")
+            tr = json.load(open(tp if os.path.exists(tp) else os.path.join(ROOT, "profiles", "fast_cells_traffic_r1.json")))
             if dom == "fast":
                 traffic = tr["dram_bytes_per_launch"] * B / tr["batch"]
         except Exception:
@@ -808,10 +996,14 @@ def main():
             fps_1, _, _ = cpu_extract_fps(wl.uniq[:8], 1, seconds_budget=3.0)
             t_match = cpu_match_seconds_per_frame(*make_frames(4, 1))
             t_ext = threads / fps_cpu
-            cpu = {"value": threads / (t_ext + t_match), "unit": "frames/s", "cores": threads, "kind": "port",
-                   "sample": "extract: %d frames over %d std::threads in %.1fs (%.1f frames/s; 1 thread %.1f frames/s); "
-                             "match: %.2f ms/frame/thread (oracle C++ port)" % (done, threads, dt, fps_cpu, fps_1,
-                                                                               1e3 * t_match)}
+            kind = cpu_extractor()[1]
+            cpu = {"value": threads / (t_ext + t_match), "unit": "frames/s", "cores": threads, "kind": kind,
+                   "sample": "extract (%s): %d frames over %d std::threads in %.1fs (%.1f frames/s; 1 thread %.1f frames/s); "
+                             "match: %.2f ms/frame/thread (oracle C++ port, one thread); value = threads / (extract + match): "
+                             "a composition of the two measurements; the image primitives under the reference code are the "
+                             "scalar cv2-pinned ones, OpenCV's SIMD FAST/resize/blur would be several times faster"
+                             % ("reference ORBextractor.cc object code, oracle/_ref" if kind == "reference" else "oracle C++ port",
+                                done, threads, dt, fps_cpu, fps_1, 1e3 * t_match)}
             if lba is not None:
                 lba["cpu_baseline_config4"] = cpu_lba(50, 20000)
         h2d, d2h = wl.e2e_bytes()
@@ -820,6 +1012,7 @@ def main():
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B,
+                       "distinct_frames_per_gpu": wl.n_distinct, "streams_per_gpu": N_STREAMS,
                        "l2": "inputs+pyramids %.0f MB per rotation > 126 MB L2 (%d batches rotated)"
                              % (POOL * B * (W * H + 2 * P) / 1e6, POOL),
                        "keypoints_last_step": nkp, "matches_last_step": {"last": nm_last, "local": nm_local}},
@@ -838,6 +1031,7 @@ def main():
             "pose_optimization": pose,
             "is_in_frustum": frustum,
             "compute_bow": bow,
+            "latency_batch1": latency,
         }
         print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:

@@ -704,34 +704,47 @@ __global__ void __launch_bounds__(SKY_THREADS) ldlt_sky_kernel(double* __restric
 // three barriers per 8 pivots instead of 64 per 32.  The back-substitution runs in the same launch, 8 unknowns
 // per step, with the next step's rows of L already in flight.
 constexpr int WIN = 128, WIN_P = WIN + 1, WIN_ROWS = WIN - 8, WPB = 8, WIN_THREADS = 512;
+constexpr int WIN_LP = 132;  // row pitch of the m-major L / L*D panels: the four k-rows of a DMMA fragment fall into different banks
 
 __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restrict__ M, int n, const int* __restrict__ reach,
-                                                             const int* __restrict__ first, double* fail,
+                                                             const int* __restrict__ first_g, double* fail,
                                                              double* __restrict__ x) {
   extern __shared__ __align__(16) double win_dyn[];
   double* A = win_dyn;                       // [WIN][WIN_P] ring of the trailing window
   double* zr = A + WIN * WIN_P;              // [WIN] right-hand side entries of the window columns
-  double* Lt = zr + WIN;                     // [8][WIN] L   of the panel rows, m-major; slot nr = rhs row
-  double* LDt = Lt + WPB * WIN;              // [8][WIN] L*D of the panel rows
+  double* Lt = zr + WIN;                     // [8][WIN_LP] L of the panel rows, m-major; slot nr = rhs row
+  double* LDt = Lt + WPB * WIN_LP;           // [8][WIN_LP] L*D of the panel rows
+  int* first = reinterpret_cast<int*>(LDt + WPB * WIN_LP);  // [n] envelope starts (read at every step: keep them on chip)
+  int* rlast = first + n;                    // [ceil(n/8)] last window row of every panel
   __shared__ double Lb[WPB][WPB];            // pivot block: strict lower = L
   __shared__ double Dib[WPB];                // 1 / D
   __shared__ double xb[WPB];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  int loaded = 0;  // rows (and rhs columns) [0, loaded) have entered the window
-  for (int k0 = 0; k0 < n; k0 += WPB) {
-    const int nb = min(WPB, n - k0);
-    const int R = min(max(reach[k0 + nb - 1], k0 + nb - 1), n - 1);  // last row of the window
-    // ---- (0) rows entering the window: columns [k0, i], zero left of the envelope (the ring slot is stale)
-    for (int i = max(loaded, k0) + warp; i <= R; i += WIN_THREADS / 32) {
+  const int npan = (n + WPB - 1) / WPB;
+  for (int i = tid; i < n; i += WIN_THREADS) first[i] = first_g[i];
+  for (int p = tid; p < npan; p += WIN_THREADS) {
+    const int k0 = p * WPB, nb = min(WPB, n - k0);
+    rlast[p] = min(max(reach[k0 + nb - 1], k0 + nb - 1), n - 1);
+  }
+  __syncthreads();
+  // rows [lo, hi] enter the window: columns [c0, i], zero left of the envelope (the ring slot is stale).
+  // Called by warps w0.. of the CTA; all loads of a call are independent.
+  auto load_rows = [&](int lo, int hi, int c0, int w0, int nwarps) {
+    for (int i = lo + (warp - w0); i <= hi; i += nwarps) {
       const int f = first[i];
       const double* Mi = M + (size_t)i * n;
       double* Ai = A + (i % WIN) * WIN_P;
-      for (int j = k0 + lane; j <= i; j += 32) Ai[j % WIN] = j >= f ? Mi[j] : 0.0;
+      for (int j = c0 + lane; j <= i; j += 32) Ai[j % WIN] = j >= f ? Mi[j] : 0.0;
       if (lane == 0) zr[i % WIN] = M[(size_t)n * n + i];
     }
-    loaded = max(loaded, R + 1);
-    __syncthreads();
-    // ---- (1) pivot block, one thread, registers only
+  };
+  load_rows(0, rlast[0], 0, 0, WIN_THREADS / 32);
+  __syncthreads();
+  for (int p = 0; p < npan; p++) {
+    const int k0 = p * WPB, nb = min(WPB, n - k0);
+    const int R = rlast[p];  // last row of the window; rows [k0, R] are resident
+    // ---- (1) pivot block, one thread, registers only; meanwhile the other warps bring in the rows that the
+    //      NEXT panel adds to the window (their ring slots are free and nothing below touches them)
     if (tid == 0) {
       double a[WPB][WPB];
 #pragma unroll
@@ -764,6 +777,8 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
           Lb[r][c] = c < r ? a[r][c] : 0.0;
           if (r < nb && c <= r) M[(size_t)(k0 + r) * n + k0 + c] = a[r][c];  // L below, D on the diagonal
         }
+    } else if (warp >= 1 && p + 1 < npan) {
+      load_rows(R + 1, rlast[p + 1], k0 + WPB, 1, WIN_THREADS / 32 - 1);
     }
     __syncthreads();
     // ---- (2) panel rows [k0+nb, R] and the rhs row: forward substitution, one thread per row
@@ -782,8 +797,8 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
 #pragma unroll
       for (int m = 0; m < WPB; m++) {
         l[m] = m < nb ? ld[m] * Dib[m] : 0.0;
-        Lt[m * WIN + tid] = l[m];
-        LDt[m * WIN + tid] = m < nb ? ld[m] : 0.0;
+        Lt[m * WIN_LP + tid] = l[m];
+        LDt[m * WIN_LP + tid] = m < nb ? ld[m] : 0.0;
       }
       double* dst = M + (size_t)(rhs ? n : i) * n + k0;
 #pragma unroll
@@ -791,45 +806,32 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
         if (m < nb) dst[m] = l[m];
     }
     __syncthreads();
-    // ---- (3) rank-nb update of the window rows / columns [r0, R] (+ rhs), 4x4 micro-tiles over window slots
+    // ---- (3) rank-nb update of the window rows / columns [r0, R] (+ rhs) on the tensor pipe: 8x8 tiles of the
+    //      lower triangle, one warp per tile, C -= L_i (8x8) * (L*D)_j^T as two fp64 DMMA m8n8k4 (k = 0..3, 4..7);
+    //      fragment layout: A[g][t], B[t][g], C[g][2t], C[g][2t+1] with g = lane / 4, t = lane % 4
     {
-      const int T = (nr + 1 + 3) >> 2;
-      const int ntile = T * (T + 1) / 2;
-      for (int t = tid; t < ntile; t += WIN_THREADS) {
-        int ti = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
-        while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
-        while (ti * (ti + 1) / 2 > t) ti--;
-        const int tj = t - ti * (ti + 1) / 2;
-        double acc[4][4];
-#pragma unroll
-        for (int a = 0; a < 4; a++)
-#pragma unroll
-          for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
-#pragma unroll
-        for (int m = 0; m < WPB; m++) {
-          const double2 li0 = *reinterpret_cast<const double2*>(&Lt[m * WIN + 4 * ti]);
-          const double2 li1 = *reinterpret_cast<const double2*>(&Lt[m * WIN + 4 * ti + 2]);
-          const double2 lj0 = *reinterpret_cast<const double2*>(&LDt[m * WIN + 4 * tj]);
-          const double2 lj1 = *reinterpret_cast<const double2*>(&LDt[m * WIN + 4 * tj + 2]);
-          const double li[4] = {li0.x, li0.y, li1.x, li1.y}, lj[4] = {lj0.x, lj0.y, lj1.x, lj1.y};
-#pragma unroll
-          for (int a = 0; a < 4; a++)
-#pragma unroll
-            for (int b = 0; b < 4; b++) acc[a][b] += li[a] * lj[b];
-        }
-#pragma unroll
-        for (int a = 0; a < 4; a++) {
-          const int wi = 4 * ti + a;
-          if (wi > nr) continue;
-          const bool rhs = wi == nr;
-          double* row = rhs ? zr : A + ((r0 + wi) % WIN) * WIN_P;
-#pragma unroll
-          for (int b = 0; b < 4; b++) {
-            const int wj = 4 * tj + b;
-            if (wj >= nr || wj > wi) continue;  // the rhs row has no column of its own; lower triangle only
-            row[(r0 + wj) % WIN] -= acc[a][b];
-          }
-        }
+      const int T8 = (nr + 1 + 7) >> 3;
+      const int ntile = T8 * (T8 + 1) / 2;
+      const int g = lane >> 2, t = lane & 3;
+      for (int tile = warp; tile < ntile; tile += WIN_THREADS / 32) {
+        int ti = (int)((sqrtf(8.f * (float)tile + 1.f) - 1.f) * 0.5f);
+        while ((ti + 1) * (ti + 2) / 2 <= tile) ti++;
+        while (ti * (ti + 1) / 2 > tile) ti--;
+        const int tj = tile - ti * (ti + 1) / 2;
+        const int wi = 8 * ti + g, wj = 8 * tj + 2 * t;
+        const double a0 = -Lt[t * WIN_LP + wi], a1 = -Lt[(t + 4) * WIN_LP + wi];
+        const double b0 = LDt[t * WIN_LP + 8 * tj + g], b1 = LDt[(t + 4) * WIN_LP + 8 * tj + g];
+        double* row = (wi == nr) ? zr : A + ((r0 + min(wi, nr)) % WIN) * WIN_P;  // the rhs row has no column of its own
+        const bool ok0 = wi <= nr && wj < nr && wj <= wi, ok1 = wi <= nr && wj + 1 < nr && wj + 1 <= wi;
+        double* p0 = row + (r0 + wj) % WIN;
+        double* p1 = row + (r0 + wj + 1) % WIN;
+        double c0 = ok0 ? *p0 : 0.0, c1 = ok1 ? *p1 : 0.0;
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                     : "+d"(c0), "+d"(c1) : "d"(a0), "d"(b0));
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                     : "+d"(c0), "+d"(c1) : "d"(a1), "d"(b1));
+        if (ok0) *p0 = c0;
+        if (ok1) *p1 = c1;
       }
     }
     __syncthreads();
@@ -1353,7 +1355,7 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
     for (int r = 0; r < nb; r++) jmin = std::min(jmin, env_first[k0 + r]);
     win_rows_max = std::max(win_rows_max, std::max(R - k0 + 1, k0 - jmin + nb));
   }
-  const bool win_ok = win_rows_max <= WIN_ROWS && n <= WIN * WIN_P;
+  const bool win_ok = win_rows_max <= WIN_ROWS && n <= 8192;  // envelope tables (4.5 bytes per unknown) share the shared memory
   static const char* ldlt_env = getenv("ORB_B200_LDLT");  // "dense" | "sky" | "win" | unset = automatic
   bool use_sky = sky_rows_max <= SKY_WMAX - 4 && n <= 32 * SKY_WMAX && sky_flops <= 6.0e7;
   if (ldlt_env && !strcmp(ldlt_env, "dense")) use_sky = false;
@@ -1522,7 +1524,7 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
       CUDA_TRYL(cudaMemsetAsync(S.d_bar, 0, 256, st));
       CUDA_TRYL(cudaMemsetAsync(D.scalars + 3, 0, sizeof(double), st));
       if (use_win) {
-        const size_t smem = sizeof(double) * (WIN * WIN_P + WIN + 2 * WPB * WIN);
+        const size_t smem = sizeof(double) * (WIN * WIN_P + WIN + 2 * WPB * WIN_LP) + sizeof(int) * ((size_t)n + (n + WPB - 1) / WPB + 4);
         CUDA_TRYL(raise_dynamic_smem((const void*)ldlt_win_kernel, smem, S.device));
         ldlt_win_kernel<<<1, WIN_THREADS, smem, st>>>(D.S, n, d_env_reach, d_env_first, D.scalars + 3, D.x);
         S.launches += 1;

@@ -346,9 +346,8 @@ fast_cells_kernel(const CUtensorMap* __restrict__ maps, int frame0,
 // half of a two-slot ring, one mbarrier per slot) while it works on the current one; all hand-offs inside the
 // cell are warp-synchronous (ballot / shuffle prefix sums, __syncwarp) -- there is no __syncthreads in the
 // kernel; the packed threshold test is ((d & 0x7f..) + K | d) on the byte MSBs (3 instructions per sample).
-// The box starts at the 4-byte aligned column left of the cell, so its row pitch is 48 bytes at 1280x720
-// (2.1 KB per cell instead of 7.3 KB through L2) and the three rows a warp touches per load instruction fall
-// into different shared-memory banks.
+// The box starts at the 16-byte aligned column left of the cell (TMA needs that) and is only as large as the
+// largest cell of the image size needs: 64 x 48 bytes at 1280x720 (3 KB per cell instead of 7.3 KB through L2).
 struct FastGeom {
   int tile_pitch, tile_rows, tile_bytes;  // TMA box = tile_pitch x tile_rows bytes (pitch multiple of 16)
   int smap_pitch, smap_bytes;             // score map with a one-pixel zero frame
@@ -380,13 +379,19 @@ fast_warp_kernel(const CUtensorMap* __restrict__ maps, int frame0, int nframes, 
   const int SW = G.smap_pitch, TP = G.tile_pitch;
   const long long total = (long long)num_cells * nframes;
   const long long gw = (long long)blockIdx.x * FASTW_WARPS + warp, NW = (long long)gridDim.x * FASTW_WARPS;
-  if (lane == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8));
+  // all mbarriers are initialised by one thread at CTA-uniform addresses (ptxas turns an init at a per-warp
+  // address into a plain store + SYNCS.CCTL sequence that faulted as an illegal instruction on the B200); this is
+  // the only block-wide barrier of the kernel
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 0; w < FASTW_WARPS; w++) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&bars[w][0])));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&bars[w][1])));
+    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   for (int i = lane; i < G.smap_bytes / 4; i += 32) reinterpret_cast<uint32_t*>(smap)[i] = 0;
-  __syncwarp();
+  __syncthreads();
   auto issue = [&](long long item, int slot) {  // lane 0 only
     const int f = (int)(item / num_cells), c = (int)(item - (long long)f * num_cells);
     const CellDesc cd = cells[c];
@@ -1132,8 +1137,9 @@ int Engine::ensure(int rows, int cols, int batch) {
     // warp-per-cell FAST geometry: box = (3 + widest cell + 6, rounded to 16) x (tallest cell + 6)
     int max_tw = 0, max_th = 0;
     for (const CellDesc& c : cells) { max_tw = std::max(max_tw, c.x1 - c.x0); max_th = std::max(max_th, c.y1 - c.y0); }
-    const char* al = getenv("ORB_B200_FAST_ALIGN");  // 4: box starts at the 4-byte aligned column (48-byte rows at 720p)
-    fw_align_mask = (al && atoi(al) == 4) ? 3 : 15;
+    // the box must start at a 16-byte aligned column: a TMA tile load whose innermost coordinate is not a
+    // multiple of 16 bytes faults as an illegal instruction (compute-sanitizer, round 2)
+    fw_align_mask = 15;
     fw_tile_pitch = (int)align_up(fw_align_mask + max_tw, 16);
     fw_tile_rows = (int)align_up(max_th, 8);  // pitch % 16 == 0 and rows % 8 == 0: every slot is 128-byte aligned for TMA
     fw_smap_pitch = max_tw - 6 + 2;

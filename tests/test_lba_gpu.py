@@ -70,11 +70,11 @@ def test_lba_envelope_solver_and_keyframe_order(oracle, lba):
     keyframe list is renumbered (reverse Cuthill-McKee) back to a narrow profile.  Both equal the oracle."""
     g, _ = scenes.lba_graph(50, 4000, seed=4)
     got = lba(scenes.lba_view(g))
-    assert got["stats"]["solver_kind"] == 1 and got["stats"]["envelope_rows_max"] <= 6 * 16 + 32
+    assert got["stats"]["solver_kind"] in (1, 2) and got["stats"]["envelope_rows_max"] <= 6 * 16 + 32
     _compare(g, oracle.lba_solve(scenes.lba_view(g)), got, "natural order")
     gs = scenes.permute_keyframes(g, np.random.default_rng(3).permutation(len(g["kf_fixed"])))
     got_s = lba(scenes.lba_view(gs))
-    assert got_s["stats"]["solver_kind"] == 1 and got_s["stats"]["envelope_rows_max"] <= 6 * 24 + 32, got_s["stats"]
+    assert got_s["stats"]["solver_kind"] in (1, 2) and got_s["stats"]["envelope_rows_max"] <= 6 * 24 + 32, got_s["stats"]
     _compare(gs, oracle.lba_solve(scenes.lba_view(gs)), got_s, "shuffled keyframes")
     # a short window: every keyframe pair shares landmarks, the envelope is the whole triangle of S
     gd, _ = scenes.lba_graph(12, 800, seed=6)
