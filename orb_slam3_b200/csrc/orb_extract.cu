@@ -88,6 +88,60 @@ resize_level_kernel(uint8_t* __restrict__ pyr, size_t frame_stride, size_t src_o
   *reinterpret_cast<uint32_t*>(base + dst_off + (size_t)y * dpitch + x4) = packed;
 }
 
+// Same arithmetic, staged: one CTA produces RS_ROWS consecutive output rows of one frame.  The (<= RS_SRC) source
+// rows they touch are copied to shared memory with coalesced 16-byte loads; the four byte gathers per output
+// pixel then hit shared memory instead of issuing four global loads each, and the per-column tables
+// (xofs, alpha) are read once per thread and reused for every row of the CTA.
+constexpr int RS_ROWS = 4, RS_SRC = 8, RS_THREADS = 256;
+
+__global__ void __launch_bounds__(RS_THREADS)
+resize_rows_kernel(uint8_t* __restrict__ pyr, size_t frame_stride, size_t src_off, int sw, int sh, int spitch,
+                   size_t dst_off, int dw, int dh, int dpitch, const int* __restrict__ xofs,
+                   const short2* __restrict__ alpha, const int* __restrict__ yofs, const short2* __restrict__ beta) {
+  extern __shared__ __align__(16) uint8_t rs_rows[];  // [RS_SRC][spitch]
+  __shared__ int s_y[RS_ROWS];
+  uint8_t* base = pyr + (size_t)blockIdx.y * frame_stride;
+  const uint8_t* S = base + src_off;
+  const int y0 = blockIdx.x * RS_ROWS, ny = min(RS_ROWS, dh - y0);
+  // source rows [lo, hi]: yofs is non-decreasing, rows are clamped like the reference clamps sy and sy + 1
+  const int lo = min(max(yofs[y0], 0), sh - 1), hi = min(max(yofs[y0 + ny - 1] + 1, 0), sh - 1);
+  const int nsrc = hi - lo + 1;  // <= RS_SRC for down-scaling factors up to 2 (host-checked)
+  const int vec = spitch >> 4;   // the slab pitch is a multiple of 64
+  for (int i = threadIdx.x; i < nsrc * vec; i += RS_THREADS) {
+    const int r = i / vec, c = i - r * vec;
+    reinterpret_cast<uint4*>(rs_rows + (size_t)r * spitch)[c] =
+        reinterpret_cast<const uint4*>(S + (size_t)(lo + r) * spitch)[c];
+  }
+  if (threadIdx.x < ny) s_y[threadIdx.x] = yofs[y0 + threadIdx.x];
+  __syncthreads();
+  for (int x4 = threadIdx.x * 4; x4 < dw; x4 += RS_THREADS * 4) {
+    int sx[4], sx1[4];
+    short2 a[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int x = min(x4 + k, dw - 1);
+      sx[k] = xofs[x];
+      sx1[k] = min(sx[k] + 1, sw - 1);
+      a[k] = alpha[x];
+    }
+    for (int r = 0; r < ny; r++) {
+      const int y = y0 + r, sy = s_y[r];
+      const uint8_t* S0 = rs_rows + (size_t)(min(max(sy, 0), sh - 1) - lo) * spitch;
+      const uint8_t* S1 = rs_rows + (size_t)(min(max(sy + 1, 0), sh - 1) - lo) * spitch;
+      const short2 b = beta[y];
+      uint32_t packed = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int h0 = S0[sx[k]] * a[k].x + S0[sx1[k]] * a[k].y;
+        const int h1 = S1[sx[k]] * a[k].x + S1[sx1[k]] * a[k].y;
+        const int v = (((b.x * (h0 >> 4)) >> 16) + ((b.y * (h1 >> 4)) >> 16) + 2) >> 2;
+        if (x4 + k < dw) packed |= (uint32_t)(v & 0xff) << (8 * k);
+      }
+      *reinterpret_cast<uint32_t*>(base + dst_off + (size_t)y * dpitch + x4) = packed;
+    }
+  }
+}
+
 // Copy the caller's level-0 images (arbitrary pitch / frame stride, device memory) into the
 // pyramid slabs: one launch for the whole batch, 16-byte accesses when the layout allows.
 __global__ void __launch_bounds__(256)
@@ -1122,6 +1176,24 @@ int Engine::ensure(int rows, int cols, int batch) {
       oct_smem_bytes = 0;
     }
   }
+  {
+    // resize_rows_kernel: RS_ROWS output rows must span <= RS_SRC source rows, and the staged rows must fit
+    resize_rows_ok = !(getenv("ORB_B200_RESIZE") && !strcmp(getenv("ORB_B200_RESIZE"), "level"));
+    size_t smem = 0;
+    for (int l = 1; l < nlevels && resize_rows_ok; l++) {
+      const LevelDev& S = levels[l - 1];
+      const LevelDev& D = levels[l];
+      smem = std::max(smem, (size_t)RS_SRC * S.pitch);
+      for (int y0 = 0; y0 < D.h; y0 += RS_ROWS) {
+        const int y1 = std::min(y0 + RS_ROWS, D.h) - 1;
+        const int lo = std::min(std::max(h_yofs[rs[l].y_off + y0], 0), S.h - 1);
+        const int hi = std::min(std::max(h_yofs[rs[l].y_off + y1] + 1, 0), S.h - 1);
+        if (hi - lo + 1 > RS_SRC) resize_rows_ok = false;
+      }
+    }
+    if (smem > 200 * 1024) resize_rows_ok = false;
+    if (resize_rows_ok) CUDA_TRY(raise_dynamic_smem((const void*)resize_rows_kernel, smem, device));
+  }
   pyr_frame_bytes = align_up(img_off, 256);
   cand_frame_elems = cand_off;
   scratch_frame_bytes = scratch_off;
@@ -1263,10 +1335,16 @@ int Engine::run_device(int f0, int batch, const int* lap_host, cudaStream_t s) {
   for (int l = 1; l < nlevels; l++) {
     const LevelDev& S = levels[l - 1];
     const LevelDev& D = levels[l];
-    dim3 grid((D.w + 4 * 256 - 1) / (4 * 256), D.h, B);
-    resize_level_kernel<<<grid, 256, 0, s>>>(pyr, pyr_frame_bytes, S.img_off, S.w, S.h, S.pitch, D.img_off,
-                                            D.w, D.h, D.pitch, d_xofs + rs[l].x_off, d_alpha + rs[l].x_off,
-                                            d_yofs + rs[l].y_off, d_beta + rs[l].y_off);
+    if (resize_rows_ok) {
+      resize_rows_kernel<<<dim3((D.h + RS_ROWS - 1) / RS_ROWS, B), RS_THREADS, (size_t)RS_SRC * S.pitch, s>>>(
+          pyr, pyr_frame_bytes, S.img_off, S.w, S.h, S.pitch, D.img_off, D.w, D.h, D.pitch, d_xofs + rs[l].x_off,
+          d_alpha + rs[l].x_off, d_yofs + rs[l].y_off, d_beta + rs[l].y_off);
+    } else {
+      dim3 grid((D.w + 4 * 256 - 1) / (4 * 256), D.h, B);
+      resize_level_kernel<<<grid, 256, 0, s>>>(pyr, pyr_frame_bytes, S.img_off, S.w, S.h, S.pitch, D.img_off,
+                                              D.w, D.h, D.pitch, d_xofs + rs[l].x_off, d_alpha + rs[l].x_off,
+                                              d_yofs + rs[l].y_off, d_beta + rs[l].y_off);
+    }
   }
   stage_end(1, s, nlevels - 1);
   // 4. blur: needs only the pyramid, so it runs on a side stream next to FAST + octree (the

@@ -10,6 +10,7 @@
 #include <string>
 #include <vector>
 
+#include "Converter.h"
 #include "Frame.h"
 #include "KeyFrame.h"
 #include "orb_b200.h"
@@ -50,8 +51,22 @@ void transform_on_device(ORBVocabulary* voc, const cv::Mat& descriptors, DBoW2::
   std::vector<int32_t> ids(n), nodes(n), ptr(n + 1), idx(n);
   std::vector<double> vals(n);
   int32_t n_words = 0, n_nodes = 0;
-  const int used = bow_transform(device_vocabulary(voc), d.data, n, /*levelsup=*/4, ids.data(), vals.data(), &n_words,
-                                 nodes.data(), ptr.data(), idx.data(), &n_nodes, n);
+  int used;
+  {
+    // Tracking (Frame::ComputeBoW) and LocalMapping (KeyFrame::ComputeBoW) call this concurrently and the handle
+    // owns per-call scratch (stream, device buffers, pinned results): one transform at a time per vocabulary
+    static std::mutex call_mu;
+    std::lock_guard<std::mutex> lk(call_mu);
+    used = bow_transform(device_vocabulary(voc), d.data, n, /*levelsup=*/4, ids.data(), vals.data(), &n_words,
+                         nodes.data(), ptr.data(), idx.data(), &n_nodes, n);
+  }
+  if (used == ORB_E_CAPACITY) {
+    // more features than one launch sorts in shared memory (8192): monocular initialisation extracts
+    // 5 x nFeatures (Tracking.cc:2536).  Rare and off the per-frame path: use the reference's own transform.
+    std::vector<cv::Mat> vCurrentDesc = Converter::toDescriptorVector(descriptors);
+    voc->transform(vCurrentDesc, bow, fv, 4);
+    return;
+  }
   if (used < 0) throw std::runtime_error(std::string("bow_transform: ") + orb_last_error());
   for (int k = 0; k < n_words; k++) bow.insert(bow.end(), DBoW2::BowVector::value_type((DBoW2::WordId)ids[k], vals[k]));
   for (int k = 0; k < n_nodes; k++) {

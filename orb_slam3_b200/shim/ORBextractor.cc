@@ -34,6 +34,21 @@ orb_extractor* handle_of(const ORBextractor* self) {
 // Used by shim/Frame_ComputeStereoMatches.cc: the engine handle behind a reference extractor object.
 orb_extractor* orbb200_handle_of(const ORBextractor* self) { return handle_of(self); }
 
+// The reference header declares an empty inline destructor (ORBextractor.h:52), so the engine cannot be freed
+// from ~ORBextractor without touching the header: Tracking::~Tracking / System::Shutdown call this hook (one
+// line each); an extractor constructed at a recycled address releases a stale entry itself.
+void orbb200_release(const ORBextractor* self) {
+  orb_extractor* h = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_handles.find(self);
+    if (it == g_handles.end()) return;
+    h = it->second;
+    g_handles.erase(it);
+  }
+  orb_destroy(h);
+}
+
 ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int _iniThFAST, int _minThFAST)
     : nfeatures(_nfeatures), scaleFactor(_scaleFactor), nlevels(_nlevels), iniThFAST(_iniThFAST),
       minThFAST(_minThFAST) {
@@ -51,6 +66,7 @@ ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int
   orb_get_inverse_scale_sigma_squares(h, mvInvLevelSigma2.data());
   orb_get_features_per_level(h, mnFeaturesPerLevel.data());
   mvImagePyramid.resize(nlevels);
+  orbb200_release(this);  // an earlier extractor lived at this address and was never released
   std::lock_guard<std::mutex> lk(g_mu);
   g_handles[this] = h;
 }
@@ -78,8 +94,11 @@ int ORBextractor::operator()(cv::InputArray _image, cv::InputArray /*_mask*/, st
     _descriptors.create(n, 32, CV_8U);
     desc.rowRange(0, n).copyTo(_descriptors.getMat());
   }
-  // host mirror of the pyramid for Frame::ComputeStereoMatches (levels are unpadded views
-  // into engine-owned pinned memory, valid until the next call on this extractor)
+  // mvImagePyramid (ORBextractor.h:83): the only reader in the reference is Frame::ComputeStereoMatches
+  // (Frame.cc:818-923).  With shim/Frame_ComputeStereoMatches.cc built in (ORB_B200_STEREO_ON_DEVICE) nothing
+  // reads the host mirror and the full-pyramid D2H per frame is skipped; otherwise the levels are refreshed as
+  // unpadded views into engine-owned pinned memory, valid until the next call on this extractor.
+#ifndef ORB_B200_STEREO_ON_DEVICE
   for (int level = 0; level < nlevels; ++level) {
     const uint8_t* p = nullptr;
     int rows = 0, cols = 0;
@@ -87,6 +106,7 @@ int ORBextractor::operator()(cv::InputArray _image, cv::InputArray /*_mask*/, st
     if (orb_pyramid(h, 0, level, &p, &rows, &cols, &step) == ORB_OK)
       mvImagePyramid[level] = cv::Mat(rows, cols, CV_8UC1, const_cast<uint8_t*>(p), step);
   }
+#endif
   return mono;
 }
 

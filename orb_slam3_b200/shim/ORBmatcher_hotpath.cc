@@ -5,9 +5,9 @@
 // -DORB_B200_HOTPATH and guard them) and add this file; signatures are the
 // reference's own (include/ORBmatcher.h:43-76).  NOT compiled in this repo's
 // image (Eigen / Sophus / DBoW2 / OpenCV headers are absent) -- see
-// INTEGRATION.md.  Pinhole, single camera (Frame::Nleft == -1) only: the
-// fisheye-stereo branches fall back to the reference bodies kept under
-// *_Reference names.
+// INTEGRATION.md.  Pinhole, single camera only (orbb200_gate.h): KannalaBrandt8 rigs
+// (monocular too) and the fisheye-stereo branches call the reference bodies kept
+// under *_Reference names.
 #include <memory>
 #include <stdexcept>
 
@@ -16,6 +16,7 @@
 #include "MapPoint.h"
 #include "ORBmatcher.h"
 #include "orb_b200.h"
+#include "orbb200_gate.h"
 
 namespace ORB_SLAM3 {
 
@@ -70,7 +71,7 @@ int ORBmatcher::DescriptorDistance(const cv::Mat& a, const cv::Mat& b) { return 
 // ORBmatcher.cc:43-141
 int ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoints, const float th,
                                    const bool bFarPoints, const float thFarPoints) {
-  if (F.Nleft != -1) return SearchByProjection_Reference(F, vpMapPoints, th, bFarPoints, thFarPoints);
+  if (!orbb200_gate::gpu_path(F)) return SearchByProjection_Reference(F, vpMapPoints, th, bFarPoints, thFarPoints);
   FrameArrays fa;
   frame_view(F, fa);
   const int n = (int)vpMapPoints.size();
@@ -97,7 +98,7 @@ int ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoint
 
 // ORBmatcher.cc:1676-1887
 int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono) {
-  if (CurrentFrame.Nleft != -1) return SearchByProjection_Reference(CurrentFrame, LastFrame, th, bMono);
+  if (!orbb200_gate::gpu_path(CurrentFrame)) return SearchByProjection_Reference(CurrentFrame, LastFrame, th, bMono);
   const Sophus::SE3f Tcw = CurrentFrame.GetPose();
   const Eigen::Vector3f twc = Tcw.inverse().translation();
   const Eigen::Vector3f tlc = LastFrame.GetPose() * twc;
@@ -136,7 +137,7 @@ int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, 
 // ORBmatcher.cc:907-1146
 int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, vector<pair<size_t, size_t> >& vMatchedPairs,
                                        const bool bOnlyStereo, const bool bCoarse) {
-  if (pKF1->mpCamera2 || pKF2->mpCamera2)
+  if (!orbb200_gate::gpu_path(pKF1) || !orbb200_gate::gpu_path(pKF2))
     return SearchForTriangulation_Reference(pKF1, pKF2, vMatchedPairs, bOnlyStereo, bCoarse);
   auto kf_view = [](KeyFrame* kf, FrameArrays& a) {
     a.taken.assign(kf->N, 0);

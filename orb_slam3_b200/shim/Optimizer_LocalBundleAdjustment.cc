@@ -11,11 +11,17 @@
 
 #include "Optimizer.h"
 #include "orb_b200.h"
+#include "orbb200_gate.h"
 
 namespace ORB_SLAM3 {
 
 void Optimizer::LocalBundleAdjustment(KeyFrame* pKF, bool* pbStopFlag, Map* pMap, int& num_fixedKF, int& num_OptKF,
                                       int& num_MPs, int& num_edges) {
+  // KannalaBrandt8 / two-camera rigs (pCamera->project edges, EdgeSE3ProjectXYZToBody for the right camera,
+  // Optimizer.cc:1366-1400) are not on the GPU path: hand the whole call to the reference body before any
+  // mnBALocalForKF / mnBAFixedForKF mark is written (the reference body writes the same marks itself)
+  if (!orbb200_gate::gpu_path(pKF))
+    return LocalBundleAdjustment_Reference(pKF, pbStopFlag, pMap, num_fixedKF, num_OptKF, num_MPs, num_edges);
   // ---- 1-3: identical to Optimizer.cc:1119-1186
   list<KeyFrame*> lLocalKeyFrames;
   lLocalKeyFrames.push_back(pKF);
@@ -84,6 +90,8 @@ void Optimizer::LocalBundleAdjustment(KeyFrame* pKF, bool* pbStopFlag, Map* pMap
       KeyFrame* pKFi = obs.first;
       if (pKFi->isBad() || pKFi->GetMap() != pCurrentMap) continue;
       const int leftIndex = get<0>(obs.second);
+      // a single-camera rig has no right-index observations (get<1> == -1, :1366); left index -1 with a right
+      // index set cannot occur here because two-camera rigs took the reference body above
       if (leftIndex == -1) continue;
       const cv::KeyPoint& kpUn = pKFi->mvKeysUn[leftIndex];
       const float ur = pKFi->mvuRight[leftIndex];

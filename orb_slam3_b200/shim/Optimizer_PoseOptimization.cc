@@ -12,11 +12,12 @@
 
 #include "Optimizer.h"
 #include "orb_b200.h"
+#include "orbb200_gate.h"
 
 namespace ORB_SLAM3 {
 
 int Optimizer::PoseOptimization(Frame* pFrame) {
-  if (pFrame->mpCamera2) return PoseOptimization_Reference(pFrame);  // rigid-body stereo: not on the GPU path
+  if (!orbb200_gate::gpu_path(*pFrame)) return PoseOptimization_Reference(pFrame);  // KB8 / rigid-body stereo: pCamera->project edges
   const int N = pFrame->N;
   std::vector<float> xw, obs, inv_sigma2;
   std::vector<size_t> index;  // edge -> keypoint i (vnIndexEdgeMono / vnIndexEdgeStereo merged, keypoint order)

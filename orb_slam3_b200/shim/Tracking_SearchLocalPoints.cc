@@ -12,11 +12,12 @@
 #include "Tracking.h"
 #include "ORBmatcher.h"
 #include "orb_b200.h"
+#include "orbb200_gate.h"
 
 namespace ORB_SLAM3 {
 
 void Tracking::SearchLocalPoints() {
-  if (mCurrentFrame.Nleft != -1) { SearchLocalPoints_Reference(); return; }
+  if (!orbb200_gate::gpu_path(mCurrentFrame)) { SearchLocalPoints_Reference(); return; }
   // :3345-3363, unchanged
   for (auto vit = mCurrentFrame.mvpMapPoints.begin(), vend = mCurrentFrame.mvpMapPoints.end(); vit != vend; vit++) {
     MapPoint* pMP = *vit;
