@@ -349,11 +349,12 @@ class Workload:
 
     # views whose frame side points at the extractor's device results (built once per pool entry)
     def _device_views(self, p):
+        from orb_slam3_b200.views import orb_frame_view, orb_lastframe_view, orb_mappoint_view
+        kp, ds, _, _, cap = self.ext.device_results()   # double-buffered: the set of the extraction just submitted
+        p = (p, kp)
         if p in self._dev_views:
             return self._dev_views[p]
-        from orb_slam3_b200.views import orb_frame_view, orb_lastframe_view, orb_mappoint_view
-        kp, ds, _, _, cap = self.ext.device_results()
-        e = self.meta[p]
+        e = self.meta[p[0]]
         curs, lasts, Fs, Ms = [], [], [], []
         for b in range(self.B):
             for which, src, lst in ((0, e["cur"][b], curs), (1, e["F"][b], Fs)):
@@ -388,29 +389,45 @@ class Workload:
         torch = self.torch
         self.main_stream = main_stream
         self.side = (torch.cuda.Stream(), torch.cuda.Stream())
+        self._match_done = {}
         self.m_last.set_stream(self.side[0].cuda_stream)
         self.m_local.set_stream(self.side[1].cuda_stream)
 
     def step_device(self, i):
         p = i % self.POOL
         d = self.dev_pool[p]
+        side = getattr(self, "side", None)
+        if side:
+            # the extractor's results are double-buffered: this extraction overwrites the set the matchers of
+            # step i-2 read (their end was recorded then), while the matchers of step i-1 may still be running
+            done = self._match_done.pop(i - 2, None)
+            if done:
+                for ev in done:
+                    self.main_stream.wait_event(ev)
         self.ext.extract_batch_device(d.data_ptr(), self.B, H, W, W, H * W, stream=self.stream)
         curs, lasts, Fs, Ms, a1, a2 = self._device_views(p)
-        side = getattr(self, "side", None)
         if side:
             for st in side:
                 st.wait_stream(self.main_stream)
         r1, _ = self.m_last.project_last_batch(curs, lasts, self.meta[p]["T"], TH_LAST, on_device=True,
                                                assign_ptrs=a1)
         r2, _ = self.m_local.project_local_batch(Fs, Ms, TH_LOCAL, on_device=True, assign_ptrs=a2)
-        if side:  # the next extraction overwrites the keypoints/descriptors the matchers read
+        if side:
+            evs = []
             for st in side:
-                self.main_stream.wait_stream(st)
+                ev = self.torch.cuda.Event()
+                ev.record(st)
+                evs.append(ev)
+            self._match_done[i] = evs
         self.nmatch_last, self.nmatch_local = r1, r2  # filled when the asynchronous batches complete
 
     def finish_device(self):
         self.m_last.synchronize()
         self.m_local.synchronize()
+        side = getattr(self, "side", None)
+        if side:  # the timed region ends on the main stream: join the matcher streams into it
+            for st in side:
+                self.main_stream.wait_stream(st)
 
     def step_host(self, i):
         from orb_slam3_b200._lib import check, ptr
@@ -424,16 +441,20 @@ class Workload:
                                               ptr(self.out_m)))
         e = self.meta[p]
         curs, Fs = [], []
+        kp, ds, _, _, dcap = self.ext.device_results()
         for b in range(B):
             for src, lst in ((e["cur"][b], curs), (e["F"][b], Fs)):
                 v = orb_frame_view()
                 C.memmove(C.byref(v), C.byref(src), C.sizeof(v))
                 v.n = int(self.out_n[b])
-                v.keys = self.out_k.data_ptr() + b * cap * 28      # the keypoints just downloaded
-                v.desc = self.out_d.data_ptr() + b * cap * 32
+                # the keypoints / descriptors were downloaded for the caller above; the matchers read the
+                # extractor's device copy (on_device = 2) instead of uploading them again
+                v.keys = kp + b * dcap * 28
+                v.desc = ds + b * dcap * 32
+                v.u_right = None
                 lst.append(v)
-        r1, _ = self.m_last.project_last_batch(curs, e["last"], e["T"], TH_LAST)
-        r2, _ = self.m_local.project_local_batch(Fs, e["mps"], TH_LOCAL)
+        r1, _ = self.m_last.project_last_batch(curs, e["last"], e["T"], TH_LAST, on_device=2)
+        r2, _ = self.m_local.project_local_batch(Fs, e["mps"], TH_LOCAL, on_device=2)
         self.nmatch_last, self.nmatch_local = r1, r2
 
     def e2e_bytes(self):
@@ -442,7 +463,7 @@ class Workload:
         d2h = int(self.B * (NFEAT + 4 * NLEVELS) * 60 + 8 * self.B)
         for b in range(self.B):
             n = e["n"][b]
-            h2d += 2 * n * 61 + e["last"][b].n * 50 + e["mps"][b].n * 59
+            h2d += 2 * n * 1 + e["last"][b].n * 50 + e["mps"][b].n * 59   # kp_taken only: keys / desc stay on the device
             d2h += 2 * n * 4
         return h2d, d2h
 

@@ -88,8 +88,10 @@ int orb_extract_batch(orb_extractor* h, int batch, const uint8_t* const* imgs, i
 
 /* Device-resident variant: d_imgs = batch frames already in HBM (frame b at
  * d_imgs + b*frame_stride, row pitch `step`), results stay in HBM.  Runs on the
- * handle's stream, or on `cuda_stream` (a cudaStream_t) when non-NULL.  Result
- * pointers are valid until the next call on the handle. */
+ * handle's stream, or on `cuda_stream` (a cudaStream_t) when non-NULL.  The results are
+ * double-buffered: orb_device_results after call i returns pointers that stay valid (and
+ * untouched) until call i + 2 on the handle, so a consumer on another stream may still be
+ * reading them while the next batch is extracted. */
 int orb_extract_batch_device(orb_extractor* h, int batch, const uint8_t* d_imgs, size_t frame_stride,
                              int rows, int cols, size_t step, const int* lap, void* cuda_stream);
 int orb_device_results(orb_extractor* h, const orb_keypoint** d_kps, const uint8_t** d_desc,
@@ -205,9 +207,11 @@ int match_triangulate(orb_matcher* m, const orb_frame_view* kf1, const orb_frame
                       int32_t* pairs_out, int cap);
 
 /* Batched forms: `count` independent problems in one submission (frames of a
- * stream, keyframe pairs).  All views are host memory unless `on_device` != 0,
- * in which case every pointer inside the views (and the outputs) is a device
- * pointer and nothing is copied.  results[k] = per-problem return value. */
+ * stream, keyframe pairs).  on_device = 0: all views are host memory.  on_device = 1: every pointer inside the
+ * views (and the outputs) is a device pointer and nothing is copied.  on_device = 2 (projection matchers):
+ * only keys / u_right / desc of the frame views are device pointers -- the device results of an extractor
+ * (orb_device_results), so the keypoints and descriptors of a frame that was just extracted are not uploaded
+ * again -- everything else, assign_out included, is host memory.  results[k] = per-problem return value. */
 int match_project_last_batch(orb_matcher* m, int count, const orb_frame_view* cur, const orb_lastframe_view* last,
                              const float* Tcw_qt7, const int32_t* forward, const int32_t* backward, float th,
                              int check_orientation, int32_t* const* assign_out, int32_t* results, int on_device);
@@ -221,10 +225,10 @@ int match_triangulate_batch(orb_matcher* m, int count, const orb_frame_view* kf1
 /* Submit subsequent batches on `cuda_stream` (a cudaStream_t) instead of the
  * matcher's own stream, e.g. the stream an extractor ran on; NULL restores it. */
 int match_set_stream(orb_matcher* m, void* cuda_stream);
-/* Asynchronous mode for device-resident batches (on_device != 0): the *_batch call returns after
+/* Asynchronous mode for device-resident batches (on_device = 1): the *_batch call returns after
  * enqueueing; `results` (which must stay valid) and the device outputs are complete after
- * match_synchronize() or the next batch on the same handle.  A candidate-buffer overflow is then
- * reported by that call as ORB_E_CAPACITY (the budget has been grown: re-submit the batch). */
+ * match_synchronize() or the next batch on the same handle.  A candidate-buffer overflow is handled inside
+ * that call: the budget is grown and the batch is run again from the inputs still staged on the device. */
 int match_set_async(orb_matcher* m, int enabled);
 int match_synchronize(orb_matcher* m);
 long long match_kernel_launches(const orb_matcher* m);

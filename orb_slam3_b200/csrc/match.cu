@@ -591,6 +591,8 @@ struct Matcher {
   int pending_count = 0;
   std::vector<size_t> pending_off;
   int32_t* pending_results = nullptr;
+  std::vector<ProjProblem> pending_P;  // the staged problems of the batch in flight (inputs stay in in_arena)
+  size_t pending_in_bytes = 0;
   int finish_pending();
 
   int init() {
@@ -623,7 +625,8 @@ struct Matcher {
 
 // Lays out host arrays in the staging blob (two passes: size, then copy).
 struct Stager {
-  bool on_device;
+  bool on_device;          // every array of the views already lives on the device
+  bool frame_dev = false;  // only the frame's keys / u_right / desc do (an extractor's device results)
   uint8_t* h_base = nullptr;
   uint8_t* d_base = nullptr;
   size_t off = 0;
@@ -641,9 +644,13 @@ struct Stager {
 
 static void stage_frame(Stager& st, const orb_frame_view& v, DevFrame& d) {
   d.n = v.n;
-  d.keys = st.put(v.keys, v.n);
-  d.u_right = st.put(v.u_right, v.n);
-  d.desc = st.put(v.desc, (size_t)v.n * 32);
+  if (st.frame_dev) {
+    d.keys = v.keys; d.u_right = v.u_right; d.desc = v.desc;
+  } else {
+    d.keys = st.put(v.keys, v.n);
+    d.u_right = st.put(v.u_right, v.n);
+    d.desc = st.put(v.desc, (size_t)v.n * 32);
+  }
   d.kp_taken = st.put(v.kp_taken, v.n);
   d.min_x = v.min_x; d.min_y = v.min_y; d.max_x = v.max_x; d.max_y = v.max_y;
   d.gwi = v.grid_w_inv; d.ghi = v.grid_h_inv;
@@ -659,6 +666,9 @@ static void stage_frame(Stager& st, const orb_frame_view& v, DevFrame& d) {
 template <class T>
 static T* carve_dev(Arena& a, size_t count) { return (T*)(a.d + a.take(count * sizeof(T))); }
 
+static int launch_projection(Matcher& M, std::vector<ProjProblem>& P, size_t in_bytes, bool all_on_device,
+                             int32_t* const* assign_out, int32_t* results, bool allow_async);
+
 int Matcher::finish_pending() {
   if (!pending) return 0;
   pending = false;
@@ -667,13 +677,15 @@ int Matcher::finish_pending() {
   float ms = 0;
   cudaEventElapsedTime(&ms, ev0, ev1);
   last_ms = ms;
-  for (int k = 0; k < pending_count; k++) {
-    const int* r = (const int*)(h_out.h + pending_off[k]);
-    if (r[1]) {
-      cand_per_query *= 4;
-      set_last_error("candidate buffer overflow in an asynchronous batch: re-submit it");
-      return ORB_E_CAPACITY;
-    }
+  bool overflow = false;
+  for (int k = 0; k < pending_count; k++)
+    if (((const int*)(h_out.h + pending_off[k]))[1]) overflow = true;
+  if (overflow) {
+    // the candidate lists of some problem did not fit: grow the budget and run the batch again, synchronously,
+    // from the inputs that are still staged on the device (the caller never sees the overflow)
+    cand_per_query *= 4;
+    return launch_projection(*this, pending_P, pending_in_bytes, true, nullptr, pending_results, false) < 0
+               ? ORB_E_CAPACITY : 0;
   }
   for (int k = 0; k < pending_count; k++) pending_results[k] = ((const int*)(h_out.h + pending_off[k]))[0];
   return 0;
@@ -688,49 +700,57 @@ static int run_projection(Matcher& M, int count, int kind, const orb_frame_view*
   if (rc) return rc;
   CUDA_TRYM(cudaSetDevice(M.device));
   if ((rc = M.finish_pending())) return rc;  // the arenas are about to be reused
+  // on_device: 0 = host views, 1 = every array of the views is device memory (assign_out too),
+  //            2 = only the frames' keys / u_right / desc are device memory (an extractor's results)
+  const bool all_dev = on_device == 1;
   std::vector<ProjProblem> P(count);
-  for (int attempt = 0; attempt < 6; attempt++) {
-    // ---- stage inputs (sizing pass, then copy pass)
-    Stager st{on_device != 0};
-    for (int pass = 0; pass < 2; pass++) {
-      st.off = 0;
-      if (pass == 1) {
-        rc = M.h_in.reserve(std::max<size_t>(st.off, 16));
+  // ---- stage inputs (sizing pass, then copy pass)
+  Stager st{all_dev};
+  st.frame_dev = on_device == 2;
+  for (int pass = 0; pass < 2; pass++) {
+    st.off = 0;
+    for (int k = 0; k < count; k++) {
+      ProjProblem& p = P[k];
+      memset(&p, 0, sizeof(p));
+      stage_frame(st, F[k], p.F);
+      p.kind = kind;
+      if (kind == 0) {
+        const orb_mappoint_view& m = mps[k];
+        p.nq = m.n;
+        p.in_view = st.put(m.track_in_view, m.n); p.is_bad = st.put(m.is_bad, m.n);
+        p.has_obs = st.put(m.has_obs, m.n);
+        p.px = st.put(m.proj_x, m.n); p.py = st.put(m.proj_y, m.n); p.pxr = st.put(m.proj_xr, m.n);
+        p.lvl = st.put(m.scale_level, m.n); p.vcos = st.put(m.view_cos, m.n); p.depth = st.put(m.depth, m.n);
+        p.qdesc = st.put(m.desc, (size_t)m.n * 32);
+      } else {
+        const orb_lastframe_view& l = last[k];
+        p.nq = l.n;
+        p.has_mp = st.put(l.has_mp, l.n); p.has_obs = st.put(l.has_obs, l.n);
+        p.wpos = st.put(l.world_pos, (size_t)l.n * 3); p.qdesc = st.put(l.desc, (size_t)l.n * 32);
+        p.octave = st.put(l.octave, l.n); p.angle = st.put(l.angle, l.n);
+        memcpy(p.T, Tcw + 7 * k, sizeof(float) * 7);
+        p.forward = forward ? forward[k] : 0; p.backward = backward ? backward[k] : 0;
+        p.check_ori = check_ori;
       }
-      for (int k = 0; k < count; k++) {
-        ProjProblem& p = P[k];
-        memset(&p, 0, sizeof(p));
-        stage_frame(st, F[k], p.F);
-        p.kind = kind;
-        if (kind == 0) {
-          const orb_mappoint_view& m = mps[k];
-          p.nq = m.n;
-          p.in_view = st.put(m.track_in_view, m.n); p.is_bad = st.put(m.is_bad, m.n);
-          p.has_obs = st.put(m.has_obs, m.n);
-          p.px = st.put(m.proj_x, m.n); p.py = st.put(m.proj_y, m.n); p.pxr = st.put(m.proj_xr, m.n);
-          p.lvl = st.put(m.scale_level, m.n); p.vcos = st.put(m.view_cos, m.n); p.depth = st.put(m.depth, m.n);
-          p.qdesc = st.put(m.desc, (size_t)m.n * 32);
-        } else {
-          const orb_lastframe_view& l = last[k];
-          p.nq = l.n;
-          p.has_mp = st.put(l.has_mp, l.n); p.has_obs = st.put(l.has_obs, l.n);
-          p.wpos = st.put(l.world_pos, (size_t)l.n * 3); p.qdesc = st.put(l.desc, (size_t)l.n * 32);
-          p.octave = st.put(l.octave, l.n); p.angle = st.put(l.angle, l.n);
-          memcpy(p.T, Tcw + 7 * k, sizeof(float) * 7);
-          p.forward = forward ? forward[k] : 0; p.backward = backward ? backward[k] : 0;
-          p.check_ori = check_ori;
-        }
-        p.th = th; p.ratio = ratio; p.far_points = far_points; p.th_far = th_far;
-      }
-      if (pass == 0) {
-        const size_t need = st.off;
-        if (M.h_in.reserve(std::max<size_t>(need, 16))) return ORB_E_CUDA;
-        if (M.in_arena.reserve(std::max<size_t>(need, 16))) return ORB_E_CUDA;
-        st.h_base = M.h_in.h;
-        st.d_base = M.in_arena.d;
-      }
+      p.th = th; p.ratio = ratio; p.far_points = far_points; p.th_far = th_far;
     }
-    const size_t in_bytes = st.off;
+    if (pass == 0) {
+      const size_t need = st.off;
+      if (M.h_in.reserve(std::max<size_t>(need, 16))) return ORB_E_CUDA;
+      if (M.in_arena.reserve(std::max<size_t>(need, 16))) return ORB_E_CUDA;
+      st.h_base = M.h_in.h;
+      st.d_base = M.in_arena.d;
+    }
+  }
+  return launch_projection(M, P, st.off, all_dev, assign_out, results, true);
+}
+
+// Scratch / output carving, the five kernels and the result read-back of a staged batch.  A candidate-buffer
+// overflow grows the budget and runs the batch again from the staged inputs.
+static int launch_projection(Matcher& M, std::vector<ProjProblem>& P, size_t in_bytes, bool on_device,
+                             int32_t* const* assign_out, int32_t* results, bool allow_async) {
+  const int count = (int)P.size();
+  for (int attempt = 0; attempt < 6; attempt++) {
     // ---- scratch + outputs
     size_t sbytes = 0, obytes = 0;
     for (int k = 0; k < count; k++) {
@@ -762,7 +782,7 @@ static int run_projection(Matcher& M, int count, int kind, const orb_frame_view*
       p.cand_cap = (int)cc;
       p.minidx = carve_dev<int>(M.scratch, nk); p.taken = carve_dev<uint8_t>(M.scratch, nk);
       if (on_device) {
-        p.assign = assign_out[k];
+        if (assign_out) p.assign = assign_out[k];  // (a retry keeps the pointer staged by the first launch)
         p.result = carve_dev<int>(M.out_arena, 2);
         out_off[k] = (uint8_t*)p.result - M.out_arena.d;
       } else {
@@ -773,9 +793,7 @@ static int run_projection(Matcher& M, int count, int kind, const orb_frame_view*
     }
     cudaStream_t s = M.user_stream ? M.user_stream : M.stream;
     CUDA_TRYM(cudaEventRecord(M.ev0, s));
-    if (!on_device && in_bytes)
-      CUDA_TRYM(cudaMemcpyAsync(M.in_arena.d, M.h_in.h, in_bytes, cudaMemcpyHostToDevice, s));
-    else if (on_device && in_bytes)  // only the scale tables were staged
+    if (in_bytes)  // host views: everything; device views: only the scale tables were staged
       CUDA_TRYM(cudaMemcpyAsync(M.in_arena.d, M.h_in.h, in_bytes, cudaMemcpyHostToDevice, s));
     CUDA_TRYM(cudaMemcpyAsync(d_probs, P.data(), sizeof(ProjProblem) * count, cudaMemcpyHostToDevice, s));
     grid_build_kernel<<<count, 256, 0, s>>>(d_probs);
@@ -796,9 +814,10 @@ static int run_projection(Matcher& M, int count, int kind, const orb_frame_view*
     const size_t out_bytes = M.out_arena.used;
     CUDA_TRYM(cudaMemcpyAsync(M.h_out.h, M.out_arena.d, out_bytes, cudaMemcpyDeviceToHost, s));
     CUDA_TRYM(cudaEventRecord(M.ev1, s));
-    if (M.async_mode && on_device) {
+    if (allow_async && M.async_mode && on_device) {
       // results land in `results` at match_synchronize() / the next batch on this handle
       M.pending = true; M.pending_count = count; M.pending_off = out_off; M.pending_results = results;
+      M.pending_P = P; M.pending_in_bytes = in_bytes;
       return count;
     }
     CUDA_TRYM(cudaStreamSynchronize(s));

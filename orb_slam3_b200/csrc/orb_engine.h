@@ -90,6 +90,18 @@ struct Engine {
   int *d_xofs = nullptr, *d_yofs = nullptr, *d_pattern_t = nullptr;
   short2 *d_alpha = nullptr, *d_beta = nullptr;
   orb_keypoint* d_kps = nullptr;
+  // Results are double-buffered: every extract_batch_* call writes the set the previous call did not use, so the
+  // keypoints / descriptors / counts of call i stay valid (for matchers still reading them on another stream)
+  // until call i + 2.  d_kps / d_desc / d_n / d_mono always point at the set of the latest call.
+  orb_keypoint* d_kps_buf[2] = {nullptr, nullptr};
+  uint8_t* d_desc_buf[2] = {nullptr, nullptr};
+  int* d_n_buf[2] = {nullptr, nullptr};
+  int* d_mono_buf[2] = {nullptr, nullptr};
+  int out_idx = 0;
+  void flip_outputs() {
+    out_idx ^= 1;
+    d_kps = d_kps_buf[out_idx]; d_desc = d_desc_buf[out_idx]; d_n = d_n_buf[out_idx]; d_mono = d_mono_buf[out_idx];
+  }
   LevelDev* d_levels = nullptr;
   CellDesc* d_cells = nullptr;
   BlurTile* d_tiles = nullptr;

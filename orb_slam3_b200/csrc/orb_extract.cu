@@ -407,17 +407,64 @@ struct FastGeom {
   int smap_pitch, smap_bytes;             // score map with a one-pixel zero frame
   int queue_cap;                          // pre-test survivors of one cell (<= band pixels)
   int per_warp_bytes;
-  int align_mask;                         // the box starts at x0 & ~align_mask (3 or 15)
 };
 constexpr int FASTW_WARPS = 8;
 
-__device__ __forceinline__ uint32_t fast_gt4_msb(uint32_t d, uint32_t K, bool hi) {
+template <bool HI>
+__device__ __forceinline__ uint32_t fast_gt4_msb(uint32_t d, uint32_t K) {
   // byte-wise d > t, result in bit 7 of every byte (other bits are garbage): t < 128: ((d & 0x7f) + 127 - t) | d,
   // t >= 128: ((d & 0x7f) + 255 - t) & d
   const uint32_t s = (d & 0x7f7f7f7fu) + K;
-  return hi ? (s & d) : (s | d);
+  return HI ? (s & d) : (s | d);
 }
 
+// Packed 4-diameter rejection test of one cell at threshold K (fast_gt4_msb) and compaction of the survivors into
+// `queue` with one ballot per byte lane.  PWD = tile pitch in words (compile-time for the common 64-byte box).
+template <bool HI, int PWD_C>
+__device__ __forceinline__ int fast_pretest(const uint32_t* __restrict__ tw32, int pwd_rt, unsigned short* queue, int nitems,
+                                            int ng, int g0, unsigned magic_g, int ox, int bw, uint32_t K, int lane) {
+  const int PWD = PWD_C ? PWD_C : pwd_rt;
+  const unsigned lt = (1u << lane) - 1u;
+  int qn = 0;
+  for (int base = 0; base < nitems; base += 32) {
+    const int idx = base + lane;
+    uint32_t m = 0;
+    int y = 0, c0 = 0;
+    if (idx < nitems) {
+      y = (int)(((unsigned)idx * magic_g) >> 20);
+      const int g = g0 + (idx - y * ng);
+      const uint32_t* rc = tw32 + (y + 3) * PWD + g;
+      const uint32_t v = rc[0];
+      const uint32_t r0 = rc[3 * PWD], r8 = rc[-3 * PWD];
+      const uint32_t r4 = __funnelshift_r(rc[0], rc[1], 24), r12 = __funnelshift_r(rc[-1], rc[0], 8);
+      const uint32_t* rp = rc + 2 * PWD;
+      const uint32_t* rm = rc - 2 * PWD;
+      const uint32_t r2 = __funnelshift_r(rp[0], rp[1], 16), r14 = __funnelshift_r(rp[-1], rp[0], 16);
+      const uint32_t r6 = __funnelshift_r(rm[0], rm[1], 16), r10 = __funnelshift_r(rm[-1], rm[0], 16);
+      m = fast_gt4_msb<HI>(__vabsdiffu4(r0, v), K) | fast_gt4_msb<HI>(__vabsdiffu4(r8, v), K);
+      m &= fast_gt4_msb<HI>(__vabsdiffu4(r4, v), K) | fast_gt4_msb<HI>(__vabsdiffu4(r12, v), K);
+      m &= fast_gt4_msb<HI>(__vabsdiffu4(r2, v), K) | fast_gt4_msb<HI>(__vabsdiffu4(r10, v), K);
+      m &= fast_gt4_msb<HI>(__vabsdiffu4(r6, v), K) | fast_gt4_msb<HI>(__vabsdiffu4(r14, v), K);
+      m &= 0x80808080u;
+      c0 = 4 * g - (ox + 3);  // band x of byte 0; only bytes whose column lies in [0, bw) count
+      if (c0 < 0) m &= 0xffffffffu << (8 * -c0);
+      if (c0 + 3 >= bw) m &= 0xffffffffu >> (8 * (c0 + 4 - bw));
+    }
+    if (__any_sync(0xffffffffu, m != 0)) {
+      const unsigned short e0 = (unsigned short)((y << 7) + c0);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const bool pk = (m >> (8 * k + 7)) & 1u;
+        const unsigned bal = __ballot_sync(0xffffffffu, pk);
+        if (pk) queue[qn + __popc(bal & lt)] = (unsigned short)(e0 + k);
+        qn += __popc(bal);
+      }
+    }
+  }
+  return qn;
+}
+
+template <int TP_C>
 __global__ void __launch_bounds__(FASTW_WARPS * 32)
 fast_warp_kernel(const CUtensorMap* __restrict__ maps, int frame0, int nframes, const CellDesc* __restrict__ cells,
                  int num_cells, const LevelDev* __restrict__ lv, int ini_th, int min_th, Cand* __restrict__ cand,
@@ -430,12 +477,10 @@ fast_warp_kernel(const CUtensorMap* __restrict__ maps, int frame0, int nframes, 
   unsigned short* queue = reinterpret_cast<unsigned short*>(smap + G.smap_bytes);
   const unsigned bar0 = (unsigned)__cvta_generic_to_shared(&bars[warp][0]);
   const unsigned tile0 = (unsigned)__cvta_generic_to_shared(wbase);
-  const int SW = G.smap_pitch, TP = G.tile_pitch;
-  const long long total = (long long)num_cells * nframes;
-  const long long gw = (long long)blockIdx.x * FASTW_WARPS + warp, NW = (long long)gridDim.x * FASTW_WARPS;
-  // all mbarriers are initialised by one thread at CTA-uniform addresses (ptxas turns an init at a per-warp
-  // address into a plain store + SYNCS.CCTL sequence that faulted as an illegal instruction on the B200); this is
-  // the only block-wide barrier of the kernel
+  const int SW = G.smap_pitch, TP = TP_C ? TP_C : G.tile_pitch;
+  const int total = num_cells * nframes;  // host-checked < 2^31
+  const int gw = blockIdx.x * FASTW_WARPS + warp, NW = gridDim.x * FASTW_WARPS;
+  // all mbarriers are initialised by one thread at CTA-uniform addresses; the only block-wide barrier of the kernel
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int w = 0; w < FASTW_WARPS; w++) {
@@ -446,22 +491,22 @@ fast_warp_kernel(const CUtensorMap* __restrict__ maps, int frame0, int nframes, 
   }
   for (int i = lane; i < G.smap_bytes / 4; i += 32) reinterpret_cast<uint32_t*>(smap)[i] = 0;
   __syncthreads();
-  auto issue = [&](long long item, int slot) {  // lane 0 only
-    const int f = (int)(item / num_cells), c = (int)(item - (long long)f * num_cells);
+  auto issue = [&](int item, int slot) {  // lane 0 only
+    const int f = item / num_cells, c = item - f * num_cells;
     const CellDesc cd = cells[c];
     const unsigned bar = bar0 + 8 * slot, dst = tile0 + slot * G.tile_bytes;
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(G.tile_bytes) : "memory");
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(dst), "l"(maps + cd.level), "r"(bar), "r"(cd.x0 & ~G.align_mask), "r"(cd.y0), "r"(frame0 + f)
+        ::"r"(dst), "l"(maps + cd.level), "r"(bar), "r"(cd.x0 & ~15), "r"(cd.y0), "r"(frame0 + f)
         : "memory");
   };
   if (gw < total && lane == 0) issue(gw, 0);
-  const uint32_t hi_ini = ini_th >= 128, hi_min = min_th >= 128;
+  const bool hi_ini = ini_th >= 128, hi_min = min_th >= 128;
   const uint32_t K_ini = 0x01010101u * (uint32_t)(hi_ini ? 255 - ini_th : 127 - ini_th);
   const uint32_t K_min = 0x01010101u * (uint32_t)(hi_min ? 255 - min_th : 127 - min_th);
   int n = 0;
-  for (long long item = gw; item < total; item += NW, n++) {
+  for (int item = gw; item < total; item += NW, n++) {
     const int slot = n & 1;
     // the other slot was read during the previous iteration; every lane is past it (the __syncwarp that ends
     // an iteration), so its refill can start now and overlaps this whole cell
@@ -479,71 +524,26 @@ fast_warp_kernel(const CUtensorMap* __restrict__ maps, int frame0, int nframes, 
             : "memory");
       }
     }
-    const int f = (int)(item / num_cells), ci = (int)(item - (long long)f * num_cells);
+    const int f = item / num_cells, ci = item - f * num_cells;
     const CellDesc cd = cells[ci];
     const uint8_t* tile = wbase + slot * G.tile_bytes;
     const int bw = cd.x1 - cd.x0 - 6, bh = cd.y1 - cd.y0 - 6;
     if (bw > 0 && bh > 0) {
-      const int ox = cd.x0 & G.align_mask;
+      const int ox = cd.x0 & 15;
       // 4-pixel groups = aligned words of a tile row that overlap the band columns [ox+3, ox+3+bw)
       const int g0 = (ox + 3) >> 2, ng = ((ox + 3 + bw + 3) >> 2) - g0;
       const int nitems = bh * ng;
       const unsigned magic_g = ((1u << 20) + ng - 1) / ng;  // idx / ng for idx < 2^20 / ng
       const uint32_t* tw32 = reinterpret_cast<const uint32_t*>(tile);
-      const int PWD = TP >> 2;
       int qn = 0, total_keep = 0;
       for (int pass = 0; pass < 2; pass++) {
         const int th_fast = pass == 0 ? ini_th : min_th;
         const uint32_t K = pass == 0 ? K_ini : K_min;
-        const bool hi = pass == 0 ? hi_ini : hi_min;
-        qn = 0;
-        // 2. packed 4-diameter rejection test, 16 visits (512 groups) per chunk, survivors appended to the queue
-        for (int base = 0; base < nitems; base += 512) {
-          unsigned long long pass_bits = 0;
-#pragma unroll 2
-          for (int it = 0; it < 16; it++) {
-            const int idx = base + it * 32 + lane;
-            if (idx >= nitems) break;
-            const int y = (int)(((unsigned)idx * magic_g) >> 20), g = g0 + (idx - y * ng);
-            const uint32_t* rc = tw32 + (y + 3) * PWD + g;
-            const uint32_t v = rc[0];
-            const uint32_t r0 = rc[3 * PWD], r8 = rc[-3 * PWD];
-            const uint32_t r4 = __funnelshift_r(rc[0], rc[1], 24), r12 = __funnelshift_r(rc[-1], rc[0], 8);
-            const uint32_t* rp = rc + 2 * PWD;
-            const uint32_t* rm = rc - 2 * PWD;
-            const uint32_t r2 = __funnelshift_r(rp[0], rp[1], 16), r14 = __funnelshift_r(rp[-1], rp[0], 16);
-            const uint32_t r6 = __funnelshift_r(rm[0], rm[1], 16), r10 = __funnelshift_r(rm[-1], rm[0], 16);
-            uint32_t m = fast_gt4_msb(__vabsdiffu4(r0, v), K, hi) | fast_gt4_msb(__vabsdiffu4(r8, v), K, hi);
-            m &= fast_gt4_msb(__vabsdiffu4(r4, v), K, hi) | fast_gt4_msb(__vabsdiffu4(r12, v), K, hi);
-            m &= fast_gt4_msb(__vabsdiffu4(r2, v), K, hi) | fast_gt4_msb(__vabsdiffu4(r10, v), K, hi);
-            m &= fast_gt4_msb(__vabsdiffu4(r6, v), K, hi) | fast_gt4_msb(__vabsdiffu4(r14, v), K, hi);
-            m &= 0x80808080u;
-            if (m) {
-              unsigned nib = ((m >> 7) & 1u) | ((m >> 14) & 2u) | ((m >> 21) & 4u) | ((m >> 28) & 8u);
-              const int c0 = 4 * g - (ox + 3);  // band x of byte 0; keep bytes whose column lies inside the band
-              if (c0 < 0) nib &= ~((1u << (-c0)) - 1u);
-              if (c0 + 3 >= bw) nib &= (1u << max(bw - c0, 0)) - 1u;
-              pass_bits |= (unsigned long long)nib << (4 * it);
-            }
-          }
-          const int cnt = __popcll(pass_bits);
-          int incl = cnt;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-          }
-          int qpos = qn + incl - cnt;
-          qn += __shfl_sync(0xffffffffu, incl, 31);
-          while (pass_bits) {
-            const int bit = __ffsll((long long)pass_bits) - 1;
-            pass_bits &= pass_bits - 1;
-            const int idx = base + (bit >> 2) * 32 + lane;
-            const int y = (int)(((unsigned)idx * magic_g) >> 20), g = g0 + (idx - y * ng);
-            const int x = 4 * g + (bit & 3) - (ox + 3);
-            queue[qpos++] = (unsigned short)((y << 7) | x);
-          }
-        }
+        // 2. packed 4-diameter rejection test; survivors go to the queue (order inside a cell is irrelevant)
+        if (pass == 0 ? hi_ini : hi_min)
+          qn = fast_pretest<true, TP_C / 4>(tw32, TP >> 2, queue, nitems, ng, g0, magic_g, ox, bw, K, lane);
+        else
+          qn = fast_pretest<false, TP_C / 4>(tw32, TP >> 2, queue, nitems, ng, g0, magic_g, ox, bw, K, lane);
         __syncwarp();
         // 3. exact segment test + score of the queued pixels on dense lanes
         for (int q = lane; q < qn; q += 32) {
@@ -1222,11 +1222,16 @@ int Engine::ensure(int rows, int cols, int batch) {
     const size_t smem = (size_t)fw_per_warp * FASTW_WARPS;
     const char* env = getenv("ORB_B200_FAST");  // "cta": the CTA-per-cell kernel
     fw_enabled = !(env && !strcmp(env, "cta")) && fw_tile_pitch <= 256 && fw_tile_rows <= 256 && smem <= 200 * 1024 &&
-                 max_tw - 6 <= 127 && max_th - 6 <= 127 && (size_t)fw_tile_pitch * fw_tile_rows == (size_t)tile_bytes;
+                 max_tw - 6 <= 127 && max_th - 6 <= 127 && (size_t)fw_tile_pitch * fw_tile_rows == (size_t)tile_bytes &&
+                 (long long)cells.size() * batch < (1ll << 30);
     if (fw_enabled) {
-      CUDA_TRY(raise_dynamic_smem((const void*)fast_warp_kernel, smem, device));
+      const void* kfn = fw_tile_pitch == 64 ? (const void*)fast_warp_kernel<64> : (const void*)fast_warp_kernel<0>;
+      CUDA_TRY(raise_dynamic_smem(kfn, smem, device));
       int per_sm = 0, sms = 0;
-      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fast_warp_kernel, FASTW_WARPS * 32, smem));
+      if (fw_tile_pitch == 64)
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fast_warp_kernel<64>, FASTW_WARPS * 32, smem));
+      else
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fast_warp_kernel<0>, FASTW_WARPS * 32, smem));
       CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
       fw_grid = sms * std::max(per_sm, 1);
     }
@@ -1241,11 +1246,15 @@ int Engine::ensure(int rows, int cols, int batch) {
   if (dalloc(&d_slot, sel_frame_elems * B)) return ORB_E_CUDA;
   if (dalloc(&d_cand_count, (size_t)nlevels * B)) return ORB_E_CUDA;
   if (dalloc(&d_sel_count, (size_t)nlevels * B)) return ORB_E_CUDA;
-  if (dalloc(&d_n, B)) return ORB_E_CUDA;
-  if (dalloc(&d_mono, B)) return ORB_E_CUDA;
+  for (int k = 0; k < 2; k++) {
+    if (dalloc(&d_n_buf[k], B)) return ORB_E_CUDA;
+    if (dalloc(&d_mono_buf[k], B)) return ORB_E_CUDA;
+    if (dalloc(&d_kps_buf[k], (size_t)out_cap * B)) return ORB_E_CUDA;
+    if (dalloc(&d_desc_buf[k], (size_t)out_cap * 32 * B)) return ORB_E_CUDA;
+  }
+  out_idx = 1;
+  flip_outputs();
   if (dalloc(&d_lap, 2 * B)) return ORB_E_CUDA;
-  if (dalloc(&d_kps, (size_t)out_cap * B)) return ORB_E_CUDA;
-  if (dalloc(&d_desc, (size_t)out_cap * 32 * B)) return ORB_E_CUDA;
   if (dalloc(&d_levels, (size_t)nlevels)) return ORB_E_CUDA;
   if (dalloc(&d_cells, cells.size())) return ORB_E_CUDA;
   if (dalloc(&d_tiles, tiles.size())) return ORB_E_CUDA;
@@ -1368,12 +1377,16 @@ int Engine::run_device(int f0, int batch, const int* lap_host, cudaStream_t s) {
     FastGeom G;
     G.tile_pitch = fw_tile_pitch; G.tile_rows = fw_tile_rows; G.tile_bytes = fw_tile_pitch * fw_tile_rows;
     G.smap_pitch = fw_smap_pitch; G.smap_bytes = fw_smap_bytes; G.queue_cap = fw_queue_cap; G.per_warp_bytes = fw_per_warp;
-    G.align_mask = fw_align_mask;
     const long long items = (long long)num_cells * B;
     const int grid = (int)std::min<long long>(fw_grid, (items + FASTW_WARPS - 1) / FASTW_WARPS);
-    fast_warp_kernel<<<grid, FASTW_WARPS * 32, (size_t)fw_per_warp * FASTW_WARPS, s>>>(
-        (const CUtensorMap*)d_tmaps_raw + 16, f0, B, d_cells, num_cells, d_levels, ini_th, min_th, cand, cand_frame_elems,
-        cand_count, nlevels, G);
+    if (fw_tile_pitch == 64)
+      fast_warp_kernel<64><<<grid, FASTW_WARPS * 32, (size_t)fw_per_warp * FASTW_WARPS, s>>>(
+          (const CUtensorMap*)d_tmaps_raw + 16, f0, B, d_cells, num_cells, d_levels, ini_th, min_th, cand, cand_frame_elems,
+          cand_count, nlevels, G);
+    else
+      fast_warp_kernel<0><<<grid, FASTW_WARPS * 32, (size_t)fw_per_warp * FASTW_WARPS, s>>>(
+          (const CUtensorMap*)d_tmaps_raw + 16, f0, B, d_cells, num_cells, d_levels, ini_th, min_th, cand, cand_frame_elems,
+          cand_count, nlevels, G);
   } else {
     fast_cells_kernel<<<dim3(num_cells, B), FAST_THREADS, 0, s>>>((const CUtensorMap*)d_tmaps_raw, f0, d_cells, d_levels, ini_th, min_th, cand,
                                                                   cand_frame_elems, cand_count, nlevels);
@@ -1414,6 +1427,7 @@ int Engine::extract_batch_host(int batch, const uint8_t* const* imgs, int rows, 
   int rc = ensure(rows, cols, std::max(batch, cap_batch_hint));
   if (rc) return rc;
   CUDA_TRY(cudaSetDevice(device));
+  flip_outputs();
   last_batch = batch;
   last_stream = stream;
   cudaStream_t s = stream;
@@ -1432,9 +1446,18 @@ int Engine::extract_batch_host(int batch, const uint8_t* const* imgs, int rows, 
   stage_begin(0, s);
   for (int c = 0; c < nchunks; c++) {
     const int f0 = c * chunk, fb = std::min(chunk, batch - f0);
-    for (int b = f0; b < f0 + fb; b++)
-      CUDA_TRY(cudaMemcpy2DAsync(d_pyr + (size_t)b * pyr_frame_bytes, L0.pitch, imgs[b], step, cols, rows,
-                                 cudaMemcpyHostToDevice, nchunks > 1 ? stream_in : s));
+    // frames that lie back to back in host memory with dense rows (a pinned [B][H][W] block) go up as ONE copy
+    // per chunk: a "2-D" copy whose rows are whole level-0 images and whose destination pitch is the slab stride
+    bool dense = step == (size_t)cols && L0.pitch == cols;
+    for (int b = f0 + 1; b < f0 + fb && dense; b++) dense = imgs[b] == imgs[b - 1] + (size_t)rows * step;
+    if (dense) {
+      CUDA_TRY(cudaMemcpy2DAsync(d_pyr + (size_t)f0 * pyr_frame_bytes, pyr_frame_bytes, imgs[f0], (size_t)rows * cols,
+                                 (size_t)rows * cols, fb, cudaMemcpyHostToDevice, nchunks > 1 ? stream_in : s));
+    } else {
+      for (int b = f0; b < f0 + fb; b++)
+        CUDA_TRY(cudaMemcpy2DAsync(d_pyr + (size_t)b * pyr_frame_bytes, L0.pitch, imgs[b], step, cols, rows,
+                                   cudaMemcpyHostToDevice, nchunks > 1 ? stream_in : s));
+    }
     if (nchunks > 1) CUDA_TRY(cudaEventRecord(chunk_events[2 * c], stream_in));
   }
   stage_end(0, s, 0);
@@ -1488,6 +1511,7 @@ int Engine::extract_batch_device(int batch, const uint8_t* d_imgs, size_t frame_
   int rc = ensure(rows, cols, std::max(batch, cap_batch_hint));
   if (rc) return rc;
   CUDA_TRY(cudaSetDevice(device));
+  flip_outputs();
   cudaStream_t s = user ? user : stream;
   last_stream = s;
   const LevelDev& L0 = levels[0];

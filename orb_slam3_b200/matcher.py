@@ -73,10 +73,10 @@ class ORBmatcher:
         bw = np.ascontiguousarray(np.zeros(B) if backward is None else backward, np.int32)
         res = np.zeros(B, np.int32)
         self._last_res = res  # must outlive an asynchronous batch
-        if on_device:
+        if int(on_device) == 1:
             outs = None
             arr = (C.c_void_p * B)(*assign_ptrs)
-        else:
+        else:  # 0: host views; 2: only keys / u_right / desc of the frame views are device pointers
             outs = [np.empty(c.n, np.int32) for c in curs]
             arr = (C.c_void_p * B)(*[o.ctypes.data for o in outs])
         check(self._lib.match_project_last_batch(self._h, B, ca, la, ptr(T), ptr(fw), ptr(bw), float(th),
@@ -91,7 +91,7 @@ class ORBmatcher:
         ma = (orb_mappoint_view * B)(*mps)
         res = np.zeros(B, np.int32)
         self._last_res = res
-        if on_device:
+        if int(on_device) == 1:
             outs = None
             arr = (C.c_void_p * B)(*assign_ptrs)
         else:
