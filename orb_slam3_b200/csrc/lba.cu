@@ -738,50 +738,73 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
       if (lane == 0) zr[i % WIN] = M[(size_t)n * n + i];
     }
   };
+  // pivot block of panel p, one thread, registers only: factors rows/cols [k0, k0+nb) of the ring in place,
+  // leaves L (strict lower) in Lb, 1/D in Dib, writes L and D to M
+  auto pivot = [&](int p) {
+    const int k0 = p * WPB, nb = min(WPB, n - k0);
+    double a[WPB][WPB];
+#pragma unroll
+    for (int r = 0; r < WPB; r++)
+#pragma unroll
+      for (int c = 0; c < WPB; c++)
+        a[r][c] = (r < nb && c <= r) ? A[((k0 + r) % WIN) * WIN_P + (k0 + c) % WIN] : (r == c ? 1.0 : 0.0);
+#pragma unroll
+    for (int k = 0; k < WPB; k++) {
+      const double d = a[k][k];
+      if (d == 0.0) *fail = 1.0;
+      double inv = (double)__frcp_rn((float)d);
+      inv = inv * (2.0 - d * inv);
+      inv = inv * (2.0 - d * inv);
+      Dib[k] = inv;
+      double l[WPB];
+#pragma unroll
+      for (int r = k + 1; r < WPB; r++) l[r] = a[r][k] * inv;
+#pragma unroll
+      for (int r = k + 1; r < WPB; r++)
+#pragma unroll
+        for (int m = k + 1; m <= r; m++) a[r][m] -= l[r] * a[m][k];
+#pragma unroll
+      for (int r = k + 1; r < WPB; r++) a[r][k] = l[r];
+    }
+#pragma unroll
+    for (int r = 0; r < WPB; r++)
+#pragma unroll
+      for (int c = 0; c < WPB; c++) {
+        Lb[r][c] = c < r ? a[r][c] : 0.0;
+        if (r < nb && c <= r) M[(size_t)(k0 + r) * n + k0 + c] = a[r][c];  // L below, D on the diagonal
+      }
+  };
+  // one 8x8 tile of the rank-nb update of panel (r0, nr): C -= L_i (8x8) * (L*D)_j^T, two fp64 DMMA m8n8k4;
+  // fragment layout A[g][t], B[t][g], C[g][2t], C[g][2t+1] with g = lane / 4, t = lane % 4
+  auto update_tile = [&](int tile, int r0, int nr) {
+    const int g = lane >> 2, t = lane & 3;
+    int ti = (int)((sqrtf(8.f * (float)tile + 1.f) - 1.f) * 0.5f);
+    while ((ti + 1) * (ti + 2) / 2 <= tile) ti++;
+    while (ti * (ti + 1) / 2 > tile) ti--;
+    const int tj = tile - ti * (ti + 1) / 2;
+    const int wi = 8 * ti + g, wj = 8 * tj + 2 * t;
+    const double a0 = -Lt[t * WIN_LP + wi], a1 = -Lt[(t + 4) * WIN_LP + wi];
+    const double b0 = LDt[t * WIN_LP + 8 * tj + g], b1 = LDt[(t + 4) * WIN_LP + 8 * tj + g];
+    double* row = (wi == nr) ? zr : A + ((r0 + min(wi, nr)) % WIN) * WIN_P;  // the rhs row has no column of its own
+    const bool ok0 = wi <= nr && wj < nr && wj <= wi, ok1 = wi <= nr && wj + 1 < nr && wj + 1 <= wi;
+    double* p0 = row + (r0 + wj) % WIN;
+    double* p1 = row + (r0 + wj + 1) % WIN;
+    double c0 = ok0 ? *p0 : 0.0, c1 = ok1 ? *p1 : 0.0;
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a0), "d"(b0));
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a1), "d"(b1));
+    if (ok0) *p0 = c0;
+    if (ok1) *p1 = c1;
+  };
   load_rows(0, rlast[0], 0, 0, WIN_THREADS / 32);
+  __syncthreads();
+  if (tid == 0) pivot(0);
   __syncthreads();
   for (int p = 0; p < npan; p++) {
     const int k0 = p * WPB, nb = min(WPB, n - k0);
-    const int R = rlast[p];  // last row of the window; rows [k0, R] are resident
-    // ---- (1) pivot block, one thread, registers only; meanwhile the other warps bring in the rows that the
-    //      NEXT panel adds to the window (their ring slots are free and nothing below touches them)
-    if (tid == 0) {
-      double a[WPB][WPB];
-#pragma unroll
-      for (int r = 0; r < WPB; r++)
-#pragma unroll
-        for (int c = 0; c < WPB; c++)
-          a[r][c] = (r < nb && c <= r) ? A[((k0 + r) % WIN) * WIN_P + (k0 + c) % WIN] : (r == c ? 1.0 : 0.0);
-#pragma unroll
-      for (int k = 0; k < WPB; k++) {
-        const double d = a[k][k];
-        if (d == 0.0) *fail = 1.0;
-        double inv = (double)__frcp_rn((float)d);
-        inv = inv * (2.0 - d * inv);
-        inv = inv * (2.0 - d * inv);
-        Dib[k] = inv;
-        double l[WPB];
-#pragma unroll
-        for (int r = k + 1; r < WPB; r++) l[r] = a[r][k] * inv;
-#pragma unroll
-        for (int r = k + 1; r < WPB; r++)
-#pragma unroll
-          for (int m = k + 1; m <= r; m++) a[r][m] -= l[r] * a[m][k];
-#pragma unroll
-        for (int r = k + 1; r < WPB; r++) a[r][k] = l[r];
-      }
-#pragma unroll
-      for (int r = 0; r < WPB; r++)
-#pragma unroll
-        for (int c = 0; c < WPB; c++) {
-          Lb[r][c] = c < r ? a[r][c] : 0.0;
-          if (r < nb && c <= r) M[(size_t)(k0 + r) * n + k0 + c] = a[r][c];  // L below, D on the diagonal
-        }
-    } else if (warp >= 1 && p + 1 < npan) {
-      load_rows(R + 1, rlast[p + 1], k0 + WPB, 1, WIN_THREADS / 32 - 1);
-    }
-    __syncthreads();
-    // ---- (2) panel rows [k0+nb, R] and the rhs row: forward substitution, one thread per row
+    const int R = rlast[p];  // last row of the window; rows [k0, R] are resident, the pivot block is factored
+    // ---- (A) panel rows [k0+nb, R] and the rhs row: forward substitution, one thread per row
     const int r0 = k0 + nb, nr = R - r0 + 1;  // nr rows under the pivot block; slot nr = rhs
     if (tid <= nr) {
       const bool rhs = tid == nr;
@@ -806,32 +829,23 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
         if (m < nb) dst[m] = l[m];
     }
     __syncthreads();
-    // ---- (3) rank-nb update of the window rows / columns [r0, R] (+ rhs) on the tensor pipe: 8x8 tiles of the
-    //      lower triangle, one warp per tile, C -= L_i (8x8) * (L*D)_j^T as two fp64 DMMA m8n8k4 (k = 0..3, 4..7);
-    //      fragment layout: A[g][t], B[t][g], C[g][2t], C[g][2t+1] with g = lane / 4, t = lane % 4
+    // ---- (B) rank-nb update of the window on the tensor pipe, with look-ahead: warp 0 updates the tile that
+    //      holds the NEXT pivot block first and then factors it (one thread) while the other warps update the
+    //      rest of the window and bring in the rows the next panel adds to it
     {
       const int T8 = (nr + 1 + 7) >> 3;
       const int ntile = T8 * (T8 + 1) / 2;
-      const int g = lane >> 2, t = lane & 3;
-      for (int tile = warp; tile < ntile; tile += WIN_THREADS / 32) {
-        int ti = (int)((sqrtf(8.f * (float)tile + 1.f) - 1.f) * 0.5f);
-        while ((ti + 1) * (ti + 2) / 2 <= tile) ti++;
-        while (ti * (ti + 1) / 2 > tile) ti--;
-        const int tj = tile - ti * (ti + 1) / 2;
-        const int wi = 8 * ti + g, wj = 8 * tj + 2 * t;
-        const double a0 = -Lt[t * WIN_LP + wi], a1 = -Lt[(t + 4) * WIN_LP + wi];
-        const double b0 = LDt[t * WIN_LP + 8 * tj + g], b1 = LDt[(t + 4) * WIN_LP + 8 * tj + g];
-        double* row = (wi == nr) ? zr : A + ((r0 + min(wi, nr)) % WIN) * WIN_P;  // the rhs row has no column of its own
-        const bool ok0 = wi <= nr && wj < nr && wj <= wi, ok1 = wi <= nr && wj + 1 < nr && wj + 1 <= wi;
-        double* p0 = row + (r0 + wj) % WIN;
-        double* p1 = row + (r0 + wj + 1) % WIN;
-        double c0 = ok0 ? *p0 : 0.0, c1 = ok1 ? *p1 : 0.0;
-        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                     : "+d"(c0), "+d"(c1) : "d"(a0), "d"(b0));
-        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                     : "+d"(c0), "+d"(c1) : "d"(a1), "d"(b1));
-        if (ok0) *p0 = c0;
-        if (ok1) *p1 = c1;
+      const bool more = p + 1 < npan;
+      // rows of the next pivot block that are not resident yet (narrow or ending envelope) are loaded by warp 0
+      const int pre = more ? min(r0 + WPB - 1, n - 1) : R;
+      if (warp == 0) {
+        if (pre > R) load_rows(R + 1, pre, r0, 0, 1);
+        update_tile(0, r0, nr);
+        __syncwarp();
+        if (tid == 0 && more) pivot(p + 1);
+      } else {
+        if (more) load_rows(max(R, pre) + 1, rlast[p + 1], r0, 1, WIN_THREADS / 32 - 1);
+        for (int tile = warp; tile < ntile; tile += WIN_THREADS / 32 - 1) update_tile(tile, r0, nr);
       }
     }
     __syncthreads();

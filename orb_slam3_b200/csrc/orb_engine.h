@@ -79,8 +79,15 @@ struct Engine {
   // device state
   bool initialized = false;
   cudaStream_t stream = nullptr, last_stream = nullptr, stream_in = nullptr, stream_out = nullptr;
-  cudaStream_t stream_side = nullptr;
-  cudaEvent_t ev_pyr_done = nullptr, ev_blur_done = nullptr;
+  // lanes: a device-resident batch can be cut into up to MAX_LANES sub-batches that run the whole kernel chain on
+  // their own streams (lane 0 = the caller's stream), so the latency-bound kernels of one sub-batch (octree) share
+  // the SMs with the issue-bound ones of another (FAST); every lane has its own blur side stream
+  static constexpr int MAX_LANES = 4;
+  cudaStream_t stream_side[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t stream_lane[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};   // [0] unused
+  cudaEvent_t ev_pyr_done[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr}, ev_blur_done[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_lane_go = nullptr, ev_lane_done[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
+  int lanes = 1;
   std::vector<cudaEvent_t> chunk_events;
   std::vector<void*> dev_allocs, host_allocs;
   uint8_t *d_pyr = nullptr, *d_blur = nullptr, *d_scratch = nullptr, *d_desc = nullptr, *d_stage = nullptr;
@@ -125,7 +132,7 @@ struct Engine {
   void stage_begin(int st, cudaStream_t s);
   void stage_end(int st, cudaStream_t s, int launches);
   int collect_times(double* ms, long long* launches, bool reset);
-  int run_device(int f0, int batch, const int* lap_host, cudaStream_t s);
+  int run_device(int f0, int batch, const int* lap_host, cudaStream_t s, int lane = 0);
   int extract_batch_host(int batch, const uint8_t* const* imgs, int rows, int cols, size_t step, const int* lap,
                          orb_keypoint* kps, uint8_t* desc, int cap, int* n, int* mono);
   int extract_batch_device(int batch, const uint8_t* d_imgs, size_t frame_stride, int rows, int cols, size_t step,

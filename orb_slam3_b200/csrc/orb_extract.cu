@@ -208,8 +208,9 @@ constexpr int FAST_TILE_PITCH = 96;  // TMA box columns (bytes): (x0 & 15) + wCe
 constexpr int FAST_BAND_MAX = 70;
 
 struct LevelTensorMaps {
-  CUtensorMap m[32];  // one 3-D (x, y, frame) uint8 map per pyramid level: [0,16) box of fast_cells_kernel,
-                      // [16,32) box of fast_warp_kernel
+  CUtensorMap m[64];  // one 3-D (x, y, frame) uint8 map per pyramid level: [0,16) box of fast_cells_kernel,
+                      // [16,32) box of fast_warp_kernel, [32,48) raw patch box of describe_tma_kernel,
+                      // [48,64) its blurred patch box (over the blurred slab)
 };
 
 __global__ void __launch_bounds__(FAST_THREADS)
@@ -944,6 +945,120 @@ describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blr
   }
 }
 
+// describe, TMA formulation: one warp per selected keypoint, its two patches arrive as 2-D tiles through the
+// tensor-memory accelerator -- the 31x31 raw patch of IC_Angle (box 48 x 32 bytes of the level's raw tensor) and
+// the 37x37 blurred patch of the steered pattern (box 64 x 38 bytes of the blurred tensor), both issued by lane 0
+// before any arithmetic and awaited on the warp's own mbarrier; the orientation moments and the 512 pattern
+// samples then read shared memory only.  Boxes start at the 16-byte aligned column left of the patch.
+constexpr int DT_WARPS = 8;
+constexpr int DT_RAW_P = 48, DT_RAW_R = 32, DT_BLR_P = 64, DT_BLR_R = 38;
+constexpr int DT_RAW_BYTES = DT_RAW_P * DT_RAW_R, DT_BLR_BYTES = DT_BLR_P * DT_BLR_R;  // 1536 + 2432: 128-byte multiples
+
+__global__ void __launch_bounds__(DT_WARPS * 32)
+describe_tma_kernel(const CUtensorMap* __restrict__ raw_maps, const CUtensorMap* __restrict__ blr_maps, int frame0,
+                    const int* __restrict__ sel, size_t sel_frame_stride, const int* __restrict__ sel_count,
+                    const int* __restrict__ slot, const LevelDev* __restrict__ lv, int nlevels,
+                    const int* __restrict__ warp_level, const int* __restrict__ pattern_t,
+                    orb_keypoint* __restrict__ kps, uint8_t* __restrict__ desc, int out_cap) {
+  __shared__ __align__(128) uint8_t s_raw[DT_WARPS][DT_RAW_BYTES];
+  __shared__ __align__(128) uint8_t s_blr[DT_WARPS][DT_BLR_BYTES];
+  __shared__ __align__(8) unsigned long long s_bar[DT_WARPS];
+  __shared__ int s_pat[1024];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 0; w < DT_WARPS; w++)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&s_bar[w])));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_pat[i] = pattern_t[i];
+  __syncthreads();
+  const int gw = blockIdx.x * DT_WARPS + warp;  // index in the sel slab
+  const int f = blockIdx.y;
+  const int level = warp_level[gw];
+  if (level < 0) return;
+  const LevelDev L = lv[level];
+  const int i = gw - L.sel_off;
+  if (i >= sel_count[f * nlevels + level]) return;
+  const int* rec = sel + (size_t)f * sel_frame_stride + 3 * (size_t)gw;
+  const int x = rec[0] + 16, y = rec[1] + 16, score = rec[2];  // add minBorder back (:884-885)
+  const int pos = slot[(size_t)f * sel_frame_stride / 3 + gw];
+  if (pos < 0) return;
+  const int ax = (x - 15) & ~15, bx = (x - 18) & ~15;
+  if (lane == 0) {
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar[warp]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(DT_RAW_BYTES + DT_BLR_BYTES) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"((unsigned)__cvta_generic_to_shared(s_raw[warp])), "l"(raw_maps + level), "r"(bar), "r"(ax), "r"(y - 15), "r"(frame0 + f)
+        : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"((unsigned)__cvta_generic_to_shared(s_blr[warp])), "l"(blr_maps + level), "r"(bar), "r"(bx), "r"(y - 18), "r"(frame0 + f)
+        : "memory");
+  }
+  {
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar[warp]);
+    unsigned done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n.reg .pred p;\n"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n"
+          "selp.u32 %0, 1, 0, p;\n}"
+          : "=r"(done)
+          : "r"(bar)
+          : "memory");
+    }
+  }
+  // ---- IC_Angle on the raw patch: lane <-> u = lane-15
+  int m10 = 0, m01 = 0;
+  if (lane < 31) {
+    const int u = lane - 15, au = abs(u);
+    const uint8_t* c = s_raw[warp] + 15 * DT_RAW_P + (x - ax) + u;
+    int colsum = 0;
+#pragma unroll
+    for (int v = -15; v <= 15; v++) {
+      const int val = (au <= c_umax[v < 0 ? -v : v]) ? (int)c[v * DT_RAW_P] : 0;
+      colsum += val;
+      m01 += v * val;
+    }
+    m10 = u * colsum;
+  }
+  m10 = __reduce_add_sync(0xffffffffu, m10);
+  m01 = __reduce_add_sync(0xffffffffu, m01);
+  const float angle = fast_atan2_deg((float)m01, (float)m10);
+  // ---- steered BRIEF: lane <-> descriptor byte
+  const float factorPI = 0.017453292519943295f;  // (float)(CV_PI/180.f)
+  const float ang = __fmul_rn(angle, factorPI);
+  const float a = glibc_sincosf::cosf_exact<true>(ang), b = glibc_sincosf::sinf_exact<true>(ang);
+  const uint8_t* bc = s_blr[warp] + 18 * DT_BLR_P + (x - bx);
+  int val = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const float x0 = (float)s_pat[(4 * k) * 32 + lane], y0 = (float)s_pat[(4 * k + 1) * 32 + lane];
+    const float x1 = (float)s_pat[(4 * k + 2) * 32 + lane], y1 = (float)s_pat[(4 * k + 3) * 32 + lane];
+    const int ry0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+    const int rx0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+    const int ry1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+    const int rx1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+    const int t0 = bc[ry0 * DT_BLR_P + rx0], t1 = bc[ry1 * DT_BLR_P + rx1];
+    val |= (t0 < t1) << k;
+  }
+  desc[((size_t)f * out_cap + pos) * 32 + lane] = (uint8_t)val;
+  if (lane == 0) {
+    orb_keypoint kp;
+    float fx = (float)x, fy = (float)y;
+    if (level != 0) { fx = __fmul_rn(fx, L.scale); fy = __fmul_rn(fy, L.scale); }
+    kp.x = fx; kp.y = fy;
+    kp.size = (float)L.patch_size;
+    kp.angle = angle;
+    kp.response = (float)score;
+    kp.octave = level;
+    kp.class_id = -1;
+    kps[(size_t)f * out_cap + pos] = kp;
+  }
+}
+
 // cosf / sinf of csrc/glibc_sincosf.h on the device (debug hook of the parity tests)
 __global__ void sincos_debug_kernel(const float* __restrict__ x, float* __restrict__ c, float* __restrict__ s, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -1035,10 +1150,17 @@ void Engine::release() {
   if (stream) cudaStreamDestroy(stream);
   if (stream_in) cudaStreamDestroy(stream_in);
   if (stream_out) cudaStreamDestroy(stream_out);
-  if (stream_side) cudaStreamDestroy(stream_side);
-  if (ev_pyr_done) cudaEventDestroy(ev_pyr_done);
-  if (ev_blur_done) cudaEventDestroy(ev_blur_done);
-  stream_side = nullptr; ev_pyr_done = ev_blur_done = nullptr;
+  for (int l = 0; l < MAX_LANES; l++) {
+    if (stream_side[l]) cudaStreamDestroy(stream_side[l]);
+    if (stream_lane[l]) cudaStreamDestroy(stream_lane[l]);
+    if (ev_pyr_done[l]) cudaEventDestroy(ev_pyr_done[l]);
+    if (ev_blur_done[l]) cudaEventDestroy(ev_blur_done[l]);
+    if (ev_lane_done[l]) cudaEventDestroy(ev_lane_done[l]);
+    stream_side[l] = stream_lane[l] = nullptr;
+    ev_pyr_done[l] = ev_blur_done[l] = ev_lane_done[l] = nullptr;
+  }
+  if (ev_lane_go) cudaEventDestroy(ev_lane_go);
+  ev_lane_go = nullptr;
   stream = stream_in = stream_out = nullptr;
   initialized = false;
   cap_rows = cap_cols = cap_batch = 0;
@@ -1065,9 +1187,18 @@ int Engine::ensure(int rows, int cols, int batch) {
   CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaStreamCreateWithFlags(&stream_in, cudaStreamNonBlocking));
   CUDA_TRY(cudaStreamCreateWithFlags(&stream_out, cudaStreamNonBlocking));
-  CUDA_TRY(cudaStreamCreateWithFlags(&stream_side, cudaStreamNonBlocking));
-  CUDA_TRY(cudaEventCreateWithFlags(&ev_pyr_done, cudaEventDisableTiming));
-  CUDA_TRY(cudaEventCreateWithFlags(&ev_blur_done, cudaEventDisableTiming));
+  for (int l = 0; l < MAX_LANES; l++) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&stream_side[l], cudaStreamNonBlocking));
+    if (l) CUDA_TRY(cudaStreamCreateWithFlags(&stream_lane[l], cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&ev_pyr_done[l], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&ev_blur_done[l], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&ev_lane_done[l], cudaEventDisableTiming));
+  }
+  CUDA_TRY(cudaEventCreateWithFlags(&ev_lane_go, cudaEventDisableTiming));
+  {
+    const char* env = getenv("ORB_B200_LANES");
+    lanes = env ? std::min(std::max(atoi(env), 1), (int)MAX_LANES) : 1;
+  }
   initialized = true;
   CUDA_TRY(cudaMemcpyToSymbol(c_pattern, h_pattern, sizeof(h_pattern)));
   CUDA_TRY(cudaMemcpyToSymbol(c_umax, umax, sizeof(umax)));
@@ -1325,7 +1456,7 @@ int Engine::collect_times(double* ms, long long* launches, bool reset) {
 
 // Everything between "level 0 is in the pyramid slab" and "results are in
 // d_kps/d_desc/d_n/d_mono" for frames [f0, f0+batch) of the slabs, on stream s.
-int Engine::run_device(int f0, int batch, const int* lap_host, cudaStream_t s) {
+int Engine::run_device(int f0, int batch, const int* lap_host, cudaStream_t s, int lane) {
   const int B = batch;
   pyramid_fetched = false;
   uint8_t* pyr = d_pyr + (size_t)f0 * pyr_frame_bytes;
@@ -1360,10 +1491,10 @@ int Engine::run_device(int f0, int batch, const int* lap_host, cudaStream_t s) {
   //    octree is a latency-bound 8-CTA-per-frame kernel that leaves most SMs idle)
   const bool side_stream_used = !profiling;
   if (side_stream_used) {
-    CUDA_TRY(cudaEventRecord(ev_pyr_done, s));
-    CUDA_TRY(cudaStreamWaitEvent(stream_side, ev_pyr_done, 0));
-    blur_kernel<<<dim3(num_tiles, B), 256, 0, stream_side>>>(pyr, blr, pyr_frame_bytes, d_tiles, d_levels);
-    CUDA_TRY(cudaEventRecord(ev_blur_done, stream_side));
+    CUDA_TRY(cudaEventRecord(ev_pyr_done[lane], s));
+    CUDA_TRY(cudaStreamWaitEvent(stream_side[lane], ev_pyr_done[lane], 0));
+    blur_kernel<<<dim3(num_tiles, B), 256, 0, stream_side[lane]>>>(pyr, blr, pyr_frame_bytes, d_tiles, d_levels);
+    CUDA_TRY(cudaEventRecord(ev_blur_done[lane], stream_side[lane]));
     stage_launches[4] += 1; total_launches += 1;
   } else {
     stage_begin(4, s);
@@ -1406,10 +1537,17 @@ int Engine::run_device(int f0, int batch, const int* lap_host, cudaStream_t s) {
   stage_end(5, s, 1);
   // 6. orientation + descriptors (one fused kernel measured faster than an orient/brief split)
   stage_begin(6, s);
-  if (side_stream_used) CUDA_TRY(cudaStreamWaitEvent(s, ev_blur_done, 0));
-  describe_kernel<<<dim3((unsigned)(sel_frame_elems / 8), B), 256, 0, s>>>(
-      pyr, blr, pyr_frame_bytes, sel, 3 * sel_frame_elems, sel_count, slot, d_levels, nlevels, d_warp_level,
-      d_pattern_t, d_kps + (size_t)f0 * out_cap, d_desc + (size_t)f0 * out_cap * 32, out_cap);
+  if (side_stream_used) CUDA_TRY(cudaStreamWaitEvent(s, ev_blur_done[lane], 0));
+  static const bool describe_tma = !(getenv("ORB_B200_DESCRIBE") && !strcmp(getenv("ORB_B200_DESCRIBE"), "ldg"));
+  if (describe_tma)
+    describe_tma_kernel<<<dim3((unsigned)(sel_frame_elems / DT_WARPS), B), DT_WARPS * 32, 0, s>>>(
+        (const CUtensorMap*)d_tmaps_raw + 32, (const CUtensorMap*)d_tmaps_raw + 48, f0, sel, 3 * sel_frame_elems, sel_count,
+        slot, d_levels, nlevels, d_warp_level, d_pattern_t, d_kps + (size_t)f0 * out_cap,
+        d_desc + (size_t)f0 * out_cap * 32, out_cap);
+  else
+    describe_kernel<<<dim3((unsigned)(sel_frame_elems / 8), B), 256, 0, s>>>(
+        pyr, blr, pyr_frame_bytes, sel, 3 * sel_frame_elems, sel_count, slot, d_levels, nlevels, d_warp_level,
+        d_pattern_t, d_kps + (size_t)f0 * out_cap, d_desc + (size_t)f0 * out_cap * 32, out_cap);
   stage_end(6, s, 1);
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -1531,6 +1669,24 @@ int Engine::extract_batch_device(int batch, const uint8_t* d_imgs, size_t frame_
   last_batch = batch;
   // L2-sized sub-batches: a chunk's pyramid, blurred pyramid and candidates stay in the
   // 126 MB L2 between resize -> FAST -> blur -> describe instead of round-tripping through HBM
+  const int nl = profiling ? 1 : std::min(lanes, batch);
+  if (nl > 1) {
+    // sub-batches on their own streams; lane 0 is the caller's stream, the others branch off after the level-0
+    // copy and are joined back before the call returns control of `s`
+    CUDA_TRY(cudaEventRecord(ev_lane_go, s));
+    const int per = (batch + nl - 1) / nl;
+    for (int l = 0; l < nl; l++) {
+      const int f0 = l * per, fb = std::min(per, batch - f0);
+      if (fb <= 0) break;
+      cudaStream_t ls = l ? stream_lane[l] : s;
+      if (l) CUDA_TRY(cudaStreamWaitEvent(ls, ev_lane_go, 0));
+      if (run_device(f0, fb, lap, ls, l)) return ORB_E_CUDA;
+      if (l) CUDA_TRY(cudaEventRecord(ev_lane_done[l], ls));
+    }
+    for (int l = 1; l < nl; l++)
+      if (l * per < batch) CUDA_TRY(cudaStreamWaitEvent(s, ev_lane_done[l], 0));
+    return batch;
+  }
   const int chunk = l2_chunk_frames(batch);
   for (int f0 = 0; f0 < batch; f0 += chunk)
     if (run_device(f0, std::min(chunk, batch - f0), lap, s)) return ORB_E_CUDA;
@@ -1561,6 +1717,18 @@ int Engine::encode_tensor_maps(int batch) {
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled failed, level " + std::to_string(l) + " rc " + std::to_string((int)r)); return ORB_E_CUDA; }
+    {
+      const cuuint32_t box3[3] = {(cuuint32_t)DT_RAW_P, (cuuint32_t)DT_RAW_R, 1};
+      r = ((EncodeFn)fn)(&tmaps->m[32 + l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, d_pyr + L.img_off, dims, strides, box3, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled (raw patch box) failed, rc " + std::to_string((int)r)); return ORB_E_CUDA; }
+      const cuuint32_t box4[3] = {(cuuint32_t)DT_BLR_P, (cuuint32_t)DT_BLR_R, 1};
+      r = ((EncodeFn)fn)(&tmaps->m[48 + l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, d_blur + L.img_off, dims, strides, box4, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled (blurred patch box) failed, rc " + std::to_string((int)r)); return ORB_E_CUDA; }
+    }
     if (fw_enabled) {
       const cuuint32_t box2[3] = {(cuuint32_t)fw_tile_pitch, (cuuint32_t)fw_tile_rows, 1};
       r = ((EncodeFn)fn)(&tmaps->m[16 + l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, d_pyr + L.img_off, dims, strides, box2, estr,
