@@ -1196,8 +1196,9 @@ int Engine::ensure(int rows, int cols, int batch) {
   }
   CUDA_TRY(cudaEventCreateWithFlags(&ev_lane_go, cudaEventDisableTiming));
   {
+    // measured on the B200 (profiles/r2_summary.md): 3 lanes give +3 % on 128-frame device-resident batches
     const char* env = getenv("ORB_B200_LANES");
-    lanes = env ? std::min(std::max(atoi(env), 1), (int)MAX_LANES) : 1;
+    lanes = env ? std::min(std::max(atoi(env), 1), (int)MAX_LANES) : 3;
   }
   initialized = true;
   CUDA_TRY(cudaMemcpyToSymbol(c_pattern, h_pattern, sizeof(h_pattern)));
@@ -1669,7 +1670,7 @@ int Engine::extract_batch_device(int batch, const uint8_t* d_imgs, size_t frame_
   last_batch = batch;
   // L2-sized sub-batches: a chunk's pyramid, blurred pyramid and candidates stay in the
   // 126 MB L2 between resize -> FAST -> blur -> describe instead of round-tripping through HBM
-  const int nl = profiling ? 1 : std::min(lanes, batch);
+  const int nl = (profiling || batch < 32) ? 1 : std::min(lanes, batch);
   if (nl > 1) {
     // sub-batches on their own streams; lane 0 is the caller's stream, the others branch off after the level-0
     // copy and are joined back before the call returns control of `s`
