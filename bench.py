@@ -346,6 +346,7 @@ class Workload:
         self.nmatch_last = np.zeros(B, np.int32)
         self.nmatch_local = np.zeros(B, np.int32)
         self._dev_views = {}
+        self._host_views = {}
 
     # views whose frame side points at the extractor's device results (built once per pool entry)
     def _device_views(self, p):
@@ -440,19 +441,25 @@ class Workload:
                                               C.c_void_p(self.out_d.data_ptr()), cap, ptr(self.out_n),
                                               ptr(self.out_m)))
         e = self.meta[p]
-        curs, Fs = [], []
         kp, ds, _, _, dcap = self.ext.device_results()
+        key = (p, kp)
+        if key not in self._host_views:
+            # the keypoints / descriptors were downloaded for the caller above; the matchers read the
+            # extractor's device copy (on_device = 2) instead of uploading them again.  The views only differ
+            # from step to step in n, so they are built once per (batch, result buffer)
+            curs, Fs = [], []
+            for b in range(B):
+                for src, lst in ((e["cur"][b], curs), (e["F"][b], Fs)):
+                    v = orb_frame_view()
+                    C.memmove(C.byref(v), C.byref(src), C.sizeof(v))
+                    v.keys = kp + b * dcap * 28
+                    v.desc = ds + b * dcap * 32
+                    v.u_right = None
+                    lst.append(v)
+            self._host_views[key] = (curs, Fs)
+        curs, Fs = self._host_views[key]
         for b in range(B):
-            for src, lst in ((e["cur"][b], curs), (e["F"][b], Fs)):
-                v = orb_frame_view()
-                C.memmove(C.byref(v), C.byref(src), C.sizeof(v))
-                v.n = int(self.out_n[b])
-                # the keypoints / descriptors were downloaded for the caller above; the matchers read the
-                # extractor's device copy (on_device = 2) instead of uploading them again
-                v.keys = kp + b * dcap * 28
-                v.desc = ds + b * dcap * 32
-                v.u_right = None
-                lst.append(v)
+            curs[b].n = Fs[b].n = int(self.out_n[b])
         r1, _ = self.m_last.project_last_batch(curs, e["last"], e["T"], TH_LAST, on_device=2)
         r2, _ = self.m_local.project_local_batch(Fs, e["mps"], TH_LOCAL, on_device=2)
         self.nmatch_last, self.nmatch_local = r1, r2

@@ -72,7 +72,7 @@ struct Engine {
   std::vector<LevelDev> levels;
   std::vector<ResizeTab> rs;
   size_t pyr_frame_bytes = 0, cand_frame_elems = 0, scratch_frame_bytes = 0, sel_frame_elems = 0;
-  int out_cap = 0, num_cells = 0, num_tiles = 0, oct_smem_node_cap = 0;
+  int out_cap = 0, num_cells = 0, num_tiles = 0, oct_smem_node_cap = 0, oct_smem_node_cap_full = 0;
   size_t oct_smem_bytes = 0;
   int cap_rows = 0, cap_cols = 0, cap_batch = 0, cap_batch_hint = 1, chunk_override = 0;
 

@@ -650,7 +650,7 @@ __global__ void __launch_bounds__(OCT_THREADS)
 octree_kernel(const Cand* __restrict__ cand, size_t cand_frame_stride, const int* __restrict__ cand_count,
               const LevelDev* __restrict__ lv, uint8_t* __restrict__ scratch, size_t scratch_frame_stride,
               int* __restrict__ sel, size_t sel_frame_stride, int* __restrict__ sel_count, int nlevels,
-              int smem_node_cap) {
+              int smem_node_cap, int smem_node_cap_full) {
   __shared__ int smem_ints[48];
   extern __shared__ int oct_dyn[];
   // level-major launch order (blockIdx.x = frame): all the heavy level-0 CTAs start in the first
@@ -672,6 +672,18 @@ octree_kernel(const Cand* __restrict__ cand, size_t cand_frame_stride, const int
     s.childcnt = q; q += 4 * nc;
     s.remap = q; q += 4 * nc;
     s.rank = q; q += nc;
+    if (smem_node_cap_full >= L.oct.node_cap) {
+      // second tier: everything the block scans walk and -- above all -- the buffer that ONE thread sorts with the
+      // libstdc++-order introsort in the overshoot phase (a few thousand dependent accesses: ~30 cycles each here
+      // instead of a trip to L1 / L2 per access)
+      s.cidx = q; q += 4 * nc;
+      s.eidx = q; q += 4 * nc;
+      s.surv = q; q += nc;
+      s.tmp = q; q += nc;
+      s.proc = q; q += nc;
+      s.expand_pos = q; q += nc;
+      s.sortbuf = reinterpret_cast<SortNode*>(q); q += 3 * nc;
+    }
   }
   const int n = min(cand_count[f * nlevels + level], L.cand_cap);
   const Cand* c = cand + (size_t)f * cand_frame_stride + L.cand_off;
@@ -1298,8 +1310,13 @@ int Engine::ensure(int rows, int cols, int batch) {
   {
     int max_nc = 0;
     for (int l = 0; l < nlevels; l++) max_nc = std::max(max_nc, levels[l].oct.node_cap);
-    const size_t need = (size_t)19 * max_nc * sizeof(int);
-    if (need <= 96 * 1024) {
+    const size_t need = (size_t)19 * max_nc * sizeof(int), need_full = (size_t)34 * max_nc * sizeof(int);
+    oct_smem_node_cap_full = 0;
+    if (need_full <= 100 * 1024 && !getenv("ORB_B200_OCTREE_SMEM_BASE")) {
+      oct_smem_node_cap = oct_smem_node_cap_full = max_nc;
+      oct_smem_bytes = need_full;
+      CUDA_TRY(raise_dynamic_smem((const void*)octree_kernel, need_full, device));
+    } else if (need <= 96 * 1024) {
       oct_smem_node_cap = max_nc;
       oct_smem_bytes = need;
       CUDA_TRY(raise_dynamic_smem((const void*)octree_kernel, need, device));
@@ -1529,7 +1546,7 @@ int Engine::run_device(int f0, int batch, const int* lap_host, cudaStream_t s, i
   octree_kernel<<<dim3(B, nlevels), OCT_THREADS, oct_smem_bytes, s>>>(cand, cand_frame_elems, cand_count, d_levels,
                                                                       scratch, scratch_frame_bytes, sel,
                                                                       3 * sel_frame_elems, sel_count, nlevels,
-                                                                      oct_smem_node_cap);
+                                                                      oct_smem_node_cap, oct_smem_node_cap_full);
   stage_end(3, s, 1);
   // 5. output layout
   stage_begin(5, s);
