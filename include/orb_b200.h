@@ -463,7 +463,7 @@ int bow_debug_host(const orb_vocab_view* v, const uint8_t* desc, int n, int leve
  * EdgeAccRW (src/G2oTypes.cc).  Graph set-up, outlier erasure and write-back stay in the shim, like for
  * LocalBundleAdjustment.  One camera per keyframe (no mpCamera2).  fp64.
  * STATUS: the per-window source (csrc/lia_core.h) is held against the oracle on the host
- * (lia_debug_host); the single-launch device path has not been run on hardware yet.
+ * (lia_debug_host); the single-launch device path is validated against the oracle on the B200.
  * ---------------------------------------------------------------------- */
 typedef struct lia_graph_view {
   /* keyframes: vpOptimizableKFs (newest first), then lFixedKeyFrames */

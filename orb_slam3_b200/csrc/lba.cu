@@ -33,6 +33,7 @@
 #include <algorithm>
 #include <chrono>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/orb_b200.h"
@@ -1184,10 +1185,21 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
   const int K = g->n_kf, L = g->n_mp, E = g->n_edges;
   // ---- structure (host): free poses, landmark CSR, pose CSR, pose-pair lists
   const auto t_host0 = std::chrono::steady_clock::now();
-  std::vector<int> free_idx(K, -1), free_kf;
+  // The analogue of g2o's buildStructure (block_solver.hpp:143-295), rebuilt for every call because every local
+  // window is a new graph.  The passes over the landmarks (pattern / pair counts, edge gather, pair fill) run on
+  // PREP_T host threads over contiguous landmark ranges; every list keeps ascending landmark order, so the result
+  // does not depend on the thread count.
+  constexpr int PREP_T = 8;
+  auto parallel = [&](auto&& fn) {
+    std::vector<std::thread> th;
+    for (int t = 1; t < PREP_T; t++) th.emplace_back([&, t] { fn(t); });
+    fn(0);
+    for (auto& x : th) x.join();
+  };
+  std::vector<int> nat_idx(K, -1), nat_kf;  // free poses in the caller's order
   for (int k = 0; k < K; k++)
-    if (!g->kf_fixed[k]) { free_idx[k] = (int)free_kf.size(); free_kf.push_back(k); }
-  const int nf = (int)free_kf.size(), n = 6 * nf;
+    if (!g->kf_fixed[k]) { nat_idx[k] = (int)nat_kf.size(); nat_kf.push_back(k); }
+  const int nf = (int)nat_kf.size(), n = 6 * nf;
   if (nf == 0) { set_last_error("lba_solve: no free keyframe"); return ORB_E_ARG; }
   std::vector<int> lm_ptr(L + 1, 0);
   for (int e = 0; e < E; e++) {
@@ -1197,48 +1209,79 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
   for (int l = 0; l < L; l++) lm_ptr[l + 1] += lm_ptr[l];
   std::vector<int> perm(E), cursor(lm_ptr.begin(), lm_ptr.end() - 1);
   for (int e = 0; e < E; e++) perm[cursor[g->e_mp[e]]++] = e;   // sorted position -> original edge
+  int lm_lo[PREP_T + 1];  // landmark ranges with about the same number of edges
+  {
+    lm_lo[0] = 0;
+    for (int t = 1; t <= PREP_T; t++) {
+      const long long want = (long long)E * t / PREP_T;
+      lm_lo[t] = t == PREP_T ? L : (int)(std::lower_bound(lm_ptr.begin(), lm_ptr.end(), (int)want) - lm_ptr.begin());
+      lm_lo[t] = std::min(std::max(lm_lo[t], lm_lo[t - 1]), L);
+    }
+  }
+  // ---- pass A: per thread, how often every unordered pair of free poses shares a landmark (caller's numbering;
+  //      a pose pairs with itself once per edge), and the useful Schur flops
+  const size_t nf2 = (size_t)nf * nf;
+  std::vector<std::vector<int>> cntT(PREP_T, std::vector<int>(nf2, 0));
+  double flopsT[PREP_T];
+  parallel([&](int t) {
+    std::vector<int>& cnt = cntT[t];
+    std::vector<int> fl;
+    double fsum = 0;
+    for (int l = lm_lo[t]; l < lm_lo[t + 1]; l++) {
+      fl.clear();
+      for (int s = lm_ptr[l]; s < lm_ptr[l + 1]; s++) {
+        const int f = nat_idx[g->e_kf[perm[s]]];
+        if (f >= 0) fl.push_back(f);
+      }
+      const double m = (double)fl.size();
+      fsum += 50 + m * (108 + 36) + m * (m + 1) / 2 * 216;
+      for (size_t a = 0; a < fl.size(); a++)
+        for (size_t b = a; b < fl.size(); b++) cnt[(size_t)std::min(fl[a], fl[b]) * nf + std::max(fl[a], fl[b])]++;
+    }
+    flopsT[t] = fsum;
+  });
+  double schur_flops = 0;
+  for (int t = 0; t < PREP_T; t++) schur_flops += flopsT[t];
+  std::vector<int> tot(nf2, 0);
+  for (int t = 0; t < PREP_T; t++)
+    for (size_t i = 0; i < nf2; i++) tot[i] += cntT[t][i];
+  // covisibility pattern of the free poses (block pattern of S); with landmark shards every rank only sees
+  // its own landmarks, so the patterns are OR-ed over the ranks: ordering, envelope and the choice of the
+  // solver kernel must be identical everywhere (all ranks factor the same matrix)
+  std::vector<uint8_t> adj(nf2, 0);
+  for (int a = 0; a < nf; a++) {
+    adj[(size_t)a * nf + a] = 1;
+    for (int b = a + 1; b < nf; b++)
+      if (tot[(size_t)a * nf + b]) adj[(size_t)a * nf + b] = adj[(size_t)b * nf + a] = 1;
+  }
+  if (S.world > 1) {
+    if (S.graph.reserve(adj.size() + 256)) return ORB_E_CUDA;
+    CUDA_TRYL(cudaMemcpyAsync(S.graph.p, adj.data(), adj.size(), cudaMemcpyHostToDevice, S.stream));
+    const int r = g_nccl.AllReduce(S.graph.p, S.graph.p, adj.size(), /*ncclUint8*/ 1, /*ncclMax*/ 2, S.comm, S.stream);
+    if (r) { set_last_error("ncclAllReduce(covisibility pattern)"); return ORB_E_NCCL; }
+    CUDA_TRYL(cudaMemcpyAsync(adj.data(), S.graph.p, adj.size(), cudaMemcpyDeviceToHost, S.stream));
+    CUDA_TRYL(cudaStreamSynchronize(S.stream));
+  }
   // Elimination order of the free poses.  The envelope solver's cost is the profile of S, so when the
   // caller's keyframe order is not already chain-like (Optimizer.cc:1135-1160 lists the current keyframe
   // first, then its covisibles) the poses are renumbered by reverse Cuthill-McKee on the covisibility
   // pattern; the natural order is kept when it is at least as good (what Eigen's AMD ordering does for g2o).
-  // covisibility pattern of the free poses (block pattern of S); with landmark shards every rank only sees
-  // its own landmarks, so the patterns are OR-ed over the ranks: ordering, envelope and the choice of the
-  // solver kernel must be identical everywhere (all ranks factor the same matrix)
-  std::vector<uint8_t> adj((size_t)nf * nf, 0);
-  {
-    std::vector<int> fl;
-    for (int l = 0; l < L; l++) {
-      fl.clear();
-      for (int s = lm_ptr[l]; s < lm_ptr[l + 1]; s++) {
-        const int f = free_idx[g->e_kf[perm[s]]];
-        if (f >= 0) fl.push_back(f);
-      }
-      for (int a : fl)
-        for (int b : fl) adj[(size_t)a * nf + b] = 1;
-    }
-    for (int a = 0; a < nf; a++) adj[(size_t)a * nf + a] = 1;
-    if (S.world > 1) {
-      if (S.graph.reserve(adj.size() + 256)) return ORB_E_CUDA;
-      CUDA_TRYL(cudaMemcpyAsync(S.graph.p, adj.data(), adj.size(), cudaMemcpyHostToDevice, S.stream));
-      const int r = g_nccl.AllReduce(S.graph.p, S.graph.p, adj.size(), /*ncclUint8*/ 1, /*ncclMax*/ 2, S.comm, S.stream);
-      if (r) { set_last_error("ncclAllReduce(covisibility pattern)"); return ORB_E_NCCL; }
-      CUDA_TRYL(cudaMemcpyAsync(adj.data(), S.graph.p, adj.size(), cudaMemcpyDeviceToHost, S.stream));
-      CUDA_TRYL(cudaStreamSynchronize(S.stream));
-    }
-  }
+  std::vector<int> pos(nf);  // pos[natural free index] = free index used from here on
+  for (int i = 0; i < nf; i++) pos[i] = i;
   if (nf > 2 && !getenv("ORB_B200_LBA_NO_REORDER")) {
-    auto profile = [&](const std::vector<int>& pos) {  // pos[f] = position of pose f
+    auto profile = [&](const std::vector<int>& q) {  // q[f] = position of pose f
       long long p = 0;
       std::vector<int> lo(nf);
       for (int i = 0; i < nf; i++) lo[i] = i;
       for (int a = 0; a < nf; a++)
         for (int b = 0; b < nf; b++)
-          if (adj[(size_t)a * nf + b] && pos[b] < pos[a]) lo[pos[a]] = std::min(lo[pos[a]], pos[b]);
+          if (adj[(size_t)a * nf + b] && q[b] < q[a]) lo[q[a]] = std::min(lo[q[a]], q[b]);
       for (int i = 0; i < nf; i++) p += i - lo[i] + 1;
       return p;
     };
-    std::vector<int> deg(nf, 0), nat(nf), order, pos(nf, -1);
-    for (int a = 0; a < nf; a++) { nat[a] = a; for (int b = 0; b < nf; b++) deg[a] += adj[(size_t)a * nf + b] && a != b; }
+    std::vector<int> deg(nf, 0), order, rpos(nf, -1);
+    for (int a = 0; a < nf; a++)
+      for (int b = 0; b < nf; b++) deg[a] += adj[(size_t)a * nf + b] && a != b;
     std::vector<uint8_t> seen(nf, 0);
     while ((int)order.size() < nf) {
       int start = -1;  // lowest-degree unvisited node of the next component
@@ -1257,81 +1300,93 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
       }
     }
     std::reverse(order.begin(), order.end());
-    for (int i = 0; i < nf; i++) pos[order[i]] = i;
-    if (profile(pos) * 10 < profile(nat) * 9) {  // renumber only for a >= 10 % smaller profile
-      std::vector<int> nk(nf);
-      for (int i = 0; i < nf; i++) nk[i] = free_kf[order[i]];
-      free_kf = nk;
-      for (int i = 0; i < nf; i++) free_idx[free_kf[i]] = i;
-      std::vector<uint8_t> adj2((size_t)nf * nf, 0);  // the pattern in the new numbering
+    for (int i = 0; i < nf; i++) rpos[order[i]] = i;
+    if (profile(rpos) * 10 < profile(pos) * 9) {  // renumber only for a >= 10 % smaller profile
+      pos = rpos;
+      std::vector<uint8_t> adj2(nf2, 0);  // the pattern in the new numbering
       for (int a = 0; a < nf; a++)
         for (int b = 0; b < nf; b++)
           if (adj[(size_t)a * nf + b]) adj2[(size_t)pos[a] * nf + pos[b]] = 1;
       adj.swap(adj2);
     }
   }
+  std::vector<int> free_idx(K, -1), free_kf(nf);
+  for (int i = 0; i < nf; i++) { free_kf[pos[i]] = nat_kf[i]; free_idx[nat_kf[i]] = pos[i]; }
+  // ---- pose pairs (i1 <= i2 in the final numbering): slots, list offsets, per-thread fill cursors
+  std::vector<int> pair_i1, pair_i2, pair_ptr(1, 0);
+  std::vector<int> inv(nf);
+  for (int i = 0; i < nf; i++) inv[pos[i]] = i;
+  auto nat_key = [&](int i1, int i2) {  // final (i1, i2) -> index into the caller-numbered count tables
+    const int a = inv[i1], b = inv[i2];
+    return (size_t)std::min(a, b) * nf + std::max(a, b);
+  };
+  std::vector<int> slot_of(nf2, -1);  // by caller-numbered key
+  for (int a = 0; a < nf; a++)
+    for (int b = a; b < nf; b++) {
+      const size_t key = nat_key(a, b);
+      const int c = tot[key];
+      if (c == 0 && a != b) continue;
+      slot_of[key] = (int)pair_i1.size();
+      pair_i1.push_back(a); pair_i2.push_back(b);
+      pair_ptr.push_back(pair_ptr.back() + c);
+    }
+  const int n_pairs = (int)pair_i1.size();
+  // cntT[t][key] <- first list position thread t writes for that pair (prefix over the threads)
+  {
+    std::vector<int> run(nf2, 0);
+    for (size_t key = 0; key < nf2; key++)
+      if (slot_of[key] >= 0) run[key] = pair_ptr[slot_of[key]];
+    for (int t = 0; t < PREP_T; t++)
+      for (size_t key = 0; key < nf2; key++) {
+        const int c = cntT[t][key];
+        cntT[t][key] = run[key];
+        run[key] += c;
+      }
+  }
+  // ---- pass B: edge gather (landmark-sorted arrays), pose CSR counts and the pair lists
   std::vector<int> se_kf(E), se_free(2 * (size_t)E);
   std::vector<uint8_t> se_st(E);
   std::vector<double> se_obs(3 * (size_t)E);
   std::vector<float> se_is2(E);
-  std::vector<int> pose_cnt(nf + 1, 0);
-  for (int s = 0; s < E; s++) {
-    const int e = perm[s];
-    se_kf[s] = g->e_kf[e];
-    se_free[s] = free_idx[g->e_kf[e]];
-    se_free[(size_t)E + s] = g->e_mp[e];
-    se_st[s] = g->e_stereo[e] ? 1 : 0;
-    memcpy(&se_obs[3 * (size_t)s], g->e_obs + 3 * (size_t)e, 3 * sizeof(double));
-    se_is2[s] = g->e_inv_sigma2[e];
-    if (se_free[s] >= 0) pose_cnt[se_free[s] + 1]++;
-  }
-  std::vector<int> pose_ptr(nf + 1, 0);
-  for (int f = 0; f < nf; f++) pose_ptr[f + 1] = pose_ptr[f] + pose_cnt[f + 1];
-  std::vector<int> pose_edges(pose_ptr[nf]), pcur(pose_ptr.begin(), pose_ptr.end() - 1);
-  for (int s = 0; s < E; s++)
-    if (se_free[s] >= 0) pose_edges[pcur[se_free[s]]++] = s;
-  // pairs: for every landmark, every (a <= b) of its free-pose edges
-  std::vector<long long> pair_count((size_t)nf * nf, 0);
-  std::vector<int> tmp;
-  double schur_flops = 0;
-  for (int l = 0; l < L; l++) {
-    tmp.clear();
-    for (int s = lm_ptr[l]; s < lm_ptr[l + 1]; s++)
-      if (se_free[s] >= 0) tmp.push_back(s);
-    const double m = (double)tmp.size();
-    schur_flops += 50 + m * (108 + 36) + m * (m + 1) / 2 * 216;
-    for (size_t a = 0; a < tmp.size(); a++)
-      for (size_t b = 0; b < tmp.size(); b++) {
-        const int fa = se_free[tmp[a]], fb = se_free[tmp[b]];
-        if (fa < fb || (fa == fb && a <= b)) pair_count[(size_t)fa * nf + fb]++;
+  std::vector<int> pair_ea(pair_ptr.back()), pair_eb(pair_ptr.back());
+  std::vector<std::vector<int>> poseT(PREP_T, std::vector<int>(nf, 0));
+  parallel([&](int t) {
+    std::vector<int>& cur = cntT[t];
+    std::vector<int>& pc = poseT[t];
+    std::vector<int> tmp;
+    for (int l = lm_lo[t]; l < lm_lo[t + 1]; l++) {
+      tmp.clear();
+      for (int s = lm_ptr[l]; s < lm_ptr[l + 1]; s++) {
+        const int e = perm[s];
+        se_kf[s] = g->e_kf[e];
+        se_free[s] = free_idx[g->e_kf[e]];
+        se_free[(size_t)E + s] = g->e_mp[e];
+        se_st[s] = g->e_stereo[e] ? 1 : 0;
+        memcpy(&se_obs[3 * (size_t)s], g->e_obs + 3 * (size_t)e, 3 * sizeof(double));
+        se_is2[s] = g->e_inv_sigma2[e];
+        if (se_free[s] >= 0) { pc[se_free[s]]++; tmp.push_back(s); }
       }
-  }
-  std::vector<int> pair_i1, pair_i2, pair_ptr(1, 0);
-  std::vector<long long> pair_slot((size_t)nf * nf, -1);
-  for (int a = 0; a < nf; a++)
-    for (int b = a; b < nf; b++) {
-      const long long c = pair_count[(size_t)a * nf + b];
-      if (c == 0 && a != b) continue;
-      pair_slot[(size_t)a * nf + b] = (long long)pair_i1.size();
-      pair_i1.push_back(a); pair_i2.push_back(b);
-      pair_ptr.push_back(pair_ptr.back() + (int)c);
-    }
-  const int n_pairs = (int)pair_i1.size();
-  std::vector<int> pair_ea(pair_ptr.back()), pair_eb(pair_ptr.back()), pair_cur(pair_ptr.begin(), pair_ptr.end() - 1);
-  for (int l = 0; l < L; l++) {
-    tmp.clear();
-    for (int s = lm_ptr[l]; s < lm_ptr[l + 1]; s++)
-      if (se_free[s] >= 0) tmp.push_back(s);
-    for (size_t a = 0; a < tmp.size(); a++)
-      for (size_t b = 0; b < tmp.size(); b++) {
-        const int fa = se_free[tmp[a]], fb = se_free[tmp[b]];
-        if (fa < fb || (fa == fb && a <= b)) {
-          const int slot = (int)pair_slot[(size_t)fa * nf + fb];
-          const int pos = pair_cur[slot]++;
-          pair_ea[pos] = tmp[a]; pair_eb[pos] = tmp[b];
+      for (size_t a = 0; a < tmp.size(); a++)
+        for (size_t b = a; b < tmp.size(); b++) {
+          const int fa = se_free[tmp[a]], fb = se_free[tmp[b]];
+          const int p2 = cur[nat_key(std::min(fa, fb), std::max(fa, fb))]++;
+          pair_ea[p2] = fa <= fb ? tmp[a] : tmp[b];
+          pair_eb[p2] = fa <= fb ? tmp[b] : tmp[a];
         }
-      }
+    }
+  });
+  std::vector<int> pose_ptr(nf + 1, 0);
+  for (int f = 0; f < nf; f++) {
+    int c = 0;
+    for (int t = 0; t < PREP_T; t++) { const int v = poseT[t][f]; poseT[t][f] = c; c += v; }  // -> per-thread offsets
+    pose_ptr[f + 1] = pose_ptr[f] + c;
   }
+  std::vector<int> pose_edges(pose_ptr[nf]);
+  parallel([&](int t) {
+    std::vector<int>& off = poseT[t];
+    for (int s = lm_ptr[lm_lo[t]]; s < lm_ptr[lm_lo[t + 1]]; s++)
+      if (se_free[s] >= 0) pose_edges[pose_ptr[se_free[s]] + off[se_free[s]]++] = s;
+  });
   // ---- row envelope of S (scalar rows): first[i] = first non-zero column, reach[c] = last row whose
   //      envelope holds a column <= c; feasibility / cost of the single-CTA envelope solver
   std::vector<int> env_first(n), env_reach(n, 0);

@@ -2,8 +2,8 @@
 // preparation of the flat graph (what the reference's vertex / edge constructors do once per call), one
 // kernel launch that runs the whole LM loop of csrc/lia_core.h in a single CTA, and the host debug hook
 // that runs the same source single-threaded.
-// STATUS: the device path compiles for sm_100a but has not been run on hardware yet (the GPU test is
-// skipped until it has); the core is held against the oracle on the host by tests/test_lia_core_host.py.
+// The device path is held against the oracle on the B200 by tests/test_lia_gpu.py; the same core runs on the
+// host in tests/test_lia_core_host.py.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>

@@ -131,7 +131,7 @@ def _lia_pack(view, it, kf, mp, chi2, dp, st):
 class LocalInertialBA:
     """Optimizer::LocalInertialBA's optimizer.optimize(opt_it) (src/Optimizer.cc:2383-2958) over the C ABI: the whole
     LM loop in one kernel launch.  No CPU fallback (`lia_debug_host` runs the kernel's source on the host for the
-    CPU tests).  The device path has not been run on hardware yet."""
+    CPU tests)."""
 
     def __init__(self, device=0):
         self._lib = _lib.lib()

@@ -4,7 +4,8 @@
 // see INTEGRATION.md); this unit shows only the part that changes: the flat graph handed to lia_solve()
 // instead of building a g2o::SparseOptimizer, and how the outputs map back.
 // NOT compiled in this repo's image (Eigen / Sophus / g2o headers absent).  The device path behind
-// lia_solve has not been on hardware yet.
+// lia_solve is validated on the B200 against the oracle (tests/test_lia_gpu.py); this unit is the graph
+// flattening only, not a finished replacement of the function.
 #include <stdexcept>
 #include <string>
 #include <vector>
