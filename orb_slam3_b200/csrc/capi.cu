@@ -189,7 +189,7 @@ int orb_debug_octree_host(const int* xys, int n, int band_w, int band_h, int n_f
 
 int orb_debug_introsort(const int* count, const int* ulx, int n, int* perm_out) {
   std::vector<orbb200::SortNode> v(n > 0 ? n : 1);
-  for (int i = 0; i < n; i++) { v[i].count = count[i]; v[i].ulx = ulx[i]; v[i].id = i; }
+  for (int i = 0; i < n; i++) v[i] = orbb200::make_sort_node(count[i], ulx[i], i);
   orbb200::introsort_emul(v.data(), n);
   for (int i = 0; i < n; i++) perm_out[i] = v[i].id;
   return n;

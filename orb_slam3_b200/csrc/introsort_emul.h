@@ -22,18 +22,22 @@
 
 namespace orbb200 {
 
-// One sortable record: ordering key (count, ulx); `id` is the payload.
-struct SortNode {
-  int count;
-  int ulx;
+// One sortable record: the ordering key (count, UL.x) packed into one word (count in the upper 20 bits, UL.x
+// < 4096 in the lower 12: one integer compare, and records that tie in the reference's comparator have equal
+// keys here too); `id` is the payload.  Eight bytes: one 64-bit load / store per move.
+struct __attribute__((aligned(8))) SortNode {
+  uint32_t key;
   int id;
 };
 
-ORB_HD bool node_less(const SortNode& a, const SortNode& b) {
-  if (a.count < b.count) return true;
-  if (a.count > b.count) return false;
-  return a.ulx < b.ulx;
+ORB_HD SortNode make_sort_node(int count, int ulx, int id) {
+  SortNode s;
+  s.key = ((uint32_t)count << 12) | (uint32_t)(ulx & 0xfff);
+  s.id = id;
+  return s;
 }
+
+ORB_HD bool node_less(const SortNode& a, const SortNode& b) { return a.key < b.key; }
 
 ORB_HD void sn_swap(SortNode& a, SortNode& b) {
   SortNode t = a;

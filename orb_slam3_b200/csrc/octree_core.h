@@ -176,8 +176,7 @@ int octree_select(BE& be, const Cand* cand, int n, const OctreeLevelParams& p,
       } else {
         for (int e = tid; e < P; e += nt) {
           const int node = s.expand_pos[e];
-          SortNode sn; sn.count = cnt[node]; sn.ulx = ulx[node]; sn.id = node;
-          s.sortbuf[e] = sn;
+          s.sortbuf[e] = make_sort_node(cnt[node], ulx[node], node);
         }
         be.sync();
         if (tid == 0) introsort_emul(s.sortbuf, P);

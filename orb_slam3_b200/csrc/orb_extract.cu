@@ -194,6 +194,48 @@ __device__ __forceinline__ int fast_best(const uint8_t* __restrict__ c, int pitc
   return best > t ? best : 0;
 }
 
+// The same score on packed 16-bit halves: the 9-arcs starting at ring positions k and k+8 are evaluated together
+// in the two halves of one register (VIMNMX.U16x2 / VIMNMX3.U16x2 are native on sm_100a), and
+// max_k max(v - mx9[k], mn9[k] - v) = max(v - min_k mx9[k], max_k mn9[k] - v) moves the subtraction out of
+// the loop.  P[k] = (r[k], r[k+8]); every array index k+8 is the half-swapped entry k.  No early exit: the callers
+// only pass pixels that already survived the packed 4-diameter test.
+__device__ __forceinline__ int fast_best_packed(const uint8_t* __restrict__ c, int pitch, int t) {
+  const int v = c[0];
+  uint32_t r[16];
+  r[0] = c[3 * pitch];      r[8] = c[-3 * pitch];      r[4] = c[3];               r[12] = c[-3];
+  r[1] = c[3 * pitch + 1];  r[2] = c[2 * pitch + 2];   r[3] = c[pitch + 3];
+  r[5] = c[-pitch + 3];     r[6] = c[-2 * pitch + 2];  r[7] = c[-3 * pitch + 1];
+  r[9] = c[-3 * pitch - 1]; r[10] = c[-2 * pitch - 2]; r[11] = c[-pitch - 3];
+  r[13] = c[pitch - 3];     r[14] = c[2 * pitch - 2];  r[15] = c[3 * pitch - 1];
+  uint32_t P[12];
+#pragma unroll
+  for (int k = 0; k < 8; k++) P[k] = r[k] | (r[k + 8] << 16);
+#pragma unroll
+  for (int k = 8; k < 12; k++) P[k] = __byte_perm(P[k - 8], 0, 0x1032);
+  uint32_t X2[10], N2[10];  // max / min over ring positions [k, k+1]
+#pragma unroll
+  for (int k = 0; k < 8; k++) { X2[k] = __vmaxu2(P[k], P[k + 1]); N2[k] = __vminu2(P[k], P[k + 1]); }
+#pragma unroll
+  for (int k = 8; k < 10; k++) { X2[k] = __byte_perm(X2[k - 8], 0, 0x1032); N2[k] = __byte_perm(N2[k - 8], 0, 0x1032); }
+  uint32_t X4[12], N4[12];  // [k, k+3]
+#pragma unroll
+  for (int k = 0; k < 8; k++) { X4[k] = __vmaxu2(X2[k], X2[k + 2]); N4[k] = __vminu2(N2[k], N2[k + 2]); }
+#pragma unroll
+  for (int k = 8; k < 12; k++) { X4[k] = __byte_perm(X4[k - 8], 0, 0x1032); N4[k] = __byte_perm(N4[k - 8], 0, 0x1032); }
+  uint32_t minmx = 0xffffffffu, maxmn = 0u;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const uint32_t last = k + 8 < 12 ? P[k + 8] : __byte_perm(P[k], 0, 0x1032);  // ring position k+8 | k
+    const uint32_t mx9 = __vimax3_u16x2(X4[k], X4[k + 4], last);   // arcs [k, k+8] | [k+8, k+16]
+    const uint32_t mn9 = __vimin3_u16x2(N4[k], N4[k + 4], last);
+    minmx = __vminu2(minmx, mx9);
+    maxmn = __vmaxu2(maxmn, mn9);
+  }
+  const int m1 = (int)min(minmx & 0xffffu, minmx >> 16), m2 = (int)max(maxmn & 0xffffu, maxmn >> 16);
+  const int best = max(v - m1, m2 - v);
+  return best > t ? best : 0;
+}
+
 // One CTA per FAST cell of ComputeKeyPointsOctTree (ORBextractor.cc:805-872):
 // score map at minTh in shared memory, 3x3 strict NMS inside the cell's band,
 // keep score>=iniTh survivors, or all survivors when there is none.
@@ -549,7 +591,7 @@ fast_warp_kernel(const CUtensorMap* __restrict__ maps, int frame0, int nframes, 
         // 3. exact segment test + score of the queued pixels on dense lanes
         for (int q = lane; q < qn; q += 32) {
           const int e = queue[q], y = e >> 7, x = e & 127;
-          const int best = fast_best(&tile[(y + 3) * TP + ox + x + 3], TP, th_fast);
+          const int best = fast_best_packed(&tile[(y + 3) * TP + ox + x + 3], TP, th_fast);
           smap[(y + 1) * SW + x + 1] = (uint8_t)best;
         }
         __syncwarp();
@@ -652,7 +694,7 @@ octree_kernel(const Cand* __restrict__ cand, size_t cand_frame_stride, const int
               int* __restrict__ sel, size_t sel_frame_stride, int* __restrict__ sel_count, int nlevels,
               int smem_node_cap, int smem_node_cap_full) {
   __shared__ int smem_ints[48];
-  extern __shared__ int oct_dyn[];
+  extern __shared__ __align__(16) int oct_dyn[];
   // level-major launch order (blockIdx.x = frame): all the heavy level-0 CTAs start in the first
   // wave and the light high levels back-fill the SMs as they drain
   const int level = blockIdx.y, f = blockIdx.x;
@@ -682,7 +724,7 @@ octree_kernel(const Cand* __restrict__ cand, size_t cand_frame_stride, const int
       s.tmp = q; q += nc;
       s.proc = q; q += nc;
       s.expand_pos = q; q += nc;
-      s.sortbuf = reinterpret_cast<SortNode*>(q); q += 3 * nc;
+      s.sortbuf = reinterpret_cast<SortNode*>(q + (nc & 1)); q += 2 * nc + 2;  // 8-byte aligned
     }
   }
   const int n = min(cand_count[f * nlevels + level], L.cand_cap);
@@ -1271,6 +1313,10 @@ int Engine::ensure(int rows, int cols, int batch) {
       return ORB_E_ARG;
     }
     o.hX = (float)o.bandW / o.nIni;
+    if (o.bandW >= 4096) {
+      set_last_error("image wider than 4127 px: the octree sort key packs UL.x into 12 bits");
+      return ORB_E_ARG;
+    }
     o.wCell = wCell; o.hCell = hCell; o.nCols = nCols;
     o.node_cap = o.N + 4 * o.nIni + 16;
     L.cand_cap = (o.bandW / 2 + nCols + 2) * (o.bandH / 2 + nRows + 2);
@@ -1310,7 +1356,7 @@ int Engine::ensure(int rows, int cols, int batch) {
   {
     int max_nc = 0;
     for (int l = 0; l < nlevels; l++) max_nc = std::max(max_nc, levels[l].oct.node_cap);
-    const size_t need = (size_t)19 * max_nc * sizeof(int), need_full = (size_t)34 * max_nc * sizeof(int);
+    const size_t need = (size_t)19 * max_nc * sizeof(int), need_full = ((size_t)33 * max_nc + 2) * sizeof(int);
     oct_smem_node_cap_full = 0;
     if (need_full <= 100 * 1024 && !getenv("ORB_B200_OCTREE_SMEM_BASE")) {
       oct_smem_node_cap = oct_smem_node_cap_full = max_nc;
