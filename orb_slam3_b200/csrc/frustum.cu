@@ -57,10 +57,14 @@ struct Frustum {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_h2d = nullptr;
   bool h2d_pending = false;
   int cap = 0;
-  float *d_in = nullptr, *h_in = nullptr;     // world_pos[3n] normal[3n] min[n] max[n]
-  uint8_t *d_flags = nullptr, *h_flags = nullptr;  // in_view[n] full[n]
-  float *d_out = nullptr, *h_out = nullptr;   // proj_x proj_y proj_xr view_cos depth, n each
-  int *d_level = nullptr, *h_level = nullptr, *d_count = nullptr, *h_count = nullptr;
+  // One input blob and one result blob per handle, each with a pinned mirror, laid out with the stride of the
+  // current call (n rounded up to 4): a host-buffer call is ONE H2D, one launch and ONE D2H -- at the 5000
+  // points of a local map the fixed cost per cudaMemcpyAsync is what the call consists of.
+  //   input : world_pos[3s] normal[3s] min_dist[s] max_dist[s]                      (floats)
+  //   result: count, 3 pad | level[s] (int) | proj_x proj_y proj_xr view_cos depth [5s] (float) | in_view[s] full[s] (bytes)
+  size_t stride = 0;
+  float *d_in = nullptr, *h_in = nullptr;
+  uint8_t *d_res = nullptr, *h_res = nullptr;
   long long launches = 0;
 
   explicit Frustum(int dev) : device(dev) {}
@@ -72,12 +76,16 @@ struct Frustum {
     if (ev_h2d) cudaEventDestroy(ev_h2d);
   }
   void release() {
-    cudaFree(d_in); cudaFree(d_flags); cudaFree(d_out); cudaFree(d_level); cudaFree(d_count);
-    cudaFreeHost(h_in); cudaFreeHost(h_flags); cudaFreeHost(h_out); cudaFreeHost(h_level); cudaFreeHost(h_count);
-    d_in = h_in = d_out = h_out = nullptr; d_flags = h_flags = nullptr;
-    d_level = h_level = d_count = h_count = nullptr;
+    cudaFree(d_in); cudaFree(d_res);
+    cudaFreeHost(h_in); cudaFreeHost(h_res);
+    d_in = h_in = nullptr; d_res = h_res = nullptr;
     cap = 0;
   }
+  static size_t res_bytes(size_t s) { return 16 + 4 * s + 20 * s + 2 * s; }
+  int* count_of(uint8_t* base) const { return reinterpret_cast<int*>(base); }
+  int* level_of(uint8_t* base) const { return reinterpret_cast<int*>(base + 16); }
+  float* out_of(uint8_t* base) const { return reinterpret_cast<float*>(base + 16 + 4 * stride); }
+  uint8_t* flags_of(uint8_t* base) const { return base + 16 + 24 * stride; }
   int ensure(int n) {
     if (!stream) {
       CUDA_TRYF(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -88,20 +96,13 @@ struct Frustum {
     if (n <= cap) return 0;
     if (h2d_pending) { CUDA_TRYF(cudaEventSynchronize(ev_h2d)); h2d_pending = false; }
     release();
-    const size_t m = (size_t)std::max(n, 1024);
+    const size_t m = ((size_t)std::max(n, 1024) + 3) & ~(size_t)3;
     CUDA_TRYF(cudaMalloc(&d_in, sizeof(float) * 8 * m));
     CUDA_TRYF(cudaMallocHost(&h_in, sizeof(float) * 8 * m));
-    CUDA_TRYF(cudaMalloc(&d_flags, 2 * m));
-    CUDA_TRYF(cudaMallocHost(&h_flags, 2 * m));
-    CUDA_TRYF(cudaMalloc(&d_out, sizeof(float) * 5 * m));
-    CUDA_TRYF(cudaMallocHost(&h_out, sizeof(float) * 5 * m));
-    CUDA_TRYF(cudaMalloc(&d_level, sizeof(int) * m));
-    CUDA_TRYF(cudaMallocHost(&h_level, sizeof(int) * m));
-    CUDA_TRYF(cudaMalloc(&d_count, sizeof(int)));
-    CUDA_TRYF(cudaMallocHost(&h_count, sizeof(int)));
+    CUDA_TRYF(cudaMalloc(&d_res, res_bytes(m)));
+    CUDA_TRYF(cudaMallocHost(&h_res, res_bytes(m)));
     // the "written only when in view" outputs start from a defined state
-    CUDA_TRYF(cudaMemset(d_out, 0, sizeof(float) * 5 * m));
-    CUDA_TRYF(cudaMemset(d_level, 0, sizeof(int) * m));
+    CUDA_TRYF(cudaMemset(d_res, 0, res_bytes(m)));
     cap = (int)m;
     return 0;
   }
@@ -128,7 +129,9 @@ struct Frustum {
 
   // uploads, launches, leaves the results on the device (after prepare())
   int enqueue(const orb_frustum_view* v, float cos_limit, cudaStream_t s) {
-    const size_t n = (size_t)v->n, c = (size_t)cap;
+    const size_t n = (size_t)v->n;
+    stride = std::max<size_t>((n + 3) & ~(size_t)3, 4);
+    const size_t c = stride;
     // the pinned staging buffer of an earlier enqueue-only call may still be in flight
     if (h2d_pending) { CUDA_TRYF(cudaEventSynchronize(ev_h2d)); h2d_pending = false; }
     if (n) {
@@ -136,19 +139,18 @@ struct Frustum {
       memcpy(h_in + 3 * c, v->normal, sizeof(float) * 3 * n);
       memcpy(h_in + 6 * c, v->min_dist, sizeof(float) * n);
       memcpy(h_in + 7 * c, v->max_dist, sizeof(float) * n);
-      CUDA_TRYF(cudaMemcpyAsync(d_in, h_in, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, s));
-      CUDA_TRYF(cudaMemcpyAsync(d_in + 3 * c, h_in + 3 * c, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, s));
-      CUDA_TRYF(cudaMemcpyAsync(d_in + 6 * c, h_in + 6 * c, sizeof(float) * n, cudaMemcpyHostToDevice, s));
-      CUDA_TRYF(cudaMemcpyAsync(d_in + 7 * c, h_in + 7 * c, sizeof(float) * n, cudaMemcpyHostToDevice, s));
+      CUDA_TRYF(cudaMemcpyAsync(d_in, h_in, sizeof(float) * 8 * c, cudaMemcpyHostToDevice, s));
       CUDA_TRYF(cudaEventRecord(ev_h2d, s));
       h2d_pending = true;
     }
-    CUDA_TRYF(cudaMemsetAsync(d_count, 0, sizeof(int), s));
+    CUDA_TRYF(cudaMemsetAsync(count_of(d_res), 0, sizeof(int), s));
     FrustumDev D;
     D.world_pos = d_in; D.normal = d_in + 3 * c; D.min_dist = d_in + 6 * c; D.max_dist = d_in + 7 * c;
-    D.in_view = d_flags; D.full = d_flags + c;
-    D.proj_x = d_out; D.proj_y = d_out + c; D.proj_xr = d_out + 2 * c; D.view_cos = d_out + 3 * c; D.depth = d_out + 4 * c;
-    D.level = d_level; D.count = d_count; D.n = v->n;
+    uint8_t* fl = flags_of(d_res);
+    float* o = out_of(d_res);
+    D.in_view = fl; D.full = fl + c;
+    D.proj_x = o; D.proj_y = o + c; D.proj_xr = o + 2 * c; D.view_cos = o + 3 * c; D.depth = o + 4 * c;
+    D.level = level_of(d_res); D.count = count_of(d_res); D.n = v->n;
     const FrustumFrame F = frustum_frame_of(*v);
     CUDA_TRYF(cudaEventRecord(ev0, s));
     if (n) {
@@ -196,34 +198,24 @@ int frame_is_in_frustum(orb_frustum* h, const orb_frustum_view* v, float cos_lim
   if ((rc = f.prepare(v->n))) return rc;
   cudaStream_t s = f.stream;
   if ((rc = f.enqueue(v, cos_limit, s))) return rc;
-  const size_t n = (size_t)v->n, c = (size_t)f.cap;
-  if (n) {
-    if (cudaMemcpyAsync(f.h_flags, f.d_flags, n, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
-        cudaMemcpyAsync(f.h_flags + c, f.d_flags + c, n, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
-        cudaMemcpyAsync(f.h_level, f.d_level, sizeof(int) * n, cudaMemcpyDeviceToHost, s) != cudaSuccess) {
-      orbb200::set_last_error("frame_is_in_frustum: D2H failed");
-      return ORB_E_CUDA;
-    }
-    for (int k = 0; k < 5; k++)
-      if (cudaMemcpyAsync(f.h_out + k * c, f.d_out + k * c, sizeof(float) * n, cudaMemcpyDeviceToHost, s) != cudaSuccess) {
-        orbb200::set_last_error("frame_is_in_frustum: D2H failed");
-        return ORB_E_CUDA;
-      }
-  }
-  if (cudaMemcpyAsync(f.h_count, f.d_count, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+  const size_t n = (size_t)v->n, c = f.stride;
+  if (cudaMemcpyAsync(f.h_res, f.d_res, Frustum::res_bytes(c), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
       cudaStreamSynchronize(s) != cudaSuccess) {
     orbb200::set_last_error(std::string("frame_is_in_frustum: ") + cudaGetErrorString(cudaGetLastError()));
     return ORB_E_CUDA;
   }
+  const uint8_t* h_flags = f.flags_of(f.h_res);
+  const float* h_out = f.out_of(f.h_res);
+  const int* h_level = f.level_of(f.h_res);
   for (size_t i = 0; i < n; i++) {
-    track_in_view[i] = f.h_flags[i];
-    proj_x[i] = f.h_out[i]; proj_y[i] = f.h_out[c + i];
-    if (f.h_flags[c + i]) {  // members the reference only writes for points in view
-      proj_xr[i] = f.h_out[2 * c + i]; view_cos[i] = f.h_out[3 * c + i]; depth[i] = f.h_out[4 * c + i];
-      scale_level[i] = f.h_level[i];
+    track_in_view[i] = h_flags[i];
+    proj_x[i] = h_out[i]; proj_y[i] = h_out[c + i];
+    if (h_flags[c + i]) {  // members the reference only writes for points in view
+      proj_xr[i] = h_out[2 * c + i]; view_cos[i] = h_out[3 * c + i]; depth[i] = h_out[4 * c + i];
+      scale_level[i] = h_level[i];
     }
   }
-  return *f.h_count;
+  return *f.count_of(f.h_res);
 }
 
 int frame_is_in_frustum_device(orb_frustum* h, const orb_frustum_view* v, float cos_limit, void* cuda_stream) {
@@ -239,17 +231,18 @@ int frame_is_in_frustum_device(orb_frustum* h, const orb_frustum_view* v, float 
 int frustum_device_results(orb_frustum* h, const uint8_t** d_track_in_view, const float** d_proj_x,
                            const float** d_proj_y, const float** d_proj_xr, const int32_t** d_scale_level,
                            const float** d_view_cos, const float** d_depth, const int32_t** d_count) {
-  if (!h || !h->f.d_out) return ORB_E_ARG;
-  const Frustum& f = h->f;
-  const size_t c = (size_t)f.cap;
-  if (d_track_in_view) *d_track_in_view = f.d_flags;
-  if (d_proj_x) *d_proj_x = f.d_out;
-  if (d_proj_y) *d_proj_y = f.d_out + c;
-  if (d_proj_xr) *d_proj_xr = f.d_out + 2 * c;
-  if (d_view_cos) *d_view_cos = f.d_out + 3 * c;
-  if (d_depth) *d_depth = f.d_out + 4 * c;
-  if (d_scale_level) *d_scale_level = f.d_level;
-  if (d_count) *d_count = f.d_count;
+  if (!h || !h->f.d_res || !h->f.stride) return ORB_E_ARG;
+  Frustum& f = h->f;
+  const size_t c = f.stride;  // layout of the latest call
+  const float* o = f.out_of(f.d_res);
+  if (d_track_in_view) *d_track_in_view = f.flags_of(f.d_res);
+  if (d_proj_x) *d_proj_x = o;
+  if (d_proj_y) *d_proj_y = o + c;
+  if (d_proj_xr) *d_proj_xr = o + 2 * c;
+  if (d_view_cos) *d_view_cos = o + 3 * c;
+  if (d_depth) *d_depth = o + 4 * c;
+  if (d_scale_level) *d_scale_level = f.level_of(f.d_res);
+  if (d_count) *d_count = f.count_of(f.d_res);
   return ORB_OK;
 }
 
