@@ -47,8 +47,10 @@ __global__ void __launch_bounds__(256) frustum_kernel(const __grid_constant__ Fr
     if (o.full) { D.proj_xr[i] = o.proj_xr; D.view_cos[i] = o.view_cos; D.depth[i] = o.depth; D.level[i] = o.level; }
     in = o.in_view;
   }
-  const unsigned m = __ballot_sync(0xffffffffu, in);
-  if ((threadIdx.x & 31) == 0 && m) atomicAdd(D.count, __popc(m));
+  if (D.count) {  // device-resident callers read the count on the device; the host path counts while it scatters
+    const unsigned m = __ballot_sync(0xffffffffu, in);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(D.count, __popc(m));
+  }
 }
 
 struct Frustum {
@@ -128,7 +130,7 @@ struct Frustum {
   }
 
   // uploads, launches, leaves the results on the device (after prepare())
-  int enqueue(const orb_frustum_view* v, float cos_limit, cudaStream_t s) {
+  int enqueue(const orb_frustum_view* v, float cos_limit, cudaStream_t s, bool device_count = true) {
     const size_t n = (size_t)v->n;
     stride = std::max<size_t>((n + 3) & ~(size_t)3, 4);
     const size_t c = stride;
@@ -143,14 +145,14 @@ struct Frustum {
       CUDA_TRYF(cudaEventRecord(ev_h2d, s));
       h2d_pending = true;
     }
-    CUDA_TRYF(cudaMemsetAsync(count_of(d_res), 0, sizeof(int), s));
+    if (device_count) CUDA_TRYF(cudaMemsetAsync(count_of(d_res), 0, sizeof(int), s));
     FrustumDev D;
     D.world_pos = d_in; D.normal = d_in + 3 * c; D.min_dist = d_in + 6 * c; D.max_dist = d_in + 7 * c;
     uint8_t* fl = flags_of(d_res);
     float* o = out_of(d_res);
     D.in_view = fl; D.full = fl + c;
     D.proj_x = o; D.proj_y = o + c; D.proj_xr = o + 2 * c; D.view_cos = o + 3 * c; D.depth = o + 4 * c;
-    D.level = level_of(d_res); D.count = count_of(d_res); D.n = v->n;
+    D.level = level_of(d_res); D.count = device_count ? count_of(d_res) : nullptr; D.n = v->n;
     const FrustumFrame F = frustum_frame_of(*v);
     CUDA_TRYF(cudaEventRecord(ev0, s));
     if (n) {
@@ -197,7 +199,7 @@ int frame_is_in_frustum(orb_frustum* h, const orb_frustum_view* v, float cos_lim
   Frustum& f = h->f;
   if ((rc = f.prepare(v->n))) return rc;
   cudaStream_t s = f.stream;
-  if ((rc = f.enqueue(v, cos_limit, s))) return rc;
+  if ((rc = f.enqueue(v, cos_limit, s, false))) return rc;
   const size_t n = (size_t)v->n, c = f.stride;
   if (cudaMemcpyAsync(f.h_res, f.d_res, Frustum::res_bytes(c), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
       cudaStreamSynchronize(s) != cudaSuccess) {
@@ -207,15 +209,17 @@ int frame_is_in_frustum(orb_frustum* h, const orb_frustum_view* v, float cos_lim
   const uint8_t* h_flags = f.flags_of(f.h_res);
   const float* h_out = f.out_of(f.h_res);
   const int* h_level = f.level_of(f.h_res);
+  int n_in_view = 0;
   for (size_t i = 0; i < n; i++) {
     track_in_view[i] = h_flags[i];
+    n_in_view += h_flags[i];
     proj_x[i] = h_out[i]; proj_y[i] = h_out[c + i];
     if (h_flags[c + i]) {  // members the reference only writes for points in view
       proj_xr[i] = h_out[2 * c + i]; view_cos[i] = h_out[3 * c + i]; depth[i] = h_out[4 * c + i];
       scale_level[i] = h_level[i];
     }
   }
-  return *f.count_of(f.h_res);
+  return n_in_view;
 }
 
 int frame_is_in_frustum_device(orb_frustum* h, const orb_frustum_view* v, float cos_limit, void* cuda_stream) {

@@ -89,10 +89,10 @@ __device__ __forceinline__ double edge_residual(const LbaDev& D, int e, const do
 }
 
 // One thread per landmark: linearise all its edges (base_binary_edge.hpp:55-120).
-// MINB = resident CTAs per SM asked from the compiler: 4 = 128 registers (no spills), 6 = 80 registers (the
-// Jacobian temporaries spill a little, 50 % more warps hide the dependent chains of this latency-bound kernel)
-template <bool LINEARIZE, int MINB>
-__global__ void __launch_bounds__(128, MINB) lin_kernel(LbaDev D) {
+// (128 registers per thread = 4 resident CTAs per SM; asking the compiler for 5 or 6 CTAs -- 102 / 80 registers
+// with spills -- was measured 3 % and 5 % slower at config 5.)
+template <bool LINEARIZE>
+__global__ void __launch_bounds__(128) lin_kernel(LbaDev D) {
   const int l = blockIdx.x * 128 + threadIdx.x;
   if (l >= D.n_mp) return;
   const double X[3] = {D.pts[3 * (size_t)l], D.pts[3 * (size_t)l + 1], D.pts[3 * (size_t)l + 2]};
@@ -1525,14 +1525,8 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
   // chi (robust) of the current state -> h_scalars[0]; all ranks see the global value
   auto eval_chi = [&](bool linearize) -> int {
     if (L) {
-      static const int lin_occ = getenv("ORB_B200_LIN_OCC") ? atoi(getenv("ORB_B200_LIN_OCC")) : 4;
-      if (linearize) {
-        if (lin_occ >= 6) lin_kernel<true, 6><<<lm_blocks, 128, 0, st>>>(D);
-        else if (lin_occ == 5) lin_kernel<true, 5><<<lm_blocks, 128, 0, st>>>(D);
-        else lin_kernel<true, 4><<<lm_blocks, 128, 0, st>>>(D);
-      } else {
-        lin_kernel<false, 4><<<lm_blocks, 128, 0, st>>>(D);
-      }
+      if (linearize) lin_kernel<true><<<lm_blocks, 128, 0, st>>>(D);
+      else lin_kernel<false><<<lm_blocks, 128, 0, st>>>(D);
     }
     reduce_kernel<<<1, 1024, 0, st>>>(D.chi_lm, L, D.scalars);
     S.launches += 2;
