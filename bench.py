@@ -854,6 +854,18 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: orb_slam3_b200 has no CPU path")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # NUMA: keep this rank's host threads (and the first touch of its pinned buffers) on the CPUs next to its GPU
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[local_rank]) if vis and vis.split(",")[local_rank].isdigit() else local_rank
+            words = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(phys), (os.cpu_count() + 63) // 64)
+            cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
+            if cpus:
+                os.sched_setaffinity(0, cpus & os.sched_getaffinity(0) or cpus)
+        except Exception:
+            pass
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     B, K, Wm, POOL = args.batch, args.steps, max(args.warmup, 3), args.pool
 
