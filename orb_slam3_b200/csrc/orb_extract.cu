@@ -449,6 +449,7 @@ struct FastGeom {
   int tile_pitch, tile_rows, tile_bytes;  // TMA box = tile_pitch x tile_rows bytes (pitch multiple of 16)
   int smap_pitch, smap_bytes;             // score map with a one-pixel zero frame
   int queue_cap;                          // pre-test survivors of one cell (<= band pixels)
+  int gq_off;                             // byte offset (from the end of the score map) of the 4-pixel group queue
   int per_warp_bytes;
 };
 constexpr int FASTW_WARPS = 8;
@@ -462,13 +463,17 @@ __device__ __forceinline__ uint32_t fast_gt4_msb(uint32_t d, uint32_t K) {
 }
 
 // Packed 4-diameter rejection test of one cell at threshold K (fast_gt4_msb) and compaction of the survivors into
-// `queue` with one ballot per byte lane.  PWD = tile pitch in words (compile-time for the common 64-byte box).
+// `queue`.  PWD = tile pitch in words (compile-time for the common 64-byte box).  Two steps, because per-pixel
+// compaction inside the scan cost more than the test itself (four ballots per visit): the scan only appends the
+// 4-pixel GROUPS that have a survivor (one ballot per visit, entry = first band column | row << 7 | nibble << 16)
+// to `gq`; the groups are expanded to pixels afterwards, 32 at a time, with one warp prefix sum per 32 groups.
 template <bool HI, int PWD_C>
-__device__ __forceinline__ int fast_pretest(const uint32_t* __restrict__ tw32, int pwd_rt, unsigned short* queue, int nitems,
-                                            int ng, int g0, unsigned magic_g, int ox, int bw, uint32_t K, int lane) {
+__device__ __forceinline__ int fast_pretest(const uint32_t* __restrict__ tw32, int pwd_rt, unsigned short* queue,
+                                            uint32_t* __restrict__ gq, int nitems, int ng, int g0, unsigned magic_g,
+                                            int ox, int bw, uint32_t K, int lane) {
   const int PWD = PWD_C ? PWD_C : pwd_rt;
   const unsigned lt = (1u << lane) - 1u;
-  int qn = 0;
+  int gn = 0;
   for (int base = 0; base < nitems; base += 32) {
     const int idx = base + lane;
     uint32_t m = 0;
@@ -493,16 +498,32 @@ __device__ __forceinline__ int fast_pretest(const uint32_t* __restrict__ tw32, i
       if (c0 < 0) m &= 0xffffffffu << (8 * -c0);
       if (c0 + 3 >= bw) m &= 0xffffffffu >> (8 * (c0 + 4 - bw));
     }
-    if (__any_sync(0xffffffffu, m != 0)) {
-      const unsigned short e0 = (unsigned short)((y << 7) + c0);
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const bool pk = (m >> (8 * k + 7)) & 1u;
-        const unsigned bal = __ballot_sync(0xffffffffu, pk);
-        if (pk) queue[qn + __popc(bal & lt)] = (unsigned short)(e0 + k);
-        qn += __popc(bal);
-      }
+    const unsigned bal = __ballot_sync(0xffffffffu, m != 0);
+    if (m) {
+      const uint32_t nib = ((((m >> 7) & 0x01010101u) * 0x01020408u) >> 24) & 0xfu;  // byte MSBs -> bits 0..3
+      gq[gn + __popc(bal & lt)] = (uint32_t)((y << 7) + c0 + 4) | (nib << 16);       // +4 keeps the low half >= 0
     }
+    gn += __popc(bal);
+  }
+  __syncwarp();
+  int qn = 0;
+  for (int gb = 0; gb < gn; gb += 32) {
+    const int gi = gb + lane;
+    const uint32_t ent = gi < gn ? gq[gi] : 0u;
+    const uint32_t nib = ent >> 16;
+    const int cnt = __popc(nib);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    int pos = qn + incl - cnt;
+    const int e0 = (int)(ent & 0xffffu) - 4;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      if ((nib >> k) & 1u) queue[pos++] = (unsigned short)(e0 + k);
+    qn += __shfl_sync(0xffffffffu, incl, 31);
   }
   return qn;
 }
@@ -518,6 +539,7 @@ fast_warp_kernel(const CUtensorMap* __restrict__ maps, int frame0, int nframes, 
   uint8_t* wbase = fw_dyn + (size_t)warp * G.per_warp_bytes;
   uint8_t* smap = wbase + 2 * G.tile_bytes;
   unsigned short* queue = reinterpret_cast<unsigned short*>(smap + G.smap_bytes);
+  uint32_t* gq = reinterpret_cast<uint32_t*>(smap + G.smap_bytes + G.gq_off);
   const unsigned bar0 = (unsigned)__cvta_generic_to_shared(&bars[warp][0]);
   const unsigned tile0 = (unsigned)__cvta_generic_to_shared(wbase);
   const int SW = G.smap_pitch, TP = TP_C ? TP_C : G.tile_pitch;
@@ -584,9 +606,9 @@ fast_warp_kernel(const CUtensorMap* __restrict__ maps, int frame0, int nframes, 
         const uint32_t K = pass == 0 ? K_ini : K_min;
         // 2. packed 4-diameter rejection test; survivors go to the queue (order inside a cell is irrelevant)
         if (pass == 0 ? hi_ini : hi_min)
-          qn = fast_pretest<true, TP_C / 4>(tw32, TP >> 2, queue, nitems, ng, g0, magic_g, ox, bw, K, lane);
+          qn = fast_pretest<true, TP_C / 4>(tw32, TP >> 2, queue, gq, nitems, ng, g0, magic_g, ox, bw, K, lane);
         else
-          qn = fast_pretest<false, TP_C / 4>(tw32, TP >> 2, queue, nitems, ng, g0, magic_g, ox, bw, K, lane);
+          qn = fast_pretest<false, TP_C / 4>(tw32, TP >> 2, queue, gq, nitems, ng, g0, magic_g, ox, bw, K, lane);
         __syncwarp();
         // 3. exact segment test + score of the queued pixels on dense lanes
         for (int q = lane; q < qn; q += 32) {
@@ -1413,7 +1435,13 @@ int Engine::ensure(int rows, int cols, int batch) {
     fw_smap_bytes = (int)align_up((size_t)fw_smap_pitch * (max_th - 6 + 2) + 4, 16);
     fw_queue_cap = (max_tw - 6) * (max_th - 6);
     const int tile_bytes = (int)align_up((size_t)fw_tile_pitch * fw_tile_rows, 128);
-    fw_per_warp = (int)align_up((size_t)2 * tile_bytes + fw_smap_bytes + 2 * (size_t)fw_queue_cap, 128);
+    int max_groups = 0;  // 4-pixel groups of the largest band, with the box starting at x0 & ~15
+    for (const CellDesc& c : cells) {
+      const int ox = c.x0 & 15, bw = c.x1 - c.x0 - 6, bh = c.y1 - c.y0 - 6;
+      if (bw > 0 && bh > 0) max_groups = std::max(max_groups, bh * (((ox + 3 + bw + 3) >> 2) - ((ox + 3) >> 2)));
+    }
+    fw_gq_off = (int)align_up(2 * (size_t)fw_queue_cap, 16);
+    fw_per_warp = (int)align_up((size_t)2 * tile_bytes + fw_smap_bytes + fw_gq_off + 4 * (size_t)max_groups, 128);
     const size_t smem = (size_t)fw_per_warp * FASTW_WARPS;
     const char* env = getenv("ORB_B200_FAST");  // "cta": the CTA-per-cell kernel
     fw_enabled = !(env && !strcmp(env, "cta")) && fw_tile_pitch <= 256 && fw_tile_rows <= 256 && smem <= 200 * 1024 &&
@@ -1571,7 +1599,7 @@ int Engine::run_device(int f0, int batch, const int* lap_host, cudaStream_t s, i
   if (fw_enabled) {
     FastGeom G;
     G.tile_pitch = fw_tile_pitch; G.tile_rows = fw_tile_rows; G.tile_bytes = fw_tile_pitch * fw_tile_rows;
-    G.smap_pitch = fw_smap_pitch; G.smap_bytes = fw_smap_bytes; G.queue_cap = fw_queue_cap; G.per_warp_bytes = fw_per_warp;
+    G.smap_pitch = fw_smap_pitch; G.smap_bytes = fw_smap_bytes; G.queue_cap = fw_queue_cap; G.gq_off = fw_gq_off; G.per_warp_bytes = fw_per_warp;
     const long long items = (long long)num_cells * B;
     const int grid = (int)std::min<long long>(fw_grid, (items + FASTW_WARPS - 1) / FASTW_WARPS);
     if (fw_tile_pitch == 64)
