@@ -20,6 +20,7 @@
 //      clearing pass, preserving the 1/30 bin quirk.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -585,7 +586,9 @@ struct Matcher {
   Pinned h_in, h_out;
   long long launches = 0;
   double last_ms = 0;
-  size_t cand_per_query = 48;  // initial candidate budget, grows on overflow
+  // initial candidate budget per query, grows on overflow (ORB_B200_MATCH_BUDGET: tests start it small to take
+  // the overflow paths)
+  size_t cand_per_query = getenv("ORB_B200_MATCH_BUDGET") ? std::max(1, atoi(getenv("ORB_B200_MATCH_BUDGET"))) : 48;
   // asynchronous mode (device-resident problems only): one batch may be in flight per handle
   bool async_mode = false, pending = false;
   int pending_count = 0;

@@ -124,3 +124,31 @@ def test_handles_with_different_parameters_interleave(oracle):
     _assert_same(ref_small, small(img), "small")
     _assert_same(ref_big, big(img), "big again")
     _assert_same(ref_small, small(img), "small again")
+
+
+def test_large_device_batch_runs_in_lanes_and_results_are_double_buffered(oracle):
+    """A device-resident batch of >= 32 frames is cut into sub-batches on separate streams (lanes); every frame
+    must still equal the oracle.  The results of call i stay intact while call i+1 runs (double buffering)."""
+    import torch
+    from orb_slam3_b200.extractor import ORBextractor
+    ext = ORBextractor(1000, 1.2, 8, 20, 7)
+    uniq = [synth_frame(480, 640, 40 + i, low_texture=(i == 3)) for i in range(6)]
+    frames = np.stack([uniq[i % 6] for i in range(40)])
+    d = torch.from_numpy(frames).cuda()
+    ext.extract_batch_device(d.data_ptr(), 40, 480, 640, 640, 480 * 640)
+    ext.synchronize()
+    kp0, ds0, n0, _, cap = ext.device_results()
+    orc = oracle.OracleExtractor(1000)
+    refs = [orc.extract(u) for u in uniq]
+    for b in (0, 1, 3, 13, 14, 26, 27, 39):          # lane boundaries at 14 / 28 for 3 lanes
+        _assert_same(refs[b % 6], ext.download_results(b), "lane frame %d" % b)
+    # second call on other frames: the first call's device buffers must be untouched until the call after that
+    d2 = torch.from_numpy(np.ascontiguousarray(frames[::-1])).cuda()
+    ext.extract_batch_device(d2.data_ptr(), 40, 480, 640, 640, 480 * 640)
+    ext.synchronize()
+    kp1, ds1, _, _, _ = ext.device_results()
+    assert kp1 != kp0 and ds1 != ds0                  # the other buffer set
+    _assert_same(refs[(39 - 5) % 6], ext.download_results(5), "second call")
+    ext.extract_batch_device(d.data_ptr(), 40, 480, 640, 640, 480 * 640)
+    ext.synchronize()
+    assert ext.device_results()[0] == kp0             # call i+2 reuses the first set

@@ -118,3 +118,74 @@ def test_empty_and_degenerate(oracle, matcher, feats):
     n_ref, a_ref = oracle.match_project_local(F, mps, 3.0, 0.8)
     n, a = matcher(0.8).SearchByProjection(F, mps, 3.0)
     assert n == n_ref and np.array_equal(a, a_ref)
+
+
+def test_frame_keys_on_the_device_and_overflow_retry(oracle, feats):
+    """on_device = 2: the frame's keypoints / descriptors are the extractor's device results, everything else is
+    host memory -- same assignments as the all-host call.  With ORB_B200_MATCH_BUDGET=1 (subprocess: the budget is
+    read when a matcher is created) every batch overflows its candidate buffer first and is re-run internally,
+    synchronously and in asynchronous mode: the caller never sees it."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = r"""
+import ctypes as C, numpy as np, sys, torch
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from orb_slam3_b200 import scenes
+from orb_slam3_b200.extractor import ORBextractor
+from orb_slam3_b200.matcher import ORBmatcher
+from orb_slam3_b200.synth import synth_frame, shifted_frame
+from orb_slam3_b200.views import orb_frame_view
+from oracle import oracle
+a = synth_frame(480, 640, 1); b = shifted_frame(a, 5, -3, 2)
+ext = ORBextractor(1000, 1.2, 8, 20, 7)
+_, ka, da = ext(a)
+d = torch.from_numpy(np.stack([b, b])).cuda()
+ext.extract_batch_device(d.data_ptr(), 2, 480, 640, 640, 480 * 640)
+ext.synchronize()
+_, kb, db = ext.download_results(0)
+kp, ds, _, _, cap = ext.device_results()
+curs, lasts, Ts, Fs, Ms = [], [], [], [], []
+for s in range(2):
+    c, l, T = scenes.last_frame_scene(ka, da, kb, db, 640, 480, (5, -3), seed=20 + s)
+    F, M = scenes.local_map_scene(kb, db, 640, 480, 500, seed=30 + s)
+    curs.append(c); lasts.append(l); Ts.append(T); Fs.append(F); Ms.append(M)
+def on_dev(v, fr):
+    w = orb_frame_view(); C.memmove(C.byref(w), C.byref(v), C.sizeof(w))
+    w.keys = kp + fr * cap * 28; w.desc = ds + fr * cap * 32; w.u_right = None
+    return w
+m1, m2 = ORBmatcher(0.9, True), ORBmatcher(0.8, True)
+r, outs = m1.project_last_batch([on_dev(c, i) for i, c in enumerate(curs)], lasts, np.stack(Ts), 15.0, on_device=2)
+for s in range(2):
+    n_ref, a_ref = oracle.match_project_last(curs[s], lasts[s], Ts[s], 15.0)
+    assert r[s] == n_ref and np.array_equal(outs[s], a_ref), ("last", s)
+r, outs = m2.project_local_batch([on_dev(f, i) for i, f in enumerate(Fs)], Ms, 3.0, on_device=2)
+for s in range(2):
+    n_ref, a_ref = oracle.match_project_local(Fs[s], Ms[s], 3.0, 0.8)
+    assert r[s] == n_ref and np.array_equal(outs[s], a_ref), ("local", s)
+# asynchronous, fully device-resident batch: overflow handled inside match_synchronize
+m3 = ORBmatcher(0.8, True); m3.set_async(True)
+dm = [{k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in M._keep.items()} for M in Ms]
+from orb_slam3_b200.views import orb_mappoint_view
+views, frames, keep = [], [], []
+for i, (F, M) in enumerate(zip(Fs, Ms)):
+    mv = orb_mappoint_view(); mv.n = M.n
+    for k in ("track_in_view", "is_bad", "has_obs", "proj_x", "proj_y", "proj_xr", "scale_level", "view_cos", "depth", "desc"):
+        setattr(mv, k, dm[i][k].data_ptr())
+    fv = on_dev(F, i)
+    tk = torch.from_numpy(F._keep[5]).cuda(); keep.append(tk)
+    fv.kp_taken = tk.data_ptr()
+    views.append(mv); frames.append(fv)
+assign = torch.full((2, cap), -7, dtype=torch.int32, device="cuda")
+r, _ = m3.project_local_batch(frames, views, 3.0, on_device=True, assign_ptrs=[assign.data_ptr() + 4 * i * cap for i in range(2)])
+m3.synchronize()
+for s in range(2):
+    n_ref, a_ref = oracle.match_project_local(Fs[s], Ms[s], 3.0, 0.8)
+    assert r[s] == n_ref and np.array_equal(assign[s, :len(a_ref)].cpu().numpy(), a_ref), ("async", s)
+print("MATCH_MODES_OK")
+""" % (os.path.dirname(here), here)
+    for budget in ("48", "1"):
+        env = dict(os.environ, ORB_B200_MATCH_BUDGET=budget)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0 and "MATCH_MODES_OK" in r.stdout, (budget, r.stdout[-1500:] + r.stderr[-3000:])
