@@ -89,17 +89,16 @@ resize_level_kernel(uint8_t* __restrict__ pyr, size_t frame_stride, size_t src_o
 }
 
 // Same arithmetic, staged: one CTA produces RS_ROWS consecutive output rows of one frame.  The (<= RS_SRC) source
-// rows they touch are copied to shared memory with coalesced 16-byte loads.  The horizontal pass runs ONCE per
-// staged source row (adjacent output rows share source rows: 1.45 instead of 2 horizontal passes per output row)
-// and leaves h >> 4 as 16-bit values in shared memory; the vertical pass combines two of them per output pixel.
-// The per-column tables (xofs, alpha) are read once per thread and reused for every row of the CTA.
+// rows they touch are copied to shared memory with coalesced 16-byte loads; the four byte gathers per output
+// pixel then hit shared memory instead of issuing four global loads each, and the per-column tables
+// (xofs, alpha) are read once per thread and reused for every row of the CTA.
 constexpr int RS_ROWS = 4, RS_SRC = 8, RS_THREADS = 256;
 
 __global__ void __launch_bounds__(RS_THREADS)
 resize_rows_kernel(uint8_t* __restrict__ pyr, size_t frame_stride, size_t src_off, int sw, int sh, int spitch,
                    size_t dst_off, int dw, int dh, int dpitch, const int* __restrict__ xofs,
                    const short2* __restrict__ alpha, const int* __restrict__ yofs, const short2* __restrict__ beta) {
-  extern __shared__ __align__(16) uint8_t rs_rows[];  // [RS_SRC][spitch] source bytes, then [RS_SRC][hp] uint16 h >> 4
+  extern __shared__ __align__(16) uint8_t rs_rows[];  // [RS_SRC][spitch]
   __shared__ int s_y[RS_ROWS];
   uint8_t* base = pyr + (size_t)blockIdx.y * frame_stride;
   const uint8_t* S = base + src_off;
@@ -108,8 +107,6 @@ resize_rows_kernel(uint8_t* __restrict__ pyr, size_t frame_stride, size_t src_of
   const int lo = min(max(yofs[y0], 0), sh - 1), hi = min(max(yofs[y0 + ny - 1] + 1, 0), sh - 1);
   const int nsrc = hi - lo + 1;  // <= RS_SRC for down-scaling factors up to 2 (host-checked)
   const int vec = spitch >> 4;   // the slab pitch is a multiple of 64
-  const int hp = (dw + 3) & ~3;  // pitch of the h rows (uint16 elements)
-  uint16_t* H = reinterpret_cast<uint16_t*>(rs_rows + (size_t)RS_SRC * spitch);
   for (int i = threadIdx.x; i < nsrc * vec; i += RS_THREADS) {
     const int r = i / vec, c = i - r * vec;
     reinterpret_cast<uint4*>(rs_rows + (size_t)r * spitch)[c] =
@@ -117,7 +114,6 @@ resize_rows_kernel(uint8_t* __restrict__ pyr, size_t frame_stride, size_t src_of
   }
   if (threadIdx.x < ny) s_y[threadIdx.x] = yofs[y0 + threadIdx.x];
   __syncthreads();
-  // horizontal pass: 4 columns per thread, every staged row
   for (int x4 = threadIdx.x * 4; x4 < dw; x4 += RS_THREADS * 4) {
     int sx[4], sx1[4];
     short2 a[4];
@@ -128,28 +124,17 @@ resize_rows_kernel(uint8_t* __restrict__ pyr, size_t frame_stride, size_t src_of
       sx1[k] = min(sx[k] + 1, sw - 1);
       a[k] = alpha[x];
     }
-    for (int r = 0; r < nsrc; r++) {
-      const uint8_t* Sr = rs_rows + (size_t)r * spitch;
-      uint32_t h[4];
-#pragma unroll
-      for (int k = 0; k < 4; k++) h[k] = (uint32_t)(Sr[sx[k]] * a[k].x + Sr[sx1[k]] * a[k].y) >> 4;  // <= 32640
-      *reinterpret_cast<uint2*>(H + (size_t)r * hp + x4) = make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
-    }
-  }
-  __syncthreads();
-  // vertical pass: 4 columns x ny rows per thread, one 32-bit store per row
-  for (int x4 = threadIdx.x * 4; x4 < dw; x4 += RS_THREADS * 4) {
     for (int r = 0; r < ny; r++) {
       const int y = y0 + r, sy = s_y[r];
-      const uint2 h0 = *reinterpret_cast<const uint2*>(H + (size_t)(min(max(sy, 0), sh - 1) - lo) * hp + x4);
-      const uint2 h1 = *reinterpret_cast<const uint2*>(H + (size_t)(min(max(sy + 1, 0), sh - 1) - lo) * hp + x4);
+      const uint8_t* S0 = rs_rows + (size_t)(min(max(sy, 0), sh - 1) - lo) * spitch;
+      const uint8_t* S1 = rs_rows + (size_t)(min(max(sy + 1, 0), sh - 1) - lo) * spitch;
       const short2 b = beta[y];
-      const int t0[4] = {(int)(h0.x & 0xffffu), (int)(h0.x >> 16), (int)(h0.y & 0xffffu), (int)(h0.y >> 16)};
-      const int t1[4] = {(int)(h1.x & 0xffffu), (int)(h1.x >> 16), (int)(h1.y & 0xffffu), (int)(h1.y >> 16)};
       uint32_t packed = 0;
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        const int v = (((b.x * t0[k]) >> 16) + ((b.y * t1[k]) >> 16) + 2) >> 2;
+        const int h0 = S0[sx[k]] * a[k].x + S0[sx1[k]] * a[k].y;
+        const int h1 = S1[sx[k]] * a[k].x + S1[sx1[k]] * a[k].y;
+        const int v = (((b.x * (h0 >> 4)) >> 16) + ((b.y * (h1 >> 4)) >> 16) + 2) >> 2;
         if (x4 + k < dw) packed |= (uint32_t)(v & 0xff) << (8 * k);
       }
       *reinterpret_cast<uint32_t*>(base + dst_off + (size_t)y * dpitch + x4) = packed;
@@ -1415,7 +1400,7 @@ int Engine::ensure(int rows, int cols, int batch) {
     for (int l = 1; l < nlevels && resize_rows_ok; l++) {
       const LevelDev& S = levels[l - 1];
       const LevelDev& D = levels[l];
-      smem = std::max(smem, (size_t)RS_SRC * (S.pitch + 2 * (((size_t)D.w + 3) & ~(size_t)3)));
+      smem = std::max(smem, (size_t)RS_SRC * S.pitch);
       for (int y0 = 0; y0 < D.h; y0 += RS_ROWS) {
         const int y1 = std::min(y0 + RS_ROWS, D.h) - 1;
         const int lo = std::min(std::max(h_yofs[rs[l].y_off + y0], 0), S.h - 1);
@@ -1583,7 +1568,7 @@ int Engine::run_device(int f0, int batch, const int* lap_host, cudaStream_t s, i
     const LevelDev& S = levels[l - 1];
     const LevelDev& D = levels[l];
     if (resize_rows_ok) {
-      resize_rows_kernel<<<dim3((D.h + RS_ROWS - 1) / RS_ROWS, B), RS_THREADS, (size_t)RS_SRC * (S.pitch + 2 * (((size_t)D.w + 3) & ~(size_t)3)), s>>>(
+      resize_rows_kernel<<<dim3((D.h + RS_ROWS - 1) / RS_ROWS, B), RS_THREADS, (size_t)RS_SRC * S.pitch, s>>>(
           pyr, pyr_frame_bytes, S.img_off, S.w, S.h, S.pitch, D.img_off, D.w, D.h, D.pitch, d_xofs + rs[l].x_off,
           d_alpha + rs[l].x_off, d_yofs + rs[l].y_off, d_beta + rs[l].y_off);
     } else {
