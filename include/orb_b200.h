@@ -542,6 +542,8 @@ int orb_debug_octree_host(const int* xys, int n, int band_w, int band_h, int n_f
                           int h_cell, int n_cols, int* out_xys, int out_cap);
 /* Host execution of the libstdc++ introsort emulation: perm_out[i] = input index. */
 int orb_debug_introsort(const int* count, const int* ulx, int n, int* perm_out);
+/* the same permutation from the level-synchronous form the octree CTA runs (csrc/introsort_emul.h) */
+int orb_debug_introsort_levels(const int* count, const int* ulx, int n, int* perm_out);
 /* cosf / sinf exactly as glibc 2.39 rounds them (csrc/glibc_sincosf.h; the reference's `(float)cos(angle)`
  * in computeOrbDescriptor, ORBextractor.cc:111-112), evaluated by a kernel on `device` (x, outputs: host
  * arrays of n floats) and by the same source on the host (fused = 1: the -mfma build of libm, 0: SSE2). */

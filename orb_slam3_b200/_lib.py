@@ -108,6 +108,7 @@ SIGNATURES = {
     "orb_debug_candidates": (_i, [_vp, _i, _i, _vp, _i]),
     "orb_debug_octree_host": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i]),
     "orb_debug_introsort": (_i, [_vp, _vp, _i, _vp]),
+    "orb_debug_introsort_levels": (_i, [_vp, _vp, _i, _vp]),
     "orb_debug_sincos_device": (_i, [_i, _vp, _sz, _vp, _vp]),
     "orb_debug_sincos_host": (_i, [_vp, _sz, _vp, _vp, _i]),
 }

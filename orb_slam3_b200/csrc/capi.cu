@@ -170,6 +170,7 @@ int orb_debug_octree_host(const int* xys, int n, int band_w, int band_h, int n_f
   std::vector<int> pt_node(n + 1), ints(nc * (10 + 16 + 5));
   std::vector<uint8_t> pt_q(n + 1);
   std::vector<SortNode> sortbuf(nc);
+  std::vector<int> sortwork(6 * nc);
   std::vector<unsigned long long> best(nc);
   OctreeScratch s;
   s.pt_node = pt_node.data(); s.pt_q = pt_q.data();
@@ -177,7 +178,7 @@ int orb_debug_octree_host(const int* xys, int n, int band_w, int band_h, int n_f
   for (int b = 0; b < 2; b++) for (int f = 0; f < 5; f++) { s.nd[b][f] = q; q += nc; }
   s.childcnt = q; q += 4 * nc; s.cidx = q; q += 4 * nc; s.eidx = q; q += 4 * nc; s.remap = q; q += 4 * nc;
   s.rank = q; q += nc; s.proc = q; q += nc; s.surv = q; q += nc; s.tmp = q; q += nc; s.expand_pos = q; q += nc;
-  s.sortbuf = sortbuf.data(); s.best = best.data();
+  s.sortbuf = sortbuf.data(); s.sortwork = sortwork.data(); s.best = best.data();
   std::vector<int> out(3 * nc);
   HostBackend be;
   int m = octree_select(be, cand.data(), n, p, s, out.data());
@@ -185,6 +186,17 @@ int orb_debug_octree_host(const int* xys, int n, int band_w, int band_h, int n_f
     out_xys[3 * i] = out[3 * i]; out_xys[3 * i + 1] = out[3 * i + 1]; out_xys[3 * i + 2] = out[3 * i + 2];
   }
   return m;
+}
+
+// the level-synchronous form (what the octree CTA runs), single-threaded on the host
+int orb_debug_introsort_levels(const int* count, const int* ulx, int n, int* perm_out) {
+  std::vector<orbb200::SortNode> v(n > 0 ? n : 1);
+  for (int i = 0; i < n; i++) v[i] = orbb200::make_sort_node(count[i], ulx[i], i);
+  std::vector<int> work(6 * (size_t)(n / 8 + 8));
+  orbb200::HostBackend be;
+  orbb200::introsort_levels(be, v.data(), n, work.data(), n / 8 + 8);
+  for (int i = 0; i < n; i++) perm_out[i] = v[i].id;
+  return n;
 }
 
 int orb_debug_introsort(const int* count, const int* ulx, int n, int* perm_out) {

@@ -175,4 +175,80 @@ ORB_HD void introsort_emul(SortNode* a, int n) {
   }
 }
 
+// ---- the same sort, level-synchronous ------------------------------------------------------------------------
+// introsort's recursion works on disjoint sub-ranges, and so does the final insertion pass: unguarded_partition
+// leaves every element left of a cut <= every element right of it, so an insertion never moves an element across
+// a cut (the scan stops at the first element that is not greater -- the left neighbour of the range at the
+// latest).  The operations of different sub-ranges therefore commute, and the permutation std::sort produces is
+// reproduced by ANY schedule that applies, per sub-range, the same operations in the same order.  Here all
+// sub-ranges of one recursion depth are processed together, one thread per sub-range: a range of more than 16
+// elements is partitioned exactly like __introsort_loop does (median of three to the front, unguarded partition,
+// heapsort at the depth limit) and hands its two halves to the next level; a range of at most 16 elements gets
+// its share of __final_insertion_sort at once (guarded for the range that starts the array, bounded by the
+// range start otherwise, which is where the unguarded scan stops anyway).  The critical path is one partition
+// per level (n, n/2, n/4, ... elements) instead of every partition and every insertion of the array in turn.
+// `work` = 6 * cap ints (two lists of (first, last, depth)), cap >= n / 8 + 4; all threads of the backend call it.
+ORB_HD void sn_bounded_linear_insert(SortNode* a, int last, int lo) {
+  SortNode val = a[last];
+  int next = last - 1;
+  while (next >= lo && node_less(val, a[next])) {
+    a[last] = a[next];
+    last = next;
+    --next;
+  }
+  a[last] = val;
+}
+
+#ifdef __CUDACC__
+#pragma nv_exec_check_disable
+#endif
+template <class BE>
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+void introsort_levels(BE& be, SortNode* a, int n, int* work, int cap) {
+  if (n <= 1) return;
+  const int tid = be.tid(), nt = be.nthreads();
+  int* cnt[2] = {be.shared_int(1), be.shared_int(2)};
+  int* list[2] = {work, work + 3 * cap};
+  if (tid == 0) {
+    int lg = 0;
+    for (int t = n; t > 1; t >>= 1) lg++;
+    list[0][0] = 0; list[0][1] = n; list[0][2] = 2 * lg;
+    *cnt[0] = 1; *cnt[1] = 0;
+  }
+  be.sync();
+  for (int level = 0;; level++) {
+    const int c = level & 1;
+    const int count = *cnt[c];
+    if (count == 0) break;
+    const int* cur = list[c];
+    int* nxt = list[c ^ 1];
+    for (int r = tid; r < count; r += nt) {
+      const int first = cur[3 * r], last = cur[3 * r + 1];
+      int depth = cur[3 * r + 2];
+      if (last - first > 16) {
+        if (depth == 0) {
+          sn_heap_sort(a + first, last - first);
+        } else {
+          --depth;
+          const int mid = first + (last - first) / 2;
+          sn_move_median_to_first(a, first, first + 1, mid, last - 1);
+          const int cut = sn_unguarded_partition(a, first + 1, last, first);
+          const int slot = be.atomic_add(cnt[c ^ 1], 2);
+          nxt[3 * slot] = first;   nxt[3 * slot + 1] = cut;  nxt[3 * slot + 2] = depth;
+          nxt[3 * slot + 3] = cut; nxt[3 * slot + 4] = last; nxt[3 * slot + 5] = depth;
+        }
+      } else if (first == 0) {
+        sn_insertion_sort(a, 0, last);
+      } else {
+        for (int i = first; i < last; ++i) sn_bounded_linear_insert(a, i, first);
+      }
+    }
+    be.sync();
+    if (tid == 0) *cnt[c] = 0;
+    be.sync();
+  }
+}
+
 }  // namespace orbb200

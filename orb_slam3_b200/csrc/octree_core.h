@@ -51,6 +51,7 @@ struct OctreeScratch {
   int* tmp;           // [node_cap]
   int* expand_pos;    // [node_cap]   nodes with >1 point, creation order
   SortNode* sortbuf;  // [node_cap]
+  int* sortwork;      // [6*node_cap] range lists of the level-synchronous sort
   unsigned long long* best;  // [node_cap]
 };
 
@@ -179,8 +180,7 @@ int octree_select(BE& be, const Cand* cand, int n, const OctreeLevelParams& p,
           s.sortbuf[e] = make_sort_node(cnt[node], ulx[node], node);
         }
         be.sync();
-        if (tid == 0) introsort_emul(s.sortbuf, P);
-        be.sync();
+        introsort_levels(be, s.sortbuf, P, s.sortwork, p.node_cap);  // ends with a barrier
         // split from the back (:701) until the list holds >= N nodes (:746)
         for (int k = tid; k < P; k += nt) {
           const int node = s.sortbuf[P - 1 - k].id;

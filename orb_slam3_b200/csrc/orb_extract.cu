@@ -705,6 +705,7 @@ __host__ __device__ inline size_t octree_scratch_layout(uint8_t* base, int cand_
   o = carve(off, sizeof(int) * (size_t)node_cap); if (s) s->tmp = (int*)(base + o);
   o = carve(off, sizeof(int) * (size_t)node_cap); if (s) s->expand_pos = (int*)(base + o);
   o = carve(off, sizeof(SortNode) * (size_t)node_cap); if (s) s->sortbuf = (SortNode*)(base + o);
+  o = carve(off, sizeof(int) * 6 * (size_t)node_cap); if (s) s->sortwork = (int*)(base + o);
   o = carve(off, sizeof(unsigned long long) * (size_t)node_cap);
   if (s) s->best = (unsigned long long*)(base + o);
   return off;
@@ -747,6 +748,7 @@ octree_kernel(const Cand* __restrict__ cand, size_t cand_frame_stride, const int
       s.proc = q; q += nc;
       s.expand_pos = q; q += nc;
       s.sortbuf = reinterpret_cast<SortNode*>(q + (nc & 1)); q += 2 * nc + 2;  // 8-byte aligned
+      s.sortwork = q; q += 6 * nc;
     }
   }
   const int n = min(cand_count[f * nlevels + level], L.cand_cap);
@@ -1378,7 +1380,7 @@ int Engine::ensure(int rows, int cols, int batch) {
   {
     int max_nc = 0;
     for (int l = 0; l < nlevels; l++) max_nc = std::max(max_nc, levels[l].oct.node_cap);
-    const size_t need = (size_t)19 * max_nc * sizeof(int), need_full = ((size_t)33 * max_nc + 2) * sizeof(int);
+    const size_t need = (size_t)19 * max_nc * sizeof(int), need_full = ((size_t)39 * max_nc + 2) * sizeof(int);
     oct_smem_node_cap_full = 0;
     if (need_full <= 100 * 1024 && !getenv("ORB_B200_OCTREE_SMEM_BASE")) {
       oct_smem_node_cap = oct_smem_node_cap_full = max_nc;

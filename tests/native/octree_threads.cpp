@@ -54,18 +54,19 @@ struct Scratch {
   std::vector<int> pt_node, ints;
   std::vector<uint8_t> pt_q;
   std::vector<SortNode> sortbuf;
+  std::vector<int> sortwork;
   std::vector<unsigned long long> best;
   std::vector<int> out;
   OctreeScratch s;
   Scratch(int n, const OctreeLevelParams& p) {
     const size_t nc = p.node_cap;
-    pt_node.resize(n + 1); ints.resize(nc * (10 + 16 + 5)); pt_q.resize(n + 1); sortbuf.resize(nc); best.resize(nc); out.assign(3 * nc, 0);
+    pt_node.resize(n + 1); ints.resize(nc * (10 + 16 + 5)); pt_q.resize(n + 1); sortbuf.resize(nc); sortwork.resize(6 * nc); best.resize(nc); out.assign(3 * nc, 0);
     s.pt_node = pt_node.data(); s.pt_q = pt_q.data();
     int* q = ints.data();
     for (int b = 0; b < 2; b++) for (int f = 0; f < 5; f++) { s.nd[b][f] = q; q += nc; }
     s.childcnt = q; q += 4 * nc; s.cidx = q; q += 4 * nc; s.eidx = q; q += 4 * nc; s.remap = q; q += 4 * nc;
     s.rank = q; q += nc; s.proc = q; q += nc; s.surv = q; q += nc; s.tmp = q; q += nc; s.expand_pos = q; q += nc;
-    s.sortbuf = sortbuf.data(); s.best = best.data();
+    s.sortbuf = sortbuf.data(); s.sortwork = sortwork.data(); s.best = best.data();
   }
 };
 

@@ -73,6 +73,8 @@ def test_introsort_emulation_equals_std_sort(oracle):
         b = np.zeros(n, np.int32)
         lib.orb_debug_introsort(L.ptr(cnt), L.ptr(ulx), n, L.ptr(b))
         assert np.array_equal(oracle.sort_nodes(cnt, ulx), b)
+        lib.orb_debug_introsort_levels(L.ptr(cnt), L.ptr(ulx), n, L.ptr(b))      # the form the octree CTA runs
+        assert np.array_equal(oracle.sort_nodes(cnt, ulx), b)
     for n in (17, 100, 1000, 5000):  # sorted / reversed / organ pipe / constant
         for cnt in (np.arange(n), np.arange(n)[::-1],
                     np.concatenate([np.arange(n // 2), np.arange(n - n // 2)[::-1]]), np.zeros(n)):
@@ -80,6 +82,8 @@ def test_introsort_emulation_equals_std_sort(oracle):
             ulx = np.zeros(n, np.int32)
             b = np.zeros(n, np.int32)
             lib.orb_debug_introsort(L.ptr(cnt), L.ptr(ulx), n, L.ptr(b))
+            assert np.array_equal(oracle.sort_nodes(cnt, ulx), b)
+            lib.orb_debug_introsort_levels(L.ptr(cnt), L.ptr(ulx), n, L.ptr(b))
             assert np.array_equal(oracle.sort_nodes(cnt, ulx), b)
 
 
