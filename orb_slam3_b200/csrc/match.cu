@@ -10,12 +10,13 @@
 //   1. static phase, fully parallel: the 64x48 grid (Frame.cc:385-416), the window
 //      query of every map point in GetFeaturesInArea order (Frame.cc:657-723), and
 //      the Hamming distance (__popc over 8 words) of every (point, candidate) pair;
-//   2. resolution rounds inside one CTA per problem: an unresolved point may
-//      finalise iff it is the lowest-index unresolved point among all points that
-//      still list any of its free candidates (atomicMin per keypoint); points that
-//      finalise in one round have disjoint candidates, so each replays the
-//      reference's scan (best / second best / ratio or best only) on the current
-//      `taken` flags -- writes to one keypoint happen in index order as in the loop;
+//   2. resolution rounds inside one CTA per problem.  A point can only ever TAKE a candidate whose distance is
+//      <= TH_HIGH, so an unresolved point claims exactly those (atomicMin of its index per keypoint); a point may
+//      finalise iff none of its still-free candidates is claimed by a lower-index unresolved point.  It then replays
+//      the reference's scan (best / second best / ratio, or best only); `takenby[c]` records WHICH point took a
+//      keypoint, and a point ignores takes by higher indices (those happen later in the reference's loop).  Takes
+//      of a round are applied after the round's barrier.  With real descriptors almost every point finalises in
+//      the first one or two rounds (the previous rule -- own ALL free candidates -- needed tens of rounds);
 //   3. rotation histogram, ComputeThreeMaxima (ORBmatcher.cc:2012-2053) and the
 //      clearing pass, preserving the 1/30 bin quirk.
 #include <cuda_runtime.h>
@@ -81,14 +82,14 @@ struct ProjProblem {
   float th, ratio, th_far;
   int far_points;
   // scratch
-  float *q_u, *q_v, *q_r, *q_aux;
-  int *q_minl, *q_maxl, *q_cnt, *q_off;
-  uint8_t* q_state;  // 0 inactive/resolved, 1 unresolved
+  int *q_cnt, *q_off;  // candidate list of point j: cand_*[q_off[j] .. q_off[j] + q_cnt[j])
+  uint8_t* q_state;    // 0 inactive/resolved, 1 unresolved, 2 finalised this round with a take to apply
   int* cand_idx;
   unsigned short* cand_dist;
   int cand_cap;
+  int* cand_used;      // [1] bump allocator over cand_*
   int* minidx;
-  uint8_t* taken;
+  int* takenby;        // [F.n] index of the point that took the keypoint; -1 taken on entry; INT_MAX free
   int *acc_kp, *acc_bin;
   // outputs
   int* assign;   // [F.n]
@@ -124,6 +125,7 @@ __device__ __forceinline__ int popc256(const uint8_t* __restrict__ a, const uint
 // ascending keypoint index inside a cell.  One CTA per frame.
 struct ProjProblem;
 __device__ const DevFrame& frame_of(const ProjProblem* probs, int k);
+__device__ void init_problem(const ProjProblem* probs, int k);
 __global__ void __launch_bounds__(256) grid_build_kernel(const ProjProblem* probs) {
   __shared__ int cnt[GRID_CELLS + 1];
   __shared__ int wsum[8];
@@ -172,6 +174,7 @@ __global__ void __launch_bounds__(256) grid_build_kernel(const ProjProblem* prob
       F.cell_items[j + 1] = v;
     }
   }
+  init_problem(probs, blockIdx.x);
 }
 
 // Frame::GetFeaturesInArea (Frame.cc:657-723) plus the static per-candidate gate
@@ -202,127 +205,165 @@ __device__ __forceinline__ void for_each_in_area(const DevFrame& F, float x, flo
   }
 }
 
-// Phase 1a: per query point, window parameters and candidate count.
-__global__ void __launch_bounds__(128) proj_setup_kernel(ProjProblem* probs) {
-  ProjProblem& P = probs[blockIdx.y];
-  const int j = blockIdx.x * 128 + threadIdx.x;
-  if (j >= P.nq) return;
-  const DevFrame& F = P.F;
-  bool active = false;
-  float u = 0, v = 0, r = 0, aux = 0;
-  int minl = 0, maxl = 0;
-  if (P.kind == 0) {
-    // ORBmatcher.cc:51-70
-    active = P.in_view[j] && !(P.far_points && P.depth[j] > P.th_far) && !P.is_bad[j];
-    if (active) {
-      const int lvl = P.lvl[j];
-      float rr = ((double)P.vcos[j] > 0.998) ? 2.5f : 4.0f;
-      if (P.th != 1.0f) rr = __fmul_rn(rr, P.th);
-      r = __fmul_rn(rr, F.scale[lvl]);
-      u = P.px[j]; v = P.py[j]; aux = P.pxr[j];
-      minl = lvl - 1; maxl = lvl;
-    }
-  } else if (P.has_mp[j]) {
-    // ORBmatcher.cc:1701-1733; Tcw * x3Dw as Sophus/Eigen evaluate it
-    const float qx = P.T[0], qy = P.T[1], qz = P.T[2], qw = P.T[3];
-    const float vx = P.wpos[3 * j], vy = P.wpos[3 * j + 1], vz = P.wpos[3 * j + 2];
-    float ux = __fsub_rn(__fmul_rn(qy, vz), __fmul_rn(qz, vy));
-    float uy = __fsub_rn(__fmul_rn(qz, vx), __fmul_rn(qx, vz));
-    float uz = __fsub_rn(__fmul_rn(qx, vy), __fmul_rn(qy, vx));
-    ux = __fadd_rn(ux, ux); uy = __fadd_rn(uy, uy); uz = __fadd_rn(uz, uz);
-    const float c0 = __fsub_rn(__fmul_rn(qy, uz), __fmul_rn(qz, uy));
-    const float c1 = __fsub_rn(__fmul_rn(qz, ux), __fmul_rn(qx, uz));
-    const float c2 = __fsub_rn(__fmul_rn(qx, uy), __fmul_rn(qy, ux));
-    const float xc = __fadd_rn(__fadd_rn(__fadd_rn(vx, __fmul_rn(qw, ux)), c0), P.T[4]);
-    const float yc = __fadd_rn(__fadd_rn(__fadd_rn(vy, __fmul_rn(qw, uy)), c1), P.T[5]);
-    const float zc = __fadd_rn(__fadd_rn(__fadd_rn(vz, __fmul_rn(qw, uz)), c2), P.T[6]);
-    const float invzc = (float)(1.0 / (double)zc);
-    if (!(invzc < 0)) {
-      u = __fadd_rn(__fdiv_rn(__fmul_rn(F.fx, xc), zc), F.cx);
-      v = __fadd_rn(__fdiv_rn(__fmul_rn(F.fy, yc), zc), F.cy);
-      if (!(u < F.min_x || u > F.max_x) && !(v < F.min_y || v > F.max_y)) {
-        active = true;
-        const int o = P.octave[j];
-        r = __fmul_rn(P.th, F.scale[o]);
-        aux = __fsub_rn(u, __fmul_rn(F.bf, invzc));  // ur (:1754)
-        if (P.forward) { minl = o; maxl = -1; }
-        else if (P.backward) { minl = 0; maxl = o; }
-        else { minl = o - 1; maxl = o + 1; }
-      }
-    }
-  }
-  int cnt = 0;
-  if (active) {
-    for_each_in_area(F, u, v, r, minl, maxl, [&](int idx) {
-      if (F.u_right) {
-        const float ur = F.u_right[idx];
-        if (ur > 0 && fabsf(__fsub_rn(aux, ur)) > r) return;
-      }
-      cnt++;
-    });
-  }
-  P.q_u[j] = u; P.q_v[j] = v; P.q_r[j] = r; P.q_aux[j] = aux;
-  P.q_minl[j] = minl; P.q_maxl[j] = maxl;
-  P.q_cnt[j] = cnt;
-  P.q_state[j] = (active && cnt > 0) ? 1 : 0;
-}
-
-// Phase 1b: exclusive scan of candidate counts (one CTA per problem).
-__global__ void __launch_bounds__(1024) proj_scan_kernel(ProjProblem* probs) {
-  __shared__ int wsum[32];
-  __shared__ int carry;
-  ProjProblem& P = probs[blockIdx.x];
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int base = 0; base < P.nq; base += 1024) {
-    const int j = base + threadIdx.x;
-    const int v = j < P.nq ? P.q_cnt[j] : 0;
-    int incl = v;
-    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-    if (lane == 31) wsum[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-      int w = wsum[lane], wi = w;
-      for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
-      wsum[lane] = wi - w;
-    }
-    __syncthreads();
-    const int excl = carry + wsum[warp] + incl - v;
-    if (j < P.nq) P.q_off[j] = excl;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry = excl + v;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    P.q_off[P.nq] = carry;
-    P.result[1] = carry > P.cand_cap ? 1 : 0;
-    P.result[0] = 0;
-  }
-  for (int i = threadIdx.x; i < P.F.n; i += 1024) {
+// Outputs / per-keypoint state of one problem, reset by the CTA that builds its grid.
+__device__ void init_problem(const ProjProblem* probs, int k) {
+  const ProjProblem& P = probs[k];
+  for (int i = threadIdx.x; i < P.F.n; i += blockDim.x) {
     P.assign[i] = -1;
-    P.taken[i] = P.F.kp_taken ? P.F.kp_taken[i] : 0;
+    P.takenby[i] = (P.F.kp_taken && P.F.kp_taken[i]) ? -1 : 0x7fffffff;
   }
+  if (threadIdx.x == 0) { P.result[0] = 0; P.result[1] = 0; *P.cand_used = 0; }
 }
 
-// Phase 1c: write candidate indices in GetFeaturesInArea order + Hamming distances.
-__global__ void __launch_bounds__(128) proj_fill_kernel(ProjProblem* probs) {
+// Phase 1: one WARP per query point.  Window parameters (ORBmatcher.cc:51-70 / :1701-1733), then the window query
+// of Frame::GetFeaturesInArea (Frame.cc:657-723) with the per-candidate gate on mvuRight (ORBmatcher.cc:92-97 /
+// :1752-1758) spread over the lanes: the cells (ix, minY..maxY) of one grid column are one contiguous CSR range,
+// lanes 0..ncol-1 fetch the ranges, a warp scan concatenates them, and lane t of a chunk tests the t-th keypoint
+// of the concatenation.  A ballot keeps the candidates in the reference's order.  The list is placed with one
+// atomicAdd per point (the order of the lists in the buffer does not matter), Hamming distances are written with it.
+constexpr int PC_WARPS = 4, PC_Q_PER_WARP = 4;
+__global__ void __launch_bounds__(PC_WARPS * 32) proj_candidates_kernel(ProjProblem* probs) {
   ProjProblem& P = probs[blockIdx.y];
-  const int j = blockIdx.x * 128 + threadIdx.x;
-  if (j >= P.nq || !P.q_state[j] || P.result[1]) return;
   const DevFrame& F = P.F;
-  const float r = P.q_r[j], aux = P.q_aux[j];
-  int o = P.q_off[j];
-  const uint8_t* d = P.qdesc + (size_t)j * 32;
-  for_each_in_area(F, P.q_u[j], P.q_v[j], r, P.q_minl[j], P.q_maxl[j], [&](int idx) {
-    if (F.u_right) {
-      const float ur = F.u_right[idx];
-      if (ur > 0 && fabsf(__fsub_rn(aux, ur)) > r) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned full = 0xffffffffu, lt = (1u << lane) - 1u;
+  const int j0 = (blockIdx.x * PC_WARPS + warp) * PC_Q_PER_WARP;
+  for (int j = j0; j < min(j0 + PC_Q_PER_WARP, P.nq); j++) {
+    bool active = false;
+    float u = 0, v = 0, r = 0, aux = 0;
+    int minl = 0, maxl = 0;
+    if (P.kind == 0) {
+      // ORBmatcher.cc:51-70
+      active = P.in_view[j] && !(P.far_points && P.depth[j] > P.th_far) && !P.is_bad[j];
+      if (active) {
+        const int lvl = P.lvl[j];
+        float rr = ((double)P.vcos[j] > 0.998) ? 2.5f : 4.0f;
+        if (P.th != 1.0f) rr = __fmul_rn(rr, P.th);
+        r = __fmul_rn(rr, F.scale[lvl]);
+        u = P.px[j]; v = P.py[j]; aux = P.pxr[j];
+        minl = lvl - 1; maxl = lvl;
+      }
+    } else if (P.has_mp[j]) {
+      // ORBmatcher.cc:1701-1733; Tcw * x3Dw as Sophus/Eigen evaluate it
+      const float qx = P.T[0], qy = P.T[1], qz = P.T[2], qw = P.T[3];
+      const float vx = P.wpos[3 * j], vy = P.wpos[3 * j + 1], vz = P.wpos[3 * j + 2];
+      float ux = __fsub_rn(__fmul_rn(qy, vz), __fmul_rn(qz, vy));
+      float uy = __fsub_rn(__fmul_rn(qz, vx), __fmul_rn(qx, vz));
+      float uz = __fsub_rn(__fmul_rn(qx, vy), __fmul_rn(qy, vx));
+      ux = __fadd_rn(ux, ux); uy = __fadd_rn(uy, uy); uz = __fadd_rn(uz, uz);
+      const float c0 = __fsub_rn(__fmul_rn(qy, uz), __fmul_rn(qz, uy));
+      const float c1 = __fsub_rn(__fmul_rn(qz, ux), __fmul_rn(qx, uz));
+      const float c2 = __fsub_rn(__fmul_rn(qx, uy), __fmul_rn(qy, ux));
+      const float xc = __fadd_rn(__fadd_rn(__fadd_rn(vx, __fmul_rn(qw, ux)), c0), P.T[4]);
+      const float yc = __fadd_rn(__fadd_rn(__fadd_rn(vy, __fmul_rn(qw, uy)), c1), P.T[5]);
+      const float zc = __fadd_rn(__fadd_rn(__fadd_rn(vz, __fmul_rn(qw, uz)), c2), P.T[6]);
+      const float invzc = (float)(1.0 / (double)zc);
+      if (!(invzc < 0)) {
+        u = __fadd_rn(__fdiv_rn(__fmul_rn(F.fx, xc), zc), F.cx);
+        v = __fadd_rn(__fdiv_rn(__fmul_rn(F.fy, yc), zc), F.cy);
+        if (!(u < F.min_x || u > F.max_x) && !(v < F.min_y || v > F.max_y)) {
+          active = true;
+          const int o = P.octave[j];
+          r = __fmul_rn(P.th, F.scale[o]);
+          aux = __fsub_rn(u, __fmul_rn(F.bf, invzc));  // ur (:1754)
+          if (P.forward) { minl = o; maxl = -1; }
+          else if (P.backward) { minl = 0; maxl = o; }
+          else { minl = o - 1; maxl = o + 1; }
+        }
+      }
     }
-    P.cand_idx[o] = idx;
-    P.cand_dist[o] = (unsigned short)popc256(d, F.desc + (size_t)idx * 32);
-    o++;
-  });
+    // Frame::GetFeaturesInArea's cell rectangle (Frame.cc:664-686)
+    int cx0 = 0, cx1 = -1, cy0 = 0, cy1 = -1;
+    if (active) {
+      cx0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(u, F.min_x), r), F.gwi)));
+      cx1 = min(GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(u, F.min_x), r), F.gwi)));
+      cy0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(v, F.min_y), r), F.ghi)));
+      cy1 = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(v, F.min_y), r), F.ghi)));
+      if (cx0 >= GRID_COLS || cx1 < 0 || cy0 >= GRID_ROWS || cy1 < 0) cx1 = cx0 - 1;
+    }
+    const bool check_levels = (minl > 0) || (maxl >= 0);
+    int cnt = 0, base = 0;
+    // two sweeps over the window: count, then (after the list is placed) write; the first two chunks of the first
+    // column group keep their verdicts in registers, which covers almost every window
+    int keep0 = -1, keep1 = -1;
+    uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;
+    for (int sweep = 0; sweep < 2; sweep++) {
+      int written = 0;
+      for (int g0 = cx0; g0 <= cx1; g0 += 32) {
+        const int ix = g0 + lane;
+        int s = 0, len = 0;
+        if (ix <= cx1) {
+          s = F.cell_start[ix * GRID_ROWS + cy0];
+          len = F.cell_start[ix * GRID_ROWS + cy1 + 1] - s;
+        }
+        int incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(full, incl, o); if (lane >= o) incl += t; }
+        const int total = __shfl_sync(full, incl, 31);
+        for (int t0 = 0; t0 < total; t0 += 32) {
+          const bool reg_chunk = g0 == cx0 && t0 < 64;
+          int pick = -1;
+          if (sweep == 1 && reg_chunk) {
+            pick = t0 == 0 ? keep0 : keep1;
+          } else {
+            const int t = t0 + lane;
+            int col = 0;  // first column whose inclusive prefix exceeds t
+#pragma unroll
+            for (int step = 16; step; step >>= 1) {
+              const int pv = __shfl_sync(full, incl, col + step - 1);
+              if (pv <= t) col += step;
+            }
+            const int cs = __shfl_sync(full, s, col), cex = __shfl_sync(full, incl - len, col);
+            if (t < total) {
+              const int idx = F.cell_items[cs + (t - cex)];
+              const orb_keypoint* kp = F.keys + idx;
+              bool ok = true;
+              if (check_levels) {
+                const int oc = kp->octave;
+                ok = oc >= minl && !(maxl >= 0 && oc > maxl);
+              }
+              if (ok) ok = fabsf(__fsub_rn(kp->x, u)) < r && fabsf(__fsub_rn(kp->y, v)) < r;
+              if (ok && F.u_right) {
+                const float ur = F.u_right[idx];
+                if (ur > 0 && fabsf(__fsub_rn(aux, ur)) > r) ok = false;
+              }
+              if (ok) pick = idx;
+            }
+            if (sweep == 0 && reg_chunk) { if (t0 == 0) keep0 = pick; else keep1 = pick; }
+          }
+          const unsigned m = __ballot_sync(full, pick >= 0);
+          if (sweep == 0) {
+            cnt += __popc(m);
+          } else {
+            if (pick >= 0) {
+              const int o = base + written + __popc(m & lt);
+              const uint4* pd = reinterpret_cast<const uint4*>(F.desc + (size_t)pick * 32);
+              const uint4 d0 = pd[0], d1 = pd[1];
+              P.cand_idx[o] = pick;
+              P.cand_dist[o] = (unsigned short)(__popc(qa.x ^ d0.x) + __popc(qa.y ^ d0.y) + __popc(qa.z ^ d0.z) +
+                                                __popc(qa.w ^ d0.w) + __popc(qb.x ^ d1.x) + __popc(qb.y ^ d1.y) +
+                                                __popc(qb.z ^ d1.z) + __popc(qb.w ^ d1.w));
+            }
+            written += __popc(m);
+          }
+        }
+      }
+      if (sweep == 0) {
+        if (cnt > 0) {
+          if (lane == 0) base = atomicAdd(P.cand_used, cnt);
+          base = __shfl_sync(full, base, 0);
+          if (base + cnt > P.cand_cap) {  // the host grows the buffer and runs the batch again
+            if (lane == 0) P.result[1] = 1;
+            cnt = 0;
+          }
+        }
+        if (lane == 0) { P.q_off[j] = base; P.q_cnt[j] = cnt; P.q_state[j] = cnt > 0 ? 1 : 0; }
+        if (cnt == 0) break;
+        const uint4* pq = reinterpret_cast<const uint4*>(P.qdesc + (size_t)j * 32);
+        qa = pq[0]; qb = pq[1];
+      }
+    }
+  }
 }
 
 // ORBmatcher::ComputeThreeMaxima (ORBmatcher.cc:2012-2053) on bin sizes.
@@ -348,7 +389,7 @@ __device__ __forceinline__ int rot_bin(float a1, float a2) {
 }
 
 // Phase 2+3: resolution rounds, one CTA per problem.
-__global__ void __launch_bounds__(1024) proj_resolve_kernel(ProjProblem* probs, int smem_nk) {
+__global__ void __launch_bounds__(1024, 1) proj_resolve_kernel(ProjProblem* probs, int smem_nk) {
   extern __shared__ int rs_dyn[];
   __shared__ int s_unresolved, s_nmatch;
   __shared__ int s_hist[HISTO_LENGTH];
@@ -357,14 +398,14 @@ __global__ void __launch_bounds__(1024) proj_resolve_kernel(ProjProblem* probs, 
   if (P.result[1]) return;  // candidate buffer overflow: host re-runs with a larger one
   const DevFrame& F = P.F;
   const int nq = P.nq, nk = F.n;
-  // per-keypoint state of the rounds (owner index, taken flag, octave) in shared memory when it
-  // fits: every round is a chain of dependent look-ups into these arrays
+  // per-keypoint state of the rounds (lowest claiming point, taker, octave) in shared memory when it fits: every
+  // round is a chain of dependent look-ups into these arrays
   const bool in_smem = nk <= smem_nk;
   int* minidx = in_smem ? rs_dyn : P.minidx;
-  uint8_t* taken = in_smem ? reinterpret_cast<uint8_t*>(rs_dyn + smem_nk) : P.taken;
-  uint8_t* oct8 = taken + smem_nk;
+  int* takenby = in_smem ? rs_dyn + smem_nk : P.takenby;
+  uint8_t* oct8 = reinterpret_cast<uint8_t*>(rs_dyn + 2 * smem_nk);
   if (in_smem)
-    for (int i = threadIdx.x; i < nk; i += 1024) { taken[i] = P.taken[i]; oct8[i] = (uint8_t)F.keys[i].octave; }
+    for (int i = threadIdx.x; i < nk; i += 1024) { takenby[i] = P.takenby[i]; oct8[i] = (uint8_t)F.keys[i].octave; }
   if (threadIdx.x == 0) s_nmatch = 0;
   for (int b = threadIdx.x; b < HISTO_LENGTH; b += 1024) s_hist[b] = 0;
   for (int j = threadIdx.x; j < nq; j += 1024) P.acc_kp[j] = -1;
@@ -372,30 +413,35 @@ __global__ void __launch_bounds__(1024) proj_resolve_kernel(ProjProblem* probs, 
   while (true) {
     if (threadIdx.x == 0) s_unresolved = 0;
     for (int i = threadIdx.x; i < nk; i += 1024) minidx[i] = 0x7fffffff;
+    // takes of the previous round (one taker per keypoint: see the claim rule)
+    for (int j = threadIdx.x; j < nq; j += 1024)
+      if (P.q_state[j] == 2) { takenby[P.acc_kp[j]] = j; P.q_state[j] = 0; }
     __syncthreads();
+    // claims: only a candidate within TH_HIGH can be taken by j; free for j = not taken by a lower index
     for (int j = threadIdx.x; j < nq; j += 1024) {
-      if (!P.q_state[j]) continue;
-      for (int e = P.q_off[j]; e < P.q_off[j + 1]; e++) {
+      if (P.q_state[j] != 1) continue;
+      const int e0 = P.q_off[j], e1 = e0 + P.q_cnt[j];
+      for (int e = e0; e < e1; e++) {
+        if (P.cand_dist[e] > TH_HIGH) continue;
         const int c = P.cand_idx[e];
-        if (!taken[c]) atomicMin(&minidx[c], j);
+        if (takenby[c] > j) atomicMin(&minidx[c], j);
       }
     }
     __syncthreads();
     for (int j = threadIdx.x; j < nq; j += 1024) {
-      if (!P.q_state[j]) continue;
+      if (P.q_state[j] != 1) continue;
+      const int e0 = P.q_off[j], e1 = e0 + P.q_cnt[j];
       bool mine = true;
-      for (int e = P.q_off[j]; e < P.q_off[j + 1] && mine; e++) {
+      for (int e = e0; e < e1 && mine; e++) {
         const int c = P.cand_idx[e];
-        if (minidx[c] != j && !((volatile uint8_t*)taken)[c]) mine = false;
+        if (takenby[c] > j && minidx[c] < j) mine = false;  // a lower unresolved point may still take it
       }
       if (!mine) { atomicAdd(&s_unresolved, 1); continue; }
-      // replay the reference scan on the current flags
+      // replay the reference scan: a keypoint is skipped iff it was taken on entry or by a lower-index point
       int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
-      for (int e = P.q_off[j]; e < P.q_off[j + 1]; e++) {
+      for (int e = e0; e < e1; e++) {
         const int c = P.cand_idx[e];
-        // free candidates of a finalising point all carry minidx == j; anything else
-        // was taken before this round or by a lower-index point in this round
-        if (minidx[c] != j) continue;
+        if (takenby[c] < j) continue;
         const int dist = P.cand_dist[e];
         if (dist < bestDist) {
           bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel;
@@ -407,14 +453,13 @@ __global__ void __launch_bounds__(1024) proj_resolve_kernel(ProjProblem* probs, 
       bool accept = bestDist <= TH_HIGH;
       if (accept && P.kind == 0) {
         // ratio only when best and second best share the level (:123-128)
-        const bool le = (float)bestDist <= __fmul_rn(P.ratio, (float)bestDist2);
-        accept = (bestLevel != bestLevel2) || le;
         if (bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(P.ratio, (float)bestDist2)) accept = false;
       }
+      int state = 0;
       if (accept) {
         P.assign[bestIdx] = j;
-        taken[bestIdx] = P.has_obs[j] ? 1 : 0;
         P.acc_kp[j] = bestIdx;
+        if (P.has_obs[j]) state = 2;  // the keypoint is closed to later points (ORBmatcher.cc:88-90 / :1748-1750)
         atomicAdd(&s_nmatch, 1);
         if (P.kind == 1 && P.check_ori) {
           const int bin = rot_bin(P.angle[j], F.keys[bestIdx].angle);
@@ -422,7 +467,7 @@ __global__ void __launch_bounds__(1024) proj_resolve_kernel(ProjProblem* probs, 
           atomicAdd(&s_hist[bin], 1);
         }
       }
-      P.q_state[j] = 0;
+      P.q_state[j] = (uint8_t)state;
     }
     __syncthreads();
     if (s_unresolved == 0) break;
@@ -748,7 +793,7 @@ static int run_projection(Matcher& M, int count, int kind, const orb_frame_view*
   return launch_projection(M, P, st.off, all_dev, assign_out, results, true);
 }
 
-// Scratch / output carving, the five kernels and the result read-back of a staged batch.  A candidate-buffer
+// Scratch / output carving, the three kernels and the result read-back of a staged batch.  A candidate-buffer
 // overflow grows the budget and runs the batch again from the staged inputs.
 static int launch_projection(Matcher& M, std::vector<ProjProblem>& P, size_t in_bytes, bool on_device,
                              int32_t* const* assign_out, int32_t* results, bool allow_async) {
@@ -758,7 +803,7 @@ static int launch_projection(Matcher& M, std::vector<ProjProblem>& P, size_t in_
     size_t sbytes = 0, obytes = 0;
     for (int k = 0; k < count; k++) {
       const size_t nq = P[k].nq, nk = P[k].F.n, cc = std::max<size_t>(nq * M.cand_per_query, 1024);
-      sbytes += 256 * 24 + (GRID_CELLS + 1 + nk) * 4 + nq * (4 * 4 + 4 * 4 + 1 + 8) + 4 + cc * 6 + nk * 5;
+      sbytes += 256 * 16 + (GRID_CELLS + 1 + nk) * 4 + nq * (2 * 4 + 1 + 8) + 4 + cc * 6 + nk * 8;
       obytes += 256 * 2 + nk * 4 + 8;
     }
     sbytes += sizeof(ProjProblem) * count + 4096;
@@ -775,15 +820,13 @@ static int launch_projection(Matcher& M, std::vector<ProjProblem>& P, size_t in_
       max_nq = std::max(max_nq, p.nq);
       p.F.cell_start = carve_dev<int>(M.scratch, GRID_CELLS + 1);
       p.F.cell_items = carve_dev<int>(M.scratch, nk);
-      p.q_u = carve_dev<float>(M.scratch, nq); p.q_v = carve_dev<float>(M.scratch, nq);
-      p.q_r = carve_dev<float>(M.scratch, nq); p.q_aux = carve_dev<float>(M.scratch, nq);
-      p.q_minl = carve_dev<int>(M.scratch, nq); p.q_maxl = carve_dev<int>(M.scratch, nq);
-      p.q_cnt = carve_dev<int>(M.scratch, nq); p.q_off = carve_dev<int>(M.scratch, nq + 1);
+      p.q_cnt = carve_dev<int>(M.scratch, nq); p.q_off = carve_dev<int>(M.scratch, nq);
+      p.cand_used = carve_dev<int>(M.scratch, 1);
       p.q_state = carve_dev<uint8_t>(M.scratch, nq);
       p.acc_kp = carve_dev<int>(M.scratch, nq); p.acc_bin = carve_dev<int>(M.scratch, nq);
       p.cand_idx = carve_dev<int>(M.scratch, cc); p.cand_dist = carve_dev<unsigned short>(M.scratch, cc);
       p.cand_cap = (int)cc;
-      p.minidx = carve_dev<int>(M.scratch, nk); p.taken = carve_dev<uint8_t>(M.scratch, nk);
+      p.minidx = carve_dev<int>(M.scratch, nk); p.takenby = carve_dev<int>(M.scratch, nk);
       if (on_device) {
         if (assign_out) p.assign = assign_out[k];  // (a retry keeps the pointer staged by the first launch)
         p.result = carve_dev<int>(M.out_arena, 2);
@@ -800,20 +843,18 @@ static int launch_projection(Matcher& M, std::vector<ProjProblem>& P, size_t in_
       CUDA_TRYM(cudaMemcpyAsync(M.in_arena.d, M.h_in.h, in_bytes, cudaMemcpyHostToDevice, s));
     CUDA_TRYM(cudaMemcpyAsync(d_probs, P.data(), sizeof(ProjProblem) * count, cudaMemcpyHostToDevice, s));
     grid_build_kernel<<<count, 256, 0, s>>>(d_probs);
-    const dim3 qgrid((max_nq + 127) / 128, count);
-    if (max_nq > 0) proj_setup_kernel<<<qgrid, 128, 0, s>>>(d_probs);
-    proj_scan_kernel<<<count, 1024, 0, s>>>(d_probs);
-    if (max_nq > 0) proj_fill_kernel<<<qgrid, 128, 0, s>>>(d_probs);
+    const int q_per_cta = PC_WARPS * PC_Q_PER_WARP;
+    if (max_nq > 0) proj_candidates_kernel<<<dim3((max_nq + q_per_cta - 1) / q_per_cta, count), PC_WARPS * 32, 0, s>>>(d_probs);
     {
       int max_nk = 0;
       for (int k = 0; k < count; k++) max_nk = std::max(max_nk, P[k].F.n);
       int smem_nk = (max_nk + 3) & ~3;
-      size_t smem_bytes = (size_t)smem_nk * 6;
+      size_t smem_bytes = (size_t)smem_nk * 9;
       if (smem_bytes > 160 * 1024) { smem_nk = 0; smem_bytes = 0; }
       CUDA_TRYM(raise_dynamic_smem((const void*)proj_resolve_kernel, smem_bytes, M.device));
       proj_resolve_kernel<<<count, 1024, smem_bytes, s>>>(d_probs, smem_nk);
     }
-    M.launches += 5;
+    M.launches += 3;
     const size_t out_bytes = M.out_arena.used;
     CUDA_TRYM(cudaMemcpyAsync(M.h_out.h, M.out_arena.d, out_bytes, cudaMemcpyDeviceToHost, s));
     CUDA_TRYM(cudaEventRecord(M.ev1, s));
