@@ -709,6 +709,11 @@ __global__ void __launch_bounds__(SKY_THREADS) ldlt_sky_kernel(double* __restric
 constexpr int WIN = 128, WIN_P = WIN + 1, WIN_ROWS = WIN - 8, WPB = 8, WIN_THREADS = 512;
 constexpr int WIN_LP = 132;  // row pitch of the m-major L / L*D panels: the four k-rows of a DMMA fragment fall into different banks
 
+// PROF (ORB_B200_LDLT_PROF): cycle counters of the phases as seen by warp 0, printed by lba_solve
+__device__ unsigned long long g_win_prof[16];
+static int win_prof_solves = 0;
+
+template <bool PROF>
 __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restrict__ M, int n, const int* __restrict__ reach,
                                                              const int* __restrict__ first_g, double* fail,
                                                              double* __restrict__ x) {
@@ -719,16 +724,23 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
   double* LDt = Lt + WPB * WIN_LP;           // [8][WIN_LP] L*D of the panel rows
   int* first = reinterpret_cast<int*>(LDt + WPB * WIN_LP);  // [n] envelope starts (read at every step: keep them on chip)
   int* rlast = first + n;                    // [ceil(n/8)] last window row of every panel
-  __shared__ double Lb[WPB][WPB];            // pivot block: strict lower = L
+  __shared__ double Lb[WPB][WPB];            // pivot block: strict lower = L, diagonal = D
   __shared__ double Dib[WPB];                // 1 / D
-  __shared__ double xb[WPB];
+  __shared__ unsigned short tile_ij[(WIN / 8) * (WIN / 8 + 1) / 2];  // lower-triangle tile number -> (ti << 8) | tj
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int npan = (n + WPB - 1) / WPB;
+  unsigned long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long t0 = 0;
+  auto tick = [&](int slot) {
+    if (PROF) { const long long t = clock64(); pc[slot] += (unsigned long long)(t - t0); t0 = t; }
+  };
   for (int i = tid; i < n; i += WIN_THREADS) first[i] = first_g[i];
   for (int p = tid; p < npan; p += WIN_THREADS) {
     const int k0 = p * WPB, nb = min(WPB, n - k0);
     rlast[p] = min(max(reach[k0 + nb - 1], k0 + nb - 1), n - 1);
   }
+  for (int ti = tid; ti < WIN / 8; ti += WIN_THREADS)
+    for (int tj = 0; tj <= ti; tj++) tile_ij[ti * (ti + 1) / 2 + tj] = (unsigned short)((ti << 8) | tj);
   __syncthreads();
   // rows [lo, hi] enter the window: columns [c0, i], zero left of the envelope (the ring slot is stale).
   // Called by warps w0.. of the CTA; all loads of a call are independent.
@@ -741,16 +753,17 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
       if (lane == 0) zr[i % WIN] = M[(size_t)n * n + i];
     }
   };
-  // pivot block of panel p, one thread, registers only: factors rows/cols [k0, k0+nb) of the ring in place,
-  // leaves L (strict lower) in Lb, 1/D in Dib, writes L and D to M
+  // pivot block of panel p, one thread, registers only: factors rows/cols [k0, k0+nb) of the ring, leaves L (strict
+  // lower) and D in Lb, 1/D in Dib; the warp writes them to M afterwards (pivot_store)
   auto pivot = [&](int p) {
     const int k0 = p * WPB, nb = min(WPB, n - k0);
     double a[WPB][WPB];
 #pragma unroll
-    for (int r = 0; r < WPB; r++)
+    for (int r = 0; r < WPB; r++) {
+      const double* Ar = A + ((k0 + r) % WIN) * WIN_P;
 #pragma unroll
-      for (int c = 0; c < WPB; c++)
-        a[r][c] = (r < nb && c <= r) ? A[((k0 + r) % WIN) * WIN_P + (k0 + c) % WIN] : (r == c ? 1.0 : 0.0);
+      for (int c = 0; c < WPB; c++) a[r][c] = (r < nb && c <= r) ? Ar[(k0 + c) % WIN] : (r == c ? 1.0 : 0.0);
+    }
 #pragma unroll
     for (int k = 0; k < WPB; k++) {
       const double d = a[k][k];
@@ -772,43 +785,69 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
 #pragma unroll
     for (int r = 0; r < WPB; r++)
 #pragma unroll
-      for (int c = 0; c < WPB; c++) {
-        Lb[r][c] = c < r ? a[r][c] : 0.0;
-        if (r < nb && c <= r) M[(size_t)(k0 + r) * n + k0 + c] = a[r][c];  // L below, D on the diagonal
-      }
+      for (int c = 0; c < WPB; c++) Lb[r][c] = c <= r ? a[r][c] : 0.0;
   };
-  // one 8x8 tile of the rank-nb update of panel (r0, nr): C -= L_i (8x8) * (L*D)_j^T, two fp64 DMMA m8n8k4;
-  // fragment layout A[g][t], B[t][g], C[g][2t], C[g][2t+1] with g = lane / 4, t = lane % 4
-  auto update_tile = [&](int tile, int r0, int nr) {
-    const int g = lane >> 2, t = lane & 3;
-    int ti = (int)((sqrtf(8.f * (float)tile + 1.f) - 1.f) * 0.5f);
-    while ((ti + 1) * (ti + 2) / 2 <= tile) ti++;
-    while (ti * (ti + 1) / 2 > tile) ti--;
-    const int tj = tile - ti * (ti + 1) / 2;
-    const int wi = 8 * ti + g, wj = 8 * tj + 2 * t;
-    const double a0 = -Lt[t * WIN_LP + wi], a1 = -Lt[(t + 4) * WIN_LP + wi];
-    const double b0 = LDt[t * WIN_LP + 8 * tj + g], b1 = LDt[(t + 4) * WIN_LP + 8 * tj + g];
+  auto pivot_store = [&](int p) {  // warp 0, after pivot(p) and a __syncwarp
+    const int k0 = p * WPB, nb = min(WPB, n - k0);
+    for (int e = lane; e < WPB * WPB; e += 32) {
+      const int r = e >> 3, c = e & 7;
+      if (r < nb && c <= r) M[(size_t)(k0 + r) * n + k0 + c] = Lb[r][c];  // L below, D on the diagonal
+    }
+  };
+  // two 8x8 tiles of the rank-nb update of panel (r0, nr): C -= L_i (8x8) * (L*D)_j^T, two fp64 DMMA m8n8k4 each;
+  // fragment layout A[g][t], B[t][g], C[g][2t], C[g][2t+1] with g = lane / 4, t = lane % 4.  Operands of both tiles
+  // are fetched before the first DMMA so the two chains overlap.
+  const int fg = lane >> 2, ft = lane & 3;
+  struct TileRef { double *p0, *p1; bool ok0, ok1; double a0, a1, b0, b1; };
+  auto tile_ref = [&](int tile, int r0, int nr, bool live) {
+    TileRef T;
+    const int tt = tile_ij[live ? tile : 0];
+    const int ti = tt >> 8, tj = tt & 255;
+    const int wi = 8 * ti + fg, wj = 8 * tj + 2 * ft;
+    T.a0 = -Lt[ft * WIN_LP + wi]; T.a1 = -Lt[(ft + 4) * WIN_LP + wi];
+    T.b0 = LDt[ft * WIN_LP + 8 * tj + fg]; T.b1 = LDt[(ft + 4) * WIN_LP + 8 * tj + fg];
     double* row = (wi == nr) ? zr : A + ((r0 + min(wi, nr)) % WIN) * WIN_P;  // the rhs row has no column of its own
-    const bool ok0 = wi <= nr && wj < nr && wj <= wi, ok1 = wi <= nr && wj + 1 < nr && wj + 1 <= wi;
-    double* p0 = row + (r0 + wj) % WIN;
-    double* p1 = row + (r0 + wj + 1) % WIN;
-    double c0 = ok0 ? *p0 : 0.0, c1 = ok1 ? *p1 : 0.0;
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(c0), "+d"(c1) : "d"(a0), "d"(b0));
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(c0), "+d"(c1) : "d"(a1), "d"(b1));
-    if (ok0) *p0 = c0;
-    if (ok1) *p1 = c1;
+    T.ok0 = live && wi <= nr && wj < nr && wj <= wi;
+    T.ok1 = live && wi <= nr && wj + 1 < nr && wj + 1 <= wi;
+    T.p0 = row + (r0 + wj) % WIN;
+    T.p1 = row + (r0 + wj + 1) % WIN;
+    return T;
+  };
+  auto update_pair = [&](int tileA, int tileB, int ntile, int r0, int nr) {
+    const TileRef X = tile_ref(tileA, r0, nr, tileA < ntile), Y = tile_ref(tileB, r0, nr, tileB < ntile);
+    double x0 = X.ok0 ? *X.p0 : 0.0, x1 = X.ok1 ? *X.p1 : 0.0;
+    double y0 = Y.ok0 ? *Y.p0 : 0.0, y1 = Y.ok1 ? *Y.p1 : 0.0;
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+        : "+d"(x0), "+d"(x1) : "d"(X.a0), "d"(X.b0));
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+        : "+d"(y0), "+d"(y1) : "d"(Y.a0), "d"(Y.b0));
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+        : "+d"(x0), "+d"(x1) : "d"(X.a1), "d"(X.b1));
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+        : "+d"(y0), "+d"(y1) : "d"(Y.a1), "d"(Y.b1));
+    if (X.ok0) *X.p0 = x0;
+    if (X.ok1) *X.p1 = x1;
+    if (Y.ok0) *Y.p0 = y0;
+    if (Y.ok1) *Y.p1 = y1;
   };
   load_rows(0, rlast[0], 0, 0, WIN_THREADS / 32);
   __syncthreads();
   if (tid == 0) pivot(0);
+  __syncwarp();
+  if (warp == 0) pivot_store(0);
   __syncthreads();
+  if (PROF) t0 = clock64();
+  constexpr int FWD_WARPS = WIN / 32;  // warps that can hold a panel row in phase (A)
   for (int p = 0; p < npan; p++) {
     const int k0 = p * WPB, nb = min(WPB, n - k0);
     const int R = rlast[p];  // last row of the window; rows [k0, R] are resident, the pivot block is factored
-    // ---- (A) panel rows [k0+nb, R] and the rhs row: forward substitution, one thread per row
+    const bool more = p + 1 < npan;
+    // rows of the next pivot block that are not resident yet (narrow or ending envelope) are loaded by warp 0 in (B)
     const int r0 = k0 + nb, nr = R - r0 + 1;  // nr rows under the pivot block; slot nr = rhs
+    const int pre = more ? min(r0 + WPB - 1, n - 1) : R;
+    // ---- (A) panel rows [k0+nb, R] and the rhs row: forward substitution, one thread per row.  The other warps
+    //      bring in the rows the NEXT panel adds to the window (their ring slots are free: the window of panel p+1
+    //      starts at r0), so the global-memory latency is off the chain.
     if (tid <= nr) {
       const bool rhs = tid == nr;
       const int i = r0 + tid;
@@ -831,89 +870,95 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
       for (int m = 0; m < WPB; m++)
         if (m < nb) dst[m] = l[m];
     }
+    if (warp >= FWD_WARPS && more) load_rows(max(R, pre) + 1, rlast[p + 1], r0, FWD_WARPS, WIN_THREADS / 32 - FWD_WARPS);
+    tick(0);
     __syncthreads();
+    tick(1);
     // ---- (B) rank-nb update of the window on the tensor pipe, with look-ahead: warp 0 updates the tile that
     //      holds the NEXT pivot block first and then factors it (one thread) while the other warps update the
-    //      rest of the window and bring in the rows the next panel adds to it
+    //      rest of the window
     {
       const int T8 = (nr + 1 + 7) >> 3;
       const int ntile = T8 * (T8 + 1) / 2;
-      const bool more = p + 1 < npan;
-      // rows of the next pivot block that are not resident yet (narrow or ending envelope) are loaded by warp 0
-      const int pre = more ? min(r0 + WPB - 1, n - 1) : R;
+      constexpr int UW = WIN_THREADS / 32 - 1;
       if (warp == 0) {
         if (pre > R) load_rows(R + 1, pre, r0, 0, 1);
-        update_tile(0, r0, nr);
+        update_pair(0, ntile, ntile, r0, nr);
         __syncwarp();
         if (tid == 0 && more) pivot(p + 1);
+        __syncwarp();
+        if (more) pivot_store(p + 1);
+        tick(2);
       } else {
-        if (more) load_rows(max(R, pre) + 1, rlast[p + 1], r0, 1, WIN_THREADS / 32 - 1);
-        for (int tile = warp; tile < ntile; tile += WIN_THREADS / 32 - 1) update_tile(tile, r0, nr);
+        for (int tile = warp; tile < ntile; tile += 2 * UW) update_pair(tile, tile + UW, ntile, r0, nr);
+        tick(2);
       }
     }
     __syncthreads();
+    tick(3);
   }
-  // ---- L^T x = z (z = row n of M, already scaled by 1/D).  8 unknowns per step; a thread owns a column of
-  //      the step's window and has the next step's 8 entries of L in flight while this step is solved.
-  double* acc = A;  // n <= WIN * WIN_P (host-checked)
+  // ---- L^T x = z (z = row n of M, already scaled by 1/D).  Four warps, one named barrier per 8 unknowns: a thread
+  //      owns one column of the step's window and has the next step's 8 entries of L in flight; the 8x8 in-block
+  //      solve is done by every thread redundantly from shared memory (the strict-lower pivot blocks are staged there
+  //      in one parallel pass: the ring is dead by now), so nothing is exchanged but acc.
+  double* acc = A;            // [n]
+  double* pblk = A + n;       // [npan][28]: L[k0+c][k0+r], r < c, at c(c-1)/2 + r   (n + 28 npan <= WIN * WIN_P: host-checked)
   for (int i = tid; i < n; i += WIN_THREADS) acc[i] = M[(size_t)n * n + i];
-  const int nblk = (n + WPB - 1) / WPB;
-  auto jmin_of = [&](int b) {
-    const int k0 = b * WPB, nb = min(WPB, n - k0);
-    int jm = k0;
-    for (int r = 0; r < nb; r++) jm = min(jm, first[k0 + r]);
-    return jm;
-  };
-  double nxt[WPB];
-  int jm_next = nblk > 0 ? jmin_of(nblk - 1) : 0;
-  {
-    const int k0 = (nblk - 1) * WPB, nb = min(WPB, n - k0), j = jm_next + tid;
-#pragma unroll
-    for (int r = 0; r < WPB; r++) nxt[r] = (r < nb && j < k0 + r) ? M[(size_t)(k0 + r) * n + j] : 0.0;
+  for (int i = tid; i < npan * 28; i += WIN_THREADS) {
+    const int bq = i / 28, e = i - bq * 28;
+    int c = 1;
+    while (c * (c + 1) / 2 <= e) c++;
+    const int r = e - c * (c - 1) / 2, k0 = bq * WPB;
+    pblk[i] = (k0 + c < n) ? M[(size_t)(k0 + c) * n + k0 + r] : 0.0;
   }
   __syncthreads();
-  for (int b = nblk - 1; b >= 0; b--) {
-    const int k0 = b * WPB, nb = min(WPB, n - k0), jm = jm_next;
-    double cur[WPB];
+  constexpr int BS_THREADS = WIN;  // one thread per window column (WIN_ROWS < WIN)
+  if (tid >= BS_THREADS) return;
+  double nxt[WPB];
+  int jm_next = 0;
+  auto fetch = [&](int bq) {
+    const int k0 = bq * WPB, nb = min(WPB, n - k0);
+    int jm = k0;
+#pragma unroll
+    for (int r = 0; r < WPB; r++)
+      if (r < nb) jm = min(jm, first[k0 + r]);
+    jm_next = jm;
+    const int j = jm + tid;
+#pragma unroll
+    for (int r = 0; r < WPB; r++) nxt[r] = (r < nb && j < k0) ? M[(size_t)(k0 + r) * n + j] : 0.0;
+  };
+  fetch(npan - 1);
+  for (int bq = npan - 1; bq >= 0; bq--) {
+    const int k0 = bq * WPB, nb = min(WPB, n - k0), jm = jm_next;
+    double cur[WPB], v[WPB];
 #pragma unroll
     for (int r = 0; r < WPB; r++) cur[r] = nxt[r];
-    if (b > 0) {  // next step's loads: independent of everything below
-      jm_next = jmin_of(b - 1);
-      const int k1 = k0 - WPB, j = jm_next + tid;
+    if (bq > 0) fetch(bq - 1);  // independent of everything below
+    const double* pb = pblk + bq * 28;
 #pragma unroll
-      for (int r = 0; r < WPB; r++) nxt[r] = (j < k1 + r) ? M[(size_t)(k1 + r) * n + j] : 0.0;
+    for (int r = 0; r < WPB; r++) v[r] = r < nb ? acc[k0 + r] : 0.0;
+#pragma unroll
+    for (int c = WPB - 1; c >= 1; c--)
+#pragma unroll
+      for (int r = 0; r < c; r++) v[r] -= pb[c * (c - 1) / 2 + r] * v[c];
+    if (tid < nb) {
+      double xv = v[0];
+#pragma unroll
+      for (int r = 1; r < WPB; r++) xv = tid == r ? v[r] : xv;
+      x[k0 + tid] = xv;
     }
-    // in-block solve: the thread that owns column k0 + c holds L[k0+r][k0+c] in cur[r]; gather them first
-    if (tid >= k0 - jm && tid < k0 - jm + nb) {
-      const int c = tid - (k0 - jm);
+    if (jm + tid < k0) {
+      double sdot = 0;
 #pragma unroll
-      for (int r = 0; r < WPB; r++) Lb[r][c] = r > c ? cur[r] : 0.0;
+      for (int r = 0; r < WPB; r++) sdot += cur[r] * v[r];
+      acc[jm + tid] -= sdot;
     }
-    __syncthreads();
-    if (tid == 0) {
-      double v[WPB];
-#pragma unroll
-      for (int r = 0; r < WPB; r++) v[r] = r < nb ? acc[k0 + r] : 0.0;
-#pragma unroll
-      for (int c = WPB - 1; c >= 0; c--)
-#pragma unroll
-        for (int r = 0; r < c; r++) v[r] -= Lb[c][r] * v[c];
-#pragma unroll
-      for (int r = 0; r < WPB; r++)
-        if (r < nb) { xb[r] = v[r]; x[k0 + r] = v[r]; }
-    }
-    __syncthreads();
-    {
-      const int j = jm + tid;
-      if (j < k0) {
-        double sdot = 0;
-#pragma unroll
-        for (int r = 0; r < WPB; r++)
-          if (r < nb) sdot += cur[r] * xb[r];
-        acc[j] -= sdot;
-      }
-    }
-    __syncthreads();
+    asm volatile("bar.sync 1, %0;" ::"n"(BS_THREADS) : "memory");
+  }
+  if (PROF) {
+    tick(4);
+    if (tid == 0 || tid == 32)
+      for (int k = 0; k < 5; k++) atomicAdd(&g_win_prof[(tid ? 8 : 0) + k], pc[k]);
   }
 }
 
@@ -1426,7 +1471,8 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
     for (int r = 0; r < nb; r++) jmin = std::min(jmin, env_first[k0 + r]);
     win_rows_max = std::max(win_rows_max, std::max(R - k0 + 1, k0 - jmin + nb));
   }
-  const bool win_ok = win_rows_max <= WIN_ROWS && n <= 8192;  // envelope tables (4.5 bytes per unknown) share the shared memory
+  // envelope tables (4.5 bytes per unknown) share the shared memory; the back-substitution keeps n + 3.5 n doubles in the ring
+  const bool win_ok = win_rows_max <= WIN_ROWS && n <= 3600;
   static const char* ldlt_env = getenv("ORB_B200_LDLT");  // "dense" | "sky" | "win" | unset = automatic
   bool use_sky = sky_rows_max <= SKY_WMAX - 4 && n <= 32 * SKY_WMAX && sky_flops <= 6.0e7;
   if (ldlt_env && !strcmp(ldlt_env, "dense")) use_sky = false;
@@ -1596,8 +1642,15 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
       CUDA_TRYL(cudaMemsetAsync(D.scalars + 3, 0, sizeof(double), st));
       if (use_win) {
         const size_t smem = sizeof(double) * (WIN * WIN_P + WIN + 2 * WPB * WIN_LP) + sizeof(int) * ((size_t)n + (n + WPB - 1) / WPB + 4);
-        CUDA_TRYL(raise_dynamic_smem((const void*)ldlt_win_kernel, smem, S.device));
-        ldlt_win_kernel<<<1, WIN_THREADS, smem, st>>>(D.S, n, d_env_reach, d_env_first, D.scalars + 3, D.x);
+        static const bool win_prof = getenv("ORB_B200_LDLT_PROF") != nullptr;
+        if (win_prof) {
+          CUDA_TRYL(raise_dynamic_smem((const void*)ldlt_win_kernel<true>, smem, S.device));
+          ldlt_win_kernel<true><<<1, WIN_THREADS, smem, st>>>(D.S, n, d_env_reach, d_env_first, D.scalars + 3, D.x);
+          win_prof_solves++;
+        } else {
+          CUDA_TRYL(raise_dynamic_smem((const void*)ldlt_win_kernel<false>, smem, S.device));
+          ldlt_win_kernel<false><<<1, WIN_THREADS, smem, st>>>(D.S, n, d_env_reach, d_env_first, D.scalars + 3, D.x);
+        }
         S.launches += 1;
       } else if (use_sky) {
         const size_t smem = sizeof(double) * 2 * 32 * SKY_WMAX;
@@ -1677,6 +1730,18 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
   for (int s = 0; s < E; s++) {
     if (chi2_out) chi2_out[perm[s]] = chi_sorted[s];
     if (depth_pos_out) depth_pos_out[perm[s]] = dep_sorted[s];
+  }
+  if (win_prof_solves > 0) {  // ORB_B200_LDLT_PROF: cycles per phase of ldlt_win_kernel<true>, summed over warp 0 and warp 1
+    unsigned long long pc[16] = {0}, zero[16] = {0};
+    cudaMemcpyFromSymbol(pc, g_win_prof, sizeof(pc));
+    cudaMemcpyToSymbol(g_win_prof, zero, sizeof(zero));
+    const double d = (double)win_prof_solves;
+    fprintf(stderr, "[orbb200 lba] ldlt_win cycles per solve (warp 0): fwd-subst+loads %.0f | barrier %.0f | update+pivot %.0f | "
+            "barrier %.0f | back-substitution %.0f  (n = %d, %d solves)\n",
+            pc[0] / d, pc[1] / d, pc[2] / d, pc[3] / d, pc[4] / d, n, win_prof_solves);
+    fprintf(stderr, "[orbb200 lba] ... (warp 1): fwd-subst %.0f | barrier %.0f | update tiles %.0f | barrier %.0f | "
+            "back-substitution %.0f\n", pc[8] / d, pc[9] / d, pc[10] / d, pc[11] / d, pc[12] / d);
+    win_prof_solves = 0;
   }
   if (stats) {
     memset(stats, 0, sizeof(*stats));

@@ -21,6 +21,7 @@
 //      clearing pass, preserving the 1/30 bin quirk.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -93,7 +94,7 @@ struct ProjProblem {
   int *acc_kp, *acc_bin;
   // outputs
   int* assign;   // [F.n]
-  int* result;   // [2]: nmatches, overflow flag
+  int* result;   // [3]: nmatches, overflow flag, resolution rounds
 };
 
 struct TriProblem {
@@ -410,7 +411,9 @@ __global__ void __launch_bounds__(1024, 1) proj_resolve_kernel(ProjProblem* prob
   for (int b = threadIdx.x; b < HISTO_LENGTH; b += 1024) s_hist[b] = 0;
   for (int j = threadIdx.x; j < nq; j += 1024) P.acc_kp[j] = -1;
   __syncthreads();
+  int rounds = 0;
   while (true) {
+    rounds++;
     if (threadIdx.x == 0) s_unresolved = 0;
     for (int i = threadIdx.x; i < nk; i += 1024) minidx[i] = 0x7fffffff;
     // takes of the previous round (one taker per keypoint: see the claim rule)
@@ -491,7 +494,7 @@ __global__ void __launch_bounds__(1024, 1) proj_resolve_kernel(ProjProblem* prob
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) P.result[0] = s_nmatch;
+  if (threadIdx.x == 0) { P.result[0] = s_nmatch; P.result[2] = rounds; }
 }
 
 // ---- SearchForTriangulation: one thread per KF1 feature-vector entry.
@@ -717,6 +720,20 @@ static T* carve_dev(Arena& a, size_t count) { return (T*)(a.d + a.take(count * s
 static int launch_projection(Matcher& M, std::vector<ProjProblem>& P, size_t in_bytes, bool all_on_device,
                              int32_t* const* assign_out, int32_t* results, bool allow_async);
 
+// ORB_B200_MATCH_DEBUG: resolution rounds and event time of the batch that just completed, on stderr
+static void debug_rounds(const Matcher& M, int kind, int count, const std::vector<size_t>& out_off) {
+  static const bool dbg = getenv("ORB_B200_MATCH_DEBUG") != nullptr;
+  if (!dbg) return;
+  long long rs = 0;
+  int rmax = 0;
+  for (int k = 0; k < count; k++) {
+    const int r = ((const int*)(M.h_out.h + out_off[k]))[2];
+    rs += r; rmax = std::max(rmax, r);
+  }
+  fprintf(stderr, "[orbb200 match] kind %d: %d problems, resolution rounds mean %.1f max %d, %.3f ms\n", kind, count,
+          (double)rs / count, rmax, M.last_ms);
+}
+
 int Matcher::finish_pending() {
   if (!pending) return 0;
   pending = false;
@@ -735,6 +752,7 @@ int Matcher::finish_pending() {
     return launch_projection(*this, pending_P, pending_in_bytes, true, nullptr, pending_results, false) < 0
                ? ORB_E_CAPACITY : 0;
   }
+  debug_rounds(*this, pending_P.empty() ? -1 : pending_P[0].kind, pending_count, pending_off);
   for (int k = 0; k < pending_count; k++) pending_results[k] = ((const int*)(h_out.h + pending_off[k]))[0];
   return 0;
 }
@@ -829,11 +847,11 @@ static int launch_projection(Matcher& M, std::vector<ProjProblem>& P, size_t in_
       p.minidx = carve_dev<int>(M.scratch, nk); p.takenby = carve_dev<int>(M.scratch, nk);
       if (on_device) {
         if (assign_out) p.assign = assign_out[k];  // (a retry keeps the pointer staged by the first launch)
-        p.result = carve_dev<int>(M.out_arena, 2);
+        p.result = carve_dev<int>(M.out_arena, 3);
         out_off[k] = (uint8_t*)p.result - M.out_arena.d;
       } else {
         out_off[k] = M.out_arena.used;
-        p.result = carve_dev<int>(M.out_arena, 2);
+        p.result = carve_dev<int>(M.out_arena, 3);
         p.assign = carve_dev<int>(M.out_arena, nk);
       }
     }
@@ -874,6 +892,7 @@ static int launch_projection(Matcher& M, std::vector<ProjProblem>& P, size_t in_
       if (r[1]) overflow = true;
     }
     if (overflow) { M.cand_per_query *= 4; continue; }
+    debug_rounds(M, P[0].kind, count, out_off);
     for (int k = 0; k < count; k++) {
       const int* r = (const int*)(M.h_out.h + out_off[k]);
       results[k] = r[0];
@@ -950,7 +969,7 @@ static int run_triangulate(Matcher& M, int count, const orb_frame_view* kf1, con
     p.match12 = carve_dev<int>(M.scratch, p.K1.n);
     p.bins = carve_dev<int>(M.scratch, p.K1.n);
     res_off[k] = M.out_arena.used;
-    p.result = carve_dev<int>(M.out_arena, 2);
+    p.result = carve_dev<int>(M.out_arena, 3);
     if (on_device) p.pairs = pairs_out[k];
     else { pair_off[k] = M.out_arena.used; p.pairs = carve_dev<int>(M.out_arena, 2 * (size_t)cap); }
   }
