@@ -732,7 +732,11 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
   unsigned long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long t0 = 0;
   auto tick = [&](int slot) {
-    if (PROF) { const long long t = clock64(); pc[slot] += (unsigned long long)(t - t0); t0 = t; }
+    if (PROF) {
+      long long t;
+      asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) :: "memory");
+      pc[slot] += (unsigned long long)(t - t0); t0 = t;
+    }
   };
   for (int i = tid; i < n; i += WIN_THREADS) first[i] = first_g[i];
   for (int p = tid; p < npan; p += WIN_THREADS) {
@@ -836,7 +840,7 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
   __syncwarp();
   if (warp == 0) pivot_store(0);
   __syncthreads();
-  if (PROF) t0 = clock64();
+  if (PROF) asm volatile("mov.u64 %0, %%clock64;" : "=l"(t0) :: "memory");
   constexpr int FWD_WARPS = WIN / 32;  // warps that can hold a panel row in phase (A)
   for (int p = 0; p < npan; p++) {
     const int k0 = p * WPB, nb = min(WPB, n - k0);
@@ -870,8 +874,9 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
       for (int m = 0; m < WPB; m++)
         if (m < nb) dst[m] = l[m];
     }
-    if (warp >= FWD_WARPS && more) load_rows(max(R, pre) + 1, rlast[p + 1], r0, FWD_WARPS, WIN_THREADS / 32 - FWD_WARPS);
     tick(0);
+    if (warp >= FWD_WARPS && more) load_rows(max(R, pre) + 1, rlast[p + 1], r0, FWD_WARPS, WIN_THREADS / 32 - FWD_WARPS);
+    tick(5);
     __syncthreads();
     tick(1);
     // ---- (B) rank-nb update of the window on the tensor pipe, with look-ahead: warp 0 updates the tile that
@@ -885,10 +890,12 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
         if (pre > R) load_rows(R + 1, pre, r0, 0, 1);
         update_pair(0, ntile, ntile, r0, nr);
         __syncwarp();
+        tick(2);
         if (tid == 0 && more) pivot(p + 1);
         __syncwarp();
+        tick(6);
         if (more) pivot_store(p + 1);
-        tick(2);
+        tick(7);
       } else {
         for (int tile = warp; tile < ntile; tile += 2 * UW) update_pair(tile, tile + UW, ntile, r0, nr);
         tick(2);
@@ -958,7 +965,7 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
   if (PROF) {
     tick(4);
     if (tid == 0 || tid == 32)
-      for (int k = 0; k < 5; k++) atomicAdd(&g_win_prof[(tid ? 8 : 0) + k], pc[k]);
+      for (int k = 0; k < 8; k++) atomicAdd(&g_win_prof[(tid ? 8 : 0) + k], pc[k]);
   }
 }
 
@@ -1736,11 +1743,12 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
     cudaMemcpyFromSymbol(pc, g_win_prof, sizeof(pc));
     cudaMemcpyToSymbol(g_win_prof, zero, sizeof(zero));
     const double d = (double)win_prof_solves;
-    fprintf(stderr, "[orbb200 lba] ldlt_win cycles per solve (warp 0): fwd-subst+loads %.0f | barrier %.0f | update+pivot %.0f | "
-            "barrier %.0f | back-substitution %.0f  (n = %d, %d solves)\n",
-            pc[0] / d, pc[1] / d, pc[2] / d, pc[3] / d, pc[4] / d, n, win_prof_solves);
-    fprintf(stderr, "[orbb200 lba] ... (warp 1): fwd-subst %.0f | barrier %.0f | update tiles %.0f | barrier %.0f | "
-            "back-substitution %.0f\n", pc[8] / d, pc[9] / d, pc[10] / d, pc[11] / d, pc[12] / d);
+    const char* names[8] = {"fwd-subst", "barrier A", "tiles", "barrier B", "back-subst", "after fwd (row loads)", "pivot", "pivot store"};
+    for (int w = 0; w < 2; w++) {
+      fprintf(stderr, "[orbb200 lba] ldlt_win cycles per solve, warp %d (n = %d):", w, n);
+      for (int k = 0; k < 8; k++) fprintf(stderr, " %s %.0f |", names[k], pc[8 * w + k] / d);
+      fprintf(stderr, "\n");
+    }
     win_prof_solves = 0;
   }
   if (stats) {

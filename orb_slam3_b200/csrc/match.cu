@@ -59,6 +59,7 @@ struct DevFrame {
   float fx, fy, cx, cy, bf, b;
   int* cell_start;  // [GRID_CELLS+1]
   int* cell_items;  // [n]
+  uint4* cell_rec;  // [n] (x, y, octave, index) of the keypoints in cell_items order: the window scans read these
 };
 
 // One projection-match problem (local-map or last-frame flavour).
@@ -89,6 +90,7 @@ struct ProjProblem {
   unsigned short* cand_dist;
   int cand_cap;
   int* cand_used;      // [1] bump allocator over cand_*
+  int* ulist;          // [2 * nq] points blocked in the current / next round
   int* minidx;
   int* takenby;        // [F.n] index of the point that took the keypoint; -1 taken on entry; INT_MAX free
   int *acc_kp, *acc_bin;
@@ -175,35 +177,13 @@ __global__ void __launch_bounds__(256) grid_build_kernel(const ProjProblem* prob
       F.cell_items[j + 1] = v;
     }
   }
-  init_problem(probs, blockIdx.x);
-}
-
-// Frame::GetFeaturesInArea (Frame.cc:657-723) plus the static per-candidate gate
-// on mvuRight (ORBmatcher.cc:92-97 / :1752-1758); calls f(idx) in reference order.
-template <class Fn>
-__device__ __forceinline__ void for_each_in_area(const DevFrame& F, float x, float y, float r, int minLevel,
-                                                 int maxLevel, Fn f) {
-  const int nMinCellX = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, F.min_x), r), F.gwi)));
-  if (nMinCellX >= GRID_COLS) return;
-  const int nMaxCellX = min(GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, F.min_x), r), F.gwi)));
-  if (nMaxCellX < 0) return;
-  const int nMinCellY = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, F.min_y), r), F.ghi)));
-  if (nMinCellY >= GRID_ROWS) return;
-  const int nMaxCellY = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, F.min_y), r), F.ghi)));
-  if (nMaxCellY < 0) return;
-  const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
-  for (int ix = nMinCellX; ix <= nMaxCellX; ix++) {
-    const int s = F.cell_start[ix * GRID_ROWS + nMinCellY], e = F.cell_start[ix * GRID_ROWS + nMaxCellY + 1];
-    for (int k = s; k < e; k++) {  // cells (ix, iy..) are contiguous in the CSR
-      const int idx = F.cell_items[k];
-      const orb_keypoint kp = F.keys[idx];
-      if (bCheckLevels) {
-        if (kp.octave < minLevel) continue;
-        if (maxLevel >= 0 && kp.octave > maxLevel) continue;
-      }
-      if (fabsf(__fsub_rn(kp.x, x)) < r && fabsf(__fsub_rn(kp.y, y)) < r) f(idx);
-    }
+  __syncthreads();
+  for (int k = threadIdx.x; k < cnt[GRID_CELLS - 1]; k += 256) {  // cnt[c] = end of cell c by now
+    const int i = F.cell_items[k];
+    const orb_keypoint kp = F.keys[i];
+    F.cell_rec[k] = make_uint4(__float_as_uint(kp.x), __float_as_uint(kp.y), (unsigned)kp.octave, (unsigned)i);
   }
+  init_problem(probs, blockIdx.x);
 }
 
 // Outputs / per-keypoint state of one problem, reset by the CTA that builds its grid.
@@ -220,11 +200,21 @@ __device__ void init_problem(const ProjProblem* probs, int k) {
 // of Frame::GetFeaturesInArea (Frame.cc:657-723) with the per-candidate gate on mvuRight (ORBmatcher.cc:92-97 /
 // :1752-1758) spread over the lanes: the cells (ix, minY..maxY) of one grid column are one contiguous CSR range,
 // lanes 0..ncol-1 fetch the ranges, a warp scan concatenates them, and lane t of a chunk tests the t-th keypoint
-// of the concatenation.  A ballot keeps the candidates in the reference's order.  The list is placed with one
-// atomicAdd per point (the order of the lists in the buffer does not matter), Hamming distances are written with it.
+// of the concatenation -- one 16-byte record of cell_rec, contiguous within a column (the scattered 28-byte
+// orb_keypoint gathers of a thread-per-point version were bound by L2 sector traffic).  A ballot keeps the
+// candidates in the reference's order.  Candidates that can never influence the point's outcome are dropped here:
+// beyond TH_HIGH a keypoint cannot be taken, and it matters as SECOND best only while ratio * dist < TH_HIGH
+// (ORBmatcher.cc:123-128); SearchByProjection(Cur, Last) has no second best at all.  The list is placed with one
+// atomicAdd per point (the order of the lists in the buffer does not matter).
 constexpr int PC_WARPS = 4, PC_Q_PER_WARP = 4;
 __global__ void __launch_bounds__(PC_WARPS * 32) proj_candidates_kernel(ProjProblem* probs) {
-  ProjProblem& P = probs[blockIdx.y];
+  __shared__ ProjProblem P;
+  {
+    const int* src = reinterpret_cast<const int*>(probs + blockIdx.y);
+    int* dst = reinterpret_cast<int*>(&P);
+    for (int i = threadIdx.x; i < (int)(sizeof(ProjProblem) / 4); i += PC_WARPS * 32) dst[i] = src[i];
+  }
+  __syncthreads();
   const DevFrame& F = P.F;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned full = 0xffffffffu, lt = (1u << lane) - 1u;
@@ -241,7 +231,7 @@ __global__ void __launch_bounds__(PC_WARPS * 32) proj_candidates_kernel(ProjProb
         float rr = ((double)P.vcos[j] > 0.998) ? 2.5f : 4.0f;
         if (P.th != 1.0f) rr = __fmul_rn(rr, P.th);
         r = __fmul_rn(rr, F.scale[lvl]);
-        u = P.px[j]; v = P.py[j]; aux = P.pxr[j];
+        u = P.px[j]; v = P.py[j]; aux = P.pxr ? P.pxr[j] : 0.f;
         minl = lvl - 1; maxl = lvl;
       }
     } else if (P.has_mp[j]) {
@@ -283,11 +273,15 @@ __global__ void __launch_bounds__(PC_WARPS * 32) proj_candidates_kernel(ProjProb
       if (cx0 >= GRID_COLS || cx1 < 0 || cy0 >= GRID_ROWS || cy1 < 0) cx1 = cx0 - 1;
     }
     const bool check_levels = (minl > 0) || (maxl >= 0);
+    uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;
+    if (cx0 <= cx1) {
+      const uint4* pq = reinterpret_cast<const uint4*>(P.qdesc + (size_t)j * 32);
+      qa = pq[0]; qb = pq[1];
+    }
     int cnt = 0, base = 0;
     // two sweeps over the window: count, then (after the list is placed) write; the first two chunks of the first
-    // column group keep their verdicts in registers, which covers almost every window
+    // column group keep their verdicts (distance << 22 | keypoint) in registers, which covers almost every window
     int keep0 = -1, keep1 = -1;
-    uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;
     for (int sweep = 0; sweep < 2; sweep++) {
       int written = 0;
       for (int g0 = cx0; g0 <= cx1; g0 += 32) {
@@ -316,19 +310,23 @@ __global__ void __launch_bounds__(PC_WARPS * 32) proj_candidates_kernel(ProjProb
             }
             const int cs = __shfl_sync(full, s, col), cex = __shfl_sync(full, incl - len, col);
             if (t < total) {
-              const int idx = F.cell_items[cs + (t - cex)];
-              const orb_keypoint* kp = F.keys + idx;
+              const uint4 rec = F.cell_rec[cs + (t - cex)];
+              const int oc = (int)rec.z, idx = (int)rec.w;
               bool ok = true;
-              if (check_levels) {
-                const int oc = kp->octave;
-                ok = oc >= minl && !(maxl >= 0 && oc > maxl);
-              }
-              if (ok) ok = fabsf(__fsub_rn(kp->x, u)) < r && fabsf(__fsub_rn(kp->y, v)) < r;
+              if (check_levels) ok = oc >= minl && !(maxl >= 0 && oc > maxl);
+              if (ok) ok = fabsf(__fsub_rn(__uint_as_float(rec.x), u)) < r && fabsf(__fsub_rn(__uint_as_float(rec.y), v)) < r;
               if (ok && F.u_right) {
                 const float ur = F.u_right[idx];
                 if (ur > 0 && fabsf(__fsub_rn(aux, ur)) > r) ok = false;
               }
-              if (ok) pick = idx;
+              if (ok) {
+                const uint4* pd = reinterpret_cast<const uint4*>(F.desc + (size_t)idx * 32);
+                const uint4 d0 = pd[0], d1 = pd[1];
+                const int dist = __popc(qa.x ^ d0.x) + __popc(qa.y ^ d0.y) + __popc(qa.z ^ d0.z) + __popc(qa.w ^ d0.w) +
+                                 __popc(qb.x ^ d1.x) + __popc(qb.y ^ d1.y) + __popc(qb.z ^ d1.z) + __popc(qb.w ^ d1.w);
+                const bool relevant = dist <= TH_HIGH || (P.kind == 0 && __fmul_rn(P.ratio, (float)dist) < (float)TH_HIGH);
+                if (relevant) pick = (dist << 22) | idx;
+              }
             }
             if (sweep == 0 && reg_chunk) { if (t0 == 0) keep0 = pick; else keep1 = pick; }
           }
@@ -338,12 +336,8 @@ __global__ void __launch_bounds__(PC_WARPS * 32) proj_candidates_kernel(ProjProb
           } else {
             if (pick >= 0) {
               const int o = base + written + __popc(m & lt);
-              const uint4* pd = reinterpret_cast<const uint4*>(F.desc + (size_t)pick * 32);
-              const uint4 d0 = pd[0], d1 = pd[1];
-              P.cand_idx[o] = pick;
-              P.cand_dist[o] = (unsigned short)(__popc(qa.x ^ d0.x) + __popc(qa.y ^ d0.y) + __popc(qa.z ^ d0.z) +
-                                                __popc(qa.w ^ d0.w) + __popc(qb.x ^ d1.x) + __popc(qb.y ^ d1.y) +
-                                                __popc(qb.z ^ d1.z) + __popc(qb.w ^ d1.w));
+              P.cand_idx[o] = pick & 0x3fffff;
+              P.cand_dist[o] = (unsigned short)(pick >> 22);
             }
             written += __popc(m);
           }
@@ -360,8 +354,6 @@ __global__ void __launch_bounds__(PC_WARPS * 32) proj_candidates_kernel(ProjProb
         }
         if (lane == 0) { P.q_off[j] = base; P.q_cnt[j] = cnt; P.q_state[j] = cnt > 0 ? 1 : 0; }
         if (cnt == 0) break;
-        const uint4* pq = reinterpret_cast<const uint4*>(P.qdesc + (size_t)j * 32);
-        qa = pq[0]; qb = pq[1];
       }
     }
   }
@@ -389,16 +381,26 @@ __device__ __forceinline__ int rot_bin(float a1, float a2) {
   return bin;
 }
 
-// Phase 2+3: resolution rounds, one CTA per problem.
+// Phase 2+3: resolution rounds, one CTA per problem, one WARP per unresolved point (its list is read 32 entries
+// at a time; a thread-per-point version spent ~10 us per round walking the lists serially).  Round 1 visits every
+// point, later rounds only the list of points that were blocked.
 __global__ void __launch_bounds__(1024, 1) proj_resolve_kernel(ProjProblem* probs, int smem_nk) {
   extern __shared__ int rs_dyn[];
-  __shared__ int s_unresolved, s_nmatch;
+  __shared__ ProjProblem P;
+  __shared__ int s_nmatch, s_nlist[2];
   __shared__ int s_hist[HISTO_LENGTH];
   __shared__ int s_ind[3];
-  ProjProblem& P = probs[blockIdx.x];
+  {
+    const int* src = reinterpret_cast<const int*>(probs + blockIdx.x);
+    int* dst = reinterpret_cast<int*>(&P);
+    for (int i = threadIdx.x; i < (int)(sizeof(ProjProblem) / 4); i += 1024) dst[i] = src[i];
+  }
+  __syncthreads();
   if (P.result[1]) return;  // candidate buffer overflow: host re-runs with a larger one
   const DevFrame& F = P.F;
   const int nq = P.nq, nk = F.n;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned full = 0xffffffffu;
   // per-keypoint state of the rounds (lowest claiming point, taker, octave) in shared memory when it fits: every
   // round is a chain of dependent look-ups into these arrays
   const bool in_smem = nk <= smem_nk;
@@ -407,74 +409,90 @@ __global__ void __launch_bounds__(1024, 1) proj_resolve_kernel(ProjProblem* prob
   uint8_t* oct8 = reinterpret_cast<uint8_t*>(rs_dyn + 2 * smem_nk);
   if (in_smem)
     for (int i = threadIdx.x; i < nk; i += 1024) { takenby[i] = P.takenby[i]; oct8[i] = (uint8_t)F.keys[i].octave; }
-  if (threadIdx.x == 0) s_nmatch = 0;
+  if (threadIdx.x == 0) { s_nmatch = 0; s_nlist[0] = 0; s_nlist[1] = 0; }
   for (int b = threadIdx.x; b < HISTO_LENGTH; b += 1024) s_hist[b] = 0;
   for (int j = threadIdx.x; j < nq; j += 1024) P.acc_kp[j] = -1;
   __syncthreads();
-  int rounds = 0;
+  int* ulist[2] = {P.ulist, P.ulist + nq};
+  int rounds = 0, n_cur = nq;  // round 1: the "list" is 0..nq-1
   while (true) {
+    const int cur = rounds & 1;
+    const bool first = rounds == 0;
     rounds++;
-    if (threadIdx.x == 0) s_unresolved = 0;
     for (int i = threadIdx.x; i < nk; i += 1024) minidx[i] = 0x7fffffff;
     // takes of the previous round (one taker per keypoint: see the claim rule)
-    for (int j = threadIdx.x; j < nq; j += 1024)
-      if (P.q_state[j] == 2) { takenby[P.acc_kp[j]] = j; P.q_state[j] = 0; }
+    if (!first)
+      for (int j = threadIdx.x; j < nq; j += 1024)
+        if (P.q_state[j] == 2) { takenby[P.acc_kp[j]] = j; P.q_state[j] = 0; }
+    if (threadIdx.x == 0) s_nlist[cur ^ 1] = 0;
     __syncthreads();
     // claims: only a candidate within TH_HIGH can be taken by j; free for j = not taken by a lower index
-    for (int j = threadIdx.x; j < nq; j += 1024) {
-      if (P.q_state[j] != 1) continue;
+    for (int i = warp; i < n_cur; i += 32) {
+      const int j = first ? i : ulist[cur][i];
+      if (first && P.q_state[j] != 1) continue;
       const int e0 = P.q_off[j], e1 = e0 + P.q_cnt[j];
-      for (int e = e0; e < e1; e++) {
+      for (int e = e0 + lane; e < e1; e += 32) {
         if (P.cand_dist[e] > TH_HIGH) continue;
         const int c = P.cand_idx[e];
         if (takenby[c] > j) atomicMin(&minidx[c], j);
       }
     }
     __syncthreads();
-    for (int j = threadIdx.x; j < nq; j += 1024) {
-      if (P.q_state[j] != 1) continue;
-      const int e0 = P.q_off[j], e1 = e0 + P.q_cnt[j];
-      bool mine = true;
-      for (int e = e0; e < e1 && mine; e++) {
-        const int c = P.cand_idx[e];
-        if (takenby[c] > j && minidx[c] < j) mine = false;  // a lower unresolved point may still take it
+    for (int i = warp; i < n_cur; i += 32) {
+      const int j = first ? i : ulist[cur][i];
+      if (first && P.q_state[j] != 1) continue;
+      const int e0 = P.q_off[j], cnt = P.q_cnt[j];
+      // the two smallest (distance, list position) keys among the free candidates: the reference's scan keeps the
+      // FIRST candidate of the smallest distance as best and the first of the next (distance, position) as second
+      unsigned k1 = 0xffffffffu, k2 = 0xffffffffu;
+      bool blocked = false;
+      for (int t = lane; t < cnt; t += 32) {
+        const int c = P.cand_idx[e0 + t];
+        const int tb = takenby[c];
+        if (tb < j) continue;  // taken on entry or by a lower-index point
+        if (minidx[c] < j) blocked = true;  // a lower unresolved point may still take it
+        const unsigned key = ((unsigned)P.cand_dist[e0 + t] << 16) | (unsigned)t;
+        if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
       }
-      if (!mine) { atomicAdd(&s_unresolved, 1); continue; }
-      // replay the reference scan: a keypoint is skipped iff it was taken on entry or by a lower-index point
-      int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
-      for (int e = e0; e < e1; e++) {
-        const int c = P.cand_idx[e];
-        if (takenby[c] < j) continue;
-        const int dist = P.cand_dist[e];
-        if (dist < bestDist) {
-          bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel;
-          bestLevel = in_smem ? (int)oct8[c] : F.keys[c].octave; bestIdx = c;
-        } else if (P.kind == 0 && dist < bestDist2) {
-          bestLevel2 = in_smem ? (int)oct8[c] : F.keys[c].octave; bestDist2 = dist;
-        }
+      if (__any_sync(full, blocked)) {
+        if (lane == 0) ulist[cur ^ 1][atomicAdd(&s_nlist[cur ^ 1], 1)] = j;
+        continue;
       }
-      bool accept = bestDist <= TH_HIGH;
-      if (accept && P.kind == 0) {
-        // ratio only when best and second best share the level (:123-128)
-        if (bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(P.ratio, (float)bestDist2)) accept = false;
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        const unsigned o1 = __shfl_xor_sync(full, k1, o), o2 = __shfl_xor_sync(full, k2, o);
+        const unsigned lo = min(k1, o1), hi = max(k1, o1);
+        k1 = lo; k2 = min(hi, min(k2, o2));
       }
+      if (lane != 0) continue;
       int state = 0;
-      if (accept) {
-        P.assign[bestIdx] = j;
-        P.acc_kp[j] = bestIdx;
-        if (P.has_obs[j]) state = 2;  // the keypoint is closed to later points (ORBmatcher.cc:88-90 / :1748-1750)
-        atomicAdd(&s_nmatch, 1);
-        if (P.kind == 1 && P.check_ori) {
-          const int bin = rot_bin(P.angle[j], F.keys[bestIdx].angle);
-          P.acc_bin[j] = bin;
-          atomicAdd(&s_hist[bin], 1);
+      if (k1 != 0xffffffffu) {
+        const int bestDist = (int)(k1 >> 16), bestIdx = P.cand_idx[e0 + (int)(k1 & 0xffffu)];
+        bool accept = bestDist <= TH_HIGH;
+        if (accept && P.kind == 0 && k2 != 0xffffffffu) {
+          // ratio only when best and second best share the level (:123-128)
+          const int c2 = P.cand_idx[e0 + (int)(k2 & 0xffffu)];
+          const int l1 = in_smem ? (int)oct8[bestIdx] : F.keys[bestIdx].octave;
+          const int l2 = in_smem ? (int)oct8[c2] : F.keys[c2].octave;
+          if (l1 == l2 && (float)bestDist > __fmul_rn(P.ratio, (float)(k2 >> 16))) accept = false;
+        }
+        if (accept) {
+          P.assign[bestIdx] = j;
+          P.acc_kp[j] = bestIdx;
+          if (P.has_obs[j]) state = 2;  // the keypoint is closed to later points (ORBmatcher.cc:88-90 / :1748-1750)
+          atomicAdd(&s_nmatch, 1);
+          if (P.kind == 1 && P.check_ori) {
+            const int bin = rot_bin(P.angle[j], F.keys[bestIdx].angle);
+            P.acc_bin[j] = bin;
+            atomicAdd(&s_hist[bin], 1);
+          }
         }
       }
       P.q_state[j] = (uint8_t)state;
     }
     __syncthreads();
-    if (s_unresolved == 0) break;
-    __syncthreads();
+    n_cur = s_nlist[cur ^ 1];
+    if (n_cur == 0) break;
   }
   if (P.kind == 1 && P.check_ori) {
     if (threadIdx.x == 0) {
@@ -821,7 +839,7 @@ static int launch_projection(Matcher& M, std::vector<ProjProblem>& P, size_t in_
     size_t sbytes = 0, obytes = 0;
     for (int k = 0; k < count; k++) {
       const size_t nq = P[k].nq, nk = P[k].F.n, cc = std::max<size_t>(nq * M.cand_per_query, 1024);
-      sbytes += 256 * 16 + (GRID_CELLS + 1 + nk) * 4 + nq * (2 * 4 + 1 + 8) + 4 + cc * 6 + nk * 8;
+      sbytes += 256 * 16 + (GRID_CELLS + 1 + nk) * 4 + nk * 16 + nq * (4 * 4 + 1 + 8) + 4 + cc * 6 + nk * 8;
       obytes += 256 * 2 + nk * 4 + 8;
     }
     sbytes += sizeof(ProjProblem) * count + 4096;
@@ -838,8 +856,9 @@ static int launch_projection(Matcher& M, std::vector<ProjProblem>& P, size_t in_
       max_nq = std::max(max_nq, p.nq);
       p.F.cell_start = carve_dev<int>(M.scratch, GRID_CELLS + 1);
       p.F.cell_items = carve_dev<int>(M.scratch, nk);
+      p.F.cell_rec = carve_dev<uint4>(M.scratch, nk);
       p.q_cnt = carve_dev<int>(M.scratch, nq); p.q_off = carve_dev<int>(M.scratch, nq);
-      p.cand_used = carve_dev<int>(M.scratch, 1);
+      p.cand_used = carve_dev<int>(M.scratch, 1); p.ulist = carve_dev<int>(M.scratch, 2 * nq);
       p.q_state = carve_dev<uint8_t>(M.scratch, nq);
       p.acc_kp = carve_dev<int>(M.scratch, nq); p.acc_bin = carve_dev<int>(M.scratch, nq);
       p.cand_idx = carve_dev<int>(M.scratch, cc); p.cand_dist = carve_dev<unsigned short>(M.scratch, cc);

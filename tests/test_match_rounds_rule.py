@@ -102,3 +102,52 @@ def test_far_candidates_do_not_serialise_the_points():
     cands = [[(j, 40)] + [(c, 130) for c in range(50, 60)] for j in range(nq)]
     a, n, rounds = in_rounds(nq, nk, cands, [True] * nq, [False] * nk, 0, 0.8, [0] * nk, random.Random(0))
     assert rounds == 1 and n == nq and a[:50] == list(range(50))
+
+
+def test_second_best_is_the_next_distance_position_key():
+    """The kernel finds best / second best as the two smallest (distance, list position) keys with a warp
+    reduction; the reference's scan (strict `<` updates, ORBmatcher.cc:99-116) ends in the same state, ties
+    included."""
+    rng = random.Random(5)
+    for _ in range(20000):
+        m = rng.randint(0, 12)
+        items = [(rng.randint(0, 7), rng.choice([30, 30, 31, 40, 40, 55, 90, 120])) for _ in range(m)]  # (level, dist)
+        bd, bl, bd2, bl2, bi = 256, -1, 256, -1, -1
+        for pos, (lv, d) in enumerate(items):
+            if d < bd:
+                bd2, bd, bl2, bl, bi = bd, d, bl, lv, pos
+            elif d < bd2:
+                bl2, bd2 = lv, d
+        keys = sorted((d << 16) | pos for pos, (_, d) in enumerate(items))
+        if not keys:
+            assert bi == -1
+            continue
+        assert (keys[0] >> 16, keys[0] & 0xffff) == (bd, bi)
+        if len(keys) > 1:
+            assert keys[1] >> 16 == bd2 and items[keys[1] & 0xffff][0] == bl2
+        else:
+            assert bd2 == 256 and bl2 == -1
+
+
+def test_dropping_irrelevant_candidates_keeps_the_result():
+    """proj_candidates_kernel drops candidates beyond TH_HIGH that cannot act as second best either
+    (ratio * dist >= TH_HIGH); SearchByProjection(Cur, Last) keeps only those within TH_HIGH."""
+    import numpy as np
+    rng = random.Random(9)
+    for trial in range(1500):
+        nk, nq, kind = rng.randint(5, 40), rng.randint(1, 50), rng.randint(0, 1)
+        ratio = rng.choice([0.6, 0.7, 0.8, 0.9])
+        lvl = [rng.randint(0, 2) for _ in range(nk)]
+        cands = []
+        for _ in range(nq):
+            cs = rng.sample(range(nk), rng.randint(0, min(nk, 10)))
+            cands.append([(c, rng.randint(60, 180)) for c in cs])
+        has_obs = [rng.random() < 0.7 for _ in range(nq)]
+        taken0 = [rng.random() < 0.15 for _ in range(nk)]
+
+        def relevant(d):
+            return d <= TH_HIGH or (kind == 0 and float(np.float32(ratio) * np.float32(d)) < TH_HIGH)
+        kept = [[(c, d) for c, d in lst if relevant(d)] for lst in cands]
+        r32 = float(np.float32(ratio))
+        assert sequential(nq, nk, cands, has_obs, taken0, kind, r32, lvl) == \
+            sequential(nq, nk, kept, has_obs, taken0, kind, r32, lvl), trial
