@@ -758,7 +758,7 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
     }
   };
   // pivot block of panel p, one thread, registers only: factors rows/cols [k0, k0+nb) of the ring, leaves L (strict
-  // lower) and D in Lb, 1/D in Dib; the warp writes them to M afterwards (pivot_store)
+  // lower) and D in Lb, 1/D in Dib; another warp writes them to M during the next phase (pivot_store)
   auto pivot = [&](int p) {
     const int k0 = p * WPB, nb = min(WPB, n - k0);
     double a[WPB][WPB];
@@ -772,7 +772,9 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
     for (int k = 0; k < WPB; k++) {
       const double d = a[k][k];
       if (d == 0.0) *fail = 1.0;
-      double inv = (double)__frcp_rn((float)d);
+      // 1/d: the hardware's fp64 reciprocal seed (MUFU.RCP64H, ~20 bits, no float round trip) + two Newton steps
+      double inv;
+      asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(inv) : "d"(d));
       inv = inv * (2.0 - d * inv);
       inv = inv * (2.0 - d * inv);
       Dib[k] = inv;
@@ -789,56 +791,64 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
 #pragma unroll
     for (int r = 0; r < WPB; r++)
 #pragma unroll
-      for (int c = 0; c < WPB; c++) Lb[r][c] = c <= r ? a[r][c] : 0.0;
+      for (int c = 0; c <= r; c++) Lb[r][c] = a[r][c];
   };
-  auto pivot_store = [&](int p) {  // warp 0, after pivot(p) and a __syncwarp
+  auto pivot_store = [&](int p) {  // one warp, in phase (A) of panel p (Lb is stable until the barrier)
     const int k0 = p * WPB, nb = min(WPB, n - k0);
     for (int e = lane; e < WPB * WPB; e += 32) {
       const int r = e >> 3, c = e & 7;
       if (r < nb && c <= r) M[(size_t)(k0 + r) * n + k0 + c] = Lb[r][c];  // L below, D on the diagonal
     }
   };
-  // two 8x8 tiles of the rank-nb update of panel (r0, nr): C -= L_i (8x8) * (L*D)_j^T, two fp64 DMMA m8n8k4 each;
-  // fragment layout A[g][t], B[t][g], C[g][2t], C[g][2t+1] with g = lane / 4, t = lane % 4.  Operands of both tiles
-  // are fetched before the first DMMA so the two chains overlap.
+  // 8x8 tiles of the rank-nb update of panel (r0, nr): C -= L_i (8x8) * (L*D)_j^T, two fp64 DMMA m8n8k4 each;
+  // fragment layout A[g][t], B[t][g], C[g][2t], C[g][2t+1] with g = lane / 4, t = lane % 4.  A warp owns a run of
+  // consecutive tiles (row-major over the lower triangle) and handles TG at a time: the operands of all of them are
+  // fetched before the first DMMA, so TG accumulator chains are in flight instead of one (the kernel is bound by
+  // the latency of its dependent chains, not by throughput).
   const int fg = lane >> 2, ft = lane & 3;
-  struct TileRef { double *p0, *p1; bool ok0, ok1; double a0, a1, b0, b1; };
-  auto tile_ref = [&](int tile, int r0, int nr, bool live) {
-    TileRef T;
-    const int tt = tile_ij[live ? tile : 0];
-    const int ti = tt >> 8, tj = tt & 255;
-    const int wi = 8 * ti + fg, wj = 8 * tj + 2 * ft;
-    T.a0 = -Lt[ft * WIN_LP + wi]; T.a1 = -Lt[(ft + 4) * WIN_LP + wi];
-    T.b0 = LDt[ft * WIN_LP + 8 * tj + fg]; T.b1 = LDt[(ft + 4) * WIN_LP + 8 * tj + fg];
-    double* row = (wi == nr) ? zr : A + ((r0 + min(wi, nr)) % WIN) * WIN_P;  // the rhs row has no column of its own
-    T.ok0 = live && wi <= nr && wj < nr && wj <= wi;
-    T.ok1 = live && wi <= nr && wj + 1 < nr && wj + 1 <= wi;
-    T.p0 = row + (r0 + wj) % WIN;
-    T.p1 = row + (r0 + wj + 1) % WIN;
-    return T;
-  };
-  auto update_pair = [&](int tileA, int tileB, int ntile, int r0, int nr) {
-    const TileRef X = tile_ref(tileA, r0, nr, tileA < ntile), Y = tile_ref(tileB, r0, nr, tileB < ntile);
-    double x0 = X.ok0 ? *X.p0 : 0.0, x1 = X.ok1 ? *X.p1 : 0.0;
-    double y0 = Y.ok0 ? *Y.p0 : 0.0, y1 = Y.ok1 ? *Y.p1 : 0.0;
-    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-        : "+d"(x0), "+d"(x1) : "d"(X.a0), "d"(X.b0));
-    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-        : "+d"(y0), "+d"(y1) : "d"(Y.a0), "d"(Y.b0));
-    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-        : "+d"(x0), "+d"(x1) : "d"(X.a1), "d"(X.b1));
-    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-        : "+d"(y0), "+d"(y1) : "d"(Y.a1), "d"(Y.b1));
-    if (X.ok0) *X.p0 = x0;
-    if (X.ok1) *X.p1 = x1;
-    if (Y.ok0) *Y.p0 = y0;
-    if (Y.ok1) *Y.p1 = y1;
+  constexpr int ZR_OFF = WIN * WIN_P;  // zr follows the ring: one index space for matrix rows and the rhs row
+  constexpr int TG = 3;  // tiles in flight per warp (90 tiles of a 96-row window = 15 warps x 2 groups of 3)
+  auto update_run = [&](int t_begin, int t_end, int r0, int nr) {
+    if (t_begin >= t_end) return;
+    int tt = tile_ij[t_begin];
+    int ti = tt >> 8, tj = tt & 255;
+    for (int tb = t_begin; tb < t_end; tb += TG) {
+      int i0[TG], i1[TG];
+      bool ok0[TG], ok1[TG];
+      double a0[TG], a1[TG], b0[TG], b1[TG], c0[TG], c1[TG];
+#pragma unroll
+      for (int u = 0; u < TG; u++) {
+        const bool live = tb + u < t_end;
+        const int wi = 8 * ti + fg, wj = 8 * tj + 2 * ft;
+        a0[u] = -Lt[ft * WIN_LP + wi]; a1[u] = -Lt[(ft + 4) * WIN_LP + wi];
+        b0[u] = LDt[ft * WIN_LP + 8 * tj + fg]; b1[u] = LDt[(ft + 4) * WIN_LP + 8 * tj + fg];
+        const int rowoff = (wi >= nr) ? ZR_OFF : ((r0 + wi) % WIN) * WIN_P;  // the rhs row has no column of its own
+        ok0[u] = live && wi <= nr && wj < nr && wj <= wi;
+        ok1[u] = live && wi <= nr && wj + 1 < nr && wj + 1 <= wi;
+        i0[u] = rowoff + (r0 + wj) % WIN;
+        i1[u] = rowoff + (r0 + wj + 1) % WIN;
+        if (tj == ti) { ti++; tj = 0; } else tj++;
+      }
+#pragma unroll
+      for (int u = 0; u < TG; u++) { c0[u] = ok0[u] ? A[i0[u]] : 0.0; c1[u] = ok1[u] ? A[i1[u]] : 0.0; }
+#pragma unroll
+      for (int u = 0; u < TG; u++)
+        asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+            : "+d"(c0[u]), "+d"(c1[u]) : "d"(a0[u]), "d"(b0[u]));
+#pragma unroll
+      for (int u = 0; u < TG; u++)
+        asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+            : "+d"(c0[u]), "+d"(c1[u]) : "d"(a1[u]), "d"(b1[u]));
+#pragma unroll
+      for (int u = 0; u < TG; u++) {
+        if (ok0[u]) A[i0[u]] = c0[u];
+        if (ok1[u]) A[i1[u]] = c1[u];
+      }
+    }
   };
   load_rows(0, rlast[0], 0, 0, WIN_THREADS / 32);
   __syncthreads();
   if (tid == 0) pivot(0);
-  __syncwarp();
-  if (warp == 0) pivot_store(0);
   __syncthreads();
   if (PROF) asm volatile("mov.u64 %0, %%clock64;" : "=l"(t0) :: "memory");
   constexpr int FWD_WARPS = WIN / 32;  // warps that can hold a panel row in phase (A)
@@ -875,6 +885,7 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
         if (m < nb) dst[m] = l[m];
     }
     tick(0);
+    if (warp == FWD_WARPS) pivot_store(p);
     if (warp >= FWD_WARPS && more) load_rows(max(R, pre) + 1, rlast[p + 1], r0, FWD_WARPS, WIN_THREADS / 32 - FWD_WARPS);
     tick(5);
     __syncthreads();
@@ -886,42 +897,59 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
       const int T8 = (nr + 1 + 7) >> 3;
       const int ntile = T8 * (T8 + 1) / 2;
       constexpr int UW = WIN_THREADS / 32 - 1;
+      const int per = (ntile - 1 + UW - 1) / UW;  // tiles 1 .. ntile-1 in runs over the other warps
       if (warp == 0) {
         if (pre > R) load_rows(R + 1, pre, r0, 0, 1);
-        update_pair(0, ntile, ntile, r0, nr);
+        update_run(0, 1, r0, nr);
         __syncwarp();
         tick(2);
         if (tid == 0 && more) pivot(p + 1);
-        __syncwarp();
         tick(6);
-        if (more) pivot_store(p + 1);
-        tick(7);
       } else {
-        for (int tile = warp; tile < ntile; tile += 2 * UW) update_pair(tile, tile + UW, ntile, r0, nr);
+        const int tb = 1 + (warp - 1) * per;
+        update_run(tb, min(tb + per, ntile), r0, nr);
         tick(2);
       }
     }
     __syncthreads();
     tick(3);
   }
-  // ---- L^T x = z (z = row n of M, already scaled by 1/D).  Four warps, one named barrier per 8 unknowns: a thread
-  //      owns one column of the step's window and has the next step's 8 entries of L in flight; the 8x8 in-block
-  //      solve is done by every thread redundantly from shared memory (the strict-lower pivot blocks are staged there
-  //      in one parallel pass: the ring is dead by now), so nothing is exchanged but acc.
+  // ---- L^T x = z (z = row n of M, already scaled by 1/D), 8 unknowns per step, four warps, one named barrier per
+  //      step.  With G = L_bb^-T (the inverse of the step's unit-triangular pivot block) the step is
+  //        x_b = G acc_b,   acc_j -= sum_c P[j][c] acc_b[c],   P = L_panel^T G,
+  //      so the chain from one step to the next is: read acc_b, 8 multiply-adds, write acc_j, barrier.  Everything
+  //      else is off the chain: the inverses of all pivot blocks are formed up front (one thread per block, staged
+  //      in the dead ring), a thread owns one column j of the step's window, has the next step's 8 entries of L in
+  //      flight and turns them into its row of P while it waits.
   double* acc = A;            // [n]
-  double* pblk = A + n;       // [npan][28]: L[k0+c][k0+r], r < c, at c(c-1)/2 + r   (n + 28 npan <= WIN * WIN_P: host-checked)
+  double* pblk = A + n;       // [npan][28]: Linv[c][r], r < c, at c(c-1)/2 + r   (n + 28 npan <= WIN * WIN_P: host-checked)
   for (int i = tid; i < n; i += WIN_THREADS) acc[i] = M[(size_t)n * n + i];
-  for (int i = tid; i < npan * 28; i += WIN_THREADS) {
-    const int bq = i / 28, e = i - bq * 28;
-    int c = 1;
-    while (c * (c + 1) / 2 <= e) c++;
-    const int r = e - c * (c - 1) / 2, k0 = bq * WPB;
-    pblk[i] = (k0 + c < n) ? M[(size_t)(k0 + c) * n + k0 + r] : 0.0;
+  for (int bq = tid; bq < npan; bq += WIN_THREADS) {
+    const int k0 = bq * WPB;
+    double Lq[WPB][WPB], Li[WPB][WPB];
+#pragma unroll
+    for (int c = 1; c < WPB; c++)
+#pragma unroll
+      for (int r = 0; r < c; r++) Lq[c][r] = (k0 + c < n) ? M[(size_t)(k0 + c) * n + k0 + r] : 0.0;
+    // inverse of the unit lower triangle, row by row: Li[c][r] = -(L[c][r] + sum_{r<m<c} L[c][m] Li[m][r])
+#pragma unroll
+    for (int c = 1; c < WPB; c++)
+#pragma unroll
+      for (int r = 0; r < c; r++) {
+        double t = Lq[c][r];
+#pragma unroll
+        for (int m = r + 1; m < c; m++) t += Lq[c][m] * Li[m][r];
+        Li[c][r] = -t;
+      }
+#pragma unroll
+    for (int c = 1; c < WPB; c++)
+#pragma unroll
+      for (int r = 0; r < c; r++) pblk[bq * 28 + c * (c - 1) / 2 + r] = Li[c][r];
   }
   __syncthreads();
   constexpr int BS_THREADS = WIN;  // one thread per window column (WIN_ROWS < WIN)
   if (tid >= BS_THREADS) return;
-  double nxt[WPB];
+  double nxt[WPB], Pc[WPB];
   int jm_next = 0;
   auto fetch = [&](int bq) {
     const int k0 = bq * WPB, nb = min(WPB, n - k0);
@@ -934,31 +962,47 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
 #pragma unroll
     for (int r = 0; r < WPB; r++) nxt[r] = (r < nb && j < k0) ? M[(size_t)(k0 + r) * n + j] : 0.0;
   };
-  fetch(npan - 1);
-  for (int bq = npan - 1; bq >= 0; bq--) {
-    const int k0 = bq * WPB, nb = min(WPB, n - k0), jm = jm_next;
-    double cur[WPB], v[WPB];
-#pragma unroll
-    for (int r = 0; r < WPB; r++) cur[r] = nxt[r];
-    if (bq > 0) fetch(bq - 1);  // independent of everything below
+  // P[j][c] = sum_{r <= c} L[k0+r][j] G[r][c],  G[r][c] = Linv[c][r], G[c][c] = 1
+  auto transform = [&](int bq) {
     const double* pb = pblk + bq * 28;
 #pragma unroll
-    for (int r = 0; r < WPB; r++) v[r] = r < nb ? acc[k0 + r] : 0.0;
+    for (int c = 0; c < WPB; c++) {
+      double t = nxt[c];
 #pragma unroll
-    for (int c = WPB - 1; c >= 1; c--)
+      for (int r = 0; r < c; r++) t += nxt[r] * pb[c * (c - 1) / 2 + r];
+      Pc[c] = t;
+    }
+  };
+  fetch(npan - 1);
+  transform(npan - 1);
+  int jm = jm_next;
+  if (npan > 1) fetch(npan - 2);
+  for (int bq = npan - 1; bq >= 0; bq--) {
+    const int k0 = bq * WPB, nb = min(WPB, n - k0);
+    // ---- the chain
+    double a[WPB];
 #pragma unroll
-      for (int r = 0; r < c; r++) v[r] -= pb[c * (c - 1) / 2 + r] * v[c];
+    for (int c = 0; c < WPB; c++) a[c] = c < nb ? acc[k0 + c] : 0.0;
+    if (jm + tid < k0) {
+      const double s0 = Pc[0] * a[0] + Pc[1] * a[1] + Pc[2] * a[2] + Pc[3] * a[3];
+      const double s1 = Pc[4] * a[4] + Pc[5] * a[5] + Pc[6] * a[6] + Pc[7] * a[7];
+      acc[jm + tid] -= s0 + s1;
+    }
+    // ---- off the chain: this step's unknowns, the next step's row of P, the loads of the step after it
     if (tid < nb) {
-      double xv = v[0];
+      const double* pb = pblk + bq * 28;
+      double xv = 0.0;
 #pragma unroll
-      for (int r = 1; r < WPB; r++) xv = tid == r ? v[r] : xv;
+      for (int c = 0; c < WPB; c++) {
+        const double g = tid < c ? pb[c * (c - 1) / 2 + tid] : (tid == c ? 1.0 : 0.0);  // G[tid][c] = Linv[c][tid]
+        xv += g * a[c];
+      }
       x[k0 + tid] = xv;
     }
-    if (jm + tid < k0) {
-      double sdot = 0;
-#pragma unroll
-      for (int r = 0; r < WPB; r++) sdot += cur[r] * v[r];
-      acc[jm + tid] -= sdot;
+    if (bq > 0) {
+      transform(bq - 1);
+      jm = jm_next;
+      if (bq > 1) fetch(bq - 2);
     }
     asm volatile("bar.sync 1, %0;" ::"n"(BS_THREADS) : "memory");
   }

@@ -84,12 +84,11 @@ struct ProjProblem {
   float th, ratio, th_far;
   int far_points;
   // scratch
-  int *q_cnt, *q_off;  // candidate list of point j: cand_*[q_off[j] .. q_off[j] + q_cnt[j])
+  int* q_cnt;          // candidate list of point j: cand_*[j * cand_slot .. + q_cnt[j])
   uint8_t* q_state;    // 0 inactive/resolved, 1 unresolved, 2 finalised this round with a take to apply
   int* cand_idx;
   unsigned short* cand_dist;
-  int cand_cap;
-  int* cand_used;      // [1] bump allocator over cand_*
+  int cand_slot;       // entries per point
   int* ulist;          // [2 * nq] points blocked in the current / next round
   int* minidx;
   int* takenby;        // [F.n] index of the point that took the keypoint; -1 taken on entry; INT_MAX free
@@ -193,21 +192,23 @@ __device__ void init_problem(const ProjProblem* probs, int k) {
     P.assign[i] = -1;
     P.takenby[i] = (P.F.kp_taken && P.F.kp_taken[i]) ? -1 : 0x7fffffff;
   }
-  if (threadIdx.x == 0) { P.result[0] = 0; P.result[1] = 0; *P.cand_used = 0; }
+  if (threadIdx.x == 0) { P.result[0] = 0; P.result[1] = 0; }
 }
 
-// Phase 1: one WARP per query point.  Window parameters (ORBmatcher.cc:51-70 / :1701-1733), then the window query
-// of Frame::GetFeaturesInArea (Frame.cc:657-723) with the per-candidate gate on mvuRight (ORBmatcher.cc:92-97 /
-// :1752-1758) spread over the lanes: the cells (ix, minY..maxY) of one grid column are one contiguous CSR range,
-// lanes 0..ncol-1 fetch the ranges, a warp scan concatenates them, and lane t of a chunk tests the t-th keypoint
-// of the concatenation -- one 16-byte record of cell_rec, contiguous within a column (the scattered 28-byte
-// orb_keypoint gathers of a thread-per-point version were bound by L2 sector traffic).  A ballot keeps the
-// candidates in the reference's order.  Candidates that can never influence the point's outcome are dropped here:
-// beyond TH_HIGH a keypoint cannot be taken, and it matters as SECOND best only while ratio * dist < TH_HIGH
-// (ORBmatcher.cc:123-128); SearchByProjection(Cur, Last) has no second best at all.  The list is placed with one
-// atomicAdd per point (the order of the lists in the buffer does not matter).
+// Phase 1: one WARP per query point, four points per warp.  The window parameters (ORBmatcher.cc:51-70 /
+// :1701-1733) of the warp's four points are computed by four lanes at once (one round of global-memory latency
+// instead of four); then, point by point, the window query of Frame::GetFeaturesInArea (Frame.cc:657-723) with the
+// per-candidate gate on mvuRight (ORBmatcher.cc:92-97 / :1752-1758) is spread over the lanes: the cells
+// (ix, minY..maxY) of one grid column are one contiguous CSR range, lanes 0..ncol-1 fetch the ranges, a warp scan
+// concatenates them, and lane t of a chunk tests the t-th keypoint of the concatenation -- one 16-byte record of
+// cell_rec, contiguous within a column (the scattered 28-byte orb_keypoint gathers of a thread-per-point version
+// were bound by L2 sector traffic).  A ballot keeps the candidates in the reference's order.  Candidates that can
+// never influence the point's outcome are dropped here: beyond TH_HIGH a keypoint cannot be taken, and it matters
+// as SECOND best only while ratio * dist < TH_HIGH (ORBmatcher.cc:123-128); SearchByProjection(Cur, Last) has no
+// second best at all.  Every point owns a fixed slot of `cand_slot` entries (no counting pass, no atomics); a
+// point that needs more raises the overflow flag and the host runs the batch again with larger slots.
 constexpr int PC_WARPS = 4, PC_Q_PER_WARP = 4;
-__global__ void __launch_bounds__(PC_WARPS * 32) proj_candidates_kernel(ProjProblem* probs) {
+__global__ void __launch_bounds__(PC_WARPS * 32, 7) proj_candidates_kernel(ProjProblem* probs) {
   __shared__ ProjProblem P;
   {
     const int* src = reinterpret_cast<const int*>(probs + blockIdx.y);
@@ -219,50 +220,67 @@ __global__ void __launch_bounds__(PC_WARPS * 32) proj_candidates_kernel(ProjProb
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned full = 0xffffffffu, lt = (1u << lane) - 1u;
   const int j0 = (blockIdx.x * PC_WARPS + warp) * PC_Q_PER_WARP;
-  for (int j = j0; j < min(j0 + PC_Q_PER_WARP, P.nq); j++) {
-    bool active = false;
-    float u = 0, v = 0, r = 0, aux = 0;
-    int minl = 0, maxl = 0;
+  if (j0 >= P.nq) return;
+  // ---- parameters of points j0 .. j0+3 on lanes 0..3
+  bool my_active = false;
+  float my_u = 0, my_v = 0, my_r = 0, my_aux = 0;
+  int my_minl = 0, my_maxl = 0;
+  if (lane < PC_Q_PER_WARP && j0 + lane < P.nq) {
+    const int j = j0 + lane;
     if (P.kind == 0) {
-      // ORBmatcher.cc:51-70
-      active = P.in_view[j] && !(P.far_points && P.depth[j] > P.th_far) && !P.is_bad[j];
-      if (active) {
-        const int lvl = P.lvl[j];
-        float rr = ((double)P.vcos[j] > 0.998) ? 2.5f : 4.0f;
+      // ORBmatcher.cc:51-70 (all inputs fetched up front: one round trip)
+      const uint8_t in_view = P.in_view[j], bad = P.is_bad[j];
+      const float depth = P.depth[j], vcos = P.vcos[j], px = P.px[j], py = P.py[j], pxr = P.pxr ? P.pxr[j] : 0.f;
+      const int lvl = P.lvl[j];
+      my_active = in_view && !(P.far_points && depth > P.th_far) && !bad;
+      if (my_active) {
+        float rr = ((double)vcos > 0.998) ? 2.5f : 4.0f;
         if (P.th != 1.0f) rr = __fmul_rn(rr, P.th);
-        r = __fmul_rn(rr, F.scale[lvl]);
-        u = P.px[j]; v = P.py[j]; aux = P.pxr ? P.pxr[j] : 0.f;
-        minl = lvl - 1; maxl = lvl;
+        my_r = __fmul_rn(rr, F.scale[lvl]);
+        my_u = px; my_v = py; my_aux = pxr;
+        my_minl = lvl - 1; my_maxl = lvl;
       }
-    } else if (P.has_mp[j]) {
+    } else {
       // ORBmatcher.cc:1701-1733; Tcw * x3Dw as Sophus/Eigen evaluate it
-      const float qx = P.T[0], qy = P.T[1], qz = P.T[2], qw = P.T[3];
+      const uint8_t has_mp = P.has_mp[j];
       const float vx = P.wpos[3 * j], vy = P.wpos[3 * j + 1], vz = P.wpos[3 * j + 2];
-      float ux = __fsub_rn(__fmul_rn(qy, vz), __fmul_rn(qz, vy));
-      float uy = __fsub_rn(__fmul_rn(qz, vx), __fmul_rn(qx, vz));
-      float uz = __fsub_rn(__fmul_rn(qx, vy), __fmul_rn(qy, vx));
-      ux = __fadd_rn(ux, ux); uy = __fadd_rn(uy, uy); uz = __fadd_rn(uz, uz);
-      const float c0 = __fsub_rn(__fmul_rn(qy, uz), __fmul_rn(qz, uy));
-      const float c1 = __fsub_rn(__fmul_rn(qz, ux), __fmul_rn(qx, uz));
-      const float c2 = __fsub_rn(__fmul_rn(qx, uy), __fmul_rn(qy, ux));
-      const float xc = __fadd_rn(__fadd_rn(__fadd_rn(vx, __fmul_rn(qw, ux)), c0), P.T[4]);
-      const float yc = __fadd_rn(__fadd_rn(__fadd_rn(vy, __fmul_rn(qw, uy)), c1), P.T[5]);
-      const float zc = __fadd_rn(__fadd_rn(__fadd_rn(vz, __fmul_rn(qw, uz)), c2), P.T[6]);
-      const float invzc = (float)(1.0 / (double)zc);
-      if (!(invzc < 0)) {
-        u = __fadd_rn(__fdiv_rn(__fmul_rn(F.fx, xc), zc), F.cx);
-        v = __fadd_rn(__fdiv_rn(__fmul_rn(F.fy, yc), zc), F.cy);
-        if (!(u < F.min_x || u > F.max_x) && !(v < F.min_y || v > F.max_y)) {
-          active = true;
-          const int o = P.octave[j];
-          r = __fmul_rn(P.th, F.scale[o]);
-          aux = __fsub_rn(u, __fmul_rn(F.bf, invzc));  // ur (:1754)
-          if (P.forward) { minl = o; maxl = -1; }
-          else if (P.backward) { minl = 0; maxl = o; }
-          else { minl = o - 1; maxl = o + 1; }
+      const int o = P.octave[j];
+      if (has_mp) {
+        const float qx = P.T[0], qy = P.T[1], qz = P.T[2], qw = P.T[3];
+        float ux = __fsub_rn(__fmul_rn(qy, vz), __fmul_rn(qz, vy));
+        float uy = __fsub_rn(__fmul_rn(qz, vx), __fmul_rn(qx, vz));
+        float uz = __fsub_rn(__fmul_rn(qx, vy), __fmul_rn(qy, vx));
+        ux = __fadd_rn(ux, ux); uy = __fadd_rn(uy, uy); uz = __fadd_rn(uz, uz);
+        const float c0 = __fsub_rn(__fmul_rn(qy, uz), __fmul_rn(qz, uy));
+        const float c1 = __fsub_rn(__fmul_rn(qz, ux), __fmul_rn(qx, uz));
+        const float c2 = __fsub_rn(__fmul_rn(qx, uy), __fmul_rn(qy, ux));
+        const float xc = __fadd_rn(__fadd_rn(__fadd_rn(vx, __fmul_rn(qw, ux)), c0), P.T[4]);
+        const float yc = __fadd_rn(__fadd_rn(__fadd_rn(vy, __fmul_rn(qw, uy)), c1), P.T[5]);
+        const float zc = __fadd_rn(__fadd_rn(__fadd_rn(vz, __fmul_rn(qw, uz)), c2), P.T[6]);
+        const float invzc = (float)(1.0 / (double)zc);
+        if (!(invzc < 0)) {
+          const float u = __fadd_rn(__fdiv_rn(__fmul_rn(F.fx, xc), zc), F.cx);
+          const float v = __fadd_rn(__fdiv_rn(__fmul_rn(F.fy, yc), zc), F.cy);
+          if (!(u < F.min_x || u > F.max_x) && !(v < F.min_y || v > F.max_y)) {
+            my_active = true;
+            my_u = u; my_v = v;
+            my_r = __fmul_rn(P.th, F.scale[o]);
+            my_aux = __fsub_rn(u, __fmul_rn(F.bf, invzc));  // ur (:1754)
+            if (P.forward) { my_minl = o; my_maxl = -1; }
+            else if (P.backward) { my_minl = 0; my_maxl = o; }
+            else { my_minl = o - 1; my_maxl = o + 1; }
+          }
         }
       }
     }
+  }
+  const int slot = P.cand_slot;
+  for (int q = 0; q < PC_Q_PER_WARP && j0 + q < P.nq; q++) {
+    const int j = j0 + q;
+    const bool active = __shfl_sync(full, (int)my_active, q) != 0;
+    const float u = __shfl_sync(full, my_u, q), v = __shfl_sync(full, my_v, q), r = __shfl_sync(full, my_r, q),
+                aux = __shfl_sync(full, my_aux, q);
+    const int minl = __shfl_sync(full, my_minl, q), maxl = __shfl_sync(full, my_maxl, q);
     // Frame::GetFeaturesInArea's cell rectangle (Frame.cc:664-686)
     int cx0 = 0, cx1 = -1, cy0 = 0, cy1 = -1;
     if (active) {
@@ -278,84 +296,62 @@ __global__ void __launch_bounds__(PC_WARPS * 32) proj_candidates_kernel(ProjProb
       const uint4* pq = reinterpret_cast<const uint4*>(P.qdesc + (size_t)j * 32);
       qa = pq[0]; qb = pq[1];
     }
-    int cnt = 0, base = 0;
-    // two sweeps over the window: count, then (after the list is placed) write; the first two chunks of the first
-    // column group keep their verdicts (distance << 22 | keypoint) in registers, which covers almost every window
-    int keep0 = -1, keep1 = -1;
-    for (int sweep = 0; sweep < 2; sweep++) {
-      int written = 0;
-      for (int g0 = cx0; g0 <= cx1; g0 += 32) {
-        const int ix = g0 + lane;
-        int s = 0, len = 0;
-        if (ix <= cx1) {
-          s = F.cell_start[ix * GRID_ROWS + cy0];
-          len = F.cell_start[ix * GRID_ROWS + cy1 + 1] - s;
-        }
-        int incl = len;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(full, incl, o); if (lane >= o) incl += t; }
-        const int total = __shfl_sync(full, incl, 31);
-        for (int t0 = 0; t0 < total; t0 += 32) {
-          const bool reg_chunk = g0 == cx0 && t0 < 64;
-          int pick = -1;
-          if (sweep == 1 && reg_chunk) {
-            pick = t0 == 0 ? keep0 : keep1;
-          } else {
-            const int t = t0 + lane;
-            int col = 0;  // first column whose inclusive prefix exceeds t
-#pragma unroll
-            for (int step = 16; step; step >>= 1) {
-              const int pv = __shfl_sync(full, incl, col + step - 1);
-              if (pv <= t) col += step;
-            }
-            const int cs = __shfl_sync(full, s, col), cex = __shfl_sync(full, incl - len, col);
-            if (t < total) {
-              const uint4 rec = F.cell_rec[cs + (t - cex)];
-              const int oc = (int)rec.z, idx = (int)rec.w;
-              bool ok = true;
-              if (check_levels) ok = oc >= minl && !(maxl >= 0 && oc > maxl);
-              if (ok) ok = fabsf(__fsub_rn(__uint_as_float(rec.x), u)) < r && fabsf(__fsub_rn(__uint_as_float(rec.y), v)) < r;
-              if (ok && F.u_right) {
-                const float ur = F.u_right[idx];
-                if (ur > 0 && fabsf(__fsub_rn(aux, ur)) > r) ok = false;
-              }
-              if (ok) {
-                const uint4* pd = reinterpret_cast<const uint4*>(F.desc + (size_t)idx * 32);
-                const uint4 d0 = pd[0], d1 = pd[1];
-                const int dist = __popc(qa.x ^ d0.x) + __popc(qa.y ^ d0.y) + __popc(qa.z ^ d0.z) + __popc(qa.w ^ d0.w) +
-                                 __popc(qb.x ^ d1.x) + __popc(qb.y ^ d1.y) + __popc(qb.z ^ d1.z) + __popc(qb.w ^ d1.w);
-                const bool relevant = dist <= TH_HIGH || (P.kind == 0 && __fmul_rn(P.ratio, (float)dist) < (float)TH_HIGH);
-                if (relevant) pick = (dist << 22) | idx;
-              }
-            }
-            if (sweep == 0 && reg_chunk) { if (t0 == 0) keep0 = pick; else keep1 = pick; }
-          }
-          const unsigned m = __ballot_sync(full, pick >= 0);
-          if (sweep == 0) {
-            cnt += __popc(m);
-          } else {
-            if (pick >= 0) {
-              const int o = base + written + __popc(m & lt);
-              P.cand_idx[o] = pick & 0x3fffff;
-              P.cand_dist[o] = (unsigned short)(pick >> 22);
-            }
-            written += __popc(m);
-          }
-        }
+    const size_t base = (size_t)j * slot;
+    int written = 0;
+    bool overflow = false;
+    for (int g0 = cx0; g0 <= cx1; g0 += 32) {
+      const int ix = g0 + lane;
+      int s = 0, len = 0;
+      if (ix <= cx1) {
+        s = F.cell_start[ix * GRID_ROWS + cy0];
+        len = F.cell_start[ix * GRID_ROWS + cy1 + 1] - s;
       }
-      if (sweep == 0) {
-        if (cnt > 0) {
-          if (lane == 0) base = atomicAdd(P.cand_used, cnt);
-          base = __shfl_sync(full, base, 0);
-          if (base + cnt > P.cand_cap) {  // the host grows the buffer and runs the batch again
-            if (lane == 0) P.result[1] = 1;
-            cnt = 0;
+      int incl = len;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(full, incl, o); if (lane >= o) incl += t; }
+      const int total = __shfl_sync(full, incl, 31);
+      for (int t0 = 0; t0 < total; t0 += 32) {
+        const int t = t0 + lane;
+        int col = 0;  // first column whose inclusive prefix exceeds t
+#pragma unroll
+        for (int step = 16; step; step >>= 1) {
+          const int pv = __shfl_sync(full, incl, col + step - 1);
+          if (pv <= t) col += step;
+        }
+        const int cs = __shfl_sync(full, s, col), cex = __shfl_sync(full, incl - len, col);
+        int pick = -1, dist = 0;
+        if (t < total) {
+          const uint4 rec = F.cell_rec[cs + (t - cex)];
+          const int oc = (int)rec.z, idx = (int)rec.w;
+          bool ok = true;
+          if (check_levels) ok = oc >= minl && !(maxl >= 0 && oc > maxl);
+          if (ok) ok = fabsf(__fsub_rn(__uint_as_float(rec.x), u)) < r && fabsf(__fsub_rn(__uint_as_float(rec.y), v)) < r;
+          if (ok && F.u_right) {
+            const float ur = F.u_right[idx];
+            if (ur > 0 && fabsf(__fsub_rn(aux, ur)) > r) ok = false;
+          }
+          if (ok) {
+            const uint4* pd = reinterpret_cast<const uint4*>(F.desc + (size_t)idx * 32);
+            const uint4 d0 = pd[0], d1 = pd[1];
+            dist = __popc(qa.x ^ d0.x) + __popc(qa.y ^ d0.y) + __popc(qa.z ^ d0.z) + __popc(qa.w ^ d0.w) +
+                   __popc(qb.x ^ d1.x) + __popc(qb.y ^ d1.y) + __popc(qb.z ^ d1.z) + __popc(qb.w ^ d1.w);
+            if (dist <= TH_HIGH || (P.kind == 0 && __fmul_rn(P.ratio, (float)dist) < (float)TH_HIGH)) pick = idx;
           }
         }
-        if (lane == 0) { P.q_off[j] = base; P.q_cnt[j] = cnt; P.q_state[j] = cnt > 0 ? 1 : 0; }
-        if (cnt == 0) break;
+        const unsigned m = __ballot_sync(full, pick >= 0);
+        const int o = written + __popc(m & lt);
+        if (pick >= 0) {
+          if (o < slot) { P.cand_idx[base + o] = pick; P.cand_dist[base + o] = (unsigned short)dist; }
+          else overflow = true;
+        }
+        written += __popc(m);
       }
     }
+    if (__any_sync(full, overflow)) {  // the host grows the slots and runs the batch again
+      if (lane == 0) P.result[1] = 1;
+      written = 0;
+    }
+    if (lane == 0) { P.q_cnt[j] = written; P.q_state[j] = written > 0 ? 1 : 0; }
   }
 }
 
@@ -381,8 +377,8 @@ __device__ __forceinline__ int rot_bin(float a1, float a2) {
   return bin;
 }
 
-// Phase 2+3: resolution rounds, one CTA per problem, one WARP per unresolved point (its list is read 32 entries
-// at a time; a thread-per-point version spent ~10 us per round walking the lists serially).  Round 1 visits every
+// Phase 2+3: resolution rounds, one CTA per problem, one thread per unresolved point (the lists are short after
+// the filtering of phase 1; a warp per point was measured slower: too few chains in flight).  Round 1 visits every
 // point, later rounds only the list of points that were blocked.
 __global__ void __launch_bounds__(1024, 1) proj_resolve_kernel(ProjProblem* probs, int smem_nk) {
   extern __shared__ int rs_dyn[];
@@ -396,11 +392,9 @@ __global__ void __launch_bounds__(1024, 1) proj_resolve_kernel(ProjProblem* prob
     for (int i = threadIdx.x; i < (int)(sizeof(ProjProblem) / 4); i += 1024) dst[i] = src[i];
   }
   __syncthreads();
-  if (P.result[1]) return;  // candidate buffer overflow: host re-runs with a larger one
+  if (P.result[1]) return;  // a candidate slot overflowed: host re-runs with larger ones
   const DevFrame& F = P.F;
-  const int nq = P.nq, nk = F.n;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned full = 0xffffffffu;
+  const int nq = P.nq, nk = F.n, slot = P.cand_slot;
   // per-keypoint state of the rounds (lowest claiming point, taker, octave) in shared memory when it fits: every
   // round is a chain of dependent look-ups into these arrays
   const bool in_smem = nk <= smem_nk;
@@ -427,65 +421,54 @@ __global__ void __launch_bounds__(1024, 1) proj_resolve_kernel(ProjProblem* prob
     if (threadIdx.x == 0) s_nlist[cur ^ 1] = 0;
     __syncthreads();
     // claims: only a candidate within TH_HIGH can be taken by j; free for j = not taken by a lower index
-    for (int i = warp; i < n_cur; i += 32) {
+    for (int i = threadIdx.x; i < n_cur; i += 1024) {
       const int j = first ? i : ulist[cur][i];
       if (first && P.q_state[j] != 1) continue;
-      const int e0 = P.q_off[j], e1 = e0 + P.q_cnt[j];
-      for (int e = e0 + lane; e < e1; e += 32) {
-        if (P.cand_dist[e] > TH_HIGH) continue;
-        const int c = P.cand_idx[e];
+      const size_t e0 = (size_t)j * slot;
+      const int cnt = P.q_cnt[j];
+      for (int t = 0; t < cnt; t++) {
+        if (P.cand_dist[e0 + t] > TH_HIGH) continue;
+        const int c = P.cand_idx[e0 + t];
         if (takenby[c] > j) atomicMin(&minidx[c], j);
       }
     }
     __syncthreads();
-    for (int i = warp; i < n_cur; i += 32) {
+    for (int i = threadIdx.x; i < n_cur; i += 1024) {
       const int j = first ? i : ulist[cur][i];
       if (first && P.q_state[j] != 1) continue;
-      const int e0 = P.q_off[j], cnt = P.q_cnt[j];
-      // the two smallest (distance, list position) keys among the free candidates: the reference's scan keeps the
-      // FIRST candidate of the smallest distance as best and the first of the next (distance, position) as second
-      unsigned k1 = 0xffffffffu, k2 = 0xffffffffu;
+      const size_t e0 = (size_t)j * slot;
+      const int cnt = P.q_cnt[j];
+      // one pass: blocked? and the reference's scan over the candidates that are free for j (a keypoint is skipped
+      // iff it was taken on entry or by a lower-index point)
       bool blocked = false;
-      for (int t = lane; t < cnt; t += 32) {
+      int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+      for (int t = 0; t < cnt; t++) {
         const int c = P.cand_idx[e0 + t];
-        const int tb = takenby[c];
-        if (tb < j) continue;  // taken on entry or by a lower-index point
-        if (minidx[c] < j) blocked = true;  // a lower unresolved point may still take it
-        const unsigned key = ((unsigned)P.cand_dist[e0 + t] << 16) | (unsigned)t;
-        if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
-      }
-      if (__any_sync(full, blocked)) {
-        if (lane == 0) ulist[cur ^ 1][atomicAdd(&s_nlist[cur ^ 1], 1)] = j;
-        continue;
-      }
-#pragma unroll
-      for (int o = 16; o; o >>= 1) {
-        const unsigned o1 = __shfl_xor_sync(full, k1, o), o2 = __shfl_xor_sync(full, k2, o);
-        const unsigned lo = min(k1, o1), hi = max(k1, o1);
-        k1 = lo; k2 = min(hi, min(k2, o2));
-      }
-      if (lane != 0) continue;
-      int state = 0;
-      if (k1 != 0xffffffffu) {
-        const int bestDist = (int)(k1 >> 16), bestIdx = P.cand_idx[e0 + (int)(k1 & 0xffffu)];
-        bool accept = bestDist <= TH_HIGH;
-        if (accept && P.kind == 0 && k2 != 0xffffffffu) {
-          // ratio only when best and second best share the level (:123-128)
-          const int c2 = P.cand_idx[e0 + (int)(k2 & 0xffffu)];
-          const int l1 = in_smem ? (int)oct8[bestIdx] : F.keys[bestIdx].octave;
-          const int l2 = in_smem ? (int)oct8[c2] : F.keys[c2].octave;
-          if (l1 == l2 && (float)bestDist > __fmul_rn(P.ratio, (float)(k2 >> 16))) accept = false;
+        if (takenby[c] < j) continue;
+        if (minidx[c] < j) { blocked = true; break; }  // a lower unresolved point may still take it
+        const int dist = P.cand_dist[e0 + t];
+        if (dist < bestDist) {
+          bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel;
+          bestLevel = in_smem ? (int)oct8[c] : F.keys[c].octave; bestIdx = c;
+        } else if (P.kind == 0 && dist < bestDist2) {
+          bestLevel2 = in_smem ? (int)oct8[c] : F.keys[c].octave; bestDist2 = dist;
         }
-        if (accept) {
-          P.assign[bestIdx] = j;
-          P.acc_kp[j] = bestIdx;
-          if (P.has_obs[j]) state = 2;  // the keypoint is closed to later points (ORBmatcher.cc:88-90 / :1748-1750)
-          atomicAdd(&s_nmatch, 1);
-          if (P.kind == 1 && P.check_ori) {
-            const int bin = rot_bin(P.angle[j], F.keys[bestIdx].angle);
-            P.acc_bin[j] = bin;
-            atomicAdd(&s_hist[bin], 1);
-          }
+      }
+      if (blocked) { ulist[cur ^ 1][atomicAdd(&s_nlist[cur ^ 1], 1)] = j; continue; }
+      bool accept = bestDist <= TH_HIGH;
+      // ratio only when best and second best share the level (:123-128)
+      if (accept && P.kind == 0 && bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(P.ratio, (float)bestDist2))
+        accept = false;
+      int state = 0;
+      if (accept) {
+        P.assign[bestIdx] = j;
+        P.acc_kp[j] = bestIdx;
+        if (P.has_obs[j]) state = 2;  // the keypoint is closed to later points (ORBmatcher.cc:88-90 / :1748-1750)
+        atomicAdd(&s_nmatch, 1);
+        if (P.kind == 1 && P.check_ori) {
+          const int bin = rot_bin(P.angle[j], F.keys[bestIdx].angle);
+          P.acc_bin[j] = bin;
+          atomicAdd(&s_hist[bin], 1);
         }
       }
       P.q_state[j] = (uint8_t)state;
@@ -654,7 +637,7 @@ struct Matcher {
   double last_ms = 0;
   // initial candidate budget per query, grows on overflow (ORB_B200_MATCH_BUDGET: tests start it small to take
   // the overflow paths)
-  size_t cand_per_query = getenv("ORB_B200_MATCH_BUDGET") ? std::max(1, atoi(getenv("ORB_B200_MATCH_BUDGET"))) : 48;
+  size_t cand_per_query = getenv("ORB_B200_MATCH_BUDGET") ? std::max(1, atoi(getenv("ORB_B200_MATCH_BUDGET"))) : 24;
   // asynchronous mode (device-resident problems only): one batch may be in flight per handle
   bool async_mode = false, pending = false;
   int pending_count = 0;
@@ -838,7 +821,7 @@ static int launch_projection(Matcher& M, std::vector<ProjProblem>& P, size_t in_
     // ---- scratch + outputs
     size_t sbytes = 0, obytes = 0;
     for (int k = 0; k < count; k++) {
-      const size_t nq = P[k].nq, nk = P[k].F.n, cc = std::max<size_t>(nq * M.cand_per_query, 1024);
+      const size_t nq = P[k].nq, nk = P[k].F.n, cc = std::max<size_t>(nq * M.cand_per_query, 16);
       sbytes += 256 * 16 + (GRID_CELLS + 1 + nk) * 4 + nk * 16 + nq * (4 * 4 + 1 + 8) + 4 + cc * 6 + nk * 8;
       obytes += 256 * 2 + nk * 4 + 8;
     }
@@ -852,17 +835,16 @@ static int launch_projection(Matcher& M, std::vector<ProjProblem>& P, size_t in_
     std::vector<size_t> out_off(count);
     for (int k = 0; k < count; k++) {
       ProjProblem& p = P[k];
-      const size_t nq = p.nq, nk = p.F.n, cc = std::max<size_t>(nq * M.cand_per_query, 1024);
+      const size_t nq = p.nq, nk = p.F.n, cc = std::max<size_t>(nq * M.cand_per_query, 16);
       max_nq = std::max(max_nq, p.nq);
       p.F.cell_start = carve_dev<int>(M.scratch, GRID_CELLS + 1);
       p.F.cell_items = carve_dev<int>(M.scratch, nk);
       p.F.cell_rec = carve_dev<uint4>(M.scratch, nk);
-      p.q_cnt = carve_dev<int>(M.scratch, nq); p.q_off = carve_dev<int>(M.scratch, nq);
-      p.cand_used = carve_dev<int>(M.scratch, 1); p.ulist = carve_dev<int>(M.scratch, 2 * nq);
+      p.q_cnt = carve_dev<int>(M.scratch, nq); p.ulist = carve_dev<int>(M.scratch, 2 * nq);
       p.q_state = carve_dev<uint8_t>(M.scratch, nq);
       p.acc_kp = carve_dev<int>(M.scratch, nq); p.acc_bin = carve_dev<int>(M.scratch, nq);
       p.cand_idx = carve_dev<int>(M.scratch, cc); p.cand_dist = carve_dev<unsigned short>(M.scratch, cc);
-      p.cand_cap = (int)cc;
+      p.cand_slot = (int)M.cand_per_query;
       p.minidx = carve_dev<int>(M.scratch, nk); p.takenby = carve_dev<int>(M.scratch, nk);
       if (on_device) {
         if (assign_out) p.assign = assign_out[k];  // (a retry keeps the pointer staged by the first launch)
