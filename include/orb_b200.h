@@ -437,7 +437,8 @@ void vocab_destroy(orb_vocab* h);
  * BowVector:     bow_ids[cap_words] ascending WordId, bow_vals[cap_words] (L1-normalised), *n_words.
  * FeatureVector: fv_node_ids[cap_words] ascending NodeId, fv_ptr[cap_words + 1], fv_idx[n] feature indices
  *                (ascending inside a node), *n_fv_nodes.  cap_words >= n is always enough.
- * n <= 8192 features per call (the per-frame sort runs in one CTA's shared memory; ORB_E_CAPACITY beyond).
+ * Any n: up to 8192 features the per-frame sort runs in one CTA's shared memory, larger frames (monocular
+ * initialisation: 5 x nFeatures) sort in global-memory scratch.
  * Returns the number of features that contributed (weight > 0), or ORB_E_*. */
 int bow_transform(orb_vocab* h, const uint8_t* desc, int n, int levelsup, int32_t* bow_ids, double* bow_vals,
                   int32_t* n_words, int32_t* fv_node_ids, int32_t* fv_ptr, int32_t* fv_idx, int32_t* n_fv_nodes,

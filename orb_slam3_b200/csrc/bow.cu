@@ -55,6 +55,16 @@ __global__ void __launch_bounds__(BOW_ASM_THREADS) bow_assemble_kernel(int n, in
   bow_assemble(be, n, P, word, weight, nid, kw, kn, flag, o);
 }
 
+// Frames with more keys than fit in shared memory (monocular initialisation extracts 5 x nFeatures, Tracking.cc:2536):
+// the same source on global-memory scratch (L2-resident; slower per stage, no limit on n)
+__global__ void __launch_bounds__(BOW_ASM_THREADS) bow_assemble_global_kernel(int n, int P, const int* word, const double* weight,
+                                                                              const int* nid, BowFrameOut o,
+                                                                              unsigned long long* keys) {
+  __shared__ int s_ints[48];
+  CtaBackend be{s_ints};
+  bow_assemble(be, n, P, word, weight, nid, keys, keys + P, reinterpret_cast<int*>(keys + 2 * (size_t)P), o);
+}
+
 static int next_pow2(int n) { int p = 2; while (p < n) p <<= 1; return p; }
 
 static int check_vocab(const orb_vocab_view* v) {
@@ -77,6 +87,8 @@ struct Vocab {
   int *d_word = nullptr, *d_nid = nullptr, *d_bow_ids = nullptr, *d_fv_nodes = nullptr, *d_fv_ptr = nullptr,
       *d_fv_idx = nullptr, *d_counts = nullptr;
   double *d_weight = nullptr, *d_bow_vals = nullptr, *d_norm = nullptr;
+  unsigned long long* d_keys = nullptr;  // global-memory sort scratch of oversized frames (P * 20 bytes)
+  size_t keys_bytes = 0;
   int *h_ints = nullptr;   // pinned: counts[3] | bow_ids | fv_nodes | fv_ptr | fv_idx
   double* h_vals = nullptr;
   long long launches = 0;
@@ -93,7 +105,8 @@ struct Vocab {
   void release_scratch() {
     cudaFree(d_desc); cudaFree(d_word); cudaFree(d_nid); cudaFree(d_bow_ids); cudaFree(d_fv_nodes);
     cudaFree(d_fv_ptr); cudaFree(d_fv_idx); cudaFree(d_counts); cudaFree(d_weight); cudaFree(d_bow_vals);
-    cudaFree(d_norm); cudaFreeHost(h_ints); cudaFreeHost(h_vals);
+    cudaFree(d_norm); cudaFree(d_keys); cudaFreeHost(h_ints); cudaFreeHost(h_vals);
+    d_keys = nullptr; keys_bytes = 0;
     d_desc = nullptr; d_word = d_nid = d_bow_ids = d_fv_nodes = d_fv_ptr = d_fv_idx = d_counts = nullptr;
     d_weight = d_bow_vals = d_norm = nullptr; h_ints = nullptr; h_vals = nullptr;
     cap = 0;
@@ -166,7 +179,13 @@ struct Vocab {
     if (rc) return rc;
     const int P = next_pow2(n);
     const size_t smem = (size_t)P * 20;
-    if (smem > 200 * 1024) { set_last_error("bow_transform: more than 8192 features per frame"); return ORB_E_CAPACITY; }
+    const bool in_smem = smem <= 200 * 1024;  // up to 8192 features per frame
+    if (!in_smem && smem > keys_bytes) {
+      cudaFree(d_keys);
+      d_keys = nullptr; keys_bytes = 0;
+      CUDA_TRYB(cudaMalloc(&d_keys, smem));
+      keys_bytes = smem;
+    }
     cudaStream_t s = stream;
     if (wait_on && wait_on != s) {  // descriptors produced on another stream
       CUDA_TRYB(cudaEventRecord(ev0, wait_on));
@@ -185,8 +204,12 @@ struct Vocab {
       bow_descend_kernel<<<(n + 127) / 128, 128, 0, s>>>(V, dd, n, levelsup, d_word, d_weight, d_nid);
       launches++;
     }
-    CUDA_TRYB(raise_dynamic_smem((const void*)bow_assemble_kernel, smem, device));
-    bow_assemble_kernel<<<1, BOW_ASM_THREADS, smem, s>>>(n, P, d_word, d_weight, d_nid, o);
+    if (in_smem) {
+      CUDA_TRYB(raise_dynamic_smem((const void*)bow_assemble_kernel, smem, device));
+      bow_assemble_kernel<<<1, BOW_ASM_THREADS, smem, s>>>(n, P, d_word, d_weight, d_nid, o);
+    } else {
+      bow_assemble_global_kernel<<<1, BOW_ASM_THREADS, 0, s>>>(n, P, d_word, d_weight, d_nid, o, d_keys);
+    }
     launches++;
     CUDA_TRYB(cudaEventRecord(ev1, s));
     CUDA_TRYB(cudaGetLastError());

@@ -807,7 +807,7 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
   // the latency of its dependent chains, not by throughput).
   const int fg = lane >> 2, ft = lane & 3;
   constexpr int ZR_OFF = WIN * WIN_P;  // zr follows the ring: one index space for matrix rows and the rhs row
-  constexpr int TG = 3;  // tiles in flight per warp (90 tiles of a 96-row window = 15 warps x 2 groups of 3)
+  constexpr int TG = 4;  // tiles in flight per warp (90 tiles of a 96-row window = 12 warps x 2 groups of 4)
   auto update_run = [&](int t_begin, int t_end, int r0, int nr) {
     if (t_begin >= t_end) return;
     int tt = tile_ij[t_begin];
@@ -845,6 +845,20 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
         if (ok1[u]) A[i1[u]] = c1[u];
       }
     }
+  };
+  // the tile of the next pivot block, on the critical path: no tile bookkeeping at all
+  auto update_tile0 = [&](int r0, int nr) {
+    const int wj = 2 * ft;
+    const double a0 = -Lt[ft * WIN_LP + fg], a1 = -Lt[(ft + 4) * WIN_LP + fg];
+    const double b0 = LDt[ft * WIN_LP + fg], b1 = LDt[(ft + 4) * WIN_LP + fg];
+    const int rowoff = (fg >= nr) ? ZR_OFF : ((r0 + fg) % WIN) * WIN_P;
+    const bool ok0 = fg <= nr && wj < nr && wj <= fg, ok1 = fg <= nr && wj + 1 < nr && wj + 1 <= fg;
+    const int i0 = rowoff + (r0 + wj) % WIN, i1 = rowoff + (r0 + wj + 1) % WIN;
+    double c0 = ok0 ? A[i0] : 0.0, c1 = ok1 ? A[i1] : 0.0;
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a0), "d"(b0));
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a1), "d"(b1));
+    if (ok0) A[i0] = c0;
+    if (ok1) A[i1] = c1;
   };
   load_rows(0, rlast[0], 0, 0, WIN_THREADS / 32);
   __syncthreads();
@@ -896,17 +910,18 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
     {
       const int T8 = (nr + 1 + 7) >> 3;
       const int ntile = T8 * (T8 + 1) / 2;
-      constexpr int UW = WIN_THREADS / 32 - 1;
-      const int per = (ntile - 1 + UW - 1) / UW;  // tiles 1 .. ntile-1 in runs over the other warps
+      // warp 0 shares its scheduler with warps 4, 8, 12: they stay idle here so that the pivot chain issues alone
+      constexpr int UW = WIN_THREADS / 32 - WIN_THREADS / 128;
       if (warp == 0) {
         if (pre > R) load_rows(R + 1, pre, r0, 0, 1);
-        update_run(0, 1, r0, nr);
+        update_tile0(r0, nr);
         __syncwarp();
         tick(2);
         if (tid == 0 && more) pivot(p + 1);
         tick(6);
-      } else {
-        const int tb = 1 + (warp - 1) * per;
+      } else if (warp & 3) {
+        const int per = (ntile - 1 + UW - 1) / UW;  // tiles 1 .. ntile-1 in runs over the update warps
+        const int tb = 1 + (warp - 1 - (warp >> 2)) * per;
         update_run(tb, min(tb + per, ntile), r0, nr);
         tick(2);
       }

@@ -36,7 +36,7 @@ struct LiaCtaBackend {
   __device__ int tid() const { return threadIdx.x; }
   __device__ int nthreads() const { return blockDim.x; }
   __device__ void sync() { __syncthreads(); }
-  __device__ void add(double* p, double v) { atomicAdd(p, v); }
+  __device__ void count(double* p) { atomicAdd(p, 1.0); }  // failure counter: integer-valued, order-independent
   __device__ double sum(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -130,7 +130,10 @@ int lia_solve(orb_lia* h, const lia_graph_view* g, double* kf_out, double* mp_ou
                o_JPa = c.take(36 * NI), o_bias = c.take(24 * NI), o_dT = c.take(4 * NI), o_last = c.take(NI),
                o_info = c.take(648 * std::max<size_t>(NI, 1)), o_infoG = c.take(72 * std::max<size_t>(NI, 1)),
                o_infoA = c.take(72 * std::max<size_t>(NI, 1)), o_pose = c.take(192 * K), o_vel = c.take(24 * K),
-               o_bg = c.take(24 * K), o_ba = c.take(24 * K), o_pt = c.take(24 * std::max<size_t>(L, 1));
+               o_bg = c.take(24 * K), o_ba = c.take(24 * K), o_pt = c.take(24 * std::max<size_t>(L, 1)),
+               o_kfptr = c.take(4 * (K + 1)), o_kfed = c.take(4 * Hs.kf_edges.size()), o_pptr = c.take(4 * Hs.pair_ptr.size()),
+               o_pea = c.take(4 * Hs.pair_ea.size()), o_peb = c.take(4 * Hs.pair_eb.size()), o_free = c.take(4 * std::max<size_t>(Hs.free_kf.size(), 1)),
+               o_icol = c.take(4 * Hs.i_color.size());
   const size_t in_bytes = c.off;
   const size_t o_poseb = c.take(192 * K), o_velb = c.take(24 * K), o_bgb = c.take(24 * K), o_bab = c.take(24 * K),
                o_ptb = c.take(24 * std::max<size_t>(L, 1)), o_H = c.take(8 * np * np), o_b = c.take(8 * np),
@@ -138,7 +141,8 @@ int lia_solve(orb_lia* h, const lia_graph_view* g, double* kf_out, double* mp_ou
                o_W = c.take(144 * std::max<size_t>(E, 1)), o_Dinv = c.take(72 * std::max<size_t>(L, 1)), o_S = c.take(8 * np * np),
                o_bs = c.take(8 * np), o_x = c.take(8 * (np + 3 * L)), o_verr = c.take(24 * std::max<size_t>(E, 1)),
                o_ierr = c.take(120 * std::max<size_t>(NI, 1)), o_Dg = c.take(8 * np), o_chi2 = c.take(8 * std::max<size_t>(E, 1)),
-               o_dpos = c.take(std::max<size_t>(E, 1)), o_stats = c.take(64);
+               o_dpos = c.take(std::max<size_t>(E, 1)), o_stats = c.take(64),
+               o_Hpe = c.take(336 * std::max<size_t>(E, 1)), o_Ye = c.take(144 * std::max<size_t>(E, 1));
   const size_t total = c.off + 16;
   if (total > S.arena_bytes) {
     cudaFree(S.d_arena);
@@ -158,6 +162,10 @@ int lia_solve(orb_lia* h, const lia_graph_view* g, double* kf_out, double* mp_ou
   put(o_last, g->i_last, NI); put(o_info, Hs.info.data(), 648 * NI); put(o_infoG, Hs.infoG.data(), 72 * NI);
   put(o_infoA, Hs.infoA.data(), 72 * NI); put(o_pose, Hs.pose.data(), 192 * K); put(o_vel, g->kf_vel, 24 * K);
   put(o_bg, g->kf_bg, 24 * K); put(o_ba, g->kf_ba, 24 * K); put(o_pt, g->mp_pos, 24 * L);
+  put(o_kfptr, Hs.kf_ptr.data(), 4 * (K + 1)); put(o_kfed, Hs.kf_edges.data(), 4 * Hs.kf_edges.size());
+  put(o_pptr, Hs.pair_ptr.data(), 4 * Hs.pair_ptr.size()); put(o_pea, Hs.pair_ea.data(), 4 * Hs.pair_ea.size());
+  put(o_peb, Hs.pair_eb.data(), 4 * Hs.pair_eb.size()); put(o_free, Hs.free_kf.data(), 4 * Hs.free_kf.size());
+  put(o_icol, Hs.i_color.data(), 4 * Hs.i_color.size());
   uint8_t* base = (uint8_t*)S.d_arena;
   cudaStream_t s = S.stream;
   CUDA_TRYI(cudaMemcpyAsync(base, img.data(), in_bytes, cudaMemcpyHostToDevice, s));
@@ -181,6 +189,9 @@ int lia_solve(orb_lia* h, const lia_graph_view* g, double* kf_out, double* mp_ou
   D.Dinv = AT(double, o_Dinv); D.S = AT(double, o_S); D.bs = AT(double, o_bs); D.x = AT(double, o_x);
   D.verr = AT(double, o_verr); D.ierr = AT(double, o_ierr); D.Dg = AT(double, o_Dg);
   D.chi2_out = AT(double, o_chi2); D.depth_pos_out = AT(uint8_t, o_dpos); D.stats = AT(double, o_stats);
+  D.kf_ptr = AT(int, o_kfptr); D.kf_edges = AT(int, o_kfed); D.pair_ptr = AT(int, o_pptr); D.pair_ea = AT(int, o_pea);
+  D.pair_eb = AT(int, o_peb); D.free_kf = AT(int, o_free); D.i_color = AT(int, o_icol);
+  D.Hpe = AT(double, o_Hpe); D.Ye = AT(double, o_Ye);
 #undef AT
   CUDA_TRYI(cudaEventRecord(S.ev0, s));
   lia_kernel<<<1, LIA_THREADS, 0, s>>>(D);

@@ -6,7 +6,10 @@
 // for the motion-only problem.  The window is small by construction (<= 25 keyframes x 15 unknowns), so
 // one CTA owns it; a batch of windows would be a grid of CTAs.
 //
-// Written against a Backend (thread index, barrier, atomic add on doubles, block sum) so that the same
+// Every sum is formed in a fixed order (per-edge terms are stored and gathered by the owner of the destination;
+// inertial edges are processed colour by colour), so a solve is bitwise reproducible -- no floating-point atomics.
+//
+// Written against a Backend (thread index, barrier, block sum, a counter add for the failure flag) so that the same
 // source runs single-threaded on the host (lia_debug_host) where the CPU tests hold it against the oracle.
 //
 // Follows (paths relative to the reference): G2oTypes.cc:172-219 (Project / ProjectStereo / isDepthPositive /
@@ -32,6 +35,11 @@ struct LiaDev {
   double fx, fy, cx, cy, bf;
   const int *e_kf, *e_mp; const uint8_t* e_stereo; const double* e_obs; const float* e_is2;
   const int *lm_ptr, *lm_edges;            // CSR: edges of every map point
+  // fixed-order accumulation (host-built, lia_host.h): edges of every keyframe, the (ea, eb) edge pairs of every
+  // ordered pair of free poses in map-point order, the free keyframes, and a colouring of the inertial edges such
+  // that edges of one colour share no keyframe
+  const int *kf_ptr, *kf_edges, *pair_ptr, *pair_ea, *pair_eb, *free_kf, *i_color;
+  int n_free, n_colors;
   const int *i_kf1, *i_kf2;
   const float *i_dR, *i_dV, *i_dP, *i_JRg, *i_JVg, *i_JVa, *i_JPg, *i_JPa, *i_bias, *i_dT;
   const uint8_t* i_last;
@@ -41,6 +49,7 @@ struct LiaDev {
   double *vel, *bg, *ba, *pt, *vel_bak, *bg_bak, *ba_bak, *pt_bak;
   // system
   double *H, *b, *Hll, *bl, *W, *Dinv, *S, *bs, *x, *verr, *ierr, *Dg;
+  double *Hpe, *Ye;                        // per visual edge: its 6x6 pose block + 6 gradient entries; W Dinv (6x3)
   // results
   double* chi2_out; uint8_t* depth_pos_out; double* stats;  // stats[6]: iterations, trials, err, err_end, lambda, np
   double huber_mono_delta, huber_mono_dsqr, huber_stereo_delta, huber_stereo_dsqr, huber_in_delta, huber_in_dsqr;
@@ -196,7 +205,8 @@ ORB_HD void l_inertial_error(const LiaDev& D, int i) {
   for (int q = 0; q < 3; q++) { r[9 + q] = D.bg[3 * k2 + q] - D.bg[3 * k1 + q]; r[12 + q] = D.ba[3 * k2 + q] - D.ba[3 * k1 + q]; }
 }
 
-// H += w Ja^T O Jb (and its transpose block), b -= w Ja^T O r, through the backend's atomic add
+// H += w Ja^T O Jb (and its transpose block), b -= w Ja^T O r.  Plain read-modify-write: the caller guarantees that
+// no other thread touches the blocks of these vertices (inertial edges are processed one colour at a time)
 #ifdef __CUDACC__
 #pragma nv_exec_check_disable
 #endif
@@ -211,8 +221,8 @@ ORB_HD void l_add_block(BE& be, const LiaDev& D, int oa, int da, const double* J
         for (int q = 0; q < d; q++) t += O[p * d + q] * Jb[q * db_ + j];
         s += Ja[p * da + i] * t;
       }
-      be.add(&D.H[(size_t)(oa + i) * D.np + ob + j], w * s);
-      if (oa != ob) be.add(&D.H[(size_t)(ob + j) * D.np + oa + i], w * s);
+      D.H[(size_t)(oa + i) * D.np + ob + j] += w * s;
+      if (oa != ob) D.H[(size_t)(ob + j) * D.np + oa + i] += w * s;
     }
 }
 #ifdef __CUDACC__
@@ -223,7 +233,7 @@ ORB_HD void l_add_b(BE& be, const LiaDev& D, int oa, int da, const double* Ja, c
   for (int i = 0; i < da; i++) {
     double s = 0;
     for (int p = 0; p < d; p++) { double t = 0; for (int q = 0; q < d; q++) t += O[p * d + q] * r[q]; s += Ja[p * da + i] * t; }
-    be.add(&D.b[oa + i], -w * s);
+    D.b[oa + i] += -w * s;
   }
 }
 
@@ -267,11 +277,12 @@ ORB_HD void l_build_point(BE& be, const LiaDev& D, int l) {
     double* We = D.W + 18 * (size_t)e;
     const int o = D.ip[k];
     if (o >= 0) {
+      double* He = D.Hpe + 42 * (size_t)e;  // gathered per keyframe by l_gather_poses
       for (int i = 0; i < 6; i++) {
-        for (int j = 0; j < 6; j++) { double a = 0; for (int p = 0; p < d; p++) a += B[p * 6 + i] * ws * B[p * 6 + j]; be.add(&D.H[(size_t)(o + i) * D.np + o + j], a); }
+        for (int j = 0; j < 6; j++) { double a = 0; for (int p = 0; p < d; p++) a += B[p * 6 + i] * ws * B[p * 6 + j]; He[i * 6 + j] = a; }
         double a = 0;
         for (int p = 0; p < d; p++) a += B[p * 6 + i] * (s * r[p]);
-        be.add(&D.b[o + i], -r1 * a);
+        He[36 + i] = -r1 * a;
         for (int j = 0; j < 3; j++) { double a2 = 0; for (int p = 0; p < d; p++) a2 += B[p * 6 + i] * ws * A[p * 3 + j]; We[i * 3 + j] = a2; }
       }
     } else {
@@ -363,6 +374,80 @@ ORB_HD void l_build_inertial(BE& be, const LiaDev& D, int i) {
   }
 }
 
+// Pose blocks of the visual edges: entry `ent` (36 of H, 6 of b) of free keyframe f = the sum over the keyframe's
+// edges in input order.  One owner per destination, so H / b start from these sums (they were zeroed).
+#ifdef __CUDACC__
+#pragma nv_exec_check_disable
+#endif
+template <class BE>
+ORB_HD void l_gather_poses(BE& be, const LiaDev& D) {
+  const int tid = be.tid(), nt = be.nthreads();
+  for (int item = tid; item < D.n_free * 42; item += nt) {
+    const int f = item / 42, ent = item - f * 42, k = D.free_kf[f], o = D.ip[k];
+    double sum = 0;
+    for (int q = D.kf_ptr[k]; q < D.kf_ptr[k + 1]; q++) sum += D.Hpe[42 * (size_t)D.kf_edges[q] + ent];
+    if (ent < 36) D.H[(size_t)(o + ent / 6) * D.np + o + ent % 6] = sum;
+    else D.b[o + ent - 36] = sum;
+  }
+}
+
+// Schur complement of the map points onto the pose side, fixed order:
+//   (1) per map point: Dinv = (Hll + lambda I)^-1 and Y_e = W_e Dinv for its edges;
+//   (2) per (free keyframe, row): bs -= sum over the keyframe's edges of Y_e b_l;
+//       per (ordered pair of free keyframes, i, j): S -= sum over the pair's edge pairs (map-point order) of Y_ea W_eb^T.
+// S and bs hold Hpp + lambda I and b on entry.  Barriers inside.
+#ifdef __CUDACC__
+#pragma nv_exec_check_disable
+#endif
+template <class BE>
+ORB_HD void l_schur(BE& be, const LiaDev& D, double lambda) {
+  const int tid = be.tid(), nt = be.nthreads(), np = D.np;
+  for (int l = tid; l < D.n_mp; l += nt) {
+    double Hl[9], Di[9];
+    for (int c = 0; c < 9; c++) Hl[c] = D.Hll[9 * (size_t)l + c];
+    Hl[0] += lambda; Hl[4] += lambda; Hl[8] += lambda;
+    const bool ok = l_inv3(Hl, Di);
+    if (!ok) {
+      be.count(&D.stats[6]);
+      for (int c = 0; c < 9; c++) Di[c] = 0;
+    }
+    for (int c = 0; c < 9; c++) D.Dinv[9 * (size_t)l + c] = Di[c];
+    for (int qa = D.lm_ptr[l]; qa < D.lm_ptr[l + 1]; qa++) {
+      const int ea = D.lm_edges[qa];
+      if (D.ip[D.e_kf[ea]] < 0) continue;
+      const double* Wa = D.W + 18 * (size_t)ea;
+      double* Y = D.Ye + 18 * (size_t)ea;
+      for (int i = 0; i < 6; i++) for (int j = 0; j < 3; j++) Y[i * 3 + j] = Wa[i * 3] * Di[j] + Wa[i * 3 + 1] * Di[3 + j] + Wa[i * 3 + 2] * Di[6 + j];
+    }
+  }
+  be.sync();
+  for (int item = tid; item < D.n_free * 6; item += nt) {
+    const int f = item / 6, i = item - f * 6, k = D.free_kf[f];
+    double sum = 0;
+    for (int q = D.kf_ptr[k]; q < D.kf_ptr[k + 1]; q++) {
+      const int e = D.kf_edges[q];
+      const double* Y = D.Ye + 18 * (size_t)e + 3 * i;
+      const double* bll = D.bl + 3 * (size_t)D.e_mp[e];
+      sum += Y[0] * bll[0] + Y[1] * bll[1] + Y[2] * bll[2];
+    }
+    D.bs[D.ip[k] + i] -= sum;
+  }
+  for (int item = tid; item < D.n_free * D.n_free * 36; item += nt) {
+    const int key = item / 36, ij = item - key * 36, i = ij / 6, j = ij - i * 6;
+    const int q0 = D.pair_ptr[key], q1 = D.pair_ptr[key + 1];
+    if (q0 == q1) continue;
+    double sum = 0;
+    for (int q = q0; q < q1; q++) {
+      const double* Y = D.Ye + 18 * (size_t)D.pair_ea[q] + 3 * i;
+      const double* Wb = D.W + 18 * (size_t)D.pair_eb[q] + 3 * j;
+      sum += Y[0] * Wb[0] + Y[1] * Wb[1] + Y[2] * Wb[2];
+    }
+    const int oa = D.ip[D.free_kf[key / D.n_free]], ob = D.ip[D.free_kf[key % D.n_free]];
+    D.S[(size_t)(oa + i) * np + ob + j] -= sum;
+  }
+  be.sync();
+}
+
 // errors of every edge, then the robust chi2 (block sum)
 #ifdef __CUDACC__
 #pragma nv_exec_check_disable
@@ -437,8 +522,14 @@ ORB_HD void lia_solve_core(BE& be, const LiaDev& D) {
     for (int i = tid; i < np; i += nt) D.b[i] = 0;
     be.sync();
     for (int l = tid; l < D.n_mp; l += nt) l_build_point(be, D, l);
-    for (int i = tid; i < D.n_inertial; i += nt) l_build_inertial(be, D, i);
     be.sync();
+    l_gather_poses(be, D);
+    be.sync();
+    for (int c = 0; c < D.n_colors; c++) {  // edges of one colour touch disjoint vertex blocks
+      for (int i = tid; i < D.n_inertial; i += nt)
+        if (D.i_color[i] == c) l_build_inertial(be, D, i);
+      be.sync();
+    }
     double rho = 0;
     int qmax = 0;
     do {
@@ -451,30 +542,7 @@ ORB_HD void lia_solve_core(BE& be, const LiaDev& D) {
       for (int i = tid; i < np; i += nt) D.bs[i] = D.b[i];
       if (tid == 0) D.stats[6] = 0;  // failure flag
       be.sync();
-      for (int l = tid; l < D.n_mp; l += nt) {
-        double Hl[9], Di[9];
-        for (int c = 0; c < 9; c++) Hl[c] = D.Hll[9 * (size_t)l + c];
-        Hl[0] += lambda; Hl[4] += lambda; Hl[8] += lambda;
-        if (!l_inv3(Hl, Di)) { be.add(&D.stats[6], 1.0); continue; }
-        for (int c = 0; c < 9; c++) D.Dinv[9 * (size_t)l + c] = Di[c];
-        const double* bll = D.bl + 3 * (size_t)l;
-        for (int qa = D.lm_ptr[l]; qa < D.lm_ptr[l + 1]; qa++) {
-          const int ea = D.lm_edges[qa], oa = D.ip[D.e_kf[ea]];
-          if (oa < 0) continue;
-          const double* Wa = D.W + 18 * (size_t)ea;
-          double Y[18];
-          for (int i = 0; i < 6; i++) for (int j = 0; j < 3; j++) Y[i * 3 + j] = Wa[i * 3] * Di[j] + Wa[i * 3 + 1] * Di[3 + j] + Wa[i * 3 + 2] * Di[6 + j];
-          for (int i = 0; i < 6; i++) be.add(&D.bs[oa + i], -(Y[i * 3] * bll[0] + Y[i * 3 + 1] * bll[1] + Y[i * 3 + 2] * bll[2]));
-          for (int qb = D.lm_ptr[l]; qb < D.lm_ptr[l + 1]; qb++) {
-            const int eb = D.lm_edges[qb], ob = D.ip[D.e_kf[eb]];
-            if (ob < 0) continue;
-            const double* Wb = D.W + 18 * (size_t)eb;
-            for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++)
-              be.add(&D.S[(size_t)(oa + i) * np + ob + j], -(Y[i * 3] * Wb[j * 3] + Y[i * 3 + 1] * Wb[j * 3 + 1] + Y[i * 3 + 2] * Wb[j * 3 + 2]));
-          }
-        }
-      }
-      be.sync();
+      l_schur(be, D, lambda);
       // dense LDL^T of S (lower triangle in place, D in Dg), right-looking, columns in order
       bool ok2 = D.stats[6] == 0;
       be.sync();
@@ -556,7 +624,7 @@ struct LiaHostBackend {
   int tid() const { return 0; }
   int nthreads() const { return 1; }
   void sync() {}
-  void add(double* p, double v) { *p += v; }
+  void count(double* p) { *p += 1.0; }
   double sum(double v) { return v; }
 };
 

@@ -60,6 +60,8 @@ inline void jacobi_eigen(std::vector<double>& A, int n, std::vector<double>& V) 
 
 struct LiaHost {
   std::vector<int> ip, iv, ig, ia, lm_ptr, lm_edges;
+  std::vector<int> kf_ptr, kf_edges, pair_ptr, pair_ea, pair_eb, free_kf, i_color;  // fixed-order accumulation (lia_core.h)
+  int n_colors = 0;
   std::vector<double> info, infoG, infoA, pose, e_obs;
   int np = 0;
 };
@@ -106,6 +108,56 @@ inline int lia_prepare(const lia_graph_view* g, LiaHost& Hs, std::string& err) {
     std::vector<int> cur(Hs.lm_ptr.begin(), Hs.lm_ptr.end() - 1);
     for (int e = 0; e < g->n_edges; e++) Hs.lm_edges[cur[g->e_mp[e]]++] = e;
   }
+  // ---- structures of the fixed-order sums: edges per keyframe (input order), free keyframes, edge pairs per ordered
+  //      pair of free keyframes (map points ascending, the pairs of one point in list order), inertial edge colours
+  Hs.kf_ptr.assign(K + 1, 0);
+  for (int e = 0; e < g->n_edges; e++) Hs.kf_ptr[g->e_kf[e] + 1]++;
+  for (int k = 0; k < K; k++) Hs.kf_ptr[k + 1] += Hs.kf_ptr[k];
+  Hs.kf_edges.resize(std::max(g->n_edges, 1));
+  {
+    std::vector<int> cur(Hs.kf_ptr.begin(), Hs.kf_ptr.end() - 1);
+    for (int e = 0; e < g->n_edges; e++) Hs.kf_edges[cur[g->e_kf[e]]++] = e;
+  }
+  std::vector<int> frank(K, -1);
+  Hs.free_kf.clear();
+  for (int k = 0; k < K; k++)
+    if (Hs.ip[k] >= 0) { frank[k] = (int)Hs.free_kf.size(); Hs.free_kf.push_back(k); }
+  const int F = (int)Hs.free_kf.size();
+  Hs.pair_ptr.assign((size_t)F * F + 1, 0);
+  for (int pass = 0; pass < 2; pass++) {
+    std::vector<int> cur;
+    if (pass == 1) {
+      for (size_t i = 0; i < (size_t)F * F; i++) Hs.pair_ptr[i + 1] += Hs.pair_ptr[i];
+      Hs.pair_ea.resize(std::max(Hs.pair_ptr[(size_t)F * F], 1)); Hs.pair_eb.resize(Hs.pair_ea.size());
+      cur.assign(Hs.pair_ptr.begin(), Hs.pair_ptr.end() - 1);
+    }
+    for (int l = 0; l < g->n_mp; l++)
+      for (int qa = Hs.lm_ptr[l]; qa < Hs.lm_ptr[l + 1]; qa++) {
+        const int ea = Hs.lm_edges[qa], fa = frank[g->e_kf[ea]];
+        if (fa < 0) continue;
+        for (int qb = Hs.lm_ptr[l]; qb < Hs.lm_ptr[l + 1]; qb++) {
+          const int eb = Hs.lm_edges[qb], fb = frank[g->e_kf[eb]];
+          if (fb < 0) continue;
+          const size_t key = (size_t)fa * F + fb;
+          if (pass == 0) Hs.pair_ptr[key + 1]++;
+          else { Hs.pair_ea[cur[key]] = ea; Hs.pair_eb[cur[key]] = eb; cur[key]++; }
+        }
+      }
+  }
+  Hs.i_color.assign(std::max(g->n_inertial, 1), 0);
+  Hs.n_colors = 0;
+  {
+    std::vector<std::vector<uint8_t>> used;  // used[c][k]: colour c already has an edge at keyframe k
+    for (int i = 0; i < g->n_inertial; i++) {
+      const int k1 = g->i_kf1[i], k2 = g->i_kf2[i];
+      int c = 0;
+      while (c < (int)used.size() && (used[c][k1] || used[c][k2])) c++;
+      if (c == (int)used.size()) used.emplace_back(K, 0);
+      used[c][k1] = used[c][k2] = 1;
+      Hs.i_color[i] = c;
+    }
+    Hs.n_colors = (int)used.size();
+  }
   const int nI = g->n_inertial;
   Hs.info.assign(81 * (size_t)std::max(nI, 1), 0.0); Hs.infoG.assign(9 * (size_t)std::max(nI, 1), 0.0);
   Hs.infoA.assign(9 * (size_t)std::max(nI, 1), 0.0);
@@ -133,6 +185,7 @@ inline int lia_prepare(const lia_graph_view* g, LiaHost& Hs, std::string& err) {
 inline void lia_fill_scalars(const lia_graph_view* g, const LiaHost& Hs, LiaDev& D) {
   D.n_kf = g->n_kf; D.n_mp = g->n_mp; D.n_edges = g->n_edges; D.n_inertial = g->n_inertial; D.np = Hs.np;
   D.iterations = g->iterations; D.lambda_init = g->lambda_init;
+  D.n_free = (int)Hs.free_kf.size(); D.n_colors = Hs.n_colors;
   for (int i = 0; i < 9; i++) D.Rcb[i] = g->Rcb[i];
   for (int i = 0; i < 3; i++) { D.tcb[i] = g->tcb[i]; D.tbc[i] = g->tbc[i]; }
   D.fx = g->fx; D.fy = g->fy; D.cx = g->cx; D.cy = g->cy; D.bf = g->bf;
@@ -157,7 +210,7 @@ inline void lia_write_out(const lia_graph_view* g, const double* pose, const dou
 // All state / system / result buffers of one solve in host memory, wired into a LiaDev
 struct LiaHostBuffers {
   std::vector<double> pose, pose_bak, vel, bg, ba, pt, vel_bak, bg_bak, ba_bak, pt_bak, H, b, Hll, bl, W, Dinv, Sm, bs, x, verr,
-      ierr, Dg, chi, st;
+      ierr, Dg, chi, st, Hpe, Ye;
   std::vector<uint8_t> dp;
   LiaDev D;
   LiaHostBuffers(const lia_graph_view* g, const LiaHost& Hs) {
@@ -170,11 +223,13 @@ struct LiaHostBuffers {
     vel_bak.resize(3 * K); bg_bak.resize(3 * K); ba_bak.resize(3 * K); pt_bak.resize(3 * L1);
     H.resize(np * np); b.resize(np); Hll.resize(9 * L1); bl.resize(3 * L1); W.resize(18 * E1); Dinv.resize(9 * L1);
     Sm.resize(np * np); bs.resize(np); x.assign(np + 3 * L, 0.0); verr.resize(3 * E1); ierr.resize(15 * N1); Dg.resize(np);
-    chi.resize(E1); st.assign(8, 0.0); dp.resize(E1);
+    chi.resize(E1); st.assign(8, 0.0); dp.resize(E1); Hpe.assign(42 * E1, 0.0); Ye.assign(18 * E1, 0.0);
     lia_fill_scalars(g, Hs, D);
     D.kf_fixed = g->kf_fixed; D.kf_has_imu = g->kf_has_imu; D.ip = Hs.ip.data(); D.iv = Hs.iv.data(); D.ig = Hs.ig.data(); D.ia = Hs.ia.data();
     D.e_kf = g->e_kf; D.e_mp = g->e_mp; D.e_stereo = g->e_stereo; D.e_obs = g->e_obs; D.e_is2 = g->e_inv_sigma2;
     D.lm_ptr = Hs.lm_ptr.data(); D.lm_edges = Hs.lm_edges.data();
+    D.kf_ptr = Hs.kf_ptr.data(); D.kf_edges = Hs.kf_edges.data(); D.pair_ptr = Hs.pair_ptr.data(); D.pair_ea = Hs.pair_ea.data();
+    D.pair_eb = Hs.pair_eb.data(); D.free_kf = Hs.free_kf.data(); D.i_color = Hs.i_color.data();
     D.i_kf1 = g->i_kf1; D.i_kf2 = g->i_kf2; D.i_dR = g->i_dR; D.i_dV = g->i_dV; D.i_dP = g->i_dP; D.i_JRg = g->i_JRg; D.i_JVg = g->i_JVg;
     D.i_JVa = g->i_JVa; D.i_JPg = g->i_JPg; D.i_JPa = g->i_JPa; D.i_bias = g->i_bias; D.i_dT = g->i_dT; D.i_last = g->i_last;
     D.info = Hs.info.data(); D.infoG = Hs.infoG.data(); D.infoA = Hs.infoA.data();
@@ -182,7 +237,7 @@ struct LiaHostBuffers {
     D.vel_bak = vel_bak.data(); D.bg_bak = bg_bak.data(); D.ba_bak = ba_bak.data(); D.pt_bak = pt_bak.data();
     D.H = H.data(); D.b = b.data(); D.Hll = Hll.data(); D.bl = bl.data(); D.W = W.data(); D.Dinv = Dinv.data(); D.S = Sm.data();
     D.bs = bs.data(); D.x = x.data(); D.verr = verr.data(); D.ierr = ierr.data(); D.Dg = Dg.data();
-    D.chi2_out = chi.data(); D.depth_pos_out = dp.data(); D.stats = st.data();
+    D.chi2_out = chi.data(); D.depth_pos_out = dp.data(); D.stats = st.data(); D.Hpe = Hpe.data(); D.Ye = Ye.data();
   }
 };
 

@@ -61,8 +61,8 @@ void transform_on_device(ORBVocabulary* voc, const cv::Mat& descriptors, DBoW2::
                          nodes.data(), ptr.data(), idx.data(), &n_nodes, n);
   }
   if (used == ORB_E_CAPACITY) {
-    // more features than one launch sorts in shared memory (8192): monocular initialisation extracts
-    // 5 x nFeatures (Tracking.cc:2536).  Rare and off the per-frame path: use the reference's own transform.
+    // caller-side capacity (cannot happen with cap_words = n; oversized frames such as the 5 x nFeatures of
+    // monocular initialisation, Tracking.cc:2536, are handled on the device): use the reference's own transform.
     std::vector<cv::Mat> vCurrentDesc = Converter::toDescriptorVector(descriptors);
     voc->transform(vCurrentDesc, bow, fv, 4);
     return;

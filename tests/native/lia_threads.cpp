@@ -1,7 +1,8 @@
 // CPU stand-in for "many threads run lia_kernel": the product's LocalInertialBA source (csrc/lia_core.h) executed by T
-// real threads with a pthread barrier as __syncthreads() and CAS loops as fp64 atomicAdd, built with
-// -fsanitize=thread.  ThreadSanitizer then checks what a single-threaded host run cannot: that every pair of
-// conflicting accesses in the kernel body is separated by a barrier or is an atomic add.  The graph comes
+// real threads with a pthread barrier as __syncthreads(), built with -fsanitize=thread.  ThreadSanitizer then checks
+// what a single-threaded host run cannot: that every pair of conflicting accesses in the kernel body is separated by
+// a barrier -- the accumulation into H / b / S is plain read-modify-write by one owner per destination (per-edge
+// terms gathered in a fixed order, inertial edges colour by colour), the only atomic is a failure counter.  The graph comes
 // from a flat binary file written by tests/test_lia_threads.py; results are compared with the
 // single-threaded run of the same source.
 //   g++ -std=c++17 -O1 -g -fsanitize=thread -pthread -I<repo>/include tests/native/lia_threads.cpp
@@ -28,10 +29,10 @@ struct ThreadsBackend {
   int tid() const { return t; }
   int nthreads() const { return T; }
   void sync() { pthread_barrier_wait(&sh->bar); }
-  void add(double* p, double v) {  // atomicAdd(double*, double)
+  void count(double* p) {  // atomicAdd(p, 1.0): the only atomic left (integer-valued failure counter)
     std::atomic_ref<double> a(*p);
     double old = a.load(std::memory_order_relaxed);
-    while (!a.compare_exchange_weak(old, old + v, std::memory_order_relaxed)) {}
+    while (!a.compare_exchange_weak(old, old + 1.0, std::memory_order_relaxed)) {}
   }
   double sum(double v) {
     sh->partial[t] = v;

@@ -11,7 +11,8 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("k,L,levelsup,n", [(10, 4, 2, 2000), (8, 3, 4, 777), (10, 5, 4, 1200), (3, 6, 3, 2),
-                                             (10, 4, 2, 2048), (10, 4, 2, 3000)])
+                                             (10, 4, 2, 2048), (10, 4, 2, 3000),
+                                             (10, 5, 4, 8192), (10, 5, 4, 10000)])  # 10000: 5 x nFeatures at monocular initialisation
 def test_host_descriptors_bitwise(oracle, k, L, levelsup, n):
     from orb_slam3_b200.bow import ORBVocabulary
     voc = scenes.synth_vocabulary(k, L, seed=7)
