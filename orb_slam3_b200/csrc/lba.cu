@@ -753,8 +753,20 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
       const int f = first[i];
       const double* Mi = M + (size_t)i * n;
       double* Ai = A + (i % WIN) * WIN_P;
-      for (int j = c0 + lane; j <= i; j += 32) Ai[j % WIN] = j >= f ? Mi[j] : 0.0;
-      if (lane == 0) zr[i % WIN] = M[(size_t)n * n + i];
+      // a row of the window has at most WIN columns: four loads per lane, all in flight together
+      double v[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int j = c0 + lane + 32 * q;
+        v[q] = (j <= i && j >= f) ? Mi[j] : 0.0;
+      }
+      const double zv = lane == 0 ? M[(size_t)n * n + i] : 0.0;
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int j = c0 + lane + 32 * q;
+        if (j <= i) Ai[j % WIN] = v[q];
+      }
+      if (lane == 0) zr[i % WIN] = zv;
     }
   };
   // pivot block of panel p, one thread, registers only: factors rows/cols [k0, k0+nb) of the ring, leaves L (strict
@@ -807,7 +819,7 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
   // the latency of its dependent chains, not by throughput).
   const int fg = lane >> 2, ft = lane & 3;
   constexpr int ZR_OFF = WIN * WIN_P;  // zr follows the ring: one index space for matrix rows and the rhs row
-  constexpr int TG = 4;  // tiles in flight per warp (90 tiles of a 96-row window = 12 warps x 2 groups of 4)
+  constexpr int TG = 3;  // tiles in flight per warp (90 tiles of a 96-row window = 15 warps x 2 groups of 3)
   auto update_run = [&](int t_begin, int t_end, int r0, int nr) {
     if (t_begin >= t_end) return;
     int tt = tile_ij[t_begin];
@@ -910,8 +922,7 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
     {
       const int T8 = (nr + 1 + 7) >> 3;
       const int ntile = T8 * (T8 + 1) / 2;
-      // warp 0 shares its scheduler with warps 4, 8, 12: they stay idle here so that the pivot chain issues alone
-      constexpr int UW = WIN_THREADS / 32 - WIN_THREADS / 128;
+      constexpr int UW = WIN_THREADS / 32 - 1;
       if (warp == 0) {
         if (pre > R) load_rows(R + 1, pre, r0, 0, 1);
         update_tile0(r0, nr);
@@ -919,9 +930,9 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
         tick(2);
         if (tid == 0 && more) pivot(p + 1);
         tick(6);
-      } else if (warp & 3) {
+      } else {
         const int per = (ntile - 1 + UW - 1) / UW;  // tiles 1 .. ntile-1 in runs over the update warps
-        const int tb = 1 + (warp - 1 - (warp >> 2)) * per;
+        const int tb = 1 + (warp - 1) * per;
         update_run(tb, min(tb + per, ntile), r0, nr);
         tick(2);
       }
@@ -964,35 +975,35 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
   __syncthreads();
   constexpr int BS_THREADS = WIN;  // one thread per window column (WIN_ROWS < WIN)
   if (tid >= BS_THREADS) return;
-  double nxt[WPB], Pc[WPB];
-  int jm_next = 0;
-  auto fetch = [&](int bq) {
+  // rows of L are fetched two steps ahead (one global-memory round trip per step would otherwise sit on the chain):
+  // two register sets, by block parity
+  double rowsE[WPB], rowsO[WPB], Pc[WPB];
+  int jmE = 0, jmO = 0;
+  auto fetch = [&](int bq, double (&rows)[WPB], int& jmr) {
     const int k0 = bq * WPB, nb = min(WPB, n - k0);
-    int jm = k0;
+    int jmv = k0;
 #pragma unroll
     for (int r = 0; r < WPB; r++)
-      if (r < nb) jm = min(jm, first[k0 + r]);
-    jm_next = jm;
-    const int j = jm + tid;
+      if (r < nb) jmv = min(jmv, first[k0 + r]);
+    jmr = jmv;
+    const int j = jmv + tid;
 #pragma unroll
-    for (int r = 0; r < WPB; r++) nxt[r] = (r < nb && j < k0) ? M[(size_t)(k0 + r) * n + j] : 0.0;
+    for (int r = 0; r < WPB; r++) rows[r] = (r < nb && j < k0) ? M[(size_t)(k0 + r) * n + j] : 0.0;
   };
   // P[j][c] = sum_{r <= c} L[k0+r][j] G[r][c],  G[r][c] = Linv[c][r], G[c][c] = 1
-  auto transform = [&](int bq) {
+  auto transform = [&](int bq, const double (&rows)[WPB]) {
     const double* pb = pblk + bq * 28;
 #pragma unroll
     for (int c = 0; c < WPB; c++) {
-      double t = nxt[c];
+      double t = rows[c];
 #pragma unroll
-      for (int r = 0; r < c; r++) t += nxt[r] * pb[c * (c - 1) / 2 + r];
+      for (int r = 0; r < c; r++) t += rows[r] * pb[c * (c - 1) / 2 + r];
       Pc[c] = t;
     }
   };
-  fetch(npan - 1);
-  transform(npan - 1);
-  int jm = jm_next;
-  if (npan > 1) fetch(npan - 2);
-  for (int bq = npan - 1; bq >= 0; bq--) {
+  int jm = 0;
+  // one step; (rows, jmr) is the register set of block bq - 1 (and, after its use, of block bq - 3)
+  auto step = [&](int bq, double (&rows)[WPB], int& jmr) {
     const int k0 = bq * WPB, nb = min(WPB, n - k0);
     // ---- the chain
     double a[WPB];
@@ -1003,7 +1014,7 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
       const double s1 = Pc[4] * a[4] + Pc[5] * a[5] + Pc[6] * a[6] + Pc[7] * a[7];
       acc[jm + tid] -= s0 + s1;
     }
-    // ---- off the chain: this step's unknowns, the next step's row of P, the loads of the step after it
+    // ---- off the chain: this step's unknowns, the next step's row of P, the loads of the step after the next
     if (tid < nb) {
       const double* pb = pblk + bq * 28;
       double xv = 0.0;
@@ -1015,11 +1026,23 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
       x[k0 + tid] = xv;
     }
     if (bq > 0) {
-      transform(bq - 1);
-      jm = jm_next;
-      if (bq > 1) fetch(bq - 2);
+      transform(bq - 1, rows);
+      jm = jmr;
+      if (bq > 2) fetch(bq - 3, rows, jmr);
     }
     asm volatile("bar.sync 1, %0;" ::"n"(BS_THREADS) : "memory");
+  };
+  {
+    const int b0 = npan - 1;
+    const bool b0_even = (b0 & 1) == 0;
+    if (b0_even) fetch(b0, rowsE, jmE); else fetch(b0, rowsO, jmO);
+    if (b0 > 0) { if (b0_even) fetch(b0 - 1, rowsO, jmO); else fetch(b0 - 1, rowsE, jmE); }
+    if (b0_even) { transform(b0, rowsE); jm = jmE; } else { transform(b0, rowsO); jm = jmO; }
+    if (b0 > 1) { if (b0_even) fetch(b0 - 2, rowsE, jmE); else fetch(b0 - 2, rowsO, jmO); }
+    for (int bq = b0; bq >= 0; bq--) {
+      if (bq & 1) step(bq, rowsE, jmE);  // block bq - 1 is even
+      else step(bq, rowsO, jmO);
+    }
   }
   if (PROF) {
     tick(4);
