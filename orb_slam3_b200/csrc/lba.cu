@@ -97,9 +97,23 @@ __global__ void __launch_bounds__(128) lin_kernel(LbaDev D) {
   if (l >= D.n_mp) return;
   const double X[3] = {D.pts[3 * (size_t)l], D.pts[3 * (size_t)l + 1], D.pts[3 * (size_t)l + 2]};
   double Hl[6] = {0, 0, 0, 0, 0, 0}, bl[3] = {0, 0, 0}, chi = 0;
-  for (int e = D.lm_ptr[l]; e < D.lm_ptr[l + 1]; e++) {
-    const int k = D.e_kf[e];
-    const double* P = D.pose + 7 * (size_t)k;
+  // the keyframe index -> pose hop is two dependent global loads: the pose of the NEXT edge is fetched while this
+  // edge is linearised (ncu: long-scoreboard stalls were 60 % of all samples at 16 warps per SM)
+  const int e_begin = D.lm_ptr[l], e_end = D.lm_ptr[l + 1];
+  int k_next = e_begin < e_end ? D.e_kf[e_begin] : 0;
+  double Pn[7];
+#pragma unroll
+  for (int c = 0; c < 7; c++) Pn[c] = D.pose[7 * (size_t)k_next + c];
+  for (int e = e_begin; e < e_end; e++) {
+    const int k = k_next;
+    double P[7];
+#pragma unroll
+    for (int c = 0; c < 7; c++) P[c] = Pn[c];
+    if (e + 1 < e_end) {
+      k_next = D.e_kf[e + 1];
+#pragma unroll
+      for (int c = 0; c < 7; c++) Pn[c] = D.pose[7 * (size_t)k_next + c];
+    }
     DQuat q = {P[0], P[1], P[2], P[3]};
     double Xc[3], r[3];
     q_rot(q, X, Xc);
@@ -819,42 +833,53 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
   // the latency of its dependent chains, not by throughput).
   const int fg = lane >> 2, ft = lane & 3;
   constexpr int ZR_OFF = WIN * WIN_P;  // zr follows the ring: one index space for matrix rows and the rhs row
-  constexpr int TG = 3;  // tiles in flight per warp (90 tiles of a 96-row window = 15 warps x 2 groups of 3)
+  constexpr int TG = 4;  // interior tiles in flight per warp
+  auto mma2 = [&](double& c0, double& c1, double a0, double a1, double b0, double b1) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a0), "d"(b0));
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a1), "d"(b1));
+  };
   auto update_run = [&](int t_begin, int t_end, int r0, int nr) {
     if (t_begin >= t_end) return;
-    int tt = tile_ij[t_begin];
-    int ti = tt >> 8, tj = tt & 255;
-    for (int tb = t_begin; tb < t_end; tb += TG) {
-      int i0[TG], i1[TG];
-      bool ok0[TG], ok1[TG];
-      double a0[TG], a1[TG], b0[TG], b1[TG], c0[TG], c1[TG];
+    const int tt = tile_ij[t_begin];
+    int ti = tt >> 8, tj = tt & 255, t = t_begin;
+    while (t < t_end) {
+      const int wi = 8 * ti + fg;
+      const double a0 = -Lt[ft * WIN_LP + wi], a1 = -Lt[(ft + 4) * WIN_LP + wi];
+      const int rowoff = (wi >= nr) ? ZR_OFF : ((r0 + wi) % WIN) * WIN_P;  // the rhs row has no column of its own
+      // tiles strictly below the diagonal in a row block that lies inside the window need no element predicates
+      // and share the row operands: TG of them at a time, all loads before the first DMMA
+      if (8 * ti + 7 <= nr) {
+        while (tj + TG <= ti && t + TG <= t_end) {
+          int i0[TG], i1[TG];
+          double b0[TG], b1[TG], c0[TG], c1[TG];
 #pragma unroll
-      for (int u = 0; u < TG; u++) {
-        const bool live = tb + u < t_end;
-        const int wi = 8 * ti + fg, wj = 8 * tj + 2 * ft;
-        a0[u] = -Lt[ft * WIN_LP + wi]; a1[u] = -Lt[(ft + 4) * WIN_LP + wi];
-        b0[u] = LDt[ft * WIN_LP + 8 * tj + fg]; b1[u] = LDt[(ft + 4) * WIN_LP + 8 * tj + fg];
-        const int rowoff = (wi >= nr) ? ZR_OFF : ((r0 + wi) % WIN) * WIN_P;  // the rhs row has no column of its own
-        ok0[u] = live && wi <= nr && wj < nr && wj <= wi;
-        ok1[u] = live && wi <= nr && wj + 1 < nr && wj + 1 <= wi;
-        i0[u] = rowoff + (r0 + wj) % WIN;
-        i1[u] = rowoff + (r0 + wj + 1) % WIN;
-        if (tj == ti) { ti++; tj = 0; } else tj++;
+          for (int u = 0; u < TG; u++) {
+            const int cj = 8 * (tj + u);
+            b0[u] = LDt[ft * WIN_LP + cj + fg]; b1[u] = LDt[(ft + 4) * WIN_LP + cj + fg];
+            i0[u] = rowoff + (r0 + cj + 2 * ft) % WIN;
+            i1[u] = rowoff + (r0 + cj + 2 * ft + 1) % WIN;
+            c0[u] = A[i0[u]]; c1[u] = A[i1[u]];
+          }
+#pragma unroll
+          for (int u = 0; u < TG; u++) mma2(c0[u], c1[u], a0, a1, b0[u], b1[u]);
+#pragma unroll
+          for (int u = 0; u < TG; u++) { A[i0[u]] = c0[u]; A[i1[u]] = c1[u]; }
+          tj += TG; t += TG;
+        }
+        if (t >= t_end) break;
       }
-#pragma unroll
-      for (int u = 0; u < TG; u++) { c0[u] = ok0[u] ? A[i0[u]] : 0.0; c1[u] = ok1[u] ? A[i1[u]] : 0.0; }
-#pragma unroll
-      for (int u = 0; u < TG; u++)
-        asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-            : "+d"(c0[u]), "+d"(c1[u]) : "d"(a0[u]), "d"(b0[u]));
-#pragma unroll
-      for (int u = 0; u < TG; u++)
-        asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-            : "+d"(c0[u]), "+d"(c1[u]) : "d"(a1[u]), "d"(b1[u]));
-#pragma unroll
-      for (int u = 0; u < TG; u++) {
-        if (ok0[u]) A[i0[u]] = c0[u];
-        if (ok1[u]) A[i1[u]] = c1[u];
+      // one tile, fully predicated (diagonal tiles, the last row block, the tail of a run)
+      {
+        const int wj = 8 * tj + 2 * ft;
+        const double b0 = LDt[ft * WIN_LP + 8 * tj + fg], b1 = LDt[(ft + 4) * WIN_LP + 8 * tj + fg];
+        const bool ok0 = wi <= nr && wj < nr && wj <= wi, ok1 = wi <= nr && wj + 1 < nr && wj + 1 <= wi;
+        const int i0 = rowoff + (r0 + wj) % WIN, i1 = rowoff + (r0 + wj + 1) % WIN;
+        double c0 = ok0 ? A[i0] : 0.0, c1 = ok1 ? A[i1] : 0.0;
+        mma2(c0, c1, a0, a1, b0, b1);
+        if (ok0) A[i0] = c0;
+        if (ok1) A[i1] = c1;
+        if (tj == ti) { ti++; tj = 0; } else tj++;
+        t++;
       }
     }
   };
@@ -922,7 +947,8 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
     {
       const int T8 = (nr + 1 + 7) >> 3;
       const int ntile = T8 * (T8 + 1) / 2;
-      constexpr int UW = WIN_THREADS / 32 - 1;
+      // warp 0 shares its scheduler with warps 4, 8, 12: they stay idle here so that the pivot chain issues alone
+      constexpr int UW = WIN_THREADS / 32 - WIN_THREADS / 128;
       if (warp == 0) {
         if (pre > R) load_rows(R + 1, pre, r0, 0, 1);
         update_tile0(r0, nr);
@@ -930,9 +956,9 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
         tick(2);
         if (tid == 0 && more) pivot(p + 1);
         tick(6);
-      } else {
+      } else if (warp & 3) {
         const int per = (ntile - 1 + UW - 1) / UW;  // tiles 1 .. ntile-1 in runs over the update warps
-        const int tb = 1 + (warp - 1) * per;
+        const int tb = 1 + (warp - 1 - (warp >> 2)) * per;
         update_run(tb, min(tb + per, ntile), r0, nr);
         tick(2);
       }
@@ -943,15 +969,20 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
   // ---- L^T x = z (z = row n of M, already scaled by 1/D), 8 unknowns per step, four warps, one named barrier per
   //      step.  With G = L_bb^-T (the inverse of the step's unit-triangular pivot block) the step is
   //        x_b = G acc_b,   acc_j -= sum_c P[j][c] acc_b[c],   P = L_panel^T G,
-  //      so the chain from one step to the next is: read acc_b, 8 multiply-adds, write acc_j, barrier.  Everything
-  //      else is off the chain: the inverses of all pivot blocks are formed up front (one thread per block, staged
-  //      in the dead ring), a thread owns one column j of the step's window, has the next step's 8 entries of L in
-  //      flight and turns them into its row of P while it waits.
+  //      so the chain from one step to the next is: read acc_b, 8 multiply-adds, write acc_j, barrier.  A warp
+  //      issues roughly one instruction every four cycles here (one warp per scheduler, dependent code), so the
+  //      step is as fast as its instruction count: the inverses of all pivot blocks and the window start of every
+  //      block are formed up front (one thread per block, staged in the dead ring), x_b = G acc_b is evaluated for
+  //      all blocks after the loop (acc_b is final once its step is done), the rows of L are fetched two steps
+  //      ahead through a running pointer and turned into the thread's row of P while it waits.
   double* acc = A;            // [n]
-  double* pblk = A + n;       // [npan][28]: Linv[c][r], r < c, at c(c-1)/2 + r   (n + 28 npan <= WIN * WIN_P: host-checked)
+  double* pblk = A + n;       // [npan][28]: Linv[c][r], r < c, at c(c-1)/2 + r   (n + 29 npan <= WIN * WIN_P: host-checked)
+  int* jmb = reinterpret_cast<int*>(pblk + (size_t)npan * 28);  // [npan] first column of the block's row window
   for (int i = tid; i < n; i += WIN_THREADS) acc[i] = M[(size_t)n * n + i];
   for (int bq = tid; bq < npan; bq += WIN_THREADS) {
-    const int k0 = bq * WPB;
+    const int k0 = bq * WPB, nb = min(WPB, n - k0);
+    int jmv = k0;
+    for (int r = 0; r < nb; r++) jmv = min(jmv, first[k0 + r]);
     double Lq[WPB][WPB], Li[WPB][WPB];
 #pragma unroll
     for (int c = 1; c < WPB; c++)
@@ -971,78 +1002,68 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
     for (int c = 1; c < WPB; c++)
 #pragma unroll
       for (int r = 0; r < c; r++) pblk[bq * 28 + c * (c - 1) / 2 + r] = Li[c][r];
+    jmb[bq] = jmv;  // (after the reads of `first`: jmb may alias nothing, it lives in the ring)
   }
   __syncthreads();
   constexpr int BS_THREADS = WIN;  // one thread per window column (WIN_ROWS < WIN)
-  if (tid >= BS_THREADS) return;
-  // rows of L are fetched two steps ahead (one global-memory round trip per step would otherwise sit on the chain):
-  // two register sets, by block parity
-  double rowsE[WPB], rowsO[WPB], Pc[WPB];
-  int jmE = 0, jmO = 0;
-  auto fetch = [&](int bq, double (&rows)[WPB], int& jmr) {
-    const int k0 = bq * WPB, nb = min(WPB, n - k0);
-    int jmv = k0;
+  if (tid < BS_THREADS) {
+    double rowsE[WPB], rowsO[WPB], Pc[WPB];  // rows of even / odd blocks, in flight two steps ahead
+    auto fetch = [&](int bq, double (&rows)[WPB]) {
+      const int k0 = bq * WPB, nb = min(WPB, n - k0), j = jmb[bq] + tid;
+      const double* src = M + (size_t)k0 * n + j;
 #pragma unroll
-    for (int r = 0; r < WPB; r++)
-      if (r < nb) jmv = min(jmv, first[k0 + r]);
-    jmr = jmv;
-    const int j = jmv + tid;
-#pragma unroll
-    for (int r = 0; r < WPB; r++) rows[r] = (r < nb && j < k0) ? M[(size_t)(k0 + r) * n + j] : 0.0;
-  };
-  // P[j][c] = sum_{r <= c} L[k0+r][j] G[r][c],  G[r][c] = Linv[c][r], G[c][c] = 1
-  auto transform = [&](int bq, const double (&rows)[WPB]) {
-    const double* pb = pblk + bq * 28;
-#pragma unroll
-    for (int c = 0; c < WPB; c++) {
-      double t = rows[c];
-#pragma unroll
-      for (int r = 0; r < c; r++) t += rows[r] * pb[c * (c - 1) / 2 + r];
-      Pc[c] = t;
-    }
-  };
-  int jm = 0;
-  // one step; (rows, jmr) is the register set of block bq - 1 (and, after its use, of block bq - 3)
-  auto step = [&](int bq, double (&rows)[WPB], int& jmr) {
-    const int k0 = bq * WPB, nb = min(WPB, n - k0);
-    // ---- the chain
-    double a[WPB];
-#pragma unroll
-    for (int c = 0; c < WPB; c++) a[c] = c < nb ? acc[k0 + c] : 0.0;
-    if (jm + tid < k0) {
-      const double s0 = Pc[0] * a[0] + Pc[1] * a[1] + Pc[2] * a[2] + Pc[3] * a[3];
-      const double s1 = Pc[4] * a[4] + Pc[5] * a[5] + Pc[6] * a[6] + Pc[7] * a[7];
-      acc[jm + tid] -= s0 + s1;
-    }
-    // ---- off the chain: this step's unknowns, the next step's row of P, the loads of the step after the next
-    if (tid < nb) {
+      for (int r = 0; r < WPB; r++) rows[r] = (r < nb && j < k0) ? src[(size_t)r * n] : 0.0;
+    };
+    // P[j][c] = sum_{r <= c} L[k0+r][j] G[r][c],  G[r][c] = Linv[c][r], G[c][c] = 1
+    auto transform = [&](int bq, const double (&rows)[WPB]) {
       const double* pb = pblk + bq * 28;
-      double xv = 0.0;
 #pragma unroll
       for (int c = 0; c < WPB; c++) {
-        const double g = tid < c ? pb[c * (c - 1) / 2 + tid] : (tid == c ? 1.0 : 0.0);  // G[tid][c] = Linv[c][tid]
-        xv += g * a[c];
+        double t = rows[c];
+#pragma unroll
+        for (int r = 0; r < c; r++) t += rows[r] * pb[c * (c - 1) / 2 + r];
+        Pc[c] = t;
       }
-      x[k0 + tid] = xv;
-    }
-    if (bq > 0) {
-      transform(bq - 1, rows);
-      jm = jmr;
-      if (bq > 2) fetch(bq - 3, rows, jmr);
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(BS_THREADS) : "memory");
-  };
-  {
+    };
+    // one step; `rows` is the register set of block bq - 1 (and, after its use, of block bq - 3)
+    auto step = [&](int bq, double (&rows)[WPB]) {
+      const int k0 = bq * WPB;
+      const int j = jmb[bq] + tid;
+      // ---- the chain (only the last block can be short: its missing slots read as zero)
+      if (j < k0) {
+        double ab[WPB];
+#pragma unroll
+        for (int c = 0; c < WPB; c++) ab[c] = (k0 + c < n) ? acc[k0 + c] : 0.0;
+        const double s0 = Pc[0] * ab[0] + Pc[1] * ab[1] + Pc[2] * ab[2] + Pc[3] * ab[3];
+        const double s1 = Pc[4] * ab[4] + Pc[5] * ab[5] + Pc[6] * ab[6] + Pc[7] * ab[7];
+        acc[j] -= s0 + s1;
+      }
+      // ---- off the chain: the next step's row of P, the loads of the step after the next
+      if (bq > 0) {
+        transform(bq - 1, rows);
+        if (bq > 2) fetch(bq - 3, rows);
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(BS_THREADS) : "memory");
+    };
     const int b0 = npan - 1;
     const bool b0_even = (b0 & 1) == 0;
-    if (b0_even) fetch(b0, rowsE, jmE); else fetch(b0, rowsO, jmO);
-    if (b0 > 0) { if (b0_even) fetch(b0 - 1, rowsO, jmO); else fetch(b0 - 1, rowsE, jmE); }
-    if (b0_even) { transform(b0, rowsE); jm = jmE; } else { transform(b0, rowsO); jm = jmO; }
-    if (b0 > 1) { if (b0_even) fetch(b0 - 2, rowsE, jmE); else fetch(b0 - 2, rowsO, jmO); }
+    if (b0_even) fetch(b0, rowsE); else fetch(b0, rowsO);
+    if (b0 > 0) { if (b0_even) fetch(b0 - 1, rowsO); else fetch(b0 - 1, rowsE); }
+    if (b0_even) transform(b0, rowsE); else transform(b0, rowsO);
+    if (b0 > 1) { if (b0_even) fetch(b0 - 2, rowsE); else fetch(b0 - 2, rowsO); }
     for (int bq = b0; bq >= 0; bq--) {
-      if (bq & 1) step(bq, rowsE, jmE);  // block bq - 1 is even
-      else step(bq, rowsO, jmO);
+      if (bq & 1) step(bq, rowsE);  // block bq - 1 is even
+      else step(bq, rowsO);
     }
+  }
+  __syncthreads();
+  // x_b = G acc_b for every block at once: G[r][c] = Linv[c][r] (c > r), 1 on the diagonal
+  for (int i = tid; i < n; i += WIN_THREADS) {
+    const int bq = i / WPB, r = i - bq * WPB, k0 = bq * WPB, nb = min(WPB, n - k0);
+    const double* pb = pblk + bq * 28;
+    double xv = acc[i];
+    for (int c = r + 1; c < nb; c++) xv += pb[c * (c - 1) / 2 + r] * acc[k0 + c];
+    x[i] = xv;
   }
   if (PROF) {
     tick(4);
@@ -1560,8 +1581,8 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
     for (int r = 0; r < nb; r++) jmin = std::min(jmin, env_first[k0 + r]);
     win_rows_max = std::max(win_rows_max, std::max(R - k0 + 1, k0 - jmin + nb));
   }
-  // envelope tables (4.5 bytes per unknown) share the shared memory; the back-substitution keeps n + 3.5 n doubles in the ring
-  const bool win_ok = win_rows_max <= WIN_ROWS && n <= 3600;
+  // envelope tables (4.5 bytes per unknown) share the shared memory; the back-substitution keeps n + 29 n / 8 doubles in the ring
+  const bool win_ok = win_rows_max <= WIN_ROWS && n <= 3400;
   static const char* ldlt_env = getenv("ORB_B200_LDLT");  // "dense" | "sky" | "win" | unset = automatic
   bool use_sky = sky_rows_max <= SKY_WMAX - 4 && n <= 32 * SKY_WMAX && sky_flops <= 6.0e7;
   if (ldlt_env && !strcmp(ldlt_env, "dense")) use_sky = false;
