@@ -67,6 +67,8 @@ struct LbaDev {
   HuberD hm, hs;
 };
 
+constexpr int HPE_STRIDE = 22;  // doubles per edge in Hpp_e: the 21 upper-triangle entries + 1 pad (16-byte records)
+
 // residual of one edge; returns chi2 (r^T Omega r)
 __device__ __forceinline__ double edge_residual(const LbaDev& D, int e, const double* Xc, double* r) {
   const float* cam = D.kf_cam + 5 * D.e_kf[e];
@@ -175,18 +177,28 @@ __global__ void __launch_bounds__(128) lin_kernel(LbaDev D) {
       bl[i] += A[i] * orr[0] + A[3 + i] * orr[1] + A[6 + i] * orr[2];
     }
     if (D.e_free[e] >= 0) {
-      double* We = D.W + 18 * (size_t)e;
-      double* He = D.Hpp_e + 21 * (size_t)e;
-      double* be = D.bp_e + 6 * (size_t)e;
+      // per-edge records (16-byte aligned: 22 / 6 / 18 doubles) written as 16-byte stores: a thread owns a whole
+      // record, so every store of a warp is its own sector -- halving the store count halves the LSU traffic
+      double he[HPE_STRIDE], bev[6], we[18];
       t = 0;
 #pragma unroll
       for (int i = 0; i < 6; i++) {
 #pragma unroll
-        for (int j = i; j < 6; j++) He[t++] = ws * (B[i] * B[j] + B[6 + i] * B[6 + j] + B[12 + i] * B[12 + j]);
-        be[i] = B[i] * orr[0] + B[6 + i] * orr[1] + B[12 + i] * orr[2];
+        for (int j = i; j < 6; j++) he[t++] = ws * (B[i] * B[j] + B[6 + i] * B[6 + j] + B[12 + i] * B[12 + j]);
+        bev[i] = B[i] * orr[0] + B[6 + i] * orr[1] + B[12 + i] * orr[2];
 #pragma unroll
-        for (int j = 0; j < 3; j++) We[i * 3 + j] = ws * (B[i] * A[j] + B[6 + i] * A[3 + j] + B[12 + i] * A[6 + j]);
+        for (int j = 0; j < 3; j++) we[i * 3 + j] = ws * (B[i] * A[j] + B[6 + i] * A[3 + j] + B[12 + i] * A[6 + j]);
       }
+      he[21] = 0.0;
+      double2* He2 = reinterpret_cast<double2*>(D.Hpp_e + HPE_STRIDE * (size_t)e);
+      double2* be2 = reinterpret_cast<double2*>(D.bp_e + 6 * (size_t)e);
+      double2* We2 = reinterpret_cast<double2*>(D.W + 18 * (size_t)e);
+#pragma unroll
+      for (int i = 0; i < HPE_STRIDE / 2; i++) He2[i] = make_double2(he[2 * i], he[2 * i + 1]);
+#pragma unroll
+      for (int i = 0; i < 3; i++) be2[i] = make_double2(bev[2 * i], bev[2 * i + 1]);
+#pragma unroll
+      for (int i = 0; i < 9; i++) We2[i] = make_double2(we[2 * i], we[2 * i + 1]);
     }
   }
   D.chi_lm[l] = chi;
@@ -219,12 +231,13 @@ __global__ void __launch_bounds__(128) pose_reduce_kernel(LbaDev D) {
   for (int i = 0; i < 27; i++) acc[i] = 0;
   for (int p = D.pose_ptr[f] + threadIdx.x; p < D.pose_ptr[f + 1]; p += 128) {
     const int e = D.pose_edges[p];
-    const double* He = D.Hpp_e + 21 * (size_t)e;
-    const double* be = D.bp_e + 6 * (size_t)e;
+    const double2* He2 = reinterpret_cast<const double2*>(D.Hpp_e + HPE_STRIDE * (size_t)e);  // 16-byte records
+    const double2* be2 = reinterpret_cast<const double2*>(D.bp_e + 6 * (size_t)e);
 #pragma unroll
-    for (int i = 0; i < 21; i++) acc[i] += He[i];
+    for (int i = 0; i < 10; i++) { const double2 v = He2[i]; acc[2 * i] += v.x; acc[2 * i + 1] += v.y; }
+    acc[20] += He2[10].x;
 #pragma unroll
-    for (int i = 0; i < 6; i++) acc[21 + i] += be[i];
+    for (int i = 0; i < 3; i++) { const double2 v = be2[i]; acc[21 + 2 * i] += v.x; acc[22 + 2 * i] += v.y; }
   }
   double tot[27];
 #pragma unroll
@@ -284,12 +297,18 @@ __global__ void __launch_bounds__(128) lm_prepare_kernel(LbaDev D, double lambda
   for (int i = 0; i < 3; i++) D.db[3 * (size_t)l + i] = Di[i * 3] * b[0] + Di[i * 3 + 1] * b[1] + Di[i * 3 + 2] * b[2];
   for (int e = D.lm_ptr[l]; e < D.lm_ptr[l + 1]; e++) {
     if (D.e_free[e] < 0) continue;
-    const double* We = D.W + 18 * (size_t)e;
-    double* Ye = D.Y + 18 * (size_t)e;
+    // 144-byte records, 16-byte aligned: nine 16-byte loads / stores instead of eighteen 8-byte ones
+    const double2* We2 = reinterpret_cast<const double2*>(D.W + 18 * (size_t)e);
+    double2* Ye2 = reinterpret_cast<double2*>(D.Y + 18 * (size_t)e);
+    double We[18], Ye[18];
+#pragma unroll
+    for (int i = 0; i < 9; i++) { const double2 v = We2[i]; We[2 * i] = v.x; We[2 * i + 1] = v.y; }
 #pragma unroll
     for (int i = 0; i < 6; i++)
 #pragma unroll
       for (int j = 0; j < 3; j++) Ye[i * 3 + j] = We[i * 3] * Di[j] + We[i * 3 + 1] * Di[3 + j] + We[i * 3 + 2] * Di[6 + j];
+#pragma unroll
+    for (int i = 0; i < 9; i++) Ye2[i] = make_double2(Ye[2 * i], Ye[2 * i + 1]);
   }
 }
 
@@ -724,7 +743,7 @@ constexpr int WIN = 128, WIN_P = WIN + 1, WIN_ROWS = WIN - 8, WPB = 8, WIN_THREA
 constexpr int WIN_LP = 132;  // row pitch of the m-major L / L*D panels: the four k-rows of a DMMA fragment fall into different banks
 
 // PROF (ORB_B200_LDLT_PROF): cycle counters of the phases as seen by warp 0, printed by lba_solve
-__device__ unsigned long long g_win_prof[16];
+__device__ unsigned long long g_win_prof[32];
 static int win_prof_solves = 0;
 
 template <bool PROF>
@@ -743,7 +762,7 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
   __shared__ unsigned short tile_ij[(WIN / 8) * (WIN / 8 + 1) / 2];  // lower-triangle tile number -> (ti << 8) | tj
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int npan = (n + WPB - 1) / WPB;
-  unsigned long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned long long pc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   long long t0 = 0;
   auto tick = [&](int slot) {
     if (PROF) {
@@ -1005,6 +1024,7 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
     jmb[bq] = jmv;  // (after the reads of `first`: jmb may alias nothing, it lives in the ring)
   }
   __syncthreads();
+  tick(8);
   constexpr int BS_THREADS = WIN;  // one thread per window column (WIN_ROWS < WIN)
   if (tid < BS_THREADS) {
     double rowsE[WPB], rowsO[WPB], Pc[WPB];  // rows of even / odd blocks, in flight two steps ahead
@@ -1038,12 +1058,16 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
         const double s1 = Pc[4] * ab[4] + Pc[5] * ab[5] + Pc[6] * ab[6] + Pc[7] * ab[7];
         acc[j] -= s0 + s1;
       }
+      tick(9);
       // ---- off the chain: the next step's row of P, the loads of the step after the next
       if (bq > 0) {
         transform(bq - 1, rows);
+        tick(10);
         if (bq > 2) fetch(bq - 3, rows);
+        tick(11);
       }
       asm volatile("bar.sync 1, %0;" ::"n"(BS_THREADS) : "memory");
+      tick(12);
     };
     const int b0 = npan - 1;
     const bool b0_even = (b0 & 1) == 0;
@@ -1051,12 +1075,14 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
     if (b0 > 0) { if (b0_even) fetch(b0 - 1, rowsO); else fetch(b0 - 1, rowsE); }
     if (b0_even) transform(b0, rowsE); else transform(b0, rowsO);
     if (b0 > 1) { if (b0_even) fetch(b0 - 2, rowsE); else fetch(b0 - 2, rowsO); }
+    tick(13);
     for (int bq = b0; bq >= 0; bq--) {
       if (bq & 1) step(bq, rowsE);  // block bq - 1 is even
       else step(bq, rowsO);
     }
   }
   __syncthreads();
+  tick(14);
   // x_b = G acc_b for every block at once: G[r][c] = Linv[c][r] (c > r), 1 on the diagonal
   for (int i = tid; i < n; i += WIN_THREADS) {
     const int bq = i / WPB, r = i - bq * WPB, k0 = bq * WPB, nb = min(WPB, n - k0);
@@ -1069,6 +1095,9 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
     tick(4);
     if (tid == 0 || tid == 32)
       for (int k = 0; k < 8; k++) atomicAdd(&g_win_prof[(tid ? 8 : 0) + k], pc[k]);
+    if (tid == 0) {  // back-substitution in detail; slot 4 is then only the x pass
+      for (int k = 8; k < 16; k++) atomicAdd(&g_win_prof[8 + k], pc[k]);
+    }
   }
 }
 
@@ -1637,7 +1666,7 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
 #undef UPLOAD
   const size_t nS = (size_t)(n + 1) * n;
   size_t wbytes = 256 * 32 + sizeof(double) * (14 * (size_t)K + 6 * (size_t)L + (size_t)L * (6 + 3 + 9 + 3 + 1) +
-                                               (size_t)E * (18 + 18 + 21 + 6 + 1) + (size_t)nf * 42 + nS + (S.world > 1 ? env_total : 1) +
+                                               (size_t)E * (18 + 18 + HPE_STRIDE + 6 + 1) + (size_t)nf * 42 + nS + (S.world > 1 ? env_total : 1) +
                                                (size_t)n + 3 * (size_t)L + (size_t)nf + L + 16) + (size_t)E;
   if (S.work.reserve(wbytes)) return ORB_E_CUDA;
   uint8_t* wp = (uint8_t*)S.work.p;
@@ -1647,7 +1676,7 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
   D.Dinv = carve<double>(wp, 9 * (size_t)L + 1); D.db = carve<double>(wp, 3 * (size_t)L + 1);
   D.chi_lm = carve<double>(wp, (size_t)L + 1);
   D.W = carve<double>(wp, 18 * (size_t)E + 1); D.Y = carve<double>(wp, 18 * (size_t)E + 1);
-  D.Hpp_e = carve<double>(wp, 21 * (size_t)E + 1); D.bp_e = carve<double>(wp, 6 * (size_t)E + 1);
+  D.Hpp_e = carve<double>(wp, HPE_STRIDE * (size_t)E + 2); D.bp_e = carve<double>(wp, 6 * (size_t)E + 1);
   D.chi2_e = carve<double>(wp, (size_t)E + 1);
   D.Hpp = carve<double>(wp, 36 * (size_t)nf); D.bp = carve<double>(wp, 6 * (size_t)nf);
   D.S = carve<double>(wp, nS);
@@ -1842,16 +1871,20 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
     if (depth_pos_out) depth_pos_out[perm[s]] = dep_sorted[s];
   }
   if (win_prof_solves > 0) {  // ORB_B200_LDLT_PROF: cycles per phase of ldlt_win_kernel<true>, summed over warp 0 and warp 1
-    unsigned long long pc[16] = {0}, zero[16] = {0};
+    unsigned long long pc[32] = {0}, zero[32] = {0};
     cudaMemcpyFromSymbol(pc, g_win_prof, sizeof(pc));
     cudaMemcpyToSymbol(g_win_prof, zero, sizeof(zero));
     const double d = (double)win_prof_solves;
-    const char* names[8] = {"fwd-subst", "barrier A", "tiles", "barrier B", "back-subst", "after fwd (row loads)", "pivot", "pivot store"};
+    const char* names[8] = {"fwd-subst", "barrier A", "tiles", "barrier B", "x pass", "after fwd (row loads)", "pivot", "pivot store"};
     for (int w = 0; w < 2; w++) {
       fprintf(stderr, "[orbb200 lba] ldlt_win cycles per solve, warp %d (n = %d):", w, n);
       for (int k = 0; k < 8; k++) fprintf(stderr, " %s %.0f |", names[k], pc[8 * w + k] / d);
       fprintf(stderr, "\n");
     }
+    const char* bn[8] = {"staging (inverse blocks)", "chain", "transform", "fetch", "barrier", "prologue", "tail barrier", "-"};
+    fprintf(stderr, "[orbb200 lba] back-substitution, thread 0:");
+    for (int k = 0; k < 7; k++) fprintf(stderr, " %s %.0f |", bn[k], pc[16 + k] / d);
+    fprintf(stderr, "\n");
     win_prof_solves = 0;
   }
   if (stats) {
