@@ -742,6 +742,19 @@ __global__ void __launch_bounds__(SKY_THREADS) ldlt_sky_kernel(double* __restric
 constexpr int WIN = 128, WIN_P = WIN + 1, WIN_ROWS = WIN - 8, WPB = 8, WIN_THREADS = 512;
 constexpr int WIN_LP = 132;  // row pitch of the m-major L / L*D panels: the four k-rows of a DMMA fragment fall into different banks
 
+// Asynchronous 8-byte copies global -> shared (LDGSTS): unlike a load into registers they are not waited for by
+// bar.sync, so a copy issued in one phase of ldlt_win_kernel can be in flight across the barriers of the next ones
+// (measured: with register loads every barrier paid the full global-memory round trip of the loads before it).
+// `valid == false` writes zeros without reading.
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int sz = valid ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // PROF (ORB_B200_LDLT_PROF): cycle counters of the phases as seen by warp 0, printed by lba_solve
 __device__ unsigned long long g_win_prof[32];
 static int win_prof_solves = 0;
@@ -757,6 +770,7 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
   double* LDt = Lt + WPB * WIN_LP;           // [8][WIN_LP] L*D of the panel rows
   int* first = reinterpret_cast<int*>(LDt + WPB * WIN_LP);  // [n] envelope starts (read at every step: keep them on chip)
   int* rlast = first + n;                    // [ceil(n/8)] last window row of every panel
+  double* stg = reinterpret_cast<double*>(rlast + ((((n + WPB - 1) / WPB) + 1) & ~1));  // [12][WIN + 8] rows on their way into the window (n = 6 x poses is even)
   __shared__ double Lb[WPB][WPB];            // pivot block: strict lower = L, diagonal = D
   __shared__ double Dib[WPB];                // 1 / D
   __shared__ unsigned short tile_ij[(WIN / 8) * (WIN / 8 + 1) / 2];  // lower-triangle tile number -> (ti << 8) | tj
@@ -916,12 +930,54 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
     if (ok0) A[i0] = c0;
     if (ok1) A[i1] = c1;
   };
+  constexpr int FWD_WARPS = WIN / 32;  // warps that can hold a panel row in phase (A)
+  constexpr int LD_WARPS = WIN_THREADS / 32 - FWD_WARPS;  // the other warps bring rows into the window
+  // A row that panel p+2 adds to the window is copied asynchronously into a staging row during phase (A) of panel
+  // p and moved into the ring during phase (A) of panel p+1 (when its slot is free): a whole panel of time for the
+  // round trip to global memory instead of a wait inside the phase.  One row per loader warp and panel; a panel that adds more
+  // rows than there are loader warps (irregular envelopes) loads the rest directly.
+  int pf_row = -1, pf_c0 = 0;
+  double* my_stg = stg + (warp >= FWD_WARPS ? warp - FWD_WARPS : 0) * (WIN + 8);
+  auto prefetch_row = [&](int i, int c0) {
+    const int f = first[i];
+    const double* Mi = M + (size_t)i * n;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int j = c0 + lane + 32 * q;
+      const bool valid = j <= i && j >= f;
+      cp_async8(my_stg + lane + 32 * q, valid ? Mi + j : M, valid);
+    }
+    if (lane == 0) cp_async8(my_stg + WIN, M + (size_t)n * n + i, true);
+    cp_async_commit();
+    pf_row = i; pf_c0 = c0;
+  };
+  auto commit_row = [&]() {
+    if (pf_row < 0) return;
+    cp_async_wait<0>();
+    double* Ai = A + (pf_row % WIN) * WIN_P;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int j = pf_c0 + lane + 32 * q;
+      if (j <= pf_row) Ai[j % WIN] = my_stg[lane + 32 * q];
+    }
+    if (lane == 0) zr[pf_row % WIN] = my_stg[WIN];
+    pf_row = -1;
+  };
+  // first new row of panel q's window (q >= 1), as phase (A) of panel q-1 computes it
+  auto new_rows_lo = [&](int q) {
+    const int r0q = q * WPB;  // = k0 + nb of panel q-1 (only the last panel is short)
+    const int preq = min(r0q + WPB - 1, n - 1);
+    return max(rlast[q - 1], preq) + 1;
+  };
   load_rows(0, rlast[0], 0, 0, WIN_THREADS / 32);
+  if (warp >= FWD_WARPS && npan > 1) {
+    const int i = new_rows_lo(1) + (warp - FWD_WARPS);
+    if (i <= rlast[1]) prefetch_row(i, WPB);
+  }
   __syncthreads();
   if (tid == 0) pivot(0);
   __syncthreads();
   if (PROF) asm volatile("mov.u64 %0, %%clock64;" : "=l"(t0) :: "memory");
-  constexpr int FWD_WARPS = WIN / 32;  // warps that can hold a panel row in phase (A)
   for (int p = 0; p < npan; p++) {
     const int k0 = p * WPB, nb = min(WPB, n - k0);
     const int R = rlast[p];  // last row of the window; rows [k0, R] are resident, the pivot block is factored
@@ -955,8 +1011,18 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
         if (m < nb) dst[m] = l[m];
     }
     tick(0);
-    if (warp == FWD_WARPS) pivot_store(p);
-    if (warp >= FWD_WARPS && more) load_rows(max(R, pre) + 1, rlast[p + 1], r0, FWD_WARPS, WIN_THREADS / 32 - FWD_WARPS);
+    if (warp >= FWD_WARPS) {
+      commit_row();  // the row of panel p+1 fetched one panel ago
+      if (warp == FWD_WARPS) pivot_store(p);
+      if (more) {
+        const int lo1 = max(R, pre) + 1 + LD_WARPS;  // rows beyond one per loader warp: directly
+        if (lo1 <= rlast[p + 1]) load_rows(lo1, rlast[p + 1], r0, FWD_WARPS, LD_WARPS);
+        if (p + 2 < npan) {
+          const int i = new_rows_lo(p + 2) + (warp - FWD_WARPS);
+          if (i <= rlast[p + 2]) prefetch_row(i, r0 + WPB);
+        }
+      }
+    }
     tick(5);
     __syncthreads();
     tick(1);
@@ -966,8 +1032,8 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
     {
       const int T8 = (nr + 1 + 7) >> 3;
       const int ntile = T8 * (T8 + 1) / 2;
-      // warp 0 shares its scheduler with warps 4, 8, 12: they stay idle here so that the pivot chain issues alone
-      constexpr int UW = WIN_THREADS / 32 - WIN_THREADS / 128;
+      // warp 0 shares its scheduler with warps 4, 8, 12: they take what is left after the other twelve warps got
+      // seven tiles each (a 96-row window: 90 tiles = 12 x 7 + 3 x 2), so the pivot chain issues almost alone
       if (warp == 0) {
         if (pre > R) load_rows(R + 1, pre, r0, 0, 1);
         update_tile0(r0, nr);
@@ -975,10 +1041,13 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
         tick(2);
         if (tid == 0 && more) pivot(p + 1);
         tick(6);
-      } else if (warp & 3) {
-        const int per = (ntile - 1 + UW - 1) / UW;  // tiles 1 .. ntile-1 in runs over the update warps
-        const int tb = 1 + (warp - 1 - (warp >> 2)) * per;
-        update_run(tb, min(tb + per, ntile), r0, nr);
+      } else {
+        const int T = ntile - 1;
+        const int light = T / 22, heavy = (T - 3 * light + 11) / 12;
+        int tb, te;
+        if (warp & 3) { tb = 1 + (warp - 1 - (warp >> 2)) * heavy; te = tb + heavy; }
+        else { const int rest = max(T - 12 * heavy, 0), per = (rest + 2) / 3; tb = 1 + 12 * heavy + ((warp >> 2) - 1) * per; te = tb + per; }
+        update_run(min(tb, ntile), min(te, ntile), r0, nr);
         tick(2);
       }
     }
@@ -1027,16 +1096,26 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
   tick(8);
   constexpr int BS_THREADS = WIN;  // one thread per window column (WIN_ROWS < WIN)
   if (tid < BS_THREADS) {
-    double rowsE[WPB], rowsO[WPB], Pc[WPB];  // rows of even / odd blocks, in flight two steps ahead
-    auto fetch = [&](int bq, double (&rows)[WPB]) {
+    double Pc[WPB];
+    double* bsr = reinterpret_cast<double*>(jmb + ((npan + 1) & ~1));  // [4][WPB][WIN]: rows of L, four blocks in flight
+    auto fetch = [&](int bq) {
       const int k0 = bq * WPB, nb = min(WPB, n - k0), j = jmb[bq] + tid;
       const double* src = M + (size_t)k0 * n + j;
+      double* dst = bsr + (bq & 3) * (WPB * WIN) + tid;
 #pragma unroll
-      for (int r = 0; r < WPB; r++) rows[r] = (r < nb && j < k0) ? src[(size_t)r * n] : 0.0;
+      for (int r = 0; r < WPB; r++) {
+        const bool valid = r < nb && j < k0;
+        cp_async8(dst + r * WIN, valid ? src + (size_t)r * n : M, valid);
+      }
+      cp_async_commit();
     };
     // P[j][c] = sum_{r <= c} L[k0+r][j] G[r][c],  G[r][c] = Linv[c][r], G[c][c] = 1
-    auto transform = [&](int bq, const double (&rows)[WPB]) {
+    auto transform = [&](int bq) {
       const double* pb = pblk + bq * 28;
+      const double* rp = bsr + (bq & 3) * (WPB * WIN) + tid;
+      double rows[WPB];
+#pragma unroll
+      for (int r = 0; r < WPB; r++) rows[r] = rp[r * WIN];
 #pragma unroll
       for (int c = 0; c < WPB; c++) {
         double t = rows[c];
@@ -1045,8 +1124,14 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
         Pc[c] = t;
       }
     };
-    // one step; `rows` is the register set of block bq - 1 (and, after its use, of block bq - 3)
-    auto step = [&](int bq, double (&rows)[WPB]) {
+    const int b0 = npan - 1;
+    fetch(b0);
+    if (b0 > 0) fetch(b0 - 1); else cp_async_commit();
+    cp_async_wait<1>();
+    transform(b0);
+    if (b0 > 1) fetch(b0 - 2); else cp_async_commit();
+    tick(13);
+    for (int bq = b0; bq >= 0; bq--) {
       const int k0 = bq * WPB;
       const int j = jmb[bq] + tid;
       // ---- the chain (only the last block can be short: its missing slots read as zero)
@@ -1059,27 +1144,19 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
         acc[j] -= s0 + s1;
       }
       tick(9);
-      // ---- off the chain: the next step's row of P, the loads of the step after the next
+      // ---- off the chain: the next step's row of P (its rows arrived two steps ago), the copies of the step after
+      //      the next.  One group is committed per step so that wait_group counts steps.
       if (bq > 0) {
-        transform(bq - 1, rows);
+        cp_async_wait<1>();
+        transform(bq - 1);
         tick(10);
-        if (bq > 2) fetch(bq - 3, rows);
+        if (bq > 2) fetch(bq - 3); else cp_async_commit();
         tick(11);
       }
       asm volatile("bar.sync 1, %0;" ::"n"(BS_THREADS) : "memory");
       tick(12);
-    };
-    const int b0 = npan - 1;
-    const bool b0_even = (b0 & 1) == 0;
-    if (b0_even) fetch(b0, rowsE); else fetch(b0, rowsO);
-    if (b0 > 0) { if (b0_even) fetch(b0 - 1, rowsO); else fetch(b0 - 1, rowsE); }
-    if (b0_even) transform(b0, rowsE); else transform(b0, rowsO);
-    if (b0 > 1) { if (b0_even) fetch(b0 - 2, rowsE); else fetch(b0 - 2, rowsO); }
-    tick(13);
-    for (int bq = b0; bq >= 0; bq--) {
-      if (bq & 1) step(bq, rowsE);  // block bq - 1 is even
-      else step(bq, rowsO);
     }
+    cp_async_wait<0>();
   }
   __syncthreads();
   tick(14);
@@ -1610,8 +1687,8 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
     for (int r = 0; r < nb; r++) jmin = std::min(jmin, env_first[k0 + r]);
     win_rows_max = std::max(win_rows_max, std::max(R - k0 + 1, k0 - jmin + nb));
   }
-  // envelope tables (4.5 bytes per unknown) share the shared memory; the back-substitution keeps n + 29 n / 8 doubles in the ring
-  const bool win_ok = win_rows_max <= WIN_ROWS && n <= 3400;
+  // envelope tables (4.5 bytes per unknown) share the shared memory; the back-substitution keeps n + 29 n / 8 + 4096 doubles in the ring
+  const bool win_ok = win_rows_max <= WIN_ROWS && n <= 2600;
   static const char* ldlt_env = getenv("ORB_B200_LDLT");  // "dense" | "sky" | "win" | unset = automatic
   bool use_sky = sky_rows_max <= SKY_WMAX - 4 && n <= 32 * SKY_WMAX && sky_flops <= 6.0e7;
   if (ldlt_env && !strcmp(ldlt_env, "dense")) use_sky = false;
@@ -1780,7 +1857,8 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
       CUDA_TRYL(cudaMemsetAsync(S.d_bar, 0, 256, st));
       CUDA_TRYL(cudaMemsetAsync(D.scalars + 3, 0, sizeof(double), st));
       if (use_win) {
-        const size_t smem = sizeof(double) * (WIN * WIN_P + WIN + 2 * WPB * WIN_LP) + sizeof(int) * ((size_t)n + (n + WPB - 1) / WPB + 4);
+        const size_t smem = sizeof(double) * (WIN * WIN_P + WIN + 2 * WPB * WIN_LP + (WIN_THREADS / 32 - WIN / 32) * (WIN + 8)) +
+                            sizeof(int) * ((size_t)n + (n + WPB - 1) / WPB + 4);
         static const bool win_prof = getenv("ORB_B200_LDLT_PROF") != nullptr;
         if (win_prof) {
           CUDA_TRYL(raise_dynamic_smem((const void*)ldlt_win_kernel<true>, smem, S.device));
