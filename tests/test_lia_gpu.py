@@ -25,7 +25,9 @@ def test_device_run_matches_the_oracle(oracle, n_opt, n_mp, seed, perturb):
     # the device sums in a fixed order, but not the oracle's: LM counts may differ once a trial is at the rounding level
     assert abs(got["stats"]["iterations"] - ref["stats"]["iterations"]) <= 1
     if got["stats"]["iterations"] == ref["stats"]["iterations"] and got["stats"]["trials"] == ref["stats"]["trials"]:
-        _compare(d, ref, got, tol=1e-6)
+        # the device build contracts a*b+c into FMAs (build.py), the oracle does not: the initial error -- a sum of
+        # terms weighted by information matrices of 1e6 and more -- agrees to ~1e-9 relative, not to the last bits
+        _compare(d, ref, got, tol=1e-6, err_tol=1e-7)
     else:
         assert abs(got["stats"]["err_end"] - ref["stats"]["err_end"]) <= 1e-3 * ref["stats"]["err_end"]
     assert lia.kernel_launches() == 1 and lia.last_ms() > 0
