@@ -240,9 +240,15 @@ double match_last_ms(orb_matcher* m);
  * Levenberg-Marquardt loop `optimizer.optimize(10)` (:1410-1411) on a flat graph.
  * The shim keeps steps 1-4 (collecting KFs/MPs/edges, :1119-1400) and 6-7
  * (outlier erase, write-back under Map::mMutexMapUpdate, :1413-1497).
- * Pinhole mono (EdgeSE3ProjectXYZ) and stereo (g2o::EdgeStereoSE3ProjectXYZ)
- * edges; EdgeSE3ProjectXYZToBody (second camera) is out of scope.
+ * Mono (EdgeSE3ProjectXYZ, Pinhole or KannalaBrandt8 camera), stereo
+ * (g2o::EdgeStereoSE3ProjectXYZ) and second-camera (EdgeSE3ProjectXYZToBody,
+ * src/OptimizableTypes.cpp:192-213, edges of :1366-1400) edges.
  * ---------------------------------------------------------------------- */
+#define ORB_CAM_PINHOLE 0 /* GeometricCamera::CAM_PINHOLE */
+#define ORB_CAM_KB8 1     /* GeometricCamera::CAM_FISHEYE (KannalaBrandt8) */
+#define LBA_EDGE_MONO 0   /* EdgeSE3ProjectXYZ, obs = kpUn.pt (:1305-1331) */
+#define LBA_EDGE_STEREO 1 /* g2o::EdgeStereoSE3ProjectXYZ, obs = kpUn.pt, mvuRight (:1332-1364) */
+#define LBA_EDGE_BODY 2   /* EdgeSE3ProjectXYZToBody, obs = mvKeysRight[rightIndex].pt (:1366-1400) */
 typedef struct lba_graph_view {
   int32_t n_kf;               /* local + fixed keyframes */
   const double* kf_pose;      /* n_kf x 7: g2o::SE3Quat(Tcw): quaternion x,y,z,w then translation (:1217, :1236) */
@@ -253,9 +259,16 @@ typedef struct lba_graph_view {
   int32_t n_edges;
   const int32_t* e_kf;        /* index into kf arrays */
   const int32_t* e_mp;        /* index into mp arrays */
-  const uint8_t* e_stereo;    /* 0: mono 2-D edge (:1305-1331), 1: stereo 3-D edge (:1332-1364) */
-  const double* e_obs;        /* n_edges x 3: kpUn.pt.x, kpUn.pt.y, mvuRight (ignored for mono) */
-  const float* e_inv_sigma2;  /* mvInvLevelSigma2[kpUn.octave] */
+  const uint8_t* e_stereo;    /* LBA_EDGE_MONO / LBA_EDGE_STEREO / LBA_EDGE_BODY */
+  const double* e_obs;        /* n_edges x 3: pt.x, pt.y, mvuRight (third entry ignored unless LBA_EDGE_STEREO) */
+  const float* e_inv_sigma2;  /* mvInvLevelSigma2[octave] */
+  /* Rig extension; every pointer may be NULL (= all keyframes carry one Pinhole camera, as above). */
+  const uint8_t* kf_cam_model;  /* n_kf: ORB_CAM_* of pKFi->mpCamera (e->pCamera of the mono edges, :1326) */
+  const float* kf_cam_dist;     /* n_kf x 4: KannalaBrandt8 k0..k3 = mvParameters[4..7]; read for ORB_CAM_KB8 only */
+  const uint8_t* kf_cam2_model; /* n_kf: ORB_CAM_* of pKFi->mpCamera2 (e->pCamera of the body edges, :1387) */
+  const float* kf_cam2;         /* n_kf x 8: fx, fy, cx, cy, k0..k3 of mpCamera2 */
+  const double* kf_trl;         /* n_kf x 7: g2o::SE3Quat(GetRelativePoseTrl()) = quaternion x,y,z,w + translation (:1384-1385);
+                                 * required when any edge is LBA_EDGE_BODY */
 } lba_graph_view;
 
 typedef struct lba_stats {

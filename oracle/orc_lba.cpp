@@ -14,6 +14,9 @@
 //   Thirdparty/g2o/g2o/types/types_six_dof_expmap.h:73-76    VertexSE3Expmap::oplusImpl
 //   src/OptimizableTypes.cpp:139-160, include/OptimizableTypes.h:99-104   mono edge
 //   src/CameraModels/Pinhole.cpp:42-48, 71-81                project / projectJac (float parameters)
+//   src/CameraModels/KannalaBrandt8.cpp:46-65, 145-175       project (atan2f / sqrtf in float) / projectJac
+//   src/OptimizableTypes.cpp:192-213, include/OptimizableTypes.h:150-185   EdgeSE3ProjectXYZToBody (second camera)
+//   src/Optimizer.cc:1366-1400                               body edges: obs, Huber (mono delta), mTrl, pCamera = mpCamera2
 //   src/Optimizer.cc:1275-1276, 1305-1364                    Huber deltas, information, edge set-up
 // The reduced system is solved with a skyline LDL^T on the dense S instead of
 // Eigen's SimplicialLDLT (un-vendored); same solution up to rounding.
@@ -30,6 +33,44 @@
 #include "orc_se3.h"
 
 namespace {
+
+// GeometricCamera::project / projectJac of the two camera models on float parameters
+// p = fx, fy, cx, cy [, k0..k3] (std::vector<float> mvParameters promoted to double as the expressions do).
+inline void cam_project(int model, const float* p, const float* k, const double X[3], double uv[2]) {
+  if (model == ORB_CAM_KB8) {  // KannalaBrandt8.cpp:46-65
+    const double x2_plus_y2 = X[0] * X[0] + X[1] * X[1];
+    const double theta = atan2f(sqrtf((float)x2_plus_y2), (float)X[2]);
+    const double psi = atan2f((float)X[1], (float)X[0]);
+    const double theta2 = theta * theta, theta3 = theta * theta2, theta5 = theta3 * theta2, theta7 = theta5 * theta2,
+                 theta9 = theta7 * theta2;
+    const double r = theta + k[0] * theta3 + k[1] * theta5 + k[2] * theta7 + k[3] * theta9;
+    uv[0] = p[0] * r * cos(psi) + p[2];
+    uv[1] = p[1] * r * sin(psi) + p[3];
+  } else {  // Pinhole.cpp:42-48
+    uv[0] = p[0] * X[0] / X[2] + p[2];
+    uv[1] = p[1] * X[1] / X[2] + p[3];
+  }
+}
+inline void cam_project_jac(int model, const float* p, const float* k, const double X[3], double J[6]) {
+  if (model == ORB_CAM_KB8) {  // KannalaBrandt8.cpp:145-175
+    const double x2 = X[0] * X[0], y2 = X[1] * X[1], z2 = X[2] * X[2];
+    const double r2 = x2 + y2, r = sqrt(r2), r3 = r2 * r;
+    const double theta = atan2(r, X[2]);
+    const double theta2 = theta * theta, theta3 = theta2 * theta, theta4 = theta2 * theta2, theta5 = theta4 * theta,
+                 theta6 = theta2 * theta4, theta7 = theta6 * theta, theta8 = theta4 * theta4, theta9 = theta8 * theta;
+    const double f = theta + theta3 * k[0] + theta5 * k[1] + theta7 * k[2] + theta9 * k[3];
+    const double fd = 1 + 3 * k[0] * theta2 + 5 * k[1] * theta4 + 7 * k[2] * theta6 + 9 * k[3] * theta8;
+    J[0] = p[0] * (fd * X[2] * x2 / (r2 * (r2 + z2)) + f * y2 / r3);
+    J[3] = p[1] * (fd * X[2] * X[1] * X[0] / (r2 * (r2 + z2)) - f * X[1] * X[0] / r3);
+    J[1] = p[0] * (fd * X[2] * X[1] * X[0] / (r2 * (r2 + z2)) - f * X[1] * X[0] / r3);
+    J[4] = p[1] * (fd * X[2] * y2 / (r2 * (r2 + z2)) + f * x2 / r3);
+    J[2] = -p[0] * fd * X[0] / (r2 + z2);
+    J[5] = -p[1] * fd * X[1] / (r2 + z2);
+  } else {  // Pinhole.cpp:71-81
+    J[0] = p[0] / X[2]; J[1] = 0.; J[2] = -p[0] * X[0] / (X[2] * X[2]);
+    J[3] = 0.; J[4] = p[1] / X[2]; J[5] = -p[1] * X[1] / (X[2] * X[2]);
+  }
+}
 
 struct Problem {
   const lba_graph_view* g;
@@ -64,7 +105,33 @@ struct Problem {
     x.assign(b.size(), 0.0);
   }
 
-  inline int dim(int e) const { return g->e_stereo[e] ? 3 : 2; }
+  inline int dim(int e) const { return g->e_stereo[e] == LBA_EDGE_STEREO ? 3 : 2; }
+  inline bool is_stereo(int e) const { return g->e_stereo[e] == LBA_EDGE_STEREO; }
+  inline bool is_body(int e) const { return g->e_stereo[e] == LBA_EDGE_BODY; }
+  // e->pCamera of a 2-D edge: mpCamera (mono, Optimizer.cc:1326) or mpCamera2 (body, :1387)
+  struct Cam { int model; const float* p; const float* k; };
+  inline Cam edge_cam(int e) const {
+    static const float zero4[4] = {0, 0, 0, 0};
+    const int k = g->e_kf[e];
+    if (is_body(e))
+      return Cam{g->kf_cam2_model ? g->kf_cam2_model[k] : ORB_CAM_PINHOLE, g->kf_cam2 + 8 * (size_t)k, g->kf_cam2 + 8 * (size_t)k + 4};
+    return Cam{g->kf_cam_model ? g->kf_cam_model[k] : ORB_CAM_PINHOLE, g->kf_cam + 5 * (size_t)k,
+               g->kf_cam_dist ? g->kf_cam_dist + 4 * (size_t)k : zero4};
+  }
+  inline SE3 trw(int k) const {  // mTrl * Tcw: SE3Quat::operator* (se3quat.h:104-110)
+    const SE3 Trl = trl(k);
+    SE3 T;
+    quat_rot(Trl.r, pose[k].t, T.t);
+    for (int i = 0; i < 3; i++) T.t[i] += Trl.t[i];
+    T.r = quat_mul(Trl.r, pose[k].r);
+    quat_normalize(T.r);
+    return T;
+  }
+  inline SE3 trl(int k) const {  // e->mTrl (:1384-1385)
+    const double* p = g->kf_trl + 7 * (size_t)k;
+    SE3 T; T.r = Quat{p[0], p[1], p[2], p[3]}; T.t[0] = p[4]; T.t[1] = p[5]; T.t[2] = p[6];
+    return T;
+  }
 
   // computeError of both edge types
   void compute_errors() {
@@ -75,6 +142,17 @@ struct Problem {
       const float* cam = g->kf_cam + 5 * k;
       const double* obs = g->e_obs + 3 * (size_t)e;
       double* r = &err[3 * (size_t)e];
+      if (!is_stereo(e)) {
+        // EdgeSE3ProjectXYZ::computeError (OptimizableTypes.h:99-104): obs - pCamera->project(Tcw.map(Xw));
+        // EdgeSE3ProjectXYZToBody::computeError (:156-161): obs - pCamera->project((mTrl * Tcw).map(Xw))
+        double Xe[3] = {Xc[0], Xc[1], Xc[2]};
+        if (is_body(e)) se3_map(trw(k), &pt[3 * (size_t)g->e_mp[e]], Xe);
+        const Cam c = edge_cam(e);
+        double uv[2];
+        cam_project(c.model, c.p, c.k, Xe, uv);
+        r[0] = obs[0] - uv[0]; r[1] = obs[1] - uv[1]; r[2] = 0;
+        continue;
+      }
       if (g->e_stereo[e]) {
         // types_six_dof_expmap.cpp:190-197: invz in float; fx.. are doubles set from floats
         const double fx = cam[0], fy = cam[1], cx = cam[2], cy = cam[3];
@@ -95,13 +173,13 @@ struct Problem {
     const double s = g->e_inv_sigma2[e];
     const double* r = &err[3 * (size_t)e];
     double c = r[0] * (s * r[0]) + r[1] * (s * r[1]);
-    if (g->e_stereo[e]) c += r[2] * (s * r[2]);
+    if (is_stereo(e)) c += r[2] * (s * r[2]);
     return c;
   }
   double robust_chi2() const {  // sparse_optimizer.cpp:100-114
     double chi = 0, r0, r1;
     for (int e = 0; e < g->n_edges; e++) {
-      (g->e_stereo[e] ? hs : hm).robustify(chi2(e), r0, r1);
+      (is_stereo(e) ? hs : hm).robustify(chi2(e), r0, r1);  // body edges: thHuberMono (:1380-1382)
       chi += r0;
     }
     return chi;
@@ -120,7 +198,7 @@ struct Problem {
       const float* cam = g->kf_cam + 5 * k;
       const double x = Xc[0], y = Xc[1], z = Xc[2];
       double A[9], B[18];  // d x 3, d x 6 row-major
-      if (g->e_stereo[e]) {
+      if (is_stereo(e)) {
         const double fx = cam[0], fy = cam[1], bf = cam[4];
         const double z_2 = z * z;
         for (int c = 0; c < 3; c++) {
@@ -134,19 +212,44 @@ struct Problem {
         B[9] = 0; B[10] = -1. / z * fy; B[11] = y / z_2 * fy;
         B[12] = B[0] - bf * y / z_2; B[13] = B[1] + bf * x / z_2; B[14] = B[2];
         B[15] = B[3]; B[16] = 0; B[17] = B[5] - bf / z_2;
-      } else {
-        // -projectJac (Pinhole.cpp:71-81), times R / SE3deriv (OptimizableTypes.cpp:139-160)
-        const double J[6] = {-(cam[0] / z), -0., -(-cam[0] * x / (z * z)), -0., -(cam[1] / z), -(-cam[1] * y / (z * z))};
+      } else if (is_body(e)) {
+        // EdgeSE3ProjectXYZToBody::linearizeOplus (OptimizableTypes.cpp:192-213):
+        //   Xi = -projectJac(X_r) * (Trl * Tlw).rotation();  Xj = -projectJac(X_r) * Rrl * SE3deriv(X_l)
+        const SE3 Trl = trl(k);
+        double Xr[3], Rrl[9], Rrw[9], J[6];
+        se3_map(Trl, Xc, Xr);
+        quat_to_R(Trl.r, Rrl);
+        quat_to_R(trw(k).r, Rrw);
+        const Cam c = edge_cam(e);
+        cam_project_jac(c.model, c.p, c.k, Xr, J);
+        for (int i = 0; i < 6; i++) J[i] = -J[i];
         for (int r = 0; r < 2; r++)
-          for (int c = 0; c < 3; c++)
-            A[r * 3 + c] = J[r * 3] * R[c] + J[r * 3 + 1] * R[3 + c] + J[r * 3 + 2] * R[6 + c];
+          for (int cc = 0; cc < 3; cc++)
+            A[r * 3 + cc] = J[r * 3] * Rrw[cc] + J[r * 3 + 1] * Rrw[3 + cc] + J[r * 3 + 2] * Rrw[6 + cc];
+        double JR[6];
+        for (int r = 0; r < 2; r++)
+          for (int cc = 0; cc < 3; cc++)
+            JR[r * 3 + cc] = J[r * 3] * Rrl[cc] + J[r * 3 + 1] * Rrl[3 + cc] + J[r * 3 + 2] * Rrl[6 + cc];
         const double D[18] = {0, z, -y, 1, 0, 0, -z, 0, x, 0, 1, 0, y, -x, 0, 0, 0, 1};
         for (int r = 0; r < 2; r++)
-          for (int c = 0; c < 6; c++)
-            B[r * 6 + c] = J[r * 3] * D[c] + J[r * 3 + 1] * D[6 + c] + J[r * 3 + 2] * D[12 + c];
+          for (int cc = 0; cc < 6; cc++)
+            B[r * 6 + cc] = JR[r * 3] * D[cc] + JR[r * 3 + 1] * D[6 + cc] + JR[r * 3 + 2] * D[12 + cc];
+      } else {
+        // -projectJac (Pinhole.cpp:71-81 / KannalaBrandt8.cpp:145-175), times R / SE3deriv (OptimizableTypes.cpp:139-160)
+        const Cam c = edge_cam(e);
+        double J[6];
+        cam_project_jac(c.model, c.p, c.k, Xc, J);
+        for (int i = 0; i < 6; i++) J[i] = -J[i];
+        for (int r = 0; r < 2; r++)
+          for (int cc = 0; cc < 3; cc++)
+            A[r * 3 + cc] = J[r * 3] * R[cc] + J[r * 3 + 1] * R[3 + cc] + J[r * 3 + 2] * R[6 + cc];
+        const double D[18] = {0, z, -y, 1, 0, 0, -z, 0, x, 0, 1, 0, y, -x, 0, 0, 0, 1};
+        for (int r = 0; r < 2; r++)
+          for (int cc = 0; cc < 6; cc++)
+            B[r * 6 + cc] = J[r * 3] * D[cc] + J[r * 3 + 1] * D[6 + cc] + J[r * 3 + 2] * D[12 + cc];
       }
       double rho0, rho1;
-      (g->e_stereo[e] ? hs : hm).robustify(chi2(e), rho0, rho1);
+      (is_stereo(e) ? hs : hm).robustify(chi2(e), rho0, rho1);
       const double s = g->e_inv_sigma2[e];
       const double ws = rho1 * s;  // weightedOmega = rho[1] * information
       const double* r = &err[3 * (size_t)e];
@@ -401,6 +504,8 @@ int orc_lba_solve(const lba_graph_view* g, const volatile uint8_t* stop, int max
     if (depth_pos_out) {
       double Xc[3];
       se3_map(P.pose[g->e_kf[e]], &P.pt[3 * (size_t)g->e_mp[e]], Xc);
+      // EdgeSE3ProjectXYZToBody::isDepthPositive (OptimizableTypes.h:135-139): depth in the second camera
+      if (P.is_body(e)) se3_map(P.trw(g->e_kf[e]), &P.pt[3 * (size_t)g->e_mp[e]], Xc);
       depth_pos_out[e] = Xc[2] > 0.0;
     }
   }
@@ -426,7 +531,7 @@ int orc_lba_reduced_system(const lba_graph_view* g, double lambda, const uint8_t
     double chi = 0, r0, r1;
     for (int e = 0; e < g->n_edges; e++) {
       if (lm_mask && !lm_mask[g->e_mp[e]]) continue;
-      (g->e_stereo[e] ? P.hs : P.hm).robustify(P.chi2(e), r0, r1);
+      (P.is_stereo(e) ? P.hs : P.hm).robustify(P.chi2(e), r0, r1);
       chi += r0;
     }
     *chi2_robust = chi;

@@ -59,6 +59,11 @@ struct LbaDev {
   const int* pose_ptr; const int* pose_edges;
   const int* pair_i1; const int* pair_i2; const int* pair_ptr; const int* pair_ea; const int* pair_eb;
   int n_pairs;
+  // rig extension (all null unless the graph has a KannalaBrandt8 camera or second-camera edges)
+  const uint8_t* kf_model;  // bit 0: mpCamera is KannalaBrandt8, bit 1: mpCamera2 is
+  const float* kf_dist;     // n_kf x 4: k0..k3 of mpCamera
+  const float* kf_cam2;     // n_kf x 8: fx fy cx cy k0..k3 of mpCamera2
+  const double* kf_trl;     // n_kf x 7: SE3Quat(Trl)
   // state
   double* pose; double* pts; double* pose_bak; double* pts_bak;
   // system
@@ -69,11 +74,92 @@ struct LbaDev {
 
 constexpr int HPE_STRIDE = 22;  // doubles per edge in Hpp_e: the 21 upper-triangle entries + 1 pad (16-byte records)
 
-// residual of one edge; returns chi2 (r^T Omega r)
-__device__ __forceinline__ double edge_residual(const LbaDev& D, int e, const double* Xc, double* r) {
+// GeometricCamera::project / projectJac(Eigen::Vector3d) of the two camera models on their float parameters
+// p = fx fy cx cy, k = k0..k3: Pinhole.cpp:42-48, 71-81; KannalaBrandt8.cpp:46-65 (theta and psi through the float
+// atan2f / sqrtf, as the reference writes them), :145-175.
+__device__ __forceinline__ void cam_project(bool kb8, const float* p, const float* k, const double* X, double* uv) {
+  if (kb8) {
+    const double x2_plus_y2 = X[0] * X[0] + X[1] * X[1];
+    // atan2f of float arguments: evaluated in fp64 and rounded once (equal to glibc's float routine except where
+    // either is an ulp off the exact value; the difference is ~1e-5 px, far inside the 1e-4 bar of the LM deltas)
+    const double theta = (double)(float)atan2((double)__fsqrt_rn((float)x2_plus_y2), (double)(float)X[2]);
+    const double psi = (double)(float)atan2((double)(float)X[1], (double)(float)X[0]);
+    const double theta2 = theta * theta, theta3 = theta * theta2, theta5 = theta3 * theta2, theta7 = theta5 * theta2,
+                 theta9 = theta7 * theta2;
+    const double r = theta + (double)k[0] * theta3 + (double)k[1] * theta5 + (double)k[2] * theta7 + (double)k[3] * theta9;
+    double sn, cs;
+    sincos(psi, &sn, &cs);
+    uv[0] = (double)p[0] * r * cs + (double)p[2];
+    uv[1] = (double)p[1] * r * sn + (double)p[3];
+  } else {
+    uv[0] = (double)p[0] * X[0] / X[2] + (double)p[2];
+    uv[1] = (double)p[1] * X[1] / X[2] + (double)p[3];
+  }
+}
+__device__ __forceinline__ void cam_project_jac(bool kb8, const float* p, const float* k, const double* X, double* J) {
+  const double fx = p[0], fy = p[1];
+  if (kb8) {
+    const double x2 = X[0] * X[0], y2 = X[1] * X[1], z2 = X[2] * X[2];
+    const double r2 = x2 + y2, r = sqrt(r2), r3 = r2 * r;
+    const double theta = atan2(r, X[2]);
+    const double theta2 = theta * theta, theta3 = theta2 * theta, theta4 = theta2 * theta2, theta5 = theta4 * theta,
+                 theta6 = theta2 * theta4, theta7 = theta6 * theta, theta8 = theta4 * theta4, theta9 = theta8 * theta;
+    const double k0 = k[0], k1 = k[1], k2 = k[2], k3 = k[3];
+    const double f = theta + theta3 * k0 + theta5 * k1 + theta7 * k2 + theta9 * k3;
+    const double fd = 1 + 3 * k0 * theta2 + 5 * k1 * theta4 + 7 * k2 * theta6 + 9 * k3 * theta8;
+    const double den = r2 * (r2 + z2);
+    J[0] = fx * (fd * X[2] * x2 / den + f * y2 / r3);
+    J[3] = fy * (fd * X[2] * X[1] * X[0] / den - f * X[1] * X[0] / r3);
+    J[1] = fx * (fd * X[2] * X[1] * X[0] / den - f * X[1] * X[0] / r3);
+    J[4] = fy * (fd * X[2] * y2 / den + f * x2 / r3);
+    J[2] = -fx * fd * X[0] / (r2 + z2);
+    J[5] = -fy * fd * X[1] / (r2 + z2);
+  } else {
+    J[0] = fx / X[2]; J[1] = 0.; J[2] = -fx * X[0] / (X[2] * X[2]);
+    J[3] = 0.; J[4] = fy / X[2]; J[5] = -fy * X[1] / (X[2] * X[2]);
+  }
+}
+// e->pCamera of a 2-D edge of a rig graph: mpCamera (mono, Optimizer.cc:1326) or mpCamera2 (body, :1387)
+struct EdgeCam { bool kb8; const float* p; const float* k; };
+__device__ __forceinline__ EdgeCam edge_cam(const LbaDev& D, int k, bool body) {
+  const uint8_t m = D.kf_model[k];
+  if (body) return EdgeCam{(m & 2) != 0, D.kf_cam2 + 8 * (size_t)k, D.kf_cam2 + 8 * (size_t)k + 4};
+  return EdgeCam{(m & 1) != 0, D.kf_cam + 5 * (size_t)k, D.kf_dist + 4 * (size_t)k};
+}
+// (mTrl * Tcw) of a body edge: SE3Quat::operator* (se3quat.h:104-110)
+__device__ __forceinline__ void body_pose(const LbaDev& D, int k, const DQuat& q, const double* t, DQuat& qrw, double* trw) {
+  const double* T = D.kf_trl + 7 * (size_t)k;
+  const DQuat qrl = {T[0], T[1], T[2], T[3]};
+  q_rot(qrl, t, trw);
+  trw[0] += T[4]; trw[1] += T[5]; trw[2] += T[6];
+  qrw = q_mul(qrl, q);
+  q_normalize(qrw);
+}
+
+// residual of one edge; returns chi2 (r^T Omega r).  RIG: the graph carries the rig extension (KannalaBrandt8 cameras
+// and / or EdgeSE3ProjectXYZToBody edges); P = the keyframe's pose (only read for body edges), X = the landmark
+template <bool RIG>
+__device__ __forceinline__ double edge_residual(const LbaDev& D, int e, const double* Xc, double* r, const double* P = nullptr,
+                                                const double* X = nullptr) {
   const float* cam = D.kf_cam + 5 * D.e_kf[e];
   const double* obs = D.e_obs + 3 * (size_t)e;
   const double s = (double)D.e_is2[e];
+  if (RIG && D.e_stereo[e] != LBA_EDGE_STEREO) {
+    // OptimizableTypes.h:99-104 / :126-133: obs - pCamera->project(T.map(Xw)), T = Tcw or mTrl * Tcw
+    const bool body = D.e_stereo[e] == LBA_EDGE_BODY;
+    const EdgeCam c = edge_cam(D, D.e_kf[e], body);
+    double Xe[3] = {Xc[0], Xc[1], Xc[2]}, uv[2];
+    if (body) {
+      DQuat qrw; double trw[3];
+      const DQuat q = {P[0], P[1], P[2], P[3]};
+      body_pose(D, D.e_kf[e], q, P + 4, qrw, trw);
+      q_rot(qrw, X, Xe);
+      Xe[0] += trw[0]; Xe[1] += trw[1]; Xe[2] += trw[2];
+    }
+    cam_project(c.kb8, c.p, c.k, Xe, uv);
+    r[0] = obs[0] - uv[0]; r[1] = obs[1] - uv[1]; r[2] = 0;
+    return r[0] * (s * r[0]) + r[1] * (s * r[1]);
+  }
   if (D.e_stereo[e]) {
     // types_six_dof_expmap.cpp:190-197: invz is a float
     const double fx = cam[0], fy = cam[1], cx = cam[2], cy = cam[3];
@@ -93,7 +179,7 @@ __device__ __forceinline__ double edge_residual(const LbaDev& D, int e, const do
 // One thread per landmark: linearise all its edges (base_binary_edge.hpp:55-120).
 // (128 registers per thread = 4 resident CTAs per SM; asking the compiler for 5 or 6 CTAs -- 102 / 80 registers
 // with spills -- was measured 3 % and 5 % slower at config 5.)
-template <bool LINEARIZE>
+template <bool LINEARIZE, bool RIG>
 __global__ void __launch_bounds__(128) lin_kernel(LbaDev D) {
   const int l = blockIdx.x * 128 + threadIdx.x;
   if (l >= D.n_mp) return;
@@ -120,18 +206,61 @@ __global__ void __launch_bounds__(128) lin_kernel(LbaDev D) {
     double Xc[3], r[3];
     q_rot(q, X, Xc);
     Xc[0] += P[4]; Xc[1] += P[5]; Xc[2] += P[6];
-    const double e2 = edge_residual(D, e, Xc, r);
+    const double e2 = edge_residual<RIG>(D, e, Xc, r, P, X);
     D.chi2_e[e] = e2;
     double rho0, rho1;
-    robustify(D.e_stereo[e] ? D.hs : D.hm, e2, rho0, rho1);
+    robustify(D.e_stereo[e] == LBA_EDGE_STEREO ? D.hs : D.hm, e2, rho0, rho1);  // body edges: thHuberMono (:1380-1382)
     chi += rho0;
     if (!LINEARIZE) continue;
-    const int d = D.e_stereo[e] ? 3 : 2;
+    const int d = D.e_stereo[e] == LBA_EDGE_STEREO ? 3 : 2;
     const float* cam = D.kf_cam + 5 * k;
     double R[9], A[9], B[18];
     q_to_R(q, R);
     const double x = Xc[0], y = Xc[1], z = Xc[2];
-    if (d == 3) {  // types_six_dof_expmap.cpp:228-274
+    if (RIG && d == 2) {
+      // EdgeSE3ProjectXYZ::linearizeOplus (OptimizableTypes.cpp:139-160) with either camera model:
+      //   Xi = -projectJac(Xc) R,  Xj = -projectJac(Xc) SE3deriv(Xc);
+      // EdgeSE3ProjectXYZToBody::linearizeOplus (:192-213):
+      //   Xi = -projectJac(X_r) (Trl Tlw).rotation(),  Xj = -projectJac(X_r) Rrl SE3deriv(X_l)
+      const bool body = D.e_stereo[e] == LBA_EDGE_BODY;
+      const EdgeCam c = edge_cam(D, k, body);
+      double J[6], Jm[6];
+      if (body) {
+        const double* T = D.kf_trl + 7 * (size_t)k;
+        const DQuat qrl = {T[0], T[1], T[2], T[3]};
+        double Xr[3], Rrl[9], trw[3];
+        q_rot(qrl, Xc, Xr);
+        Xr[0] += T[4]; Xr[1] += T[5]; Xr[2] += T[6];
+        cam_project_jac(c.kb8, c.p, c.k, Xr, J);
+        q_to_R(qrl, Rrl);
+        DQuat qrw;
+        body_pose(D, k, q, P + 4, qrw, trw);
+        q_to_R(qrw, R);  // the landmark Jacobian rotates with the second camera
+#pragma unroll
+        for (int rr = 0; rr < 2; rr++)
+#pragma unroll
+          for (int cc = 0; cc < 3; cc++)
+            Jm[rr * 3 + cc] = -(J[rr * 3] * Rrl[cc] + J[rr * 3 + 1] * Rrl[3 + cc] + J[rr * 3 + 2] * Rrl[6 + cc]);
+      } else {
+        cam_project_jac(c.kb8, c.p, c.k, Xc, J);
+#pragma unroll
+        for (int i = 0; i < 6; i++) Jm[i] = -J[i];
+      }
+#pragma unroll
+      for (int rr = 0; rr < 2; rr++) {
+#pragma unroll
+        for (int cc = 0; cc < 3; cc++)
+          A[rr * 3 + cc] = -(J[rr * 3] * R[cc] + J[rr * 3 + 1] * R[3 + cc] + J[rr * 3 + 2] * R[6 + cc]);
+        const double j0 = Jm[rr * 3], j1 = Jm[rr * 3 + 1], j2 = Jm[rr * 3 + 2];
+        // SE3deriv rows: (0,z,-y,1,0,0) (-z,0,x,0,1,0) (y,-x,0,0,0,1)
+        B[rr * 6 + 0] = -j1 * z + j2 * y; B[rr * 6 + 1] = j0 * z - j2 * x; B[rr * 6 + 2] = -j0 * y + j1 * x;
+        B[rr * 6 + 3] = j0; B[rr * 6 + 4] = j1; B[rr * 6 + 5] = j2;
+      }
+#pragma unroll
+      for (int cc = 0; cc < 3; cc++) A[6 + cc] = 0;
+#pragma unroll
+      for (int cc = 12; cc < 18; cc++) B[cc] = 0;
+    } else if (d == 3) {  // types_six_dof_expmap.cpp:228-274
       const double fx = cam[0], fy = cam[1], bf = cam[4];
       const double z_2 = z * z;
 #pragma unroll
@@ -1277,6 +1406,13 @@ __global__ void depth_kernel(LbaDev D, uint8_t* out) {
   const double* P = D.pose + 7 * (size_t)D.e_kf[e];
   DQuat q = {P[0], P[1], P[2], P[3]};
   double Xc[3];
+  if (D.kf_trl && D.e_stereo[e] == LBA_EDGE_BODY) {  // OptimizableTypes.h:135-139: depth in the second camera
+    DQuat qrw; double trw[3];
+    body_pose(D, D.e_kf[e], q, P + 4, qrw, trw);
+    q_rot(qrw, D.pts + 3 * (size_t)l, Xc);
+    out[e] = (Xc[2] + trw[2]) > 0.0;
+    return;
+  }
   q_rot(q, D.pts + 3 * (size_t)l, Xc);
   out[e] = (Xc[2] + P[6]) > 0.0;
 }
@@ -1465,10 +1601,24 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
   const int nf = (int)nat_kf.size(), n = 6 * nf;
   if (nf == 0) { set_last_error("lba_solve: no free keyframe"); return ORB_E_ARG; }
   std::vector<int> lm_ptr(L + 1, 0);
+  bool any_body = false;
   for (int e = 0; e < E; e++) {
     if (g->e_mp[e] < 0 || g->e_mp[e] >= L || g->e_kf[e] < 0 || g->e_kf[e] >= K) { set_last_error("edge index"); return ORB_E_ARG; }
+    if (g->e_stereo[e] > LBA_EDGE_BODY) { set_last_error("lba_solve: unknown edge type"); return ORB_E_ARG; }
+    any_body |= g->e_stereo[e] == LBA_EDGE_BODY;
     lm_ptr[g->e_mp[e] + 1]++;
   }
+  // rig extension of the view: KannalaBrandt8 cameras and / or second-camera (EdgeSE3ProjectXYZToBody) edges take the
+  // general-camera instantiation of lin_kernel; plain Pinhole windows keep the specialised one
+  bool any_kb8 = false;
+  for (int k = 0; k < K && g->kf_cam_model; k++) any_kb8 |= g->kf_cam_model[k] == ORB_CAM_KB8;
+  if (any_kb8 && !g->kf_cam_dist) { set_last_error("lba_solve: kf_cam_model names a KannalaBrandt8 camera but kf_cam_dist is NULL"); return ORB_E_ARG; }
+  if (any_body && (!g->kf_cam2 || !g->kf_trl)) { set_last_error("lba_solve: LBA_EDGE_BODY edges need kf_cam2 and kf_trl"); return ORB_E_ARG; }
+  for (int k = 0; k < K; k++)
+    if ((g->kf_cam_model && g->kf_cam_model[k] > ORB_CAM_KB8) || (any_body && g->kf_cam2_model && g->kf_cam2_model[k] > ORB_CAM_KB8)) {
+      set_last_error("lba_solve: unknown camera model"); return ORB_E_ARG;
+    }
+  const bool rig = any_kb8 || any_body;
   for (int l = 0; l < L; l++) lm_ptr[l + 1] += lm_ptr[l];
   std::vector<int> perm(E), cursor(lm_ptr.begin(), lm_ptr.end() - 1);
   for (int e = 0; e < E; e++) perm[cursor[g->e_mp[e]]++] = e;   // sorted position -> original edge
@@ -1498,8 +1648,11 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
       }
       const double m = (double)fl.size();
       fsum += 50 + m * (108 + 36) + m * (m + 1) / 2 * 216;
+      // two edges of one landmark on the SAME pose (left + right camera of a rig) contribute both cross terms
+      // Y_a W_b^T and Y_b W_a^T to the pose's diagonal block (g2o adds both edges into one H_pl block)
       for (size_t a = 0; a < fl.size(); a++)
-        for (size_t b = a; b < fl.size(); b++) cnt[(size_t)std::min(fl[a], fl[b]) * nf + std::max(fl[a], fl[b])]++;
+        for (size_t b = a; b < fl.size(); b++)
+          cnt[(size_t)std::min(fl[a], fl[b]) * nf + std::max(fl[a], fl[b])] += (a != b && fl[a] == fl[b]) ? 2 : 1;
     }
     flopsT[t] = fsum;
   });
@@ -1624,7 +1777,7 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
         se_kf[s] = g->e_kf[e];
         se_free[s] = free_idx[g->e_kf[e]];
         se_free[(size_t)E + s] = g->e_mp[e];
-        se_st[s] = g->e_stereo[e] ? 1 : 0;
+        se_st[s] = g->e_stereo[e];
         memcpy(&se_obs[3 * (size_t)s], g->e_obs + 3 * (size_t)e, 3 * sizeof(double));
         se_is2[s] = g->e_inv_sigma2[e];
         if (se_free[s] >= 0) { pc[se_free[s]]++; tmp.push_back(s); }
@@ -1635,6 +1788,11 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
           const int p2 = cur[nat_key(std::min(fa, fb), std::max(fa, fb))]++;
           pair_ea[p2] = fa <= fb ? tmp[a] : tmp[b];
           pair_eb[p2] = fa <= fb ? tmp[b] : tmp[a];
+          if (a != b && fa == fb) {  // same pose twice: the transposed cross term as well (see pass A)
+            const int p3 = cur[nat_key(fa, fa)]++;
+            pair_ea[p3] = tmp[b];
+            pair_eb[p3] = tmp[a];
+          }
         }
     }
   });
@@ -1697,7 +1855,7 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
   // ---- device memory
   size_t gbytes = 256 * 24 + sizeof(int) * 2 * (size_t)n + sizeof(long long) * ((size_t)n + 2) + sizeof(int) * ((size_t)L + 1 + 3 * (size_t)E + nf + (nf + 1) + pose_edges.size() +
                                             2 * (size_t)n_pairs + pair_ptr.size() + 2 * pair_ea.size()) +
-                  (size_t)E * (1 + 24 + 4) + (size_t)K * 20;
+                  (size_t)E * (1 + 24 + 4) + (size_t)K * 20 + (rig ? 256 * 4 + (size_t)K * (1 + 16 + 32 + 56) : 0);
   if (S.graph.reserve(gbytes)) return ORB_E_CUDA;
   uint8_t* gp = (uint8_t*)S.graph.p;
   LbaDev D;
@@ -1717,6 +1875,26 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
   UPLOAD(e_obs, double, se_obs.data(), 3 * (size_t)E);
   UPLOAD(e_is2, float, se_is2.data(), (size_t)E);
   UPLOAD(kf_cam, float, g->kf_cam, 5 * (size_t)K);
+  std::vector<uint8_t> model;  // (function scope: the copies below are asynchronous)
+  std::vector<float> dist, cam2;
+  std::vector<double> trl;
+  if (rig) {
+    model.assign(K, 0);
+    dist.assign(4 * (size_t)K, 0.f); cam2.assign(8 * (size_t)K, 0.f);
+    trl.assign(7 * (size_t)K, 0.0);
+    for (int k = 0; k < K; k++) {
+      if (g->kf_cam_model && g->kf_cam_model[k] == ORB_CAM_KB8) { model[k] |= 1; memcpy(&dist[4 * (size_t)k], g->kf_cam_dist + 4 * (size_t)k, 16); }
+      if (any_body) {
+        if (g->kf_cam2_model && g->kf_cam2_model[k] == ORB_CAM_KB8) model[k] |= 2;
+        memcpy(&cam2[8 * (size_t)k], g->kf_cam2 + 8 * (size_t)k, 32);
+        memcpy(&trl[7 * (size_t)k], g->kf_trl + 7 * (size_t)k, 56);
+      } else trl[7 * (size_t)k + 3] = 1.0;
+    }
+    UPLOAD(kf_model, uint8_t, model.data(), (size_t)K);
+    UPLOAD(kf_dist, float, dist.data(), 4 * (size_t)K);
+    UPLOAD(kf_cam2, float, cam2.data(), 8 * (size_t)K);
+    UPLOAD(kf_trl, double, trl.data(), 7 * (size_t)K);
+  }
   UPLOAD(free_kf, int, free_kf.data(), (size_t)nf);
   UPLOAD(pose_ptr, int, pose_ptr.data(), (size_t)nf + 1);
   UPLOAD(pose_edges, int, pose_edges.data(), pose_edges.size());
@@ -1787,8 +1965,11 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
   // chi (robust) of the current state -> h_scalars[0]; all ranks see the global value
   auto eval_chi = [&](bool linearize) -> int {
     if (L) {
-      if (linearize) lin_kernel<true><<<lm_blocks, 128, 0, st>>>(D);
-      else lin_kernel<false><<<lm_blocks, 128, 0, st>>>(D);
+      if (rig) {  // KannalaBrandt8 cameras / second-camera edges: the general-camera instantiation
+        if (linearize) lin_kernel<true, true><<<lm_blocks, 128, 0, st>>>(D);
+        else lin_kernel<false, true><<<lm_blocks, 128, 0, st>>>(D);
+      } else if (linearize) lin_kernel<true, false><<<lm_blocks, 128, 0, st>>>(D);
+      else lin_kernel<false, false><<<lm_blocks, 128, 0, st>>>(D);
     }
     reduce_kernel<<<1, 1024, 0, st>>>(D.chi_lm, L, D.scalars);
     S.launches += 2;

@@ -60,8 +60,9 @@ class LocalBundleAdjustment:
 
     @classmethod
     def outliers(cls, graph_dict, result):
-        """Edges the reference erases after optimize(): chi2 > 5.991 (mono) / 7.815 (stereo) or depth <= 0."""
-        st = np.asarray(graph_dict["e_stereo"]).astype(bool)
+        """Edges the reference erases after optimize(): chi2 > 5.991 (mono and second-camera edges, Optimizer.cc:1424,
+        :1438) / 7.815 (stereo, :1453) or depth <= 0."""
+        st = np.asarray(graph_dict["e_stereo"]) == 1
         th = np.where(st, cls.CHI2_STEREO, cls.CHI2_MONO)
         return (result["chi2"] > th) | (result["depth_pos"] == 0)
 

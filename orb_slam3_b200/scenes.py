@@ -236,6 +236,79 @@ def lba_graph(n_kf_opt, n_mp, seed=0, fixed_frac=0.1, stereo_frac=0.8, outlier_f
     return g, truth
 
 
+def kb8_project(p8, X):
+    """KannalaBrandt8::project (KannalaBrandt8.cpp:46-65) of points X[...,3], p8 = fx, fy, cx, cy, k0..k3; fp64 throughout
+    (scene generation only: the solvers restate the float atan2f / sqrtf of the reference themselves)."""
+    r = np.hypot(X[..., 0], X[..., 1])
+    th = np.arctan2(r, X[..., 2])
+    psi = np.arctan2(X[..., 1], X[..., 0])
+    t2 = th * th
+    rd = th * (1 + t2 * (p8[4] + t2 * (p8[5] + t2 * (p8[6] + t2 * p8[7]))))
+    return np.stack([p8[0] * rd * np.cos(psi) + p8[2], p8[1] * rd * np.sin(psi) + p8[3]], -1)
+
+
+def lba_rig_graph(n_kf_opt, n_mp, seed=0, model1=1, model2=1, right_frac=0.6, left_drop=0.15, mono_only=False):
+    """LocalBundleAdjustment graph of a two-camera rig (Optimizer.cc:1305-1331 + :1366-1400):
+    the geometry of `lba_graph`, observed by a left camera (mono edges, EdgeSE3ProjectXYZ with pCamera = mpCamera)
+    and a right camera at Trl (body edges, EdgeSE3ProjectXYZToBody with pCamera = mpCamera2); model 1 =
+    KannalaBrandt8 (TUM-VI-like intrinsics), 0 = Pinhole.  A landmark seen by a keyframe has a left observation, a
+    right one, or both (the two edges then share the pose and the landmark).  `mono_only`: a monocular fisheye rig
+    (no second camera, no body edges).  Returns (graph dict incl. the rig fields of lba_graph_view, truth)."""
+    g, truth = lba_graph(n_kf_opt, n_mp, seed=seed, stereo_frac=0.0)
+    rng = np.random.default_rng(seed + 7919)
+    K, E = len(g["kf_fixed"]), len(g["e_kf"])
+    kb_l = np.array([190.97, 190.97, 254.93, 256.89, 0.0034823894, 0.0007150348, -0.0020532361, 0.00020293673], np.float32)
+    kb_r = np.array([190.44, 190.44, 252.59, 254.94, 0.0034003171, 0.0017662782, -0.0026631420, 0.00032997288], np.float32)
+    ph_l = np.array([700.0, 700.0, 640.0, 360.0, 0, 0, 0, 0], np.float32)
+    ph_r = np.array([705.0, 698.0, 633.0, 366.0, 0, 0, 0, 0], np.float32)
+    c1 = kb_l if model1 == 1 else ph_l
+    c2 = kb_r if model2 == 1 else ph_r
+    # Trl: 10 cm baseline and a small relative rotation (a real calibration is never the identity)
+    w = np.array([0.004, -0.011, 0.007])
+    th = np.linalg.norm(w)
+    q_rl = np.concatenate([np.sin(th / 2) * w / th, [np.cos(th / 2)]])
+    t_rl = np.array([-0.1009, 0.0019, 0.0012])
+    trl = np.concatenate([q_rl, t_rl]).astype(np.float32).astype(np.float64)  # Sophus::SE3f cast to double (:1384-1385)
+    trl[:4] /= np.linalg.norm(trl[:4])
+
+    def proj(model, c, X):
+        if model == 1:
+            return kb8_project(c.astype(np.float64), X)
+        return np.stack([c[0] * X[:, 0] / X[:, 2] + c[2], c[1] * X[:, 1] / X[:, 2] + c[3]], -1)
+
+    Tcw, pts = truth["kf_pose"], truth["mp_pos"]
+    Xl = _qrot_many(Tcw[g["e_kf"], :4], pts[g["e_mp"]]) + Tcw[g["e_kf"], 4:]
+    Xr = _qrot_many(trl[None, :4], Xl) + trl[None, 4:]
+    octv = rng.integers(0, 8, (E, 2))
+    sig = 1.2 ** octv
+    uv_l = proj(model1, c1, Xl) + rng.normal(0, 1, (E, 2)) * sig[:, :1]
+    uv_r = proj(model2, c2, Xr) + rng.normal(0, 1, (E, 2)) * sig[:, 1:]
+    out = rng.random((E, 2)) < 0.02
+    uv_l[out[:, 0], 0] += rng.choice([-50.0, 50.0], out[:, 0].sum())
+    uv_r[out[:, 1], 1] += rng.choice([-50.0, 50.0], out[:, 1].sum())
+    has_r = (rng.random(E) < right_frac) & (not mono_only)
+    has_l = ~(has_r & (rng.random(E) < left_drop))
+    inv_sigma2 = (1.0 / (scale_factors() ** 2)).astype(np.float32)
+    il, ir = np.nonzero(has_l)[0], np.nonzero(has_r)[0]
+    # per landmark: the observing keyframes in order, a keyframe's left edge before its right one (:1296-1400)
+    order = np.argsort(np.concatenate([2 * il, 2 * ir + 1]), kind="stable")
+    src = np.concatenate([il, ir])[order]
+    typ = np.concatenate([np.zeros(len(il), np.uint8), np.full(len(ir), 2, np.uint8)])[order]
+    obs = np.where((typ == 0)[:, None], uv_l[src], uv_r[src]).astype(np.float32).astype(np.float64)
+    h = dict(g)
+    h["e_kf"], h["e_mp"], h["e_stereo"] = g["e_kf"][src], g["e_mp"][src], typ
+    h["e_obs"] = np.concatenate([obs, np.full((len(src), 1), -1.0)], 1)
+    h["e_inv_sigma2"] = np.where(typ == 0, inv_sigma2[octv[src, 0]], inv_sigma2[octv[src, 1]]).astype(np.float32)
+    h["kf_cam"] = np.tile(np.concatenate([c1[:4], [0.0]]).astype(np.float32), (K, 1))  # mbf unused: no stereo edges
+    h["kf_cam_model"] = np.full(K, model1, np.uint8)
+    h["kf_cam_dist"] = np.tile(c1[4:], (K, 1))
+    if not mono_only:
+        h["kf_cam2_model"] = np.full(K, model2, np.uint8)
+        h["kf_cam2"] = np.tile(c2, (K, 1))
+        h["kf_trl"] = np.tile(trl, (K, 1))
+    return h, truth
+
+
 def lba_rough_graph(seed=4):
     """Small graph with a wild start and almost no damping: forces rejected LM trials."""
     g, truth = lba_graph(5, 60, seed=seed)
@@ -252,8 +325,9 @@ def permute_keyframes(g, perm):
     inv = np.empty_like(perm)
     inv[perm] = np.arange(len(perm))
     h = dict(g)
-    for k in ("kf_pose", "kf_fixed", "kf_cam"):
-        h[k] = np.ascontiguousarray(g[k][perm])
+    for k in ("kf_pose", "kf_fixed", "kf_cam", "kf_cam_model", "kf_cam_dist", "kf_cam2_model", "kf_cam2", "kf_trl"):
+        if k in g:
+            h[k] = np.ascontiguousarray(g[k][perm])
     h["e_kf"] = inv[g["e_kf"]].astype(np.int32)
     return h
 

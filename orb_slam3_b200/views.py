@@ -129,7 +129,8 @@ class lba_graph_view(C.Structure):
     _fields_ = [("n_kf", _i), ("kf_pose", _vp), ("kf_fixed", _vp), ("kf_cam", _vp),
                 ("n_mp", _i), ("mp_pos", _vp),
                 ("n_edges", _i), ("e_kf", _vp), ("e_mp", _vp), ("e_stereo", _vp), ("e_obs", _vp),
-                ("e_inv_sigma2", _vp)]
+                ("e_inv_sigma2", _vp),
+                ("kf_cam_model", _vp), ("kf_cam_dist", _vp), ("kf_cam2_model", _vp), ("kf_cam2", _vp), ("kf_trl", _vp)]
 
 
 class lba_stats(C.Structure):
@@ -145,11 +146,18 @@ class lba_stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
-def make_lba_graph_view(kf_pose, kf_fixed, kf_cam, mp_pos, e_kf, e_mp, e_stereo, e_obs, e_inv_sigma2):
+def make_lba_graph_view(kf_pose, kf_fixed, kf_cam, mp_pos, e_kf, e_mp, e_stereo, e_obs, e_inv_sigma2,
+                        kf_cam_model=None, kf_cam_dist=None, kf_cam2_model=None, kf_cam2=None, kf_trl=None):
     a = dict(kf_pose=_arr(kf_pose, np.float64), kf_fixed=_arr(kf_fixed, np.uint8), kf_cam=_arr(kf_cam, np.float32),
              mp_pos=_arr(mp_pos, np.float64), e_kf=_arr(e_kf, np.int32), e_mp=_arr(e_mp, np.int32),
              e_stereo=_arr(e_stereo, np.uint8), e_obs=_arr(e_obs, np.float64),
              e_inv_sigma2=_arr(e_inv_sigma2, np.float32))
+    # rig extension (include/orb_b200.h): absent = NULL = one Pinhole camera per keyframe
+    for name, val, dt in (("kf_cam_model", kf_cam_model, np.uint8), ("kf_cam_dist", kf_cam_dist, np.float32),
+                          ("kf_cam2_model", kf_cam2_model, np.uint8), ("kf_cam2", kf_cam2, np.float32),
+                          ("kf_trl", kf_trl, np.float64)):
+        if val is not None:
+            a[name] = _arr(val, dt)
     v = lba_graph_view()
     v.n_kf, v.n_mp, v.n_edges = len(a["kf_fixed"]), len(a["mp_pos"]), len(a["e_kf"])
     for k, arr in a.items():

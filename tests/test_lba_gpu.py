@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-4
 
 
-def _compare(g, ref, got, ctx=""):
+def _compare(g, ref, got, ctx="", chi_tol=1e-6):
     assert got["iterations"] == ref["iterations"], (ctx, got["iterations"], ref["iterations"])
     assert got["stats"]["trials"] == ref["stats"]["trials"], ctx
     for key in ("kf_pose", "mp_pos"):
@@ -27,8 +27,8 @@ def _compare(g, ref, got, ctx=""):
     tgot = got["kf_pose"][:, 4:] - g["kf_pose"][:, 4:]
     rel = np.linalg.norm(tgot - tref) / max(np.linalg.norm(tref), 1e-30)
     assert rel < TOL, (ctx, "delta translation rel", rel)
-    assert abs(got["stats"]["chi2_final"] - ref["stats"]["chi2_final"]) <= 1e-8 * ref["stats"]["chi2_final"]
-    assert np.allclose(got["chi2"], ref["chi2"], rtol=1e-6, atol=1e-6)
+    assert abs(got["stats"]["chi2_final"] - ref["stats"]["chi2_final"]) <= 1e-2 * chi_tol * ref["stats"]["chi2_final"]
+    assert np.allclose(got["chi2"], ref["chi2"], rtol=chi_tol, atol=chi_tol)
     assert np.array_equal(got["depth_pos"], ref["depth_pos"])
 
 
@@ -63,6 +63,46 @@ def test_lba_config5_200kf_80k_landmarks(oracle, lba):
     _compare(g, ref, got, "config5")
     from orb_slam3_b200.optimizer import LocalBundleAdjustment as LBA
     assert np.array_equal(LBA.outliers(g, ref), LBA.outliers(g, got))
+
+
+@pytest.mark.parametrize("K,L,seed,model1,model2,mono_only", [(5, 60, 2, 1, 1, False), (12, 800, 3, 1, 1, False),
+                                                                 (12, 800, 4, 0, 1, False), (12, 800, 5, 1, 0, False),
+                                                                 (12, 800, 6, 0, 0, False), (12, 800, 7, 1, 0, True),
+                                                                 (40, 6000, 8, 1, 1, False)])
+def test_lba_second_camera_and_fisheye_edges(oracle, lba, K, L, seed, model1, model2, mono_only):
+    """EdgeSE3ProjectXYZToBody edges of a two-camera rig (OptimizableTypes.cpp:192-213,
+    Optimizer.cc:1366-1400) and KannalaBrandt8 cameras on the mono edges (:1326), every combination of the two camera
+    models; a keyframe's left and right observation of one landmark share the pose block.  The device evaluates
+    KannalaBrandt8::project's float atan2f in fp64 and rounds once, so single residuals may differ from the host
+    libm's by an ulp of theta or psi (a few 1e-5 px; 2 r dr / sigma^2 is then up to ~1e-3 in an edge's chi2): chi2 is
+    compared at 1e-3, the LM deltas at the 1e-4 bar as everywhere."""
+    g, _ = scenes.lba_rig_graph(K, L, seed=seed, model1=model1, model2=model2, mono_only=mono_only)
+    gv = scenes.lba_view(g)
+    ref, got = oracle.lba_solve(gv), lba(gv)
+    kb8 = model1 == 1 or (model2 == 1 and not mono_only)
+    _compare(g, ref, got, "rig K%d" % K, chi_tol=1e-3 if kb8 else 1e-6)
+    from orb_slam3_b200.optimizer import LocalBundleAdjustment as LBA
+    margin = np.abs(ref["chi2"] - 5.991) > 1e-2   # an edge sitting on the threshold may fall either way
+    assert np.array_equal(LBA.outliers(g, ref)[margin], LBA.outliers(g, got)[margin])
+    if not mono_only:
+        assert (g["e_stereo"] == 2).any()
+
+
+def test_lba_rig_views_are_validated(lba):
+    from orb_slam3_b200._lib import OrbError
+    g, _ = scenes.lba_rig_graph(5, 60, seed=2)
+    h = dict(g)
+    del h["kf_trl"]
+    with pytest.raises(OrbError):
+        lba(scenes.lba_view(h))          # body edges without Trl
+    h = dict(g)
+    del h["kf_cam_dist"]
+    with pytest.raises(OrbError):
+        lba(scenes.lba_view(h))          # a KannalaBrandt8 model without its distortion coefficients
+    h = dict(g)
+    h["e_stereo"] = np.where(g["e_stereo"] == 2, 3, g["e_stereo"]).astype(np.uint8)
+    with pytest.raises(OrbError):
+        lba(scenes.lba_view(h))          # unknown edge type
 
 
 def test_lba_envelope_solver_and_keyframe_order(oracle, lba):

@@ -45,8 +45,28 @@ def _exp_mul(d, pose):
     return out
 
 
-def _residual(pose, X, obs, cam, stereo, float_invz=True):
+def _project(model, p, X, exact_float=True):
+    """GeometricCamera::project(Eigen::Vector3d): Pinhole.cpp:42-48 / KannalaBrandt8.cpp:46-65 (theta and psi through
+    float atan2f / sqrtf; `exact_float=False` keeps them in fp64 for the finite differences)."""
+    p = [float(v) for v in p]
+    if model == 0:
+        return np.array([p[0] * X[0] / X[2] + p[2], p[1] * X[1] / X[2] + p[3]])
+    if exact_float:
+        th = float(np.arctan2(np.sqrt(np.float32(X[0] * X[0] + X[1] * X[1])), np.float32(X[2])))
+        psi = float(np.arctan2(np.float32(X[1]), np.float32(X[0])))
+    else:
+        th, psi = np.arctan2(np.hypot(X[0], X[1]), X[2]), np.arctan2(X[1], X[0])
+    r = th + p[4] * th ** 3 + p[5] * th ** 5 + p[6] * th ** 7 + p[7] * th ** 9
+    return np.array([p[0] * r * np.cos(psi) + p[2], p[1] * r * np.sin(psi) + p[3]])
+
+
+def _residual(pose, X, obs, cam, stereo, float_invz=True, rig=None):
     Xc = _qrot(pose[:4], X) + pose[4:]
+    if stereo == 2:   # EdgeSE3ProjectXYZToBody (OptimizableTypes.h:126-133)
+        Xr = _qrot(rig["trl"][:4], Xc) + rig["trl"][4:]
+        return np.asarray(obs[:2]) - _project(rig["model2"], rig["cam2"], Xr, float_invz)
+    if rig is not None and rig["model1"] == 1:   # EdgeSE3ProjectXYZ with a KannalaBrandt8 camera
+        return np.asarray(obs[:2]) - _project(1, list(cam[:4]) + list(rig["dist"]), Xc, float_invz)
     fx, fy, cx, cy, bf = [float(c) for c in cam]
     if stereo:
         invz = float(np.float32(1.0) / np.float32(Xc[2])) if float_invz else 1.0 / Xc[2]
@@ -68,8 +88,15 @@ def _numpy_lm(g, max_iters=10, lambda_init=0.0):
     dm = float(np.float32(np.sqrt(5.991)))
     ds = float(np.float32(np.sqrt(7.815)))
 
+    def rig_of(k):
+        if "kf_cam_model" not in g:
+            return None
+        return dict(model1=int(g["kf_cam_model"][k]), dist=g["kf_cam_dist"][k],
+                    model2=int(g["kf_cam2_model"][k]) if "kf_cam2_model" in g else 0,
+                    cam2=g["kf_cam2"][k] if "kf_cam2" in g else None, trl=g["kf_trl"][k] if "kf_trl" in g else None)
+
     def huber(e, st):
-        d = ds if st else dm
+        d = ds if st == 1 else dm
         dsqr = float(np.float32(d * d))
         if e <= dsqr:
             return e, 1.0
@@ -77,7 +104,7 @@ def _numpy_lm(g, max_iters=10, lambda_init=0.0):
 
     def errors(pose, pts):
         return [_residual(pose[g["e_kf"][e]], pts[g["e_mp"][e]], g["e_obs"][e], g["kf_cam"][g["e_kf"][e]],
-                          g["e_stereo"][e]) for e in range(ne)]
+                          g["e_stereo"][e], rig=rig_of(g["e_kf"][e])) for e in range(ne)]
 
     def rchi(errs):
         return sum(huber(float(g["e_inv_sigma2"][e]) * float(r @ r), g["e_stereo"][e])[0] for e, r in enumerate(errs))
@@ -93,19 +120,20 @@ def _numpy_lm(g, max_iters=10, lambda_init=0.0):
         for e in range(ne):
             k, l, st = g["e_kf"][e], g["e_mp"][e], g["e_stereo"][e]
             cam, obs = g["kf_cam"][k], g["e_obs"][e]
-            d = 3 if st else 2
+            d = 3 if st == 1 else 2
+            rg = rig_of(k)
             A = np.zeros((d, 3))
             B = np.zeros((d, 6))
             for c in range(3):
                 dx = np.zeros(3)
                 dx[c] = h
-                A[:, c] = (_residual(pose[k], pts[l] + dx, obs, cam, st, False) -
-                           _residual(pose[k], pts[l] - dx, obs, cam, st, False)) / (2 * h)
+                A[:, c] = (_residual(pose[k], pts[l] + dx, obs, cam, st, False, rg) -
+                           _residual(pose[k], pts[l] - dx, obs, cam, st, False, rg)) / (2 * h)
             for c in range(6):
                 dd = np.zeros(6)
                 dd[c] = h
-                B[:, c] = (_residual(_exp_mul(dd, pose[k]), pts[l], obs, cam, st, False) -
-                           _residual(_exp_mul(-dd, pose[k]), pts[l], obs, cam, st, False)) / (2 * h)
+                B[:, c] = (_residual(_exp_mul(dd, pose[k]), pts[l], obs, cam, st, False, rg) -
+                           _residual(_exp_mul(-dd, pose[k]), pts[l], obs, cam, st, False, rg)) / (2 * h)
             s = float(g["e_inv_sigma2"][e])
             _, w = huber(s * float(errs[e] @ errs[e]), st)
             sl = slice(npz + 3 * l, npz + 3 * l + 3)
@@ -166,6 +194,24 @@ def test_oracle_lm_equals_numpy_lm(oracle, seed, lam0):
     dx = np.abs(r["mp_pos"] - pts).max()
     step = np.abs(r["mp_pos"] - g["mp_pos"]).max()
     assert dp < tol and dx < 10 * tol * max(step, 1.0), (dp, dx, step)
+
+
+@pytest.mark.parametrize("model1,model2,mono_only", [(1, 1, False), (0, 1, False), (1, 0, False), (0, 0, False), (1, 0, True)])
+def test_oracle_rig_edges_equal_numpy_lm(oracle, model1, model2, mono_only):
+    """EdgeSE3ProjectXYZToBody (second camera at Trl) and KannalaBrandt8 mono edges -- the
+    oracle's analytic Jacobians (OptimizableTypes.cpp:192-213, KannalaBrandt8.cpp:145-175) against finite differences
+    of an independent residual, through the whole LM loop."""
+    g, _ = scenes.lba_rig_graph(5, 60, seed=2, model1=model1, model2=model2, mono_only=mono_only)
+    assert mono_only or (g["e_stereo"] == 2).sum() > 50
+    r = oracle.lba_solve(scenes.lba_view(g), max_iters=4)
+    pose, pts, chi, trials = _numpy_lm(g, max_iters=4)
+    assert trials == r["stats"]["trials"]
+    assert abs(chi - r["stats"]["chi2_final"]) <= 1e-6 * chi
+    dp = np.abs(r["kf_pose"] - pose).max()
+    dx = np.abs(r["mp_pos"] - pts).max()
+    step = np.abs(r["mp_pos"] - g["mp_pos"]).max()
+    assert dp < 1e-6 and dx < 1e-5 * max(step, 1.0), (dp, dx, step)
+    assert r["depth_pos"].all()
 
 
 def test_fixed_keyframes_and_outputs(oracle):
