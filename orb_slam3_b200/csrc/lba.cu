@@ -884,14 +884,19 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+__device__ __forceinline__ int wmod(int v) { return v & (WIN - 1); }  // v % WIN for v >= 0 (ring indices)
+static_assert((WIN & (WIN - 1)) == 0, "ring size must be a power of two");
+
 // PROF (ORB_B200_LDLT_PROF): cycle counters of the phases as seen by warp 0, printed by lba_solve
 __device__ unsigned long long g_win_prof[32];
 static int win_prof_solves = 0;
 
-template <bool PROF>
+template <bool PROF, bool FWD_MMA>
 __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restrict__ M, int n, const int* __restrict__ reach,
                                                              const int* __restrict__ first_g, double* fail,
-                                                             double* __restrict__ x) {
+                                                             double* __restrict__ x, int flags) {
+  // flags (experiments, ORB_B200_LDLT_FLAGS): bit 0 = equal tile shares for all 15 tile warps (measured +2 %), bit 1 =
+  // generic three-at-a-time tile loop update_run3 (measured +7 %), bit 2 = reversed warp numbering for the roles
   extern __shared__ __align__(16) double win_dyn[];
   double* A = win_dyn;                       // [WIN][WIN_P] ring of the trailing window
   double* zr = A + WIN * WIN_P;              // [WIN] right-hand side entries of the window columns
@@ -902,8 +907,12 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
   double* stg = reinterpret_cast<double*>(rlast + ((((n + WPB - 1) / WPB) + 1) & ~1));  // [12][WIN + 8] rows on their way into the window (n = 6 x poses is even)
   __shared__ double Lb[WPB][WPB];            // pivot block: strict lower = L, diagonal = D
   __shared__ double Dib[WPB];                // 1 / D
+  __shared__ double Gi[WPB][WPB];            // inverse of the unit lower-triangular pivot block (phase (A) on the tensor pipe)
   __shared__ unsigned short tile_ij[(WIN / 8) * (WIN / 8 + 1) / 2];  // lower-triangle tile number -> (ti << 8) | tj
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // flags bit 2 numbers the warps against the hardware's order (a scheduler picks the eligible warp with the highest
+  // hardware id first, so the pivot warp would be served first): measured, no difference (4.06 vs 4.07 ms).
+  const int lane = threadIdx.x & 31;
+  const int warp = (flags & 4) ? (WIN_THREADS / 32 - 1) - (int)(threadIdx.x >> 5) : (int)(threadIdx.x >> 5), tid = warp * 32 + lane;
   const int npan = (n + WPB - 1) / WPB;
   unsigned long long pc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   long long t0 = 0;
@@ -928,7 +937,7 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
     for (int i = lo + (warp - w0); i <= hi; i += nwarps) {
       const int f = first[i];
       const double* Mi = M + (size_t)i * n;
-      double* Ai = A + (i % WIN) * WIN_P;
+      double* Ai = A + (wmod(i)) * WIN_P;
       // a row of the window has at most WIN columns: four loads per lane, all in flight together
       double v[4];
 #pragma unroll
@@ -940,9 +949,9 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
 #pragma unroll
       for (int q = 0; q < 4; q++) {
         const int j = c0 + lane + 32 * q;
-        if (j <= i) Ai[j % WIN] = v[q];
+        if (j <= i) Ai[wmod(j)] = v[q];
       }
-      if (lane == 0) zr[i % WIN] = zv;
+      if (lane == 0) zr[wmod(i)] = zv;
     }
   };
   // pivot block of panel p, one thread, registers only: factors rows/cols [k0, k0+nb) of the ring, leaves L (strict
@@ -952,9 +961,9 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
     double a[WPB][WPB];
 #pragma unroll
     for (int r = 0; r < WPB; r++) {
-      const double* Ar = A + ((k0 + r) % WIN) * WIN_P;
+      const double* Ar = A + (wmod(k0 + r)) * WIN_P;
 #pragma unroll
-      for (int c = 0; c < WPB; c++) a[r][c] = (r < nb && c <= r) ? Ar[(k0 + c) % WIN] : (r == c ? 1.0 : 0.0);
+      for (int c = 0; c < WPB; c++) a[r][c] = (r < nb && c <= r) ? Ar[wmod(k0 + c)] : (r == c ? 1.0 : 0.0);
     }
 #pragma unroll
     for (int k = 0; k < WPB; k++) {
@@ -980,6 +989,25 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
     for (int r = 0; r < WPB; r++)
 #pragma unroll
       for (int c = 0; c <= r; c++) Lb[r][c] = a[r][c];
+  };
+  // G = L_bb^-1 (unit lower triangular) after pivot(): lane r of the pivot's warp forms column r,
+  // g[c] = -sum_{m<c} L[c][m] g[m] below the diagonal (L[c][c] = 1), one uniform instruction stream for the eight
+  // lanes.  Phase (A) multiplies the panel rows by G^T on the tensor pipe instead of substituting one thread per row.
+  auto pivot_inverse = [&]() {
+    __syncwarp();
+    if (lane < WPB) {
+      double g[WPB];
+      g[0] = lane == 0 ? 1.0 : 0.0;
+#pragma unroll
+      for (int c = 1; c < WPB; c++) {
+        double t = 0.0;
+#pragma unroll
+        for (int m = 0; m < c; m++) t += Lb[c][m] * g[m];
+        g[c] = c > lane ? -t : (c == lane ? 1.0 : 0.0);
+      }
+#pragma unroll
+      for (int c = 0; c < WPB; c++) Gi[c][lane] = g[c];
+    }
   };
   auto pivot_store = [&](int p) {  // one warp, in phase (A) of panel p (Lb is stable until the barrier)
     const int k0 = p * WPB, nb = min(WPB, n - k0);
@@ -1007,7 +1035,7 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
     while (t < t_end) {
       const int wi = 8 * ti + fg;
       const double a0 = -Lt[ft * WIN_LP + wi], a1 = -Lt[(ft + 4) * WIN_LP + wi];
-      const int rowoff = (wi >= nr) ? ZR_OFF : ((r0 + wi) % WIN) * WIN_P;  // the rhs row has no column of its own
+      const int rowoff = (wi >= nr) ? ZR_OFF : (wmod(r0 + wi)) * WIN_P;  // the rhs row has no column of its own
       // tiles strictly below the diagonal in a row block that lies inside the window need no element predicates
       // and share the row operands: TG of them at a time, all loads before the first DMMA
       if (8 * ti + 7 <= nr) {
@@ -1018,8 +1046,8 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
           for (int u = 0; u < TG; u++) {
             const int cj = 8 * (tj + u);
             b0[u] = LDt[ft * WIN_LP + cj + fg]; b1[u] = LDt[(ft + 4) * WIN_LP + cj + fg];
-            i0[u] = rowoff + (r0 + cj + 2 * ft) % WIN;
-            i1[u] = rowoff + (r0 + cj + 2 * ft + 1) % WIN;
+            i0[u] = rowoff + wmod(r0 + cj + 2 * ft);
+            i1[u] = rowoff + wmod(r0 + cj + 2 * ft + 1);
             c0[u] = A[i0[u]]; c1[u] = A[i1[u]];
           }
 #pragma unroll
@@ -1035,7 +1063,7 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
         const int wj = 8 * tj + 2 * ft;
         const double b0 = LDt[ft * WIN_LP + 8 * tj + fg], b1 = LDt[(ft + 4) * WIN_LP + 8 * tj + fg];
         const bool ok0 = wi <= nr && wj < nr && wj <= wi, ok1 = wi <= nr && wj + 1 < nr && wj + 1 <= wi;
-        const int i0 = rowoff + (r0 + wj) % WIN, i1 = rowoff + (r0 + wj + 1) % WIN;
+        const int i0 = rowoff + wmod(r0 + wj), i1 = rowoff + wmod(r0 + wj + 1);
         double c0 = ok0 ? A[i0] : 0.0, c1 = ok1 ? A[i1] : 0.0;
         mma2(c0, c1, a0, a1, b0, b1);
         if (ok0) A[i0] = c0;
@@ -1045,21 +1073,59 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
       }
     }
   };
+  // FWD_MMA build: every tile through one path, three at a time with all operand loads first.  A warp runs this as
+  // one dependent instruction stream (one eligible warp per scheduler issues every ~4 cycles), so what counts is the
+  // number of instructions per tile, not their latency: tile coordinates come from the table, the predicates are the
+  // only per-tile branches, and nothing is carried from tile to tile.
+  auto update_run3 = [&](int t_begin, int t_end, int r0, int nr) {
+    constexpr int G = 3;
+    const int acol = ft * WIN_LP + fg, ccol = r0 + 2 * ft;
+    for (int t = t_begin; t < t_end; t += G) {
+      int i0[G], i1[G];
+      bool ok0[G], ok1[G];
+      double a0[G], a1[G], b0[G], b1[G], c0[G], c1[G];
+#pragma unroll
+      for (int u = 0; u < G; u++) {
+        const bool live = t + u < t_end;
+        const int tt = tile_ij[min(t + u, t_end - 1)];
+        const int ti8 = (tt >> 8) * 8, tj8 = (tt & 255) * 8;
+        const int wi = ti8 + fg, wj = tj8 + 2 * ft;
+        a0[u] = -Lt[acol + ti8]; a1[u] = -Lt[acol + 4 * WIN_LP + ti8];
+        b0[u] = LDt[acol + tj8]; b1[u] = LDt[acol + 4 * WIN_LP + tj8];
+        const int rowoff = (wi >= nr) ? ZR_OFF : wmod(r0 + wi) * WIN_P;  // the rhs row has no column of its own
+        ok0[u] = live && wi <= nr && wj < nr && wj <= wi;
+        ok1[u] = live && wi <= nr && wj + 1 < nr && wj + 1 <= wi;
+        i0[u] = rowoff + wmod(ccol + tj8); i1[u] = rowoff + wmod(ccol + tj8 + 1);
+        c0[u] = ok0[u] ? A[i0[u]] : 0.0; c1[u] = ok1[u] ? A[i1[u]] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < G; u++) mma2(c0[u], c1[u], a0[u], a1[u], b0[u], b1[u]);
+#pragma unroll
+      for (int u = 0; u < G; u++) {
+        if (ok0[u]) A[i0[u]] = c0[u];
+        if (ok1[u]) A[i1[u]] = c1[u];
+      }
+    }
+  };
   // the tile of the next pivot block, on the critical path: no tile bookkeeping at all
   auto update_tile0 = [&](int r0, int nr) {
     const int wj = 2 * ft;
     const double a0 = -Lt[ft * WIN_LP + fg], a1 = -Lt[(ft + 4) * WIN_LP + fg];
     const double b0 = LDt[ft * WIN_LP + fg], b1 = LDt[(ft + 4) * WIN_LP + fg];
-    const int rowoff = (fg >= nr) ? ZR_OFF : ((r0 + fg) % WIN) * WIN_P;
+    const int rowoff = (fg >= nr) ? ZR_OFF : (wmod(r0 + fg)) * WIN_P;
     const bool ok0 = fg <= nr && wj < nr && wj <= fg, ok1 = fg <= nr && wj + 1 < nr && wj + 1 <= fg;
-    const int i0 = rowoff + (r0 + wj) % WIN, i1 = rowoff + (r0 + wj + 1) % WIN;
+    const int i0 = rowoff + wmod(r0 + wj), i1 = rowoff + wmod(r0 + wj + 1);
     double c0 = ok0 ? A[i0] : 0.0, c1 = ok1 ? A[i1] : 0.0;
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a0), "d"(b0));
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a1), "d"(b1));
     if (ok0) A[i0] = c0;
     if (ok1) A[i1] = c1;
   };
-  constexpr int FWD_WARPS = WIN / 32;  // warps that can hold a panel row in phase (A)
+  // warps of phase (A): one thread per panel row (WIN / 32 warps hold a whole window), or -- on the tensor pipe --
+  // four 8-row blocks per warp; the other warps bring rows into the window
+  // (measured: eight forward warps + eight loaders is 6 % slower than four + twelve -- 4.06 vs 3.81 ms per optimize(10)
+  // at config 5 -- although phase (A) itself gets shorter)
+  constexpr int FWD_WARPS = WIN / 32;
   constexpr int LD_WARPS = WIN_THREADS / 32 - FWD_WARPS;  // the other warps bring rows into the window
   // A row that panel p+2 adds to the window is copied asynchronously into a staging row during phase (A) of panel
   // p and moved into the ring during phase (A) of panel p+1 (when its slot is free): a whole panel of time for the
@@ -1083,13 +1149,13 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
   auto commit_row = [&]() {
     if (pf_row < 0) return;
     cp_async_wait<0>();
-    double* Ai = A + (pf_row % WIN) * WIN_P;
+    double* Ai = A + (wmod(pf_row)) * WIN_P;
 #pragma unroll
     for (int q = 0; q < 4; q++) {
       const int j = pf_c0 + lane + 32 * q;
-      if (j <= pf_row) Ai[j % WIN] = my_stg[lane + 32 * q];
+      if (j <= pf_row) Ai[wmod(j)] = my_stg[lane + 32 * q];
     }
-    if (lane == 0) zr[pf_row % WIN] = my_stg[WIN];
+    if (lane == 0) zr[wmod(pf_row)] = my_stg[WIN];
     pf_row = -1;
   };
   // first new row of panel q's window (q >= 1), as phase (A) of panel q-1 computes it
@@ -1104,7 +1170,10 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
     if (i <= rlast[1]) prefetch_row(i, WPB);
   }
   __syncthreads();
-  if (tid == 0) pivot(0);
+  if (warp == 0) {
+    if (tid == 0) pivot(0);
+    if (FWD_MMA) pivot_inverse();
+  }
   __syncthreads();
   if (PROF) asm volatile("mov.u64 %0, %%clock64;" : "=l"(t0) :: "memory");
   for (int p = 0; p < npan; p++) {
@@ -1117,13 +1186,49 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
     // ---- (A) panel rows [k0+nb, R] and the rhs row: forward substitution, one thread per row.  The other warps
     //      bring in the rows the NEXT panel adds to the window (their ring slots are free: the window of panel p+1
     //      starts at r0), so the global-memory latency is off the chain.
-    if (tid <= nr) {
+    if (FWD_MMA) {
+      // (L*D) rows = A_rows * L_bb^-T: one 8-row block per warp trip, two fp64 DMMA m8n8k4 (A[g][t] = window row
+      // g, panel column t / t+4; B[t][g] = G[g][t] / G[g][t+4]; C[g][2t], C[g][2t+1]); L = (L*D) / D.  The rhs row
+      // is row nr of the window (zr).  Blocks of a warp are independent: all operand loads first.
+      if (warp < FWD_WARPS) {
+        const int nblk = (nr + 1 + 7) >> 3;
+        const double g0 = Gi[fg][ft], g1 = Gi[fg][ft + 4];
+        const double di0 = Dib[2 * ft], di1 = Dib[2 * ft + 1];
+        constexpr int FB = (WIN / 8 + FWD_WARPS - 1) / FWD_WARPS;  // row blocks per forward warp
+        double a0[FB], a1[FB], c0[FB], c1[FB];
+#pragma unroll
+        for (int u = 0; u < FB; u++) {
+          const int wi = 8 * (warp + u * FWD_WARPS) + fg;
+          const bool valid = warp + u * FWD_WARPS < nblk && wi <= nr;
+          const int rowoff = (wi >= nr) ? ZR_OFF : (wmod(r0 + wi)) * WIN_P;
+          a0[u] = (valid && ft < nb) ? A[rowoff + wmod(k0 + ft)] : 0.0;
+          a1[u] = (valid && ft + 4 < nb) ? A[rowoff + wmod(k0 + ft + 4)] : 0.0;
+          c0[u] = 0.0; c1[u] = 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < FB; u++)
+          if (warp + u * FWD_WARPS < nblk) mma2(c0[u], c1[u], a0[u], a1[u], g0, g1);
+#pragma unroll
+        for (int u = 0; u < FB; u++) {
+          if (warp + u * FWD_WARPS >= nblk) continue;
+          const int wi = 8 * (warp + u * FWD_WARPS) + fg;
+          const double l0 = c0[u] * di0, l1 = c1[u] * di1;   // columns >= nb: c = 0 (a = 0 there and G is triangular)
+          Lt[(2 * ft) * WIN_LP + wi] = l0; Lt[(2 * ft + 1) * WIN_LP + wi] = l1;
+          LDt[(2 * ft) * WIN_LP + wi] = c0[u]; LDt[(2 * ft + 1) * WIN_LP + wi] = c1[u];
+          if (wi <= nr) {
+            double* dst = M + (size_t)(wi == nr ? n : r0 + wi) * n + k0 + 2 * ft;
+            if (2 * ft + 1 < nb) *reinterpret_cast<double2*>(dst) = make_double2(l0, l1);  // n even, k0 % 8 == 0: 16-byte aligned
+            else if (2 * ft < nb) dst[0] = l0;
+          }
+        }
+      }
+    } else if (tid <= nr) {
       const bool rhs = tid == nr;
       const int i = r0 + tid;
-      double* src = rhs ? zr : A + (i % WIN) * WIN_P;
+      double* src = rhs ? zr : A + (wmod(i)) * WIN_P;
       double ld[WPB], l[WPB];
 #pragma unroll
-      for (int m = 0; m < WPB; m++) ld[m] = m < nb ? src[(k0 + m) % WIN] : 0.0;
+      for (int m = 0; m < WPB; m++) ld[m] = m < nb ? src[wmod(k0 + m)] : 0.0;
 #pragma unroll
       for (int m = 1; m < WPB; m++)
 #pragma unroll
@@ -1169,14 +1274,23 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
         __syncwarp();
         tick(2);
         if (tid == 0 && more) pivot(p + 1);
+        if (FWD_MMA && more) pivot_inverse();
         tick(6);
+      } else if (FWD_MMA && (flags & 1)) {
+        // equal shares: the pivot warp's chain (tile, 8 reciprocals, inverse) is longer than any share
+        const int per = (ntile - 1 + 14) / 15;
+        const int tb = 1 + (warp - 1) * per;
+        if (flags & 2) update_run3(min(tb, ntile), min(tb + per, ntile), r0, nr);
+        else update_run(min(tb, ntile), min(tb + per, ntile), r0, nr);
+        tick(2);
       } else {
         const int T = ntile - 1;
         const int light = T / 22, heavy = (T - 3 * light + 11) / 12;
         int tb, te;
         if (warp & 3) { tb = 1 + (warp - 1 - (warp >> 2)) * heavy; te = tb + heavy; }
         else { const int rest = max(T - 12 * heavy, 0), per = (rest + 2) / 3; tb = 1 + 12 * heavy + ((warp >> 2) - 1) * per; te = tb + per; }
-        update_run(min(tb, ntile), min(te, ntile), r0, nr);
+        if (FWD_MMA && (flags & 2)) update_run3(min(tb, ntile), min(te, ntile), r0, nr);
+        else update_run(min(tb, ntile), min(te, ntile), r0, nr);
         tick(2);
       }
     }
@@ -2041,14 +2155,21 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
         const size_t smem = sizeof(double) * (WIN * WIN_P + WIN + 2 * WPB * WIN_LP + (WIN_THREADS / 32 - WIN / 32) * (WIN + 8)) +
                             sizeof(int) * ((size_t)n + (n + WPB - 1) / WPB + 4);
         static const bool win_prof = getenv("ORB_B200_LDLT_PROF") != nullptr;
-        if (win_prof) {
-          CUDA_TRYL(raise_dynamic_smem((const void*)ldlt_win_kernel<true>, smem, S.device));
-          ldlt_win_kernel<true><<<1, WIN_THREADS, smem, st>>>(D.S, n, d_env_reach, d_env_first, D.scalars + 3, D.x);
-          win_prof_solves++;
-        } else {
-          CUDA_TRYL(raise_dynamic_smem((const void*)ldlt_win_kernel<false>, smem, S.device));
-          ldlt_win_kernel<false><<<1, WIN_THREADS, smem, st>>>(D.S, n, d_env_reach, d_env_first, D.scalars + 3, D.x);
+        // ORB_B200_LDLT_FWD=thread: the forward substitution of the panel rows one thread per row (the A/B baseline
+        // of profiles/r2_summary.md) instead of on the tensor pipe through the inverse pivot block
+        static const bool fwd_thread = getenv("ORB_B200_LDLT_FWD") && !strcmp(getenv("ORB_B200_LDLT_FWD"), "thread");
+        const void* kfn = win_prof ? (fwd_thread ? (const void*)ldlt_win_kernel<true, false> : (const void*)ldlt_win_kernel<true, true>)
+                                   : (fwd_thread ? (const void*)ldlt_win_kernel<false, false> : (const void*)ldlt_win_kernel<false, true>);
+        CUDA_TRYL(raise_dynamic_smem(kfn, smem, S.device));
+        {
+          double* Mp = D.S; int nn = n; const int* rp = d_env_reach; const int* fp = d_env_first;
+          double* failp = D.scalars + 3; double* xp = D.x;
+          static const int win_flags = getenv("ORB_B200_LDLT_FLAGS") ? atoi(getenv("ORB_B200_LDLT_FLAGS")) : 0;
+          int fl = win_flags;
+          void* args[] = {&Mp, &nn, &rp, &fp, &failp, &xp, &fl};
+          CUDA_TRYL(cudaLaunchKernel(kfn, dim3(1), dim3(WIN_THREADS), args, smem, st));
         }
+        if (win_prof) win_prof_solves++;
         S.launches += 1;
       } else if (use_sky) {
         const size_t smem = sizeof(double) * 2 * 32 * SKY_WMAX;
