@@ -531,7 +531,8 @@ def run_lba_gpu(rank, world, device):
             "chi2_initial": best["chi2_initial"], "chi2_final": best["chi2_final"],
             "stage_ms": {k: best[k] for k in ("ms_linearize", "ms_schur", "ms_solve", "ms_update")},
             "reduced_solver": {0: "dense cooperative LDLT", 1: "envelope LDLT (32-column panels, one CTA)",
-                               2: "window-resident envelope LDLT (8-column panels, one CTA)"}[best["solver_kind"]],
+                               2: "window-resident envelope LDLT (8-column panels, one CTA)",
+                               3: "window-resident envelope LDLT from both ends (two CTAs + dense separator block)"}[best["solver_kind"]],
             "envelope_rows_max": best["envelope_rows_max"],
             "schur_gflops_sparse": 1e3 * schur_tf,
             "roofline": {"bound": "tensor", "kernel": "schur_pairs_kernel (fp64 DMMA m8n8k4)", "achieved": schur_tf,

@@ -281,7 +281,8 @@ typedef struct lba_stats {
   int32_t n_free_kf, n_pairs;
   double schur_flops;         /* block-sparse useful flops per trial */
   int32_t solver_kind;        /* reduced solve: 0 = dense cooperative LDL^T (all SMs), 1 = envelope LDL^T, 32-column panels
-                               * (one CTA), 2 = window-resident envelope LDL^T, 8-column panels (one CTA, shared memory) */
+                               * (one CTA), 2 = window-resident envelope LDL^T, 8-column panels (one CTA, shared memory),
+                               * 3 = the same from both ends at once (two CTAs + a dense separator block) */
   int32_t envelope_rows_max;  /* tallest panel window of the row envelope of S (rows) */
   double ms_host_prep;        /* host wall time before the first kernel: edge sort, CSRs, pair lists, ordering, uploads queued */
   double ms_wall;             /* host wall time of the whole call (prep + H2D + kernels + D2H + un-sort) */

@@ -26,6 +26,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <float.h>
+#include <limits.h>
 #include <stdlib.h>
 #include <math.h>
 #include <string.h>
@@ -891,10 +892,30 @@ static_assert((WIN & (WIN - 1)) == 0, "ring size must be a power of two");
 __device__ unsigned long long g_win_prof[32];
 static int win_prof_solves = 0;
 
+// One side of a solve: the matrix (its own (n+1) x n buffer), its envelope tables, and -- for the two-sided solve --
+// where the side stops.  WinArgs.mode: 0 = factor everything and back-substitute (one CTA, side 0);
+// 1 = factor panels [0, pend) and write the window that is left (the separator rows with this side's Schur
+// update applied, + their right-hand side entries) to `dump` (row pitch wd = esep - ksep, rhs at dump[wd * wd]);
+// 2 = back-substitute columns [0, ksep) given the separator's solution xs.  Modes 1 and 2 run one CTA per side.
+struct WinSide {
+  double* M; const int* reach; const int* first; double* dump;
+  int n, pend, ksep, esep;
+};
+struct WinArgs {
+  WinSide s[2];
+  double* fail; double* x; const double* xs;
+  int flags, mode, msep;  // msep: first separator column in the caller's numbering (side 1 runs in reversed numbering)
+};
+
 template <bool PROF, bool FWD_MMA>
-__global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restrict__ M, int n, const int* __restrict__ reach,
-                                                             const int* __restrict__ first_g, double* fail,
-                                                             double* __restrict__ x, int flags) {
+__global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(const WinArgs wa) {
+  const WinSide& sd = wa.s[blockIdx.x];
+  double* __restrict__ M = sd.M;
+  const int n = sd.n, flags = wa.flags, mode = wa.mode;
+  const int* __restrict__ reach = sd.reach;
+  const int* __restrict__ first_g = sd.first;
+  double* fail = wa.fail;
+  double* __restrict__ x = wa.x;
   // flags (experiments, ORB_B200_LDLT_FLAGS): bit 0 = equal tile shares for all 15 tile warps (measured +2 %), bit 1 =
   // generic three-at-a-time tile loop update_run3 (measured +7 %), bit 2 = reversed warp numbering for the roles
   extern __shared__ __align__(16) double win_dyn[];
@@ -1164,22 +1185,25 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
     const int preq = min(r0q + WPB - 1, n - 1);
     return max(rlast[q - 1], preq) + 1;
   };
-  load_rows(0, rlast[0], 0, 0, WIN_THREADS / 32);
-  if (warp >= FWD_WARPS && npan > 1) {
-    const int i = new_rows_lo(1) + (warp - FWD_WARPS);
-    if (i <= rlast[1]) prefetch_row(i, WPB);
-  }
-  __syncthreads();
-  if (warp == 0) {
-    if (tid == 0) pivot(0);
-    if (FWD_MMA) pivot_inverse();
+  const int pend = mode == 1 ? sd.pend : (mode == 2 ? 0 : npan);  // panels this CTA eliminates
+  if (pend > 0) {
+    load_rows(0, rlast[0], 0, 0, WIN_THREADS / 32);
+    if (warp >= FWD_WARPS && pend > 1) {
+      const int i = new_rows_lo(1) + (warp - FWD_WARPS);
+      if (i <= rlast[1]) prefetch_row(i, WPB);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      if (tid == 0) pivot(0);
+      if (FWD_MMA) pivot_inverse();
+    }
   }
   __syncthreads();
   if (PROF) asm volatile("mov.u64 %0, %%clock64;" : "=l"(t0) :: "memory");
-  for (int p = 0; p < npan; p++) {
+  for (int p = 0; p < pend; p++) {
     const int k0 = p * WPB, nb = min(WPB, n - k0);
     const int R = rlast[p];  // last row of the window; rows [k0, R] are resident, the pivot block is factored
-    const bool more = p + 1 < npan;
+    const bool more = p + 1 < pend;
     // rows of the next pivot block that are not resident yet (narrow or ending envelope) are loaded by warp 0 in (B)
     const int r0 = k0 + nb, nr = R - r0 + 1;  // nr rows under the pivot block; slot nr = rhs
     const int pre = more ? min(r0 + WPB - 1, n - 1) : R;
@@ -1251,7 +1275,7 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
       if (more) {
         const int lo1 = max(R, pre) + 1 + LD_WARPS;  // rows beyond one per loader warp: directly
         if (lo1 <= rlast[p + 1]) load_rows(lo1, rlast[p + 1], r0, FWD_WARPS, LD_WARPS);
-        if (p + 2 < npan) {
+        if (p + 2 < pend) {
           const int i = new_rows_lo(p + 2) + (warp - FWD_WARPS);
           if (i <= rlast[p + 2]) prefetch_row(i, r0 + WPB);
         }
@@ -1306,10 +1330,29 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
   //      block are formed up front (one thread per block, staged in the dead ring), x_b = G acc_b is evaluated for
   //      all blocks after the loop (acc_b is final once its step is done), the rows of L are fetched two steps
   //      ahead through a running pointer and turned into the thread's row of P while it waits.
+  if (mode == 1) {
+    // the window that is left: rows [ks, R] x columns [ks, row] of the ring (entries left of a row's envelope were
+    // zeroed when the row came in) and their rhs entries -- the separator block with this side's update applied
+    const int ks = pend * WPB, R = rlast[pend - 1], wd = sd.esep - sd.ksep;
+    for (int i = ks + warp; i <= R; i += WIN_THREADS / 32) {
+      const double* Ai = A + wmod(i) * WIN_P;
+      for (int j = ks + lane; j <= i; j += 32) sd.dump[(size_t)(i - ks) * wd + (j - ks)] = Ai[wmod(j)];
+    }
+    for (int j = ks + tid; j <= R; j += WIN_THREADS) sd.dump[(size_t)wd * wd + (j - ks)] = zr[wmod(j)];
+    return;
+  }
+  // mode 2: columns >= ksep are solved (the separator, xs) or belong to the other side (zero here): their blocks
+  // enter the loop below with an identity pivot block and only update columns < ksep
+  const int ksep = mode == 2 ? sd.ksep : n, esep = mode == 2 ? sd.esep : n;
   double* acc = A;            // [n]
   double* pblk = A + n;       // [npan][28]: Linv[c][r], r < c, at c(c-1)/2 + r   (n + 29 npan <= WIN * WIN_P: host-checked)
   int* jmb = reinterpret_cast<int*>(pblk + (size_t)npan * 28);  // [npan] first column of the block's row window
-  for (int i = tid; i < n; i += WIN_THREADS) acc[i] = M[(size_t)n * n + i];
+  for (int i = tid; i < n; i += WIN_THREADS) {
+    double v = 0.0;
+    if (i < ksep) v = M[(size_t)n * n + i];
+    else if (i < esep) v = wa.xs[(blockIdx.x ? n - 1 - i : i) - wa.msep];  // side 1 counts from the other end
+    acc[i] = v;
+  }
   for (int bq = tid; bq < npan; bq += WIN_THREADS) {
     const int k0 = bq * WPB, nb = min(WPB, n - k0);
     int jmv = k0;
@@ -1318,7 +1361,7 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
 #pragma unroll
     for (int c = 1; c < WPB; c++)
 #pragma unroll
-      for (int r = 0; r < c; r++) Lq[c][r] = (k0 + c < n) ? M[(size_t)(k0 + c) * n + k0 + r] : 0.0;
+      for (int r = 0; r < c; r++) Lq[c][r] = (k0 + c < n && k0 < ksep) ? M[(size_t)(k0 + c) * n + k0 + r] : 0.0;
     // inverse of the unit lower triangle, row by row: Li[c][r] = -(L[c][r] + sum_{r<m<c} L[c][m] Li[m][r])
 #pragma unroll
     for (int c = 1; c < WPB; c++)
@@ -1347,7 +1390,7 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
       double* dst = bsr + (bq & 3) * (WPB * WIN) + tid;
 #pragma unroll
       for (int r = 0; r < WPB; r++) {
-        const bool valid = r < nb && j < k0;
+        const bool valid = r < nb && j < min(k0, ksep);
         cp_async8(dst + r * WIN, valid ? src + (size_t)r * n : M, valid);
       }
       cp_async_commit();
@@ -1367,7 +1410,7 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
         Pc[c] = t;
       }
     };
-    const int b0 = npan - 1;
+    const int b0 = (esep + WPB - 1) / WPB - 1;  // = npan - 1 unless the blocks beyond the separator are skipped
     fetch(b0);
     if (b0 > 0) fetch(b0 - 1); else cp_async_commit();
     cp_async_wait<1>();
@@ -1378,7 +1421,7 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
       const int k0 = bq * WPB;
       const int j = jmb[bq] + tid;
       // ---- the chain (only the last block can be short: its missing slots read as zero)
-      if (j < k0) {
+      if (j < min(k0, ksep)) {
         double ab[WPB];
 #pragma unroll
         for (int c = 0; c < WPB; c++) ab[c] = (k0 + c < n) ? acc[k0 + c] : 0.0;
@@ -1404,13 +1447,15 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
   __syncthreads();
   tick(14);
   // x_b = G acc_b for every block at once: G[r][c] = Linv[c][r] (c > r), 1 on the diagonal
-  for (int i = tid; i < n; i += WIN_THREADS) {
+  for (int i = tid; i < ksep; i += WIN_THREADS) {
     const int bq = i / WPB, r = i - bq * WPB, k0 = bq * WPB, nb = min(WPB, n - k0);
     const double* pb = pblk + bq * 28;
     double xv = acc[i];
     for (int c = r + 1; c < nb; c++) xv += pb[c * (c - 1) / 2 + r] * acc[k0 + c];
-    x[i] = xv;
+    x[blockIdx.x ? n - 1 - i : i] = xv;
   }
+  if (mode == 2 && blockIdx.x == 0)
+    for (int i = ksep + tid; i < esep; i += WIN_THREADS) x[i] = wa.xs[i - ksep];
   if (PROF) {
     tick(4);
     if (tid == 0 || tid == 32)
@@ -1418,6 +1463,57 @@ __global__ void __launch_bounds__(WIN_THREADS) ldlt_win_kernel(double* __restric
     if (tid == 0) {  // back-substitution in detail; slot 4 is then only the x pass
       for (int k = 8; k < 16; k++) atomicAdd(&g_win_prof[8 + k], pc[k]);
     }
+  }
+}
+
+// ---- two-sided reduced solve ("burn at both ends")
+// The pivot chain of ldlt_win_kernel is sequential, but an envelope matrix can be eliminated from both ends at once:
+// the first m columns top-down by one CTA, the last n - e columns bottom-up by a second CTA (= top-down on the matrix
+// with rows and columns in reverse order, P S P), where [m, e) -- the separator -- is wide enough that no row >= e
+// reaches a column < m.  Each side leaves its Schur update of the separator block; the updates add up, the separator
+// (a dense block of <= WIN_ROWS - 8 unknowns) is factored and solved by one CTA, and the two sides back-substitute
+// in parallel.  Same arithmetic per pivot as the one-sided kernel, half the chain; the order of the operations is
+// fixed, so a solve stays bitwise reproducible.
+//
+// rev_gather_kernel: side 1's matrix M1 = P S P inside its (monotone) row envelope first1, rows [0, e1); the
+// separator block and the separator's rhs entries start from zero there, so that side 1's window ends up holding
+// only its update (-Delta_B).  One CTA per row of M1 (+ one for the rhs row).
+__global__ void __launch_bounds__(128) rev_gather_kernel(const double* __restrict__ S, double* __restrict__ M1, int n,
+                                                         const int* __restrict__ first1, int m1, int e1) {
+  const int a = blockIdx.x;
+  if (a == e1) {  // rhs row
+    for (int b = threadIdx.x; b < e1; b += 128) M1[(size_t)n * n + b] = b >= m1 ? 0.0 : S[(size_t)n * n + (n - 1 - b)];
+    return;
+  }
+  const int j = n - 1 - a;
+  for (int b = first1[a] + threadIdx.x; b <= a; b += 128) {
+    const int i = n - 1 - b;  // i >= j: S[i][j] is a lower-triangle entry
+    M1[(size_t)a * n + b] = (a >= m1 && b >= m1) ? 0.0 : S[(size_t)i * n + j];
+  }
+}
+// sep_merge_kernel: the separator system (w unknowns, dense lower triangle + rhs row, row pitch w) =
+// side 0's window (S - Delta_T on rows <= R0, the untouched S below) + side 1's window (-Delta_B, in reversed
+// numbering, rows <= R1).  One CTA per separator row (+ one for the rhs).
+__global__ void __launch_bounds__(128) sep_merge_kernel(const double* __restrict__ S, int n, int m, int w, int R0, int m1, int R1,
+                                                        const double* __restrict__ dump0, const double* __restrict__ dump1,
+                                                        double* __restrict__ Msep) {
+  const int si = blockIdx.x;
+  if (si == w) {
+    for (int t = threadIdx.x; t < w; t += 128) {
+      const int i = m + t, a = n - 1 - i;
+      double v = i <= R0 ? dump0[(size_t)w * w + t] : S[(size_t)n * n + i];
+      if (a <= R1) v += dump1[(size_t)w * w + (a - m1)];
+      Msep[(size_t)w * w + t] = v;
+    }
+    return;
+  }
+  const int i = m + si;
+  for (int sj = threadIdx.x; sj <= si; sj += 128) {
+    const int j = m + sj;
+    double v = i <= R0 ? dump0[(size_t)si * w + sj] : S[(size_t)i * n + j];
+    const int a = n - 1 - j, b = n - 1 - i;  // the same entry in side 1's numbering (a >= b)
+    if (a <= R1) v += dump1[(size_t)(a - m1) * w + (b - m1)];
+    Msep[(size_t)si * w + sj] = v;
   }
 }
 
@@ -1966,10 +2062,50 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
   if (ldlt_env && !strcmp(ldlt_env, "dense")) use_sky = false;
   if (ldlt_env && !strcmp(ldlt_env, "sky")) use_sky = sky_rows_max <= SKY_WMAX - 4 && n <= 32 * SKY_WMAX;
   bool use_win = win_ok && !(ldlt_env && (!strcmp(ldlt_env, "sky") || !strcmp(ldlt_env, "dense")));
+  // ---- two-sided plan (see rev_gather_kernel): side 0 eliminates the panels [0, ts_p0), side 1 -- in reversed
+  //      numbering -- the panels [0, ts_p1) = the last 8 ts_p1 columns; separator [ts_m, ts_e2).  ORB_B200_LDLT=win
+  //      pins the one-sided kernel, =win2 takes the two-sided one whenever a separator exists; automatic: from 50
+  //      panels on (the separator's own dense factorisation and the four extra launches cost about 15 panels).
+  bool use_two = false;
+  int ts_m = 0, ts_e2 = 0, ts_p0 = 0, ts_p1 = 0, ts_w = 0, ts_R0 = 0, ts_R1 = 0;
+  std::vector<int> first1, reach1;
+  if (use_win && !(ldlt_env && !strcmp(ldlt_env, "win")) && ((ldlt_env && !strcmp(ldlt_env, "win2")) || n >= 50 * WPB)) {
+    first1.resize(n); reach1.assign(n, 0);
+    for (int a = 0; a < n; a++) first1[a] = n - 1 - env_reach[n - 1 - a];  // column envelope of S = row envelope of P S P
+    for (int a = 0; a < n; a++) reach1[first1[a]] = std::max(reach1[first1[a]], a);
+    for (int c = 1; c < n; c++) reach1[c] = std::max(reach1[c], reach1[c - 1]);
+    int rows1 = 0;
+    for (int k0 = 0; k0 < n; k0 += WPB) {
+      const int nb = std::min(WPB, n - k0);
+      const int R = std::min(std::max(reach1[k0 + nb - 1], k0 + nb - 1), n - 1);
+      int jmin = k0;
+      for (int r = 0; r < nb; r++) jmin = std::min(jmin, first1[k0 + r]);
+      rows1 = std::max(rows1, std::max(R - k0 + 1, k0 - jmin + nb));
+    }
+    int best = INT_MAX;
+    for (int pm = 1; rows1 <= WIN_ROWS && WPB * pm < n; pm++) {
+      const int m = WPB * pm, e = env_reach[m - 1] + 1;  // rows >= e do not reach a column < m
+      const int p1 = (n - e) / WPB;
+      if (p1 < 1) break;
+      const int e2 = n - WPB * p1, w = e2 - m;
+      if (w < WPB || w > WIN_ROWS - WPB) continue;
+      if (std::max(pm, p1) < best) {
+        best = std::max(pm, p1);
+        ts_m = m; ts_e2 = e2; ts_p0 = pm; ts_p1 = p1; ts_w = w;
+      }
+    }
+    if (best != INT_MAX) {
+      use_two = true;
+      ts_R0 = std::min(std::max(env_reach[ts_m - 1], ts_m - 1), n - 1);
+      const int m1 = WPB * ts_p1;
+      ts_R1 = std::min(std::max(reach1[m1 - 1], m1 - 1), n - 1);
+    }
+  }
   // ---- device memory
   size_t gbytes = 256 * 24 + sizeof(int) * 2 * (size_t)n + sizeof(long long) * ((size_t)n + 2) + sizeof(int) * ((size_t)L + 1 + 3 * (size_t)E + nf + (nf + 1) + pose_edges.size() +
                                             2 * (size_t)n_pairs + pair_ptr.size() + 2 * pair_ea.size()) +
-                  (size_t)E * (1 + 24 + 4) + (size_t)K * 20 + (rig ? 256 * 4 + (size_t)K * (1 + 16 + 32 + 56) : 0);
+                  (size_t)E * (1 + 24 + 4) + (size_t)K * 20 + (rig ? 256 * 4 + (size_t)K * (1 + 16 + 32 + 56) : 0) +
+                  (use_two ? 256 * 4 + sizeof(int) * (2 * (size_t)n + 2 * (size_t)ts_w) : 0);
   if (S.graph.reserve(gbytes)) return ORB_E_CUDA;
   uint8_t* gp = (uint8_t*)S.graph.p;
   LbaDev D;
@@ -2026,6 +2162,23 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
     CUDA_TRYL(cudaMemcpyAsync(dptr, env_reach.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
     d_env_reach = dptr;
   }
+  const int *d_first1 = nullptr, *d_reach1 = nullptr, *d_sep_first = nullptr, *d_sep_reach = nullptr;
+  std::vector<int> sep_first, sep_reach;
+  if (use_two) {
+    sep_first.assign(ts_w, 0); sep_reach.assign(ts_w, ts_w - 1);  // the separator block is dense
+    int* dptr = carve<int>(gp, (size_t)n);
+    CUDA_TRYL(cudaMemcpyAsync(dptr, first1.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
+    d_first1 = dptr;
+    dptr = carve<int>(gp, (size_t)n);
+    CUDA_TRYL(cudaMemcpyAsync(dptr, reach1.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
+    d_reach1 = dptr;
+    dptr = carve<int>(gp, (size_t)ts_w);
+    CUDA_TRYL(cudaMemcpyAsync(dptr, sep_first.data(), sizeof(int) * ts_w, cudaMemcpyHostToDevice, st));
+    d_sep_first = dptr;
+    dptr = carve<int>(gp, (size_t)ts_w);
+    CUDA_TRYL(cudaMemcpyAsync(dptr, sep_reach.data(), sizeof(int) * ts_w, cudaMemcpyHostToDevice, st));
+    d_sep_reach = dptr;
+  }
   const long long* d_env_rowp = nullptr;
   {
     long long* dptr = carve<long long>(gp, (size_t)n + 2);
@@ -2036,7 +2189,8 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
   const size_t nS = (size_t)(n + 1) * n;
   size_t wbytes = 256 * 32 + sizeof(double) * (14 * (size_t)K + 6 * (size_t)L + (size_t)L * (6 + 3 + 9 + 3 + 1) +
                                                (size_t)E * (18 + 18 + HPE_STRIDE + 6 + 1) + (size_t)nf * 42 + nS + (S.world > 1 ? env_total : 1) +
-                                               (size_t)n + 3 * (size_t)L + (size_t)nf + L + 16) + (size_t)E;
+                                               (size_t)n + 3 * (size_t)L + (size_t)nf + L + 16) + (size_t)E +
+                  (use_two ? 256 * 5 + sizeof(double) * (nS + 3 * ((size_t)ts_w + 1) * ts_w + WIN) : 0);
   if (S.work.reserve(wbytes)) return ORB_E_CUDA;
   uint8_t* wp = (uint8_t*)S.work.p;
   D.pose = carve<double>(wp, 7 * (size_t)K); D.pose_bak = carve<double>(wp, 7 * (size_t)K);
@@ -2054,6 +2208,16 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
   D.scale_part = carve<double>(wp, (size_t)nf + L + 1);
   D.scalars = carve<double>(wp, 16);
   uint8_t* d_depth = carve<uint8_t>(wp, (size_t)E + 1);
+  double *d_M1 = nullptr, *d_dump0 = nullptr, *d_dump1 = nullptr, *d_Msep = nullptr, *d_xs = nullptr;
+  if (use_two) {
+    d_M1 = carve<double>(wp, nS);
+    d_dump0 = carve<double>(wp, ((size_t)ts_w + 1) * ts_w); d_dump1 = carve<double>(wp, ((size_t)ts_w + 1) * ts_w);
+    d_Msep = carve<double>(wp, ((size_t)ts_w + 1) * ts_w);
+    d_xs = carve<double>(wp, WIN);
+    // outside its envelope the reversed matrix is never written: zero once per solve (its back-substitution reads
+    // whole 8-row blocks from the leftmost envelope start of the block)
+    CUDA_TRYL(cudaMemsetAsync(d_M1, 0, sizeof(double) * nS, st));
+  }
   const float thm = (float)sqrt(5.991), ths = (float)sqrt(7.815);  // Optimizer.cc:1275-1276
   D.hm.delta = thm; D.hm.dsqr = (double)(float)((double)thm * (double)thm);
   D.hs.delta = ths; D.hs.dsqr = (double)(float)((double)ths * (double)ths);
@@ -2161,16 +2325,35 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
         const void* kfn = win_prof ? (fwd_thread ? (const void*)ldlt_win_kernel<true, false> : (const void*)ldlt_win_kernel<true, true>)
                                    : (fwd_thread ? (const void*)ldlt_win_kernel<false, false> : (const void*)ldlt_win_kernel<false, true>);
         CUDA_TRYL(raise_dynamic_smem(kfn, smem, S.device));
-        {
-          double* Mp = D.S; int nn = n; const int* rp = d_env_reach; const int* fp = d_env_first;
-          double* failp = D.scalars + 3; double* xp = D.x;
-          static const int win_flags = getenv("ORB_B200_LDLT_FLAGS") ? atoi(getenv("ORB_B200_LDLT_FLAGS")) : 0;
-          int fl = win_flags;
-          void* args[] = {&Mp, &nn, &rp, &fp, &failp, &xp, &fl};
+        static const int win_flags = getenv("ORB_B200_LDLT_FLAGS") ? atoi(getenv("ORB_B200_LDLT_FLAGS")) : 0;
+        WinArgs wa;
+        memset(&wa, 0, sizeof(wa));
+        wa.fail = D.scalars + 3; wa.flags = win_flags;
+        void* args[] = {&wa};
+        if (!use_two) {
+          wa.s[0] = WinSide{D.S, d_env_reach, d_env_first, nullptr, n, 0, 0, 0};
+          wa.x = D.x; wa.mode = 0;
           CUDA_TRYL(cudaLaunchKernel(kfn, dim3(1), dim3(WIN_THREADS), args, smem, st));
+          S.launches += 1;
+        } else {
+          const int m1 = WPB * ts_p1, e1 = n - ts_m;
+          rev_gather_kernel<<<e1 + 1, 128, 0, st>>>(D.S, d_M1, n, d_first1, m1, e1);
+          wa.s[0] = WinSide{D.S, d_env_reach, d_env_first, d_dump0, n, ts_p0, ts_m, ts_e2};
+          wa.s[1] = WinSide{d_M1, d_reach1, d_first1, d_dump1, n, ts_p1, m1, e1};
+          wa.mode = 1;
+          CUDA_TRYL(cudaLaunchKernel(kfn, dim3(2), dim3(WIN_THREADS), args, smem, st));
+          sep_merge_kernel<<<ts_w + 1, 128, 0, st>>>(D.S, n, ts_m, ts_w, ts_R0, m1, ts_R1, d_dump0, d_dump1, d_Msep);
+          WinArgs ws;
+          memset(&ws, 0, sizeof(ws));
+          ws.fail = D.scalars + 3; ws.flags = win_flags; ws.mode = 0; ws.x = d_xs;
+          ws.s[0] = WinSide{d_Msep, d_sep_reach, d_sep_first, nullptr, ts_w, 0, 0, 0};
+          void* sargs[] = {&ws};
+          CUDA_TRYL(cudaLaunchKernel(kfn, dim3(1), dim3(WIN_THREADS), sargs, smem, st));
+          wa.mode = 2; wa.xs = d_xs; wa.x = D.x; wa.msep = ts_m;
+          CUDA_TRYL(cudaLaunchKernel(kfn, dim3(2), dim3(WIN_THREADS), args, smem, st));
+          S.launches += 5;
         }
         if (win_prof) win_prof_solves++;
-        S.launches += 1;
       } else if (use_sky) {
         const size_t smem = sizeof(double) * 2 * 32 * SKY_WMAX;
         CUDA_TRYL(raise_dynamic_smem((const void*)ldlt_sky_kernel, smem, S.device));
@@ -2275,7 +2458,7 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
     cudaEventElapsedTime(&tot, S.ev[0], S.ev[7]);
     stats->ms_total = tot; stats->ms_linearize = ms_lin; stats->ms_schur = ms_schur; stats->ms_solve = ms_solve;
     stats->ms_update = ms_upd; stats->n_free_kf = nf; stats->n_pairs = n_pairs; stats->schur_flops = schur_flops;
-    stats->solver_kind = use_win ? 2 : (use_sky ? 1 : 0); stats->envelope_rows_max = use_win ? win_rows_max : sky_rows_max;
+    stats->solver_kind = use_win ? (use_two ? 3 : 2) : (use_sky ? 1 : 0); stats->envelope_rows_max = use_win ? win_rows_max : sky_rows_max;
     stats->ms_host_prep = ms_host_prep;
     stats->ms_wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
     stats->allreduce_bytes_per_trial = S.world > 1 ? (double)env_total * sizeof(double) : 0.0;

@@ -1,2 +1,2 @@
-for f in 0 1 3 4 5; do echo "flags $f"; ORB_B200_LDLT_FLAGS=$f python scripts/lba_prof.py 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_total'], d['ms_solve'])"; done
-for f in 0 1; do echo "prof flags $f"; ORB_B200_LDLT_FLAGS=$f ORB_B200_LDLT_PROF=1 python scripts/lba_prof.py 2>&1 | tail -4 | head -2; done
+# A/B of the reduced-solve variants at config 5 (and config 4): ms_total / ms_solve per optimize(10)
+for m in win win2; do for cfg in "200 80000" "50 20000"; do echo "ORB_B200_LDLT=$m $cfg"; ORB_B200_LDLT=$m python scripts/lba_prof.py $cfg 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_total'], d['ms_solve'], d['solver_kind'])"; done; done
