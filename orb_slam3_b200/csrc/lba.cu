@@ -177,9 +177,120 @@ __device__ __forceinline__ double edge_residual(const LbaDev& D, int e, const do
   return r[0] * (s * r[0]) + r[1] * (s * r[1]);
 }
 
-// One thread per landmark: linearise all its edges (base_binary_edge.hpp:55-120).
-// (128 registers per thread = 4 resident CTAs per SM; asking the compiler for 5 or 6 CTAs -- 102 / 80 registers
-// with spills -- was measured 3 % and 5 % slower at config 5.)
+// Jacobians of one edge at camera-frame point Xc (pose P = quaternion q + t, landmark X): A = d r / d X (d x 3),
+// B = d r / d pose (d x 6), rows padded to three (base_binary_edge.hpp:55-120 calls linearizeOplus of the edge type).
+template <bool RIG>
+__device__ __forceinline__ void edge_jacobians(const LbaDev& D, int e, int k, const DQuat& q, const double* P, const double* Xc,
+                                               double* A, double* B) {
+  const int d = D.e_stereo[e] == LBA_EDGE_STEREO ? 3 : 2;
+  const float* cam = D.kf_cam + 5 * k;
+  double R[9];
+  q_to_R(q, R);
+  const double x = Xc[0], y = Xc[1], z = Xc[2];
+  if (RIG && d == 2) {
+    // EdgeSE3ProjectXYZ::linearizeOplus (OptimizableTypes.cpp:139-160) with either camera model:
+    //   Xi = -projectJac(Xc) R,  Xj = -projectJac(Xc) SE3deriv(Xc);
+    // EdgeSE3ProjectXYZToBody::linearizeOplus (:192-213):
+    //   Xi = -projectJac(X_r) (Trl Tlw).rotation(),  Xj = -projectJac(X_r) Rrl SE3deriv(X_l)
+    const bool body = D.e_stereo[e] == LBA_EDGE_BODY;
+    const EdgeCam c = edge_cam(D, k, body);
+    double J[6], Jm[6];
+    if (body) {
+      const double* T = D.kf_trl + 7 * (size_t)k;
+      const DQuat qrl = {T[0], T[1], T[2], T[3]};
+      double Xr[3], Rrl[9], trw[3];
+      q_rot(qrl, Xc, Xr);
+      Xr[0] += T[4]; Xr[1] += T[5]; Xr[2] += T[6];
+      cam_project_jac(c.kb8, c.p, c.k, Xr, J);
+      q_to_R(qrl, Rrl);
+      DQuat qrw;
+      body_pose(D, k, q, P + 4, qrw, trw);
+      q_to_R(qrw, R);  // the landmark Jacobian rotates with the second camera
+#pragma unroll
+      for (int rr = 0; rr < 2; rr++)
+#pragma unroll
+        for (int cc = 0; cc < 3; cc++)
+          Jm[rr * 3 + cc] = -(J[rr * 3] * Rrl[cc] + J[rr * 3 + 1] * Rrl[3 + cc] + J[rr * 3 + 2] * Rrl[6 + cc]);
+    } else {
+      cam_project_jac(c.kb8, c.p, c.k, Xc, J);
+#pragma unroll
+      for (int i = 0; i < 6; i++) Jm[i] = -J[i];
+    }
+#pragma unroll
+    for (int rr = 0; rr < 2; rr++) {
+#pragma unroll
+      for (int cc = 0; cc < 3; cc++)
+        A[rr * 3 + cc] = -(J[rr * 3] * R[cc] + J[rr * 3 + 1] * R[3 + cc] + J[rr * 3 + 2] * R[6 + cc]);
+      const double j0 = Jm[rr * 3], j1 = Jm[rr * 3 + 1], j2 = Jm[rr * 3 + 2];
+      // SE3deriv rows: (0,z,-y,1,0,0) (-z,0,x,0,1,0) (y,-x,0,0,0,1)
+      B[rr * 6 + 0] = -j1 * z + j2 * y; B[rr * 6 + 1] = j0 * z - j2 * x; B[rr * 6 + 2] = -j0 * y + j1 * x;
+      B[rr * 6 + 3] = j0; B[rr * 6 + 4] = j1; B[rr * 6 + 5] = j2;
+    }
+#pragma unroll
+    for (int cc = 0; cc < 3; cc++) A[6 + cc] = 0;
+#pragma unroll
+    for (int cc = 12; cc < 18; cc++) B[cc] = 0;
+  } else if (d == 3) {  // types_six_dof_expmap.cpp:228-274
+    const double fx = cam[0], fy = cam[1], bf = cam[4];
+    const double z_2 = z * z;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      A[c] = -fx * R[c] / z + fx * x * R[6 + c] / z_2;
+      A[3 + c] = -fy * R[3 + c] / z + fy * y * R[6 + c] / z_2;
+      A[6 + c] = A[c] - bf * R[6 + c] / z_2;
+    }
+    B[0] = x * y / z_2 * fx; B[1] = -(1 + (x * x / z_2)) * fx; B[2] = y / z * fx;
+    B[3] = -1. / z * fx; B[4] = 0; B[5] = x / z_2 * fx;
+    B[6] = (1 + y * y / z_2) * fy; B[7] = -x * y / z_2 * fy; B[8] = -x / z * fy;
+    B[9] = 0; B[10] = -1. / z * fy; B[11] = y / z_2 * fy;
+    B[12] = B[0] - bf * y / z_2; B[13] = B[1] + bf * x / z_2; B[14] = B[2];
+    B[15] = B[3]; B[16] = 0; B[17] = B[5] - bf / z_2;
+  } else {  // OptimizableTypes.cpp:139-160 with Pinhole::projectJac
+    const double fx = cam[0], fy = cam[1];
+    const double J0 = -(fx / z), J2 = fx * x / (z * z), J4 = -(fy / z), J5 = fy * y / (z * z);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      A[c] = J0 * R[c] + J2 * R[6 + c];
+      A[3 + c] = J4 * R[3 + c] + J5 * R[6 + c];
+      A[6 + c] = 0;
+    }
+    // SE3deriv rows: (0,z,-y,1,0,0) (-z,0,x,0,1,0) (y,-x,0,0,0,1)
+    B[0] = J2 * y;          B[1] = J0 * z - J2 * x; B[2] = -J0 * y; B[3] = J0; B[4] = 0;  B[5] = J2;
+    B[6] = -J4 * z + J5 * y; B[7] = -J5 * x;        B[8] = J4 * x;  B[9] = 0;  B[10] = J4; B[11] = J5;
+#pragma unroll
+    for (int c = 12; c < 18; c++) B[c] = 0;
+  }
+}
+
+// Per-edge pose-side records (16-byte aligned: 22 / 6 / 18 doubles) written as 16-byte stores: a thread owns a whole
+// record, so every store of a warp is its own sector -- halving the store count halves the LSU traffic
+__device__ __forceinline__ void store_pose_records(const LbaDev& D, int e, const double* A, const double* B, double ws,
+                                                   const double* orr) {
+  double he[HPE_STRIDE], bev[6], we[18];
+  int t = 0;
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+#pragma unroll
+    for (int j = i; j < 6; j++) he[t++] = ws * (B[i] * B[j] + B[6 + i] * B[6 + j] + B[12 + i] * B[12 + j]);
+    bev[i] = B[i] * orr[0] + B[6 + i] * orr[1] + B[12 + i] * orr[2];
+#pragma unroll
+    for (int j = 0; j < 3; j++) we[i * 3 + j] = ws * (B[i] * A[j] + B[6 + i] * A[3 + j] + B[12 + i] * A[6 + j]);
+  }
+  he[21] = 0.0;
+  double2* He2 = reinterpret_cast<double2*>(D.Hpp_e + HPE_STRIDE * (size_t)e);
+  double2* be2 = reinterpret_cast<double2*>(D.bp_e + 6 * (size_t)e);
+  double2* We2 = reinterpret_cast<double2*>(D.W + 18 * (size_t)e);
+#pragma unroll
+  for (int i = 0; i < HPE_STRIDE / 2; i++) He2[i] = make_double2(he[2 * i], he[2 * i + 1]);
+#pragma unroll
+  for (int i = 0; i < 3; i++) be2[i] = make_double2(bev[2 * i], bev[2 * i + 1]);
+#pragma unroll
+  for (int i = 0; i < 9; i++) We2[i] = make_double2(we[2 * i], we[2 * i + 1]);
+}
+
+// One thread per landmark: all its edges (base_binary_edge.hpp:55-120).  LINEARIZE = false evaluates the robust chi2 of
+// a trial state; the linearising pass runs one thread per EDGE instead (lin_edge_kernel + lm_gather_kernel below) unless
+// ORB_B200_LIN=landmark.
 template <bool LINEARIZE, bool RIG>
 __global__ void __launch_bounds__(128) lin_kernel(LbaDev D) {
   const int l = blockIdx.x * 128 + threadIdx.x;
@@ -213,84 +324,8 @@ __global__ void __launch_bounds__(128) lin_kernel(LbaDev D) {
     robustify(D.e_stereo[e] == LBA_EDGE_STEREO ? D.hs : D.hm, e2, rho0, rho1);  // body edges: thHuberMono (:1380-1382)
     chi += rho0;
     if (!LINEARIZE) continue;
-    const int d = D.e_stereo[e] == LBA_EDGE_STEREO ? 3 : 2;
-    const float* cam = D.kf_cam + 5 * k;
-    double R[9], A[9], B[18];
-    q_to_R(q, R);
-    const double x = Xc[0], y = Xc[1], z = Xc[2];
-    if (RIG && d == 2) {
-      // EdgeSE3ProjectXYZ::linearizeOplus (OptimizableTypes.cpp:139-160) with either camera model:
-      //   Xi = -projectJac(Xc) R,  Xj = -projectJac(Xc) SE3deriv(Xc);
-      // EdgeSE3ProjectXYZToBody::linearizeOplus (:192-213):
-      //   Xi = -projectJac(X_r) (Trl Tlw).rotation(),  Xj = -projectJac(X_r) Rrl SE3deriv(X_l)
-      const bool body = D.e_stereo[e] == LBA_EDGE_BODY;
-      const EdgeCam c = edge_cam(D, k, body);
-      double J[6], Jm[6];
-      if (body) {
-        const double* T = D.kf_trl + 7 * (size_t)k;
-        const DQuat qrl = {T[0], T[1], T[2], T[3]};
-        double Xr[3], Rrl[9], trw[3];
-        q_rot(qrl, Xc, Xr);
-        Xr[0] += T[4]; Xr[1] += T[5]; Xr[2] += T[6];
-        cam_project_jac(c.kb8, c.p, c.k, Xr, J);
-        q_to_R(qrl, Rrl);
-        DQuat qrw;
-        body_pose(D, k, q, P + 4, qrw, trw);
-        q_to_R(qrw, R);  // the landmark Jacobian rotates with the second camera
-#pragma unroll
-        for (int rr = 0; rr < 2; rr++)
-#pragma unroll
-          for (int cc = 0; cc < 3; cc++)
-            Jm[rr * 3 + cc] = -(J[rr * 3] * Rrl[cc] + J[rr * 3 + 1] * Rrl[3 + cc] + J[rr * 3 + 2] * Rrl[6 + cc]);
-      } else {
-        cam_project_jac(c.kb8, c.p, c.k, Xc, J);
-#pragma unroll
-        for (int i = 0; i < 6; i++) Jm[i] = -J[i];
-      }
-#pragma unroll
-      for (int rr = 0; rr < 2; rr++) {
-#pragma unroll
-        for (int cc = 0; cc < 3; cc++)
-          A[rr * 3 + cc] = -(J[rr * 3] * R[cc] + J[rr * 3 + 1] * R[3 + cc] + J[rr * 3 + 2] * R[6 + cc]);
-        const double j0 = Jm[rr * 3], j1 = Jm[rr * 3 + 1], j2 = Jm[rr * 3 + 2];
-        // SE3deriv rows: (0,z,-y,1,0,0) (-z,0,x,0,1,0) (y,-x,0,0,0,1)
-        B[rr * 6 + 0] = -j1 * z + j2 * y; B[rr * 6 + 1] = j0 * z - j2 * x; B[rr * 6 + 2] = -j0 * y + j1 * x;
-        B[rr * 6 + 3] = j0; B[rr * 6 + 4] = j1; B[rr * 6 + 5] = j2;
-      }
-#pragma unroll
-      for (int cc = 0; cc < 3; cc++) A[6 + cc] = 0;
-#pragma unroll
-      for (int cc = 12; cc < 18; cc++) B[cc] = 0;
-    } else if (d == 3) {  // types_six_dof_expmap.cpp:228-274
-      const double fx = cam[0], fy = cam[1], bf = cam[4];
-      const double z_2 = z * z;
-#pragma unroll
-      for (int c = 0; c < 3; c++) {
-        A[c] = -fx * R[c] / z + fx * x * R[6 + c] / z_2;
-        A[3 + c] = -fy * R[3 + c] / z + fy * y * R[6 + c] / z_2;
-        A[6 + c] = A[c] - bf * R[6 + c] / z_2;
-      }
-      B[0] = x * y / z_2 * fx; B[1] = -(1 + (x * x / z_2)) * fx; B[2] = y / z * fx;
-      B[3] = -1. / z * fx; B[4] = 0; B[5] = x / z_2 * fx;
-      B[6] = (1 + y * y / z_2) * fy; B[7] = -x * y / z_2 * fy; B[8] = -x / z * fy;
-      B[9] = 0; B[10] = -1. / z * fy; B[11] = y / z_2 * fy;
-      B[12] = B[0] - bf * y / z_2; B[13] = B[1] + bf * x / z_2; B[14] = B[2];
-      B[15] = B[3]; B[16] = 0; B[17] = B[5] - bf / z_2;
-    } else {  // OptimizableTypes.cpp:139-160 with Pinhole::projectJac
-      const double fx = cam[0], fy = cam[1];
-      const double J0 = -(fx / z), J2 = fx * x / (z * z), J4 = -(fy / z), J5 = fy * y / (z * z);
-#pragma unroll
-      for (int c = 0; c < 3; c++) {
-        A[c] = J0 * R[c] + J2 * R[6 + c];
-        A[3 + c] = J4 * R[3 + c] + J5 * R[6 + c];
-        A[6 + c] = 0;
-      }
-      // SE3deriv rows: (0,z,-y,1,0,0) (-z,0,x,0,1,0) (y,-x,0,0,0,1)
-      B[0] = J2 * y;          B[1] = J0 * z - J2 * x; B[2] = -J0 * y; B[3] = J0; B[4] = 0;  B[5] = J2;
-      B[6] = -J4 * z + J5 * y; B[7] = -J5 * x;        B[8] = J4 * x;  B[9] = 0;  B[10] = J4; B[11] = J5;
-#pragma unroll
-      for (int c = 12; c < 18; c++) B[c] = 0;
-    }
+    double A[9], B[18];
+    edge_jacobians<RIG>(D, e, k, q, P, Xc, A, B);
     const double s = (double)D.e_is2[e];
     const double ws = rho1 * s;
     double orr[3];
@@ -306,30 +341,7 @@ __global__ void __launch_bounds__(128) lin_kernel(LbaDev D) {
       }
       bl[i] += A[i] * orr[0] + A[3 + i] * orr[1] + A[6 + i] * orr[2];
     }
-    if (D.e_free[e] >= 0) {
-      // per-edge records (16-byte aligned: 22 / 6 / 18 doubles) written as 16-byte stores: a thread owns a whole
-      // record, so every store of a warp is its own sector -- halving the store count halves the LSU traffic
-      double he[HPE_STRIDE], bev[6], we[18];
-      t = 0;
-#pragma unroll
-      for (int i = 0; i < 6; i++) {
-#pragma unroll
-        for (int j = i; j < 6; j++) he[t++] = ws * (B[i] * B[j] + B[6 + i] * B[6 + j] + B[12 + i] * B[12 + j]);
-        bev[i] = B[i] * orr[0] + B[6 + i] * orr[1] + B[12 + i] * orr[2];
-#pragma unroll
-        for (int j = 0; j < 3; j++) we[i * 3 + j] = ws * (B[i] * A[j] + B[6 + i] * A[3 + j] + B[12 + i] * A[6 + j]);
-      }
-      he[21] = 0.0;
-      double2* He2 = reinterpret_cast<double2*>(D.Hpp_e + HPE_STRIDE * (size_t)e);
-      double2* be2 = reinterpret_cast<double2*>(D.bp_e + 6 * (size_t)e);
-      double2* We2 = reinterpret_cast<double2*>(D.W + 18 * (size_t)e);
-#pragma unroll
-      for (int i = 0; i < HPE_STRIDE / 2; i++) He2[i] = make_double2(he[2 * i], he[2 * i + 1]);
-#pragma unroll
-      for (int i = 0; i < 3; i++) be2[i] = make_double2(bev[2 * i], bev[2 * i + 1]);
-#pragma unroll
-      for (int i = 0; i < 9; i++) We2[i] = make_double2(we[2 * i], we[2 * i + 1]);
-    }
+    if (D.e_free[e] >= 0) store_pose_records(D, e, A, B, ws, orr);
   }
   D.chi_lm[l] = chi;
   if (LINEARIZE) {
@@ -338,6 +350,69 @@ __global__ void __launch_bounds__(128) lin_kernel(LbaDev D) {
     for (int i = 0; i < 6; i++) H[i] = Hl[i];
     D.bl[3 * (size_t)l] = bl[0]; D.bl[3 * (size_t)l + 1] = bl[1]; D.bl[3 * (size_t)l + 2] = bl[2];
   }
+}
+
+// The linearising pass, one thread per EDGE: a landmark has ~6.5 edges, so the thread-per-landmark kernel above runs
+// 6.5 x fewer threads, each a serial loop of dependent loads (edge -> keyframe -> pose) -- ncu: 12 % of the DRAM
+// throughput, 13 % of the issue slots.  Here every edge is its own thread; its contribution to the landmark block
+// (H_ll upper triangle, b_l, robust chi2: 10 doubles) goes to a per-edge record that lm_gather_kernel adds up per
+// landmark in edge order -- the same order of additions as the serial loop.
+constexpr int LMC_STRIDE = 10;
+template <bool RIG>
+__global__ void __launch_bounds__(128) lin_edge_kernel(LbaDev D, double* __restrict__ lmc) {
+  const int e = blockIdx.x * 128 + threadIdx.x;
+  if (e >= D.n_edges) return;
+  const int k = D.e_kf[e], l = D.e_free[D.n_edges + e];
+  double P[7], X[3];
+#pragma unroll
+  for (int c = 0; c < 7; c++) P[c] = D.pose[7 * (size_t)k + c];
+#pragma unroll
+  for (int c = 0; c < 3; c++) X[c] = D.pts[3 * (size_t)l + c];
+  DQuat q = {P[0], P[1], P[2], P[3]};
+  double Xc[3], r[3];
+  q_rot(q, X, Xc);
+  Xc[0] += P[4]; Xc[1] += P[5]; Xc[2] += P[6];
+  const double e2 = edge_residual<RIG>(D, e, Xc, r, P, X);
+  D.chi2_e[e] = e2;
+  double rho0, rho1;
+  robustify(D.e_stereo[e] == LBA_EDGE_STEREO ? D.hs : D.hm, e2, rho0, rho1);
+  double A[9], B[18];
+  edge_jacobians<RIG>(D, e, k, q, P, Xc, A, B);
+  const double s = (double)D.e_is2[e];
+  const double ws = rho1 * s;
+  double orr[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) orr[i] = -(s * r[i]) * rho1;
+  double rec[LMC_STRIDE];
+  int t = 0;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+#pragma unroll
+    for (int j = i; j < 3; j++) rec[t++] = ws * (A[i] * A[j] + A[3 + i] * A[3 + j] + A[6 + i] * A[6 + j]);
+    rec[6 + i] = A[i] * orr[0] + A[3 + i] * orr[1] + A[6 + i] * orr[2];
+  }
+  rec[9] = rho0;
+  double2* o2 = reinterpret_cast<double2*>(lmc + LMC_STRIDE * (size_t)e);
+#pragma unroll
+  for (int i = 0; i < LMC_STRIDE / 2; i++) o2[i] = make_double2(rec[2 * i], rec[2 * i + 1]);
+  if (D.e_free[e] >= 0) store_pose_records(D, e, A, B, ws, orr);
+}
+__global__ void __launch_bounds__(128) lm_gather_kernel(LbaDev D, const double* __restrict__ lmc) {
+  const int l = blockIdx.x * 128 + threadIdx.x;
+  if (l >= D.n_mp) return;
+  double acc[LMC_STRIDE];
+#pragma unroll
+  for (int i = 0; i < LMC_STRIDE; i++) acc[i] = 0;
+  for (int e = D.lm_ptr[l]; e < D.lm_ptr[l + 1]; e++) {
+    const double2* r2 = reinterpret_cast<const double2*>(lmc + LMC_STRIDE * (size_t)e);
+#pragma unroll
+    for (int i = 0; i < LMC_STRIDE / 2; i++) { const double2 v = r2[i]; acc[2 * i] += v.x; acc[2 * i + 1] += v.y; }
+  }
+  double* H = D.Hll + 6 * (size_t)l;
+#pragma unroll
+  for (int i = 0; i < 6; i++) H[i] = acc[i];
+  D.bl[3 * (size_t)l] = acc[6]; D.bl[3 * (size_t)l + 1] = acc[7]; D.bl[3 * (size_t)l + 2] = acc[8];
+  D.chi_lm[l] = acc[9];
 }
 
 __device__ __forceinline__ double block_sum(double v, double* sm) {
@@ -2190,7 +2265,8 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
   size_t wbytes = 256 * 32 + sizeof(double) * (14 * (size_t)K + 6 * (size_t)L + (size_t)L * (6 + 3 + 9 + 3 + 1) +
                                                (size_t)E * (18 + 18 + HPE_STRIDE + 6 + 1) + (size_t)nf * 42 + nS + (S.world > 1 ? env_total : 1) +
                                                (size_t)n + 3 * (size_t)L + (size_t)nf + L + 16) + (size_t)E +
-                  (use_two ? 256 * 5 + sizeof(double) * (nS + 3 * ((size_t)ts_w + 1) * ts_w + WIN) : 0);
+                  (use_two ? 256 * 5 + sizeof(double) * (nS + 3 * ((size_t)ts_w + 1) * ts_w + WIN) : 0) +
+                  256 + sizeof(double) * (LMC_STRIDE * (size_t)E + 2);
   if (S.work.reserve(wbytes)) return ORB_E_CUDA;
   uint8_t* wp = (uint8_t*)S.work.p;
   D.pose = carve<double>(wp, 7 * (size_t)K); D.pose_bak = carve<double>(wp, 7 * (size_t)K);
@@ -2208,6 +2284,7 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
   D.scale_part = carve<double>(wp, (size_t)nf + L + 1);
   D.scalars = carve<double>(wp, 16);
   uint8_t* d_depth = carve<uint8_t>(wp, (size_t)E + 1);
+  double* d_lmc = carve<double>(wp, LMC_STRIDE * (size_t)E + 2);  // per-edge landmark-block records of lin_edge_kernel
   double *d_M1 = nullptr, *d_dump0 = nullptr, *d_dump1 = nullptr, *d_Msep = nullptr, *d_xs = nullptr;
   if (use_two) {
     d_M1 = carve<double>(wp, nS);
@@ -2243,7 +2320,13 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
   // chi (robust) of the current state -> h_scalars[0]; all ranks see the global value
   auto eval_chi = [&](bool linearize) -> int {
     if (L) {
-      if (rig) {  // KannalaBrandt8 cameras / second-camera edges: the general-camera instantiation
+      static const bool lin_by_landmark = getenv("ORB_B200_LIN") && !strcmp(getenv("ORB_B200_LIN"), "landmark");
+      if (linearize && !lin_by_landmark) {  // one thread per edge + a per-landmark gather
+        if (rig) lin_edge_kernel<true><<<(E + 127) / 128, 128, 0, st>>>(D, d_lmc);
+        else lin_edge_kernel<false><<<(E + 127) / 128, 128, 0, st>>>(D, d_lmc);
+        lm_gather_kernel<<<lm_blocks, 128, 0, st>>>(D, d_lmc);
+        S.launches += 1;
+      } else if (rig) {  // KannalaBrandt8 cameras / second-camera edges: the general-camera instantiation
         if (linearize) lin_kernel<true, true><<<lm_blocks, 128, 0, st>>>(D);
         else lin_kernel<false, true><<<lm_blocks, 128, 0, st>>>(D);
       } else if (linearize) lin_kernel<true, false><<<lm_blocks, 128, 0, st>>>(D);
