@@ -428,13 +428,14 @@ __device__ __forceinline__ double block_sum(double v, double* sm) {
 }
 
 // One CTA per free pose: H_pp (full symmetric 6x6) and b_p.
-__global__ void __launch_bounds__(128) pose_reduce_kernel(LbaDev D) {
-  __shared__ double sm[4];
+constexpr int POSE_THREADS = 512;  // a free pose has a few thousand edges at config 5: 128 threads left the gather latency exposed
+__global__ void __launch_bounds__(POSE_THREADS) pose_reduce_kernel(LbaDev D) {
+  __shared__ double sm[POSE_THREADS / 32];
   const int f = blockIdx.x;
   double acc[27];
 #pragma unroll
   for (int i = 0; i < 27; i++) acc[i] = 0;
-  for (int p = D.pose_ptr[f] + threadIdx.x; p < D.pose_ptr[f + 1]; p += 128) {
+  for (int p = D.pose_ptr[f] + threadIdx.x; p < D.pose_ptr[f + 1]; p += POSE_THREADS) {
     const int e = D.pose_edges[p];
     const double2* He2 = reinterpret_cast<const double2*>(D.Hpp_e + HPE_STRIDE * (size_t)e);  // 16-byte records
     const double2* be2 = reinterpret_cast<const double2*>(D.bp_e + 6 * (size_t)e);
@@ -482,7 +483,9 @@ __global__ void __launch_bounds__(1024) maxdiag_kernel(LbaDev D, const double* H
   if (threadIdx.x == 0) { for (int w = 0; w < 32; w++) m = fmax(m, sm[w]); *out = m; }
 }
 
-// Per landmark: D^-1 = (H_ll + lambda I)^-1 (cofactors), D^-1 b_l, Y_e = W_e D^-1.
+// Per landmark: D^-1 = (H_ll + lambda I)^-1 (cofactors), D^-1 b_l; WITH_Y: also Y_e = W_e D^-1 of its edges
+// (ORB_B200_LIN=landmark); otherwise y_edge_kernel forms Y one thread per edge.
+template <bool WITH_Y>
 __global__ void __launch_bounds__(128) lm_prepare_kernel(LbaDev D, double lambda) {
   const int l = blockIdx.x * 128 + threadIdx.x;
   if (l >= D.n_mp) return;
@@ -500,6 +503,7 @@ __global__ void __launch_bounds__(128) lm_prepare_kernel(LbaDev D, double lambda
   const double* b = D.bl + 3 * (size_t)l;
 #pragma unroll
   for (int i = 0; i < 3; i++) D.db[3 * (size_t)l + i] = Di[i * 3] * b[0] + Di[i * 3 + 1] * b[1] + Di[i * 3 + 2] * b[2];
+  if (!WITH_Y) return;
   for (int e = D.lm_ptr[l]; e < D.lm_ptr[l + 1]; e++) {
     if (D.e_free[e] < 0) continue;
     // 144-byte records, 16-byte aligned: nine 16-byte loads / stores instead of eighteen 8-byte ones
@@ -515,6 +519,27 @@ __global__ void __launch_bounds__(128) lm_prepare_kernel(LbaDev D, double lambda
 #pragma unroll
     for (int i = 0; i < 9; i++) Ye2[i] = make_double2(Ye[2 * i], Ye[2 * i + 1]);
   }
+}
+
+// Y_e = W_e D_l^-1, one thread per edge (the edges of a landmark are neighbours: its D^-1 comes from L1 / L2).
+__global__ void __launch_bounds__(128) y_edge_kernel(LbaDev D) {
+  const int e = blockIdx.x * 128 + threadIdx.x;
+  if (e >= D.n_edges || D.e_free[e] < 0) return;
+  const double* Di = D.Dinv + 9 * (size_t)D.e_free[D.n_edges + e];
+  double Dl[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++) Dl[i] = Di[i];
+  const double2* We2 = reinterpret_cast<const double2*>(D.W + 18 * (size_t)e);
+  double2* Ye2 = reinterpret_cast<double2*>(D.Y + 18 * (size_t)e);
+  double We[18], Ye[18];
+#pragma unroll
+  for (int i = 0; i < 9; i++) { const double2 v = We2[i]; We[2 * i] = v.x; We[2 * i + 1] = v.y; }
+#pragma unroll
+  for (int i = 0; i < 6; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) Ye[i * 3 + j] = We[i * 3] * Dl[j] + We[i * 3 + 1] * Dl[3 + j] + We[i * 3 + 2] * Dl[6 + j];
+#pragma unroll
+  for (int i = 0; i < 9; i++) Ye2[i] = make_double2(Ye[2 * i], Ye[2 * i + 1]);
 }
 
 // The Schur contraction on the tensor cores: one CTA (4 warps) per pose pair
@@ -573,11 +598,11 @@ __global__ void __launch_bounds__(256) schur_pairs_kernel(LbaDev D) {
 }
 
 // b_s = b_p - sum_e W_e (D^-1 b_l): row n of the S buffer.  One CTA per free pose.
-__global__ void __launch_bounds__(128) bschur_kernel(LbaDev D) {
-  __shared__ double sm[4];
+__global__ void __launch_bounds__(POSE_THREADS) bschur_kernel(LbaDev D) {
+  __shared__ double sm[POSE_THREADS / 32];
   const int f = blockIdx.x;
   double acc[6] = {0, 0, 0, 0, 0, 0};
-  for (int p = D.pose_ptr[f] + threadIdx.x; p < D.pose_ptr[f + 1]; p += 128) {
+  for (int p = D.pose_ptr[f] + threadIdx.x; p < D.pose_ptr[f + 1]; p += POSE_THREADS) {
     const int e = D.pose_edges[p];
     // landmark of edge e: binary search in lm_ptr is avoided by storing db per edge landmark via e_mp
     const double* We = D.W + 18 * (size_t)e;
@@ -2339,6 +2364,7 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
   double lambda = -1, ni = 2, chi_first = 0, currentChi = 0;
   int nBad = 0, trials = 0, iters = 0;
   float ms_lin = 0, ms_schur = 0, ms_solve = 0, ms_upd = 0;
+  bool lin_pending = false;
   auto lap = [&](int a, int b, float& acc) {
     float t = 0;
     if (cudaEventElapsedTime(&t, S.ev[a], S.ev[b]) == cudaSuccess) acc += t;
@@ -2346,9 +2372,14 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
   for (int it = 0; it < max_iters && !terminate(); it++) {
     CUDA_TRYL(cudaEventRecord(S.ev[1], st));
     eval_chi(true);
-    pose_reduce_kernel<<<nf, 128, 0, st>>>(D);
+    pose_reduce_kernel<<<nf, POSE_THREADS, 0, st>>>(D);
     S.launches++;
-    if (S.world > 1 && (rc = allreduce(D.scalars, 1))) return rc;  // global robust chi2
+    // From the second iteration on the host already knows the robust chi2 of this state: it is the chi2 of the trial
+    // that was just accepted (or, after a rejected trial, of the restored state) -- g2o's activeRobustChi2() at the top
+    // of an iteration (optimization_algorithm_levenberg.cpp:69-70) re-evaluates the same edges at the same estimates.
+    // No read-back, no stream synchronisation and no all-reduce there: the linearisation is queued behind the trial.
+    const bool need_chi = it == 0;
+    if (need_chi && S.world > 1 && (rc = allreduce(D.scalars, 1))) return rc;  // global robust chi2
     if (it == 0 && !(lambda_init > 0)) {
       // computeLambdaInit: max |diag| over all free vertices of the *global* Hessian
       if (S.world == 1) {
@@ -2363,11 +2394,15 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
       }
       S.launches++;
     }
-    CUDA_TRYL(cudaMemcpyAsync(S.h_scalars, D.scalars, 5 * sizeof(double), cudaMemcpyDeviceToHost, st));
     CUDA_TRYL(cudaEventRecord(S.ev[2], st));
-    CUDA_TRYL(cudaStreamSynchronize(st));
-    lap(1, 2, ms_lin);
-    currentChi = S.h_scalars[0];
+    if (need_chi) {
+      CUDA_TRYL(cudaMemcpyAsync(S.h_scalars, D.scalars, 5 * sizeof(double), cudaMemcpyDeviceToHost, st));
+      CUDA_TRYL(cudaStreamSynchronize(st));
+      lap(1, 2, ms_lin);
+      currentChi = S.h_scalars[0];
+    } else {
+      lin_pending = true;  // ev[1] -> ev[2] is read after the trial's synchronisation
+    }
     double tempChi = currentChi;
     const double iniChi = currentChi;
     if (it == 0) {
@@ -2382,9 +2417,17 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
       CUDA_TRYL(cudaEventRecord(S.ev[3], st));
       // Schur complement
       CUDA_TRYL(cudaMemsetAsync(D.S, 0, sizeof(double) * nS, st));
-      if (L) lm_prepare_kernel<<<lm_blocks, 128, 0, st>>>(D, lambda);
+      {
+        static const bool y_by_landmark = getenv("ORB_B200_LIN") && !strcmp(getenv("ORB_B200_LIN"), "landmark");
+        if (L && y_by_landmark) lm_prepare_kernel<true><<<lm_blocks, 128, 0, st>>>(D, lambda);
+        else if (L) {
+          lm_prepare_kernel<false><<<lm_blocks, 128, 0, st>>>(D, lambda);
+          y_edge_kernel<<<(E + 127) / 128, 128, 0, st>>>(D);
+          S.launches += 1;
+        }
+      }
       schur_pairs_kernel<<<n_pairs, 256, 0, st>>>(D);
-      bschur_kernel<<<nf, 128, 0, st>>>(D);
+      bschur_kernel<<<nf, POSE_THREADS, 0, st>>>(D);
       S.launches += 3;
       // landmark shards: every rank holds its partial H_pp, b_p and Schur terms; one sum gives (S | b_s)
       if (S.world > 1) {
@@ -2469,6 +2512,7 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
       CUDA_TRYL(cudaMemcpyAsync(S.h_scalars, D.scalars, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
       CUDA_TRYL(cudaEventRecord(S.ev[6], st));
       CUDA_TRYL(cudaStreamSynchronize(st));
+      if (lin_pending) { lap(1, 2, ms_lin); lin_pending = false; }
       lap(3, 4, ms_schur); lap(4, 5, ms_solve); lap(5, 6, ms_upd);
       const bool ok2 = S.h_scalars[3] == 0.0;
       tempChi = S.h_scalars[0];
