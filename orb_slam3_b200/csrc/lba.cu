@@ -1833,6 +1833,30 @@ struct Solver {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[8];
   DevBuf graph, work;
+  // Host side of the structure build: the landmark-sorted edge arrays and the pair lists (tens of MB at config 5) are
+  // written straight into one persistent pinned block -- fresh std::vectors cost a page fault per 4 KB on every call
+  // and their cudaMemcpyAsync goes through the driver's pageable staging path.
+  uint8_t* pin_base = nullptr;
+  size_t pin_cap = 0, pin_off = 0;
+  int pin_reserve(size_t bytes) {
+    pin_off = 0;
+    if (bytes <= pin_cap) return 0;
+    if (pin_base) cudaFreeHost(pin_base);
+    pin_base = nullptr; pin_cap = 0;
+    const size_t want = bytes + bytes / 4;
+    if (cudaHostAlloc((void**)&pin_base, want, cudaHostAllocDefault) != cudaSuccess) {
+      set_last_error("lba_solve: cudaHostAlloc of the structure arena");
+      return ORB_E_CUDA;
+    }
+    pin_cap = want;
+    return 0;
+  }
+  template <class T>
+  T* pin_take(size_t count) {
+    T* r = (T*)(pin_base + pin_off);
+    pin_off += (count * sizeof(T) + 255) & ~(size_t)255;
+    return r;
+  }
   double* h_scalars = nullptr;  // pinned
   unsigned* d_bar = nullptr;
   int sm_count = 0, ldlt_blocks = 0;
@@ -1868,10 +1892,20 @@ struct Solver {
     if (graph.p) cudaFree(graph.p);
     if (work.p) cudaFree(work.p);
     cudaFreeHost(h_scalars);
+    if (pin_base) cudaFreeHost(pin_base);
     cudaFree(d_bar);
     for (auto& e : ev) cudaEventDestroy(e);
     cudaStreamDestroy(stream);
   }
+};
+
+template <class T>
+struct PinView {  // the slice of Solver's pinned arena that stands in for a std::vector
+  T* p; size_t n;
+  T& operator[](size_t i) { return p[i]; }
+  const T& operator[](size_t i) const { return p[i]; }
+  T* data() { return p; }
+  size_t size() const { return n; }
 };
 
 template <class T>
@@ -2070,11 +2104,13 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
       }
   }
   // ---- pass B: edge gather (landmark-sorted arrays), pose CSR counts and the pair lists
-  std::vector<int> se_kf(E), se_free(2 * (size_t)E);
-  std::vector<uint8_t> se_st(E);
-  std::vector<double> se_obs(3 * (size_t)E);
-  std::vector<float> se_is2(E);
-  std::vector<int> pair_ea(pair_ptr.back()), pair_eb(pair_ptr.back());
+  const size_t n_pair_entries = (size_t)pair_ptr.back();
+  if (S.pin_reserve(256 * 8 + (size_t)E * (4 + 8 + 1 + 24 + 4 + 4) + 8 * n_pair_entries)) return ORB_E_CUDA;
+  PinView<int> se_kf{S.pin_take<int>(E), (size_t)E}, se_free{S.pin_take<int>(2 * (size_t)E), 2 * (size_t)E};
+  PinView<uint8_t> se_st{S.pin_take<uint8_t>(E), (size_t)E};
+  PinView<double> se_obs{S.pin_take<double>(3 * (size_t)E), 3 * (size_t)E};
+  PinView<float> se_is2{S.pin_take<float>(E), (size_t)E};
+  PinView<int> pair_ea{S.pin_take<int>(n_pair_entries), n_pair_entries}, pair_eb{S.pin_take<int>(n_pair_entries), n_pair_entries};
   std::vector<std::vector<int>> poseT(PREP_T, std::vector<int>(nf, 0));
   parallel([&](int t) {
     std::vector<int>& cur = cntT[t];
@@ -2112,7 +2148,7 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
     for (int t = 0; t < PREP_T; t++) { const int v = poseT[t][f]; poseT[t][f] = c; c += v; }  // -> per-thread offsets
     pose_ptr[f + 1] = pose_ptr[f] + c;
   }
-  std::vector<int> pose_edges(pose_ptr[nf]);
+  PinView<int> pose_edges{S.pin_take<int>((size_t)pose_ptr[nf]), (size_t)pose_ptr[nf]};  // <= E entries (reserved above)
   parallel([&](int t) {
     std::vector<int>& off = poseT[t];
     for (int s = lm_ptr[lm_lo[t]]; s < lm_ptr[lm_lo[t + 1]]; s++)

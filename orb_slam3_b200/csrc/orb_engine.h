@@ -144,6 +144,7 @@ struct Engine {
   int fw_tile_pitch = 0, fw_tile_rows = 0, fw_smap_pitch = 0, fw_smap_bytes = 0, fw_queue_cap = 0, fw_per_warp = 0;
   int fw_grid = 0, fw_align_mask = 15, fw_gq_off = 0;
   bool fw_enabled = false;
+  bool resize_words_ok = false;  // resize_words_kernel (word loads + PRMT + IDP.2A) applies as well
   bool resize_rows_ok = false;  // resize_rows_kernel (shared-memory staged) applies to this pyramid geometry
   int encode_tensor_maps(int batch);
   int l2_chunk_frames(int batch) const;

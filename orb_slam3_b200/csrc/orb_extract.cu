@@ -142,6 +142,69 @@ resize_rows_kernel(uint8_t* __restrict__ pyr, size_t frame_stride, size_t src_of
   }
 }
 
+// Third form of the same arithmetic (default): the four output pixels of a thread read a span of at most eight
+// consecutive source bytes, so instead of eight byte loads per source row pair the thread loads three aligned words
+// per row, shifts them to the span's start (2 SHF) and picks each pixel's byte pair with one PRMT whose selector is
+// fixed for the thread; the horizontal pass h = S[sx] * a.x + S[sx1] * a.y is then ONE integer dot product
+// (IDP.2A: two signed 16-bit coefficients x two unsigned bytes).  ncu on resize_rows_kernel: LSU-bound on the byte
+// gathers from shared memory (issue 67 %, DRAM 7 %).  Requires the span sx1[3] - sx[0] <= 7 (host-checked: any
+// down-scaling factor up to 2; ORB-SLAM3's is 1.2).
+__global__ void __launch_bounds__(RS_THREADS)
+resize_words_kernel(uint8_t* __restrict__ pyr, size_t frame_stride, size_t src_off, int sw, int sh, int spitch,
+                    size_t dst_off, int dw, int dh, int dpitch, const int* __restrict__ xofs,
+                    const short2* __restrict__ alpha, const int* __restrict__ yofs, const short2* __restrict__ beta) {
+  extern __shared__ __align__(16) uint8_t rs_rows[];  // [RS_SRC][spitch] + 16 bytes of slack for the last word loads
+  __shared__ int s_y[RS_ROWS];
+  uint8_t* base = pyr + (size_t)blockIdx.y * frame_stride;
+  const uint8_t* S = base + src_off;
+  const int y0 = blockIdx.x * RS_ROWS, ny = min(RS_ROWS, dh - y0);
+  const int lo = min(max(yofs[y0], 0), sh - 1), hi = min(max(yofs[y0 + ny - 1] + 1, 0), sh - 1);
+  const int nsrc = hi - lo + 1;
+  const int vec = spitch >> 4;
+  for (int i = threadIdx.x; i < nsrc * vec; i += RS_THREADS) {
+    const int r = i / vec, c = i - r * vec;
+    reinterpret_cast<uint4*>(rs_rows + (size_t)r * spitch)[c] =
+        reinterpret_cast<const uint4*>(S + (size_t)(lo + r) * spitch)[c];
+  }
+  if (threadIdx.x < ny) s_y[threadIdx.x] = yofs[y0 + threadIdx.x];
+  __syncthreads();
+  for (int x4 = threadIdx.x * 4; x4 < dw; x4 += RS_THREADS * 4) {
+    uint32_t selp[4], ab[4];
+    int sx0 = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int x = min(x4 + k, dw - 1);
+      const int sx = xofs[x], sx1 = min(sx + 1, sw - 1);
+      if (k == 0) sx0 = sx;
+      // PRMT selector: byte 0 <- span[sx - sx0], byte 1 <- span[sx1 - sx0], bytes 2, 3 <- (don't care)
+      selp[k] = (uint32_t)(sx - sx0) | ((uint32_t)(sx1 - sx0) << 4);
+      const short2 a = alpha[x];
+      ab[k] = (uint32_t)(uint16_t)a.x | ((uint32_t)(uint16_t)a.y << 16);
+    }
+    const int w0 = sx0 >> 2, sh8 = (sx0 & 3) * 8;
+    for (int r = 0; r < ny; r++) {
+      const int y = y0 + r, sy = s_y[r];
+      const uint32_t* R0 = reinterpret_cast<const uint32_t*>(rs_rows + (size_t)(min(max(sy, 0), sh - 1) - lo) * spitch) + w0;
+      const uint32_t* R1 = reinterpret_cast<const uint32_t*>(rs_rows + (size_t)(min(max(sy + 1, 0), sh - 1) - lo) * spitch) + w0;
+      const uint32_t a0 = R0[0], a1 = R0[1], a2 = R0[2], c0 = R1[0], c1 = R1[1], c2 = R1[2];
+      // the eight bytes that start at sx0, of both rows
+      const uint32_t p0 = __funnelshift_r(a0, a1, sh8), p1 = __funnelshift_r(a1, a2, sh8);
+      const uint32_t q0 = __funnelshift_r(c0, c1, sh8), q1 = __funnelshift_r(c1, c2, sh8);
+      const short2 b = beta[y];
+      uint32_t packed = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        // unsigned overload: unsigned 16-bit coefficients (<= 2048) x unsigned bytes, lo16 * byte 0 + hi16 * byte 1
+        const int h0 = (int)__dp2a_lo(ab[k], __byte_perm(p0, p1, selp[k]), 0u);
+        const int h1 = (int)__dp2a_lo(ab[k], __byte_perm(q0, q1, selp[k]), 0u);
+        const int v = (((b.x * (h0 >> 4)) >> 16) + ((b.y * (h1 >> 4)) >> 16) + 2) >> 2;
+        if (x4 + k < dw) packed |= (uint32_t)(v & 0xff) << (8 * k);
+      }
+      *reinterpret_cast<uint32_t*>(base + dst_off + (size_t)y * dpitch + x4) = packed;
+    }
+  }
+}
+
 // Copy the caller's level-0 images (arbitrary pitch / frame stride, device memory) into the
 // pyramid slabs: one launch for the whole batch, 16-byte accesses when the layout allows.
 __global__ void __launch_bounds__(256)
@@ -1412,6 +1475,21 @@ int Engine::ensure(int rows, int cols, int batch) {
     }
     if (smem > 200 * 1024) resize_rows_ok = false;
     if (resize_rows_ok) CUDA_TRY(raise_dynamic_smem((const void*)resize_rows_kernel, smem, device));
+    // resize_words_kernel: the source bytes of four consecutive output pixels must lie within eight bytes, and the
+    // horizontal coefficients must be non-negative (they are: 2048 (1 - fx), 2048 fx); ORB_B200_RESIZE=rows pins the
+    // byte-gather kernel
+    resize_words_ok = resize_rows_ok && !(getenv("ORB_B200_RESIZE") && !strcmp(getenv("ORB_B200_RESIZE"), "rows"));
+    for (int l = 1; l < nlevels && resize_words_ok; l++) {
+      const LevelDev& S = levels[l - 1];
+      const LevelDev& D = levels[l];
+      for (int x4 = 0; x4 < D.w; x4 += 4) {
+        const int xa = h_xofs[rs[l].x_off + x4], xb = h_xofs[rs[l].x_off + std::min(x4 + 3, D.w - 1)];
+        if (std::min(xb + 1, S.w - 1) - xa > 7 || xb < xa) resize_words_ok = false;
+      }
+      for (int x = 0; x < D.w; x++)
+        if (h_alpha[rs[l].x_off + x].x < 0 || h_alpha[rs[l].x_off + x].y < 0) resize_words_ok = false;
+    }
+    if (resize_words_ok) CUDA_TRY(raise_dynamic_smem((const void*)resize_words_kernel, smem + 16, device));
   }
   pyr_frame_bytes = align_up(img_off, 256);
   cand_frame_elems = cand_off;
@@ -1569,7 +1647,11 @@ int Engine::run_device(int f0, int batch, const int* lap_host, cudaStream_t s, i
   for (int l = 1; l < nlevels; l++) {
     const LevelDev& S = levels[l - 1];
     const LevelDev& D = levels[l];
-    if (resize_rows_ok) {
+    if (resize_rows_ok && resize_words_ok) {
+      resize_words_kernel<<<dim3((D.h + RS_ROWS - 1) / RS_ROWS, B), RS_THREADS, (size_t)RS_SRC * S.pitch + 16, s>>>(
+          pyr, pyr_frame_bytes, S.img_off, S.w, S.h, S.pitch, D.img_off, D.w, D.h, D.pitch, d_xofs + rs[l].x_off,
+          d_alpha + rs[l].x_off, d_yofs + rs[l].y_off, d_beta + rs[l].y_off);
+    } else if (resize_rows_ok) {
       resize_rows_kernel<<<dim3((D.h + RS_ROWS - 1) / RS_ROWS, B), RS_THREADS, (size_t)RS_SRC * S.pitch, s>>>(
           pyr, pyr_frame_bytes, S.img_off, S.w, S.h, S.pitch, D.img_off, D.w, D.h, D.pitch, d_xofs + rs[l].x_off,
           d_alpha + rs[l].x_off, d_yofs + rs[l].y_off, d_beta + rs[l].y_off);
