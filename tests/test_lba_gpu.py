@@ -144,6 +144,15 @@ def test_lba_every_reduced_solver_kernel(mode):
         "    got = lba(scenes.lba_view(g))\n"
         "    assert got['stats']['solver_kind'] == (%d if K > 9 or %d != 3 else 2), got['stats']\n"
         "    _compare(g, oracle.lba_solve(scenes.lba_view(g)), got, 'K%%d' %% K)\n"
+        "# keyframes listed in covisibility order instead of along the trajectory (renumbered by reverse Cuthill-McKee:\n"
+        "# pose blocks enter the envelope in uneven steps), and a rig window with two edges per landmark and keyframe\n"
+        "g, _ = scenes.lba_graph(60, 9000, seed=5)\n"
+        "g = scenes.permute_keyframes(g, np.random.default_rng(1).permutation(len(g['kf_fixed'])))\n"
+        "got = lba(scenes.lba_view(g))\n"
+        "_compare(g, oracle.lba_solve(scenes.lba_view(g)), got, 'shuffled')\n"
+        "g, _ = scenes.lba_rig_graph(40, 6000, seed=8)\n"
+        "got = lba(scenes.lba_view(g))\n"
+        "_compare(g, oracle.lba_solve(scenes.lba_view(g)), got, 'rig', chi_tol=1e-3)\n"
         "print('SOLVER_OK')\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)),
                                     {"dense": 0, "sky": 1, "win": 2, "win2": 3}[mode], {"dense": 0, "sky": 1, "win": 2, "win2": 3}[mode])
     env = dict(os.environ, ORB_B200_LDLT=mode)
