@@ -4,7 +4,7 @@
 // bow_transform() of liborbb200.so against a vocabulary uploaded once per process; the two std::maps
 // are rebuilt from the flat outputs (already in key order, so every insert is an O(1) hinted insert).
 // The vocabulary object stays the reference's (loading, scoring, KeyFrameDatabase are untouched).
-// NOT compiled in this repo's image (OpenCV / Eigen headers absent) -- see INTEGRATION.md.
+// Syntax-checked against the reference's headers over stand-ins for its third-party libraries (tests/test_shim_syntax.py); not linked here -- see INTEGRATION.md.
 #include <mutex>
 #include <stdexcept>
 #include <string>

@@ -3,11 +3,11 @@
 // forward to liborbb200.so.  Build inside the ORB_SLAM3 tree: delete the bodies
 // of these methods from src/ORBmatcher.cc (or compile that file with
 // -DORB_B200_HOTPATH and guard them) and add this file; signatures are the
-// reference's own (include/ORBmatcher.h:43-76).  NOT compiled in this repo's
-// image (Eigen / Sophus / DBoW2 / OpenCV headers are absent) -- see
-// INTEGRATION.md.  Pinhole, single camera only (orbb200_gate.h): KannalaBrandt8 rigs
+// reference's own (include/ORBmatcher.h:43-76).  Syntax-checked against the reference's headers over stand-ins for its third-party libraries
+// (tests/test_shim_syntax.py); not linked here -- see INTEGRATION.md.  Pinhole, single camera only (orbb200_gate.h): KannalaBrandt8 rigs
 // (monocular too) and the fisheye-stereo branches call the reference bodies kept
 // under *_Reference names.
+#include <cstring>
 #include <memory>
 #include <stdexcept>
 

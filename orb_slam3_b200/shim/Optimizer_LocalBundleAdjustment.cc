@@ -3,8 +3,8 @@
 // MapPoints, fixed KFs, edge set-up) and 6-7 (outlier erase, write-back under
 // Map::mMutexMapUpdate) are the reference's logic on its own data structures;
 // step 5, g2o's optimizer.optimize(10), is lba_solve() of liborbb200.so.  Build
-// inside the ORB_SLAM3 tree in place of that one function.  NOT compiled in this
-// repo's image (Eigen / Sophus / g2o headers absent) -- see INTEGRATION.md.
+// inside the ORB_SLAM3 tree in place of that one function.  Syntax-checked against the reference's headers
+// over stand-ins for its third-party libraries (tests/test_shim_syntax.py); not linked here -- see INTEGRATION.md.
 #include <map>
 #include <memory>
 #include <stdexcept>

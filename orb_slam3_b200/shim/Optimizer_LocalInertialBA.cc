@@ -3,7 +3,7 @@
 // logic on its own data structures (kept verbatim in the tree under `#ifndef ORB_B200_HOTPATH` ordering,
 // see INTEGRATION.md); this unit shows only the part that changes: the flat graph handed to lia_solve()
 // instead of building a g2o::SparseOptimizer, and how the outputs map back.
-// NOT compiled in this repo's image (Eigen / Sophus / g2o headers absent).  The device path behind
+// Syntax-checked against the reference's headers over stand-ins for its third-party libraries (tests/test_shim_syntax.py).  The device path behind
 // lia_solve is validated on the B200 against the oracle (tests/test_lia_gpu.py); this unit is the graph
 // flattening only, not a finished replacement of the function.
 #include <stdexcept>

@@ -4,7 +4,7 @@
 // with their chi2 re-classification are pose_optimize() of liborbb200.so (one kernel launch).
 // Build inside the ORB_SLAM3 tree in place of that one function (the reference body goes under
 // `#ifndef ORB_B200_HOTPATH`, kept as PoseOptimization_Reference for the fisheye-stereo rig).
-// NOT compiled in this repo's image (Eigen / Sophus / g2o headers absent) -- see INTEGRATION.md.
+// Syntax-checked against the reference's headers over stand-ins for its third-party libraries (tests/test_shim_syntax.py); not linked here -- see INTEGRATION.md.
 #include <mutex>
 #include <stdexcept>
 #include <string>

@@ -4,7 +4,7 @@
 // writes on each MapPoint are written back from the flat outputs.  The fisheye-stereo rig
 // (Frame::Nleft != -1) keeps the reference loop.  Everything else (visibility counters, thresholds,
 // the SearchByProjection call, which shim/ORBmatcher_hotpath.cc already routes to the engine) is the
-// reference's own logic.  NOT compiled in this repo's image (Eigen / Sophus headers absent).
+// reference's own logic.  Syntax-checked against the reference's headers over stand-ins for its third-party libraries (tests/test_shim_syntax.py); not linked here -- see INTEGRATION.md.
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -50,10 +50,13 @@ void Tracking::SearchLocalPoints() {
   orb_frustum_view v;
   v.n = n;
   v.world_pos = pos.data(); v.normal = nrm.data(); v.min_dist = dmin.data(); v.max_dist = dmax.data();
-  const Eigen::Matrix3f& R = mCurrentFrame.mRcw;   // Frame::UpdatePoseMatrices (Frame.cc:472-479)
+  // mRcw / mtcw are private; Frame::UpdatePoseMatrices (Frame.cc:472-479) sets them to exactly these two expressions
+  const Sophus::SE3<float> Tcw = mCurrentFrame.GetPose();
+  const Eigen::Matrix3f R = Tcw.rotationMatrix();
+  const Eigen::Vector3f t = Tcw.translation(), Ow = mCurrentFrame.GetOw();
   for (int r = 0; r < 3; r++)
     for (int c = 0; c < 3; c++) v.Rcw[3 * r + c] = R(r, c);
-  for (int k = 0; k < 3; k++) { v.tcw[k] = mCurrentFrame.mtcw[k]; v.Ow[k] = mCurrentFrame.mOw[k]; }
+  for (int k = 0; k < 3; k++) { v.tcw[k] = t[k]; v.Ow[k] = Ow[k]; }
   v.fx = mCurrentFrame.fx; v.fy = mCurrentFrame.fy; v.cx = mCurrentFrame.cx; v.cy = mCurrentFrame.cy;
   v.bf = mCurrentFrame.mbf;
   v.min_x = Frame::mnMinX; v.max_x = Frame::mnMaxX; v.min_y = Frame::mnMinY; v.max_y = Frame::mnMaxY;

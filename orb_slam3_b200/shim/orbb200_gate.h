@@ -14,7 +14,7 @@
 namespace ORB_SLAM3 {
 namespace orbb200_gate {
 
-inline bool pinhole_single(const GeometricCamera* cam, const GeometricCamera* cam2, int nleft) {
+inline bool pinhole_single(GeometricCamera* cam, GeometricCamera* cam2, int nleft) {  // GetType() is not a const member
   return cam && cam->GetType() == GeometricCamera::CAM_PINHOLE && !cam2 && nleft == -1;
 }
 inline bool gpu_path(const Frame& F) { return pinhole_single(F.mpCamera, F.mpCamera2, F.Nleft); }

@@ -1,0 +1,3 @@
+// SYNTAX-CHECK STAND-IN, not OpenCV (see ../opencv.hpp).
+#pragma once
+#include "../opencv.hpp"
