@@ -29,6 +29,9 @@ def main(ref, out):
               "LocalBundleAdjustment_Reference")
     t = patch(t, r"int static PoseOptimization\(Frame\* pFrame\);", "    int static PoseOptimization_Reference(Frame* pFrame);",
               "PoseOptimization_Reference")
+    t = patch(t, r"void static LocalInertialBA\(KeyFrame\* pKF,[^;]*;",
+              "    void static LocalInertialBA_Reference(KeyFrame* pKF, bool *pbStopFlag, Map *pMap, int& num_fixedKF, int& num_OptKF, int& num_MPs, int& num_edges, bool bLarge, bool bRecInit);",
+              "LocalInertialBA_Reference")
     open(P("Optimizer.h"), "w").write(t)
 
     t = open(P("ORBmatcher.h")).read()
