@@ -315,6 +315,10 @@ long long lba_kernel_launches(const lba_solver* s);
 /* Measurement helper: dense fp64 tensor-pipe peak (DMMA m8n8k4 issued from registers by a full grid, best of
  * `reps` launches, CUDA events) in TFLOP/s -- the denominator of the Schur roofline in bench.py. */
 int lba_measure_fp64_mma_peak(int device, int reps, double* tflops_out);
+/* Host-only test hook: the plan of the two-sided reduced solve (solver_kind 3) for a row envelope -- env_reach[c] =
+ * last row whose envelope holds a column <= c.  out9 = ok, m, e2, p0, p1, w, R0, R1, WIN_ROWS; first1 / reach1
+ * (n ints each, may be NULL) = side 1's tables.  No device needed. */
+int lba_debug_two_sided_plan(int n, const int* env_reach, int* out9, int* first1_out, int* reach1_out);
 
 /* ------------------------------------------------------------------------
  * void Frame::ComputeStereoMatches() (src/Frame.cc:811-981), SURVEY.md 8(f-1).

@@ -67,6 +67,7 @@ SIGNATURES = {
     "lba_solve": (_i, [_vp, _vp, _vp, _i, C.c_double, _vp, _vp, _vp, _vp, _vp]),
     "lba_kernel_launches": (C.c_longlong, [_vp]),
     "lba_measure_fp64_mma_peak": (_i, [_i, _i, _vp]),
+    "lba_debug_two_sided_plan": (_i, [_i, _vp, _vp, _vp, _vp]),
     "stereo_create": (_i, [_i, _vp]),
     "stereo_destroy": (None, [_vp]),
     "stereo_match": (_i, [_vp, _vp, _vp, C.c_float, C.c_float, _vp, _vp, _i]),

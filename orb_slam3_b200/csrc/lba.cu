@@ -40,6 +40,7 @@
 #include "../../include/orb_b200.h"
 #include "se3_dev.cuh"
 #include "orb_engine.h"
+#include "ldlt_plan.h"
 
 namespace orbb200 {
 
@@ -2206,35 +2207,11 @@ static int solve_impl(Solver& S, const lba_graph_view* g, const volatile uint8_t
   int ts_m = 0, ts_e2 = 0, ts_p0 = 0, ts_p1 = 0, ts_w = 0, ts_R0 = 0, ts_R1 = 0;
   std::vector<int> first1, reach1;
   if (use_win && !(ldlt_env && !strcmp(ldlt_env, "win")) && ((ldlt_env && !strcmp(ldlt_env, "win2")) || n >= 50 * WPB)) {
-    first1.resize(n); reach1.assign(n, 0);
-    for (int a = 0; a < n; a++) first1[a] = n - 1 - env_reach[n - 1 - a];  // column envelope of S = row envelope of P S P
-    for (int a = 0; a < n; a++) reach1[first1[a]] = std::max(reach1[first1[a]], a);
-    for (int c = 1; c < n; c++) reach1[c] = std::max(reach1[c], reach1[c - 1]);
-    int rows1 = 0;
-    for (int k0 = 0; k0 < n; k0 += WPB) {
-      const int nb = std::min(WPB, n - k0);
-      const int R = std::min(std::max(reach1[k0 + nb - 1], k0 + nb - 1), n - 1);
-      int jmin = k0;
-      for (int r = 0; r < nb; r++) jmin = std::min(jmin, first1[k0 + r]);
-      rows1 = std::max(rows1, std::max(R - k0 + 1, k0 - jmin + nb));
-    }
-    int best = INT_MAX;
-    for (int pm = 1; rows1 <= WIN_ROWS && WPB * pm < n; pm++) {
-      const int m = WPB * pm, e = env_reach[m - 1] + 1;  // rows >= e do not reach a column < m
-      const int p1 = (n - e) / WPB;
-      if (p1 < 1) break;
-      const int e2 = n - WPB * p1, w = e2 - m;
-      if (w < WPB || w > WIN_ROWS - WPB) continue;
-      if (std::max(pm, p1) < best) {
-        best = std::max(pm, p1);
-        ts_m = m; ts_e2 = e2; ts_p0 = pm; ts_p1 = p1; ts_w = w;
-      }
-    }
-    if (best != INT_MAX) {
+    TwoSidedPlan plan = plan_two_sided(n, env_reach, WPB, WIN_ROWS);  // csrc/ldlt_plan.h (held on the CPU by tests/test_ldlt_plan.py)
+    if (plan.ok) {
       use_two = true;
-      ts_R0 = std::min(std::max(env_reach[ts_m - 1], ts_m - 1), n - 1);
-      const int m1 = WPB * ts_p1;
-      ts_R1 = std::min(std::max(reach1[m1 - 1], m1 - 1), n - 1);
+      ts_m = plan.m; ts_e2 = plan.e2; ts_p0 = plan.p0; ts_p1 = plan.p1; ts_w = plan.w; ts_R0 = plan.R0; ts_R1 = plan.R1;
+      first1.swap(plan.first1); reach1.swap(plan.reach1);
     }
   }
   // ---- device memory
@@ -2685,6 +2662,18 @@ int lba_solve(lba_solver* s, const lba_graph_view* g, const volatile uint8_t* st
 }
 
 long long lba_kernel_launches(const lba_solver* s) { return s ? s->s.launches : 0; }
+
+// Host-only: the two-sided plan for a row envelope (env_reach as lba_solve builds it), for the CPU test of the scheme.
+int lba_debug_two_sided_plan(int n, const int* env_reach, int* out9, int* first1_out, int* reach1_out) {
+  if (n <= 0 || !env_reach || !out9) { orbb200::set_last_error("lba_debug_two_sided_plan: bad argument"); return ORB_E_ARG; }
+  const std::vector<int> reach(env_reach, env_reach + n);
+  const orbb200::TwoSidedPlan P = orbb200::plan_two_sided(n, reach, orbb200::WPB, orbb200::WIN_ROWS);
+  const int o[9] = {P.ok ? 1 : 0, P.m, P.e2, P.p0, P.p1, P.w, P.R0, P.R1, orbb200::WIN_ROWS};
+  memcpy(out9, o, sizeof(o));
+  if (first1_out) memcpy(first1_out, P.first1.data(), sizeof(int) * n);
+  if (reach1_out) memcpy(reach1_out, P.reach1.data(), sizeof(int) * n);
+  return ORB_OK;
+}
 
 int lba_measure_fp64_mma_peak(int device, int reps, double* tflops_out) {
   if (!tflops_out || reps < 1) return ORB_E_ARG;
