@@ -224,6 +224,37 @@ def cpu_lba(K, L, seed=0):
             "value": st["trials"] / (st["ms_total"] / 1e3), "unit": "LM iterations/s", "threads": 1}
 
 
+def lba_rig_leg(device):
+    """SURVEY.md 8a row a17 in the bench line: a fisheye stereo rig window (KannalaBrandt8 cameras on the mono edges,
+    EdgeSE3ProjectXYZToBody edges for the second camera) of config-4 size through lba_solve, beside the oracle port on
+    one host thread (timed = its CPU baseline; its result = the parity figures)."""
+    from oracle import oracle as O
+    from orb_slam3_b200 import scenes
+    from orb_slam3_b200.optimizer import LocalBundleAdjustment
+    K, L = 50, 20000
+    g, _ = scenes.lba_rig_graph(K, L, seed=0)
+    gv = scenes.lba_view(g)
+    lba = LocalBundleAdjustment(device=device)
+    best, res = None, None
+    for rep in range(3):
+        r = lba(gv)
+        if rep > 0 and (best is None or r["stats"]["ms_total"] < best["ms_total"]):
+            best, res = r["stats"], r
+    ref = O.lba_solve(gv)
+    dref, dgot = ref["mp_pos"] - g["mp_pos"], res["mp_pos"] - g["mp_pos"]
+    tref, tgot = ref["kf_pose"][:, 4:] - g["kf_pose"][:, 4:], res["kf_pose"][:, 4:] - g["kf_pose"][:, 4:]
+    return {"config": "fisheye stereo rig: %d KF x %d landmarks, %d mono (KannalaBrandt8) + %d second-camera edges"
+                      % (K, L, int((g["e_stereo"] == 0).sum()), int((g["e_stereo"] == 2).sum())),
+            "iterations": best["iterations"], "trials": best["trials"], "ms_total": best["ms_total"],
+            "value": best["trials"] / (best["ms_total"] * 1e-3), "unit": "LM iterations/s",
+            "cpu_port": {"value": ref["stats"]["trials"] / (ref["stats"]["ms_total"] / 1e3), "unit": "LM iterations/s", "threads": 1},
+            "parity_vs_oracle": {"same_iterations_and_trials": bool(ref["iterations"] == res["iterations"] and
+                                                                     ref["stats"]["trials"] == best["trials"]),
+                                 "rel_delta_points": float(np.linalg.norm(dgot - dref) / max(np.linalg.norm(dref), 1e-30)),
+                                 "rel_delta_translations": float(np.linalg.norm(tgot - tref) / max(np.linalg.norm(tref), 1e-30)),
+                                 "tolerance": 1e-4}}
+
+
 def run_reference(args):
     """The reference's own CPU implementation of the path: ORBextractor.cc compiled unmodified (oracle/_ref) when
     that library was built (kind "reference"), else the oracle port; matchers and LBA are the oracle port (their
@@ -1047,6 +1078,7 @@ def main():
                                 done, threads, dt, fps_cpu, fps_1, 1e3 * t_match)}
             if lba is not None:
                 lba["cpu_baseline_config4"] = cpu_lba(50, 20000)
+                lba["config4_fisheye_rig"] = _guarded(lba_rig_leg, local_rank)
         h2d, d2h = wl.e2e_bytes()
         line = {
             "metric": METRIC, "value": fps_dev, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
