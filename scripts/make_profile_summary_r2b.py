@@ -43,10 +43,21 @@ for name, c, oc in (("4 (50 KF x 20000 landmarks)", c4, o4), ("5 (200 KF x 80000
              % (c["stage_ms"]["ms_linearize"], c["stage_ms"]["ms_schur"], c["stage_ms"]["ms_solve"], c["stage_ms"]["ms_update"],
                 c["reduced_solver"], oc["stage_ms"]["ms_linearize"], oc["stage_ms"]["ms_schur"], oc["stage_ms"]["ms_solve"],
                 oc["stage_ms"]["ms_update"]))
+rig = d["lba"].get("config4_fisheye_rig")
+if rig and "value" in rig:
+    o.append("| LocalBA, %s (row a17) | **%.0f** LM iterations/s (%.2f ms); oracle port on one host thread: %.1f; parity vs oracle: same iteration / trial counts %s, relative error of the landmark / translation deltas %.1e / %.1e (bar 1e-4) | not built |"
+             % (rig["config"], rig["value"], rig["ms_total"], rig["cpu_port"]["value"], rig["parity_vs_oracle"]["same_iterations_and_trials"],
+                rig["parity_vs_oracle"]["rel_delta_points"], rig["parity_vs_oracle"]["rel_delta_translations"]))
 n5 = n2["lba"]["config5"]
 o.append("| 2xB200 | %.0f frames/s resident, %.0f e2e; config 5 sharded by landmark: %.0f LM iterations/s (%.2f ms), `sharded_equals_single` = %s (max dpose %.1e); configs[2] stereo streams: %.0f pairs/s | 72706 / 45258; 893 |"
          % (n2["value"], n2["e2e"]["value"], n5["value"], n5["ms_total"], n5["sharded_equals_single"],
             n5["max_abs_dpose_vs_single"], n2["stereo"]["value"]))
+if os.path.exists(os.path.join(P, "bench_r2b_n4.json")):
+    n4 = load("bench_r2b_n4.json")
+    m5 = n4["lba"]["config5"]
+    o.append("| 4xB200 (before the ranks were lined up ahead of the timed region, see DESIGN.md 5) | %.0f frames/s resident, %.0f e2e; config 5 sharded: %.0f LM iterations/s (%.2f ms; linearize / Schur / solve / update %.2f / %.2f / %.2f / %.2f), `sharded_equals_single` = %s | 160569 / 72044; 916 |"
+             % (n4["value"], n4["e2e"]["value"], m5["value"], m5["ms_total"], m5["stage_ms"]["ms_linearize"], m5["stage_ms"]["ms_schur"],
+                m5["stage_ms"]["ms_solve"], m5["stage_ms"]["ms_update"], m5["sharded_equals_single"]))
 o.append("")
 o.append("## Where a step goes (CUDA events per stage in a serial profiling pass, ms per %d-frame step)\n" % B)
 o.append("| stage | ms/step | us/frame | `r2_summary.md` us/frame |\n|---|---|---|---|")
