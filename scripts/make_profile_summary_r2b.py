@@ -58,6 +58,13 @@ if os.path.exists(os.path.join(P, "bench_r2b_n4.json")):
     o.append("| 4xB200 (before the ranks were lined up ahead of the timed region, see DESIGN.md 5) | %.0f frames/s resident, %.0f e2e; config 5 sharded: %.0f LM iterations/s (%.2f ms; linearize / Schur / solve / update %.2f / %.2f / %.2f / %.2f), `sharded_equals_single` = %s | 160569 / 72044; 916 |"
              % (n4["value"], n4["e2e"]["value"], m5["value"], m5["ms_total"], m5["stage_ms"]["ms_linearize"], m5["stage_ms"]["ms_schur"],
                 m5["stage_ms"]["ms_solve"], m5["stage_ms"]["ms_update"], m5["sharded_equals_single"]))
+for nn, f in ((2, "bench_r2c_n2.json"), (4, "bench_r2c_n4.json")):
+    if os.path.exists(os.path.join(P, f)):
+        x = load(f)
+        m5 = x["lba"]["config5"]
+        o.append("| %dxB200, ranks lined up before the timed region | %.0f frames/s resident, %.0f e2e; config 5 sharded: **%.0f** LM iterations/s (%.2f ms; linearize / Schur / solve / update %.2f / %.2f / %.2f / %.2f), `sharded_equals_single` = %s; through the C ABI %.0f | |"
+                 % (nn, x["value"], x["e2e"]["value"], m5["value"], m5["ms_total"], m5["stage_ms"]["ms_linearize"], m5["stage_ms"]["ms_schur"],
+                    m5["stage_ms"]["ms_solve"], m5["stage_ms"]["ms_update"], m5["sharded_equals_single"], m5["e2e"]["value"]))
 o.append("")
 o.append("## Where a step goes (CUDA events per stage in a serial profiling pass, ms per %d-frame step)\n" % B)
 o.append("| stage | ms/step | us/frame | `r2_summary.md` us/frame |\n|---|---|---|---|")
