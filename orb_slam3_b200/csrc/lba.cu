@@ -428,10 +428,29 @@ __device__ __forceinline__ double block_sum(double v, double* sm) {
   return t;
 }
 
+// The same reduction for NV values per thread with two barriers instead of 2 NV (same order of additions as NV calls
+// of block_sum: shuffle tree inside a warp, then the warp partials in warp order); totals valid in threads 0..NV-1.
+template <int NV, int NW>
+__device__ __forceinline__ double block_sum_many(double* v, double (*sm)[NV]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; k++)
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], o);
+  __syncthreads();
+  if (lane == 0)
+#pragma unroll
+    for (int k = 0; k < NV; k++) sm[warp][k] = v[k];
+  __syncthreads();
+  double t = 0;
+  if (threadIdx.x < NV)
+    for (int w = 0; w < NW; w++) t += sm[w][threadIdx.x];
+  return t;
+}
+
 // One CTA per free pose: H_pp (full symmetric 6x6) and b_p.
 constexpr int POSE_THREADS = 512;  // a free pose has a few thousand edges at config 5: 128 threads left the gather latency exposed
 __global__ void __launch_bounds__(POSE_THREADS) pose_reduce_kernel(LbaDev D) {
-  __shared__ double sm[POSE_THREADS / 32];
+  __shared__ double sm[POSE_THREADS / 32][27];
   const int f = blockIdx.x;
   double acc[27];
 #pragma unroll
@@ -446,18 +465,16 @@ __global__ void __launch_bounds__(POSE_THREADS) pose_reduce_kernel(LbaDev D) {
 #pragma unroll
     for (int i = 0; i < 3; i++) { const double2 v = be2[i]; acc[21 + 2 * i] += v.x; acc[22 + 2 * i] += v.y; }
   }
-  double tot[27];
-#pragma unroll
-  for (int i = 0; i < 27; i++) tot[i] = block_sum(acc[i], sm);
-  if (threadIdx.x == 0) {
-    int t = 0;
-    for (int i = 0; i < 6; i++)
-      for (int j = i; j < 6; j++) {
-        D.Hpp[36 * (size_t)f + i * 6 + j] = tot[t];
-        D.Hpp[36 * (size_t)f + j * 6 + i] = tot[t];
-        t++;
-      }
-    for (int i = 0; i < 6; i++) D.bp[6 * (size_t)f + i] = tot[21 + i];
+  const double tot = block_sum_many<27, POSE_THREADS / 32>(acc, sm);  // thread k < 27 holds total k
+  if (threadIdx.x < 21) {
+    // upper-triangle index k -> (i, j), row-major over i <= j
+    int i = 0, k = (int)threadIdx.x;
+    while (k >= 6 - i) { k -= 6 - i; i++; }
+    const int j = i + k;
+    D.Hpp[36 * (size_t)f + i * 6 + j] = tot;
+    D.Hpp[36 * (size_t)f + j * 6 + i] = tot;
+  } else if (threadIdx.x < 27) {
+    D.bp[6 * (size_t)f + (threadIdx.x - 21)] = tot;
   }
 }
 
@@ -600,7 +617,7 @@ __global__ void __launch_bounds__(256) schur_pairs_kernel(LbaDev D) {
 
 // b_s = b_p - sum_e W_e (D^-1 b_l): row n of the S buffer.  One CTA per free pose.
 __global__ void __launch_bounds__(POSE_THREADS) bschur_kernel(LbaDev D) {
-  __shared__ double sm[POSE_THREADS / 32];
+  __shared__ double sm[POSE_THREADS / 32][6];
   const int f = blockIdx.x;
   double acc[6] = {0, 0, 0, 0, 0, 0};
   for (int p = D.pose_ptr[f] + threadIdx.x; p < D.pose_ptr[f + 1]; p += POSE_THREADS) {
@@ -611,11 +628,8 @@ __global__ void __launch_bounds__(POSE_THREADS) bschur_kernel(LbaDev D) {
 #pragma unroll
     for (int i = 0; i < 6; i++) acc[i] += We[i * 3] * d[0] + We[i * 3 + 1] * d[1] + We[i * 3 + 2] * d[2];
   }
-#pragma unroll
-  for (int i = 0; i < 6; i++) {
-    const double t = block_sum(acc[i], sm);
-    if (threadIdx.x == 0) D.S[(size_t)D.n * D.n + 6 * f + i] = D.bp[6 * (size_t)f + i] - t;
-  }
+  const double t = block_sum_many<6, POSE_THREADS / 32>(acc, sm);
+  if (threadIdx.x < 6) D.S[(size_t)D.n * D.n + 6 * f + threadIdx.x] = D.bp[6 * (size_t)f + threadIdx.x] - t;
 }
 
 // Landmark shards exchange only the row envelope of (S | b_s): rows are packed back to back for the
