@@ -9,6 +9,7 @@
                        (BASELINE.json configs[0]).
   match_scene.npz    : oracle results of the three matchers on a seeded scene.
   lba_small.npz      : oracle optimize(10) result on lba_graph(8, 300, seed=1).
+  lba_rig_small.npz  : the same on lba_rig_graph(8, 300, seed=1) (fisheye stereo rig, second-camera edges).
   stereo_640x480.npz : oracle Frame::ComputeStereoMatches on synth_frame(480,640,5) / stereo_right(.., 6, (5,30,17)).
   pose_small.npz     : oracle Optimizer::PoseOptimization on pose_scene(400, seed=7).
   frustum_small.npz  : oracle Frame::isInFrustum on frustum_scene(3000, seed=2).
@@ -71,6 +72,12 @@ g, _ = scenes.lba_graph(8, 300, seed=1)
 r = O.lba_solve(scenes.lba_view(g))
 np.savez_compressed(os.path.join(out, "lba_small.npz"), kf_pose=r["kf_pose"], mp_pos=r["mp_pos"], chi2=r["chi2"],
                     iterations=r["iterations"], trials=r["stats"]["trials"], chi2_final=r["stats"]["chi2_final"])
+# ---- LBA on a fisheye stereo rig: KannalaBrandt8 mono edges + EdgeSE3ProjectXYZToBody edges
+g, _ = scenes.lba_rig_graph(8, 300, seed=1)
+r = O.lba_solve(scenes.lba_view(g))
+np.savez_compressed(os.path.join(out, "lba_rig_small.npz"), kf_pose=r["kf_pose"], mp_pos=r["mp_pos"], chi2=r["chi2"],
+                    iterations=r["iterations"], trials=r["stats"]["trials"], chi2_final=r["stats"]["chi2_final"],
+                    n_body=int((g["e_stereo"] == 2).sum()))
 # ---- ComputeStereoMatches
 sl = synth_frame(480, 640, 5)
 sr = stereo_right(sl, 6, disparities=(5, 30, 17))

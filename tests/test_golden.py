@@ -59,6 +59,14 @@ def test_oracle_reproduces_golden(oracle):
     assert r["iterations"] == int(zl["iterations"]) and r["stats"]["trials"] == int(zl["trials"])
     assert np.allclose(r["kf_pose"], zl["kf_pose"], rtol=0, atol=1e-9)
     assert np.allclose(r["mp_pos"], zl["mp_pos"], rtol=0, atol=1e-7)
+    # fisheye stereo rig (row a17): KannalaBrandt8 mono edges + second-camera edges
+    g, _ = scenes.lba_rig_graph(8, 300, seed=1)
+    assert int((g["e_stereo"] == 2).sum()) == int(_load("lba_rig_small.npz")["n_body"])
+    r = oracle.lba_solve(scenes.lba_view(g))
+    zr = _load("lba_rig_small.npz")
+    assert r["iterations"] == int(zr["iterations"]) and r["stats"]["trials"] == int(zr["trials"])
+    assert np.allclose(r["kf_pose"], zr["kf_pose"], rtol=0, atol=1e-9)
+    assert np.allclose(r["mp_pos"], zr["mp_pos"], rtol=0, atol=1e-7)
 
 
 def _stereo_inputs():
@@ -171,3 +179,10 @@ def test_gpu_reproduces_golden():
     step = np.abs(zl["mp_pos"] - g["mp_pos"]).max()
     assert np.abs(r["mp_pos"] - zl["mp_pos"]).max() < 1e-4 * step
     assert np.abs(r["kf_pose"] - zl["kf_pose"]).max() < 1e-6
+    g, _ = scenes.lba_rig_graph(8, 300, seed=1)
+    r = LocalBundleAdjustment()(scenes.lba_view(g))
+    zr = _load("lba_rig_small.npz")
+    assert r["iterations"] == int(zr["iterations"]) and r["stats"]["trials"] == int(zr["trials"])
+    step = np.abs(zr["mp_pos"] - g["mp_pos"]).max()
+    assert np.abs(r["mp_pos"] - zr["mp_pos"]).max() < 1e-4 * step
+    assert np.abs(r["kf_pose"] - zr["kf_pose"]).max() < 1e-6
