@@ -104,6 +104,8 @@ struct Mat {
 };
 struct MatExpr { MatExpr() {} MatExpr(const Mat&) {} operator Mat() const { return Mat(); } Mat t() const { return Mat(); } Mat inv(int = 0) const { return Mat(); } };
 template <class T> struct Mat_ : Mat { Mat_() {} Mat_(int, int) {} template <class U> Mat_(const U&) {} T& operator()(int, int) { static T t; return t; } T& operator()(int) { static T t; return t; } };
+template <class T> struct MatCommaInitializer_ { template <class U> MatCommaInitializer_& operator,(const U&) { return *this; } operator Mat() const { return Mat(); } operator Mat_<T>() const { return Mat_<T>(); } };
+template <class T, class U> MatCommaInitializer_<T> operator<<(const Mat_<T>&, const U&) { return MatCommaInitializer_<T>(); }
 inline MatExpr operator*(const Mat&, const Mat&) { return MatExpr(); } inline MatExpr operator+(const Mat&, const Mat&) { return MatExpr(); }
 inline MatExpr operator-(const Mat&, const Mat&) { return MatExpr(); } inline MatExpr operator-(const Mat&) { return MatExpr(); }
 inline MatExpr operator*(const Mat&, double) { return MatExpr(); } inline MatExpr operator*(double, const Mat&) { return MatExpr(); }

@@ -185,4 +185,7 @@ def test_gpu_reproduces_golden():
     assert r["iterations"] == int(zr["iterations"]) and r["stats"]["trials"] == int(zr["trials"])
     step = np.abs(zr["mp_pos"] - g["mp_pos"]).max()
     assert np.abs(r["mp_pos"] - zr["mp_pos"]).max() < 1e-4 * step
-    assert np.abs(r["kf_pose"] - zr["kf_pose"]).max() < 1e-6
+    # poses: 1e-4 of the largest pose update (the fisheye window moves its keyframes by centimetres; its float atan2f is
+    # evaluated differently on the device, see test_lba_gpu.py::test_lba_second_camera_and_fisheye_edges)
+    pose_step = np.abs(zr["kf_pose"] - g["kf_pose"]).max()
+    assert np.abs(r["kf_pose"] - zr["kf_pose"]).max() < 1e-4 * pose_step, pose_step
