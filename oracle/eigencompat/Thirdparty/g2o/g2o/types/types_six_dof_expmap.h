@@ -64,7 +64,7 @@ class OptimizableGraph : public HyperGraph {
     virtual void setToOriginImpl() {} virtual void oplusImpl(const double*) {}
     void setFixed(bool f) { _fixed = f; } bool fixed() const { return _fixed; } void setMarginalized(bool m) { _marg = m; }
    protected:
-    bool _fixed = false, _marg = false;
+    bool _fixed = false, _marg = false, _marginalized = false;
   };
   class Edge : public HyperGraph::Edge {
    public:

@@ -185,19 +185,14 @@ struct Problem {
     return chi;
   }
 
-  // linearizeOplus + constructQuadraticForm for every edge, copyB
-  void build_system() {
-    std::fill(Hpp.begin(), Hpp.end(), 0.0);
-    std::fill(Hll.begin(), Hll.end(), 0.0);
-    std::fill(b.begin(), b.end(), 0.0);
-    for (int e = 0; e < g->n_edges; e++) {
-      const int k = g->e_kf[e], l = g->e_mp[e], d = dim(e);
+  // linearizeOplus of one edge: A = d err / d point (d x 3), B = d err / d pose (d x 6), row-major
+  void edge_jac(int e, double* A, double* B) const {
+      const int k = g->e_kf[e], l = g->e_mp[e];
       double Xc[3], R[9];
       se3_map(pose[k], &pt[3 * (size_t)l], Xc);
       quat_to_R(pose[k].r, R);
       const float* cam = g->kf_cam + 5 * k;
       const double x = Xc[0], y = Xc[1], z = Xc[2];
-      double A[9], B[18];  // d x 3, d x 6 row-major
       if (is_stereo(e)) {
         const double fx = cam[0], fy = cam[1], bf = cam[4];
         const double z_2 = z * z;
@@ -248,6 +243,17 @@ struct Problem {
           for (int cc = 0; cc < 6; cc++)
             B[r * 6 + cc] = J[r * 3] * D[cc] + J[r * 3 + 1] * D[6 + cc] + J[r * 3 + 2] * D[12 + cc];
       }
+  }
+
+  // linearizeOplus + constructQuadraticForm for every edge, copyB
+  void build_system() {
+    std::fill(Hpp.begin(), Hpp.end(), 0.0);
+    std::fill(Hll.begin(), Hll.end(), 0.0);
+    std::fill(b.begin(), b.end(), 0.0);
+    for (int e = 0; e < g->n_edges; e++) {
+      const int k = g->e_kf[e], l = g->e_mp[e], d = dim(e);
+      double A[9], B[18];  // d x 3, d x 6 row-major
+      edge_jac(e, A, B);
       double rho0, rho1;
       (is_stereo(e) ? hs : hm).robustify(chi2(e), rho0, rho1);
       const double s = g->e_inv_sigma2[e];
@@ -517,6 +523,24 @@ int orc_lba_solve(const lba_graph_view* g, const volatile uint8_t* stop, int max
     stats->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
   }
   return iters;
+}
+
+// One edge at the input estimates: err (3, third entry 0 for 2-D edges), A = d err / d point (d x 3), B = d err / d pose
+// (d x 6), isDepthPositive -- what tests/test_ref_edges.py holds against the reference's own computeError() /
+// linearizeOplus() (oracle/_ref/libref_edges.so).
+int orc_lba_edge(const lba_graph_view* g, int e, double* err3, double* A9, double* B18, uint8_t* depth_pos) {
+  if (!g || e < 0 || e >= g->n_edges) return -1;
+  Problem P(g);
+  P.compute_errors();
+  for (int i = 0; i < 3; i++) err3[i] = P.err[3 * (size_t)e + i];
+  for (int i = 0; i < 9; i++) A9[i] = 0;
+  for (int i = 0; i < 18; i++) B18[i] = 0;
+  P.edge_jac(e, A9, B18);
+  double Xc[3];
+  se3_map(P.pose[g->e_kf[e]], &P.pt[3 * (size_t)g->e_mp[e]], Xc);
+  if (P.is_body(e)) se3_map(P.trw(g->e_kf[e]), &P.pt[3 * (size_t)g->e_mp[e]], Xc);
+  *depth_pos = Xc[2] > 0.0;
+  return 0;
 }
 
 // One linearisation at the input estimates: robust chi2, and for damping

@@ -168,6 +168,21 @@ struct PoseProblem {
 
 extern "C" {
 
+// One edge of the frame's graph at its input pose: err (3), Jacobian d err / d pose (d x 6 row-major) -- held against the
+// reference's EdgeSE3ProjectXYZOnlyPose::computeError / linearizeOplus object code (tests/test_ref_edges.py).
+int orc_pose_edge(const pose_opt_view* v, int e, double* err3, double* B18) {
+  if (!v || e < 0 || e >= v->n) return -1;
+  PoseProblem P(v);
+  P.T.r = Quat{v->pose[0], v->pose[1], v->pose[2], v->pose[3]};
+  quat_normalize(P.T.r);
+  P.T.t[0] = v->pose[4]; P.T.t[1] = v->pose[5]; P.T.t[2] = v->pose[6];
+  P.compute_error(e);
+  for (int i = 0; i < 3; i++) err3[i] = P.err[3 * (size_t)e + i];
+  for (int i = 0; i < 18; i++) B18[i] = 0;
+  P.jacobian(e, B18);
+  return 0;
+}
+
 // Returns nInitialCorrespondences - nBad (Optimizer.cc:1114).  pose_out: quaternion xyzw + translation
 // (SE3quat_recov before the cast to float); outlier_out[n] = mvbOutlier of the edges; chi2_out[n] (optional)
 // = the chi2 each edge was last classified with; stats_out (optional) = {rounds run, LM iterations, LM trials}.
