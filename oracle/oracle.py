@@ -272,6 +272,23 @@ def lba_solve(g, max_iters=10, lambda_init=0.0, stop=None):
                 trace=trace[:st.trials].copy())
 
 
+def lba_edge(g, e):
+    """One edge of an lba_graph_view at its input estimates: err[3], A[d x 3] = d err / d point, B[d x 6] = d err / d pose
+    (3 rows, the third zero for 2-D edges), isDepthPositive."""
+    err, A, B, dp = np.zeros(3), np.zeros((3, 3)), np.zeros((3, 6)), C.c_uint8(0)
+    rc = lib().orc_lba_edge(C.byref(g), int(e), _ptr(err), _ptr(A), _ptr(B), C.byref(dp))
+    assert rc == 0
+    return err, A, B, bool(dp.value)
+
+
+def pose_edge(v, e):
+    """One edge of a pose_opt_view at its input pose: err[3], B[3 x 6] = d err / d pose."""
+    err, B = np.zeros(3), np.zeros((3, 6))
+    rc = lib().orc_pose_edge(C.byref(v), int(e), _ptr(err), _ptr(B))
+    assert rc == 0
+    return err, B
+
+
 def lba_reduced_system(g, lam, lm_mask=None):
     nf = int((np.ctypeslib.as_array(C.cast(g.kf_fixed, C.POINTER(C.c_uint8)), (g.n_kf,)) == 0).sum())
     n = 6 * nf

@@ -30,6 +30,78 @@ def available():
     return os.path.exists(LIB_PATH) or build() is not None
 
 
+# ---- oracle/_ref/libref_edges.so: the reference's BA edges / camera models (OptimizableTypes.cpp, Pinhole.cpp,
+#      KannalaBrandt8.cpp compiled unmodified against oracle/eigencompat/)
+EDGES_LIB_PATH = os.path.join(_HERE, "_ref", "libref_edges.so")
+_edges = None
+
+
+def build_edges(force=False):
+    if not os.path.exists(os.path.join(REFERENCE, "src", "OptimizableTypes.cpp")):
+        return None
+    cmd = ["make", "-C", _HERE, "REF=" + REFERENCE] + (["-B"] if force else []) + ["_ref/libref_edges.so"]
+    subprocess.check_call(cmd, stdout=subprocess.DEVNULL)
+    return EDGES_LIB_PATH
+
+
+def edges_available():
+    return os.path.exists(EDGES_LIB_PATH) or build_edges() is not None
+
+
+def edges_lib():
+    global _edges
+    if _edges is None:
+        if not os.path.exists(EDGES_LIB_PATH) and build_edges() is None:
+            raise FileNotFoundError("oracle/_ref/libref_edges.so is not built and %s is absent" % REFERENCE)
+        L = C.CDLL(EDGES_LIB_PATH)
+        vp = C.c_void_p
+        L.ref_cam_project.argtypes = [C.c_int, vp, vp, vp]
+        L.ref_cam_project_jac.argtypes = [C.c_int, vp, vp, vp]
+        L.ref_edge_binary.argtypes = [C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_int)]
+        L.ref_edge_unary.argtypes = [C.c_int, vp, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_int)]
+        _edges = L
+    return _edges
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def edge_binary(model, p8, pose7, X, obs, trl7=None):
+    """The reference's EdgeSE3ProjectXYZ (trl7 None) / EdgeSE3ProjectXYZToBody: computeError, linearizeOplus,
+    isDepthPositive.  Returns err[2], Jxi[2,3] (point), Jxj[2,6] (pose), depth_positive."""
+    p8, pose7, X, obs = (np.ascontiguousarray(p8, np.float32), np.ascontiguousarray(pose7, np.float64),
+                         np.ascontiguousarray(X, np.float64), np.ascontiguousarray(obs, np.float64))
+    t = None if trl7 is None else np.ascontiguousarray(trl7, np.float64)
+    err, Jxi, Jxj, dp = np.zeros(2), np.zeros((2, 3)), np.zeros((2, 6)), C.c_int(0)
+    edges_lib().ref_edge_binary(int(model), _p(p8), _p(pose7), None if t is None else _p(t), _p(X), _p(obs), _p(err), _p(Jxi),
+                                _p(Jxj), C.byref(dp))
+    return err, Jxi, Jxj, bool(dp.value)
+
+
+def edge_unary(model, p8, pose7, Xw, obs, trl7=None):
+    """EdgeSE3ProjectXYZOnlyPose / OnlyPoseToBody: err[2], Jxi[2,6], depth_positive."""
+    p8, pose7, Xw, obs = (np.ascontiguousarray(p8, np.float32), np.ascontiguousarray(pose7, np.float64),
+                          np.ascontiguousarray(Xw, np.float64), np.ascontiguousarray(obs, np.float64))
+    t = None if trl7 is None else np.ascontiguousarray(trl7, np.float64)
+    err, J, dp = np.zeros(2), np.zeros((2, 6)), C.c_int(0)
+    edges_lib().ref_edge_unary(int(model), _p(p8), _p(pose7), None if t is None else _p(t), _p(Xw), _p(obs), _p(err), _p(J),
+                               C.byref(dp))
+    return err, J, bool(dp.value)
+
+
+def cam_project(model, p8, X):
+    p8, X, uv = np.ascontiguousarray(p8, np.float32), np.ascontiguousarray(X, np.float64), np.zeros(2)
+    edges_lib().ref_cam_project(int(model), _p(p8), _p(X), _p(uv))
+    return uv
+
+
+def cam_project_jac(model, p8, X):
+    p8, X, J = np.ascontiguousarray(p8, np.float32), np.ascontiguousarray(X, np.float64), np.zeros((2, 3))
+    edges_lib().ref_cam_project_jac(int(model), _p(p8), _p(X), _p(J))
+    return J
+
+
 _lib = None
 
 

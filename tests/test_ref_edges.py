@@ -1,0 +1,113 @@
+"""The oracle's bundle-adjustment edges against THE REFERENCE'S OWN OBJECT CODE (oracle/_ref/libref_edges.so):
+/root/reference/src/OptimizableTypes.cpp, src/CameraModels/Pinhole.cpp and KannalaBrandt8.cpp compiled unmodified
+(oracle/Makefile) over a functional stand-in for the slice of Eigen / g2o they use (oracle/eigencompat/: the image has
+no Eigen).  Residuals (computeError), Jacobians (linearizeOplus), isDepthPositive of
+  EdgeSE3ProjectXYZ            (LocalBundleAdjustment's mono edge),
+  EdgeSE3ProjectXYZToBody      (its second-camera edge, a17),
+  EdgeSE3ProjectXYZOnlyPose    (PoseOptimization's mono edge, 8f-2),
+and project / projectJac of both camera models are the reference's control flow and formulas as object code; what is
+NOT the reference's here is the matrix arithmetic underneath (plain loops instead of Eigen's expression templates:
+same operations, possibly in another order), hence 1e-9 relative instead of bit equality.  The stereo edge
+(g2o::EdgeStereoSE3ProjectXYZ, a16) lives in the vendored g2o, whose core headers need far more of Eigen: it stays
+pinned by the finite-difference test of test_lba_oracle.py.  The library is built where /root/reference exists and
+travels prebuilt to the GPU box; skipped when absent."""
+import numpy as np
+import pytest
+
+from orb_slam3_b200 import scenes
+
+PIN = np.array([700.0, 705.0, 640.0, 360.0, 0, 0, 0, 0], np.float32)
+KB8 = np.array([190.97, 190.44, 254.93, 256.89, 0.0034823894, 0.0007150348, -0.0020532361, 0.00020293673], np.float32)
+
+
+@pytest.fixture(scope="module")
+def ref():
+    from oracle import ref as R
+    if not R.edges_available():
+        pytest.skip("oracle/_ref/libref_edges.so is not built and the reference tree is absent")
+    return R
+
+
+def _close(a, b, tol=1e-9):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return np.abs(a - b).max() <= tol * max(1.0, np.abs(b).max())
+
+
+def test_camera_models_project_and_jacobian(ref):
+    """The reference's project() / projectJac() object code against an independent numpy restatement (the one the
+    finite-difference LM of test_lba_oracle.py uses) -- this also shows the stand-in arithmetic does what it says."""
+    from test_lba_oracle import _project
+    rng = np.random.default_rng(0)
+    for model, p in ((0, PIN), (1, KB8)):
+        for _ in range(200):
+            X = np.array([rng.uniform(-3, 3), rng.uniform(-2, 2), rng.uniform(1.5, 30)])
+            uv = ref.cam_project(model, p, X)
+            assert _close(uv, _project(model, p, X, exact_float=True), 2e-6 if model else 1e-12)   # KB8: float atan2f, host libm vs numpy
+            J = ref.cam_project_jac(model, p, X)
+            h = 1e-6
+            Jn = np.stack([(_project(model, p, X + h * np.eye(3)[c], False) - _project(model, p, X - h * np.eye(3)[c], False)) / (2 * h)
+                           for c in range(3)], 1)
+            assert np.abs(J - Jn).max() <= 1e-5 * max(1.0, np.abs(Jn).max())
+
+
+@pytest.mark.parametrize("model1,model2", [(0, 0), (1, 1), (0, 1), (1, 0)])
+def test_lba_edges_equal_the_reference_object_code(oracle, ref, model1, model2):
+    """Every mono and second-camera edge of a rig window: err, d err / d point, d err / d pose, isDepthPositive."""
+    g, _ = scenes.lba_rig_graph(6, 120, seed=3, model1=model1, model2=model2)
+    gv = scenes.lba_view(g)
+    n_mono = n_body = 0
+    for e in range(0, len(g["e_kf"]), 3):
+        k, l, typ = int(g["e_kf"][e]), int(g["e_mp"][e]), int(g["e_stereo"][e])
+        pose = g["kf_pose"][k].copy()
+        pose[:4] /= np.linalg.norm(pose[:4])
+        if typ == 2:
+            p8 = g["kf_cam2"][k]
+            r_err, r_A, r_B, r_dp = ref.edge_binary(int(g["kf_cam2_model"][k]), p8, pose, g["mp_pos"][l], g["e_obs"][e][:2], g["kf_trl"][k])
+            n_body += 1
+        else:
+            p8 = np.concatenate([g["kf_cam"][k][:4], g["kf_cam_dist"][k]])
+            r_err, r_A, r_B, r_dp = ref.edge_binary(int(g["kf_cam_model"][k]), p8, pose, g["mp_pos"][l], g["e_obs"][e][:2])
+            n_mono += 1
+        err, A, B, dp = oracle.lba_edge(gv, e)
+        assert _close(err[:2], r_err) and err[2] == 0, (e, typ, err, r_err)
+        assert _close(A[:2], r_A), (e, typ, A[:2], r_A)
+        assert _close(B[:2], r_B), (e, typ, B[:2], r_B)
+        assert dp == r_dp
+    assert n_mono > 50 and n_body > 30
+
+
+def test_pinhole_window_edges_equal_the_reference_object_code(oracle, ref):
+    """The mono edges of a plain Pinhole window (the stereo edges are g2o's: see the module docstring)."""
+    g, _ = scenes.lba_graph(6, 150, seed=2, stereo_frac=0.5)
+    gv = scenes.lba_view(g)
+    n = 0
+    for e in np.nonzero(g["e_stereo"] == 0)[0][::2]:
+        k, l = int(g["e_kf"][e]), int(g["e_mp"][e])
+        pose = g["kf_pose"][k].copy()
+        pose[:4] /= np.linalg.norm(pose[:4])
+        p8 = np.concatenate([g["kf_cam"][k][:4], np.zeros(4, np.float32)])
+        r_err, r_A, r_B, r_dp = ref.edge_binary(0, p8, pose, g["mp_pos"][l], g["e_obs"][e][:2])
+        err, A, B, dp = oracle.lba_edge(gv, int(e))
+        assert _close(err[:2], r_err) and _close(A[:2], r_A) and _close(B[:2], r_B) and dp == r_dp, e
+        n += 1
+    assert n > 100
+
+
+def test_pose_optimization_mono_edges_equal_the_reference_object_code(oracle, ref):
+    """EdgeSE3ProjectXYZOnlyPose (Optimizer.cc:868-893) of a PoseOptimization frame."""
+    v, _ = scenes.pose_scene(300, seed=4, stereo_frac=0.5)
+    import ctypes as C
+    xw = np.ctypeslib.as_array(C.cast(v.xw, C.POINTER(C.c_float)), (v.n * 3,)).reshape(-1, 3).astype(np.float64)
+    obs = np.ctypeslib.as_array(C.cast(v.obs, C.POINTER(C.c_float)), (v.n * 3,)).reshape(-1, 3).astype(np.float64)
+    pose = np.array(list(v.pose))
+    pose[:4] /= np.linalg.norm(pose[:4])
+    p8 = np.array([v.fx, v.fy, v.cx, v.cy, 0, 0, 0, 0], np.float32)
+    n = 0
+    for e in range(v.n):
+        if obs[e, 2] >= 0:
+            continue
+        r_err, r_J, r_dp = ref.edge_unary(0, p8, pose, xw[e], obs[e, :2])
+        err, B = oracle.pose_edge(v, e)
+        assert _close(err[:2], r_err) and _close(B[:2], r_J), e
+        n += 1
+    assert n > 100
