@@ -21,7 +21,11 @@
 
 #include <algorithm>
 #include <cmath>
+#include <fstream>
+#include <iostream>
 #include <memory>
+#include <sstream>
+#include <string>
 #include <vector>
 
 extern "C" {
@@ -34,6 +38,7 @@ float orc_fast_atan2(float y, float x);
 #define CV_PI 3.1415926535897932384626433832795
 #define CV_8U 0
 #define CV_8UC1 0
+#define CV_32F 5  /* named by DBoW2's FORB::toMat32F (never called here); Mat elements are bytes */
 #define CVCOMPAT_DIE(msg)                                                     \
   do {                                                                        \
     fprintf(stderr, "cvcompat: unsupported use: %s (%s:%d)\n", msg, __FILE__, __LINE__); \
@@ -282,5 +287,25 @@ struct KeyPointsFilter {
     }
   }
 };
+
+// cv::FileStorage / FileNode: named by DBoW2's TemplatedVocabulary::save / load (YAML), which oracle/_ref never calls
+// (the vocabulary comes in through loadFromTextFile): declarations that type-check, nothing more.
+struct FileNodeIterator;
+struct FileNode {
+  FileNode operator[](const std::string&) const { return FileNode(); } FileNode operator[](const char*) const { return FileNode(); }
+  FileNode operator[](int) const { return FileNode(); }
+  bool empty() const { return true; } int type() const { return 0; } size_t size() const { return 0; }
+  operator int() const { return 0; } operator float() const { return 0; } operator double() const { return 0; } operator std::string() const { return std::string(); }
+  enum { NONE = 0, INT = 1, REAL = 2, STRING = 3, SEQ = 4, MAP = 5 };
+};
+template <class T> void operator>>(const FileNode&, T&) {}
+struct FileStorage {
+  enum { READ = 0, WRITE = 1 };
+  FileStorage() {} FileStorage(const std::string&, int) {}
+  bool isOpened() const { return false; } void release() {}
+  FileNode operator[](const std::string&) const { return FileNode(); } FileNode operator[](const char*) const { return FileNode(); }
+  FileNode getFirstTopLevelNode() const { return FileNode(); }
+};
+template <class T> FileStorage& operator<<(FileStorage& fs, const T&) { return fs; }
 
 }  // namespace cv

@@ -4,7 +4,8 @@
 // Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1127-1195 and :1218-1258, FORB.cpp:81-101,
 // BowVector.cpp:34-84, FeatureVector.cpp:31-45), SURVEY.md 8(f-4), with the same containers
 // (std::map) on a flat vocabulary.  TF_IDF / TF weighting, L1 scoring (the ORB vocabulary).
-// PARITY UNPINNED BY THE REFERENCE; an independent Python reading pins it (tests/test_bow_oracle.py).
+// Pinned by the reference's own DBoW2 object code (oracle/_ref/libref_bow.so, tests/test_ref_bow.py: bit for bit) and by
+// an independent Python reading (tests/test_bow_oracle.py).
 #include <math.h>
 #include <stdint.h>
 #include <string.h>

@@ -197,3 +197,84 @@ def extract_throughput(frames, nfeatures, nthreads, iters):
     dt = lib().ref_extract_throughput(nfeatures, 1.2, 8, 20, 7, _ptr(frames), frames.shape[0], frames.shape[1],
                                       frames.shape[2], nthreads, iters, C.byref(tot))
     return dt, tot.value
+
+
+# ---- oracle/_ref/libref_bow.so: the reference's vendored DBoW2 (FORB.cpp, BowVector.cpp, FeatureVector.cpp,
+#      ScoringObject.cpp, DUtils, TemplatedVocabulary.h instantiated for FORB) compiled unmodified against oracle/cvcompat/
+BOW_LIB_PATH = os.path.join(_HERE, "_ref", "libref_bow.so")
+_bow = None
+
+
+def build_bow(force=False):
+    if not os.path.exists(os.path.join(REFERENCE, "Thirdparty", "DBoW2", "DBoW2", "FORB.cpp")):
+        return None
+    cmd = ["make", "-C", _HERE, "REF=" + REFERENCE] + (["-B"] if force else []) + ["_ref/libref_bow.so"]
+    subprocess.check_call(cmd, stdout=subprocess.DEVNULL)
+    return BOW_LIB_PATH
+
+
+def bow_available():
+    return os.path.exists(BOW_LIB_PATH) or build_bow() is not None
+
+
+def bow_lib():
+    global _bow
+    if _bow is None:
+        if not os.path.exists(BOW_LIB_PATH) and build_bow() is None:
+            raise FileNotFoundError("oracle/_ref/libref_bow.so is not built and %s is absent" % REFERENCE)
+        L = C.CDLL(BOW_LIB_PATH)
+        vp = C.c_void_p
+        L.ref_voc_load_text.restype = vp
+        L.ref_voc_load_text.argtypes = [C.c_char_p]
+        L.ref_voc_free.argtypes = [vp]
+        L.ref_voc_size.restype = C.c_uint
+        L.ref_voc_size.argtypes = [vp]
+        L.ref_voc_transform.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.POINTER(C.c_int), vp, vp, vp, C.POINTER(C.c_int)]
+        _bow = L
+    return _bow
+
+
+def write_vocabulary_text(path, k, L, child_ptr, child_ids, desc, weight):
+    """A flat vocabulary (the arrays of orb_vocab_view, node ids in creation order, parents before children) in the
+    ORBvoc.txt format TemplatedVocabulary::loadFromTextFile reads (TemplatedVocabulary.h:1338-1419): `k L scoring
+    weighting`, then one line per node `parent is_leaf d0 .. d31 weight`.  No trailing newline: the loader's
+    `while(!f.eof())` would turn an empty last line into a node."""
+    n = len(weight)
+    parent = np.zeros(n, np.int64)
+    for p in range(n):
+        parent[child_ids[child_ptr[p]:child_ptr[p + 1]]] = p
+    lines = ["%d %d 0 0" % (k, L)]   # L1_NORM, TF_IDF: the ORB vocabulary's settings
+    for i in range(1, n):
+        leaf = child_ptr[i + 1] == child_ptr[i]
+        lines.append("%d %d %s %s" % (parent[i], 1 if leaf else 0, " ".join(str(int(b)) for b in desc[i]), repr(float(weight[i]))))
+    with open(path, "w") as f:
+        f.write("\n".join(lines))
+
+
+class RefVocabulary:
+    def __init__(self, path):
+        self._h = bow_lib().ref_voc_load_text(path.encode())
+        if not self._h:
+            raise RuntimeError("loadFromTextFile failed: " + path)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            bow_lib().ref_voc_free(self._h)
+            self._h = None
+
+    def size(self):
+        return int(bow_lib().ref_voc_size(self._h))
+
+    def transform(self, desc, levelsup=4):
+        """DBoW2 transform as Frame::ComputeBoW calls it.  Returns dict(bow_ids, bow_vals, fv_node_ids, fv_ptr, fv_idx)."""
+        desc = np.ascontiguousarray(desc, np.uint8)
+        n = len(desc)
+        cap = max(n, 1)
+        ids, vals = np.zeros(cap, np.uint32), np.zeros(cap)
+        fn, fp, fi = np.zeros(cap, np.uint32), np.zeros(cap + 1, np.int32), np.zeros(cap, np.int32)
+        nw, nn = C.c_int(0), C.c_int(0)
+        rc = bow_lib().ref_voc_transform(self._h, _p(desc), n, int(levelsup), cap, _p(ids), _p(vals), C.byref(nw), _p(fn), _p(fp),
+                                         _p(fi), C.byref(nn))
+        assert rc == 0
+        return dict(bow_ids=ids[:nw.value].astype(np.int32), bow_vals=vals[:nw.value].copy(), fv_node_ids=fn[:nn.value].astype(np.int32),
+                    fv_ptr=fp[:nn.value + 1].copy(), fv_idx=fi[:fp[nn.value]].copy())
