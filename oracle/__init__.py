@@ -2,6 +2,7 @@
 
 May be imported only by tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline / --impl reference legs.  See orc_common.h for the pinning note
-("parity unpinned" by the reference's own tests; pinned against cv2 4.13).
+(the reference ships no tests; pinned against the reference's own sources
+compiled unmodified into oracle/_ref/, and against cv2 4.13 underneath).
 """
 from .oracle import *  # noqa: F401,F403

@@ -21,9 +21,13 @@
 
 #include <algorithm>
 #include <cmath>
+#include <climits>
 #include <fstream>
 #include <iostream>
+#include <list>
+#include <map>
 #include <memory>
+#include <set>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -165,6 +169,23 @@ class Mat {
   }
   void locateROI(Size& whole, Point& ofs) const { whole = Size(whole_cols, whole_rows); ofs = Point(ofs_x, ofs_y); }
   bool isSubmatrix() const { return rows != whole_rows || cols != whole_cols; }
+  // ---- named by src/Frame.cc / ORBmatcher.cc / MapPoint.cc (oracle/_ref/libref_front.so) on paths that build float
+  //      matrices (calibration, serialisation, drawing): they type-check, and abort if a run ever reaches them
+  Mat(int r, int c, int type, void* user) : Mat() { (void)r; (void)c; (void)type; (void)user; CVCOMPAT_DIE("Mat over user data of another type"); }
+  template <typename T> T& at(int i) { return *(T*)(data + (size_t)i * sizeof(T)); }
+  template <typename T> const T& at(int i) const { return *(const T*)(data + (size_t)i * sizeof(T)); }
+  size_t elemSize() const { return 1; }
+  size_t total() const { return (size_t)rows * cols; }
+  bool isContinuous() const { return step.v == (size_t)cols; }
+  Mat reshape(int, int = 0) const { CVCOMPAT_DIE("reshape"); return Mat(); }
+  Mat t() const { CVCOMPAT_DIE("t"); return Mat(); }
+  Mat inv(int = 0) const { CVCOMPAT_DIE("inv"); return Mat(); }
+  Mat col(int) const { CVCOMPAT_DIE("col"); return Mat(); }
+  void convertTo(const Mat&, int, double = 1, double = 0) const { CVCOMPAT_DIE("convertTo"); }
+  int channels() const { return 1; }
+  int depth() const { return 0; }
+  static Mat eye(int r, int c, int type) { (void)r; (void)c; (void)type; CVCOMPAT_DIE("eye"); return Mat(); }
+  static Mat ones(int r, int c, int type) { (void)r; (void)c; (void)type; CVCOMPAT_DIE("ones"); return Mat(); }
 
  private:
   std::shared_ptr<uchar> buf;
@@ -287,6 +308,45 @@ struct KeyPointsFilter {
     }
   }
 };
+
+// ---- types and functions the front-end sources name outside the paths oracle/_ref runs (type-check only)
+template <typename T> struct Point3_ {
+  T x, y, z;
+  Point3_() : x(0), y(0), z(0) {}
+  Point3_(T a, T b, T c) : x(a), y(b), z(c) {}
+};
+typedef Point3_<float> Point3f; typedef Point3_<double> Point3d; typedef Point_<double> Point2d;
+template <typename T> struct Mat_ : Mat {
+  Mat_() {} Mat_(int, int) { CVCOMPAT_DIE("Mat_"); } Mat_(const Mat&) {}
+  T& operator()(int, int) { static T t; CVCOMPAT_DIE("Mat_()"); return t; } T& operator()(int) { static T t; CVCOMPAT_DIE("Mat_()"); return t; }
+};
+template <typename T> struct MatCommaInitializer_ { template <class U> MatCommaInitializer_& operator,(const U&) { return *this; } operator Mat() const { return Mat(); } operator Mat_<T>() const { return Mat_<T>(); } };
+template <typename T, class U> MatCommaInitializer_<T> operator<<(const Mat_<T>&, const U&) { CVCOMPAT_DIE("Mat_ <<"); return MatCommaInitializer_<T>(); }
+struct Scalar { double val[4]; Scalar(double a = 0, double b = 0, double c = 0, double d = 0) : val{a, b, c, d} {} };
+struct DMatch { int queryIdx, trainIdx, imgIdx; float distance; };
+struct BFMatcher { BFMatcher(int = 4, bool = false) {} template <class... A> void match(const A&...) const { CVCOMPAT_DIE("BFMatcher"); } template <class... A> void knnMatch(const A&...) const { CVCOMPAT_DIE("BFMatcher"); } };
+enum { NORM_L1 = 2, NORM_L2 = 4, NORM_HAMMING = 6, CV_32FC1 = 5, CV_64F = 6 };
+inline std::ostream& operator<<(std::ostream& o, const Mat&) { return o; }
+inline Mat operator*(const Mat&, const Mat&) { CVCOMPAT_DIE("Mat * Mat"); return Mat(); }
+inline Mat operator+(const Mat&, const Mat&) { CVCOMPAT_DIE("Mat + Mat"); return Mat(); }
+inline Mat operator-(const Mat&, const Mat&) { CVCOMPAT_DIE("Mat - Mat"); return Mat(); }
+inline Mat operator-(const Mat&) { CVCOMPAT_DIE("-Mat"); return Mat(); }
+inline Mat operator*(const Mat&, double) { CVCOMPAT_DIE("Mat * s"); return Mat(); }
+inline Mat operator/(const Mat&, double) { CVCOMPAT_DIE("Mat / s"); return Mat(); }
+template <class... A> void undistortPoints(const A&...) { CVCOMPAT_DIE("undistortPoints"); }
+template <class... A> void hconcat(const A&...) { CVCOMPAT_DIE("hconcat"); }
+template <class... A> void vconcat(const A&...) { CVCOMPAT_DIE("vconcat"); }
+namespace fisheye { template <class... A> void undistortPoints(const A&...) { CVCOMPAT_DIE("fisheye::undistortPoints"); } }
+// cv::norm(a, b, NORM_L1) of two 8-bit matrices of the same size: the SAD of Frame::ComputeStereoMatches (Frame.cc:908-923),
+// an exact integer sum returned as double like cv::norm does
+inline double norm(const Mat& a, const Mat& b, int type) {
+  if (type != NORM_L1 || a.rows != b.rows || a.cols != b.cols) CVCOMPAT_DIE("norm: only L1 of equal sizes");
+  long long s = 0;
+  for (int y = 0; y < a.rows; y++) { const uchar* p = a.ptr(y); const uchar* q = b.ptr(y); for (int x = 0; x < a.cols; x++) s += p[x] > q[x] ? p[x] - q[x] : q[x] - p[x]; }
+  return (double)s;
+}
+template <typename T> double norm(const Point_<T>& p) { return std::sqrt((double)p.x * p.x + (double)p.y * p.y); }
+template <typename T> double norm(const Point3_<T>& p) { return std::sqrt((double)p.x * p.x + (double)p.y * p.y + (double)p.z * p.z); }
 
 // cv::FileStorage / FileNode: named by DBoW2's TemplatedVocabulary::save / load (YAML), which oracle/_ref never calls
 // (the vocabulary comes in through loadFromTextFile): declarations that type-check, nothing more.

@@ -63,6 +63,7 @@ class OptimizableGraph : public HyperGraph {
     virtual bool read(std::istream&) { return true; } virtual bool write(std::ostream&) const { return true; }
     virtual void setToOriginImpl() {} virtual void oplusImpl(const double*) {}
     void setFixed(bool f) { _fixed = f; } bool fixed() const { return _fixed; } void setMarginalized(bool m) { _marg = m; }
+    void updateCache() {}
    protected:
     bool _fixed = false, _marg = false, _marginalized = false;
   };
@@ -117,6 +118,13 @@ template <int D, class E, class VertexXi, class VertexXj> class BaseBinaryEdge :
  protected:
   using BaseEdge<D, E>::_measurement; using BaseEdge<D, E>::_information; using BaseEdge<D, E>::_error; using HyperGraph::Edge::_vertices;
   JacobianXiOplusType _jacobianOplusXi; JacobianXjOplusType _jacobianOplusXj;
+};
+template <int D, class E> class BaseMultiEdge : public BaseEdge<D, E> {  // (G2oTypes.h's inertial edges: members only)
+ public:
+  typedef Eigen::Matrix<double, D, Eigen::Dynamic> JacobianType;
+ protected:
+  using BaseEdge<D, E>::_measurement; using BaseEdge<D, E>::_information; using BaseEdge<D, E>::_error; using HyperGraph::Edge::_vertices;
+  std::vector<JacobianType> _jacobianOplus;
 };
 class VertexSE3Expmap : public BaseVertex<6, SE3Quat> {};
 class VertexSBAPointXYZ : public BaseVertex<3, Eigen::Vector3d> {};

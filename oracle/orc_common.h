@@ -14,8 +14,15 @@
 //     generated from it under tests/golden/ref_*.npz (scripts/make_golden_ref.py);
 //   * the un-vendored OpenCV arithmetic underneath (resize, FAST, GaussianBlur, fastAtan2): cv2 4.13 (Python),
 //     bit-exact -- tests/test_oracle_vs_cv2.py + tests/golden/primitives_cv2.npz;
-//   * matchers / g2o / DBoW2 rows: "parity unpinned" by the reference (their translation units need Eigen /
-//     Sophus); pinned by independent numpy restatements and the reference sources cited per function.
+//   * matcher rows (a10, a11, a13), Frame::isInFrustum, Frame::ComputeStereoMatches: the reference's own object code --
+//     ORBmatcher.cc, Frame.cc, KeyFrame.cc, MapPoint.cc compiled UNMODIFIED against cvcompat/ + eigencompat/ into
+//     oracle/_ref/libref_front.so, real Frame / KeyFrame / MapPoint objects -- tests/test_ref_front.py (exact);
+//   * BA edges (EdgeSE3ProjectXYZ / ToBody / OnlyPose) and both camera models: OptimizableTypes.cpp, Pinhole.cpp,
+//     KannalaBrandt8.cpp as object code (libref_edges.so) -- tests/test_ref_edges.py (1e-9);
+//   * Frame::ComputeBoW's transform: the vendored DBoW2 as object code (libref_bow.so) -- tests/test_ref_bow.py (exact);
+//   * g2o's stereo edge, its LM / block solver and the inertial edges of G2oTypes.cc: "parity unpinned" by the reference
+//     (those translation units need the real Eigen); pinned by independent numpy restatements, finite differences and
+//     dense solves, with the reference lines cited per function.
 #pragma once
 #include <stdint.h>
 

@@ -278,3 +278,103 @@ class RefVocabulary:
         assert rc == 0
         return dict(bow_ids=ids[:nw.value].astype(np.int32), bow_vals=vals[:nw.value].copy(), fv_node_ids=fn[:nn.value].astype(np.int32),
                     fv_ptr=fp[:nn.value + 1].copy(), fv_idx=fi[:fp[nn.value]].copy())
+
+
+# ---- oracle/_ref/libref_front.so: the reference's front-end object code -- ORBmatcher.cc, Frame.cc, MapPoint.cc and
+#      Pinhole.cpp compiled unmodified (oracle/Makefile); real Frame / MapPoint objects filled from the flat views
+FRONT_LIB_PATH = os.path.join(_HERE, "_ref", "libref_front.so")
+_front = None
+
+
+def build_front(force=False):
+    if not os.path.exists(os.path.join(REFERENCE, "src", "ORBmatcher.cc")):
+        return None
+    _o.build()
+    cmd = ["make", "-C", _HERE, "REF=" + REFERENCE] + (["-B"] if force else []) + ["_ref/libref_front.so"]
+    subprocess.check_call(cmd, stdout=subprocess.DEVNULL)
+    return FRONT_LIB_PATH
+
+
+def front_available():
+    return os.path.exists(FRONT_LIB_PATH) or build_front() is not None
+
+
+def front_lib():
+    global _front
+    if _front is None:
+        if not os.path.exists(FRONT_LIB_PATH) and build_front() is None:
+            raise FileNotFoundError("oracle/_ref/libref_front.so is not built and %s is absent" % REFERENCE)
+        _o.lib()
+        L = C.CDLL(FRONT_LIB_PATH)
+        vp = C.c_void_p
+        L.ref_front_project_local.argtypes = [vp, vp, C.c_float, C.c_float, C.c_int, C.c_float, vp]
+        L.ref_front_project_last.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float, vp]
+        L.ref_front_is_in_frustum.argtypes = [vp, C.c_float, vp, vp, vp, vp, vp, vp, vp]
+        L.ref_front_stereo_match.argtypes = [C.c_int, vp, vp, C.c_int, vp, vp, C.c_int, vp, vp, vp, vp, vp, C.c_float, C.c_float,
+                                             C.c_float, vp, vp]
+        L.ref_front_triangulate.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp]
+        _front = L
+    return _front
+
+
+def front_project_local(F, mps, th, nn_ratio, far_points=False, th_far=50.0):
+    """The reference's ORBmatcher(nn_ratio).SearchByProjection(Frame&, vector<MapPoint*>&, th, bFarPoints, thFarPoints)."""
+    out = np.empty(F.n, np.int32)
+    n = front_lib().ref_front_project_local(C.byref(F), C.byref(mps), th, nn_ratio, int(far_points), th_far, _p(out))
+    return n, out
+
+
+def front_project_last(cur, last, Tcw_qt7, th, forward=False, backward=False, check_ori=True, nn_ratio=0.9):
+    """The reference's ORBmatcher(nn_ratio, checkOri).SearchByProjection(Cur, Last, th, bMono)."""
+    T = np.ascontiguousarray(Tcw_qt7, np.float32)
+    out = np.empty(cur.n, np.int32)
+    n = front_lib().ref_front_project_last(C.byref(cur), C.byref(last), _p(T), int(forward), int(backward), th, int(check_ori),
+                                           nn_ratio, _p(out))
+    return n, out
+
+
+def front_is_in_frustum(view, viewing_cos_limit=0.5, out=None):
+    """The reference's Frame::isInFrustum over all points of an orb_frustum_view (outputs like oracle.is_in_frustum)."""
+    if out is None:
+        n = view.n
+        out = dict(track_in_view=np.zeros(n, np.uint8), proj_x=np.zeros(n, np.float32), proj_y=np.zeros(n, np.float32),
+                   proj_xr=np.zeros(n, np.float32), scale_level=np.zeros(n, np.int32),
+                   view_cos=np.zeros(n, np.float32), depth=np.zeros(n, np.float32))
+    k = front_lib().ref_front_is_in_frustum(C.byref(view), float(viewing_cos_limit),
+                                            *[_p(out[f]) for f in ("track_in_view", "proj_x", "proj_y", "proj_xr", "scale_level",
+                                                                   "view_cos", "depth")])
+    return k, out
+
+
+def front_stereo_match(kl, dl, kr, dr, pyr_l, pyr_r, bf, b, scale_factor=1.2):
+    """The reference's Frame::ComputeStereoMatches (arguments like oracle.stereo_match).  Returns (n_kept, mvuRight, mvDepth)."""
+    nl = len(pyr_l)
+    Lv = [np.ascontiguousarray(a, np.uint8) for a in pyr_l]
+    Rv = [np.ascontiguousarray(a, np.uint8) for a in pyr_r]
+    pl = (C.c_void_p * nl)(*[a.ctypes.data for a in Lv])
+    pr = (C.c_void_p * nl)(*[a.ctypes.data for a in Rv])
+    lw = np.array([a.shape[1] for a in Lv], np.int32)
+    lh = np.array([a.shape[0] for a in Lv], np.int32)
+    ls = np.array([a.strides[0] for a in Lv], np.int32)
+    kl = np.ascontiguousarray(kl); kr = np.ascontiguousarray(kr)
+    dl = np.ascontiguousarray(dl, np.uint8); dr = np.ascontiguousarray(dr, np.uint8)
+    ur = np.zeros(len(kl), np.float32)
+    dp = np.zeros(len(kl), np.float32)
+    n = front_lib().ref_front_stereo_match(len(kl), _p(kl), _p(dl), len(kr), _p(kr), _p(dr), nl, pl, pr, _p(lw), _p(lh), _p(ls),
+                                           float(scale_factor), float(bf), float(b), _p(ur), _p(dp))
+    return n, ur, dp
+
+
+def front_triangulate(kf1, kf2, fv1, fv2, T1w_qt7, T2w_qt7, only_stereo=False, coarse=False, check_ori=True, cap=None):
+    """The reference's ORBmatcher(0.6, check_ori).SearchForTriangulation(pKF1, pKF2, ...) on KeyFrames at the two poses.
+    Returns (n, pairs, F12, ep): F12 / ep are what the reference derives from the poses (Pinhole.cpp:107-112, ORBmatcher.cc:917-920),
+    the inputs of oracle.match_triangulate / the C ABI."""
+    cap = cap or max(kf1.n, 1)
+    T1 = np.ascontiguousarray(T1w_qt7, np.float32)
+    T2 = np.ascontiguousarray(T2w_qt7, np.float32)
+    out = np.empty((cap, 2), np.int32)
+    F12 = np.zeros(9, np.float32)
+    ep = np.zeros(2, np.float32)
+    n = front_lib().ref_front_triangulate(C.byref(kf1), C.byref(kf2), C.byref(fv1), C.byref(fv2), _p(T1), _p(T2), int(only_stereo),
+                                          int(coarse), int(check_ori), _p(out), cap, _p(F12), _p(ep))
+    return n, out[:n], F12, ep
