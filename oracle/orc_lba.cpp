@@ -154,10 +154,12 @@ struct Problem {
         continue;
       }
       if (g->e_stereo[e]) {
-        // types_six_dof_expmap.cpp:190-197: invz in float; fx.. are doubles set from floats
+        // types_six_dof_expmap.cpp:190-197: `const float invz = 1.0f/trans_xyz[2]` -- the quotient is formed in double
+        // (trans_xyz[2] is a double) and THEN rounded to float; bf arrives as `const float&`, so bf*invz is a float product;
+        // fx.. are doubles set from floats
         const double fx = cam[0], fy = cam[1], cx = cam[2], cy = cam[3];
         const float bf = (float)(double)cam[4];
-        const float invz = 1.0f / (float)Xc[2];
+        const float invz = (float)(1.0 / Xc[2]);
         const double u = Xc[0] * invz * fx + cx;
         const double v = Xc[1] * invz * fy + cy;
         r[0] = obs[0] - u; r[1] = obs[1] - v; r[2] = obs[2] - (u - bf * invz);

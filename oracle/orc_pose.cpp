@@ -86,7 +86,7 @@ struct PoseProblem {
     const double ou = v->obs[3 * e], ov = v->obs[3 * e + 1];
     if (stereo(e)) {
       const double fx = v->fx, fy = v->fy, cx = v->cx, cy = v->cy, bf = v->bf;  // e->fx = pFrame->fx ... (:906-910)
-      const float invz = 1.0f / (float)Xc[2];
+      const float invz = (float)(1.0 / Xc[2]);   // :340 `1.0f/trans_xyz[2]`: double quotient, rounded to float
       const double pu = Xc[0] * invz * fx + cx;
       const double pv = Xc[1] * invz * fy + cy;
       r[0] = ou - pu; r[1] = ov - pv; r[2] = (double)v->obs[3 * e + 2] - (pu - bf * invz);

@@ -378,3 +378,54 @@ def front_triangulate(kf1, kf2, fv1, fv2, T1w_qt7, T2w_qt7, only_stereo=False, c
     n = front_lib().ref_front_triangulate(C.byref(kf1), C.byref(kf2), C.byref(fv1), C.byref(fv2), _p(T1), _p(T2), int(only_stereo),
                                           int(coarse), int(check_ori), _p(out), cap, _p(F12), _p(ep))
     return n, out[:n], F12, ep
+
+
+# ---- oracle/_ref/libref_g2o.so: the vendored g2o's types_six_dof_expmap.{h,cpp} as object code (stereo edges)
+G2O_LIB_PATH = os.path.join(_HERE, "_ref", "libref_g2o.so")
+_g2o = None
+
+
+def build_g2o(force=False):
+    if not os.path.exists(os.path.join(REFERENCE, "Thirdparty", "g2o", "g2o", "types", "types_six_dof_expmap.cpp")):
+        return None
+    cmd = ["make", "-C", _HERE, "REF=" + REFERENCE] + (["-B"] if force else []) + ["_ref/libref_g2o.so"]
+    subprocess.check_call(cmd, stdout=subprocess.DEVNULL)
+    return G2O_LIB_PATH
+
+
+def g2o_available():
+    return os.path.exists(G2O_LIB_PATH) or build_g2o() is not None
+
+
+def g2o_lib():
+    global _g2o
+    if _g2o is None:
+        if not os.path.exists(G2O_LIB_PATH) and build_g2o() is None:
+            raise FileNotFoundError("oracle/_ref/libref_g2o.so is not built and %s is absent" % REFERENCE)
+        L = C.CDLL(G2O_LIB_PATH)
+        vp = C.c_void_p
+        L.ref_g2o_edge_binary.argtypes = [C.c_int, vp, vp, vp, vp, C.c_double, vp, vp, vp, vp, vp]
+        L.ref_g2o_edge_unary.argtypes = [C.c_int, vp, vp, vp, vp, C.c_double, vp, vp, vp, vp]
+        _g2o = L
+    return _g2o
+
+
+def g2o_edge_binary(stereo, k5, pose7, X, obs, info=1.0):
+    """g2o::EdgeStereoSE3ProjectXYZ (stereo) / g2o::EdgeSE3ProjectXYZ: err[d], Jxi[d,3] (point), Jxj[d,6] (pose),
+    isDepthPositive, chi2 = e' (info I) e; d = 3 / 2.  k5 = fx fy cx cy bf."""
+    d = 3 if stereo else 2
+    k5, pose7, X, obs = (np.ascontiguousarray(a, np.float64) for a in (k5, pose7, X, obs))
+    err, Jxi, Jxj, dp, chi = np.zeros(d), np.zeros((d, 3)), np.zeros((d, 6)), C.c_int(0), C.c_double(0)
+    g2o_lib().ref_g2o_edge_binary(int(stereo), _p(k5), _p(pose7), _p(X), _p(obs), float(info), _p(err), _p(Jxi), _p(Jxj),
+                                  C.byref(dp), C.byref(chi))
+    return err, Jxi, Jxj, bool(dp.value), chi.value
+
+
+def g2o_edge_unary(stereo, k5, pose7, Xw, obs, info=1.0):
+    """g2o::EdgeStereoSE3ProjectXYZOnlyPose / g2o::EdgeSE3ProjectXYZOnlyPose: err[d], Jxi[d,6], isDepthPositive, chi2."""
+    d = 3 if stereo else 2
+    k5, pose7, Xw, obs = (np.ascontiguousarray(a, np.float64) for a in (k5, pose7, Xw, obs))
+    err, J, dp, chi = np.zeros(d), np.zeros((d, 6)), C.c_int(0), C.c_double(0)
+    g2o_lib().ref_g2o_edge_unary(int(stereo), _p(k5), _p(pose7), _p(Xw), _p(obs), float(info), _p(err), _p(J), C.byref(dp),
+                                 C.byref(chi))
+    return err, J, bool(dp.value), chi.value

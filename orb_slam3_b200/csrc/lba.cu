@@ -163,10 +163,10 @@ __device__ __forceinline__ double edge_residual(const LbaDev& D, int e, const do
     return r[0] * (s * r[0]) + r[1] * (s * r[1]);
   }
   if (D.e_stereo[e]) {
-    // types_six_dof_expmap.cpp:190-197: invz is a float
+    // types_six_dof_expmap.cpp:190-197: invz = 1.0f/trans_xyz[2] is the DOUBLE quotient rounded to float; bf*invz a float product
     const double fx = cam[0], fy = cam[1], cx = cam[2], cy = cam[3];
     const float bf = cam[4];
-    const float invz = __fdiv_rn(1.0f, (float)Xc[2]);
+    const float invz = __double2float_rn(__ddiv_rn(1.0, Xc[2]));
     const double u = Xc[0] * (double)invz * fx + cx;
     const double v = Xc[1] * (double)invz * fy + cy;
     r[0] = obs[0] - u; r[1] = obs[1] - v; r[2] = obs[2] - (u - (double)__fmul_rn(bf, invz));

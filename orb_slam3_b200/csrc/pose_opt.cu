@@ -86,7 +86,7 @@ __device__ __forceinline__ double edge_error(const PoseJob& J, const EdgeIn& E, 
   const double s = E.is2;
   if (E.ur >= 0) {
     const double fx = J.fx, fy = J.fy, cx = J.cx, cy = J.cy, bf = J.bf;
-    const float invz = 1.0f / (float)Xc[2];  // types_six_dof_expmap.cpp:340
+    const float invz = __double2float_rn(__ddiv_rn(1.0, Xc[2]));  // types_six_dof_expmap.cpp:340: double quotient rounded to float
     const double pu = Xc[0] * invz * fx + cx;
     const double pv = Xc[1] * invz * fy + cy;
     r[0] = (double)E.u - pu; r[1] = (double)E.v - pv; r[2] = (double)E.ur - (pu - bf * invz);

@@ -69,10 +69,12 @@ def _residual(pose, X, obs, cam, stereo, float_invz=True, rig=None):
         return np.asarray(obs[:2]) - _project(1, list(cam[:4]) + list(rig["dist"]), Xc, float_invz)
     fx, fy, cx, cy, bf = [float(c) for c in cam]
     if stereo:
-        invz = float(np.float32(1.0) / np.float32(Xc[2])) if float_invz else 1.0 / Xc[2]
+        invz = float(np.float32(1.0 / Xc[2])) if float_invz else 1.0 / Xc[2]   # `1.0f/trans_xyz[2]`: double quotient -> float
         u = Xc[0] * invz * fx + cx
         v = Xc[1] * invz * fy + cy
-        return np.array([obs[0] - u, obs[1] - v, obs[2] - (u - float(np.float32(bf)) * invz)])
+        # cam_project takes bf as `const float&`: with the float invz the product bf*invz is a float product
+        bz = float(np.float32(bf) * np.float32(invz)) if float_invz else float(np.float32(bf)) * invz
+        return np.array([obs[0] - u, obs[1] - v, obs[2] - (u - bz)])
     return np.array([obs[0] - (fx * Xc[0] / Xc[2] + cx), obs[1] - (fy * Xc[1] / Xc[2] + cy)])
 
 

@@ -7,10 +7,11 @@ no Eigen).  Residuals (computeError), Jacobians (linearizeOplus), isDepthPositiv
   EdgeSE3ProjectXYZOnlyPose    (PoseOptimization's mono edge, 8f-2),
 and project / projectJac of both camera models are the reference's control flow and formulas as object code; what is
 NOT the reference's here is the matrix arithmetic underneath (plain loops instead of Eigen's expression templates:
-same operations, possibly in another order), hence 1e-9 relative instead of bit equality.  The stereo edge
-(g2o::EdgeStereoSE3ProjectXYZ, a16) lives in the vendored g2o, whose core headers need far more of Eigen: it stays
-pinned by the finite-difference test of test_lba_oracle.py.  The library is built where /root/reference exists and
-travels prebuilt to the GPU box; skipped when absent."""
+same operations, possibly in another order), hence 1e-9 relative instead of bit equality.
+The stereo edges -- g2o::EdgeStereoSE3ProjectXYZ (a16) and g2o::EdgeStereoSE3ProjectXYZOnlyPose (8f-2) -- live in the
+vendored g2o: oracle/_ref/libref_g2o.so is Thirdparty/g2o/g2o/types/types_six_dof_expmap.{h,cpp} piped unmodified into the
+compiler over stand-ins for the g2o core headers they include (oracle/Makefile), held to the same 1e-9.
+The libraries are built where /root/reference exists and travel prebuilt to the GPU box; skipped when absent."""
 import numpy as np
 import pytest
 
@@ -111,3 +112,58 @@ def test_pose_optimization_mono_edges_equal_the_reference_object_code(oracle, re
         assert _close(err[:2], r_err) and _close(B[:2], r_J), e
         n += 1
     assert n > 100
+
+
+@pytest.fixture(scope="module")
+def g2o(ref):
+    if not ref.g2o_available():
+        pytest.skip("oracle/_ref/libref_g2o.so is not built and the reference tree is absent")
+    return ref
+
+
+def test_lba_stereo_edges_equal_the_vendored_g2o_object_code(oracle, g2o):
+    """g2o::EdgeStereoSE3ProjectXYZ (row a16: float invz in cam_project, the 3x3 / 3x6 Jacobians) on every stereo edge of a
+    window, and g2o's own EdgeSE3ProjectXYZ on the mono ones (the formulas OptimizableTypes.cpp generalises)."""
+    g, _ = scenes.lba_graph(6, 150, seed=5, stereo_frac=0.6)
+    gv = scenes.lba_view(g)
+    n_st = n_mono = 0
+    for e in range(len(g["e_kf"])):
+        k, l, st = int(g["e_kf"][e]), int(g["e_mp"][e]), int(g["e_stereo"][e])
+        pose = g["kf_pose"][k].copy()
+        pose[:4] /= np.linalg.norm(pose[:4])
+        info = float(g["e_inv_sigma2"][e])
+        r_err, r_A, r_B, r_dp, r_chi = g2o.g2o_edge_binary(st, g["kf_cam"][k], pose, g["mp_pos"][l], g["e_obs"][e], info)
+        err, A, B, dp = oracle.lba_edge(gv, e)
+        d = 3 if st else 2
+        assert _close(err[:d], r_err), (e, st, err, r_err)
+        assert _close(A[:d], r_A), (e, st, A[:d], r_A)
+        assert _close(B[:d], r_B), (e, st, B[:d], r_B)
+        assert dp == r_dp
+        assert _close(info * float(err[:d] @ err[:d]), r_chi)
+        if not st:
+            assert err[2] == 0 and not A[2].any() and not B[2].any()
+        n_st += st
+        n_mono += 1 - st
+    assert n_st > 300 and n_mono > 200
+
+
+def test_pose_optimization_edges_equal_the_vendored_g2o_object_code(oracle, g2o):
+    """g2o::EdgeStereoSE3ProjectXYZOnlyPose (Optimizer.cc:897-935) and g2o's EdgeSE3ProjectXYZOnlyPose of a frame."""
+    import ctypes as C
+    v, _ = scenes.pose_scene(400, seed=6, stereo_frac=0.6)
+    xw = np.ctypeslib.as_array(C.cast(v.xw, C.POINTER(C.c_float)), (v.n * 3,)).reshape(-1, 3).astype(np.float64)
+    obs = np.ctypeslib.as_array(C.cast(v.obs, C.POINTER(C.c_float)), (v.n * 3,)).reshape(-1, 3).astype(np.float64)
+    pose = np.array(list(v.pose))
+    pose[:4] /= np.linalg.norm(pose[:4])
+    k5 = np.array([v.fx, v.fy, v.cx, v.cy, v.bf])
+    n_st = n_mono = 0
+    for e in range(v.n):
+        st = int(obs[e, 2] >= 0)
+        r_err, r_J, r_dp, _ = g2o.g2o_edge_unary(st, k5, pose, xw[e], obs[e])
+        err, B = oracle.pose_edge(v, e)
+        d = 3 if st else 2
+        assert _close(err[:d], r_err), (e, st, err, r_err)
+        assert _close(B[:d], r_J), (e, st)
+        n_st += st
+        n_mono += 1 - st
+    assert n_st > 150 and n_mono > 100
