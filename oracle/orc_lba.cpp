@@ -401,6 +401,75 @@ void schur(const Problem& P, double lambda, std::vector<double>& S, std::vector<
   }
 }
 
+
+// The operations g2o's LM driver calls on its Solver / SparseOptimizer (optimization_algorithm_levenberg.cpp:61-169), over a
+// Problem: buildSystem, setLambda + solve (Schur + LDL^T + landmark back-substitution, block_solver.hpp:354-486), update,
+// push / pop / discardTop, the diagonal computeLambdaInit scans and the sum computeScale forms.  orc_lba_solve below runs
+// its restated control law on them; the orc_lba_stepper_* entry points expose the SAME operations so that the reference's
+// own control law -- optimization_algorithm_levenberg.cpp compiled unmodified into oracle/_ref/libref_lm.so -- can drive
+// them too (tests/test_ref_lm.py holds the two drivers equal).
+struct Stepper {
+  Problem P;
+  const int nf, n;
+  const size_t nvec;
+  std::vector<double> S, bs, Dinv, D;
+  std::vector<int> first;
+  std::vector<std::vector<SE3>> pose_stack;
+  std::vector<std::vector<double>> pt_stack;
+  explicit Stepper(const lba_graph_view* g) : P(g), nf(P.nf), n(6 * P.nf), nvec(P.b.size()) {}
+  double max_diagonal() const {  // computeLambdaInit: max |H_jj| over all free vertices
+    double mx = 0;
+    for (int f = 0; f < nf; f++)
+      for (int j = 0; j < 6; j++) mx = std::max(std::fabs(P.Hpp[36 * (size_t)f + j * 7]), mx);
+    for (int l = 0; l < P.g->n_mp; l++)
+      for (int j = 0; j < 3; j++) mx = std::max(std::fabs(P.Hll[9 * (size_t)l + j * 4]), mx);
+    return mx;
+  }
+  void push() { pose_stack.push_back(P.pose); pt_stack.push_back(P.pt); }
+  void pop() { P.pose = pose_stack.back(); P.pt = pt_stack.back(); discard_top(); }
+  void discard_top() { pose_stack.pop_back(); pt_stack.pop_back(); }
+  bool solve(double lambda) {  // setLambda(lambda) + solve(): x is left stale when the factorisation fails
+    const lba_graph_view* g = P.g;
+    schur(P, lambda, S, bs, Dinv, nullptr);
+    const bool ok = skyline_ldlt(S, n, first, D);
+    if (!ok) return false;
+    for (int i = 0; i < n; i++) P.x[i] = bs[i];
+    skyline_solve(S, first, D, n, P.x.data());
+    for (int l = 0; l < g->n_mp; l++) {  // xl = Dinv (bl - W^T xp)
+      double c[3] = {P.b[(size_t)n + 3 * (size_t)l], P.b[(size_t)n + 3 * (size_t)l + 1], P.b[(size_t)n + 3 * (size_t)l + 2]};
+      for (int e : P.lm_edges[l]) {
+        const int f = P.free_idx[g->e_kf[e]];
+        if (f < 0) continue;
+        const double* We = &P.W[18 * (size_t)e];
+        for (int j = 0; j < 3; j++)
+          for (int i = 0; i < 6; i++) c[j] -= We[i * 3 + j] * P.x[6 * f + i];
+      }
+      const double* Di = &Dinv[9 * (size_t)l];
+      for (int i = 0; i < 3; i++) P.x[(size_t)n + 3 * (size_t)l + i] = Di[i * 3] * c[0] + Di[i * 3 + 1] * c[1] + Di[i * 3 + 2] * c[2];
+    }
+    return true;
+  }
+  void update(const double* x) {  // oplus on every free vertex (sparse_optimizer.cpp:421-432)
+    const lba_graph_view* g = P.g;
+    for (int k = 0; k < g->n_kf; k++)
+      if (P.free_idx[k] >= 0) P.pose[k] = se3_exp_mul(&x[6 * (size_t)P.free_idx[k]], P.pose[k]);
+    for (size_t i = 0; i < 3 * (size_t)g->n_mp; i++) P.pt[i] += x[(size_t)n + i];
+  }
+  double scale(double lambda) const {  // computeScale
+    double sc = 0;
+    for (size_t j = 0; j < nvec; j++) sc += P.x[j] * (lambda * P.x[j] + P.b[j]);
+    return sc;
+  }
+  void results(double* kf_pose_out, double* mp_pos_out) const {
+    for (int k = 0; k < P.g->n_kf; k++) {
+      double* o = kf_pose_out + 7 * k;
+      o[0] = P.pose[k].r.x; o[1] = P.pose[k].r.y; o[2] = P.pose[k].r.z; o[3] = P.pose[k].r.w;
+      o[4] = P.pose[k].t[0]; o[5] = P.pose[k].t[1]; o[6] = P.pose[k].t[2];
+    }
+    memcpy(mp_pos_out, P.pt.data(), sizeof(double) * 3 * (size_t)P.g->n_mp);
+  }
+};
+
 }  // namespace
 
 extern "C" {
@@ -410,16 +479,12 @@ int orc_lba_solve(const lba_graph_view* g, const volatile uint8_t* stop, int max
                   double* kf_pose_out, double* mp_pos_out, double* chi2_out, uint8_t* depth_pos_out,
                   lba_stats* stats, double* trace /* per trial: lambda, tempChi, rho, accepted; cap 4*128 */) {
   auto t_begin = std::chrono::steady_clock::now();
-  Problem P(g);
-  const int nf = P.nf, n = 6 * nf;
-  const size_t nvec = P.b.size();
+  Stepper st(g);
+  Problem& P = st.P;
+  const int nf = st.nf;
   double lambda = -1, ni = 2;
   int nBad = 0, trials = 0, iters = 0, stopped = 0;
   double chi_first = 0, currentChi = 0;
-  std::vector<double> S, bs, Dinv, D;
-  std::vector<int> first;
-  std::vector<SE3> pose_bak;
-  std::vector<double> pt_bak;
   auto terminate = [&]() { return stop && *stop; };
   for (int it = 0; it < max_iters && !terminate(); it++) {
     P.compute_errors();
@@ -430,48 +495,20 @@ int orc_lba_solve(const lba_graph_view* g, const volatile uint8_t* stop, int max
     P.build_system();
     if (it == 0) {
       if (lambda_init > 0) lambda = lambda_init;
-      else {  // computeLambdaInit: tau * max diagonal over all free vertices
-        double mx = 0;
-        for (int f = 0; f < nf; f++)
-          for (int j = 0; j < 6; j++) mx = std::max(std::fabs(P.Hpp[36 * (size_t)f + j * 7]), mx);
-        for (int l = 0; l < g->n_mp; l++)
-          for (int j = 0; j < 3; j++) mx = std::max(std::fabs(P.Hll[9 * (size_t)l + j * 4]), mx);
-        lambda = 1e-5 * mx;
-      }
+      else lambda = 1e-5 * st.max_diagonal();  // computeLambdaInit: tau * max diagonal over all free vertices
       ni = 2; nBad = 0;
     }
     double rho = 0;
     int qmax = 0;
     do {
-      pose_bak = P.pose; pt_bak = P.pt;  // push
-      schur(P, lambda, S, bs, Dinv, nullptr);
-      bool ok2 = skyline_ldlt(S, n, first, D);
-      if (ok2) {
-        for (int i = 0; i < n; i++) P.x[i] = bs[i];
-        skyline_solve(S, first, D, n, P.x.data());
-        for (int l = 0; l < g->n_mp; l++) {  // xl = Dinv (bl - W^T xp)
-          double c[3] = {P.b[(size_t)n + 3 * (size_t)l], P.b[(size_t)n + 3 * (size_t)l + 1], P.b[(size_t)n + 3 * (size_t)l + 2]};
-          for (int e : P.lm_edges[l]) {
-            const int f = P.free_idx[g->e_kf[e]];
-            if (f < 0) continue;
-            const double* We = &P.W[18 * (size_t)e];
-            for (int j = 0; j < 3; j++)
-              for (int i = 0; i < 6; i++) c[j] -= We[i * 3 + j] * P.x[6 * f + i];
-          }
-          const double* Di = &Dinv[9 * (size_t)l];
-          for (int i = 0; i < 3; i++) P.x[(size_t)n + 3 * (size_t)l + i] = Di[i * 3] * c[0] + Di[i * 3 + 1] * c[1] + Di[i * 3 + 2] * c[2];
-        }
-      }
-      // update (oplus) -- g2o updates even when the solve failed; x then holds stale values
-      for (int k = 0; k < g->n_kf; k++)
-        if (P.free_idx[k] >= 0) P.pose[k] = se3_exp_mul(&P.x[6 * (size_t)P.free_idx[k]], P.pose[k]);
-      for (size_t i = 0; i < 3 * (size_t)g->n_mp; i++) P.pt[i] += P.x[(size_t)n + i];
+      st.push();
+      const bool ok2 = st.solve(lambda);
+      st.update(P.x.data());  // g2o updates even when the solve failed; x then holds stale values
       P.compute_errors();
       tempChi = P.robust_chi2();
       if (!ok2) tempChi = std::numeric_limits<double>::max();
       rho = currentChi - tempChi;
-      double scale = 0;
-      for (size_t j = 0; j < nvec; j++) scale += P.x[j] * (lambda * P.x[j] + P.b[j]);
+      double scale = st.scale(lambda);
       scale += 1e-3;
       rho /= scale;
       const bool accept = rho > 0 && std::isfinite(tempChi);
@@ -486,10 +523,11 @@ int orc_lba_solve(const lba_graph_view* g, const volatile uint8_t* stop, int max
         lambda *= scaleFactor;
         ni = 2;
         currentChi = tempChi;
+        st.discard_top();
       } else {
         lambda *= ni;
         ni *= 2;
-        P.pose = pose_bak; P.pt = pt_bak;  // pop
+        st.pop();
       }
       qmax++;
       trials++;
@@ -501,12 +539,7 @@ int orc_lba_solve(const lba_graph_view* g, const volatile uint8_t* stop, int max
     if (nBad >= 3) break;
   }
   if (terminate()) stopped = 1;
-  for (int k = 0; k < g->n_kf; k++) {
-    double* o = kf_pose_out + 7 * k;
-    o[0] = P.pose[k].r.x; o[1] = P.pose[k].r.y; o[2] = P.pose[k].r.z; o[3] = P.pose[k].r.w;
-    o[4] = P.pose[k].t[0]; o[5] = P.pose[k].t[1]; o[6] = P.pose[k].t[2];
-  }
-  memcpy(mp_pos_out, P.pt.data(), sizeof(double) * 3 * (size_t)g->n_mp);
+  st.results(kf_pose_out, mp_pos_out);
   for (int e = 0; e < g->n_edges; e++) {
     if (chi2_out) chi2_out[e] = P.chi2(e);  // errors of the last evaluated trial
     if (depth_pos_out) {
@@ -526,6 +559,30 @@ int orc_lba_solve(const lba_graph_view* g, const volatile uint8_t* stop, int max
   }
   return iters;
 }
+
+// ---- the Stepper's operations one by one (see struct Stepper): what the reference's LM driver object code calls
+void* orc_lba_stepper_open(const lba_graph_view* g) { return new Stepper(g); }
+void orc_lba_stepper_close(void* h) { delete static_cast<Stepper*>(h); }
+void orc_lba_stepper_compute_errors(void* h) { static_cast<Stepper*>(h)->P.compute_errors(); }
+double orc_lba_stepper_robust_chi2(void* h) { return static_cast<Stepper*>(h)->P.robust_chi2(); }
+void orc_lba_stepper_build_system(void* h) { static_cast<Stepper*>(h)->P.build_system(); }
+// free vertices in g2o's index order for this problem: poses first (6-dimensional), then landmarks (3)
+int orc_lba_stepper_n_vertices(void* h) { Stepper* s = static_cast<Stepper*>(h); return s->nf + s->P.g->n_mp; }
+int orc_lba_stepper_vertex_dim(void* h, int v) { return v < static_cast<Stepper*>(h)->nf ? 6 : 3; }
+double orc_lba_stepper_hessian(void* h, int v, int i, int j) {
+  Stepper* s = static_cast<Stepper*>(h);
+  if (v < s->nf) return s->P.Hpp[36 * (size_t)v + i * 6 + j];
+  return s->P.Hll[9 * (size_t)(v - s->nf) + i * 3 + j];
+}
+int orc_lba_stepper_solve(void* h, double lambda) { return static_cast<Stepper*>(h)->solve(lambda) ? 1 : 0; }
+double* orc_lba_stepper_x(void* h) { return static_cast<Stepper*>(h)->P.x.data(); }
+double* orc_lba_stepper_b(void* h) { return static_cast<Stepper*>(h)->P.b.data(); }
+size_t orc_lba_stepper_vector_size(void* h) { return static_cast<Stepper*>(h)->nvec; }
+void orc_lba_stepper_update(void* h, const double* x) { static_cast<Stepper*>(h)->update(x); }
+void orc_lba_stepper_push(void* h) { static_cast<Stepper*>(h)->push(); }
+void orc_lba_stepper_pop(void* h) { static_cast<Stepper*>(h)->pop(); }
+void orc_lba_stepper_discard_top(void* h) { static_cast<Stepper*>(h)->discard_top(); }
+void orc_lba_stepper_results(void* h, double* kf_pose_out, double* mp_pos_out) { static_cast<Stepper*>(h)->results(kf_pose_out, mp_pos_out); }
 
 // One edge at the input estimates: err (3, third entry 0 for 2-D edges), A = d err / d point (d x 3), B = d err / d pose
 // (d x 6), isDepthPositive -- what tests/test_ref_edges.py holds against the reference's own computeError() /
