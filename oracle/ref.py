@@ -429,3 +429,47 @@ def g2o_edge_unary(stereo, k5, pose7, Xw, obs, info=1.0):
     g2o_lib().ref_g2o_edge_unary(int(stereo), _p(k5), _p(pose7), _p(Xw), _p(obs), float(info), _p(err), _p(J), C.byref(dp),
                                  C.byref(chi))
     return err, J, bool(dp.value), chi.value
+
+
+# ---- oracle/_ref/libref_lm.so: g2o's optimization_algorithm_levenberg.cpp as object code over the oracle's Stepper
+LM_LIB_PATH = os.path.join(_HERE, "_ref", "libref_lm.so")
+_lm = None
+
+
+def build_lm(force=False):
+    if not os.path.exists(os.path.join(REFERENCE, "Thirdparty", "g2o", "g2o", "core", "optimization_algorithm_levenberg.cpp")):
+        return None
+    _o.build()
+    cmd = ["make", "-C", _HERE, "REF=" + REFERENCE] + (["-B"] if force else []) + ["_ref/libref_lm.so"]
+    subprocess.check_call(cmd, stdout=subprocess.DEVNULL)
+    return LM_LIB_PATH
+
+
+def lm_available():
+    return os.path.exists(LM_LIB_PATH) or build_lm() is not None
+
+
+def lm_lib():
+    global _lm
+    if _lm is None:
+        if not os.path.exists(LM_LIB_PATH) and build_lm() is None:
+            raise FileNotFoundError("oracle/_ref/libref_lm.so is not built and %s is absent" % REFERENCE)
+        _o.lib()
+        L = C.CDLL(LM_LIB_PATH)
+        vp = C.c_void_p
+        L.ref_lm_optimize.argtypes = [vp, vp, C.c_int, C.c_double, vp, vp, vp, vp]
+        _lm = L
+    return _lm
+
+
+def lm_optimize(g, max_iters=10, lambda_init=0.0):
+    """optimizer.optimize(max_iters) driven by the reference's OptimizationAlgorithmLevenberg object code over the
+    oracle's linearise / Schur / LDL^T / update operations.  Returns dict like oracle.lba_solve (trace rows: lambda,
+    tempChi, NaN, accepted)."""
+    kf = np.zeros((g.n_kf, 7))
+    mp = np.zeros((g.n_mp, 3))
+    out4 = np.zeros(4)
+    trace = np.zeros((128, 4))
+    it = lm_lib().ref_lm_optimize(C.byref(g), None, int(max_iters), float(lambda_init), _p(kf), _p(mp), _p(out4), _p(trace))
+    return dict(iterations=it, trials=int(out4[1]), chi2_final=out4[2], lambda_final=out4[3], kf_pose=kf, mp_pos=mp,
+                trace=trace[:int(out4[1])].copy())
