@@ -281,6 +281,13 @@ def lba_edge(g, e):
     return err, A, B, bool(dp.value)
 
 
+def huber(th, e):
+    """RobustKernelHuber with setDelta((float)th): (rho(e), rho'(e)) of the squared error e."""
+    out = np.zeros(2)
+    lib().orc_huber(C.c_float(th), C.c_double(e), _ptr(out))
+    return out
+
+
 def pose_edge(v, e):
     """One edge of a pose_opt_view at its input pose: err[3], B[3 x 6] = d err / d pose."""
     err, B = np.zeros(3), np.zeros((3, 6))

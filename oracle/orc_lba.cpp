@@ -560,6 +560,10 @@ int orc_lba_solve(const lba_graph_view* g, const volatile uint8_t* stop, int max
   return iters;
 }
 
+// The Huber kernel of orc_se3.h for delta = (float)th (Optimizer.cc:1275-1276 hands g2o a float): rho[0], rho[1] --
+// tests/test_ref_edges.py holds it against RobustKernelHuber's object code (oracle/_ref/libref_g2o.so).
+void orc_huber(float th, double e, double* rho2) { Huber(th).robustify(e, rho2[0], rho2[1]); }
+
 // ---- the Stepper's operations one by one (see struct Stepper): what the reference's LM driver object code calls
 void* orc_lba_stepper_open(const lba_graph_view* g) { return new Stepper(g); }
 void orc_lba_stepper_close(void* h) { delete static_cast<Stepper*>(h); }

@@ -406,6 +406,7 @@ def g2o_lib():
         vp = C.c_void_p
         L.ref_g2o_edge_binary.argtypes = [C.c_int, vp, vp, vp, vp, C.c_double, vp, vp, vp, vp, vp]
         L.ref_g2o_edge_unary.argtypes = [C.c_int, vp, vp, vp, vp, C.c_double, vp, vp, vp, vp]
+        L.ref_g2o_huber.argtypes = [C.c_double, C.c_double, vp]
         _g2o = L
     return _g2o
 
@@ -473,3 +474,10 @@ def lm_optimize(g, max_iters=10, lambda_init=0.0):
     it = lm_lib().ref_lm_optimize(C.byref(g), None, int(max_iters), float(lambda_init), _p(kf), _p(mp), _p(out4), _p(trace))
     return dict(iterations=it, trials=int(out4[1]), chi2_final=out4[2], lambda_final=out4[3], kf_pose=kf, mp_pos=mp,
                 trace=trace[:int(out4[1])].copy())
+
+
+def g2o_huber(delta, e):
+    """g2o::RobustKernelHuber: setDelta(delta), robustify(e) -> rho[3] (rho, rho', rho'')."""
+    rho = np.zeros(3)
+    g2o_lib().ref_g2o_huber(float(delta), float(e), _p(rho))
+    return rho

@@ -167,3 +167,16 @@ def test_pose_optimization_edges_equal_the_vendored_g2o_object_code(oracle, g2o)
         n_st += st
         n_mono += 1 - st
     assert n_st > 150 and n_mono > 100
+
+
+def test_huber_kernel_equals_the_vendored_g2o_object_code(oracle, g2o):
+    """RobustKernelHuber::setDelta / robustify (robust_kernel_impl.cpp:65-91, float dsqr): rho and rho' bit for bit, for
+    both thresholds of LocalBundleAdjustment (Optimizer.cc:1275-1276), on both sides of and exactly at delta^2."""
+    rng = np.random.default_rng(0)
+    for th in (np.float32(np.sqrt(5.991)), np.float32(np.sqrt(7.815))):
+        dsqr = float(np.float32(float(th) * float(th)))
+        es = np.concatenate([rng.uniform(0, 3 * dsqr, 500), rng.uniform(0, 1e4, 200), [0.0, dsqr, np.nextafter(dsqr, 0), np.nextafter(dsqr, 1e9)]])
+        for e in es:
+            r = g2o.g2o_huber(float(th), float(e))
+            o = oracle.huber(th, float(e))
+            assert o[0] == r[0] and o[1] == r[1], (float(th), e, o, r)
