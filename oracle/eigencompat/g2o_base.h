@@ -14,6 +14,7 @@ namespace g2o {
 typedef Eigen::Matrix<double, 6, 1> Vector6d; typedef Eigen::Matrix<double, 7, 1> Vector7d;
 typedef Eigen::Matrix<double, 3, 1> Vector3d; typedef Eigen::Matrix<double, 2, 1> Vector2d; typedef Eigen::Matrix<double, 3, 3> Matrix3d;
 using Eigen::Quaterniond;
+#ifndef G2O_BASE_REAL_SE3QUAT   // (oracle/Makefile, libref_g2o.so: the reference's own se3quat.h is in use instead)
 class SE3Quat {
  public:
   SE3Quat() {}
@@ -39,6 +40,7 @@ class SE3Quat {
   Eigen::Quaterniond _r;
   Eigen::Vector3d _t;
 };
+#endif
 class Sim3 {  // type-check only
  public:
   Sim3() {} template <class... A> Sim3(const A&...) {}
@@ -67,6 +69,7 @@ class OptimizableGraph : public HyperGraph {
    public:
     virtual bool read(std::istream&) { return true; } virtual bool write(std::ostream&) const { return true; }
     virtual void setToOriginImpl() {} virtual void oplusImpl(const double*) {}
+    void oplus(const double* v) { oplusImpl(v); updateCache(); }   // optimizable_graph.h:296-300
     void setFixed(bool f) { _fixed = f; } bool fixed() const { return _fixed; } void setMarginalized(bool m) { _marg = m; }
     void updateCache() {}
    protected:

@@ -288,6 +288,13 @@ def huber(th, e):
     return out
 
 
+def se3_oplus(pose7, update6):
+    """VertexSE3Expmap::oplusImpl: SE3Quat::exp(update6) * pose7 (quaternion xyzw + t), normalised like g2o does."""
+    out = np.zeros(7)
+    lib().orc_se3_oplus(_ptr(np.ascontiguousarray(pose7, np.float64)), _ptr(np.ascontiguousarray(update6, np.float64)), _ptr(out))
+    return out
+
+
 def pose_edge(v, e):
     """One edge of a pose_opt_view at its input pose: err[3], B[3 x 6] = d err / d pose."""
     err, B = np.zeros(3), np.zeros((3, 6))

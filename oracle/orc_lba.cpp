@@ -564,6 +564,15 @@ int orc_lba_solve(const lba_graph_view* g, const volatile uint8_t* stop, int max
 // tests/test_ref_edges.py holds it against RobustKernelHuber's object code (oracle/_ref/libref_g2o.so).
 void orc_huber(float th, double e, double* rho2) { Huber(th).robustify(e, rho2[0], rho2[1]); }
 
+// se3_exp_mul of orc_se3.h -- VertexSE3Expmap::oplusImpl: SE3Quat::exp(update) * estimate -- on its own:
+// tests/test_ref_edges.py holds it against the reference's se3quat.h as object code (oracle/_ref/libref_g2o.so).
+void orc_se3_oplus(const double* pose7, const double* update6, double* out7) {
+  SE3 T; T.r = Quat{pose7[0], pose7[1], pose7[2], pose7[3]}; quat_normalize(T.r);
+  T.t[0] = pose7[4]; T.t[1] = pose7[5]; T.t[2] = pose7[6];
+  const SE3 o = se3_exp_mul(update6, T);
+  out7[0] = o.r.x; out7[1] = o.r.y; out7[2] = o.r.z; out7[3] = o.r.w; out7[4] = o.t[0]; out7[5] = o.t[1]; out7[6] = o.t[2];
+}
+
 // ---- the Stepper's operations one by one (see struct Stepper): what the reference's LM driver object code calls
 void* orc_lba_stepper_open(const lba_graph_view* g) { return new Stepper(g); }
 void orc_lba_stepper_close(void* h) { delete static_cast<Stepper*>(h); }

@@ -407,6 +407,8 @@ def g2o_lib():
         L.ref_g2o_edge_binary.argtypes = [C.c_int, vp, vp, vp, vp, C.c_double, vp, vp, vp, vp, vp]
         L.ref_g2o_edge_unary.argtypes = [C.c_int, vp, vp, vp, vp, C.c_double, vp, vp, vp, vp]
         L.ref_g2o_huber.argtypes = [C.c_double, C.c_double, vp]
+        L.ref_g2o_oplus.argtypes = [vp, vp, vp]
+        L.ref_g2o_se3_map.argtypes = [vp, vp, vp]
         _g2o = L
     return _g2o
 
@@ -481,3 +483,16 @@ def g2o_huber(delta, e):
     rho = np.zeros(3)
     g2o_lib().ref_g2o_huber(float(delta), float(e), _p(rho))
     return rho
+
+
+def g2o_oplus(pose7, update6):
+    """g2o::VertexSE3Expmap::oplus(update6) on the estimate pose7, with the reference's own se3quat.h: the new pose7."""
+    out = np.zeros(7)
+    g2o_lib().ref_g2o_oplus(_p(np.ascontiguousarray(pose7, np.float64)), _p(np.ascontiguousarray(update6, np.float64)), _p(out))
+    return out
+
+
+def g2o_se3_map(pose7, X):
+    out = np.zeros(3)
+    g2o_lib().ref_g2o_se3_map(_p(np.ascontiguousarray(pose7, np.float64)), _p(np.ascontiguousarray(X, np.float64)), _p(out))
+    return out

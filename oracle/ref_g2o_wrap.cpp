@@ -80,4 +80,21 @@ void ref_g2o_edge_unary(int stereo, const double* k5, const double* pose7, const
   }
 }
 
+// VertexSE3Expmap::oplusImpl (types_six_dof_expmap.h:64-67): estimate <- SE3Quat::exp(update) * estimate, with the reference's
+// own se3quat.h (exp: Rodrigues + V, Quaterniond(R), operator*, normalizeRotation).  out7 = quaternion x y z w + translation.
+void ref_g2o_oplus(const double* pose7, const double* update6, double* out7) {
+  g2o::VertexSE3Expmap v;
+  v.setEstimate(se3(pose7));
+  v.oplus(update6);
+  const g2o::SE3Quat& T = v.estimate();
+  out7[0] = T.rotation().x(); out7[1] = T.rotation().y(); out7[2] = T.rotation().z(); out7[3] = T.rotation().w();
+  out7[4] = T.translation()[0]; out7[5] = T.translation()[1]; out7[6] = T.translation()[2];
+}
+
+// SE3Quat::map and SE3Quat::operator* / inverse of the reference's se3quat.h (what the edges call), for direct checks
+void ref_g2o_se3_map(const double* pose7, const double* X, double* out3) {
+  const Eigen::Vector3d r = se3(pose7).map(Eigen::Vector3d(X[0], X[1], X[2]));
+  out3[0] = r[0]; out3[1] = r[1]; out3[2] = r[2];
+}
+
 }  // extern "C"

@@ -180,3 +180,28 @@ def test_huber_kernel_equals_the_vendored_g2o_object_code(oracle, g2o):
             r = g2o.g2o_huber(float(th), float(e))
             o = oracle.huber(th, float(e))
             assert o[0] == r[0] and o[1] == r[1], (float(th), e, o, r)
+
+
+def test_vertex_oplus_equals_the_vendored_g2o_object_code(oracle, g2o):
+    """VertexSE3Expmap::oplusImpl = SE3Quat::exp(update) * estimate (row a22) with the reference's own se3quat.h: the
+    Rodrigues / V formulas, the theta < 1e-5 branch, Quaterniond(R) in all four branches (rotations up to pi), operator*
+    and normalizeRotation -- against the oracle's se3_exp_mul."""
+    rng = np.random.default_rng(1)
+    n_small = n_big = 0
+    for i in range(3000):
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q)
+        pose = np.concatenate([q if q[3] > 0 else -q, rng.normal(0, 5, 3)])
+        if i % 3 == 0:      # LM-sized steps
+            up = rng.normal(0, 1, 6) * 10.0 ** rng.uniform(-9, -2)
+        elif i % 3 == 1:    # the small-angle branch with a large translation part
+            up = np.concatenate([rng.normal(0, 1, 3) * 1e-6, rng.normal(0, 1, 3)])
+        else:               # large rotations: trace(R) <= 0 picks one of the three other branches of Quaterniond(R)
+            w = rng.normal(size=3)
+            up = np.concatenate([w / np.linalg.norm(w) * rng.uniform(2.0, np.pi), rng.normal(0, 1, 3)])
+        n_small += np.linalg.norm(up[:3]) < 1e-5
+        n_big += np.linalg.norm(up[:3]) > 2
+        a, b = oracle.se3_oplus(pose, up), g2o.g2o_oplus(pose, up)
+        assert np.abs(a - b).max() <= 1e-12 * max(1.0, np.abs(b).max()), (i, up, a, b)
+        assert abs(np.linalg.norm(b[:4]) - 1) < 1e-12 and b[3] >= 0
+    assert n_small > 500 and n_big > 500
