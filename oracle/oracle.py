@@ -256,18 +256,20 @@ def match_triangulate(kf1, kf2, fv1, fv2, F12, ep, only_stereo=False, coarse=Fal
 
 
 # ---- local BA (views: orb_slam3_b200/views.py lba_graph_view / lba_stats, interface types)
-def lba_solve(g, max_iters=10, lambda_init=0.0, stop=None):
-    """optimize(max_iters) on the flat graph view g.  Returns dict(kf_pose, mp_pos, chi2, depth_pos, stats, trace)."""
+def lba_solve(g, max_iters=10, lambda_init=0.0, stop=None, driver=None):
+    """optimize(max_iters) on the flat graph view g.  Returns dict(kf_pose, mp_pos, chi2, depth_pos, stats, trace).
+    driver: address of an orc_lm_driver that runs the LM control law (None = the restated one; oracle.ref.lm_driver() =
+    the reference's optimization_algorithm_levenberg.cpp as object code)."""
     from orb_slam3_b200.views import lba_stats
     kf = np.zeros((g.n_kf, 7))
     mp = np.zeros((g.n_mp, 3))
     chi2 = np.zeros(g.n_edges)
     dp = np.zeros(g.n_edges, np.uint8)
     st = lba_stats()
-    trace = np.zeros((128, 4))
+    trace = np.full((128, 4), np.nan)
     sp = _ptr(stop) if stop is not None else None
-    it = lib().orc_lba_solve(C.byref(g), sp, max_iters, lambda_init, _ptr(kf), _ptr(mp), _ptr(chi2), _ptr(dp),
-                             C.byref(st), _ptr(trace))
+    it = lib().orc_lba_solve_lm(C.byref(g), sp, max_iters, C.c_double(lambda_init), _ptr(kf), _ptr(mp), _ptr(chi2), _ptr(dp),
+                                C.byref(st), _ptr(trace), C.c_void_p(driver))
     return dict(iterations=it, kf_pose=kf, mp_pos=mp, chi2=chi2, depth_pos=dp, stats=st.as_dict(),
                 trace=trace[:st.trials].copy())
 
@@ -341,15 +343,18 @@ def stereo_match(kl, dl, kr, dr, pyr_l, pyr_r, bf, b, scale_factor=1.2):
     return n, ur, dp, sad
 
 
-def pose_optimize(view):
+def pose_optimize(view, driver=None):
     """Optimizer::PoseOptimization (Optimizer.cc:814-1115) on a pose_opt_view.
-    Returns dict(inliers, pose[7], outlier[n] bool, chi2[n], stats = rounds / LM iterations / LM trials)."""
+    Returns dict(inliers, pose[7], outlier[n] bool, chi2[n], stats = rounds / LM iterations / LM trials, trace).
+    driver: as for lba_solve."""
     pose = np.zeros(7)
     out = np.zeros(max(view.n, 1), np.uint8)
     chi2 = np.zeros(max(view.n, 1))
     stats = np.zeros(3, np.int32)
-    n = lib().orc_pose_optimize(C.byref(view), _ptr(pose), _ptr(out), _ptr(chi2), _ptr(stats))
-    return dict(inliers=n, pose=pose, outlier=out[:view.n].astype(bool), chi2=chi2[:view.n], stats=stats)
+    trace = np.full((128, 4), np.nan)
+    n = lib().orc_pose_optimize_lm(C.byref(view), _ptr(pose), _ptr(out), _ptr(chi2), _ptr(stats), C.c_void_p(driver), _ptr(trace))
+    return dict(inliers=n, pose=pose, outlier=out[:view.n].astype(bool), chi2=chi2[:view.n], stats=stats,
+                trace=trace[:min(int(stats[2]), 128)].copy())
 
 
 def is_in_frustum(view, viewing_cos_limit=0.5, out=None):
@@ -386,17 +391,19 @@ def bow_transform(vocab_view, desc, levelsup=4):
 from orb_slam3_b200.views import lia_graph_view, make_lia_view  # noqa: E402,F401  (interface types only)
 
 
-def lia_solve(v):
+def lia_solve(v, driver=None):
+    """Optimizer::LocalInertialBA's optimize() on a lia_graph_view (driver: as for lba_solve)."""
     kf = np.zeros((v.n_kf, 21))
     mp = np.zeros((v.n_mp, 3))
     chi2 = np.zeros(max(v.n_edges, 1))
     dp = np.zeros(max(v.n_edges, 1), np.uint8)
     st = np.zeros(6)
-    it = lib().orc_lia_solve(C.byref(v), _ptr(kf), _ptr(mp), _ptr(chi2), _ptr(dp), _ptr(st))
+    trace = np.full((128, 4), np.nan)
+    it = lib().orc_lia_solve_lm(C.byref(v), _ptr(kf), _ptr(mp), _ptr(chi2), _ptr(dp), _ptr(st), C.c_void_p(driver), _ptr(trace))
     return dict(iterations=it, Rcw=kf[:, :9].reshape(-1, 3, 3), tcw=kf[:, 9:12], vel=kf[:, 12:15], bg=kf[:, 15:18],
                 ba=kf[:, 18:21], mp_pos=mp, chi2=chi2[:v.n_edges], depth_pos=dp[:v.n_edges],
                 stats=dict(iterations=int(st[0]), trials=int(st[1]), err=st[2], err_end=st[3], lambda_final=st[4],
-                           dim=int(st[5])))
+                           dim=int(st[5])), trace=trace[:min(int(st[1]), 128)].copy())
 
 
 def lia_linearize(v, delta=None):

@@ -31,6 +31,7 @@
 #include "../include/orb_b200.h"
 
 #include "orc_se3.h"
+#include "orc_lm_ops.h"
 
 namespace {
 
@@ -416,6 +417,7 @@ struct Stepper {
   std::vector<int> first;
   std::vector<std::vector<SE3>> pose_stack;
   std::vector<std::vector<double>> pt_stack;
+  const volatile uint8_t* stop = nullptr;   // pbStopFlag -> optimizer.setForceStopFlag (Optimizer.cc:1153-1154)
   explicit Stepper(const lba_graph_view* g) : P(g), nf(P.nf), n(6 * P.nf), nvec(P.b.size()) {}
   double max_diagonal() const {  // computeLambdaInit: max |H_jj| over all free vertices
     double mx = 0;
@@ -470,75 +472,51 @@ struct Stepper {
   }
 };
 
+const orc_lm_ops* lba_ops() {
+  static const orc_lm_ops ops = {
+      [](void* h) { static_cast<Stepper*>(h)->P.compute_errors(); },
+      [](void* h) { return static_cast<Stepper*>(h)->P.robust_chi2(); },
+      [](void* h) { static_cast<Stepper*>(h)->P.build_system(); },
+      // free vertices: poses first (6-dimensional), then landmarks (3)
+      [](void* h) { Stepper* s = static_cast<Stepper*>(h); return s->nf + s->P.g->n_mp; },
+      [](void* h, int v) { return v < static_cast<Stepper*>(h)->nf ? 6 : 3; },
+      [](void* h, int v, int i, int j) {
+        Stepper* s = static_cast<Stepper*>(h);
+        return v < s->nf ? s->P.Hpp[36 * (size_t)v + i * 6 + j] : s->P.Hll[9 * (size_t)(v - s->nf) + i * 3 + j];
+      },
+      [](void* h, double lambda) { return static_cast<Stepper*>(h)->solve(lambda) ? 1 : 0; },
+      [](void* h) { return static_cast<Stepper*>(h)->P.x.data(); },
+      [](void* h) { return static_cast<Stepper*>(h)->P.b.data(); },
+      [](void* h) { return static_cast<Stepper*>(h)->nvec; },
+      [](void* h, const double* x) { static_cast<Stepper*>(h)->update(x); },
+      [](void* h) { static_cast<Stepper*>(h)->push(); },
+      [](void* h) { static_cast<Stepper*>(h)->pop(); },
+      [](void* h) { static_cast<Stepper*>(h)->discard_top(); },
+      [](void* h) { Stepper* s = static_cast<Stepper*>(h); return (s->stop && *s->stop) ? 1 : 0; },
+  };
+  return &ops;
+}
+
 }  // namespace
+
+extern "C" const orc_lm_ops* orc_lba_stepper_ops() { return lba_ops(); }
 
 extern "C" {
 
-// Full optimize(max_iters).  Outputs as lba_solve of include/orb_b200.h.
-int orc_lba_solve(const lba_graph_view* g, const volatile uint8_t* stop, int max_iters, double lambda_init,
-                  double* kf_pose_out, double* mp_pos_out, double* chi2_out, uint8_t* depth_pos_out,
-                  lba_stats* stats, double* trace /* per trial: lambda, tempChi, rho, accepted; cap 4*128 */) {
+// Full optimize(max_iters).  Outputs as lba_solve of include/orb_b200.h.  lm = the driver of the LM control law (NULL: the
+// restated one, orc_lm_restated; tests/test_ref_lm.py passes the reference's own object code, oracle/_ref/libref_lm.so).
+int orc_lba_solve_lm(const lba_graph_view* g, const volatile uint8_t* stop, int max_iters, double lambda_init,
+                     double* kf_pose_out, double* mp_pos_out, double* chi2_out, uint8_t* depth_pos_out,
+                     lba_stats* stats, double* trace /* per trial: lambda, tempChi, rho, accepted; cap 4*128 */, orc_lm_driver lm) {
   auto t_begin = std::chrono::steady_clock::now();
+  if (!lm) lm = orc_lm_restated;
   Stepper st(g);
+  st.stop = stop;
   Problem& P = st.P;
-  const int nf = st.nf;
-  double lambda = -1, ni = 2;
-  int nBad = 0, trials = 0, iters = 0, stopped = 0;
-  double chi_first = 0, currentChi = 0;
-  auto terminate = [&]() { return stop && *stop; };
-  for (int it = 0; it < max_iters && !terminate(); it++) {
-    P.compute_errors();
-    currentChi = P.robust_chi2();
-    double tempChi = currentChi;
-    const double iniChi = currentChi;
-    if (it == 0) chi_first = currentChi;
-    P.build_system();
-    if (it == 0) {
-      if (lambda_init > 0) lambda = lambda_init;
-      else lambda = 1e-5 * st.max_diagonal();  // computeLambdaInit: tau * max diagonal over all free vertices
-      ni = 2; nBad = 0;
-    }
-    double rho = 0;
-    int qmax = 0;
-    do {
-      st.push();
-      const bool ok2 = st.solve(lambda);
-      st.update(P.x.data());  // g2o updates even when the solve failed; x then holds stale values
-      P.compute_errors();
-      tempChi = P.robust_chi2();
-      if (!ok2) tempChi = std::numeric_limits<double>::max();
-      rho = currentChi - tempChi;
-      double scale = st.scale(lambda);
-      scale += 1e-3;
-      rho /= scale;
-      const bool accept = rho > 0 && std::isfinite(tempChi);
-      if (trace && trials < 128) {
-        trace[4 * trials] = lambda; trace[4 * trials + 1] = tempChi; trace[4 * trials + 2] = rho;
-        trace[4 * trials + 3] = accept ? 1 : 0;
-      }
-      if (accept) {
-        double alpha = 1. - std::pow((2 * rho - 1), 3);
-        alpha = std::min(alpha, 2. / 3.);
-        const double scaleFactor = std::max(1. / 3., alpha);
-        lambda *= scaleFactor;
-        ni = 2;
-        currentChi = tempChi;
-        st.discard_top();
-      } else {
-        lambda *= ni;
-        ni *= 2;
-        st.pop();
-      }
-      qmax++;
-      trials++;
-    } while (rho < 0 && qmax < 10 && !terminate());
-    iters++;
-    if (qmax == 10 || rho == 0) break;  // Terminate
-    if ((iniChi - currentChi) * 1e3 < iniChi) nBad++;
-    else nBad = 0;
-    if (nBad >= 3) break;
-  }
-  if (terminate()) stopped = 1;
+  orc_lm_report rep = {};
+  rep.trace = trace;
+  const int iters = lm(orc_lba_stepper_ops(), &st, max_iters, lambda_init, &rep);
+  const int stopped = (stop && *stop) ? 1 : 0;
   st.results(kf_pose_out, mp_pos_out);
   for (int e = 0; e < g->n_edges; e++) {
     if (chi2_out) chi2_out[e] = P.chi2(e);  // errors of the last evaluated trial
@@ -552,9 +530,9 @@ int orc_lba_solve(const lba_graph_view* g, const volatile uint8_t* stop, int max
   }
   if (stats) {
     memset(stats, 0, sizeof(*stats));
-    stats->iterations = iters; stats->trials = trials; stats->stopped = stopped;
-    stats->chi2_initial = chi_first; stats->chi2_final = currentChi; stats->lambda_final = lambda;
-    stats->n_free_kf = nf;
+    stats->iterations = iters; stats->trials = rep.trials; stats->stopped = stopped;
+    stats->chi2_initial = rep.chi_first; stats->chi2_final = rep.chi_final; stats->lambda_final = rep.lambda_final;
+    stats->n_free_kf = st.nf;
     stats->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
   }
   return iters;
@@ -573,29 +551,11 @@ void orc_se3_oplus(const double* pose7, const double* update6, double* out7) {
   out7[0] = o.r.x; out7[1] = o.r.y; out7[2] = o.r.z; out7[3] = o.r.w; out7[4] = o.t[0]; out7[5] = o.t[1]; out7[6] = o.t[2];
 }
 
-// ---- the Stepper's operations one by one (see struct Stepper): what the reference's LM driver object code calls
-void* orc_lba_stepper_open(const lba_graph_view* g) { return new Stepper(g); }
-void orc_lba_stepper_close(void* h) { delete static_cast<Stepper*>(h); }
-void orc_lba_stepper_compute_errors(void* h) { static_cast<Stepper*>(h)->P.compute_errors(); }
-double orc_lba_stepper_robust_chi2(void* h) { return static_cast<Stepper*>(h)->P.robust_chi2(); }
-void orc_lba_stepper_build_system(void* h) { static_cast<Stepper*>(h)->P.build_system(); }
-// free vertices in g2o's index order for this problem: poses first (6-dimensional), then landmarks (3)
-int orc_lba_stepper_n_vertices(void* h) { Stepper* s = static_cast<Stepper*>(h); return s->nf + s->P.g->n_mp; }
-int orc_lba_stepper_vertex_dim(void* h, int v) { return v < static_cast<Stepper*>(h)->nf ? 6 : 3; }
-double orc_lba_stepper_hessian(void* h, int v, int i, int j) {
-  Stepper* s = static_cast<Stepper*>(h);
-  if (v < s->nf) return s->P.Hpp[36 * (size_t)v + i * 6 + j];
-  return s->P.Hll[9 * (size_t)(v - s->nf) + i * 3 + j];
+int orc_lba_solve(const lba_graph_view* g, const volatile uint8_t* stop, int max_iters, double lambda_init,
+                  double* kf_pose_out, double* mp_pos_out, double* chi2_out, uint8_t* depth_pos_out,
+                  lba_stats* stats, double* trace) {
+  return orc_lba_solve_lm(g, stop, max_iters, lambda_init, kf_pose_out, mp_pos_out, chi2_out, depth_pos_out, stats, trace, nullptr);
 }
-int orc_lba_stepper_solve(void* h, double lambda) { return static_cast<Stepper*>(h)->solve(lambda) ? 1 : 0; }
-double* orc_lba_stepper_x(void* h) { return static_cast<Stepper*>(h)->P.x.data(); }
-double* orc_lba_stepper_b(void* h) { return static_cast<Stepper*>(h)->P.b.data(); }
-size_t orc_lba_stepper_vector_size(void* h) { return static_cast<Stepper*>(h)->nvec; }
-void orc_lba_stepper_update(void* h, const double* x) { static_cast<Stepper*>(h)->update(x); }
-void orc_lba_stepper_push(void* h) { static_cast<Stepper*>(h)->push(); }
-void orc_lba_stepper_pop(void* h) { static_cast<Stepper*>(h)->pop(); }
-void orc_lba_stepper_discard_top(void* h) { static_cast<Stepper*>(h)->discard_top(); }
-void orc_lba_stepper_results(void* h, double* kf_pose_out, double* mp_pos_out) { static_cast<Stepper*>(h)->results(kf_pose_out, mp_pos_out); }
 
 // One edge at the input estimates: err (3, third entry 0 for 2-D edges), A = d err / d point (d x 3), B = d err / d pose
 // (d x 6), isDepthPositive -- what tests/test_ref_edges.py holds against the reference's own computeError() /

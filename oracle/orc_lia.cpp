@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "orc_lia.h"
+#include "orc_lm_ops.h"
 
 namespace {
 
@@ -505,100 +506,115 @@ struct Problem {
   }
 };
 
+// What g2o's LM driver calls (orc_lm_ops.h) over a Problem: the block solver's Schur complement on the pose side
+// (block_solver.hpp:373-486), the dense LDL^T, the landmark back-substitution, oplus, push / pop.
+struct LiaStepper {
+  Problem P;
+  const int np;
+  const size_t nvec;
+  std::vector<double> x, ball, S, bs, Dinv;
+  struct State { std::vector<Pose> pose; std::vector<double> vel, bg, ba, pt; };
+  std::vector<State> stack;
+  explicit LiaStepper(const lia_graph_view* g)
+      : P(g), np(P.np), nvec((size_t)P.np + 3 * (size_t)g->n_mp), x(nvec, 0.0), ball(nvec, 0.0), bs(P.np), Dinv(9 * (size_t)g->n_mp) {}
+  void build_system() {
+    P.build_system();
+    memcpy(ball.data(), P.b.data(), sizeof(double) * np);
+    memcpy(ball.data() + np, P.bl.data(), sizeof(double) * 3 * (size_t)P.g->n_mp);
+  }
+  bool solve(double lambda) {
+    const lia_graph_view* g = P.g;
+    S = P.H;
+    for (int i = 0; i < np; i++) { S[(size_t)i * np + i] += lambda; bs[i] = P.b[i]; }
+    bool ok2 = true;
+    for (int l = 0; l < g->n_mp; l++) {
+      double Hl[9];
+      memcpy(Hl, &P.Hll[9 * (size_t)l], 72);
+      Hl[0] += lambda; Hl[4] += lambda; Hl[8] += lambda;
+      double* Di = &Dinv[9 * (size_t)l];
+      if (!inv3(Hl, Di)) { ok2 = false; break; }
+      const double* bll = &P.bl[3 * (size_t)l];
+      for (int ea : P.lm_edges[l]) {
+        const int oa = P.ip[g->e_kf[ea]];
+        if (oa < 0) continue;
+        const double* Wa = &P.W[18 * (size_t)ea];
+        double Y[18];
+        for (int i = 0; i < 6; i++) for (int j = 0; j < 3; j++) Y[i * 3 + j] = Wa[i * 3] * Di[j] + Wa[i * 3 + 1] * Di[3 + j] + Wa[i * 3 + 2] * Di[6 + j];
+        for (int i = 0; i < 6; i++) bs[oa + i] -= Y[i * 3] * bll[0] + Y[i * 3 + 1] * bll[1] + Y[i * 3 + 2] * bll[2];
+        for (int eb : P.lm_edges[l]) {
+          const int ob = P.ip[g->e_kf[eb]];
+          if (ob < 0) continue;
+          const double* Wb = &P.W[18 * (size_t)eb];
+          for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++)
+            S[(size_t)(oa + i) * np + ob + j] -= Y[i * 3] * Wb[j * 3] + Y[i * 3 + 1] * Wb[j * 3 + 1] + Y[i * 3 + 2] * Wb[j * 3 + 2];
+        }
+      }
+    }
+    if (ok2) ok2 = ldlt_solve(S, np, bs.data(), x.data());
+    if (ok2) {
+      for (int l = 0; l < g->n_mp; l++) {
+        double c[3] = {P.bl[3 * (size_t)l], P.bl[3 * (size_t)l + 1], P.bl[3 * (size_t)l + 2]};
+        for (int e : P.lm_edges[l]) {
+          const int o = P.ip[g->e_kf[e]];
+          if (o < 0) continue;
+          const double* We = &P.W[18 * (size_t)e];
+          for (int j = 0; j < 3; j++) for (int i = 0; i < 6; i++) c[j] -= We[i * 3 + j] * x[o + i];
+        }
+        const double* Di = &Dinv[9 * (size_t)l];
+        for (int i = 0; i < 3; i++) x[(size_t)np + 3 * (size_t)l + i] = Di[i * 3] * c[0] + Di[i * 3 + 1] * c[1] + Di[i * 3 + 2] * c[2];
+      }
+    }
+    return ok2;
+  }
+  void update(const double* xv) { P.update(std::vector<double>(xv, xv + nvec)); }
+  void push() { stack.push_back(State{P.pose, P.vel, P.bg, P.ba, P.pt}); }
+  void pop() { State& s = stack.back(); P.pose = s.pose; P.vel = s.vel; P.bg = s.bg; P.ba = s.ba; P.pt = s.pt; stack.pop_back(); }
+};
+
+const orc_lm_ops* lia_ops() {
+  static const orc_lm_ops ops = {
+      [](void* h) { static_cast<LiaStepper*>(h)->P.compute_errors(); },
+      [](void* h) { return static_cast<LiaStepper*>(h)->P.robust_chi2(); },
+      [](void* h) { static_cast<LiaStepper*>(h)->build_system(); },
+      // (computeLambdaInit only scans these when no user lambda is set; LocalInertialBA always sets one, :2517-2520)
+      [](void* h) { return 1 + static_cast<LiaStepper*>(h)->P.g->n_mp; },
+      [](void* h, int v) { return v == 0 ? static_cast<LiaStepper*>(h)->np : 3; },
+      [](void* h, int v, int i, int j) {
+        LiaStepper* s = static_cast<LiaStepper*>(h);
+        return v == 0 ? s->P.H[(size_t)i * s->np + j] : s->P.Hll[9 * (size_t)(v - 1) + i * 3 + j];
+      },
+      [](void* h, double lambda) { return static_cast<LiaStepper*>(h)->solve(lambda) ? 1 : 0; },
+      [](void* h) { return static_cast<LiaStepper*>(h)->x.data(); },
+      [](void* h) { return static_cast<LiaStepper*>(h)->ball.data(); },
+      [](void* h) { return static_cast<LiaStepper*>(h)->nvec; },
+      [](void* h, const double* x) { static_cast<LiaStepper*>(h)->update(x); },
+      [](void* h) { static_cast<LiaStepper*>(h)->push(); },
+      [](void* h) { static_cast<LiaStepper*>(h)->pop(); },
+      [](void* h) { static_cast<LiaStepper*>(h)->stack.pop_back(); },
+      nullptr,
+  };
+  return &ops;
+}
+
 }  // namespace
 
 extern "C" {
 
 // optimizer.optimize(opt_it).  Outputs: kf_out n_kf x 21 (Rcw 9, tcw 3, vel 3, bg 3, ba 3), mp_out n_mp x 3,
 // chi2_out / depth_pos_out per visual edge (e->chi2(), isDepthPositive()), stats[6] = iterations, trials,
-// err (activeRobustChi2 before), err_end (after), lambda_final, pose-side dimension.
-int orc_lia_solve(const lia_graph_view* g, double* kf_out, double* mp_out, double* chi2_out, uint8_t* depth_pos_out,
-                  double* stats) {
-  Problem P(g);
-  const int np = P.np;
-  const size_t nvec = (size_t)np + 3 * (size_t)g->n_mp;
-  std::vector<double> x(nvec, 0.0), S, bs(np), Dinv(9 * (size_t)g->n_mp);
-  double lambda = g->lambda_init, ni = 2, chi_first = 0, currentChi = 0;
-  int nBad = 0, trials = 0, iters = 0;
-  for (int it = 0; it < g->iterations; it++) {
-    P.compute_errors();
-    currentChi = P.robust_chi2();
-    double tempChi = currentChi;
-    const double iniChi = currentChi;
-    if (it == 0) { chi_first = currentChi; lambda = g->lambda_init; ni = 2; nBad = 0; }  // computeLambdaInit: user value
-    P.build_system();
-    double rho = 0;
-    int qmax = 0;
-    do {
-      const std::vector<Pose> pose_bak = P.pose;
-      const std::vector<double> vel_bak = P.vel, bg_bak = P.bg, ba_bak = P.ba, pt_bak = P.pt;
-      // Schur complement on the pose side (block_solver.hpp:373-486); lambda on every diagonal
-      S = P.H;
-      for (int i = 0; i < np; i++) { S[(size_t)i * np + i] += lambda; bs[i] = P.b[i]; }
-      bool ok2 = true;
-      for (int l = 0; l < g->n_mp; l++) {
-        double Hl[9];
-        memcpy(Hl, &P.Hll[9 * (size_t)l], 72);
-        Hl[0] += lambda; Hl[4] += lambda; Hl[8] += lambda;
-        double* Di = &Dinv[9 * (size_t)l];
-        if (!inv3(Hl, Di)) { ok2 = false; break; }
-        const double* bll = &P.bl[3 * (size_t)l];
-        for (int ea : P.lm_edges[l]) {
-          const int oa = P.ip[g->e_kf[ea]];
-          if (oa < 0) continue;
-          const double* Wa = &P.W[18 * (size_t)ea];
-          double Y[18];
-          for (int i = 0; i < 6; i++) for (int j = 0; j < 3; j++) Y[i * 3 + j] = Wa[i * 3] * Di[j] + Wa[i * 3 + 1] * Di[3 + j] + Wa[i * 3 + 2] * Di[6 + j];
-          for (int i = 0; i < 6; i++) bs[oa + i] -= Y[i * 3] * bll[0] + Y[i * 3 + 1] * bll[1] + Y[i * 3 + 2] * bll[2];
-          for (int eb : P.lm_edges[l]) {
-            const int ob = P.ip[g->e_kf[eb]];
-            if (ob < 0) continue;
-            const double* Wb = &P.W[18 * (size_t)eb];
-            for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++)
-              S[(size_t)(oa + i) * np + ob + j] -= Y[i * 3] * Wb[j * 3] + Y[i * 3 + 1] * Wb[j * 3 + 1] + Y[i * 3 + 2] * Wb[j * 3 + 2];
-          }
-        }
-      }
-      if (ok2) ok2 = ldlt_solve(S, np, bs.data(), x.data());
-      if (ok2) {
-        for (int l = 0; l < g->n_mp; l++) {
-          double c[3] = {P.bl[3 * (size_t)l], P.bl[3 * (size_t)l + 1], P.bl[3 * (size_t)l + 2]};
-          for (int e : P.lm_edges[l]) {
-            const int o = P.ip[g->e_kf[e]];
-            if (o < 0) continue;
-            const double* We = &P.W[18 * (size_t)e];
-            for (int j = 0; j < 3; j++) for (int i = 0; i < 6; i++) c[j] -= We[i * 3 + j] * x[o + i];
-          }
-          const double* Di = &Dinv[9 * (size_t)l];
-          for (int i = 0; i < 3; i++) x[(size_t)np + 3 * (size_t)l + i] = Di[i * 3] * c[0] + Di[i * 3 + 1] * c[1] + Di[i * 3 + 2] * c[2];
-        }
-      }
-      P.update(x);
-      P.compute_errors();
-      tempChi = P.robust_chi2();
-      if (!ok2) tempChi = std::numeric_limits<double>::max();
-      rho = currentChi - tempChi;
-      double scale = 1e-3;
-      for (int j = 0; j < np; j++) scale += x[j] * (lambda * x[j] + P.b[j]);
-      for (size_t j = 0; j < 3 * (size_t)g->n_mp; j++) scale += x[(size_t)np + j] * (lambda * x[(size_t)np + j] + P.bl[j]);
-      rho /= scale;
-      if (rho > 0 && std::isfinite(tempChi)) {
-        double alpha = 1. - pow((2 * rho - 1), 3);
-        alpha = std::min(alpha, 2. / 3.);
-        lambda *= std::max(1. / 3., alpha);
-        ni = 2;
-        currentChi = tempChi;
-      } else {
-        lambda *= ni; ni *= 2;
-        P.pose = pose_bak; P.vel = vel_bak; P.bg = bg_bak; P.ba = ba_bak; P.pt = pt_bak;
-      }
-      qmax++; trials++;
-    } while (rho < 0 && qmax < 10);
-    iters++;
-    if (qmax == 10 || rho == 0) break;
-    if ((iniChi - currentChi) * 1e3 < iniChi) nBad++; else nBad = 0;
-    if (nBad >= 3) break;
-  }
+// err (activeRobustChi2 before), err_end (after), lambda_final, pose-side dimension.  lm = the driver of the LM control
+// law (NULL: orc_lm_restated; tests/test_ref_lm.py passes the reference's own object code); trace optional (128 x 4).
+int orc_lia_solve_lm(const lia_graph_view* g, double* kf_out, double* mp_out, double* chi2_out, uint8_t* depth_pos_out,
+                     double* stats, orc_lm_driver lm, double* trace) {
+  if (!lm) lm = orc_lm_restated;
+  LiaStepper st(g);
+  Problem& P = st.P;
+  const int np = st.np;
+  orc_lm_report rep = {};
+  rep.trace = trace;
+  const int iters = lm(lia_ops(), &st, g->iterations, g->lambda_init, &rep);  // setUserLambdaInit(lambda_init)
+  const int trials = rep.trials;
+  const double chi_first = rep.chi_first, currentChi = rep.chi_final, lambda = rep.lambda_final;
   for (int k = 0; k < g->n_kf; k++) {
     double* o = kf_out + 21 * (size_t)k;
     memcpy(o, P.pose[k].Rcw, 72); memcpy(o + 9, P.pose[k].tcw, 24);
@@ -635,6 +651,11 @@ int orc_lia_linearize(const lia_graph_view* g, const double* delta, double* chi2
     *chi2_delta_out = P.robust_chi2();
   }
   return P.np;
+}
+
+int orc_lia_solve(const lia_graph_view* g, double* kf_out, double* mp_out, double* chi2_out, uint8_t* depth_pos_out,
+                  double* stats) {
+  return orc_lia_solve_lm(g, kf_out, mp_out, chi2_out, depth_pos_out, stats, nullptr, nullptr);
 }
 
 }  // extern "C"

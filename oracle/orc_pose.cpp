@@ -25,6 +25,7 @@
 
 #include "../include/orb_b200.h"
 #include "orc_se3.h"
+#include "orc_lm_ops.h"
 
 namespace {
 
@@ -162,9 +163,111 @@ struct PoseProblem {
       }
     }
   }
+  // ---- what g2o's LM driver calls (orc_lm_ops.h)
+  double x[6] = {0, 0, 0, 0, 0, 0};  // the solver's _x survives a failed solve
+  std::vector<SE3> stack;
+  bool solve(double lambda) {        // BlockSolverX + LinearSolverDense: (H + lambda I) x = b by Eigen::LDLT
+    double Hl[36];
+    memcpy(Hl, H, sizeof(Hl));
+    for (int j = 0; j < 6; j++) Hl[j * 7] += lambda;
+    return ldlt6_solve(Hl, b, x);    // a failed solve leaves x as it was
+  }
 };
 
+const orc_lm_ops* pose_ops() {
+  static const orc_lm_ops ops = {
+      [](void* h) { static_cast<PoseProblem*>(h)->compute_active_errors(); },
+      [](void* h) { return static_cast<PoseProblem*>(h)->active_robust_chi2(); },
+      [](void* h) { static_cast<PoseProblem*>(h)->build_system(); },
+      [](void*) { return 1; },
+      [](void*, int) { return 6; },
+      [](void* h, int, int i, int j) { return static_cast<PoseProblem*>(h)->H[i * 6 + j]; },
+      [](void* h, double lambda) { return static_cast<PoseProblem*>(h)->solve(lambda) ? 1 : 0; },
+      [](void* h) { return static_cast<PoseProblem*>(h)->x; },
+      [](void* h) { return static_cast<PoseProblem*>(h)->b; },
+      [](void*) { return (size_t)6; },
+      [](void* h, const double* x) { PoseProblem* P = static_cast<PoseProblem*>(h); P->T = se3_exp_mul(x, P->T); },
+      [](void* h) { PoseProblem* P = static_cast<PoseProblem*>(h); P->stack.push_back(P->T); },
+      [](void* h) { PoseProblem* P = static_cast<PoseProblem*>(h); P->T = P->stack.back(); P->stack.pop_back(); },
+      [](void* h) { static_cast<PoseProblem*>(h)->stack.pop_back(); },
+      nullptr,
+  };
+  return &ops;
+}
+
 }  // namespace
+
+// The restated control law of optimization_algorithm_levenberg.cpp:61-169 (+ sparse_optimizer.cpp:354-419's loop around it)
+// over an orc_lm_ops table: the driver every oracle optimiser uses unless it is handed another one.
+extern "C" int orc_lm_restated(const orc_lm_ops* ops, void* h, int max_iters, double lambda_init, orc_lm_report* rep) {
+  double lambda = -1, ni = 2, currentChi = 0, chi_first = 0;
+  int nBad = 0, iters = 0;
+  const size_t nvec = ops->vector_size(h);
+  auto terminate = [&]() { return ops->terminate && ops->terminate(h); };
+  for (int it = 0; it < max_iters && !terminate(); it++) {
+    ops->compute_errors(h);
+    currentChi = ops->robust_chi2(h);
+    double tempChi = currentChi;
+    const double iniChi = currentChi;
+    if (it == 0) chi_first = currentChi;
+    ops->build_system(h);
+    if (it == 0) {
+      if (lambda_init > 0) lambda = lambda_init;
+      else {  // computeLambdaInit: tau * max |H_jj| over all vertices
+        double mx = 0;
+        for (int v = 0, nv = ops->n_vertices(h); v < nv; v++)
+          for (int j = 0, d = ops->vertex_dim(h, v); j < d; j++) mx = std::max(std::fabs(ops->hessian(h, v, j, j)), mx);
+        lambda = 1e-5 * mx;
+      }
+      ni = 2; nBad = 0;
+    }
+    double rho = 0;
+    int qmax = 0;
+    do {
+      ops->push(h);
+      const bool ok2 = ops->solve(h, lambda) != 0;
+      ops->update(h, ops->x(h));  // g2o updates even when the solve failed; x then holds stale values
+      ops->compute_errors(h);
+      tempChi = ops->robust_chi2(h);
+      if (!ok2) tempChi = std::numeric_limits<double>::max();
+      rho = currentChi - tempChi;
+      double scale = 0;  // computeScale
+      const double *x = ops->x(h), *b = ops->b(h);
+      for (size_t j = 0; j < nvec; j++) scale += x[j] * (lambda * x[j] + b[j]);
+      scale += 1e-3;
+      rho /= scale;
+      const bool accept = rho > 0 && std::isfinite(tempChi);
+      if (rep) {
+        if (rep->trace && rep->trace_rows < 128) {
+          double* r = rep->trace + 4 * (size_t)rep->trace_rows;
+          r[0] = lambda; r[1] = tempChi; r[2] = rho; r[3] = accept ? 1 : 0;
+        }
+        rep->trace_rows++;
+        rep->trials++;
+      }
+      if (accept) {
+        double alpha = 1. - std::pow((2 * rho - 1), 3);
+        alpha = std::min(alpha, 2. / 3.);
+        lambda *= std::max(1. / 3., alpha);
+        ni = 2;
+        currentChi = tempChi;
+        ops->discard_top(h);
+      } else {
+        lambda *= ni;
+        ni *= 2;
+        ops->pop(h);
+      }
+      qmax++;
+    } while (rho < 0 && qmax < 10 && !terminate());
+    iters++;
+    if (qmax == 10 || rho == 0) break;  // Terminate
+    if ((iniChi - currentChi) * 1e3 < iniChi) nBad++;
+    else nBad = 0;
+    if (nBad >= 3) break;
+  }
+  if (rep) { rep->iterations = iters; rep->lambda_final = lambda; rep->chi_first = chi_first; rep->chi_final = currentChi; }
+  return iters;
+}
 
 extern "C" {
 
@@ -186,8 +289,12 @@ int orc_pose_edge(const pose_opt_view* v, int e, double* err3, double* B18) {
 // Returns nInitialCorrespondences - nBad (Optimizer.cc:1114).  pose_out: quaternion xyzw + translation
 // (SE3quat_recov before the cast to float); outlier_out[n] = mvbOutlier of the edges; chi2_out[n] (optional)
 // = the chi2 each edge was last classified with; stats_out (optional) = {rounds run, LM iterations, LM trials}.
-int orc_pose_optimize(const pose_opt_view* v, double* pose_out, uint8_t* outlier_out, double* chi2_out,
-                      int* stats_out) {
+// lm = the driver that runs optimizer.optimize(10) on the frame's graph (NULL: orc_lm_restated); trace (optional): the
+// trials of all rounds, 4 doubles each (lambda, chi2, -, accepted), cap 128 rows.
+int orc_pose_optimize_lm(const pose_opt_view* v, double* pose_out, uint8_t* outlier_out, double* chi2_out,
+                         int* stats_out, orc_lm_driver lm, double* trace) {
+  if (!lm) lm = orc_lm_restated;
+  int trace_rows = 0;
   const int n = v->n;
   if (stats_out) stats_out[0] = stats_out[1] = stats_out[2] = 0;
   SE3 T0;
@@ -206,56 +313,12 @@ int orc_pose_optimize(const pose_opt_view* v, double* pose_out, uint8_t* outlier
   for (int round = 0; round < 4; round++) {
     P.T = T0;  // every round restarts from the frame pose (:1012-1013)
     // ---- optimizer.optimize(10)
-    double lambda = -1, ni = 2;
-    int nBadLM = 0;
-    double x[6] = {0, 0, 0, 0, 0, 0};  // the solver's _x survives a failed solve
-    for (int it = 0; it < 10; it++) {
-      P.compute_active_errors();
-      double currentChi = P.active_robust_chi2();
-      double tempChi = currentChi;
-      const double iniChi = currentChi;
-      P.build_system();
-      if (it == 0) {
-        double mx = 0;
-        for (int j = 0; j < 6; j++) mx = std::max(std::fabs(P.H[j * 7]), mx);
-        lambda = 1e-5 * mx;
-        ni = 2; nBadLM = 0;
-      }
-      double rho = 0;
-      int qmax = 0;
-      do {
-        const SE3 backup = P.T;  // push
-        double Hl[36];
-        memcpy(Hl, P.H, sizeof(Hl));
-        for (int j = 0; j < 6; j++) Hl[j * 7] += lambda;
-        const bool ok2 = ldlt6_solve(Hl, P.b, x);  // a failed solve leaves x as it was
-        P.T = se3_exp_mul(x, P.T);
-        P.compute_active_errors();
-        tempChi = P.active_robust_chi2();
-        if (!ok2) tempChi = std::numeric_limits<double>::max();
-        rho = currentChi - tempChi;
-        double scale = 1e-3;
-        for (int j = 0; j < 6; j++) scale += x[j] * (lambda * x[j] + P.b[j]);
-        rho /= scale;
-        if (rho > 0 && std::isfinite(tempChi)) {
-          double alpha = 1. - std::pow((2 * rho - 1), 3);
-          alpha = std::min(alpha, 2. / 3.);
-          lambda *= std::max(1. / 3., alpha);
-          ni = 2;
-          currentChi = tempChi;
-        } else {
-          lambda *= ni;
-          ni *= 2;
-          P.T = backup;  // pop
-        }
-        qmax++;
-        if (stats_out) stats_out[2]++;
-      } while (rho < 0 && qmax < 10);
-      if (stats_out) stats_out[1]++;
-      if (qmax == 10 || rho == 0) break;
-      if ((iniChi - currentChi) * 1e3 < iniChi) nBadLM++;
-      else nBadLM = 0;
-      if (nBadLM >= 3) break;
+    {
+      orc_lm_report rep = {};
+      rep.trace = trace; rep.trace_rows = trace_rows;
+      const int iters = lm(pose_ops(), &P, 10, 0.0, &rep);
+      trace_rows = rep.trace_rows;
+      if (stats_out) { stats_out[1] += iters; stats_out[2] += rep.trials; }
     }
     // ---- classification (:1018-1096)
     nBad = 0;
@@ -272,6 +335,11 @@ int orc_pose_optimize(const pose_opt_view* v, double* pose_out, uint8_t* outlier
   }
   write_pose(P.T);
   return n - nBad;
+}
+
+int orc_pose_optimize(const pose_opt_view* v, double* pose_out, uint8_t* outlier_out, double* chi2_out,
+                      int* stats_out) {
+  return orc_pose_optimize_lm(v, pose_out, outlier_out, chi2_out, stats_out, nullptr, nullptr);
 }
 
 }  // extern "C"

@@ -457,25 +457,14 @@ def lm_lib():
     if _lm is None:
         if not os.path.exists(LM_LIB_PATH) and build_lm() is None:
             raise FileNotFoundError("oracle/_ref/libref_lm.so is not built and %s is absent" % REFERENCE)
-        _o.lib()
-        L = C.CDLL(LM_LIB_PATH)
-        vp = C.c_void_p
-        L.ref_lm_optimize.argtypes = [vp, vp, C.c_int, C.c_double, vp, vp, vp, vp]
-        _lm = L
+        _lm = C.CDLL(LM_LIB_PATH)
     return _lm
 
 
-def lm_optimize(g, max_iters=10, lambda_init=0.0):
-    """optimizer.optimize(max_iters) driven by the reference's OptimizationAlgorithmLevenberg object code over the
-    oracle's linearise / Schur / LDL^T / update operations.  Returns dict like oracle.lba_solve (trace rows: lambda,
-    tempChi, NaN, accepted)."""
-    kf = np.zeros((g.n_kf, 7))
-    mp = np.zeros((g.n_mp, 3))
-    out4 = np.zeros(4)
-    trace = np.zeros((128, 4))
-    it = lm_lib().ref_lm_optimize(C.byref(g), None, int(max_iters), float(lambda_init), _p(kf), _p(mp), _p(out4), _p(trace))
-    return dict(iterations=it, trials=int(out4[1]), chi2_final=out4[2], lambda_final=out4[3], kf_pose=kf, mp_pos=mp,
-                trace=trace[:int(out4[1])].copy())
+def lm_driver():
+    """Address of ref_lm_driver (an orc_lm_driver, oracle/orc_lm_ops.h): optimizer.optimize() run by the reference's
+    OptimizationAlgorithmLevenberg object code.  Pass it as `driver=` to oracle.lba_solve / pose_optimize / lia_solve."""
+    return C.cast(lm_lib().ref_lm_driver, C.c_void_p).value
 
 
 def g2o_huber(delta, e):

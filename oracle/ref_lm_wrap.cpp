@@ -2,131 +2,109 @@
 // /root/reference/Thirdparty/g2o/g2o/core/optimization_algorithm_levenberg.h and .cpp piped UNMODIFIED into the compiler
 // (oracle/Makefile) over the interface stand-ins of oracle/eigencompat/g2o_unit/core/.  This file is appended to the same
 // header in a second pipe.  It implements those interfaces -- g2o::Solver, g2o::SparseOptimizer, the vertices
-// computeLambdaInit scans -- by forwarding every call to the oracle's Stepper operations (orc_lba.cpp:
-// orc_lba_stepper_*), and runs SparseOptimizer::optimize's outer loop (sparse_optimizer.cpp:354-419, restated below: it is
-// the `for` around _algorithm->solve) on top.  So the control law -- lambda initialisation, the trial loop, rho, the
+// computeLambdaInit scans -- by forwarding every call to an orc_lm_ops table (orc_lm_ops.h: the operations of one of the
+// oracle's optimisers), and runs SparseOptimizer::optimize's outer loop (sparse_optimizer.cpp:354-419, restated below: it
+// is the `for` around _algorithm->solve) on top.  So the control law -- lambda initialisation, the trial loop, rho, the
 // accept / reject updates of lambda and ni, maxTrialsAfterFailure, the nBad stop added by ORB-SLAM3 -- is the reference's
-// own object code, and the linear algebra underneath is the oracle's.  tests/test_ref_lm.py holds orc_lba_solve (the
-// restated control law over the same operations) equal to it: iterations, trials, every lambda, every chi2, the result.
-// Nothing in the product links this.
+// own object code, and the linear algebra underneath is the oracle's.  ref_lm_driver has the orc_lm_driver signature: the
+// oracle's optimisers take it in place of their restated control law (orc_lm_restated), and tests/test_ref_lm.py holds
+// the two equal -- iterations, trials, every lambda, every chi2, the result.  Nothing in the product links this.
+#include <cmath>
 #include <cstring>
 
-#include "../../../../include/orb_b200.h"
-
-extern "C" {
-void* orc_lba_stepper_open(const lba_graph_view* g);
-void orc_lba_stepper_close(void* h);
-void orc_lba_stepper_compute_errors(void* h);
-double orc_lba_stepper_robust_chi2(void* h);
-void orc_lba_stepper_build_system(void* h);
-int orc_lba_stepper_n_vertices(void* h);
-int orc_lba_stepper_vertex_dim(void* h, int v);
-double orc_lba_stepper_hessian(void* h, int v, int i, int j);
-int orc_lba_stepper_solve(void* h, double lambda);
-double* orc_lba_stepper_x(void* h);
-double* orc_lba_stepper_b(void* h);
-size_t orc_lba_stepper_vector_size(void* h);
-void orc_lba_stepper_update(void* h, const double* x);
-void orc_lba_stepper_push(void* h);
-void orc_lba_stepper_pop(void* h);
-void orc_lba_stepper_discard_top(void* h);
-void orc_lba_stepper_results(void* h, double* kf_pose_out, double* mp_pos_out);
-}
+#include "../../../orc_lm_ops.h"
 
 namespace {
 
-struct Trace {  // one row per trial, like orc_lba_solve's: lambda, tempChi, (rho is private to the driver: NaN), accepted
-  double* rows;
-  int n;
-  double lambda;
-  void trial_lambda(double l) { lambda = l; }
-  void trial_chi(double chi) { if (rows && n < 128) { rows[4 * n] = lambda; rows[4 * n + 1] = chi; rows[4 * n + 2] = NAN; rows[4 * n + 3] = -1; } }
-  void trial_end(bool accepted) { if (rows && n < 128) rows[4 * n + 3] = accepted ? 1 : 0; n++; }
-};
-
-class StepperVertex : public g2o::OptimizableGraph::Vertex {
- public:
-  StepperVertex(void* h, int v) : _h(h), _v(v) {}
-  int dimension() const override { return orc_lba_stepper_vertex_dim(_h, _v); }
-  const double& hessian(int i, int j) const override { _tmp = orc_lba_stepper_hessian(_h, _v, i, j); return _tmp; }
- private:
-  void* _h; int _v; mutable double _tmp = 0;
-};
-
-class StepperOptimizer : public g2o::SparseOptimizer {
- public:
-  StepperOptimizer(void* h, Trace* t, const volatile uint8_t* stop) : _h(h), _t(t), _stop(stop), _pending(false) {
-    const int n = orc_lba_stepper_n_vertices(h);
-    for (int v = 0; v < n; v++) _iv.push_back(new StepperVertex(h, v));
+struct Run {  // what the adapters observe of the driver's private state
+  const orc_lm_ops* ops; void* h; orc_lm_report* rep;
+  double lambda = 0, candidate = 0;
+  bool pending = false, first = true;
+  void trial_chi(double chi) {
+    candidate = chi;
+    if (rep->trace && rep->trace_rows < 128) { double* r = rep->trace + 4 * (size_t)rep->trace_rows; r[0] = lambda; r[1] = chi; r[2] = NAN; r[3] = -1; }
   }
-  ~StepperOptimizer() override { for (auto* v : _iv) delete v; }
-  void computeActiveErrors() override { orc_lba_stepper_compute_errors(_h); }
+  void trial_end(bool accepted) {
+    if (rep->trace && rep->trace_rows < 128) rep->trace[4 * (size_t)rep->trace_rows + 3] = accepted ? 1 : 0;
+    if (accepted) rep->chi_final = candidate;
+    rep->trace_rows++; rep->trials++;
+  }
+};
+
+class OpsVertex : public g2o::OptimizableGraph::Vertex {
+ public:
+  OpsVertex(Run* r, int v) : _r(r), _v(v) {}
+  int dimension() const override { return _r->ops->vertex_dim(_r->h, _v); }
+  const double& hessian(int i, int j) const override { _tmp = _r->ops->hessian(_r->h, _v, i, j); return _tmp; }
+ private:
+  Run* _r; int _v; mutable double _tmp = 0;
+};
+
+class OpsOptimizer : public g2o::SparseOptimizer {
+ public:
+  explicit OpsOptimizer(Run* r) : _r(r) {
+    const int n = r->ops->n_vertices(r->h);
+    for (int v = 0; v < n; v++) _iv.push_back(new OpsVertex(r, v));
+  }
+  ~OpsOptimizer() override { for (auto* v : _iv) delete v; }
+  void computeActiveErrors() override { _r->ops->compute_errors(_r->h); }
   double activeRobustChi2() const override {
-    const double chi = orc_lba_stepper_robust_chi2(_h);
-    if (_pending) { _t->trial_chi(chi); _pending = false; }
+    const double chi = _r->ops->robust_chi2(_r->h);
+    if (_r->pending) { _r->trial_chi(chi); _r->pending = false; }
+    else { if (_r->first) { _r->rep->chi_first = chi; _r->first = false; } _r->rep->chi_final = chi; }  // currentChi of an iteration
     return chi;
   }
-  void push() override { orc_lba_stepper_push(_h); }
-  void pop() override { orc_lba_stepper_pop(_h); _t->trial_end(false); }
-  void discardTop() override { orc_lba_stepper_discard_top(_h); _t->trial_end(true); }
-  void update(const double* x) override { orc_lba_stepper_update(_h, x); _pending = true; }
+  void push() override { _r->ops->push(_r->h); }
+  void pop() override { _r->ops->pop(_r->h); _r->trial_end(false); }
+  void discardTop() override { _r->ops->discard_top(_r->h); _r->trial_end(true); }
+  void update(const double* x) override { _r->ops->update(_r->h, x); _r->pending = true; }
   const g2o::OptimizableGraph::VertexContainer& indexMapping() const override { return _iv; }
-  bool terminate() override { return _stop && *_stop; }
+  bool terminate() override { return _r->ops->terminate && _r->ops->terminate(_r->h); }
  private:
-  void* _h; Trace* _t; const volatile uint8_t* _stop; mutable bool _pending;
+  Run* _r;
   g2o::OptimizableGraph::VertexContainer _iv;
 };
 
-class StepperSolver : public g2o::Solver {  // BlockSolver<6,3> + LinearSolverEigen as the oracle restates them
+class OpsSolver : public g2o::Solver {  // the block solver + linear solver of the optimiser, as its oracle restates them
  public:
-  StepperSolver(void* h, g2o::SparseOptimizer* opt, Trace* t) : _h(h), _t(t), _lambda(0) {
+  OpsSolver(Run* r, g2o::SparseOptimizer* opt) : _r(r) {
     _optimizer = opt;
-    _x = orc_lba_stepper_x(h); _b = orc_lba_stepper_b(h); _xSize = orc_lba_stepper_vector_size(h);
+    _x = r->ops->x(r->h); _b = r->ops->b(r->h); _xSize = r->ops->vector_size(r->h);
   }
   bool buildStructure(bool) override { return true; }
-  bool buildSystem() override { orc_lba_stepper_build_system(_h); return true; }
-  bool setLambda(double lambda, bool) override { _lambda = lambda; _t->trial_lambda(lambda); return true; }
-  bool solve() override { return orc_lba_stepper_solve(_h, _lambda) != 0; }
-  void restoreDiagonal() override {}   // the Stepper adds lambda to copies of the diagonal blocks
+  bool buildSystem() override { _r->ops->build_system(_r->h); return true; }
+  bool setLambda(double lambda, bool) override { _r->lambda = lambda; return true; }
+  bool solve() override { return _r->ops->solve(_r->h, _r->lambda) != 0; }
+  void restoreDiagonal() override {}   // the oracle adds lambda to copies of the diagonal blocks
   bool schur() override { return true; }
  private:
-  void* _h; Trace* _t; double _lambda;
+  Run* _r;
 };
 
 }  // namespace
 
-extern "C" {
-
-// optimizer.optimize(max_iters) with OptimizationAlgorithmLevenberg (+ setUserLambdaInit(lambda_init) when > 0), the way
-// Optimizer::LocalBundleAdjustment sets it up (Optimizer.cc:1142-1153, :1410-1411).  out4 = iterations, trials,
-// final robust chi2, final lambda; trace = 128 rows of (lambda, tempChi, NaN, accepted).  Returns iterations.
-int ref_lm_optimize(const lba_graph_view* g, const volatile uint8_t* stop, int max_iters, double lambda_init, double* kf_pose_out,
-                    double* mp_pos_out, double* out4, double* trace) {
-  void* h = orc_lba_stepper_open(g);
-  Trace t{trace, 0, 0.0};
-  int done;
-  {
-    StepperOptimizer optimizer(h, &t, stop);
-    StepperSolver solver(h, &optimizer, &t);
-    g2o::OptimizationAlgorithmLevenberg algorithm(&solver);
-    algorithm.setOptimizer(&optimizer);
-    if (lambda_init > 0) algorithm.setUserLambdaInit(lambda_init);
-    // SparseOptimizer::optimize (sparse_optimizer.cpp:354-419)
-    int cjIterations = 0;
-    bool ok = true;
-    g2o::OptimizationAlgorithm::SolverResult result = g2o::OptimizationAlgorithm::OK;
-    for (int i = 0; i < max_iters && !optimizer.terminate() && ok; i++) {
-      result = algorithm.solve(i, false);
-      ok = (result == g2o::OptimizationAlgorithm::OK);
-      ++cjIterations;
-    }
-    done = (result == g2o::OptimizationAlgorithm::Fail) ? 0 : cjIterations;
-    orc_lba_stepper_compute_errors(h);
-    out4[0] = done; out4[1] = t.n; out4[2] = orc_lba_stepper_robust_chi2(h); out4[3] = algorithm.currentLambda();
+// optimizer.optimize(max_iters) with OptimizationAlgorithmLevenberg (+ setUserLambdaInit(lambda_init) when > 0), the way the
+// Optimizer functions set it up (Optimizer.cc:1142-1153, :1410-1411; :838-846; :2503-2520).  An orc_lm_driver.
+extern "C" int ref_lm_driver(const orc_lm_ops* ops, void* h, int max_iters, double lambda_init, orc_lm_report* rep) {
+  orc_lm_report local = {};
+  if (!rep) rep = &local;
+  Run run{ops, h, rep};
+  OpsOptimizer optimizer(&run);
+  OpsSolver solver(&run, &optimizer);
+  g2o::OptimizationAlgorithmLevenberg algorithm(&solver);
+  algorithm.setOptimizer(&optimizer);
+  if (lambda_init > 0) algorithm.setUserLambdaInit(lambda_init);
+  // SparseOptimizer::optimize (sparse_optimizer.cpp:354-419)
+  int cjIterations = 0;
+  bool ok = true;
+  g2o::OptimizationAlgorithm::SolverResult result = g2o::OptimizationAlgorithm::OK;
+  for (int i = 0; i < max_iters && !optimizer.terminate() && ok; i++) {
+    result = algorithm.solve(i, false);
+    ok = (result == g2o::OptimizationAlgorithm::OK);
+    ++cjIterations;
   }
-  orc_lba_stepper_results(h, kf_pose_out, mp_pos_out);
-  orc_lba_stepper_close(h);
+  const int done = (result == g2o::OptimizationAlgorithm::Fail) ? 0 : cjIterations;
+  rep->iterations = done;
+  rep->lambda_final = algorithm.currentLambda();
   return done;
 }
-
-}  // extern "C"

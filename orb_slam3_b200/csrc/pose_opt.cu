@@ -295,8 +295,9 @@ __global__ void __launch_bounds__(PO_THREADS) pose_opt_kernel(const PoseDev D) {
           double tempChi = chi[0];
           if (!s_ok) tempChi = DBL_MAX;
           double rho = s_cur - tempChi;
-          double scale = 1e-3;
+          double scale = 0;  // computeScale (:181-188), then `scale += 1e-3` (:124-125): in that order
           for (int j = 0; j < 6; j++) scale += s_x[j] * (s_lambda * s_x[j] + s_b[j]);
+          scale += 1e-3;
           rho /= scale;
           if (rho > 0 && isfinite(tempChi)) {
             double alpha = 1. - pow((2 * rho - 1), 3.0);
