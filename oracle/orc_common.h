@@ -22,8 +22,9 @@
 //   * Frame::ComputeBoW's transform: the vendored DBoW2 as object code (libref_bow.so) -- tests/test_ref_bow.py (exact);
 //   * g2o's stereo edges (EdgeStereoSE3ProjectXYZ, ...OnlyPose), SE3Quat (exp / oplus) and RobustKernelHuber: the vendored
 //     types_six_dof_expmap.{h,cpp}, se3quat.h, robust_kernel*.cpp as object code (libref_g2o.so) -- tests/test_ref_edges.py;
-//   * the LM control law: optimization_algorithm_levenberg.cpp as object code (libref_lm.so) driving this oracle's own
-//     Stepper operations -- tests/test_ref_lm.py (bit for bit);
+//   * the LM control law of all three optimisers (LocalBundleAdjustment, PoseOptimization, LocalInertialBA):
+//     optimization_algorithm_levenberg.cpp as object code (libref_lm.so) driving this oracle's own operations through
+//     orc_lm_ops.h -- tests/test_ref_lm.py (bit for bit);
 //   * g2o's Hessian accumulation / block solver and the inertial edges of G2oTypes.cc: "parity unpinned" by the reference
 //     (those translation units need the real Eigen); pinned by independent numpy restatements, finite differences and
 //     dense solves, with the reference lines cited per function.
