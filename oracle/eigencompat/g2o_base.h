@@ -90,8 +90,12 @@ template <int D, class T> class BaseVertex : public OptimizableGraph::Vertex {
   static const int Dimension = D;
   typedef T EstimateType;
   const T& estimate() const { return _estimate; } void setEstimate(const T& t) { _estimate = t; }
+  // base_vertex.h: the vertex's block of the Hessian and of the right-hand side (there: Maps into the solver's memory)
+  Eigen::Matrix<double, D, 1>& b() { return _b; } Eigen::Matrix<double, D, D>& A() { return _hessianBlock; }
+  void clearQuadraticForm() { _b.setZero(); _hessianBlock.setZero(); }
  protected:
   T _estimate;
+  Eigen::Matrix<double, D, 1> _b; Eigen::Matrix<double, D, D> _hessianBlock;
 };
 template <int D, class E> class BaseEdge : public OptimizableGraph::Edge {
  public:
@@ -104,14 +108,18 @@ template <int D, class E> class BaseEdge : public OptimizableGraph::Edge {
   void setInformation(const InformationType& i) { _information = i; }
   const ErrorVector& error() const { return _error; }
   double chi2() const { return _error.dot(_information * _error); }
+  // base_edge.h:102-109 (the second-order term is commented out there as well)
+  InformationType robustInformation(const Eigen::Vector3d& rho) { InformationType result = rho[1] * _information; return result; }
  protected:
   E _measurement; InformationType _information; ErrorVector _error;
 };
 template <int D, class E, class VertexXi> class BaseUnaryEdge : public BaseEdge<D, E> {
  public:
   typedef Eigen::Matrix<double, D, VertexXi::Dimension> JacobianXiOplusType;
+  typedef typename BaseEdge<D, E>::InformationType InformationType; typedef typename BaseEdge<D, E>::ErrorVector ErrorVector;
   BaseUnaryEdge() { this->resize(1); }
   const JacobianXiOplusType& jacobianOplusXi() const { return _jacobianOplusXi; }
+  void constructQuadraticForm();   // defined by the reference's base_unary_edge.hpp where oracle/Makefile pipes it in
  protected:
   using BaseEdge<D, E>::_measurement; using BaseEdge<D, E>::_information; using BaseEdge<D, E>::_error; using HyperGraph::Edge::_vertices;
   JacobianXiOplusType _jacobianOplusXi;
@@ -120,12 +128,19 @@ template <int D, class E, class VertexXi, class VertexXj> class BaseBinaryEdge :
  public:
   typedef Eigen::Matrix<double, D, VertexXi::Dimension> JacobianXiOplusType;
   typedef Eigen::Matrix<double, D, VertexXj::Dimension> JacobianXjOplusType;
+  typedef typename BaseEdge<D, E>::InformationType InformationType; typedef typename BaseEdge<D, E>::ErrorVector ErrorVector;
   BaseBinaryEdge() { this->resize(2); }
   const JacobianXiOplusType& jacobianOplusXi() const { return _jacobianOplusXi; }
   const JacobianXjOplusType& jacobianOplusXj() const { return _jacobianOplusXj; }
+  // base_binary_edge.h: the off-diagonal block this edge contributes to (there: Maps into the solver's memory)
+  typedef Eigen::Matrix<double, VertexXi::Dimension, VertexXj::Dimension> HessianBlockType;
+  typedef Eigen::Matrix<double, VertexXj::Dimension, VertexXi::Dimension> HessianBlockTransposedType;
+  void constructQuadraticForm();   // defined by the reference's base_binary_edge.hpp where oracle/Makefile pipes it in
+  const HessianBlockType& hessianBlock() const { return _hessian; }
  protected:
   using BaseEdge<D, E>::_measurement; using BaseEdge<D, E>::_information; using BaseEdge<D, E>::_error; using HyperGraph::Edge::_vertices;
   JacobianXiOplusType _jacobianOplusXi; JacobianXjOplusType _jacobianOplusXj;
+  bool _hessianRowMajor = false; HessianBlockType _hessian; HessianBlockTransposedType _hessianTransposed;
 };
 template <int D, class E> class BaseMultiEdge : public BaseEdge<D, E> {  // (G2oTypes.h's inertial edges: members only)
  public:

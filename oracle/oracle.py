@@ -274,6 +274,15 @@ def lba_solve(g, max_iters=10, lambda_init=0.0, stop=None, driver=None):
                 trace=trace[:st.trials].copy())
 
 
+def lba_system(g):
+    """The normal equations build_system() forms at the input estimates: dict(Hpp[n_kf,6,6], Hll[n_mp,3,3], W[n_edges,6,3],
+    bp[n_kf,6], bl[n_mp,3]); rows of fixed keyframes are zero."""
+    out = dict(Hpp=np.zeros((g.n_kf, 6, 6)), Hll=np.zeros((g.n_mp, 3, 3)), W=np.zeros((g.n_edges, 6, 3)),
+               bp=np.zeros((g.n_kf, 6)), bl=np.zeros((g.n_mp, 3)))
+    lib().orc_lba_system(C.byref(g), *[_ptr(out[k]) for k in ("Hpp", "Hll", "W", "bp", "bl")])
+    return out
+
+
 def lba_edge(g, e):
     """One edge of an lba_graph_view at its input estimates: err[3], A[d x 3] = d err / d point, B[d x 6] = d err / d pose
     (3 rows, the third zero for 2-D edges), isDepthPositive."""
@@ -341,6 +350,13 @@ def stereo_match(kl, dl, kr, dr, pyr_l, pyr_r, bf, b, scale_factor=1.2):
     n = lib().orc_stereo_match(len(kl), _ptr(kl), _ptr(dl), len(kr), _ptr(kr), _ptr(dr), nl, pl, pr, _ptr(lw), _ptr(lh),
                                _ptr(ls), _ptr(scale), _ptr(inv), float(bf), float(b), _ptr(ur), _ptr(dp), _ptr(sad))
     return n, ur, dp, sad
+
+
+def pose_system(view):
+    """(H[6,6], b[6]) of PoseOptimization's first linearisation (all edges active, robust)."""
+    H, b = np.zeros((6, 6)), np.zeros(6)
+    lib().orc_pose_system(C.byref(view), _ptr(H), _ptr(b))
+    return H, b
 
 
 def pose_optimize(view, driver=None):

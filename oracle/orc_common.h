@@ -25,9 +25,11 @@
 //   * the LM control law of all three optimisers (LocalBundleAdjustment, PoseOptimization, LocalInertialBA):
 //     optimization_algorithm_levenberg.cpp as object code (libref_lm.so) driving this oracle's own operations through
 //     orc_lm_ops.h -- tests/test_ref_lm.py (bit for bit);
-//   * g2o's Hessian accumulation / block solver and the inertial edges of G2oTypes.cc: "parity unpinned" by the reference
-//     (those translation units need the real Eigen); pinned by independent numpy restatements, finite differences and
-//     dense solves, with the reference lines cited per function.
+//   * the accumulation of the edges into the normal equations: constructQuadraticForm() of base_binary_edge.hpp /
+//     base_unary_edge.hpp as object code (libref_g2o.so) over whole windows / frames -- tests/test_ref_edges.py (1e-12);
+//   * g2o's block solver (Schur complement, sparse LDL^T) and the inertial edges of G2oTypes.cc: "parity unpinned" by the
+//     reference (those translation units need the real Eigen); pinned by independent numpy restatements, finite
+//     differences and dense solves, with the reference lines cited per function.
 #pragma once
 #include <stdint.h>
 

@@ -557,6 +557,27 @@ int orc_lba_solve(const lba_graph_view* g, const volatile uint8_t* stop, int max
   return orc_lba_solve_lm(g, stop, max_iters, lambda_init, kf_pose_out, mp_pos_out, chi2_out, depth_pos_out, stats, trace, nullptr);
 }
 
+// The normal equations at the input estimates as build_system() leaves them: Hpp n_kf x 36 (zero rows for fixed
+// keyframes), Hll n_mp x 9, W n_edges x 18 (6 x 3 per edge: B^T wOmega A), bp n_kf x 6, bl n_mp x 3 --
+// tests/test_ref_edges.py holds them against g2o's constructQuadraticForm() object code (oracle/_ref/libref_g2o.so).
+int orc_lba_system(const lba_graph_view* g, double* Hpp, double* Hll, double* W, double* bp, double* bl) {
+  Problem P(g);
+  P.compute_errors();
+  P.build_system();
+  memset(Hpp, 0, sizeof(double) * 36 * (size_t)g->n_kf);
+  memset(bp, 0, sizeof(double) * 6 * (size_t)g->n_kf);
+  for (int k = 0; k < g->n_kf; k++) {
+    const int f = P.free_idx[k];
+    if (f < 0) continue;
+    memcpy(Hpp + 36 * (size_t)k, &P.Hpp[36 * (size_t)f], sizeof(double) * 36);
+    memcpy(bp + 6 * (size_t)k, &P.b[6 * (size_t)f], sizeof(double) * 6);
+  }
+  memcpy(Hll, P.Hll.data(), sizeof(double) * 9 * (size_t)g->n_mp);
+  memcpy(W, P.W.data(), sizeof(double) * 18 * (size_t)g->n_edges);
+  memcpy(bl, &P.b[(size_t)6 * P.nf], sizeof(double) * 3 * (size_t)g->n_mp);
+  return P.nf;
+}
+
 // One edge at the input estimates: err (3, third entry 0 for 2-D edges), A = d err / d point (d x 3), B = d err / d pose
 // (d x 6), isDepthPositive -- what tests/test_ref_edges.py holds against the reference's own computeError() /
 // linearizeOplus() (oracle/_ref/libref_edges.so).

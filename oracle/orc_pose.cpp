@@ -286,6 +286,20 @@ int orc_pose_edge(const pose_opt_view* v, int e, double* err3, double* B18) {
   return 0;
 }
 
+// The 6 x 6 system build_system() forms at the input pose with every edge active and robust (the first linearisation of
+// the first round) -- tests/test_ref_edges.py holds it against BaseUnaryEdge::constructQuadraticForm's object code.
+int orc_pose_system(const pose_opt_view* v, double* H36, double* b6) {
+  PoseProblem P(v);
+  P.T.r = Quat{v->pose[0], v->pose[1], v->pose[2], v->pose[3]};
+  quat_normalize(P.T.r);
+  P.T.t[0] = v->pose[4]; P.T.t[1] = v->pose[5]; P.T.t[2] = v->pose[6];
+  P.compute_active_errors();
+  P.build_system();
+  memcpy(H36, P.H, sizeof(P.H));
+  memcpy(b6, P.b, sizeof(P.b));
+  return 0;
+}
+
 // Returns nInitialCorrespondences - nBad (Optimizer.cc:1114).  pose_out: quaternion xyzw + translation
 // (SE3quat_recov before the cast to float); outlier_out[n] = mvbOutlier of the edges; chi2_out[n] (optional)
 // = the chi2 each edge was last classified with; stats_out (optional) = {rounds run, LM iterations, LM trials}.

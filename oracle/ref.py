@@ -408,6 +408,8 @@ def g2o_lib():
         L.ref_g2o_edge_unary.argtypes = [C.c_int, vp, vp, vp, vp, C.c_double, vp, vp, vp, vp]
         L.ref_g2o_huber.argtypes = [C.c_double, C.c_double, vp]
         L.ref_g2o_oplus.argtypes = [vp, vp, vp]
+        L.ref_g2o_build_system.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.ref_g2o_pose_system.argtypes = [vp, vp, vp]
         L.ref_g2o_se3_map.argtypes = [vp, vp, vp]
         _g2o = L
     return _g2o
@@ -485,3 +487,21 @@ def g2o_se3_map(pose7, X):
     out = np.zeros(3)
     g2o_lib().ref_g2o_se3_map(_p(np.ascontiguousarray(pose7, np.float64)), _p(np.ascontiguousarray(X, np.float64)), _p(out))
     return out
+
+
+def g2o_build_system(g):
+    """computeError + linearizeOplus + constructQuadraticForm of every edge of a Pinhole window, in edge order, as the
+    vendored g2o's object code: dict like oracle.lba_system."""
+    out = dict(Hpp=np.zeros((g.n_kf, 6, 6)), Hll=np.zeros((g.n_mp, 3, 3)), W=np.zeros((g.n_edges, 6, 3)),
+               bp=np.zeros((g.n_kf, 6)), bl=np.zeros((g.n_mp, 3)))
+    rc = g2o_lib().ref_g2o_build_system(C.byref(g), *[_p(out[k]) for k in ("Hpp", "Hll", "W", "bp", "bl")])
+    if rc != 0:
+        raise ValueError("second-camera edges are not g2o types")
+    return out
+
+
+def g2o_pose_system(view):
+    """(H[6,6], b[6]): BaseUnaryEdge::constructQuadraticForm over the pose-only edges of a pose_opt_view (object code)."""
+    H, b = np.zeros((6, 6)), np.zeros(6)
+    g2o_lib().ref_g2o_pose_system(C.byref(view), _p(H), _p(b))
+    return H, b

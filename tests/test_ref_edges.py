@@ -205,3 +205,28 @@ def test_vertex_oplus_equals_the_vendored_g2o_object_code(oracle, g2o):
         assert np.abs(a - b).max() <= 1e-12 * max(1.0, np.abs(b).max()), (i, up, a, b)
         assert abs(np.linalg.norm(b[:4]) - 1) < 1e-12 and b[3] >= 0
     assert n_small > 500 and n_big > 500
+
+
+@pytest.mark.parametrize("kf,mp,seed,stereo_frac", [(8, 300, 1, 0.8), (6, 150, 5, 0.0), (12, 600, 2, 1.0)])
+def test_normal_equations_equal_g2o_construct_quadratic_form(oracle, g2o, kf, mp, seed, stereo_frac):
+    """Row a18: every edge's contribution to the Hessian blocks and the right-hand side -- information, the Huber weight
+    rho'(chi2) on both, the off-diagonal block A' wOmega B -- accumulated edge by edge by BaseBinaryEdge::
+    constructQuadraticForm (base_binary_edge.hpp:57-120) as object code, against the oracle's build_system()."""
+    g, _ = scenes.lba_graph(kf, mp, seed=seed, stereo_frac=stereo_frac)   # 2 % gross outliers: the kernel is active
+    gv = scenes.lba_view(g)
+    a, b = oracle.lba_system(gv), g2o.g2o_build_system(gv)
+    for k in ("Hpp", "Hll", "W", "bp", "bl"):
+        assert np.abs(a[k]).max() > 0
+        assert np.abs(a[k] - b[k]).max() <= 1e-12 * np.abs(b[k]).max(), k
+    fixed = g["kf_fixed"] != 0
+    assert fixed.any() and not a["Hpp"][fixed].any() and not b["Hpp"][fixed].any()   # a fixed vertex gets no block
+
+
+@pytest.mark.parametrize("n,seed,stereo_frac", [(400, 6, 0.6), (50, 2, 0.0), (900, 3, 1.0)])
+def test_pose_system_equals_g2o_construct_quadratic_form(oracle, g2o, n, seed, stereo_frac):
+    """8f-2: BaseUnaryEdge::constructQuadraticForm (base_unary_edge.hpp:42-72) over the frame's edges."""
+    v, _ = scenes.pose_scene(n, seed=seed, stereo_frac=stereo_frac)
+    H, b = oracle.pose_system(v)
+    Hr, br = g2o.g2o_pose_system(v)
+    assert np.abs(H - Hr).max() <= 1e-12 * np.abs(Hr).max() and np.abs(b - br).max() <= 1e-12 * np.abs(br).max()
+    assert np.abs(H - H.T).max() <= 1e-12 * np.abs(H).max()
