@@ -422,6 +422,14 @@ def lia_solve(v, driver=None):
                            dim=int(st[5])), trace=trace[:min(int(st[1]), 128)].copy())
 
 
+def lia_edge(v, e):
+    """One visual edge of a lia_graph_view at its input state: err[3], A[3,3], B[3,6], isDepthPositive."""
+    err, A, B, dp = np.zeros(3), np.zeros((3, 3)), np.zeros((3, 6)), C.c_uint8(0)
+    rc = lib().orc_lia_edge(C.byref(v), int(e), _ptr(err), _ptr(A), _ptr(B), C.byref(dp))
+    assert rc == 0
+    return err, A, B, bool(dp.value)
+
+
 def lia_linearize(v, delta=None):
     """(robust chi2, b) at the input state, and robust chi2 after oplus(delta)."""
     chi, chid = C.c_double(), C.c_double()

@@ -27,6 +27,8 @@
 //     orc_lm_ops.h -- tests/test_ref_lm.py (bit for bit);
 //   * the accumulation of the edges into the normal equations: constructQuadraticForm() of base_binary_edge.hpp /
 //     base_unary_edge.hpp as object code (libref_g2o.so) over whole windows / frames -- tests/test_ref_edges.py (1e-12);
+//   * the visual edges of LocalInertialBA (EdgeMono / EdgeStereo): src/G2oTypes.cc as object code (libref_vi.so) --
+//     tests/test_ref_edges.py (1e-12);
 //   * g2o's block solver (Schur complement, sparse LDL^T) and the inertial edges of G2oTypes.cc: "parity unpinned" by the
 //     reference (those translation units need the real Eigen); pinned by independent numpy restatements, finite
 //     differences and dense solves, with the reference lines cited per function.

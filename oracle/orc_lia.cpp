@@ -355,29 +355,37 @@ struct Problem {
     }
   }
 
+  // EdgeMono / EdgeStereo::linearizeOplus (G2oTypes.cc:290-345): A = d err / d point (d x 3), B = d err / d pose (d x 6),
+  // row-major, third row zero for a mono edge
+  void vis_jac(int e, double A[9], double B[18]) const {
+    const int k = g->e_kf[e], l = g->e_mp[e], d = g->e_stereo[e] ? 3 : 2;
+    double Rbc[9];
+    tr(g->Rcb, Rbc);
+    const Pose& P = pose[k];
+    double Xc[3], Xb[3];
+    mv(P.Rcw, &pt[3 * (size_t)l], Xc);
+    for (int c = 0; c < 3; c++) Xc[c] += P.tcw[c];
+    mv(Rbc, Xc, Xb);
+    for (int c = 0; c < 3; c++) Xb[c] += g->tbc[c];
+    const double x = Xc[0], y = Xc[1], z = Xc[2];
+    double pj[9] = {g->fx / z, 0, -g->fx * x / (z * z), 0, g->fy / z, -g->fy * y / (z * z), 0, 0, 0};
+    if (d == 3) { pj[6] = pj[0]; pj[7] = pj[1]; pj[8] = pj[2] + (double)g->bf * (1.0 / (z * z)); }
+    double PR[9];
+    mm(pj, P.Rcw, A);
+    for (int c = 0; c < 9; c++) A[c] = -A[c];                       // _jacobianOplusXi = -proj_jac * Rcw
+    mm(pj, g->Rcb, PR);
+    const double D[18] = {0, Xb[2], -Xb[1], 1, 0, 0, -Xb[2], 0, Xb[0], 0, 1, 0, Xb[1], -Xb[0], 0, 0, 0, 1};
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 6; c++) B[r * 6 + c] = PR[r * 3] * D[c] + PR[r * 3 + 1] * D[6 + c] + PR[r * 3 + 2] * D[12 + c];
+  }
+
   void build_system() {
     std::fill(H.begin(), H.end(), 0.0); std::fill(b.begin(), b.end(), 0.0);
     std::fill(Hll.begin(), Hll.end(), 0.0); std::fill(bl.begin(), bl.end(), 0.0);
-    double Rbc[9];
-    tr(g->Rcb, Rbc);
     for (int e = 0; e < g->n_edges; e++) {  // EdgeMono / EdgeStereo::linearizeOplus + constructQuadraticForm
       const int k = g->e_kf[e], l = g->e_mp[e], d = g->e_stereo[e] ? 3 : 2;
-      const Pose& P = pose[k];
-      double Xc[3], Xb[3];
-      mv(P.Rcw, &pt[3 * (size_t)l], Xc);
-      for (int c = 0; c < 3; c++) Xc[c] += P.tcw[c];
-      mv(Rbc, Xc, Xb);
-      for (int c = 0; c < 3; c++) Xb[c] += g->tbc[c];
-      const double x = Xc[0], y = Xc[1], z = Xc[2];
-      double pj[9] = {g->fx / z, 0, -g->fx * x / (z * z), 0, g->fy / z, -g->fy * y / (z * z), 0, 0, 0};
-      if (d == 3) { pj[6] = pj[0]; pj[7] = pj[1]; pj[8] = pj[2] + (double)g->bf * (1.0 / (z * z)); }
-      double A[9], B[18], PR[9];
-      mm(pj, P.Rcw, A);
-      for (int c = 0; c < 9; c++) A[c] = -A[c];                       // _jacobianOplusXi = -proj_jac * Rcw
-      mm(pj, g->Rcb, PR);
-      const double D[18] = {0, Xb[2], -Xb[1], 1, 0, 0, -Xb[2], 0, Xb[0], 0, 1, 0, Xb[1], -Xb[0], 0, 0, 0, 1};
-      for (int r = 0; r < 3; r++)
-        for (int c = 0; c < 6; c++) B[r * 6 + c] = PR[r * 3] * D[c] + PR[r * 3 + 1] * D[6 + c] + PR[r * 3 + 2] * D[12 + c];
+      double A[9], B[18];
+      vis_jac(e, A, B);
       double r0, r1;
       (d == 3 ? hs : hm).robustify(vchi2(e), r0, r1);
       const double s = g->e_inv_sigma2[e], ws = r1 * s;
@@ -656,6 +664,22 @@ int orc_lia_linearize(const lia_graph_view* g, const double* delta, double* chi2
 int orc_lia_solve(const lia_graph_view* g, double* kf_out, double* mp_out, double* chi2_out, uint8_t* depth_pos_out,
                   double* stats) {
   return orc_lia_solve_lm(g, kf_out, mp_out, chi2_out, depth_pos_out, stats, nullptr, nullptr);
+}
+
+// One visual edge at the input state: err (3), A = d err / d point, B = d err / d pose (3 x 3 / 3 x 6 row-major, third
+// row zero for EdgeMono), isDepthPositive -- tests/test_ref_edges.py holds it against the reference's EdgeMono / EdgeStereo
+// (src/G2oTypes.cc, include/G2oTypes.h) as object code.
+int orc_lia_edge(const lia_graph_view* g, int e, double* err3, double* A9, double* B18, uint8_t* depth_pos) {
+  if (!g || e < 0 || e >= g->n_edges) return -1;
+  Problem P(g);
+  P.compute_errors();
+  for (int i = 0; i < 3; i++) err3[i] = P.verr[3 * (size_t)e + i];
+  P.vis_jac(e, A9, B18);
+  if (!g->e_stereo[e]) { for (int i = 6; i < 9; i++) A9[i] = 0; for (int i = 12; i < 18; i++) B18[i] = 0; }
+  const Pose& Q = P.pose[g->e_kf[e]];
+  const double* X = &P.pt[3 * (size_t)g->e_mp[e]];
+  if (depth_pos) *depth_pos = (Q.Rcw[6] * X[0] + Q.Rcw[7] * X[1] + Q.Rcw[8] * X[2] + Q.tcw[2]) > 0.0;
+  return 0;
 }
 
 }  // extern "C"

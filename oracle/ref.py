@@ -505,3 +505,35 @@ def g2o_pose_system(view):
     H, b = np.zeros((6, 6)), np.zeros(6)
     g2o_lib().ref_g2o_pose_system(C.byref(view), _p(H), _p(b))
     return H, b
+
+
+# ---- oracle/_ref/libref_vi.so: src/G2oTypes.cc as object code (the visual edges of LocalInertialBA)
+VI_LIB_PATH = os.path.join(_HERE, "_ref", "libref_vi.so")
+_vi = None
+
+
+def build_vi(force=False):
+    if not os.path.exists(os.path.join(REFERENCE, "src", "G2oTypes.cc")):
+        return None
+    cmd = ["make", "-C", _HERE, "REF=" + REFERENCE] + (["-B"] if force else []) + ["_ref/libref_vi.so"]
+    subprocess.check_call(cmd, stdout=subprocess.DEVNULL)
+    return VI_LIB_PATH
+
+
+def vi_available():
+    return os.path.exists(VI_LIB_PATH) or build_vi() is not None
+
+
+def vi_edge(v, e):
+    """The reference's EdgeMono / EdgeStereo (src/G2oTypes.cc) on edge e of a lia_graph_view at its input state:
+    err[3], A[3,3] = d err / d point, B[3,6] = d err / d pose (third rows zero for EdgeMono), isDepthPositive."""
+    global _vi
+    if _vi is None:
+        if not os.path.exists(VI_LIB_PATH) and build_vi() is None:
+            raise FileNotFoundError("oracle/_ref/libref_vi.so is not built and %s is absent" % REFERENCE)
+        _vi = C.CDLL(VI_LIB_PATH)
+        _vi.ref_vi_edge.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    err, A, B, dp = np.zeros(3), np.zeros((3, 3)), np.zeros((3, 6)), C.c_int(0)
+    rc = _vi.ref_vi_edge(C.byref(v), int(e), _p(err), _p(A), _p(B), C.byref(dp))
+    assert rc == 0
+    return err, A, B, bool(dp.value)

@@ -230,3 +230,29 @@ def test_pose_system_equals_g2o_construct_quadratic_form(oracle, g2o, n, seed, s
     Hr, br = g2o.g2o_pose_system(v)
     assert np.abs(H - Hr).max() <= 1e-12 * np.abs(Hr).max() and np.abs(b - br).max() <= 1e-12 * np.abs(br).max()
     assert np.abs(H - H.T).max() <= 1e-12 * np.abs(H).max()
+
+
+@pytest.mark.parametrize("n_opt,n_mp,seed", [(6, 300, 0), (4, 120, 3)])
+def test_inertial_ba_visual_edges_equal_the_reference_object_code(oracle, n_opt, n_mp, seed):
+    """8f-4b: EdgeMono / EdgeStereo of LocalInertialBA (Optimizer.cc:2636-2735) -- src/G2oTypes.cc compiled unmodified into
+    oracle/_ref/libref_vi.so, run on an ImuCamPose filled from the view -- computeError, linearizeOplus (the body-frame
+    SE3 derivative through Rcb / tbc), isDepthPositive, on every visual edge of a window."""
+    from oracle import ref as R
+    if not R.vi_available():
+        pytest.skip("oracle/_ref/libref_vi.so is not built and the reference tree is absent")
+    d, _ = scenes.lia_scene(n_opt, n_mp, seed=seed)
+    v = oracle.make_lia_view(d)
+    n_st = n_mono = 0
+    for e in range(v.n_edges):
+        err, A, B, dp = oracle.lia_edge(v, e)
+        r_err, r_A, r_B, r_dp = R.vi_edge(v, e)
+        # the residual is a difference of ~1e3 px quantities: 1e-12 px absolute
+        assert np.abs(err - r_err).max() <= 1e-12 * max(1.0, np.abs(d["e_obs"][e]).max()), (e, err, r_err)
+        assert _close(A, r_A, 1e-12) and _close(B, r_B, 1e-12), e
+        assert dp == r_dp
+        st = int(d["e_stereo"][e])
+        if not st:
+            assert err[2] == 0 and not A[2].any() and not B[2].any()
+        n_st += st
+        n_mono += 1 - st
+    assert n_st > 100 and n_mono > 50
