@@ -127,3 +127,59 @@ def test_search_for_triangulation_is_the_reference(oracle, feats, seed, stereo, 
     assert counts[0] <= counts[2] + 3      # (rotation-histogram pruning can differ by a few between the passes)
     if pose == "across_shift":
         assert counts[0] < counts[2] // 2  # an epipolar geometry the true shift contradicts rejects most candidates
+
+
+def test_matchers_degenerate_inputs_follow_the_reference(oracle, feats):
+    """Nothing in view; identical descriptors everywhere (every decision is a tie, resolved by the order in which
+    GetFeaturesInArea returns the candidates); map points without observations (never blocking, slots overwritten);
+    an empty map-point list."""
+    ka, da, kb, db = feats
+    F, mps = scenes.local_map_scene(ka, da, 640, 480, 10, seed=1)
+    mps._keep["track_in_view"][:] = 0
+    n0, a0 = oracle.match_project_local(F, mps, 3.0, 0.8)
+    n1, a1 = ref.front_project_local(F, mps, 3.0, 0.8)
+    assert n0 == n1 == 0 and np.array_equal(a0, a1)
+
+    d0 = np.zeros_like(da)
+    F, mps = scenes.local_map_scene(ka, d0, 640, 480, 0, seed=2)
+    mps._keep["desc"][:] = 0
+    for th in (1.0, 3.0, 10.0):
+        n0, a0 = oracle.match_project_local(F, mps, th, 0.8)
+        n1, a1 = ref.front_project_local(F, mps, th, 0.8)
+        assert n0 == n1 and np.array_equal(a0, a1), th
+
+    cur, last, Tcw = scenes.last_frame_scene(ka, da, kb, db, 640, 480, (5, -3), seed=4, obs0_frac=1.0)
+    n0, a0 = oracle.match_project_last(cur, last, Tcw, 30.0, check_ori=True)
+    n1, a1 = ref.front_project_last(cur, last, Tcw, 30.0, check_ori=True)
+    assert n0 == n1 and np.array_equal(np.where(a0 < 0, -1, a0), a1)
+
+    cur, last, Tcw = scenes.last_frame_scene(ka, np.zeros_like(da), kb, np.zeros_like(db), 640, 480, (5, -3), seed=5)
+    last._keep["desc"][:] = 0
+    n0, a0 = oracle.match_project_last(cur, last, Tcw, 15.0, check_ori=False)
+    n1, a1 = ref.front_project_last(cur, last, Tcw, 15.0, check_ori=False)
+    assert n0 == n1 and np.array_equal(np.where(a0 < 0, -1, a0), a1)
+
+    F, mps = scenes.local_map_scene(ka[:0], da[:0], 640, 480, 0, seed=3)
+    assert F.n == 0 and mps.n == 0
+    n0, a0 = oracle.match_project_local(F, mps, 3.0, 0.8)
+    n1, a1 = ref.front_project_local(F, mps, 3.0, 0.8)
+    assert n0 == n1 == 0
+
+
+def test_compute_stereo_matches_degenerate_inputs_follow_the_reference(oracle):
+    """No right keypoints; identical images (zero disparity, every SAD window a perfect match: the sub-pixel parabola
+    degenerates); several disparity bands with noise-free windows."""
+    left = synth_frame(480, 640, 12)
+    el = oracle.OracleExtractor(800)
+    kl, dl, _ = el.extract(left)
+    pl = [el.level_image(l) for l in range(8)]
+    for right in (left.copy(), stereo_right(left, 13, disparities=(40, 3), noise=0)):
+        er = oracle.OracleExtractor(800)
+        kr, dr, _ = er.extract(right)
+        pr = [er.level_image(l) for l in range(8)]
+        n0, ur0, dp0, _ = oracle.stereo_match(kl, dl, kr, dr, pl, pr, 386.0, 0.5514)
+        n1, ur1, dp1 = ref.front_stereo_match(kl, dl, kr, dr, pl, pr, 386.0, 0.5514)
+        assert n0 == n1 and np.array_equal(ur0, ur1) and np.array_equal(dp0, dp1)
+    n0, ur0, dp0, _ = oracle.stereo_match(kl, dl, kr[:0], dr[:0], pl, pr, 386.0, 0.5514)
+    n1, ur1, dp1 = ref.front_stereo_match(kl, dl, kr[:0], dr[:0], pl, pr, 386.0, 0.5514)
+    assert n0 == n1 == 0 and np.array_equal(ur0, ur1) and np.array_equal(dp0, dp1)
