@@ -116,6 +116,8 @@ class OracleExtractor:
         n = C.c_int(0)
         mono = lib().orc_extract(self._h, _ptr(img), img.shape[0], img.shape[1], img.strides[0],
                                  int(lap[0]), int(lap[1]), _ptr(kps), _ptr(desc), cap, C.byref(n))
+        if mono == -3:
+            raise ValueError("aspect ratio < 0.5 at some pyramid level: undefined in the reference (nIni == 0, ORBextractor.cc:560)")
         if mono < 0:
             raise RuntimeError("oracle extract rc=%d" % mono)
         return kps[:n.value].copy(), desc[:n.value].copy(), mono

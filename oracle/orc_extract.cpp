@@ -29,6 +29,7 @@
 #include <chrono>
 #include <list>
 #include <thread>
+#include <stdexcept>
 #include <vector>
 
 #include "orc_common.h"
@@ -365,6 +366,9 @@ struct Extractor {
   std::vector<orc_keypoint> distribute_octtree(const std::vector<orc_keypoint>& pts, int minX,
                                                int maxX, int minY, int maxY, int N) {
     const int nIni = (int)std::round(static_cast<float>(maxX - minX) / (maxY - minY));
+    // a level more than twice as tall as wide gives nIni == 0: the reference then divides by zero and indexes an empty
+    // vector (undefined behaviour); the C ABI rejects such images with ORB_E_ARG and the oracle reports them the same way
+    if (nIni < 1) throw std::domain_error("aspect ratio < 0.5: nIni == 0 is undefined in the reference");
     const float hX = static_cast<float>(maxX - minX) / nIni;
     std::list<OctNode> nodes;
     std::vector<OctNode*> ini(nIni);
@@ -595,7 +599,11 @@ void orc_extractor_destroy(void* h) { delete (Extractor*)h; }
 
 int orc_extract(void* h, const uint8_t* img, int rows, int cols, int step, int lap0, int lap1,
                 orc_keypoint* kps, uint8_t* desc, int cap, int* n_out) {
-  return ((Extractor*)h)->extract(img, rows, cols, step, lap0, lap1, kps, desc, cap, n_out);
+  try {
+    return ((Extractor*)h)->extract(img, rows, cols, step, lap0, lap1, kps, desc, cap, n_out);
+  } catch (const std::domain_error&) {
+    return -3;
+  }
 }
 
 // --- introspection used by the parity tests to localise a mismatch ---
